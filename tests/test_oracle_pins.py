@@ -1,0 +1,393 @@
+"""Pins for the CPU oracle: the restatement (oracle/svo_oracle.cpp, oracle/pyoracle.py) must agree
+with (a) golden vectors generated from the real OpenCV (tests/golden/make_golden.py),
+(b) the real OpenCV live when cv2 is importable, (c) the Gauss-Newton known-answer values of
+SURVEY.md Appendix A.7 (independently derived) and (d) the anchor numbers of Appendix A.6.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import pyoracle as po
+from stereo_vo_b200 import synth
+
+try:
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+needs_cv2 = pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+
+
+def xys(k):
+    return np.stack([k["x"], k["y"], k["response"]], 1).astype(np.int32)
+
+
+# ---------------------------------------------------------------- FAST (stage2_detect.cpp:510-511)
+@pytest.mark.parametrize("name,count", [("0L", 625), ("0R", 474)])
+def test_fast_port_matches_golden_on_reference_fixtures(golden, name, count):
+    img = golden["img_" + name]
+    ref = golden[f"fast_{name}_th20"]
+    assert len(ref) == count                      # SURVEY A.6 anchor
+    got = xys(orc.fast9(img, 20))
+    assert np.array_equal(got, ref)
+    assert np.array_equal(po.fast9(img, 20), ref)  # numpy restatement too
+
+
+def test_fast_first_keypoints_anchor(golden):
+    # first FAST keypoints of 0L
+    assert golden["fast_0L_th20"][:5].tolist() == [[79, 66, 21], [65, 70, 20], [72, 72, 23], [69, 80, 28], [71, 80, 31]]
+
+
+@needs_cv2
+@pytest.mark.parametrize("th", [5, 20, 30])
+@pytest.mark.parametrize("shape", [(64, 80), (97, 131), (7, 7), (6, 40), (240, 320)])
+def test_fast_port_matches_cv2_live(th, shape):
+    rng = np.random.default_rng(th * 1000 + shape[0])
+    img = synth.make_texture(rng, *shape)
+    ref = xys(orc.cv2_kps_to_array(cv2.FastFeatureDetector_create(th).detect(img)))
+    assert np.array_equal(xys(orc.fast9(img, th)), ref.reshape(-1, 3))
+
+
+# ---------------------------------------------------------------- ORB::compute (stage2_detect.cpp:512)
+def test_gauss_kernel_bits():
+    if cv2 is not None:
+        assert np.array_equal(cv2.getGaussianKernel(7, 2, cv2.CV_32F).ravel().view(np.uint32), po.GAUSS7.view(np.uint32))
+    assert abs(float(po.GAUSS7.sum()) - 1.0) < 1e-6
+
+
+def test_blur_matches_golden(golden):
+    assert np.array_equal(orc.blur7(golden["blur_in"]), golden["blur_out"])
+    assert np.array_equal(po.blur7_exact(golden["blur_in"]), golden["blur_out"])
+
+
+@pytest.mark.parametrize("name,count,checksum", [("0L", 514, 1832643), ("0R", 443, 1602098)])
+def test_orb_port_matches_golden_on_reference_fixtures(golden, name, count, checksum):
+    img = golden["img_" + name]
+    k, d = orc.orb_compute(img, orc.fast9(img, 20))
+    assert len(k) == count
+    assert int(d.astype(np.int64).sum()) == checksum          # SURVEY A.6 byte-sum checksum
+    assert np.array_equal(xys(k), golden[f"orbkp_{name}_th20"])
+    assert np.array_equal(d, golden[f"orbdesc_{name}_th20"])
+
+
+@needs_cv2
+def test_orb_port_matches_cv2_live():
+    rng = np.random.default_rng(5)
+    img = synth.make_texture(rng, 200, 260)
+    k_ref, d_ref = orc.cv2_fast_orb(img, 20)
+    k, d = orc.orb_compute(img, orc.fast9(img, 20))
+    assert np.array_equal(xys(k), xys(k_ref)) and np.array_equal(d, d_ref)
+    # boundary behaviour: x,y in [31, W-31) x [31, H-31)
+    assert k["x"].min() >= 31 and k["x"].max() < 260 - 31 and k["y"].min() >= 31 and k["y"].max() < 200 - 31
+
+
+def test_orb_pattern_table():
+    p = po.load_orb_pattern()
+    assert p.shape == (256, 4) and int(np.abs(p).max()) == 13
+    assert p[:4].tolist() == [[8, -3, 9, 5], [4, 2, 7, -12], [-11, 9, -8, 2], [7, -12, 12, -13]]
+    assert p[-1].tolist() == [-1, -6, 0, -11]
+    # angle = -1 deg (FAST keypoints) rounds to the same offsets as 0 deg
+    a = np.deg2rad(-1.0)
+    c, s = np.float32(np.cos(a)), np.float32(np.sin(a))
+    for col in (0, 2):
+        x = p[:, col].astype(np.float32)
+        y = p[:, col + 1].astype(np.float32)
+        assert np.array_equal(np.rint(x * c - y * s).astype(int), p[:, col])
+        assert np.array_equal(np.rint(x * s + y * c).astype(int), p[:, col + 1])
+
+
+# ---------------------------------------------------------------- BFMatcher (S3:88-94, S4:137-142)
+def test_bf_match_golden_ties(golden):
+    q, t, ref = golden["bf_rand_q"], golden["bf_rand_t"], golden["bf_rand"]
+    m = orc.bf_match(q, t)
+    assert np.array_equal(m["trainIdx"], ref[:, 0]) and np.array_equal(m["distance"].astype(np.int32), ref[:, 1])
+    assert np.array_equal(m["queryIdx"], np.arange(len(q))) and not m["imgIdx"].any()
+    i, d = po.bf_match(q, t)
+    assert np.array_equal(i, ref[:, 0]) and np.array_equal(d, ref[:, 1])
+    # the duplicated rows make the lowest index win
+    assert (ref[:30, 0] == np.arange(30)).all() and (ref[:30, 1] == 0).all()
+
+
+def test_bf_match_fixture_and_lr_filter_anchors(golden):
+    dL, dR = golden["orbdesc_0L_th20"], golden["orbdesc_0R_th20"]
+    m = orc.bf_match(dL, dR)
+    ref = golden["bf_0L_0R"]
+    assert np.array_equal(m["trainIdx"], ref[:, 0]) and np.array_equal(m["distance"].astype(np.int32), ref[:, 1])
+    # number of matches kept by the S3:155-175 filter on 0L/0R
+    kL = np.zeros(len(dL), orc.KEYPOINT)
+    kR = np.zeros(len(dR), orc.KEYPOINT)
+    kL["x"], kL["y"] = golden["orbkp_0L_th20"][:, 0], golden["orbkp_0L_th20"][:, 1]
+    kR["x"], kR["y"] = golden["orbkp_0R_th20"][:, 0], golden["orbkp_0R_th20"][:, 1]
+    expect = {(0, 40): 219, (0, 60): 223, (1, 40): 319, (1, 60): 334, (2, 40): 342, (2, 60): 361}
+    for (yd, th), n in expect.items():
+        assert len(orc.lr_filter(m, kL, kR, False, yd, th, 800)) == n
+
+
+def test_bf_match_empty():
+    q = np.zeros((3, 32), np.uint8)
+    assert len(orc.bf_match(q, np.zeros((0, 32), np.uint8))) == 0
+    assert len(orc.bf_match(np.zeros((0, 32), np.uint8), q)) == 0
+
+
+# ---------------------------------------------------------------- glue: sorts, filters
+def test_non_max_sup_is_top_k_by_response_with_std_sort_ties():
+    rng = np.random.default_rng(0)
+    n = 3000
+    k = np.zeros(n, orc.KEYPOINT)
+    # FAST-like: distinct non-adjacent positions, few distinct integer responses
+    pos = rng.permutation(200 * 150)[:n]
+    k["x"] = (pos % 200) * 2 + 31
+    k["y"] = (pos // 200) * 2 + 31
+    k["response"] = rng.integers(20, 60, n)
+    order = np.lexsort((k["x"], k["y"]))
+    k = k[order]
+    d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    ok, od, sel = orc.non_max_sup(1000, k, d, 3, 400, 500, sort_mode=0)
+    ok_s, od_s, sel_s = orc.non_max_sup(1000, k, d, 3, 400, 500, sort_mode=1)
+    assert len(ok) == len(ok_s) == 1000
+    assert np.array_equal(od, d[sel])
+    # responses are non-increasing in both modes and the multiset of kept responses is equal
+    assert (np.diff(ok["response"]) <= 0).all() and (np.diff(ok_s["response"]) <= 0).all()
+    assert np.array_equal(np.sort(ok["response"]), np.sort(ok_s["response"]))
+    # stable mode keeps input order inside ties; the faithful mode (introsort) does not
+    assert np.array_equal(sel_s, np.argsort(-k["response"], kind="stable")[:1000])
+    assert not np.array_equal(sel, sel_s)
+
+
+def test_non_max_sup_grid_occupancy_min_distance():
+    # min_distance=10 -> cell = 5 px; a weaker keypoint in the same or a 4-neighbour cell is dropped
+    k = np.zeros(4, orc.KEYPOINT)
+    k["x"] = [50, 52, 57, 80]
+    k["y"] = [50, 51, 50, 50]
+    k["response"] = [40, 30, 35, 10]
+    ok, _, sel = orc.non_max_sup(10, k, np.zeros((4, 32), np.uint8), 10, 100, 100)
+    assert sel.tolist() == [0, 3]
+
+
+def test_update_indexes_sorts_by_row():
+    rng = np.random.default_rng(1)
+    n = 500
+    k = np.zeros(n, orc.KEYPOINT)
+    k["x"] = rng.integers(31, 600, n)
+    k["y"] = rng.integers(31, 440, n)
+    k["response"] = rng.integers(20, 60, n)
+    d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    ks, ds, perm, row_index = orc.update_indexes(k, d, 480)
+    assert (np.diff(ks["y"]) >= 0).all()
+    assert np.array_equal(ks, k[perm]) and np.array_equal(ds, d[perm])
+    ks2, _, perm2, _ = orc.update_indexes(k, d, 480, sort_mode=1)
+    assert np.array_equal(perm2, np.argsort(k["y"], kind="stable"))
+    # reference quirk (S2:103-129): rows before the first feature's row are 0, the tail stays 0
+    assert row_index[: int(ks["y"][0])].sum() == 0 and row_index[int(ks["y"][-1]):].sum() == 0
+    assert row_index[int(ks["y"][0])] == int((ks["y"] == ks["y"][0]).sum())
+
+
+def test_lr_filter_int_truncation_and_disparity():
+    kL = np.zeros(4, orc.KEYPOINT)
+    kR = np.zeros(4, orc.KEYPOINT)
+    kL["x"] = [100, 100, 100, 100]
+    kL["y"] = [50, 50, 50, 50]
+    kR["x"] = [90, 100, 99.5, 90]     # disp 10, 0 (rejected: < 1), int(0.5)=0 (rejected), 10
+    kR["y"] = [51.9, 50, 50, 52]      # int(-1.9) = -1 -> |.|=1 ok; last: -2 rejected
+    m = np.zeros(4, orc.DMATCH)
+    m["queryIdx"] = np.arange(4)
+    m["trainIdx"] = np.arange(4)
+    m["distance"] = [40, 10, 10, 10]
+    out = orc.lr_filter(m, kL, kR, False, 1.0, 40, 640)
+    assert out["queryIdx"].tolist() == [0]
+    m["distance"][0] = 41
+    assert len(orc.lr_filter(m, kL, kR, False, 1.0, 40, 640)) == 0
+
+
+def test_lr_filter_robust_1to1():
+    kL = np.zeros(3, orc.KEYPOINT)
+    kR = np.zeros(2, orc.KEYPOINT)
+    kL["x"] = 100
+    kR["x"] = 90
+    m = np.zeros(3, orc.DMATCH)
+    m["queryIdx"] = [0, 1, 2]
+    m["trainIdx"] = [0, 0, 1]
+    m["distance"] = [12, 7, 9]
+    out = orc.lr_filter(m, kL, kR, True, 1.0, 40, 640)
+    assert out["queryIdx"].tolist() == [1, 2]
+
+
+def test_track_filter_is_sequential_greedy():
+    # pair 0 rejected by distance -> it must NOT claim its train indices, so pair 1 survives (S4:145-160)
+    mL = np.zeros(4, orc.DMATCH)
+    mR = np.zeros(4, orc.DMATCH)
+    mL["queryIdx"] = mR["queryIdx"] = np.arange(4)
+    mL["trainIdx"] = [5, 5, 2, 2]
+    mR["trainIdx"] = [5, 5, 3, 2]
+    mL["distance"] = [50, 10, 10, 10]
+    mR["distance"] = [10, 10, 10, 10]
+    l, r = orc.track_filter(mL, mR, 8, 40)
+    assert l["queryIdx"].tolist() == [1, 2]      # pair 3 collides with pair 2 on the left train index
+    tp = orc.track_consistency(l, r, None, None)
+    assert tp.tolist() == [[1, 5]]                # pair 2: left/right train differ -> dropped (S4:282)
+
+
+def test_track_consistency_applies_masks_only_if_both_have_8():
+    n = 12
+    mL = np.zeros(n, orc.DMATCH)
+    mL["queryIdx"] = np.arange(n)
+    mL["trainIdx"] = np.arange(n)
+    mR = mL.copy()
+    inlL = np.ones(n, np.uint8)
+    inlR = np.ones(n, np.uint8)
+    inlL[0] = 0
+    assert len(orc.track_consistency(mL, mR, inlL, inlR)) == n - 1
+    inlR[:5] = 0                                   # right has only 7 inliers -> filter skipped entirely
+    assert len(orc.track_consistency(mL, mR, inlL, inlR)) == n
+
+
+# ---------------------------------------------------------------- Gauss-Newton KATs
+def _kat_inputs(noise):
+    rng = np.random.default_rng(12345)
+    N = 200
+    X = rng.uniform(-3, 3, N)
+    Y = rng.uniform(-2, 2, N)
+    Z = rng.uniform(2, 10, N)
+    fx = fy = 500.0
+    cx, cy, B = 320.0, 240.0, 0.12
+    w = np.array([0.01, -0.02, 0.005])
+    t = np.array([0.05, -0.01, 0.10])
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    R = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+    P = np.stack([X, Y, Z], 1)
+    Pc = P @ R.T + t
+
+    def proj(P):
+        l = np.stack([fx * P[:, 0] / P[:, 2] + cx, fy * P[:, 1] / P[:, 2] + cy], 1)
+        r = np.stack([fx * (P[:, 0] - B) / P[:, 2] + cx, fy * P[:, 1] / P[:, 2] + cy], 1)
+        return l, r
+    pl, pr = proj(P)
+    cl, cr = proj(Pc)
+    if noise:
+        pl = pl + rng.normal(0, 0.3, (N, 2))
+        pr = pr + rng.normal(0, 0.3, (N, 2))
+        cl = cl + rng.normal(0, 0.3, (N, 2))
+        cr = cr + rng.normal(0, 0.3, (N, 2))
+        cl[:20] += rng.uniform(-40, 40, (20, 2))
+    arrs = [v.astype(np.float32) for v in (pl, pr, cl, cr)]
+    return arrs, orc.make_camera(fx, fy, cx, cy, B), N
+
+
+def test_gn_kat_1_noise_free():
+    a, cam, N = _kat_inputs(False)
+    res, resid, inl = orc.stage5(*a, np.ones(N, np.float32), np.arange(N), 480, 640, 3, cam,
+                                 orc.LSParams.defaults(), np.zeros(6), survivors=np.ones(N, np.uint8))
+    assert (res.valid, res.error_code, res.num_it, res.num_it_final, len(inl)) == (1, 0, 10, 2, 200)
+    np.testing.assert_allclose(res.delta_pose[:], [0.0100000046, -0.0200000058, 0.0049999945,
+                                                   0.0500000267, -0.0099999787, 0.1000000043], atol=2e-9)
+    np.testing.assert_allclose(res.out_pose_rotvec[:], [-0.0100000046, 0.0200000058, -0.0049999945], atol=2e-9)
+    np.testing.assert_allclose(res.out_pose_t[:], [-0.0519427322, 0.0092594182, -0.0990768330], atol=2e-9)
+
+
+def test_gn_kat_2_noise_and_outliers():
+    a, cam, N = _kat_inputs(True)
+    res, resid, inl = orc.stage5(*a, np.ones(N, np.float32), np.arange(N), 480, 640, 3, cam,
+                                 orc.LSParams.defaults(), np.zeros(6), survivors=np.ones(N, np.uint8))
+    assert (res.valid, res.num_it, res.num_it_final, len(inl)) == (1, 10, 2, 180)
+    # the survey's numpy model did not include the float32 residual subtraction (B-18): 1e-8 slack
+    np.testing.assert_allclose(res.delta_pose[:], [0.0100106921, -0.0200267613, 0.0048923695,
+                                                   0.0498795155, -0.0101671208, 0.0996805624], atol=1e-8)
+
+
+def test_gn_svd_solve_against_numpy():
+    a, cam, N = _kat_inputs(True)
+    rc, new, grad, res, cost = orc.eval_rgn(*a, cam, orc.LSParams.defaults(), np.zeros(6))
+    assert rc == 0
+    # rebuild H from finite differences of nothing: instead check H*x = g through a second
+    # evaluation path: numerically the step must satisfy the normal equations built by numpy
+    # from the oracle's own residual/Jacobian definition (small-angle branch at zero pose).
+    l1l, l1r, l2l, l2r = [v.astype(np.float64) for v in a]
+    fx, cx, cy, B = 500.0, 320.0, 240.0, 0.12
+    b_d = B / (fx * (cx - l1r[:, 0]) + fx * (l1l[:, 0] - cx))
+    X, Y, Z = b_d * fx * (l1l[:, 0] - cx), b_d * fx * (l1l[:, 1] - cy), b_d * fx * fx
+    H = np.zeros((6, 6))
+    g = np.zeros(6)
+    for m in range(N):
+        Xc, Yc, Zc = X[m], Y[m], Z[m]
+        X2 = Xc - B
+        d3 = [(0, -Zc, Yc), (Zc, 0, -Xc), (-Yc, Xc, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
+        J = np.zeros((4, 6))
+        for j, (xd, yd, zd) in enumerate(d3):
+            J[0, j] = fx * (xd * Zc - Xc * zd) / Zc ** 2
+            J[1, j] = fx * (yd * Zc - Yc * zd) / Zc ** 2
+            J[2, j] = fx * (xd * Zc - X2 * zd) / Zc ** 2
+            J[3, j] = J[1, j]
+        px = np.array([fx * Xc / Zc + cx, fx * Yc / Zc + cy, fx * X2 / Zc + cx, fx * Yc / Zc + cy]).astype(np.float32)
+        obs = np.array([a[2][m, 0], a[2][m, 1], a[3][m, 0], a[3][m, 1]], np.float32)
+        r = (obs - px).astype(np.float64)
+        s = float(r @ r)
+        rho = 1 / np.sqrt(1 + s / 9.0)
+        g += rho * (J.T @ r)
+        H += J.T @ J
+    np.testing.assert_allclose(grad, g, rtol=1e-9, atol=1e-6)
+    np.testing.assert_allclose(new, np.linalg.solve(H, g), rtol=1e-7, atol=1e-12)
+
+
+def test_gn_too_few_points_and_bad_cond():
+    a, cam, N = _kat_inputs(False)
+    b = [v[:7] for v in a]
+    res, resid, inl = orc.stage5(*b, np.ones(7, np.float32), np.arange(7), 480, 640, 3, cam,
+                                 orc.LSParams.defaults(), np.zeros(6), survivors=np.ones(7, np.uint8))
+    assert res.valid == 0 and res.num_it == 0 and res.reached_end == 0 and len(resid) == 0
+    # zero disparity everywhere -> b_d = inf -> every Jacobian is rejected -> H = 0 -> cond = NaN
+    c = [v[:20].copy() for v in a]
+    c[1][:, 0] = c[0][:, 0]
+    res, resid, inl = orc.stage5(*c, np.ones(20, np.float32), np.arange(20), 480, 640, 3, cam,
+                                 orc.LSParams.defaults(), np.zeros(6), survivors=np.ones(20, np.uint8))
+    assert res.valid == 0 and res.bad_cond == 1 and res.error_code == orc.VOEC["voecBadCondNumber"]
+
+
+# ---------------------------------------------------------------- whole pipeline vs golden (cv2-generated)
+@pytest.mark.parametrize("backend", ["port"] + (["cv2"] if cv2 is not None else []))
+def test_pipeline_c1_matches_golden(golden, backend):
+    frames, cam = synth.make_sequence("c1", seed=3, n_frames=3)
+    camo = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    masks = {}
+
+    def golden_ransac(p1, p2):
+        return masks["q"].pop(0)
+
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend=backend,
+                              ransac="cv2" if backend == "cv2" else golden_ransac)
+    for i, (L, R) in enumerate(frames):
+        if i > 0:
+            masks["q"] = [golden[f"c1_f{i}_inlL"], golden[f"c1_f{i}_inlR"]]
+        o = est.process_new_image_pair(L, R, camo)
+        f = o["frame"]
+        assert np.array_equal(xys(f.kpsL), golden[f"c1_f{i}_kpsL"])
+        assert np.array_equal(xys(f.kpsR), golden[f"c1_f{i}_kpsR"])
+        assert np.array_equal(f.descL, golden[f"c1_f{i}_descL"])
+        assert np.array_equal(f.descR, golden[f"c1_f{i}_descR"])
+        gm = golden[f"c1_f{i}_matches"]
+        assert np.array_equal(np.stack([f.matches["queryIdx"], f.matches["trainIdx"],
+                                        f.matches["distance"].astype(np.int32)], 1), gm)
+        assert np.array_equal(o["tracked"], golden[f"c1_f{i}_tracked"])
+        assert [o["error_code"], int(o["valid"]), o["num_it"], o["num_it_final"]] == golden[f"c1_f{i}_status"].tolist()
+        if i > 0:
+            np.testing.assert_allclose(o["pose"]["delta"], golden[f"c1_f{i}_delta"], atol=1e-12)
+            np.testing.assert_allclose(o["out_residual"], golden[f"c1_f{i}_residual"], rtol=1e-12)
+    assert o["valid"] and abs(o["pose"]["t"][0] - 0.05) < 5e-3   # the generator moves 0.05 m / frame
+
+
+def test_first_frame_and_bad_tracking_state_machine():
+    frames, cam = synth.make_sequence("c1", seed=4, n_frames=2)
+    camo = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend="port", ransac="off")
+    o = est.process_new_image_pair(*frames[0], camo)
+    assert o["error_code"] == orc.VOEC["voecFirstIteration"] and not o["valid"]
+    first = est.cur
+    # an unrelated image pair -> (almost) nothing tracks -> voecBadTracking, prev frame is retained (P:86-89)
+    rng = np.random.default_rng(99)
+    junk = synth.make_texture(rng, 240, 320)
+    junk2 = synth.make_texture(rng, 240, 320)
+    o = est.process_new_image_pair(junk, junk2, camo)
+    assert o["error_code"] == orc.VOEC["voecBadTracking"] and not o["valid"]
+    o = est.process_new_image_pair(*frames[1], camo)
+    assert est.prev is first                       # matched against the older frame
+    assert o["valid"] and o["error_code"] == orc.VOEC["voecNone"]
