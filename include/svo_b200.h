@@ -1,0 +1,217 @@
+/* svo_b200.h -- C-ABI of the B200-native stereo visual-odometry hot path.
+ *
+ * Drop-in boundary for the data-parallel path of famoreno/stereo-vo's
+ * rso::CStereoOdometryEstimator (libstereo-odometry/include/libstereo-odometry.h:147-1047) in its
+ * FAST+ORB / smDescBF / ifmDescBF / robust Gauss-Newton configuration.  The reference has no FFI of
+ * its own: its boundary is the C++ class API plus the private stage seams.  Every entry point
+ * below names the reference interface it replaces (file:line under /root/reference/libstereo-odometry).
+ * The C++ host shim with the reference's class/member names lives in stereo_vo_b200/host/.
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; no C++/torch types cross this boundary
+ *  - every function returns SVO_OK (0) or a negative svo_status; the message of the last failure
+ *    is available from svo_last_error().  Numerical / tracking failures are NOT errors: they travel
+ *    in svo_result.error_code with the reference's VOErrorCode values (libstereo-odometry.h:142)
+ *  - the library never frees or keeps caller memory; outputs go to caller buffers with capacities
+ *  - one svo_ctx per GPU; it owns `max_seqs` independent sequence slots (one slot == one
+ *    CStereoOdometryEstimator instance's mutable state: prev/cur frame, last pose, ID counter)
+ *  - there is no CPU fallback: every entry point fails with SVO_ERR_CUDA when no device is usable
+ */
+#ifndef SVO_B200_H
+#define SVO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_B200_ABI_VERSION 1
+
+typedef enum svo_status {
+    SVO_OK = 0,
+    SVO_ERR_ARG = -1,        /* bad argument (the reference throws via THROW_EXCEPTION / ASSERT_) */
+    SVO_ERR_CUDA = -2,       /* CUDA runtime failure or no usable device */
+    SVO_ERR_CAPACITY = -3,   /* a per-image capacity of the context was exceeded (see svo_config) */
+    SVO_ERR_STATE = -4       /* call not valid in the current state (e.g. no current frame) */
+} svo_status;
+
+/* VOErrorCode, libstereo-odometry.h:142 -- same numeric values */
+typedef enum svo_vo_error {
+    SVO_VOEC_NONE = 0,
+    SVO_VOEC_BAD_COND_NUMBER = 1,
+    SVO_VOEC_INCR_FUNC_COST_STG1 = 2,
+    SVO_VOEC_INCR_FUNC_COST_STG2 = 3,
+    SVO_VOEC_FIRST_ITERATION = 4,
+    SVO_VOEC_BAD_TRACKING = 5
+} svo_vo_error;
+
+/* cv::KeyPoint (28 B) and cv::DMatch (16 B) field order, so the shim can memcpy
+ * (TKeyPointList / TDMatchList, libstereo-odometry.h:108-109) */
+typedef struct svo_keypoint { float x, y, size, angle, response; int32_t octave, class_id; } svo_keypoint;
+typedef struct svo_dmatch { int32_t queryIdx, trainIdx, imgIdx; float distance; } svo_dmatch;
+
+/* the fields of mrpt::utils::TStereoCamera that the path reads (stage5_optimization.cpp:510-515) */
+typedef struct svo_camera {
+    double fxl, fyl, cxl, cyl;   /* leftCamera.fx(), fy(), cx(), cy() */
+    double fxr, fyr, cxr, cyr;   /* rightCamera */
+    double baseline;             /* rightCameraPose[0] */
+} svo_camera;
+
+/* Parameters of the path; names and defaults follow the reference's param structs
+ * (TDetectParams :383-447, TLeftRightMatchParams :449-499, TLeastSquaresParams :313-350,
+ *  TGeneralParams :266-283).  svo_default_config() fills the values of SURVEY.md Appendix C. */
+typedef struct svo_config {
+    int32_t abi_version;          /* SVO_B200_ABI_VERSION */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t width, height;        /* image size (all slots) */
+    int32_t max_seqs;             /* number of sequence slots (batch size upper bound) */
+    int32_t max_corners;          /* capacity: FAST corners per image that survive the 31-px border filter */
+    /* TDetectParams */
+    int32_t orb_nfeats;           /* 500 -> cap 2*orb_nfeats keypoints (stage2_detect.cpp:405, nOctaves=1) */
+    int32_t fast_threshold;       /* m_current_fast_th == initial_FAST_threshold, 20 */
+    int32_t non_maximal_suppression; /* true */
+    int32_t min_distance;         /* 3 (must be >= 2: the reference divides by uint(min_distance/2)) */
+    /* TLeftRightMatchParams */
+    double  max_y_diff;           /* 1 */
+    int32_t orb_threshold;        /* m_current_orb_th == orb_max_distance, 40 */
+    int32_t enable_robust_1to1_match; /* false */
+    /* inter-frame: the reference always runs both cv::findFundamentalMat filters
+     * (stage4_match_consecutive.cpp:202,237); 0 skips them (documented deviation for A/B tests) */
+    int32_t fundmat_filter;       /* 1 */
+    /* TLeastSquaresParams */
+    int32_t use_robust_kernel;    /* true */
+    double  kernel_param;         /* 3 */
+    int32_t max_iters;            /* 100 */
+    int32_t initial_max_iters;    /* 10 */
+    double  min_mod_out_vector;   /* 1e-3 */
+    int32_t max_incr_cost;        /* 3 */
+    double  residual_threshold;   /* 10 */
+    int32_t bad_tracking_th;      /* 5 */
+    int32_t use_previous_pose_as_initial; /* true */
+    /* TGeneralParams */
+    int32_t vo_use_matches_ids;   /* false */
+    /* 0 = reproduce libstdc++ std::sort's permutation (stage2_detect.cpp:89,242,324) exactly;
+     * 1 = stable order (diagnostic; compare with the oracle's sort_mode=1) */
+    int32_t sort_mode;
+} svo_config;
+
+/* POD mirror of TStereoOdometryResult (libstereo-odometry.h:235-264) for nOctaves == 1.
+ * The variable-length members (outliers, out_residual) are fetched with svo_get_* below. */
+typedef struct svo_result {
+    double  out_pose[16];         /* outPose as row-major 4x4 (pose of the current frame wrt the previous) */
+    double  out_pose_rotvec[3];   /* same pose: rotation vector */
+    double  out_pose_t[3];        /*            translation */
+    double  out_pose_ypr[3];      /*            yaw, pitch, roll (CPose3D convention) */
+    double  delta_pose[6];        /* the optimiser's (w1,w2,w3,t1,t2,t3) = inverse of outPose */
+    int32_t num_it, num_it_final;
+    int32_t valid;
+    int32_t error_code;           /* svo_vo_error */
+    int32_t tracked_feats_from_last_KF, tracked_feats_from_last_frame;
+    int32_t detected_left, detected_right;   /* detected_feats[0].first / .second */
+    int32_t stereo_matches;                  /* stereo_matches[0] */
+    int32_t n_outliers;                      /* outliers.size()  (holds the INLIERS, stage5_optimization.cpp:601-610) */
+    int32_t n_residuals;                     /* out_residual.size() */
+    int32_t status;                          /* svo_status of this slot's step (capacity overflow etc.) */
+} svo_result;
+
+typedef struct svo_ctx svo_ctx;
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+void svo_default_config(svo_config* cfg);                       /* ctor defaults + SURVEY Appendix C */
+int  svo_create(const svo_config* cfg, svo_ctx** out);          /* CStereoOdometryEstimator(), common.cpp:28-50 */
+void svo_destroy(svo_ctx* ctx);                                 /* ~CStereoOdometryEstimator(), common.cpp:52-61 */
+const char* svo_last_error(const svo_ctx* ctx);                 /* ctx may be NULL: last creation error */
+int  svo_reset_slot(svo_ctx* ctx, int32_t slot);                /* fresh estimator state for one slot */
+
+/* ---- the pipeline: processNewImagePair (process_new_image_pair.cpp:41-385) ----------------- */
+/* One call == one processNewImagePair per listed slot, all slots advanced together on the GPU.
+ * left/right: n pointers to 8-bit gray, rectified images (host memory), row stride in bytes.
+ * slots: n distinct slot indices (NULL = 0..n-1).  cams: n cameras (one per slot).
+ * repeat: request_data.repeat per slot (NULL = all false).  results: n entries (host). */
+int svo_process_batch(svo_ctx* ctx, int32_t n, const int32_t* slots,
+                      const uint8_t* const* left, const uint8_t* const* right, size_t stride_bytes,
+                      const svo_camera* cams, const uint8_t* repeat, svo_result* results);
+
+/* Same, images already resident in device memory (HBM): d_left/d_right point to n images each,
+ * image i at d_left + i*image_pitch_bytes, rows `stride_bytes` apart.  Results stay on the device
+ * until svo_fetch_results(); the call only enqueues work on the context's stream. */
+int svo_process_batch_device(svo_ctx* ctx, int32_t n, const int32_t* slots,
+                             const uint8_t* d_left, const uint8_t* d_right, size_t stride_bytes,
+                             size_t image_pitch_bytes, const svo_camera* cams, const uint8_t* repeat);
+int svo_fetch_results(svo_ctx* ctx, int32_t n, const int32_t* slots, svo_result* results); /* syncs */
+int svo_synchronize(svo_ctx* ctx);
+
+/* Single pair on slot 0: the literal processNewImagePair(request, result) seam. */
+int svo_process_pair(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t stride_bytes,
+                     const svo_camera* cam, int32_t repeat, svo_result* result);
+
+/* ---- state readers (getValues, libstereo-odometry.h:704-724, and result vectors) ------------ */
+/* which: 0 = current frame, 1 = previous frame.  side: 0 = left, 1 = right.
+ * Each returns the element count (>= 0) or a negative svo_status; at most `cap` elements are written. */
+int svo_get_keypoints(svo_ctx* ctx, int32_t slot, int32_t which, int32_t side, svo_keypoint* out, int32_t cap);
+int svo_get_descriptors(svo_ctx* ctx, int32_t slot, int32_t which, int32_t side, uint8_t* out, int32_t cap_rows);
+int svo_get_matches(svo_ctx* ctx, int32_t slot, int32_t which, svo_dmatch* out, int32_t cap);
+int svo_get_match_ids(svo_ctx* ctx, int32_t slot, int32_t which, int64_t* out, int32_t cap);
+int svo_get_tracked_pairs(svo_ctx* ctx, int32_t slot, int64_t* out_pairs /* cap x 2 */, int32_t cap);
+int svo_get_residuals(svo_ctx* ctx, int32_t slot, double* out, int32_t cap);
+int svo_get_outliers(svo_ctx* ctx, int32_t slot, int64_t* out, int32_t cap);
+/* debugging / parity seams inside stage 4: the greedy-filtered matL/matR lists (train indices)
+ * and the two RANSAC inlier masks (stage4_match_consecutive.cpp:145-160, 202, 237) */
+int svo_get_track_candidates(svo_ctx* ctx, int32_t slot, int32_t* out_query, int32_t* out_trainL,
+                             int32_t* out_trainR, uint8_t* out_inlL, uint8_t* out_inlR, int32_t cap);
+
+/* ---- per-stage entries (the internal seams, usable on their own) ---------------------------- */
+/* FAST + ORB::compute + m_non_max_sup + m_update_indexes for one host image
+ * (stage2_detect.cpp:502-515, 590-597, 618).  Uses slot 0's scratch; does not touch slot state. */
+int svo_detect(svo_ctx* ctx, const uint8_t* img, size_t stride_bytes,
+               svo_keypoint* out_kps, uint8_t* out_desc, int32_t cap);
+
+/* cv::BFMatcher(NORM_HAMMING,false).match(query, train)
+ * (stage3_match_left_right.cpp:88-94, stage4_match_consecutive.cpp:137-142): host buffers,
+ * 32-byte descriptors, out has nq entries (0 written when nq == 0 or nt == 0).  Returns count. */
+int svo_match_hamming(svo_ctx* ctx, const uint8_t* query, int32_t nq, const uint8_t* train, int32_t nt,
+                      svo_dmatch* out);
+/* device-resident variant for the microbench (BASELINE.json config 5): `reps` independent problems,
+ * problem r at d_query + r*nq*32 / d_train + r*nt*32, packed results (dist << 16 | trainIdx) to d_out. */
+int svo_match_hamming_device(svo_ctx* ctx, const uint8_t* d_query, int32_t nq, const uint8_t* d_train,
+                             int32_t nt, int32_t reps, uint32_t* d_out);
+
+/* stage3 BF branch: match + 1-to-1 + epipolar/threshold/disparity filter
+ * (stage3_match_left_right.cpp:83-178) on caller keypoints/descriptors.  Returns kept count. */
+int svo_match_lr(svo_ctx* ctx, const svo_keypoint* kpsL, const uint8_t* descL, int32_t nL,
+                 const svo_keypoint* kpsR, const uint8_t* descR, int32_t nR, svo_dmatch* out, int32_t cap);
+
+/* getChangeInPose (libstereo-odometry.h:162-172, common.cpp:355-413): stage 5 alone on caller data.
+ * tracked_pairs: n_tracked x 2 (pre_match_idx, cur_match_idx).  ini_estimation: 6 doubles or NULL
+ * (used only when use_custom_initial_pose != 0, which also keeps m_last_computed_pose untouched).
+ * Runs on `slot` (its m_last_computed_pose is the warm start otherwise).  Returns result->valid. */
+int svo_get_change_in_pose(svo_ctx* ctx, int32_t slot,
+                           const int64_t* tracked_pairs, int32_t n_tracked,
+                           const svo_dmatch* pre_matches, int32_t n_pre, const svo_dmatch* cur_matches, int32_t n_cur,
+                           const svo_keypoint* pre_left, int32_t n_pl, const svo_keypoint* pre_right, int32_t n_pr,
+                           const svo_keypoint* cur_left, int32_t n_cl, const svo_keypoint* cur_right, int32_t n_cr,
+                           const svo_camera* cam, int32_t use_custom_initial_pose, const double* ini_estimation,
+                           svo_result* result);
+
+/* cv::findFundamentalMat(p1, p2, FM_RANSAC, 1.0, 0.99, mask) (stage4_match_consecutive.cpp:202,237):
+ * n x 2 float32 points (host), mask n bytes.  Returns the inlier count, 0 (and an all-zero mask)
+ * when no model was found or n < 7. */
+int svo_fundmat_ransac(svo_ctx* ctx, const float* p1, const float* p2, int32_t n, uint8_t* mask);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+int svo_abi_version(void);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+int64_t svo_kernel_launches(const svo_ctx* ctx);
+/* raw CUDA stream of the context (cudaStream_t as void*), for event timing on the launching stream */
+void* svo_stream(svo_ctx* ctx);
+/* per-stage device times of the last svo_process_batch* call, in ms, measured with CUDA events on
+ * the context's stream when enabled with svo_enable_stage_timing(ctx, 1).  names: static strings. */
+int svo_enable_stage_timing(svo_ctx* ctx, int32_t on);
+int svo_get_stage_times(svo_ctx* ctx, const char** names, float* ms, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_B200_H */

@@ -1,0 +1,740 @@
+// capi.cu -- the C-ABI of include/svo_b200.h: context, memory pools in HBM, stream-ordered
+// pipeline of the hot path, state readers.  No CPU implementation of any stage exists in this
+// library: every entry point needs a CUDA device and fails with SVO_ERR_CUDA otherwise.
+#include "../../include/svo_b200.h"
+#include "detect.cuh"
+#include "gn.cuh"
+#include "match.cuh"
+#include "ransac.cuh"
+#include "svo_internal.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace svo;
+
+static_assert(sizeof(svo_result) == sizeof(Result), "svo_result and svo::Result must have the same layout");
+static_assert(sizeof(svo_camera) == sizeof(Camera), "svo_camera and svo::Camera must have the same layout");
+static_assert(sizeof(svo_keypoint) == 28 && sizeof(svo_dmatch) == 16, "cv::KeyPoint / cv::DMatch layout");
+
+static thread_local std::string g_create_error;
+
+enum { ST_H2D = 0, ST_DETECT, ST_MATCH_LR, ST_TRACK, ST_RANSAC, ST_CONSIST, ST_GN, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"h2d", "stg2.detect", "stg3.match_lr", "stg4.track_match",
+                                            "stg4.fundmat_ransac", "stg4.consistency", "stg5.optimize"};
+
+struct svo_ctx {
+    svo_config cfg;
+    Pools P;
+    GnScratch G;
+    RansacScratch RS;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> dev_allocs;
+    std::vector<void*> host_allocs;
+    int n_slots_alloc = 0;      // max_seqs + 1 (the last slot serves the per-stage entry points)
+    int hidden_slot = 0;
+    int pitch = 0;              // row pitch of the internal image planes (W rounded up to 16)
+    uint8_t* d_stageL = nullptr;
+    uint8_t* d_stageR = nullptr;
+    uint8_t* d_repeat = nullptr;
+    Camera* d_cams_batch = nullptr;
+    uint32_t* d_occ = nullptr;
+    int occ_words = 0;
+    uint32_t* d_sort_scratch = nullptr;
+    // pinned host staging
+    int32_t* h_slots = nullptr;
+    uint8_t* h_repeat = nullptr;
+    Camera* h_cams = nullptr;
+    Result* h_results = nullptr;
+    std::string err;
+    int launches_i = 0;
+    int64_t launches = 0;
+    int timing = 0;
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    float stage_ms[ST_COUNT] = {};
+    bool have_times = false;
+};
+
+namespace {
+
+int fail(svo_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(svo_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, SVO_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail((c), e_, #call); } while (0)
+
+template <class T>
+cudaError_t dalloc(svo_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(q, 0, count * sizeof(T) + 16);
+    c->dev_allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return e;
+}
+template <class T>
+cudaError_t halloc(svo_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    memset(q, 0, count * sizeof(T));
+    c->host_allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return e;
+}
+
+__global__ void scatter_cams_kernel(Pools P, const Camera* cams, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) P.cam[P.slots[i]] = cams[i];
+}
+
+__global__ void reset_slot_kernel(Pools P, int slot) {
+    SlotState s;
+    memset(&s, 0, sizeof(s));
+    P.state[slot] = s;
+    Result r;
+    memset(&r, 0, sizeof(r));
+    P.result[slot] = r;
+}
+
+bool valid_slot(const svo_ctx* c, int slot) { return slot >= 0 && slot < c->cfg.max_seqs; }
+
+void record(svo_ctx* c, int i) { if (c->timing) cudaEventRecord(c->ev[i], c->stream); }
+
+// enqueue one pipeline step on device images
+int run_step(svo_ctx* c, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride, size_t image_pitch,
+             bool have_repeat) {
+    Pools& P = c->P;
+    int& L = c->launches_i;
+    L = 0;
+    scatter_cams_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(P, c->d_cams_batch, n);
+    CU(c, launch_begin_step(P, n, have_repeat ? c->d_repeat : nullptr, c->stream));
+    L += 2;
+    record(c, ST_DETECT);
+    CU(c, launch_detect(P, n, d_left, d_right, stride, image_pitch, c->pitch, c->d_occ, c->occ_words,
+                        c->d_sort_scratch, c->stream, &L));
+    record(c, ST_MATCH_LR);
+    CU(c, launch_match_lr(P, n, c->stream, &L));
+    record(c, ST_TRACK);
+    CU(c, launch_track_match(P, n, c->stream, &L));
+    record(c, ST_RANSAC);
+    if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, c->RS, n, c->stream, &L));
+    record(c, ST_CONSIST);
+    CU(c, launch_consistency(P, n, c->stream, &L));
+    record(c, ST_GN);
+    CU(c, launch_gn(P, c->G, n, /*external=*/0, /*custom pose=*/0, /*assume_fast_kps=*/1, c->stream, &L));
+    record(c, ST_COUNT);
+    c->launches += L;
+    c->have_times = c->timing != 0;
+    return SVO_OK;
+}
+
+int upload_batch_meta(svo_ctx* c, int n, const int32_t* slots, const svo_camera* cams, const uint8_t* repeat) {
+    if (n <= 0 || n > c->cfg.max_seqs) return fail(c, SVO_ERR_ARG, "batch size out of range");
+    if (!cams) return fail(c, SVO_ERR_ARG, "cams is NULL");
+    std::vector<char> seen(c->cfg.max_seqs, 0);
+    for (int i = 0; i < n; ++i) {
+        const int s = slots ? slots[i] : i;
+        if (!valid_slot(c, s)) return fail(c, SVO_ERR_ARG, "slot index out of range");
+        if (seen[s]) return fail(c, SVO_ERR_ARG, "duplicate slot in one batch");
+        seen[s] = 1;
+        c->h_slots[i] = s;
+        memcpy(&c->h_cams[i], &cams[i], sizeof(Camera));
+        c->h_repeat[i] = repeat ? repeat[i] : 0;
+    }
+    CU(c, cudaMemcpyAsync(c->P.slots, c->h_slots, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_cams_batch, c->h_cams, n * sizeof(Camera), cudaMemcpyHostToDevice, c->stream));
+    if (repeat) CU(c, cudaMemcpyAsync(c->d_repeat, c->h_repeat, n, cudaMemcpyHostToDevice, c->stream));
+    return SVO_OK;
+}
+
+// make `slot` the only batch item (used by readers / per-stage entries that launch kernels)
+int set_single_slot(svo_ctx* c, int slot) {
+    c->h_slots[0] = slot;
+    CU(c, cudaMemcpyAsync(c->P.slots, c->h_slots, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    return SVO_OK;
+}
+
+int get_state(svo_ctx* c, int slot, SlotState* s) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(s, c->P.state + slot, sizeof(SlotState), cudaMemcpyDeviceToHost));
+    return SVO_OK;
+}
+
+int frame_buf(const SlotState& s, int which) { return which == 0 ? s.cur : (s.cur ^ 1); }
+
+}  // namespace
+
+extern "C" {
+
+int svo_abi_version(void) { return SVO_B200_ABI_VERSION; }
+
+void svo_default_config(svo_config* cfg) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = SVO_B200_ABI_VERSION;
+    cfg->device = 0;
+    cfg->width = 640;
+    cfg->height = 480;
+    cfg->max_seqs = 1;
+    cfg->max_corners = 16384;
+    cfg->orb_nfeats = 500;               // TDetectParams ctor, stage2_detect.cpp:44-58
+    cfg->fast_threshold = 20;
+    cfg->non_maximal_suppression = 1;
+    cfg->min_distance = 3;
+    cfg->max_y_diff = 1.0;               // SURVEY Appendix C (ctor default 0, stage3_match_left_right.cpp:54)
+    cfg->orb_threshold = 40;             // orb_max_distance, stage3_match_left_right.cpp:50
+    cfg->enable_robust_1to1_match = 0;
+    cfg->fundmat_filter = 1;
+    cfg->use_robust_kernel = 1;          // TLeastSquaresParams ctor, common.cpp:69-82
+    cfg->kernel_param = 3.0;
+    cfg->max_iters = 100;
+    cfg->initial_max_iters = 10;
+    cfg->min_mod_out_vector = 1e-3;
+    cfg->max_incr_cost = 3;
+    cfg->residual_threshold = 10.0;
+    cfg->bad_tracking_th = 5;
+    cfg->use_previous_pose_as_initial = 1;
+    cfg->vo_use_matches_ids = 0;
+    cfg->sort_mode = 0;
+}
+
+const char* svo_last_error(const svo_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int svo_create(const svo_config* cfg, svo_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, SVO_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (cfg->abi_version != SVO_B200_ABI_VERSION) return fail(nullptr, SVO_ERR_ARG, "ABI version mismatch");
+    if (cfg->width < 64 || cfg->height < 64 || cfg->width > kMaxImgDim || cfg->height > kMaxImgDim)
+        return fail(nullptr, SVO_ERR_ARG, "image size must be within [64, 4096]");
+    if (cfg->max_seqs < 1 || cfg->max_seqs > 65536) return fail(nullptr, SVO_ERR_ARG, "max_seqs out of range");
+    if (cfg->orb_nfeats < 1) return fail(nullptr, SVO_ERR_ARG, "orb_nfeats must be positive");
+    if (cfg->min_distance < 2) return fail(nullptr, SVO_ERR_ARG, "min_distance must be >= 2 (the reference divides by uint(min_distance/2))");
+    if (cfg->fast_threshold < 1 || cfg->fast_threshold > 254) return fail(nullptr, SVO_ERR_ARG, "fast_threshold out of range");
+    if (cfg->max_corners < 16) return fail(nullptr, SVO_ERR_ARG, "max_corners too small");
+    const int quota = 2 * cfg->orb_nfeats;    // size_t(orb_nfeats*(2*nOctaves)/(2^nOctaves-1)), nOctaves = 1
+    const int kp_cap = cfg->non_maximal_suppression ? std::min(quota, cfg->max_corners) : cfg->max_corners;
+    if (kp_cap > 65535) return fail(nullptr, SVO_ERR_ARG, "more than 65535 keypoints per image are not supported");
+    if (cfg->max_corners >= (1 << 24)) return fail(nullptr, SVO_ERR_ARG, "max_corners too large");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SVO_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                               " (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SVO_ERR_ARG, "device ordinal out of range");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+
+    svo_ctx* c = new (std::nothrow) svo_ctx();
+    if (!c) return fail(nullptr, SVO_ERR_ARG, "out of host memory");
+    c->cfg = *cfg;
+    Params& p = c->P.p;
+    p.W = cfg->width; p.H = cfg->height; p.max_seqs = cfg->max_seqs; p.max_corners = cfg->max_corners;
+    p.kp_cap = kp_cap; p.quota = quota; p.fast_th = cfg->fast_threshold; p.nms = cfg->non_maximal_suppression;
+    p.min_distance = cfg->min_distance; p.max_y_diff = cfg->max_y_diff; p.orb_th = cfg->orb_threshold;
+    p.robust_1to1 = cfg->enable_robust_1to1_match; p.fundmat_filter = cfg->fundmat_filter;
+    p.use_robust_kernel = cfg->use_robust_kernel; p.kernel_param = cfg->kernel_param; p.max_iters = cfg->max_iters;
+    p.initial_max_iters = cfg->initial_max_iters; p.min_mod_out_vector = cfg->min_mod_out_vector;
+    p.max_incr_cost = cfg->max_incr_cost; p.residual_threshold = cfg->residual_threshold;
+    p.bad_tracking_th = cfg->bad_tracking_th; p.use_prev_pose = cfg->use_previous_pose_as_initial;
+    p.use_ids = cfg->vo_use_matches_ids; p.sort_mode = cfg->sort_mode;
+
+    const int S = cfg->max_seqs + 1;
+    c->n_slots_alloc = S;
+    c->hidden_slot = cfg->max_seqs;
+    c->pitch = (cfg->width + 15) & ~15;
+    const size_t plane = (size_t)c->pitch * cfg->height;
+    const size_t cap = (size_t)kp_cap;
+    Pools& P = c->P;
+#define DA(ptr, count) do { cudaError_t e2 = dalloc(c, &(ptr), (count)); if (e2 != cudaSuccess) { int rc = cuda_fail(nullptr, e2, "cudaMalloc " #ptr); svo_destroy(c); return rc; } } while (0)
+#define HA(ptr, count) do { cudaError_t e2 = halloc(c, &(ptr), (count)); if (e2 != cudaSuccess) { int rc = cuda_fail(nullptr, e2, "cudaMallocHost " #ptr); svo_destroy(c); return rc; } } while (0)
+    DA(P.state, S); DA(P.result, S); DA(P.cam, S);
+    DA(P.blur, S * 2 * plane); DA(P.score, S * 2 * plane);
+    DA(P.cand_pos, (size_t)S * 2 * cfg->max_corners); DA(P.n_cand, S * 2);
+    DA(P.kp, S * 4 * cap); DA(P.desc, S * 4 * cap * 2); DA(P.n_kp, S * 4);
+    DA(P.match, S * 2 * cap); DA(P.n_match, S * 2); DA(P.mdesc, S * 4 * cap * 2); DA(P.match_id, S * 2 * cap);
+    DA(P.lr_best, S * cap); DA(P.tr_best, S * 2 * cap); DA(P.tcand, S * cap); DA(P.n_tcand, S);
+    DA(P.inl, S * 2 * cap); DA(P.n_inl, S * 2); DA(P.tracked, S * cap); DA(P.n_tracked, S);
+    DA(P.residual, S * cap); DA(P.outliers, S * cap); DA(P.slots, S);
+    DA(c->d_stageL, (size_t)S * plane); DA(c->d_stageR, (size_t)S * plane);
+    DA(c->d_repeat, S); DA(c->d_cams_batch, S);
+    // occupancy grids (only touched when uint(min_distance/2) != 1): worst case 1-px... cells >= 2 px
+    {
+        const unsigned cell = (unsigned)(cfg->min_distance / 2.0);
+        const float inv = 1.0f / (float)cell;
+        const unsigned glx = (unsigned)(1 + cfg->width * inv), gly = (unsigned)(1 + cfg->height * inv);
+        c->occ_words = (int)((glx * gly + 31) / 32) + 1;
+    }
+    DA(c->d_occ, (size_t)S * 2 * c->occ_words);
+    DA(c->d_sort_scratch, cfg->sort_mode ? (size_t)S * 2 * cfg->max_corners : 16);
+    GnScratch& G = c->G;
+    DA(G.prev, S * cap); DA(G.obs, S * cap); DA(G.lmk, S * cap * 3); DA(G.mask, S * cap);
+    DA(G.cur_idx, S * cap); DA(G.ini_pose, S * 6);
+    G.residual = P.residual;
+    G.occ = c->d_occ;               // the aux NMS of stage 5 runs after stage 2 is finished: same scratch
+    G.occ_words = 2 * c->occ_words;
+    {
+        cudaError_t e2 = alloc_ransac(c->RS, S, kp_cap, c->dev_allocs);
+        if (e2 != cudaSuccess) { int rc = cuda_fail(nullptr, e2, "alloc_ransac"); svo_destroy(c); return rc; }
+        c->RS.slots = P.slots; c->RS.inl = P.inl; c->RS.n_inl = P.n_inl;
+    }
+    HA(c->h_slots, S); HA(c->h_repeat, S); HA(c->h_cams, S); HA(c->h_results, S);
+#undef DA
+#undef HA
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { int rc = cuda_fail(nullptr, e, "cudaStreamCreate"); svo_destroy(c); return rc; }
+    for (int i = 0; i <= ST_COUNT; ++i) cudaEventCreate(&c->ev[i]);
+    if ((e = configure_detect(p)) != cudaSuccess || (e = configure_match(p)) != cudaSuccess ||
+        (e = configure_gn(p)) != cudaSuccess || (e = configure_ransac(kp_cap)) != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "kernel configuration (shared memory)");
+        svo_destroy(c);
+        return rc;
+    }
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { int rc = cuda_fail(nullptr, e, "cudaDeviceSynchronize"); svo_destroy(c); return rc; }
+    *out = c;
+    return SVO_OK;
+}
+
+void svo_destroy(svo_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (int i = 0; i <= ST_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (void* p : c->dev_allocs) cudaFree(p);
+    for (void* p : c->host_allocs) cudaFreeHost(p);
+    delete c;
+}
+
+int svo_reset_slot(svo_ctx* c, int32_t slot) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "slot index out of range");
+    reset_slot_kernel<<<1, 1, 0, c->stream>>>(c->P, slot);
+    CU(c, cudaGetLastError());
+    return SVO_OK;
+}
+
+int svo_synchronize(svo_ctx* c) {
+    if (!c) return SVO_ERR_ARG;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}
+
+void* svo_stream(svo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int64_t svo_kernel_launches(const svo_ctx* c) { return c ? c->launches : 0; }
+
+int svo_enable_stage_timing(svo_ctx* c, int32_t on) {
+    if (!c) return SVO_ERR_ARG;
+    c->timing = on;
+    return SVO_OK;
+}
+
+int svo_get_stage_times(svo_ctx* c, const char** names, float* ms, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (!c->have_times) return 0;
+    CU(c, cudaStreamSynchronize(c->stream));
+    int n = 0;
+    for (int i = 0; i < ST_COUNT && n < cap; ++i) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]) != cudaSuccess) t = 0;
+        if (names) names[n] = kStageNames[i];
+        if (ms) ms[n] = t;
+        ++n;
+    }
+    return n;
+}
+
+int svo_process_batch_device(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t* d_left, const uint8_t* d_right,
+                             size_t stride, size_t image_pitch, const svo_camera* cams, const uint8_t* repeat) {
+    if (!c) return SVO_ERR_ARG;
+    if (!d_left || !d_right) return fail(c, SVO_ERR_ARG, "image pointer is NULL");
+    if (stride < (size_t)c->cfg.width) return fail(c, SVO_ERR_ARG, "stride smaller than the image width");
+    CU(c, cudaSetDevice(c->cfg.device));
+    int rc = upload_batch_meta(c, n, slots, cams, repeat);
+    if (rc != SVO_OK) return rc;
+    record(c, ST_H2D);
+    return run_step(c, n, d_left, d_right, stride, image_pitch, repeat != nullptr);
+}
+
+int svo_fetch_results(svo_ctx* c, int32_t n, const int32_t* slots, svo_result* results) {
+    if (!c || !results) return SVO_ERR_ARG;
+    if (n <= 0 || n > c->cfg.max_seqs) return fail(c, SVO_ERR_ARG, "batch size out of range");
+    int lo = c->cfg.max_seqs, hi = -1;
+    for (int i = 0; i < n; ++i) {
+        const int s = slots ? slots[i] : i;
+        if (!valid_slot(c, s)) return fail(c, SVO_ERR_ARG, "slot index out of range");
+        lo = std::min(lo, s); hi = std::max(hi, s);
+    }
+    CU(c, cudaMemcpyAsync(c->h_results + lo, c->P.result + lo, (size_t)(hi - lo + 1) * sizeof(Result),
+                          cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    int rc = SVO_OK;
+    for (int i = 0; i < n; ++i) {
+        const int s = slots ? slots[i] : i;
+        memcpy(&results[i], &c->h_results[s], sizeof(svo_result));
+    }
+    // per-slot step status (capacity overflow) lives in the slot state
+    std::vector<SlotState> st(hi - lo + 1);
+    CU(c, cudaMemcpy(st.data(), c->P.state + lo, st.size() * sizeof(SlotState), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const int s = slots ? slots[i] : i;
+        results[i].status = st[s - lo].status;
+        if (st[s - lo].status != 0) { results[i].valid = 0; rc = st[s - lo].status; }
+    }
+    if (rc == SVO_ERR_CAPACITY) return fail(c, rc, "max_corners exceeded for at least one image (raise svo_config.max_corners)");
+    return rc;
+}
+
+int svo_process_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t* const* left,
+                      const uint8_t* const* right, size_t stride, const svo_camera* cams, const uint8_t* repeat,
+                      svo_result* results) {
+    if (!c) return SVO_ERR_ARG;
+    if (!left || !right || !results) return fail(c, SVO_ERR_ARG, "NULL argument");
+    if (stride < (size_t)c->cfg.width) return fail(c, SVO_ERR_ARG, "stride smaller than the image width");
+    CU(c, cudaSetDevice(c->cfg.device));
+    int rc = upload_batch_meta(c, n, slots, cams, repeat);
+    if (rc != SVO_OK) return rc;
+    record(c, ST_H2D);
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t plane = (size_t)c->pitch * H;
+    // contiguous batches go up in one copy per side
+    bool contig = true;
+    for (int i = 1; i < n && contig; ++i)
+        contig = left[i] == left[0] + (size_t)i * stride * H && right[i] == right[0] + (size_t)i * stride * H;
+    if (contig && stride == (size_t)c->pitch) {
+        CU(c, cudaMemcpyAsync(c->d_stageL, left[0], plane * n, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_stageR, right[0], plane * n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int i = 0; i < n; ++i) {
+            if (!left[i] || !right[i]) return fail(c, SVO_ERR_ARG, "image pointer is NULL");
+            CU(c, cudaMemcpy2DAsync(c->d_stageL + i * plane, c->pitch, left[i], stride, W, H, cudaMemcpyHostToDevice, c->stream));
+            CU(c, cudaMemcpy2DAsync(c->d_stageR + i * plane, c->pitch, right[i], stride, W, H, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    rc = run_step(c, n, c->d_stageL, c->d_stageR, c->pitch, plane, repeat != nullptr);
+    if (rc != SVO_OK) return rc;
+    return svo_fetch_results(c, n, slots, results);
+}
+
+int svo_process_pair(svo_ctx* c, const uint8_t* left, const uint8_t* right, size_t stride, const svo_camera* cam,
+                     int32_t repeat, svo_result* result) {
+    const int32_t slot = 0;
+    const uint8_t rep = repeat ? 1 : 0;
+    return svo_process_batch(c, 1, &slot, &left, &right, stride, cam, repeat ? &rep : nullptr, result);
+}
+
+// ---- readers -------------------------------------------------------------------------------------
+int svo_get_keypoints(svo_ctx* c, int32_t slot, int32_t which, int32_t side, svo_keypoint* out, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (which | 1) != 1 || (side | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/which/side");
+    SlotState s;
+    int rc = get_state(c, slot, &s);
+    if (rc) return rc;
+    if (which == 0 ? !s.has_cur : !s.has_prev) return fail(c, SVO_ERR_STATE, "frame not present");
+    const size_t f = frame_idx(slot, frame_buf(s, which), side);
+    int n = 0;
+    CU(c, cudaMemcpy(&n, c->P.n_kp + f, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int2> tmp(n);
+    if (n) CU(c, cudaMemcpy(tmp.data(), c->P.kp + f * c->P.p.kp_cap, n * sizeof(int2), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; ++i) {
+        svo_keypoint k;
+        k.x = (float)(tmp[i].x & 0xFFFF); k.y = (float)((unsigned)tmp[i].x >> 16);
+        k.size = 7.f; k.angle = -1.f; k.response = (float)tmp[i].y; k.octave = 0; k.class_id = -1;   // cv::FAST keypoints
+        out[i] = k;
+    }
+    return n;
+}
+
+int svo_get_descriptors(svo_ctx* c, int32_t slot, int32_t which, int32_t side, uint8_t* out, int32_t cap_rows) {
+    if (!c) return SVO_ERR_ARG;
+    if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (which | 1) != 1 || (side | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/which/side");
+    SlotState s;
+    int rc = get_state(c, slot, &s);
+    if (rc) return rc;
+    if (which == 0 ? !s.has_cur : !s.has_prev) return fail(c, SVO_ERR_STATE, "frame not present");
+    const size_t f = frame_idx(slot, frame_buf(s, which), side);
+    int n = 0;
+    CU(c, cudaMemcpy(&n, c->P.n_kp + f, sizeof(int), cudaMemcpyDeviceToHost));
+    const int m = std::min(n, cap_rows);
+    if (m > 0) CU(c, cudaMemcpy(out, c->P.desc + f * c->P.p.kp_cap * 2, (size_t)m * 32, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int svo_get_matches(svo_ctx* c, int32_t slot, int32_t which, svo_dmatch* out, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (which | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/which");
+    SlotState s;
+    int rc = get_state(c, slot, &s);
+    if (rc) return rc;
+    if (which == 0 ? !s.has_cur : !s.has_prev) return fail(c, SVO_ERR_STATE, "frame not present");
+    const size_t pi = pair_idx(slot, frame_buf(s, which));
+    int n = 0;
+    CU(c, cudaMemcpy(&n, c->P.n_match + pi, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int4> tmp(n);
+    if (n) CU(c, cudaMemcpy(tmp.data(), c->P.match + pi * c->P.p.kp_cap, n * sizeof(int4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; ++i) {
+        svo_dmatch m = {tmp[i].x, tmp[i].y, 0, (float)tmp[i].z};
+        out[i] = m;
+    }
+    return n;
+}
+
+int svo_get_match_ids(svo_ctx* c, int32_t slot, int32_t which, int64_t* out, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot) || (which | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/which");
+    if (!c->cfg.vo_use_matches_ids) return 0;
+    SlotState s;
+    int rc = get_state(c, slot, &s);
+    if (rc) return rc;
+    if (which == 0 ? !s.has_cur : !s.has_prev) return fail(c, SVO_ERR_STATE, "frame not present");
+    const size_t pi = pair_idx(slot, frame_buf(s, which));
+    int n = 0;
+    CU(c, cudaMemcpy(&n, c->P.n_match + pi, sizeof(int), cudaMemcpyDeviceToHost));
+    const int m = std::min(n, cap);
+    static_assert(sizeof(long long) == sizeof(int64_t), "");
+    if (m > 0) CU(c, cudaMemcpy(out, c->P.match_id + pi * c->P.p.kp_cap, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int svo_get_tracked_pairs(svo_ctx* c, int32_t slot, int64_t* out_pairs, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    CU(c, cudaStreamSynchronize(c->stream));
+    int n = 0;
+    CU(c, cudaMemcpy(&n, c->P.n_tracked + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int2> tmp(n);
+    if (n) CU(c, cudaMemcpy(tmp.data(), c->P.tracked + (size_t)slot * c->P.p.kp_cap, n * sizeof(int2), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; ++i) { out_pairs[2 * i] = tmp[i].x; out_pairs[2 * i + 1] = tmp[i].y; }
+    return n;
+}
+
+int svo_get_residuals(svo_ctx* c, int32_t slot, double* out, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    CU(c, cudaStreamSynchronize(c->stream));
+    Result r;
+    CU(c, cudaMemcpy(&r, c->P.result + slot, sizeof(Result), cudaMemcpyDeviceToHost));
+    const int m = std::min(r.n_residuals, cap);
+    if (m > 0) CU(c, cudaMemcpy(out, c->P.residual + (size_t)slot * c->P.p.kp_cap, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    return r.n_residuals;
+}
+
+int svo_get_outliers(svo_ctx* c, int32_t slot, int64_t* out, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    CU(c, cudaStreamSynchronize(c->stream));
+    Result r;
+    CU(c, cudaMemcpy(&r, c->P.result + slot, sizeof(Result), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> tmp(r.n_outliers);
+    if (r.n_outliers) CU(c, cudaMemcpy(tmp.data(), c->P.outliers + (size_t)slot * c->P.p.kp_cap, r.n_outliers * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < r.n_outliers && i < cap; ++i) out[i] = tmp[i];
+    return r.n_outliers;
+}
+
+int svo_get_track_candidates(svo_ctx* c, int32_t slot, int32_t* out_query, int32_t* out_trainL, int32_t* out_trainR,
+                             uint8_t* out_inlL, uint8_t* out_inlR, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    CU(c, cudaStreamSynchronize(c->stream));
+    int n = 0;
+    CU(c, cudaMemcpy(&n, c->P.n_tcand + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    const size_t kc = c->P.p.kp_cap;
+    std::vector<int4> tmp(n);
+    std::vector<uint8_t> il(n), ir(n);
+    if (n) {
+        CU(c, cudaMemcpy(tmp.data(), c->P.tcand + (size_t)slot * kc, n * sizeof(int4), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(il.data(), c->P.inl + ((size_t)slot * 2 + 0) * kc, n, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(ir.data(), c->P.inl + ((size_t)slot * 2 + 1) * kc, n, cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < n && i < cap; ++i) {
+        if (out_query) out_query[i] = tmp[i].x;
+        if (out_trainL) out_trainL[i] = tmp[i].y;
+        if (out_trainR) out_trainR[i] = tmp[i].z;
+        if (out_inlL) out_inlL[i] = il[i];
+        if (out_inlR) out_inlR[i] = ir[i];
+    }
+    return n;
+}
+
+// ---- per-stage entries ---------------------------------------------------------------------------
+int svo_detect(svo_ctx* c, const uint8_t* img, size_t stride, svo_keypoint* out_kps, uint8_t* out_desc, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (!img) return fail(c, SVO_ERR_ARG, "image pointer is NULL");
+    if (stride < (size_t)c->cfg.width) return fail(c, SVO_ERR_ARG, "stride smaller than the image width");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const int hs = c->hidden_slot;
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t plane = (size_t)c->pitch * H;
+    int rc = set_single_slot(c, hs);
+    if (rc) return rc;
+    CU(c, cudaMemcpy2DAsync(c->d_stageL, c->pitch, img, stride, W, H, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpy2DAsync(c->d_stageR, c->pitch, img, stride, W, H, cudaMemcpyHostToDevice, c->stream));
+    CU(c, launch_begin_step(c->P, 1, nullptr, c->stream));
+    int L = 1;
+    CU(c, launch_detect(c->P, 1, c->d_stageL, c->d_stageR, c->pitch, plane, c->pitch, c->d_occ, c->occ_words,
+                        c->d_sort_scratch, c->stream, &L));
+    c->launches += L;
+    const int n = svo_get_keypoints(c, hs, 0, 0, out_kps, cap);
+    if (n < 0) return n;
+    SlotState s;
+    rc = get_state(c, hs, &s);
+    if (rc) return rc;
+    if (s.status != 0) return fail(c, s.status, "max_corners exceeded (raise svo_config.max_corners)");
+    if (out_desc) { const int m = svo_get_descriptors(c, hs, 0, 0, out_desc, cap); if (m < 0) return m; }
+    return n;
+}
+
+int svo_match_hamming_device(svo_ctx* c, const uint8_t* d_q, int32_t nq, const uint8_t* d_t, int32_t nt, int32_t reps,
+                             uint32_t* d_out) {
+    if (!c) return SVO_ERR_ARG;
+    if (nq < 0 || nt < 0 || nt > 65535 || reps < 0) return fail(c, SVO_ERR_ARG, "bad sizes (train rows must be <= 65535)");
+    CU(c, launch_hamming_raw(d_q, nq, d_t, nt, reps, d_out, c->stream));
+    if (nq > 0 && reps > 0) c->launches += 1;
+    return SVO_OK;
+}
+
+int svo_match_hamming(svo_ctx* c, const uint8_t* query, int32_t nq, const uint8_t* train, int32_t nt, svo_dmatch* out) {
+    if (!c) return SVO_ERR_ARG;
+    if (nq < 0 || nt < 0 || nt > 65535) return fail(c, SVO_ERR_ARG, "bad sizes (train rows must be <= 65535)");
+    if (nq == 0 || nt == 0) return 0;   // BFMatcher returns no matches
+    if (!query || !train || !out) return fail(c, SVO_ERR_ARG, "NULL argument");
+    CU(c, cudaSetDevice(c->cfg.device));
+    uint8_t *dq = nullptr, *dt = nullptr;
+    uint32_t* dout = nullptr;
+    CU(c, cudaMalloc(&dq, (size_t)nq * 32));
+    cudaError_t e = cudaMalloc(&dt, (size_t)nt * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)nq * 4);
+    std::vector<uint32_t> h(nq);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dq, query, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dt, train, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = launch_hamming_raw(dq, nq, dt, nt, 1, dout, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), dout, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dq); cudaFree(dt); cudaFree(dout);
+    if (e != cudaSuccess) return cuda_fail(c, e, "svo_match_hamming");
+    c->launches += 1;
+    for (int i = 0; i < nq; ++i) {
+        svo_dmatch m = {i, (int32_t)(h[i] & 0xFFFFu), 0, (float)(h[i] >> 16)};
+        out[i] = m;
+    }
+    return nq;
+}
+
+static int upload_kps(svo_ctx* c, const svo_keypoint* k, int n, int2* d_dst) {
+    std::vector<int2> tmp(n);
+    for (int i = 0; i < n; ++i) {
+        const float x = k[i].x, y = k[i].y;
+        if (!(x >= 0 && y >= 0 && x < kMaxImgDim && y < kMaxImgDim) || x != std::floor(x) || y != std::floor(y))
+            return fail(c, SVO_ERR_ARG, "svo_match_lr needs integer keypoint coordinates inside the image (FAST keypoints)");
+        tmp[i] = make_int2(((int)y << 16) | (int)x, (int)k[i].response);
+    }
+    if (n) CU(c, cudaMemcpyAsync(d_dst, tmp.data(), n * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}
+
+int svo_match_lr(svo_ctx* c, const svo_keypoint* kpsL, const uint8_t* descL, int32_t nL, const svo_keypoint* kpsR,
+                 const uint8_t* descR, int32_t nR, svo_dmatch* out, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    const int kc = c->P.p.kp_cap;
+    if (nL < 0 || nR < 0 || nL > kc || nR > kc) return fail(c, SVO_ERR_ARG, "more keypoints than the context's capacity (2*orb_nfeats)");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const int hs = c->hidden_slot;
+    int rc = set_single_slot(c, hs);
+    if (rc) return rc;
+    CU(c, launch_begin_step(c->P, 1, nullptr, c->stream));
+    SlotState s;
+    rc = get_state(c, hs, &s);
+    if (rc) return rc;
+    const size_t fL = frame_idx(hs, s.cur, 0), fR = frame_idx(hs, s.cur, 1);
+    rc = upload_kps(c, kpsL, nL, c->P.kp + fL * kc);
+    if (rc) return rc;
+    rc = upload_kps(c, kpsR, nR, c->P.kp + fR * kc);
+    if (rc) return rc;
+    if (nL) CU(c, cudaMemcpyAsync(c->P.desc + fL * kc * 2, descL, (size_t)nL * 32, cudaMemcpyHostToDevice, c->stream));
+    if (nR) CU(c, cudaMemcpyAsync(c->P.desc + fR * kc * 2, descR, (size_t)nR * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->P.n_kp + fL, &nL, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->P.n_kp + fR, &nR, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    int L = 1;
+    CU(c, launch_match_lr(c->P, 1, c->stream, &L));
+    c->launches += L;
+    return svo_get_matches(c, hs, 0, out, cap);
+}
+
+int svo_get_change_in_pose(svo_ctx* c, int32_t slot, const int64_t* tracked_pairs, int32_t n_tracked,
+                           const svo_dmatch* pre_matches, int32_t n_pre, const svo_dmatch* cur_matches, int32_t n_cur,
+                           const svo_keypoint* pre_left, int32_t n_pl, const svo_keypoint* pre_right, int32_t n_pr,
+                           const svo_keypoint* cur_left, int32_t n_cl, const svo_keypoint* cur_right, int32_t n_cr,
+                           const svo_camera* cam, int32_t use_custom_initial_pose, const double* ini_estimation,
+                           svo_result* result) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    if (!cam || !result || n_tracked < 0) return fail(c, SVO_ERR_ARG, "NULL argument");
+    const int kc = c->P.p.kp_cap;
+    if (n_tracked > kc) return fail(c, SVO_ERR_ARG, "more tracked pairs than the context's capacity (2*orb_nfeats)");
+    CU(c, cudaSetDevice(c->cfg.device));
+    // S5:419-461 on the host side of the seam: flatten the index chains into four point lists
+    std::vector<float4> prev(n_tracked), obs(n_tracked);
+    std::vector<int32_t> cur_idx(n_tracked);
+    const float W = (float)c->cfg.width, H = (float)c->cfg.height;
+    for (int i = 0; i < n_tracked; ++i) {
+        const int64_t a = tracked_pairs[2 * i], b = tracked_pairs[2 * i + 1];
+        if (a < 0 || a >= n_pre || b < 0 || b >= n_cur) return fail(c, SVO_ERR_ARG, "tracked pair index out of range");
+        const svo_dmatch& pm = pre_matches[a];
+        const svo_dmatch& cm = cur_matches[b];
+        if (pm.queryIdx < 0 || pm.queryIdx >= n_pl || pm.trainIdx < 0 || pm.trainIdx >= n_pr || cm.queryIdx < 0 ||
+            cm.queryIdx >= n_cl || cm.trainIdx < 0 || cm.trainIdx >= n_cr)
+            return fail(c, SVO_ERR_ARG, "match index out of range");
+        const svo_keypoint& pl = pre_left[pm.queryIdx];
+        if (!(pl.x >= 0 && pl.x < W && pl.y >= 0 && pl.y < H)) return fail(c, SVO_ERR_ARG, "previous-left keypoint outside the image");
+        prev[i] = make_float4(pl.x, pl.y, pre_right[pm.trainIdx].x, pl.response);
+        obs[i] = make_float4(cur_left[cm.queryIdx].x, cur_left[cm.queryIdx].y, cur_right[cm.trainIdx].x, cur_right[cm.trainIdx].y);
+        cur_idx[i] = (int32_t)b;
+    }
+    int rc = set_single_slot(c, slot);
+    if (rc) return rc;
+    const size_t base = (size_t)slot * kc;
+    if (n_tracked) {
+        CU(c, cudaMemcpyAsync(c->G.prev + base, prev.data(), n_tracked * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->G.obs + base, obs.data(), n_tracked * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->G.cur_idx + base, cur_idx.data(), n_tracked * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(c, cudaMemcpyAsync(c->P.n_tracked + slot, &n_tracked, 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->P.cam + slot, cam, sizeof(Camera), cudaMemcpyHostToDevice, c->stream));
+    double ini[6] = {0, 0, 0, 0, 0, 0};
+    if (use_custom_initial_pose && ini_estimation) memcpy(ini, ini_estimation, sizeof(ini));
+    CU(c, cudaMemcpyAsync(c->G.ini_pose + (size_t)slot * 6, ini, sizeof(ini), cudaMemcpyHostToDevice, c->stream));
+    // a fresh TStereoOdometryResult (libstereo-odometry.h:251-263)
+    Result zero;
+    memset(&zero, 0, sizeof(zero));
+    CU(c, cudaMemcpyAsync(c->P.result + slot, &zero, sizeof(zero), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    int L = 0;
+    CU(c, launch_gn(c->P, c->G, 1, /*external=*/1, use_custom_initial_pose ? 1 : 0, /*assume_fast_kps=*/0, c->stream, &L));
+    c->launches += L;
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(result, c->P.result + slot, sizeof(Result), cudaMemcpyDeviceToHost));
+    return result->valid;
+}
+
+int svo_fundmat_ransac(svo_ctx* c, const float* p1, const float* p2, int32_t n, uint8_t* mask) {
+    if (!c) return SVO_ERR_ARG;
+    if (n < 0 || (n > 0 && (!p1 || !p2 || !mask))) return fail(c, SVO_ERR_ARG, "bad arguments");
+    if (n > c->P.p.kp_cap) return fail(c, SVO_ERR_ARG, "more points than the context's capacity (2*orb_nfeats)");
+    CU(c, cudaSetDevice(c->cfg.device));
+    int inl = 0;
+    cudaError_t e = ransac_host_points(c->RS, c->hidden_slot, p1, p2, n, mask, &inl, c->stream);
+    if (e != cudaSuccess) return cuda_fail(c, e, "svo_fundmat_ransac");
+    c->launches += 1;
+    return inl;
+}
+
+}  // extern "C"

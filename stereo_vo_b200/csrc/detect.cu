@@ -1,0 +1,442 @@
+// detect.cu -- stage 2 of the hot path on sm_100a: FAST-9/16 + 7x7 blur + top-K selection +
+// row sort + 256-bit BRIEF.  Replaces, for the dmFAST_ORB branch,
+//   cv::FastFeatureDetector::detect + cv::ORB::compute   stage2_detect.cpp:510-512
+//   m_non_max_sup (8-arg)                                stage2_detect.cpp:296-370 (called :590-597)
+//   m_update_indexes                                     stage2_detect.cpp:65-130  (called :618)
+//
+// Order of work differs from the reference (which describes every corner and then throws most
+// descriptors away, see the authors' TODO at stage2_detect.cpp:507): corners are selected first and
+// only the survivors are described.  A descriptor depends on its own keypoint only and the border
+// filter of ORB::compute is applied before the selection, so the results are identical.
+#include "detect.cuh"
+#include "introsort_emul.cuh"
+
+namespace svo {
+
+// ------------------------------------------------------------------------------------------------
+// K1  fast_blur_kernel: one CTA per 64x32 tile.
+//   in : 8-bit image (HBM, read once through shared memory, halo 4)
+//   out: blur  (7x7 sigma=2, OpenCV float32 FMA order, rint, saturate)        1 B / px
+//        score (FAST-9/16 corner score after strict 3x3 NMS and the 31-px ORB border filter) 1 B / px
+// Roofline: algorithmic HBM traffic 3 B / px; the kernel is integer-ALU bound (about 250 lane-ops
+// per pixel for the ring test and the arc min/max network), not HBM bound.
+// ------------------------------------------------------------------------------------------------
+constexpr int TW = 64, TH = 32, HALO = 4;
+constexpr int SIN_W = TW + 2 * HALO;   // 72
+constexpr int SIN_H = TH + 2 * HALO;   // 40
+constexpr int SSC_W = TW + 4;          // score tile with halo 1, padded to 68
+constexpr int K1_THREADS = 256;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+// cv::getGaussianKernel(7, 2, CV_32F) bit patterns
+__device__ __forceinline__ float gk(int i) {
+    const uint32_t b[7] = {0x3D8FAFB1u, 0x3E06387Eu, 0x3E434A39u, 0x3E5D4AE0u, 0x3E434A39u, 0x3E06387Eu, 0x3D8FAFB1u};
+    return __uint_as_float(b[i]);
+}
+
+// FAST-9/16 score of the pixel at s (shared memory, row pitch SIN_W); 0 if it is not a corner.
+__device__ __forceinline__ int fast9_score(const uint8_t* __restrict__ s, int th) {
+    const int v = s[0];
+    int d[16];
+    d[0] = v - s[3 * SIN_W + 0];   d[1] = v - s[3 * SIN_W + 1];   d[2] = v - s[2 * SIN_W + 2];   d[3] = v - s[1 * SIN_W + 3];
+    d[4] = v - s[3];               d[5] = v - s[-1 * SIN_W + 3];  d[6] = v - s[-2 * SIN_W + 2];  d[7] = v - s[-3 * SIN_W + 1];
+    d[8] = v - s[-3 * SIN_W + 0];  d[9] = v - s[-3 * SIN_W - 1];  d[10] = v - s[-2 * SIN_W - 2]; d[11] = v - s[-1 * SIN_W - 3];
+    d[12] = v - s[-3];             d[13] = v - s[1 * SIN_W - 3];  d[14] = v - s[2 * SIN_W - 2];  d[15] = v - s[3 * SIN_W - 1];
+    unsigned dark = 0, bright = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        dark |= (unsigned)(d[k] > th) << k;
+        bright |= (unsigned)(d[k] < -th) << k;
+    }
+    // 9 contiguous set bits on the 16-ring
+    dark |= dark << 16;
+    bright |= bright << 16;
+    unsigned t = dark & (dark >> 1);
+    t &= t >> 2; t &= t >> 4; t &= dark >> 8;
+    unsigned u = bright & (bright >> 1);
+    u &= u >> 2; u &= u >> 4; u &= bright >> 8;
+    if (((t | u) & 0xFFFFu) == 0) return 0;
+    // score = max over the 16 arcs of length 9 of min(d) and of min(-d), minus 1
+    int lo2[16], hi2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
+    int lo4[16], hi4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
+    int best = -1024;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
+        best = max(best, max(lo9, -hi9));
+    }
+    return best - 1;
+}
+
+__global__ void __launch_bounds__(K1_THREADS)
+fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __restrict__ imgR,
+                 size_t stride, size_t image_pitch, int pitch_out) {
+    __shared__ __align__(16) uint8_t s_in[SIN_H * SIN_W];
+    __shared__ float s_row[(TH + 6) * TW];
+    __shared__ __align__(4) uint8_t s_sc[(TH + 2) * SSC_W];
+
+    const int W = P.p.W, H = P.p.H;
+    const int item = blockIdx.z >> 1, side = blockIdx.z & 1;
+    const int slot = P.slots[item];
+    const uint8_t* __restrict__ img = (side ? imgR : imgL) + (size_t)item * image_pitch;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.x;
+
+    // 1. stage the tile with halo 4 (REFLECT_101 outside the image, only the blur looks there)
+    for (int i = tid; i < SIN_H * SIN_W; i += K1_THREADS) {
+        const int r = i / SIN_W, c = i - r * SIN_W;
+        const int gy = reflect101(y0 - HALO + r, H), gx = reflect101(x0 - HALO + c, W);
+        s_in[i] = __ldg(img + (size_t)gy * stride + gx);
+    }
+    __syncthreads();
+
+    // 2. blur, row pass: rows y0-3 .. y0+TH+2  (float32, sequential FMA left to right)
+    for (int i = tid; i < (TH + 6) * TW; i += K1_THREADS) {
+        const int r = i / TW, c = i - r * TW;
+        const uint8_t* p = s_in + (r + 1) * SIN_W + c + 1;   // column x-3
+        float acc = __fmul_rn(gk(0), (float)p[0]);
+#pragma unroll
+        for (int t = 1; t < 7; ++t) acc = __fmaf_rn(gk(t), (float)p[t], acc);
+        s_row[i] = acc;
+    }
+    // 3. FAST score on the tile plus a 1-px ring (needed by the 3x3 NMS)
+    const int th = P.p.fast_th;
+    for (int i = tid; i < (TH + 2) * (TW + 2); i += K1_THREADS) {
+        const int r = i / (TW + 2), c = i - r * (TW + 2);
+        const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+        int sc = 0;
+        if (gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3)
+            sc = fast9_score(s_in + (r + HALO - 1) * SIN_W + (c + HALO - 1), th);
+        s_sc[r * SSC_W + c] = (uint8_t)sc;
+    }
+    __syncthreads();
+
+    // 4. blur column pass + NMS / border filter; 4 pixels per thread, 32-bit stores
+    uint8_t* __restrict__ blur_out = P.blur + img_idx(slot, side) * (size_t)pitch_out * H;
+    uint8_t* __restrict__ score_out = P.score + img_idx(slot, side) * (size_t)pitch_out * H;
+    for (int i = tid; i < TH * TW / 4; i += K1_THREADS) {
+        const int r = i / (TW / 4), c4 = (i - r * (TW / 4)) * 4;
+        const int gy = y0 + r, gx = x0 + c4;
+        if (gy >= H || gx >= pitch_out) continue;
+        uint32_t bw = 0, sw = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c4 + q;
+            const float* rr = s_row + (r + 3) * TW + c;
+            float acc = __fmul_rn(gk(3), rr[0]);
+#pragma unroll
+            for (int j = 1; j <= 3; ++j) acc = __fmaf_rn(gk(3 + j), __fadd_rn(rr[j * TW], rr[-j * TW]), acc);
+            int v = __float2int_rn(acc);   // round half to even
+            v = min(255, max(0, v));
+            bw |= (uint32_t)v << (8 * q);
+            const uint8_t* sp = s_sc + (r + 1) * SSC_W + (c + 1);
+            const int s = sp[0];
+            const int x = gx + q;
+            bool keep = s > 0 && x >= kOrbEdge && x < W - kOrbEdge && gy >= kOrbEdge && gy < H - kOrbEdge;
+            if (keep) {
+                keep = s > sp[-SSC_W - 1] && s > sp[-SSC_W] && s > sp[-SSC_W + 1] && s > sp[-1] && s > sp[1] &&
+                       s > sp[SSC_W - 1] && s > sp[SSC_W] && s > sp[SSC_W + 1];
+            }
+            sw |= (uint32_t)(keep ? s : 0) << (8 * q);
+        }
+        *reinterpret_cast<uint32_t*>(blur_out + (size_t)gy * pitch_out + gx) = bw;
+        *reinterpret_cast<uint32_t*>(score_out + (size_t)gy * pitch_out + gx) = sw;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  select_kernel: one CTA per image.
+//   A. row-major ordered compaction of the score map  -> candidate words  score<<24 | ordinal
+//   B. std::sort emulation by response (descending)                       S2:322-324
+//   C. greedy grid occupancy, first `quota` survivors                     S2:331-369
+//   D. std::sort emulation by row (ascending)                             S2:87-89
+//   E. write keypoints in final order
+// ------------------------------------------------------------------------------------------------
+constexpr int K2_THREADS = 256;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int wsum = (lane < K2_THREADS / 32) ? s_warp[lane] : 0;
+    int wincl = wsum;
+#pragma unroll
+    for (int o = 1; o < K2_THREADS / 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += t;
+    }
+    const int wexcl = __shfl_sync(0xffffffffu, wincl - wsum, wid);
+    total = __shfl_sync(0xffffffffu, wincl, K2_THREADS / 32 - 1);
+    __syncthreads();
+    return wexcl + incl - v;
+}
+
+// rank-based stable sort (diagnostic sort_mode = 1): O(n^2 / threads)
+template <bool Desc, int Shift>
+__device__ void block_stable_sort(uint32_t* a, uint32_t* tmp, int n) {
+    const KeyComp<Desc, Shift> C;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t v = a[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const uint32_t w = a[j];
+            rank += (C.lt(w, v) || (!C.lt(v, w) && j < i)) ? 1 : 0;
+        }
+        tmp[rank] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = tmp[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(K2_THREADS)
+select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_words_per_img,
+              uint32_t* __restrict__ sort_scratch) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* s_a = smem;                          // [max_corners]
+    uint32_t* s_b = smem + P.p.max_corners;        // [kp_cap]
+    __shared__ int s_warp[K2_THREADS / 32];
+    __shared__ int s_n, s_nsel;
+
+    const int W = P.p.W, H = P.p.H;
+    const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
+    const int slot = P.slots[item];
+    const int tid = threadIdx.x;
+    const uint8_t* __restrict__ score = P.score + img_idx(slot, side) * (size_t)pitch * H;
+    uint32_t* __restrict__ cand_pos = P.cand_pos + img_idx(slot, side) * (size_t)P.p.max_corners;
+
+    // ---- A. ordered compaction ---------------------------------------------------------------
+    const int segs = pitch / 16;
+    const int rows = max(0, H - 2 * kOrbEdge);
+    const int total_segs = rows * segs;
+    int base = 0;
+    bool overflow = false;
+    for (int g0 = 0; g0 < total_segs; g0 += K2_THREADS) {
+        const int g = g0 + tid;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        int y = 0, x = 0;
+        if (g < total_segs) {
+            y = kOrbEdge + g / segs;
+            x = (g % segs) * 16;
+            v = *reinterpret_cast<const uint4*>(score + (size_t)y * pitch + x);
+        }
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            // number of non-zero bytes in w[q]
+            const uint32_t nz = ((w[q] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w[q]) & 0x80808080u;
+            cnt += __popc(nz);
+        }
+        int total;
+        const int off = block_exclusive_scan(cnt, s_warp, total);
+        if (cnt) {
+            int o = base + off;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t s = (w[q] >> (8 * b)) & 0xFFu;
+                    if (s) {
+                        if (o < P.p.max_corners) {
+                            s_a[o] = (s << 24) | (uint32_t)o;
+                            cand_pos[o] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * q + b);
+                        }
+                        ++o;
+                    }
+                }
+        }
+        base += total;
+    }
+    if (base > P.p.max_corners) { overflow = true; base = P.p.max_corners; }
+    const int n = base;
+    if (tid == 0) {
+        P.n_cand[img_idx(slot, side)] = n;
+        if (overflow) P.state[slot].status = -3;  // SVO_ERR_CAPACITY
+    }
+    __syncthreads();
+
+    const int cur = P.state[slot].cur;
+    int2* __restrict__ kp_out = P.kp + frame_idx(slot, cur, side) * (size_t)P.p.kp_cap;
+    int n_sel;
+
+    if (P.p.nms) {
+        // ---- B. sort by response, descending (KeypointResponseSorter) ------------------------------
+        if (P.p.sort_mode == 0) {
+            if (tid == 0) introsort_seq<true, 24>(s_a, n);
+            __syncthreads();
+        } else {
+            block_stable_sort<true, 24>(s_a, sort_scratch + (size_t)blockIdx.x * P.p.max_corners, n);
+        }
+        // ---- C. greedy occupancy grid ---------------------------------------------------------------
+        const unsigned cell = (unsigned)(P.p.min_distance / 2.0);     // S2:331
+        if (cell == 1) {
+            // FAST's strict 3x3 NMS leaves no two corners in 8-adjacent pixels, and with 1-px cells a
+            // corner only blocks its own pixel and the 4 neighbours: nothing is ever rejected.
+            n_sel = min(n, P.p.quota);
+        } else {
+            if (tid == 0) {
+                const float cell_inv = 1.0f / (float)cell;                 // S2:332
+                const unsigned glx = (unsigned)(1 + W * cell_inv), gly = (unsigned)(1 + H * cell_inv);
+                uint32_t* occ = occ_scratch + (size_t)blockIdx.x * occ_words_per_img;
+                for (unsigned i = 0; i < (glx * gly + 31) / 32; ++i) occ[i] = 0;
+                auto get = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; return (occ[b >> 5] >> (b & 31)) & 1u; };
+                auto set = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; occ[b >> 5] |= 1u << (b & 31); };
+                int c = 0, k = 0;
+                while (c < P.p.quota && k < n) {
+                    const uint32_t wd = s_a[k++];
+                    const uint32_t pos = cand_pos[wd & 0xFFFFFFu];
+                    const unsigned sx = (unsigned)((float)(pos & 0xFFFFu) * cell_inv);
+                    const unsigned sy = (unsigned)((float)(pos >> 16) * cell_inv);
+                    if (get(sx, sy)) continue;
+                    set(sx, sy);
+                    if (sx > 0) set(sx - 1, sy);
+                    if (sy > 0) set(sx, sy - 1);
+                    if (sx < glx - 1) set(sx + 1, sy);
+                    if (sy < gly - 1) set(sx, sy + 1);
+                    s_a[c++] = wd;   // c <= k-1: in-place compaction of the survivors
+                }
+                s_nsel = c;
+            }
+            __syncthreads();
+            n_sel = s_nsel;
+        }
+    } else {
+        n_sel = min(n, P.p.kp_cap);   // feats_vector.swap(...)  S2:613
+    }
+
+    // ---- D. sort by row (KpRowSorter), ascending ----------------------------------------------------
+    for (int k = tid; k < n_sel; k += K2_THREADS) {
+        const uint32_t pos = cand_pos[s_a[k] & 0xFFFFFFu];
+        s_b[k] = (pos & 0xFFFF0000u) | (uint32_t)k;   // y << 16 | position in the selection order
+    }
+    __syncthreads();
+    if (P.p.sort_mode == 0) {
+        if (tid == 0) introsort_seq<false, 16>(s_b, n_sel);
+        __syncthreads();
+    } else {
+        block_stable_sort<false, 16>(s_b, sort_scratch + (size_t)blockIdx.x * P.p.max_corners, n_sel);
+    }
+    // ---- E. emit ------------------------------------------------------------------------------------
+    for (int i = tid; i < n_sel; i += K2_THREADS) {
+        const uint32_t wd = s_a[s_b[i] & 0xFFFFu];
+        kp_out[i] = make_int2((int)cand_pos[wd & 0xFFFFFFu], (int)(wd >> 24));
+    }
+    if (tid == 0) {
+        P.n_kp[frame_idx(slot, cur, side)] = n_sel;
+        if (side == 0) P.result[slot].detected_left = n_sel; else P.result[slot].detected_right = n_sel;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  brief_kernel: one warp per keypoint, lane l produces descriptor byte l (tests 8l..8l+7).
+//   bit i = blur[y+ay_i][x+ax_i] < blur[y+by_i][x+bx_i]      (cv::ORB::compute, S2:512)
+// ------------------------------------------------------------------------------------------------
+__constant__ int8_t c_orb_pattern[256][4] = {
+#include "orb_pattern.inc"
+};
+
+constexpr int K3_WARPS = 8;
+
+__global__ void __launch_bounds__(K3_WARPS * 32)
+brief_kernel(Pools P, int pitch) {
+    __shared__ int s_off[512];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        s_off[2 * i] = c_orb_pattern[i][1] * pitch + c_orb_pattern[i][0];
+        s_off[2 * i + 1] = c_orb_pattern[i][3] * pitch + c_orb_pattern[i][2];
+    }
+    __syncthreads();
+    const int item = blockIdx.y >> 1, side = blockIdx.y & 1;
+    const int slot = P.slots[item];
+    const int cur = P.state[slot].cur;
+    const size_t f = frame_idx(slot, cur, side);
+    const int n = P.n_kp[f];
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * K3_WARPS + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const int2 kp = P.kp[f * P.p.kp_cap + k];
+    const int x = kp.x & 0xFFFF, y = (unsigned)kp.x >> 16;
+    const uint8_t* __restrict__ c = P.blur + img_idx(slot, side) * (size_t)pitch * P.p.H + (size_t)y * pitch + x;
+    unsigned v = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int i = lane * 8 + t;
+        const int a = c[s_off[2 * i]], b = c[s_off[2 * i + 1]];
+        v |= (unsigned)(a < b) << t;
+    }
+    reinterpret_cast<uint8_t*>(P.desc + (f * P.p.kp_cap + k) * 2)[lane] = (uint8_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0  begin_step_kernel: the prev/cur shift rule of processNewImagePair (P:86-100)
+// ------------------------------------------------------------------------------------------------
+__global__ void begin_step_kernel(Pools P, int n, const uint8_t* __restrict__ repeat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = P.slots[i];
+    SlotState& s = P.state[slot];
+    const int rep = repeat ? repeat[i] : 0;
+    if (!rep && s.m_error != 5 /*voecBadTracking*/ && s.m_error != 1 /*voecBadCondNumber*/) {
+        // m_prev_imgpair = m_current_imgpair: the buffers swap roles, the old "prev" gets overwritten
+        s.has_prev = s.has_cur;
+        s.cur ^= 1;
+    }
+    s.repeat = rep;
+    s.m_error = 0;
+    s.status = 0;
+    s.has_cur = 1;
+    Result& r = P.result[slot];
+    r.error_code = 0;
+    r.valid = 0;
+    r.num_it = r.num_it_final = 0;
+    r.n_outliers = 0;
+    r.n_residuals = 0;
+    r.tracked_frame = 0;
+    r.tracked_kf = 0;
+    r.status = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+int detect_smem_bytes(const Params& p) { return (p.max_corners + p.kp_cap) * (int)sizeof(uint32_t); }
+
+cudaError_t configure_detect(const Params& p) {
+    return cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, detect_smem_bytes(p));
+}
+
+cudaError_t launch_begin_step(const Pools& P, int n, const uint8_t* d_repeat, cudaStream_t st) {
+    begin_step_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, n, d_repeat);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_detect(const Pools& P, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
+                          size_t image_pitch, int pitch_out, uint32_t* occ_scratch, int occ_words_per_img,
+                          uint32_t* sort_scratch, cudaStream_t st, int* launches) {
+    const dim3 g1((P.p.W + TW - 1) / TW, (P.p.H + TH - 1) / TH, 2 * n);
+    fast_blur_kernel<<<g1, K1_THREADS, 0, st>>>(P, d_left, d_right, stride, image_pitch, pitch_out);
+    const int smem = detect_smem_bytes(P.p);
+    select_kernel<<<2 * n, K2_THREADS, smem, st>>>(P, pitch_out, occ_scratch, occ_words_per_img, sort_scratch);
+    const dim3 g3((P.p.kp_cap + K3_WARPS - 1) / K3_WARPS, 2 * n);
+    brief_kernel<<<g3, K3_WARPS * 32, 0, st>>>(P, pitch_out);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+
+}  // namespace svo

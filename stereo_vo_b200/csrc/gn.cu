@@ -1,0 +1,513 @@
+// gn.cu -- stage 5 of the hot path on sm_100a: robust Gauss-Newton SE(3) refinement of the stereo
+// reprojection error, one persistent CTA per stereo pair, no host synchronisation between
+// iterations.  Replaces
+//   stage5_optimize                stage5_optimization.cpp:392-736
+//   m_evalRGN                      stage5_optimization.cpp:275-390
+//   m_pinhole_stereo_projection    stage5_optimization.cpp:35-257
+//   m_non_max_sup (aux, 5-arg)     stage2_detect.cpp:225-283  (called stage5_optimization.cpp:470-474)
+//   Eigen::JacobiSVD solve         stage5_optimization.cpp:375-388
+//   CPose3DRotVec::getInverse / CPose3D(rotvec)   stage5_optimization.cpp:717-718
+// and keeps the reference's quirks: unweighted Hessian with weighted gradient (:364-365), the
+// Jacobian typo at :162, float32 residual subtraction (:335-338), `timesInc` shared by both loops
+// (:547), result.outliers holding the inliers (:601-610).
+//
+// Per correspondence and iteration: 4 residuals + 4x6 Jacobian in FP64, pseudo-Huber weight,
+// accumulation of the 21 upper-triangle entries of J^T J, the 6 entries of J^T r and the cost with
+// warp shuffles, then a cross-warp sum in shared memory; thread 0 solves the 6x6 system.
+// HBM traffic is ~40 B per correspondence (L2 resident across iterations): the kernel is bound by
+// FP64 latency and the block-wide reduction, not by bandwidth.
+#include "gn.cuh"
+#include "introsort_emul.cuh"
+#include <cfloat>
+
+namespace svo {
+
+constexpr int GN_THREADS = 256;
+constexpr int NACC = 28;   // 21 (H upper triangle) + 6 (g) + 1 (cost)
+
+struct RotDeriv {
+    double r[3][3];
+    double dr[3][3][3];   // dr[row][col][k] = d r(row,col) / d w_k
+    int small;
+};
+
+// S5:45-163
+__device__ void rot_and_derivs(const double* dp, RotDeriv& o) {
+    const double w1 = dp[0], w2 = dp[1], w3 = dp[2];
+    const double w12 = w1 * w1, w22 = w2 * w2, w32 = w3 * w3;
+    const double tt = sqrt(w1 * w1 + w2 * w2 + w3 * w3);
+    const double tt2 = tt * tt, tt3 = tt2 * tt, tt4 = tt3 * tt;
+    const double sin_tt = sin(tt), cos_tt = cos(tt);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) o.dr[i][j][k] = 0;
+    o.small = tt < 1e-5;
+    if (o.small) {
+        o.r[0][0] = 1;   o.r[0][1] = -w3; o.r[0][2] = w2;
+        o.r[1][0] = w3;  o.r[1][1] = 1;   o.r[1][2] = -w1;
+        o.r[2][0] = -w2; o.r[2][1] = w1;  o.r[2][2] = 1;
+        o.dr[0][1][2] = -1; o.dr[0][2][1] = 1;
+        o.dr[1][0][2] = 1;  o.dr[1][2][0] = -1;
+        o.dr[2][0][1] = -1; o.dr[2][1][0] = 1;
+        return;
+    }
+    const double u = (cos_tt - 1) / tt2;
+    const double dudw1 = ((-sin_tt * w1 / tt) * tt2 - (cos_tt - 1) * 2 * w1) / tt4;
+    const double dudw2 = ((-sin_tt * w2 / tt) * tt2 - (cos_tt - 1) * 2 * w2) / tt4;
+    const double dudw3 = ((-sin_tt * w3 / tt) * tt2 - (cos_tt - 1) * 2 * w3) / tt4;
+    const double v = sin_tt / tt;
+    const double dvdw1 = w1 * (tt * cos_tt - sin_tt) / tt3;
+    const double dvdw2 = w2 * (tt * cos_tt - sin_tt) / tt3;
+    const double dvdw3 = w3 * (tt * cos_tt - sin_tt) / tt3;
+    o.r[0][0] = (w22 + w32) * u + 1;    o.r[0][1] = -w3 * v - w1 * w2 * u;  o.r[0][2] = w2 * v - w1 * w3 * u;
+    o.r[1][0] = w3 * v - w1 * w2 * u;   o.r[1][1] = (w12 + w32) * u + 1;    o.r[1][2] = -w1 * v - w2 * w3 * u;
+    o.r[2][0] = -w2 * v - w1 * w3 * u;  o.r[2][1] = w1 * v - w2 * w3 * u;   o.r[2][2] = (w12 + w22) * u + 1;
+    o.dr[0][0][0] = (w22 + w32) * dudw1;
+    o.dr[0][0][1] = 2 * w2 * u + (w22 + w32) * dudw2;
+    o.dr[0][0][2] = 2 * w3 * u + (w22 + w32) * dudw3;
+    o.dr[0][1][0] = -w3 * dvdw1 - (w2 * u + w1 * w2 * dudw1);
+    o.dr[0][1][1] = -w3 * dvdw2 - (w1 * u + w1 * w2 * dudw2);
+    o.dr[0][1][2] = -(v + w3 * dvdw3) - w1 * w2 * dudw3;
+    o.dr[0][2][0] = w2 * dvdw1 - (w3 * u + w1 * w3 * dudw1);
+    o.dr[0][2][1] = (v + w2 * dvdw2) - w1 * w3 * dudw2;
+    o.dr[0][2][2] = w2 * dvdw3 - (w1 * u + w1 * w3 * dudw3);
+    o.dr[1][0][0] = w3 * dvdw1 - (w2 * u + w1 * w2 * dudw1);
+    o.dr[1][0][1] = w3 * dvdw2 - (w1 * u + w1 * w2 * dudw2);
+    o.dr[1][0][2] = (v + w3 * dvdw3) - w1 * w2 * dudw3;
+    o.dr[1][1][0] = 2 * w1 * u + (w12 + w32) * dudw1;
+    o.dr[1][1][1] = (w12 + w32) * dudw2;
+    o.dr[1][1][2] = 2 * w3 * u + (w12 + w32) * dudw3;
+    o.dr[1][2][0] = -(v + w1 * dvdw1) - w2 * w3 * dudw1;
+    o.dr[1][2][1] = -w1 * dvdw2 - (w3 * u + w2 * w3 * dudw2);
+    o.dr[1][2][2] = -w1 * dvdw3 - (w2 * u + w2 * w3 * dudw3);
+    o.dr[2][0][0] = -w2 * dvdw1 - (w3 * u + w1 * w3 * dudw1);
+    o.dr[2][0][1] = -(v + w2 * dvdw2) - w1 * w3 * dudw2;
+    o.dr[2][0][2] = -w2 * dvdw3 - (w1 * u + w1 * w3 * dudw3);
+    o.dr[2][1][0] = (v + w1 * dvdw1) - w2 * w3 * dudw1;
+    o.dr[2][1][1] = w1 * dvdw2 - (w3 * u + w2 * w3 * dudw2);
+    o.dr[2][1][2] = w1 * dvdw3 - (w2 * u + w2 * w3 * dudw3);
+    o.dr[2][2][0] = 2 * w1 * u + (w12 + w22) * dudw1;
+    o.dr[2][2][1] = 2 * w2 * u + (w12 + w22) * dudw2;
+    o.dr[2][2][2] = (w22 + w32) * dudw3;   // sic, reference typo S5:162
+}
+
+// Symmetric 6x6 eigen-decomposition by cyclic Jacobi; stands in for Eigen::JacobiSVD on the
+// (symmetric positive semi-definite) Hessian: singular values = |eigenvalues|.
+// Returns false when the condition number sigma_max/sigma_min would be NaN (S5:379-386).
+__device__ bool solve6(const double* Hu /* 21 upper-triangle entries, row-major */, const double* g, double* x) {
+    double A[6][6], V[6][6];
+    bool finite = true;
+    {
+        int k = 0;
+        for (int i = 0; i < 6; ++i)
+            for (int j = i; j < 6; ++j) {
+                A[i][j] = A[j][i] = Hu[k++];
+                finite = finite && isfinite(A[i][j]);
+            }
+    }
+    if (!finite) return false;
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0, diag = 0;
+        for (int i = 0; i < 6; ++i) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < 6; ++j) off += A[i][j] * A[i][j]; }
+        if (off <= diag * 1e-34 || off == 0.0) break;
+        for (int p = 0; p < 5; ++p)
+            for (int q = p + 1; q < 6; ++q) {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 6; ++k) {   // columns p,q
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 6; ++k) {   // rows p,q
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 6; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    double smax = 0, smin = DBL_MAX;
+    for (int i = 0; i < 6; ++i) { const double s = fabs(A[i][i]); smax = fmax(smax, s); smin = fmin(smin, s); }
+    if (smax == 0.0 && smin == 0.0) return false;          // 0/0 = NaN
+    const double thr = fmax(smax * 6.0 * DBL_EPSILON, DBL_MIN);   // Eigen SVDBase::rank() threshold
+    for (int i = 0; i < 6; ++i) x[i] = 0;
+    for (int k = 0; k < 6; ++k) {
+        if (!(fabs(A[k][k]) > thr)) continue;
+        double proj = 0;
+        for (int i = 0; i < 6; ++i) proj += V[i][k] * g[i];
+        proj /= A[k][k];
+        for (int i = 0; i < 6; ++i) x[i] += V[i][k] * proj;
+    }
+    return true;
+}
+
+__device__ void rodrigues(const double* w, double R[3][3]) {
+    const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    double a, b;
+    if (th < 1e-12) { a = 1.0; b = 0.5; }
+    else { a = sin(th) / th; b = (1 - cos(th)) / (th * th); }
+    const double K[3][3] = {{0, -w[2], w[1]}, {w[2], 0, -w[0]}, {-w[1], w[0], 0}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double k2 = 0;
+            for (int k = 0; k < 3; ++k) k2 += K[i][k] * K[k][j];
+            R[i][j] = (i == j ? 1.0 : 0.0) + a * K[i][j] + b * k2;
+        }
+}
+
+struct GNShared {
+    RotDeriv R;
+    double acc[GN_THREADS / 32][NACC];
+    double pose[6];
+    double step[6];
+    double cCost, pCost;
+    int done, abort, fail;
+    unsigned timesInc;
+    int n_non_masked;
+};
+
+// one m_evalRGN (S5:275-390); returns through sh: step, cCost, fail
+__device__ void eval_rgn(const GnScratch& G, size_t base, int T, const Camera& cam, const Params& p, GNShared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) rot_and_derivs(sh.pose, sh.R);
+    __syncthreads();
+    const RotDeriv& R = sh.R;
+    double dp[6];
+    for (int i = 0; i < 6; ++i) dp[i] = sh.pose[i];
+    const double b2 = p.use_robust_kernel ? p.kernel_param * p.kernel_param : 0;
+    const double b2_1 = p.use_robust_kernel ? 1. / b2 : 0;
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0;
+    for (int m = tid; m < T; m += GN_THREADS) {
+        if (!G.mask[base + m]) continue;
+        const double X1p = G.lmk[(base + m) * 3 + 0], Y1p = G.lmk[(base + m) * 3 + 1], Z1p = G.lmk[(base + m) * 3 + 2];
+        const double X1c = R.r[0][0] * X1p + R.r[0][1] * Y1p + R.r[0][2] * Z1p + dp[3];
+        const double Y1c = R.r[1][0] * X1p + R.r[1][1] * Y1p + R.r[1][2] * Z1p + dp[4];
+        const double Z1c = R.r[2][0] * X1p + R.r[2][1] * Y1p + R.r[2][2] * Z1p + dp[5];
+        const double X2c = X1c - cam.baseline;
+        const float px0 = (float)(cam.fxl * X1c / Z1c + cam.cxl);
+        const float px1 = (float)(cam.fyl * Y1c / Z1c + cam.cyl);
+        const float px2 = (float)(cam.fxr * X2c / Z1c + cam.cxr);
+        const float px3 = (float)(cam.fyr * Y1c / Z1c + cam.cyr);
+        double J[4][6];
+        bool good = true;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double X1cd, Y1cd, Z1cd;
+            if (j < 3) {
+                if (R.small) {
+                    if (j == 0)      { X1cd = 0;    Y1cd = -Z1p; Z1cd = Y1p; }
+                    else if (j == 1) { X1cd = Z1p;  Y1cd = 0;    Z1cd = -X1p; }
+                    else             { X1cd = -Y1p; Y1cd = X1p;  Z1cd = 0; }
+                } else {
+                    X1cd = R.dr[0][0][j] * X1p + R.dr[0][1][j] * Y1p + R.dr[0][2][j] * Z1p;
+                    Y1cd = R.dr[1][0][j] * X1p + R.dr[1][1][j] * Y1p + R.dr[1][2][j] * Z1p;
+                    Z1cd = R.dr[2][0][j] * X1p + R.dr[2][1][j] * Y1p + R.dr[2][2][j] * Z1p;
+                }
+            } else {
+                X1cd = (j == 3); Y1cd = (j == 4); Z1cd = (j == 5);
+            }
+            J[0][j] = cam.fxl * (X1cd * Z1c - X1c * Z1cd) / (Z1c * Z1c);
+            J[1][j] = cam.fyl * (Y1cd * Z1c - Y1c * Z1cd) / (Z1c * Z1c);
+            J[2][j] = cam.fxr * (X1cd * Z1c - X2c * Z1cd) / (Z1c * Z1c);
+            J[3][j] = cam.fyr * (Y1cd * Z1c - Y1c * Z1cd) / (Z1c * Z1c);
+            good = good && isfinite(J[0][j]) && isfinite(J[1][j]) && isfinite(J[2][j]) && isfinite(J[3][j]);
+        }
+        if (!good) continue;   // m_jacobian_is_good, S5:322
+        const float4 ob = G.obs[base + m];
+        const double r0 = (double)(ob.x - px0), r1 = (double)(ob.y - px1);   // float32 subtraction, S5:335-338
+        const double r2 = (double)(ob.z - px2), r3 = (double)(ob.w - px3);
+        const double s = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+        G.residual[base + m] = s;
+        double rho_p = 1, fi;
+        if (p.use_robust_kernel) {
+            const double n = sqrt(1 + (s * b2_1));
+            rho_p = 1 / n;
+            fi = b2 * (n - 1);
+        } else {
+            fi = 0.5 * s;
+        }
+        acc[27] += fi;
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            acc[21 + a] += rho_p * (J[0][a] * r0 + J[1][a] * r1 + J[2][a] * r2 + J[3][a] * r3);
+#pragma unroll
+            for (int b = a; b < 6; ++b)
+                acc[k++] += J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b] + J[3][a] * J[3][b];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh.acc[wid][i] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot[NACC];
+        for (int i = 0; i < NACC; ++i) {
+            double v = 0;
+            for (int w = 0; w < GN_THREADS / 32; ++w) v += sh.acc[w][i];
+            tot[i] = v;
+        }
+        sh.cCost = tot[27];
+        sh.fail = solve6(tot, tot + 21, sh.step) ? 0 : 1;
+    }
+    __syncthreads();
+}
+
+// S5:528-544 / S5:623-638; returns the number of survivors
+__device__ int triangulate(const GnScratch& G, size_t base, int T, const Camera& cam, int* s_cnt) {
+    int cnt = 0;
+    for (int m = threadIdx.x; m < T; m += GN_THREADS) {
+        if (!G.mask[base + m]) continue;
+        ++cnt;
+        const float4 pp = G.prev[base + m];   // l1l.x, l1l.y, l1r.x, response
+        const double ul = pp.x, vl = pp.y, ur = pp.z;
+        const double b_d = cam.baseline / (cam.fxl * (cam.cxr - ur) + cam.fxr * (ul - cam.cxl));
+        G.lmk[(base + m) * 3 + 0] = b_d * cam.fxr * (ul - cam.cxl);
+        G.lmk[(base + m) * 3 + 1] = b_d * cam.fxr * (vl - cam.cyl);
+        G.lmk[(base + m) * 3 + 2] = b_d * cam.fxl * cam.fxr;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    int tot = 0;
+    for (int w = 0; w < GN_THREADS / 32; ++w) tot += s_cnt[w];
+    __syncthreads();
+    return tot;
+}
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fast_kps) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];   // [cap] uint32 index + [cap] float key (aux NMS)
+    __shared__ GNShared sh;
+    __shared__ int s_cnt[GN_THREADS / 32];
+    const int slot = P.slots[blockIdx.x];
+    SlotState& st = P.state[slot];
+    Result& res = P.result[slot];
+    const Params& p = P.p;
+    const int tid = threadIdx.x;
+    const size_t cap = (size_t)p.kp_cap;
+    const size_t base = (size_t)slot * cap;
+    const Camera cam = P.cam[slot];
+
+    if (!external) {
+        if (!st.has_prev) return;               // voecFirstIteration already reported (P:348-352)
+        if (st.m_error == 5) return;            // voecBadTracking: stage 5 is skipped (P:332)
+    }
+    const int T = P.n_tracked[slot];
+    const int cur = st.cur, prev = cur ^ 1;
+
+    // ---- S5:419-461: gather the four point lists ----------------------------------------------------
+    if (!external) {
+        const int4* mp = P.match + pair_idx(slot, prev) * cap;
+        const int4* mc = P.match + pair_idx(slot, cur) * cap;
+        const int2* kpl = P.kp + frame_idx(slot, prev, 0) * cap;
+        const int2* kpr = P.kp + frame_idx(slot, prev, 1) * cap;
+        const int2* kcl = P.kp + frame_idx(slot, cur, 0) * cap;
+        const int2* kcr = P.kp + frame_idx(slot, cur, 1) * cap;
+        for (int i = tid; i < T; i += GN_THREADS) {
+            const int2 tp = P.tracked[base + i];
+            const int4 a = mp[tp.x], b = mc[tp.y];
+            const int2 pl = kpl[a.x], pr = kpr[a.y], cl = kcl[b.x], cr = kcr[b.y];
+            G.prev[base + i] = make_float4((float)(pl.x & 0xFFFF), (float)((unsigned)pl.x >> 16), (float)(pr.x & 0xFFFF), (float)pl.y);
+            G.obs[base + i] = make_float4((float)(cl.x & 0xFFFF), (float)((unsigned)cl.x >> 16),
+                                          (float)(cr.x & 0xFFFF), (float)((unsigned)cr.x >> 16));
+        }
+    }
+    for (int i = tid; i < T; i += GN_THREADS) G.residual[base + i] = DBL_MAX;   // S5:296
+    __syncthreads();
+
+    // ---- S5:465-474: aux non-max-suppression on the previous-left points ----------------------------
+    const unsigned cell = (unsigned)(p.min_distance / 2.0);
+    if (assume_fast_kps && cell == 1) {
+        // keypoints produced by stage 2 are distinct and never 8-adjacent: with 1-px cells all survive
+        for (int i = tid; i < T; i += GN_THREADS) G.mask[base + i] = 1;
+    } else {
+        uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_dyn);
+        float* s_key = reinterpret_cast<float*>(s_dyn) + cap;
+        for (int i = tid; i < T; i += GN_THREADS) { s_idx[i] = i; s_key[i] = G.prev[base + i].w; G.mask[base + i] = 0; }
+        __syncthreads();
+        if (tid == 0) {
+            IndexedDescComp c{s_key};
+            if (p.sort_mode == 0) introsort_seq_c(c, s_idx, T);
+            else insertion_sort_(c, s_idx, 0, T);
+            const float cell_inv = 1.0f / (float)cell;
+            const unsigned glx = (unsigned)(1 + p.W * cell_inv), gly = (unsigned)(1 + p.H * cell_inv);
+            uint32_t* occ = G.occ + (size_t)slot * G.occ_words;
+            for (unsigned i = 0; i < (glx * gly + 31) / 32; ++i) occ[i] = 0;
+            auto get = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; return (occ[b >> 5] >> (b & 31)) & 1u; };
+            auto set = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; occ[b >> 5] |= 1u << (b & 31); };
+            int c_feats = 0, k = 0;
+            while (c_feats < T && k < T) {
+                const uint32_t idx = s_idx[k++];
+                const float4 pp = G.prev[base + idx];
+                const unsigned sx = (unsigned)(pp.x * cell_inv), sy = (unsigned)(pp.y * cell_inv);
+                if (sx >= glx || sy >= gly) continue;   // outside the image: the reference would index out of bounds
+                if (get(sx, sy)) continue;
+                set(sx, sy);
+                if (sx > 0) set(sx - 1, sy);
+                if (sy > 0) set(sx, sy - 1);
+                if (sx < glx - 1) set(sx + 1, sy);
+                if (sy < gly - 1) set(sx, sy + 1);
+                G.mask[base + idx] = 1;
+                ++c_feats;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- initial pose (S5:500-507) ------------------------------------------------------------------
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) {
+            double v = 0;
+            if (use_custom_pose) v = G.ini_pose[(size_t)slot * 6 + i];
+            else if (p.use_prev_pose) v = st.last_pose[i];
+            sh.pose[i] = v;
+        }
+        sh.cCost = 0; sh.pCost = 0; sh.done = 0; sh.abort = 0; sh.fail = 0; sh.timesInc = 0;
+        res.n_outliers = 0;
+        res.n_residuals = 0;
+    }
+    __syncthreads();
+
+    int n_non_masked = triangulate(G, base, T, cam, s_cnt);
+    if (n_non_masked < 8) {   // S5:521-526
+        if (tid == 0) { res.valid = 0; res.n_residuals = 0; }
+        return;
+    }
+
+    // ---- first loop (S5:549-598) --------------------------------------------------------------------
+    int num_it = 0;
+    while (num_it < p.initial_max_iters && !sh.done && !sh.abort) {
+        if (tid == 0) sh.pCost = sh.cCost;
+        __syncthreads();
+        eval_rgn(G, base, T, cam, p, sh);
+        if (tid == 0) res.error_code = sh.fail ? 1 : 0;   // S5:564: result.error_code = out_error_code
+        if (sh.fail) {
+            if (tid == 0) { st.m_error = 1; res.valid = 0; res.num_it = num_it; }   // S5:384, S5:569-573
+            return;
+        }
+        if (tid == 0) {
+            double m = 0;
+            for (int k = 0; k < 6; ++k) { sh.pose[k] += sh.step[k]; m += sh.step[k] * sh.step[k]; }
+            if (num_it > 0) {
+                sh.done = sqrt(m) < p.min_mod_out_vector;
+                if (sh.pCost < sh.cCost) {
+                    if (++sh.timesInc > (unsigned)p.max_incr_cost) { res.error_code = 2; sh.abort = 1; }
+                }
+            }
+        }
+        ++num_it;
+        __syncthreads();
+    }
+    if (tid == 0) res.num_it = num_it;
+
+    // ---- S5:601-611: inliers; result.outliers receives their current-match indices ------------------
+    {
+        int basec = 0;
+        int32_t* outl = P.outliers + base;
+        for (int i0 = 0; i0 < T; i0 += GN_THREADS) {
+            const int i = i0 + tid;
+            int in = 0;
+            if (i < T) {
+                if (G.residual[base + i] > p.residual_threshold) G.mask[base + i] = 0;
+                else in = 1;
+            }
+            // block exclusive scan of `in`
+            const int lane = tid & 31, wid = tid >> 5;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (lane == 0) s_cnt[wid] = __popc(bal);
+            __syncthreads();
+            int woff = 0, tot = 0;
+            for (int w = 0; w < GN_THREADS / 32; ++w) { if (w < wid) woff += s_cnt[w]; tot += s_cnt[w]; }
+            if (in) outl[basec + woff + __popc(bal & ((1u << lane) - 1))] = external ? G.cur_idx[base + i] : P.tracked[base + i].y;
+            basec += tot;
+            __syncthreads();
+        }
+        if (tid == 0) res.n_outliers = basec;
+    }
+    __syncthreads();
+    n_non_masked = triangulate(G, base, T, cam, s_cnt);
+    if (n_non_masked < 8) {   // S5:616-621
+        if (tid == 0) { res.valid = 0; res.n_residuals = T; }
+        return;
+    }
+
+    // ---- refinement loop (S5:650-700) ----------------------------------------------------------------
+    if (tid == 0) { sh.done = 0; sh.abort = 0; }
+    __syncthreads();
+    int num_it_final = 0;
+    while (num_it_final < p.max_iters && !sh.done && !sh.abort) {
+        if (tid == 0) sh.pCost = sh.cCost;
+        __syncthreads();
+        eval_rgn(G, base, T, cam, p, sh);
+        if (sh.fail) {   // S5:670-675 (result.error_code is not touched here; m_error is, S5:384)
+            if (tid == 0) { st.m_error = 1; res.valid = 0; res.n_residuals = T; res.num_it_final = num_it_final; }
+            return;
+        }
+        if (tid == 0) {
+            double m = 0;
+            for (int k = 0; k < 6; ++k) { sh.pose[k] += sh.step[k]; m += sh.step[k] * sh.step[k]; }
+            if (num_it_final > 0) {
+                sh.done = sqrt(m) < p.min_mod_out_vector;
+                if (sh.pCost < sh.cCost) {
+                    if (++sh.timesInc > (unsigned)p.max_incr_cost) { sh.abort = 1; res.error_code = 3; }
+                }
+            }
+        }
+        ++num_it_final;
+        __syncthreads();
+    }
+
+    // ---- S5:715-727: outPose = CPose3D( CPose3DRotVec(deltaPose).getInverse() ) ----------------------
+    if (tid == 0) {
+        res.num_it_final = num_it_final;
+        double dp[6], Rm[3][3], Ri[3][3];
+        for (int k = 0; k < 6; ++k) { dp[k] = sh.pose[k]; res.delta_pose[k] = dp[k]; }
+        rodrigues(dp, Rm);
+        for (int i = 0; i < 3; ++i) {
+            res.out_pose_rotvec[i] = -dp[i];
+            res.out_pose_t[i] = -(Rm[0][i] * dp[3] + Rm[1][i] * dp[4] + Rm[2][i] * dp[5]);
+        }
+        rodrigues(res.out_pose_rotvec, Ri);
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) res.out_pose[4 * i + j] = Ri[i][j];
+            res.out_pose[4 * i + 3] = res.out_pose_t[i];
+        }
+        res.out_pose[12] = res.out_pose[13] = res.out_pose[14] = 0;
+        res.out_pose[15] = 1;
+        res.out_pose_ypr[1] = atan2(-Ri[2][0], hypot(Ri[0][0], Ri[1][0]));
+        res.out_pose_ypr[0] = atan2(Ri[1][0], Ri[0][0]);
+        res.out_pose_ypr[2] = atan2(Ri[2][1], Ri[2][2]);
+        if (!use_custom_pose && p.use_prev_pose)
+            for (int k = 0; k < 6; ++k) st.last_pose[k] = dp[k];   // S5:720-721
+        res.n_residuals = T;
+        res.valid = sh.abort ? 0 : 1;   // S5:727
+    }
+}
+
+cudaError_t configure_gn(const Params& p) {
+    return cudaFuncSetAttribute(gn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * 8));
+}
+
+cudaError_t launch_gn(const Pools& P, const GnScratch& G, int n, int external, int use_custom_pose,
+                      int assume_fast_kps, cudaStream_t st, int* launches) {
+    gn_kernel<<<n, GN_THREADS, P.p.kp_cap * 8, st>>>(P, G, external, use_custom_pose, assume_fast_kps);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace svo

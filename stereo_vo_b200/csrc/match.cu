@@ -1,0 +1,386 @@
+// match.cu -- stages 3 and 4 of the hot path on sm_100a: brute-force 256-bit Hamming matching,
+// the left/right filter, the greedy inter-frame filter and the consistency check.  Replaces
+//   cv::BFMatcher(NORM_HAMMING,false).match      stage3_match_left_right.cpp:88-94,
+//                                                stage4_match_consecutive.cpp:137-142
+//   1-to-1 + epipolar/threshold/disparity filter stage3_match_left_right.cpp:124-175
+//   descriptor gather                            stage4_match_consecutive.cpp:97-131
+//   greedy distance/collision filter             stage4_match_consecutive.cpp:145-160
+//   F-matrix mask application + consistency + ID management   stage4_match_consecutive.cpp:243-305
+//   tracking statistics and the bad-tracking gate             stage4_match_consecutive.cpp:743-752,
+//                                                             process_new_image_pair.cpp:326-330
+#include "match.cuh"
+
+namespace svo {
+
+// ------------------------------------------------------------------------------------------------
+// K4  hamming_kernel: for every query row the packed minimum (distance << 16 | trainIdx) over all
+// train rows, i.e. smallest distance, lowest index among ties -- BFMatcher's rule.
+//   CTA = 128 threads, QPT queries per thread held in registers (8 words each); the train set streams
+//   through shared memory in tiles of TILE rows (32 B each, read as two broadcast LDS.128).
+// Roofline: 8 XOR + 8 POPC per pair-distance; the POPC pipe (16 lanes/clk/SM) binds, HBM traffic is
+// 32 B per descriptor once (L2 serves the re-reads of the train tile by the other CTAs).
+// ------------------------------------------------------------------------------------------------
+constexpr int HM_THREADS = 128;
+constexpr int HM_QPT = 2;
+constexpr int HM_TILE = 512;   // train rows per shared-memory tile (16 KB)
+
+struct HammingProblem {
+    const uint4* q; const uint4* t; uint32_t* out; int nq, nt;
+};
+
+__device__ __forceinline__ HammingProblem pipeline_problem(const Pools& P, int mode, int item) {
+    HammingProblem h;
+    const int slot = P.slots[item];
+    const SlotState& s = P.state[slot];
+    const int cur = s.cur, prev = cur ^ 1;
+    const size_t cap = (size_t)P.p.kp_cap;
+    if (mode == 0) {          // left -> right of the current frame (S3:91-94)
+        h.q = P.desc + frame_idx(slot, cur, 0) * cap * 2;
+        h.t = P.desc + frame_idx(slot, cur, 1) * cap * 2;
+        h.nq = P.n_kp[frame_idx(slot, cur, 0)];
+        h.nt = P.n_kp[frame_idx(slot, cur, 1)];
+        h.out = P.lr_best + (size_t)slot * cap;
+    } else {                  // prev -> cur, mode 1 = left-left, 2 = right-right (S4:141-142)
+        const int side = mode - 1;
+        h.q = P.mdesc + frame_idx(slot, prev, side) * cap * 2;
+        h.t = P.mdesc + frame_idx(slot, cur, side) * cap * 2;
+        h.nq = s.has_prev ? P.n_match[pair_idx(slot, prev)] : 0;
+        h.nt = P.n_match[pair_idx(slot, cur)];
+        h.out = P.tr_best + ((size_t)slot * 2 + side) * cap;
+    }
+    return h;
+}
+
+__device__ __forceinline__ void hamming_body(const HammingProblem& h, uint4* s_t) {
+    const int tid = threadIdx.x;
+    const int q0 = blockIdx.x * (HM_THREADS * HM_QPT);
+    if (q0 >= h.nq) return;
+    uint4 qa[HM_QPT], qb[HM_QPT];
+    uint32_t best[HM_QPT];
+#pragma unroll
+    for (int r = 0; r < HM_QPT; ++r) {
+        const int qi = q0 + r * HM_THREADS + tid;
+        best[r] = 0xFFFFFFFFu;
+        if (qi < h.nq) { qa[r] = h.q[2 * (size_t)qi]; qb[r] = h.q[2 * (size_t)qi + 1]; }
+        else { qa[r] = make_uint4(0, 0, 0, 0); qb[r] = qa[r]; }
+    }
+    for (int t0 = 0; t0 < h.nt; t0 += HM_TILE) {
+        const int rows = min(HM_TILE, h.nt - t0);
+        __syncthreads();
+        for (int i = tid; i < rows * 2; i += HM_THREADS) s_t[i] = h.t[2 * (size_t)t0 + i];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < rows; ++j) {
+            const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
+#pragma unroll
+            for (int r = 0; r < HM_QPT; ++r) {
+                const int d = __popc(qa[r].x ^ ta.x) + __popc(qa[r].y ^ ta.y) + __popc(qa[r].z ^ ta.z) + __popc(qa[r].w ^ ta.w) +
+                              __popc(qb[r].x ^ tb.x) + __popc(qb[r].y ^ tb.y) + __popc(qb[r].z ^ tb.z) + __popc(qb[r].w ^ tb.w);
+                best[r] = min(best[r], ((uint32_t)d << 16) | (uint32_t)(t0 + j));
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < HM_QPT; ++r) {
+        const int qi = q0 + r * HM_THREADS + tid;
+        if (qi < h.nq) h.out[qi] = best[r];
+    }
+}
+
+__global__ void __launch_bounds__(HM_THREADS)
+hamming_pipeline_kernel(Pools P, int mode_base, int n_modes) {
+    __shared__ uint4 s_t[HM_TILE * 2];
+    const int item = blockIdx.y / n_modes, mode = mode_base + blockIdx.y % n_modes;
+    const HammingProblem h = pipeline_problem(P, mode, item);
+    hamming_body(h, s_t);
+}
+
+__global__ void __launch_bounds__(HM_THREADS)
+hamming_raw_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, uint32_t* __restrict__ out) {
+    __shared__ uint4 s_t[HM_TILE * 2];
+    HammingProblem h;
+    h.q = q + (size_t)blockIdx.y * nq * 2;
+    h.t = t + (size_t)blockIdx.y * nt * 2;
+    h.out = out + (size_t)blockIdx.y * nq;
+    h.nq = nq; h.nt = nt;
+    hamming_body(h, s_t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide exclusive scan helper (256 threads)
+// ------------------------------------------------------------------------------------------------
+constexpr int FT = 256;
+__device__ __forceinline__ int scan256(int v, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int wsum = (lane < FT / 32) ? s_warp[lane] : 0;
+    int wincl = wsum;
+#pragma unroll
+    for (int o = 1; o < FT / 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += t;
+    }
+    const int wexcl = __shfl_sync(0xffffffffu, wincl - wsum, wid);
+    total = __shfl_sync(0xffffffffu, wincl, FT / 32 - 1);
+    __syncthreads();
+    return wexcl + incl - v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  lr_filter_kernel: one CTA per slot.  S3:124-175 + descriptor gather of S4:105-131.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT)
+lr_filter_kernel(Pools P) {
+    extern __shared__ uint32_t s_rc[];   // right_cand: (distance<<16 | queryIdx) per right keypoint
+    __shared__ int s_warp[FT / 32];
+    const int slot = P.slots[blockIdx.x];
+    SlotState& st = P.state[slot];
+    const int cur = st.cur;
+    const size_t cap = (size_t)P.p.kp_cap;
+    const size_t fL = frame_idx(slot, cur, 0), fR = frame_idx(slot, cur, 1);
+    const int nL = P.n_kp[fL], nR = P.n_kp[fR];
+    const uint32_t* __restrict__ best = P.lr_best + (size_t)slot * cap;
+    const int2* __restrict__ kpL = P.kp + fL * cap;
+    const int2* __restrict__ kpR = P.kp + fR * cap;
+    const int tid = threadIdx.x;
+    const int n_in = (nR > 0) ? nL : 0;   // BFMatcher returns no matches for an empty train set
+
+    if (P.p.robust_1to1) {   // S3:124-148: per right keypoint the left one with the smallest distance
+        for (int i = tid; i < nR; i += FT) s_rc[i] = 0xFFFFFFFFu;
+        __syncthreads();
+        for (int k = tid; k < n_in; k += FT) {
+            const uint32_t b = best[k];
+            atomicMin(&s_rc[b & 0xFFFFu], (b & 0xFFFF0000u) | (uint32_t)k);  // strict '>' in the reference: first k wins ties
+        }
+        __syncthreads();
+    }
+    int4* __restrict__ mout = P.match + pair_idx(slot, cur) * cap;
+    uint4* __restrict__ mdL = P.mdesc + frame_idx(slot, cur, 0) * cap * 2;
+    uint4* __restrict__ mdR = P.mdesc + frame_idx(slot, cur, 1) * cap * 2;
+    const uint4* __restrict__ dL = P.desc + fL * cap * 2;
+    const uint4* __restrict__ dR = P.desc + fR * cap * 2;
+    int base = 0;
+    for (int k0 = 0; k0 < n_in; k0 += FT) {
+        const int k = k0 + tid;
+        int keep = 0, t = 0, dist = 0;
+        if (k < n_in) {
+            const uint32_t b = best[k];
+            t = (int)(b & 0xFFFFu);
+            dist = (int)(b >> 16);
+            keep = 1;
+            if (P.p.robust_1to1 && (int)(s_rc[t] & 0xFFFFu) != k) keep = 0;
+            const int2 l = kpL[k], r = kpR[t];
+            // S3:162-165: float differences truncated to int (coordinates are integers here)
+            const int diff = (int)((float)((unsigned)l.x >> 16) - (float)((unsigned)r.x >> 16));
+            const int disp = (int)((float)(l.x & 0xFFFF) - (float)(r.x & 0xFFFF));
+            if ((double)abs(diff) > P.p.max_y_diff || (float)dist > (float)P.p.orb_th ||
+                (double)disp < 1.0 || (double)disp > (double)P.p.W) keep = 0;
+        }
+        int total;
+        const int off = scan256(keep, s_warp, total);
+        if (keep) {
+            const int m = base + off;
+            mout[m] = make_int4(k, t, dist, 0);
+            mdL[2 * m] = dL[2 * k]; mdL[2 * m + 1] = dL[2 * k + 1];
+            mdR[2 * m] = dR[2 * t]; mdR[2 * m + 1] = dR[2 * t + 1];
+        }
+        base += total;
+    }
+    if (tid == 0) {
+        P.n_match[pair_idx(slot, cur)] = base;
+        P.result[slot].stereo_matches = base;
+    }
+    // S3:67,172-173: on the first frame every kept match receives a fresh ID
+    if (P.p.use_ids && !st.has_prev) {
+        long long* ids = P.match_id + pair_idx(slot, cur) * cap;
+        const long long b0 = st.last_match_id;
+        for (int m = tid; m < base; m += FT) ids[m] = b0 + m;
+        __syncthreads();
+        if (tid == 0) st.last_match_id = b0 + base;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7  track_filter_kernel: one warp per slot; the filter is order dependent (a pair only claims its
+// train indices if it is itself kept), so lane 0 walks the list while the warp stages the inputs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+track_filter_kernel(Pools P) {
+    extern __shared__ uint32_t s_mem[];   // [2*cap] packed best + [2*ceil(cap/32)] bitmaps
+    const int slot = P.slots[blockIdx.x];
+    const SlotState& st = P.state[slot];
+    const int cur = st.cur, prev = cur ^ 1;
+    const int cap = P.p.kp_cap;
+    const int lane = threadIdx.x;
+    const int Mp = st.has_prev ? P.n_match[pair_idx(slot, prev)] : 0;
+    const int Mc = P.n_match[pair_idx(slot, cur)];
+    const int n_in = (Mc > 0) ? Mp : 0;
+    uint32_t* s_l = s_mem;
+    uint32_t* s_r = s_mem + cap;
+    uint32_t* bmL = s_mem + 2 * cap;
+    const int bw = (cap + 31) / 32;
+    uint32_t* bmR = bmL + bw;
+    const uint32_t* __restrict__ bl = P.tr_best + ((size_t)slot * 2 + 0) * cap;
+    const uint32_t* __restrict__ br = P.tr_best + ((size_t)slot * 2 + 1) * cap;
+    for (int i = lane; i < n_in; i += 32) { s_l[i] = bl[i]; s_r[i] = br[i]; }
+    for (int i = lane; i < 2 * bw; i += 32) bmL[i] = 0;
+    __syncwarp();
+    int4* __restrict__ out = P.tcand + (size_t)slot * cap;
+    if (lane == 0) {
+        int m = 0;
+        const uint32_t th = (uint32_t)P.p.orb_th;
+        for (int k = 0; k < n_in; ++k) {
+            const uint32_t a = s_l[k], b = s_r[k];
+            const uint32_t tl = a & 0xFFFFu, tr = b & 0xFFFFu;
+            if ((a >> 16) > th || (b >> 16) > th) continue;
+            if (((bmL[tl >> 5] >> (tl & 31)) & 1u) || ((bmR[tr >> 5] >> (tr & 31)) & 1u)) continue;
+            bmL[tl >> 5] |= 1u << (tl & 31);
+            bmR[tr >> 5] |= 1u << (tr & 31);
+            out[m++] = make_int4(k, (int)tl, (int)tr, 0);
+        }
+        P.n_tcand[slot] = m;
+        // masks default to "not computed": zero inliers => filter skipped (S4:243-259)
+        P.n_inl[slot * 2 + 0] = 0;
+        P.n_inl[slot * 2 + 1] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9  consistency_kernel: one CTA per slot.  S4:243-305, S4:743-752, P:326-330, P:348-352.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT)
+consistency_kernel(Pools P) {
+    __shared__ int s_warp[FT / 32];
+    extern __shared__ uint32_t s_tr[];   // tracked flag per current match (ID management)
+    const int slot = P.slots[blockIdx.x];
+    SlotState& st = P.state[slot];
+    Result& res = P.result[slot];
+    const int cur = st.cur, prev = cur ^ 1;
+    const size_t cap = (size_t)P.p.kp_cap;
+    const int tid = threadIdx.x;
+    if (!st.has_prev) {                      // first iteration (P:348-352)
+        if (tid == 0) { res.error_code = 4; res.valid = 0; P.n_tracked[slot] = 0; }
+        return;
+    }
+    const int n = P.n_tcand[slot];
+    const int4* __restrict__ tc = P.tcand + (size_t)slot * cap;
+    const uint8_t* __restrict__ inlL = P.inl + ((size_t)slot * 2 + 0) * cap;
+    const uint8_t* __restrict__ inlR = P.inl + ((size_t)slot * 2 + 1) * cap;
+    const bool use_masks = P.p.fundmat_filter && P.n_inl[slot * 2] >= 8 && P.n_inl[slot * 2 + 1] >= 8;  // S4:205,240,243
+    int2* __restrict__ out = P.tracked + (size_t)slot * cap;
+    const int Mc = P.n_match[pair_idx(slot, cur)];
+    const bool ids = P.p.use_ids != 0;
+    long long* idc = P.match_id + pair_idx(slot, cur) * cap;
+    const long long* idp = P.match_id + pair_idx(slot, prev) * cap;
+    if (ids) {
+        for (int i = tid; i < Mc; i += FT) s_tr[i] = 0;
+        __syncthreads();
+    }
+    int base = 0;
+    for (int k0 = 0; k0 < n; k0 += FT) {
+        const int k = k0 + tid;
+        int keep = 0;
+        int4 c = make_int4(0, 0, 0, 0);
+        if (k < n) {
+            c = tc[k];
+            keep = 1;
+            if (use_masks && (inlL[k] == 0 || inlR[k] == 0)) keep = 0;
+            if (c.y != c.z) keep = 0;        // S4:282 (the query indices are equal by construction)
+        }
+        int total;
+        const int off = scan256(keep, s_warp, total);
+        if (keep) {
+            out[base + off] = make_int2(c.x, c.y);
+            if (ids) { idc[c.y] = idp[c.x]; s_tr[c.y] = 1; }   // S4:288-292
+        }
+        base += total;
+    }
+    __syncthreads();
+    int kf = 0;
+    if (ids) {
+        // S4:300-305: untracked current matches get new IDs in index order
+        long long b0 = st.last_match_id;
+        int nb = 0;
+        for (int k0 = 0; k0 < Mc; k0 += FT) {
+            const int k = k0 + tid;
+            const int fresh = (k < Mc && !s_tr[k]) ? 1 : 0;
+            int total;
+            const int off = scan256(fresh, s_warp, total);
+            if (fresh) idc[k] = b0 + nb + off;
+            nb += total;
+        }
+        __syncthreads();
+        // S4:747-751
+        int cnt = 0;
+        for (int k = tid; k < Mc; k += FT) cnt += (idc[k] <= st.last_kf_max_id) ? 1 : 0;
+        int total;
+        scan256(cnt, s_warp, total);
+        kf = total;
+        if (tid == 0) st.last_match_id = b0 + nb;
+    }
+    if (tid == 0) {
+        P.n_tracked[slot] = base;
+        res.tracked_frame = base;
+        res.tracked_kf = kf;
+        if (base < P.p.bad_tracking_th) {    // P:326-330
+            st.m_error = 5;
+            res.error_code = 5;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_match_lr(const Pools& P, int n, cudaStream_t st, int* launches) {
+    const int per = HM_THREADS * HM_QPT;
+    dim3 g((P.p.kp_cap + per - 1) / per, n);
+    hamming_pipeline_kernel<<<g, HM_THREADS, 0, st>>>(P, 0, 1);
+    lr_filter_kernel<<<n, FT, P.p.kp_cap * sizeof(uint32_t), st>>>(P);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_track_match(const Pools& P, int n, cudaStream_t st, int* launches) {
+    const int per = HM_THREADS * HM_QPT;
+    dim3 g((P.p.kp_cap + per - 1) / per, 2 * n);
+    hamming_pipeline_kernel<<<g, HM_THREADS, 0, st>>>(P, 1, 2);
+    const int bw = (P.p.kp_cap + 31) / 32;
+    track_filter_kernel<<<n, 32, (2 * P.p.kp_cap + 2 * bw) * sizeof(uint32_t), st>>>(P);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_consistency(const Pools& P, int n, cudaStream_t st, int* launches) {
+    consistency_kernel<<<n, FT, P.p.kp_cap * sizeof(uint32_t), st>>>(P);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hamming_raw(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int reps, uint32_t* d_out,
+                               cudaStream_t st) {
+    if (nq <= 0 || reps <= 0) return cudaSuccess;
+    const int per = HM_THREADS * HM_QPT;
+    dim3 g((nq + per - 1) / per, reps);
+    hamming_raw_kernel<<<g, HM_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(d_q), nq,
+                                                  reinterpret_cast<const uint4*>(d_t), nt, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t configure_match(const Params& p) {
+    cudaError_t e = cudaFuncSetAttribute(track_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((2 * p.kp_cap + 2 * ((p.kp_cap + 31) / 32)) * sizeof(uint32_t)));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lr_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * sizeof(uint32_t)));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(consistency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * sizeof(uint32_t)));
+}
+
+}  // namespace svo

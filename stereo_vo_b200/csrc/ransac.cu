@@ -1,0 +1,246 @@
+// ransac.cu -- the two cv::findFundamentalMat(p1, p2, FM_RANSAC, 1.0, 0.99, mask) calls of
+// stage4_match_consecutive.cpp:171-241 on sm_100a, one CTA per (stereo pair, side).
+//
+// OpenCV's estimator is sequential (adaptive iteration count, one RNG stream), but iteration k's
+// sample does not depend on the models of earlier iterations: thread 0 draws the next 8 samples
+// from the exact cv::RNG stream (including the duplicate and collinearity re-draws), the 8 warps solve
+// and score them concurrently, and thread 0 then replays OpenCV's "best so far / update niters" logic in
+// iteration order.  The result is the inlier mask OpenCV returns (see fundmat_core.cuh for the one
+// floating-point caveat).  With >= 15 points this is RANSAC, with 8..14 LMedS, with 7 an all-ones mask
+// and with < 7 no mask (zero inliers), as in cv::findFundamentalMat.
+#include "fundmat_core.cuh"
+#include "ransac.cuh"
+
+namespace svo {
+
+constexpr int RS_WARPS = 8;
+constexpr int RS_THREADS = RS_WARPS * 32;
+
+struct RsShared {
+    CvRng rng;
+    double F[RS_WARPS][27];
+    double best[9];
+    double minMedian;
+    Pt2f ms1[RS_WARPS][7], ms2[RS_WARPS][7];
+    int found[RS_WARPS];
+    int nmodels[RS_WARPS];
+    int good[RS_WARPS][3];
+    float median[RS_WARPS][3];
+    int iter_base, niters, maxGood, stop, have_model;
+    int wsum[RS_WARPS];
+};
+
+// S4:181-232: point sets of the left-left and right-right problems from the greedy-filtered lists
+__global__ void __launch_bounds__(256)
+ransac_prepare_kernel(Pools P, RansacScratch R) {
+    const int slot = P.slots[blockIdx.x];
+    const SlotState& st = P.state[slot];
+    const size_t cap = (size_t)P.p.kp_cap;
+    const int n = st.has_prev ? P.n_tcand[slot] : 0;
+    const int cur = st.cur, prev = cur ^ 1;
+    const int4* __restrict__ tc = P.tcand + (size_t)slot * cap;
+    const int4* __restrict__ mp = P.match + pair_idx(slot, prev) * cap;
+    const int4* __restrict__ mc = P.match + pair_idx(slot, cur) * cap;
+    for (int side = 0; side < 2; ++side) {
+        const int2* __restrict__ kp = P.kp + frame_idx(slot, prev, side) * cap;
+        const int2* __restrict__ kc = P.kp + frame_idx(slot, cur, side) * cap;
+        float2* __restrict__ o1 = R.p1 + ((size_t)slot * 2 + side) * cap;
+        float2* __restrict__ o2 = R.p2 + ((size_t)slot * 2 + side) * cap;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const int4 c = tc[k];
+            const int4 a = mp[c.x], b = mc[side ? c.z : c.y];
+            const int2 p = kp[side ? a.y : a.x], q = kc[side ? b.y : b.x];
+            o1[k] = make_float2((float)(p.x & 0xFFFF), (float)((unsigned)p.x >> 16));
+            o2[k] = make_float2((float)(q.x & 0xFFFF), (float)((unsigned)q.x >> 16));
+        }
+        if (threadIdx.x == 0) R.n_pts[slot * 2 + side] = n;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+fundmat_kernel(RansacScratch R) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ RsShared sh;
+    const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
+    const int slot = R.slots[item];
+    const size_t prob = (size_t)slot * 2 + side;
+    const int n = R.n_pts[prob];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    Pt2f* m1 = reinterpret_cast<Pt2f*>(s_dyn);
+    Pt2f* m2 = m1 + R.kp_cap;
+    uint8_t* __restrict__ mask = R.inl + prob * R.kp_cap;
+    const float2* __restrict__ g1 = R.p1 + prob * R.kp_cap;
+    const float2* __restrict__ g2 = R.p2 + prob * R.kp_cap;
+
+    if (n < 7) {                       // findFundamentalMat returns an empty Mat and no mask
+        if (tid == 0) R.n_inl[prob] = 0;
+        return;
+    }
+    if (n == 7) {                      // mask.setTo(1)
+        if (tid < 7) mask[tid] = 1;
+        if (tid == 0) R.n_inl[prob] = 7;
+        return;
+    }
+    for (int i = tid; i < n; i += RS_THREADS) {
+        const float2 a = g1[i], b = g2[i];
+        m1[i].x = a.x; m1[i].y = a.y; m2[i].x = b.x; m2[i].y = b.y;
+    }
+    const bool lmeds = n < 15;
+    if (tid == 0) {
+        sh.rng.seed();
+        sh.iter_base = 0;
+        sh.maxGood = 0;
+        sh.stop = 0;
+        sh.have_model = 0;
+        sh.minMedian = DBL_MAX;
+        if (lmeds) { const int it = ransac_update_num_iters(kFmConfidence, 0.45, kFmModelPoints, kFmMaxIters); sh.niters = it > 3 ? it : 3; }
+        else sh.niters = kFmMaxIters;
+    }
+    __syncthreads();
+    const float thr = (float)(kFmThreshold * kFmThreshold);
+
+    while (!sh.stop) {
+        // ---- thread 0: the next RS_WARPS samples from the cv::RNG stream ------------------------------
+        if (tid == 0) {
+            for (int w = 0; w < RS_WARPS; ++w) {
+                sh.found[w] = -1;   // not needed
+                if (sh.iter_base + w >= sh.niters) break;
+                int idx[7];
+                const bool ok = get_subset7(m1, m2, n, sh.rng, lmeds ? 1000 : 10000, idx, sh.ms1[w], sh.ms2[w]);
+                sh.found[w] = ok ? 1 : 0;
+                if (!ok) break;
+            }
+        }
+        __syncthreads();
+        // ---- every warp: solve and score its sample -------------------------------------------------
+        if (sh.found[wid] == 1) {
+            if (lane == 0) sh.nmodels[wid] = run_7point(sh.ms1[wid], sh.ms2[wid], sh.F[wid]);
+            __syncwarp();
+            const int nm = sh.nmodels[wid];
+            for (int i = 0; i < nm; ++i) {
+                const double* F = sh.F[wid] + 9 * i;
+                if (!lmeds) {
+                    int good = 0;
+                    for (int k = lane; k < n; k += 32) good += fm_error(F, m1[k], m2[k]) <= thr ? 1 : 0;
+                    for (int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(0xffffffffu, good, o);
+                    if (lane == 0) sh.good[wid][i] = good;
+                } else if (lane == 0) {
+                    float e[14];
+                    for (int k = 0; k < n; ++k) {   // n <= 14: insertion sort, element n/2 is nth_element's answer
+                        const float v = fm_error(F, m1[k], m2[k]);
+                        int j = k;
+                        while (j > 0 && e[j - 1] > v) { e[j] = e[j - 1]; --j; }
+                        e[j] = v;
+                    }
+                    sh.median[wid][i] = e[n / 2];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- thread 0: OpenCV's sequential bookkeeping, in iteration order ------------------------------
+        if (tid == 0) {
+            for (int w = 0; w < RS_WARPS; ++w) {
+                const int iter = sh.iter_base + w;
+                if (iter >= sh.niters) { sh.stop = 1; break; }
+                if (sh.found[w] != 1) { sh.stop = 1; break; }   // getSubset failed: return false (iter 0) or break
+                const int nm = sh.nmodels[w];
+                for (int i = 0; i < nm; ++i) {
+                    if (!lmeds) {
+                        const int good = sh.good[w][i];
+                        if (good > max(sh.maxGood, kFmModelPoints - 1)) {
+                            sh.maxGood = good;
+                            for (int q = 0; q < 9; ++q) sh.best[q] = sh.F[w][9 * i + q];
+                            sh.have_model = 1;
+                            sh.niters = ransac_update_num_iters(kFmConfidence, (double)(n - good) / n, kFmModelPoints, sh.niters);
+                        }
+                    } else {
+                        const double med = (double)sh.median[w][i];
+                        if (med < sh.minMedian) {
+                            sh.minMedian = med;
+                            for (int q = 0; q < 9; ++q) sh.best[q] = sh.F[w][9 * i + q];
+                            sh.have_model = 1;
+                        }
+                    }
+                }
+            }
+            sh.iter_base += RS_WARPS;
+            if (sh.iter_base >= sh.niters) sh.stop = 1;
+        }
+        __syncthreads();
+    }
+    // ---- final mask -------------------------------------------------------------------------------------
+    float t = thr;
+    if (lmeds) {
+        double sigma = 2.5 * 1.4826 * (1 + 5. / (n - kFmModelPoints)) * sqrt(sh.minMedian);
+        sigma = fmax(sigma, 0.001);
+        t = (float)(sigma * sigma);
+    }
+    int cnt = 0;
+    for (int k = tid; k < n; k += RS_THREADS) {
+        const int in = sh.have_model ? (fm_error(sh.best, m1[k], m2[k]) <= t ? 1 : 0) : 0;
+        mask[k] = (uint8_t)in;
+        cnt += in;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) sh.wsum[wid] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < RS_WARPS; ++w) tot += sh.wsum[w];
+        R.n_inl[prob] = tot;
+    }
+}
+
+cudaError_t alloc_ransac(RansacScratch& R, int n_slots, int kp_cap, std::vector<void*>& allocs) {
+    R.kp_cap = kp_cap;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)n_slots * 2 * kp_cap * sizeof(float2));
+    if (e != cudaSuccess) return e;
+    allocs.push_back(p); R.p1 = (float2*)p;
+    e = cudaMalloc(&p, (size_t)n_slots * 2 * kp_cap * sizeof(float2));
+    if (e != cudaSuccess) return e;
+    allocs.push_back(p); R.p2 = (float2*)p;
+    e = cudaMalloc(&p, (size_t)n_slots * 2 * sizeof(int32_t));
+    if (e != cudaSuccess) return e;
+    allocs.push_back(p); R.n_pts = (int32_t*)p;
+    return cudaMemset(R.n_pts, 0, (size_t)n_slots * 2 * sizeof(int32_t));
+}
+
+static int ransac_smem(int kp_cap) { return 2 * kp_cap * (int)sizeof(Pt2f); }
+
+cudaError_t configure_ransac(int kp_cap) {
+    return cudaFuncSetAttribute(fundmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ransac_smem(kp_cap));
+}
+
+cudaError_t launch_ransac(const Pools& P, const RansacScratch& R, int n, cudaStream_t st, int* launches) {
+    ransac_prepare_kernel<<<n, 256, 0, st>>>(P, R);
+    fundmat_kernel<<<2 * n, RS_THREADS, ransac_smem(R.kp_cap), st>>>(R);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t ransac_host_points(const RansacScratch& R, int scratch_slot, const float* p1, const float* p2, int n,
+                               uint8_t* mask, int* n_inliers, cudaStream_t st) {
+    const size_t prob = (size_t)scratch_slot * 2;
+    cudaError_t e = cudaMemcpyAsync(R.slots, &scratch_slot, sizeof(int), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    if (n > 0) {
+        if ((e = cudaMemcpyAsync(R.p1 + prob * R.kp_cap, p1, (size_t)n * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(R.p2 + prob * R.kp_cap, p2, (size_t)n * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    }
+    const int zero = 0;
+    if ((e = cudaMemcpyAsync(R.n_pts + prob, &n, sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(R.n_pts + prob + 1, &zero, sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;   // the host sources above are stack / caller memory
+    fundmat_kernel<<<2, RS_THREADS, ransac_smem(R.kp_cap), st>>>(R);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(n_inliers, R.n_inl + prob, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (n > 0) {
+        if (n < 7) memset(mask, 0, n);
+        else if ((e = cudaMemcpy(mask, R.inl + prob * R.kp_cap, n, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace svo

@@ -1,0 +1,107 @@
+// svo_internal.cuh -- device-side data layout shared by all kernels of the stereo-VO hot path.
+//
+// HBM layout (all arrays are pooled per context, indexed by slot / buffer / side):
+//   slot  s in [0, max_seqs)   one CStereoOdometryEstimator's mutable state
+//   buf   b in {0,1}           ping-pong frame storage: m_current_imgpair / m_prev_imgpair
+//                              (libstereo-odometry.h:829); which one is "current" is SlotState.cur
+//   side  d in {0,1}           left / right image
+// Keypoints are kept as (y<<16|x, score) pairs, descriptors as 32-byte rows (two uint4), matches as
+// int4 {queryIdx, trainIdx, distance, 0}; expansion to cv::KeyPoint / cv::DMatch layout happens only
+// in the C-ABI readers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svo {
+
+constexpr int kOrbEdge = 31;        // cv::ORB edgeThreshold (border filter inside ORB::compute)
+constexpr int kMaxImgDim = 4096;    // x and y are packed in 16 bits each, grid occupancy bitmaps sized from it
+
+struct SlotState {                  // mutable members of the estimator (libstereo-odometry.h:733-754)
+    int32_t cur;                    // buffer index holding m_current_imgpair
+    int32_t has_cur, has_prev;      // m_current_imgpair.present(), m_prev_imgpair.present()
+    int32_t m_error;                // VOErrorCode kept across calls (process_new_image_pair.cpp:86-95)
+    int32_t repeat;                 // request_data.repeat of the step being processed
+    int32_t status;                 // svo_status of the step (capacity overflow ...)
+    uint32_t it_counter;            // m_it_counter
+    int32_t  pad;
+    long long last_match_id;        // m_last_match_ID
+    long long last_kf_max_id;       // m_last_kf_max_id
+    double last_pose[6];            // m_last_computed_pose
+};
+
+struct Camera { double fxl, fyl, cxl, cyl, fxr, fyr, cxr, cyr, baseline; };
+
+struct Params {                     // device copy of svo_config (see include/svo_b200.h)
+    int32_t W, H, max_seqs, max_corners, kp_cap;
+    int32_t quota;                  // kps_to_detect[0] = 2*orb_nfeats for nOctaves == 1 (stage2_detect.cpp:405)
+    int32_t fast_th, nms, min_distance;
+    double  max_y_diff;
+    int32_t orb_th, robust_1to1, fundmat_filter;
+    int32_t use_robust_kernel;
+    double  kernel_param;
+    int32_t max_iters, initial_max_iters;
+    double  min_mod_out_vector;
+    int32_t max_incr_cost;
+    double  residual_threshold;
+    int32_t bad_tracking_th, use_prev_pose, use_ids, sort_mode;
+};
+
+// Device result record: same layout as svo_result in include/svo_b200.h (static_assert in capi.cu).
+struct Result {
+    double  out_pose[16];
+    double  out_pose_rotvec[3];
+    double  out_pose_t[3];
+    double  out_pose_ypr[3];
+    double  delta_pose[6];
+    int32_t num_it, num_it_final;
+    int32_t valid;
+    int32_t error_code;
+    int32_t tracked_kf, tracked_frame;
+    int32_t detected_left, detected_right;
+    int32_t stereo_matches;
+    int32_t n_outliers;
+    int32_t n_residuals;
+    int32_t status;
+};
+
+// All device pointers of a context, passed by value to kernels.
+struct Pools {
+    Params p;
+    SlotState* state;      // [max_seqs]
+    Result* result;        // [max_seqs]
+    Camera* cam;           // [max_seqs]
+    // per (slot, side) scratch of one step
+    uint8_t* blur;         // [max_seqs*2][H*W]   7x7 blurred image
+    uint8_t* score;        // [max_seqs*2][H*W]   FAST score after 3x3 NMS and 31-px border filter, 0 = none
+    uint32_t* cand_pos;    // [max_seqs*2][max_corners]  y<<16|x of raw corners in row-major order
+    int32_t* n_cand;       // [max_seqs*2]
+    // per (slot, buf, side) frame data
+    int2* kp;              // [max_seqs*2*2][kp_cap]  {y<<16|x, score}
+    uint4* desc;           // [max_seqs*2*2][kp_cap][2]
+    int32_t* n_kp;         // [max_seqs*2*2]
+    // per (slot, buf) stereo matches
+    int4* match;           // [max_seqs*2][kp_cap]  {queryIdx, trainIdx, distance, 0}
+    int32_t* n_match;      // [max_seqs*2]
+    uint4* mdesc;          // [max_seqs*2*2][kp_cap][2]  descriptor rows gathered per match (S4:105-131)
+    long long* match_id;   // [max_seqs*2][kp_cap]
+    // per slot scratch of one step
+    uint32_t* lr_best;     // [max_seqs][kp_cap]   (distance<<16 | trainIdx) per left keypoint
+    uint32_t* tr_best;     // [max_seqs*2][kp_cap] tracking: side 0 = left-left, 1 = right-right
+    int4* tcand;           // [max_seqs][kp_cap]   after the greedy filter: {queryIdx, trainL, trainR, 0}
+    int32_t* n_tcand;      // [max_seqs]
+    uint8_t* inl;          // [max_seqs*2][kp_cap] RANSAC masks (left-left, right-right)
+    int32_t* n_inl;        // [max_seqs*2]         inlier counts
+    int2* tracked;         // [max_seqs][kp_cap]   {pre_match_idx, cur_match_idx}
+    int32_t* n_tracked;    // [max_seqs]
+    double* residual;      // [max_seqs][kp_cap]
+    int32_t* outliers;     // [max_seqs][kp_cap]
+    // batch description of the running step
+    int32_t* slots;        // [max_seqs] slot index of batch item i
+};
+
+__host__ __device__ inline size_t img_idx(int slot, int side) { return (size_t)slot * 2 + side; }
+__host__ __device__ inline size_t frame_idx(int slot, int buf, int side) { return ((size_t)slot * 2 + buf) * 2 + side; }
+__host__ __device__ inline size_t pair_idx(int slot, int buf) { return (size_t)slot * 2 + buf; }
+
+}  // namespace svo

@@ -1,0 +1,66 @@
+// Host harness (test only): sequential findFundamentalMat(FM_RANSAC, 1.0, 0.99) built from
+// stereo_vo_b200/csrc/fundmat_core.cuh, used to pin that header against cv2 on the CPU.
+// The CUDA kernel (ransac.cu) evaluates the same iterations in parallel batches.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../stereo_vo_b200/csrc/fundmat_core.cuh"
+using namespace svo;
+
+extern "C" int fundmat_host(const float* p1, const float* p2, int n, uint8_t* mask, double* bestF) {
+    const Pt2f* m1 = reinterpret_cast<const Pt2f*>(p1);
+    const Pt2f* m2 = reinterpret_cast<const Pt2f*>(p2);
+    if (n < 7) return -1;                       // findFundamentalMat returns an empty Mat, no mask
+    if (n == 7) { std::memset(mask, 1, 7); return 7; }
+    CvRng rng;
+    rng.seed();
+    int idx[7];
+    Pt2f ms1[7], ms2[7];
+    double F[27], best[9] = {0};
+    if (n >= 15) {   // RANSACPointSetRegistrator::run
+        int niters = kFmMaxIters, maxGood = 0;
+        const float thr = (float)(kFmThreshold * kFmThreshold);
+        for (int iter = 0; iter < niters; ++iter) {
+            if (!get_subset7(m1, m2, n, rng, 10000, idx, ms1, ms2)) { if (iter == 0) return 0; break; }
+            const int nm = run_7point(ms1, ms2, F);
+            for (int i = 0; i < nm; ++i) {
+                int good = 0;
+                for (int k = 0; k < n; ++k) good += fm_error(F + 9 * i, m1[k], m2[k]) <= thr;
+                if (good > std::max(maxGood, kFmModelPoints - 1)) {
+                    maxGood = good;
+                    std::memcpy(best, F + 9 * i, sizeof(best));
+                    niters = ransac_update_num_iters(kFmConfidence, (double)(n - good) / n, kFmModelPoints, niters);
+                }
+            }
+        }
+        std::memset(mask, 0, n);
+        if (maxGood > 0) for (int k = 0; k < n; ++k) mask[k] = fm_error(best, m1[k], m2[k]) <= thr;
+        if (bestF) std::memcpy(bestF, best, sizeof(best));
+        return maxGood;
+    }
+    // LMeDSPointSetRegistrator::run (8 <= n < 15)
+    int niters = ransac_update_num_iters(kFmConfidence, 0.45, kFmModelPoints, kFmMaxIters);
+    niters = std::max(niters, 3);
+    double minMedian = DBL_MAX;
+    std::vector<float> err(n);
+    for (int iter = 0; iter < niters; ++iter) {
+        if (!get_subset7(m1, m2, n, rng, 1000, idx, ms1, ms2)) { if (iter == 0) return 0; break; }
+        const int nm = run_7point(ms1, ms2, F);
+        for (int i = 0; i < nm; ++i) {
+            for (int k = 0; k < n; ++k) err[k] = fm_error(F + 9 * i, m1[k], m2[k]);
+            std::nth_element(err.begin(), err.begin() + n / 2, err.end());
+            const double median = err[n / 2];
+            if (median < minMedian) { minMedian = median; std::memcpy(best, F + 9 * i, sizeof(best)); }
+        }
+    }
+    std::memset(mask, 0, n);
+    if (!(minMedian < DBL_MAX)) return 0;
+    double sigma = 2.5 * 1.4826 * (1 + 5. / (n - kFmModelPoints)) * std::sqrt(minMedian);
+    sigma = std::max(sigma, 0.001);
+    const float thr = (float)(sigma * sigma);
+    int good = 0;
+    for (int k = 0; k < n; ++k) { mask[k] = fm_error(best, m1[k], m2[k]) <= thr; good += mask[k]; }
+    if (bestF) std::memcpy(bestF, best, sizeof(best));
+    return good;
+}

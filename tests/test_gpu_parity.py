@@ -1,0 +1,478 @@
+"""GPU parity tests: the CUDA path behind the C-ABI (libsvo_b200.so) against the CPU oracle on the same
+seeded inputs, against the committed OpenCV-generated goldens, and through size-independent
+properties at BASELINE.json's full sizes.  Integer / index work must be bit-exact; the pose tolerance
+is the one north_star states: 1e-4 rad and 1e-3 m.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from stereo_vo_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_RAD = 1e-4
+POSE_TOL_M = 1e-3
+
+
+def xys(k):
+    return np.stack([k["x"], k["y"], k["response"]], 1).astype(np.int32)
+
+
+def mtuple(m):
+    return np.stack([m["queryIdx"], m["trainIdx"], m["distance"].astype(np.int32)], 1)
+
+
+def ocam(cam):
+    return orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+
+
+def gcam(cam):
+    return capi.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+
+
+@pytest.fixture(scope="module")
+def ctx_c1():
+    c = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=8)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------------------------ K4 Hamming matcher
+@pytest.mark.parametrize("nq,nt", [(1, 1), (5, 3), (127, 129), (256, 512), (1000, 999), (300, 257), (4096, 4096)])
+def test_match_hamming_bit_exact(ctx_c1, nq, nt):
+    rng = np.random.default_rng(nq * 7 + nt)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    if nt >= 100:                       # 10 % duplicated train rows and exact copies in the query: ties
+        dup = rng.integers(0, nt, nt // 10)
+        t[rng.integers(0, nt, nt // 10)] = t[dup]
+        q[: min(nq, 40)] = t[rng.integers(0, nt, min(nq, 40))]
+    got = ctx_c1.match_hamming(q, t)
+    ref = orc.bf_match(q, t)
+    assert np.array_equal(got["trainIdx"], ref["trainIdx"])
+    assert np.array_equal(got["distance"], ref["distance"])
+    assert np.array_equal(got["queryIdx"], np.arange(nq)) and not got["imgIdx"].any()
+
+
+def test_match_hamming_golden_and_empty(ctx_c1, golden):
+    got = ctx_c1.match_hamming(golden["bf_rand_q"], golden["bf_rand_t"])
+    assert np.array_equal(np.stack([got["trainIdx"], got["distance"].astype(np.int32)], 1), golden["bf_rand"])
+    got = ctx_c1.match_hamming(golden["orbdesc_0L_th20"], golden["orbdesc_0R_th20"])
+    assert np.array_equal(np.stack([got["trainIdx"], got["distance"].astype(np.int32)], 1), golden["bf_0L_0R"])
+    z = np.zeros((0, 32), np.uint8)
+    assert len(ctx_c1.match_hamming(z, golden["bf_rand_t"])) == 0
+    assert len(ctx_c1.match_hamming(golden["bf_rand_q"], z)) == 0
+
+
+def test_match_hamming_linearity_property(ctx_c1):
+    # XOR-ing every descriptor of both sets with one constant leaves every distance unchanged
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 256, (2000, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (1777, 32), dtype=np.uint8)
+    c = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    a = ctx_c1.match_hamming(q, t)
+    b = ctx_c1.match_hamming(q ^ c, t ^ c)
+    assert np.array_equal(a, b)
+    # a query that is a train row matches itself (or an earlier duplicate) at distance 0
+    s = ctx_c1.match_hamming(t, t)
+    assert (s["distance"] == 0).all() and (s["trainIdx"] <= np.arange(len(t))).all()
+
+
+# ------------------------------------------------------------------------------------ stage 2
+def _check_detect(ctx, img, quota):
+    k, d = ctx.detect(img)
+    H, W = img.shape
+    rk, rd = orc.orb_compute(img, orc.fast9(img, 20))
+    rk, rd, _ = orc.non_max_sup(quota, rk, rd, 3, H, W)
+    rk, rd, _, _ = orc.update_indexes(rk, rd, H)
+    assert np.array_equal(xys(k), xys(rk))          # same keypoints in the same order (std::sort tie order)
+    assert np.array_equal(d, rd)
+    assert (k["size"] == 7).all() and (k["angle"] == -1).all() and (k["class_id"] == -1).all()
+    return k, d
+
+
+def test_detect_c1_bit_exact(ctx_c1):
+    for seed in (0, 1):
+        frames, _ = synth.make_sequence("c1", seed=seed, n_frames=1)
+        for img in frames[0]:
+            k, d = _check_detect(ctx_c1, img, 200)
+            assert len(k) == 200
+
+
+def test_detect_reference_fixtures(golden):
+    ctx = capi.Context(width=800, height=600, orb_nfeats=500, max_seqs=1)
+    try:
+        for name, count in (("0L", 514), ("0R", 443)):
+            img = golden["img_" + name]
+            k, d = _check_detect(ctx, img, 1000)
+            assert len(k) == count               # no cap: all FAST corners inside the ORB border survive
+            # same multiset as the OpenCV golden (which is in row-major order before the two sorts)
+            g = golden[f"orbkp_{name}_th20"]
+            assert sorted(map(tuple, xys(k))) == sorted(map(tuple, g))
+    finally:
+        ctx.close()
+
+
+def test_detect_flat_and_tiny_content(ctx_c1):
+    flat = np.full((240, 320), 128, np.uint8)
+    k, d = ctx_c1.detect(flat)
+    assert len(k) == 0 and len(d) == 0
+    one = flat.copy()
+    one[100:103, 150:153] = 255                    # a single blob: a handful of corners, no cap
+    _check_detect(ctx_c1, one, 200)
+
+
+def test_detect_capacity_overflow_is_reported():
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, max_corners=64)
+    try:
+        frames, _ = synth.make_sequence("c1", seed=0, n_frames=1)
+        with pytest.raises(capi.SvoError) as e:
+            ctx.detect(frames[0][0])
+        assert e.value.code == capi.SVO_ERR_CAPACITY
+    finally:
+        ctx.close()
+
+
+def test_detect_stable_sort_mode_matches_oracle_stable():
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, sort_mode=1)
+    try:
+        frames, _ = synth.make_sequence("c1", seed=5, n_frames=1)
+        img = frames[0][0]
+        k, d = ctx.detect(img)
+        rk, rd = orc.orb_compute(img, orc.fast9(img, 20))
+        rk, rd, _ = orc.non_max_sup(200, rk, rd, 3, 240, 320, sort_mode=1)
+        rk, rd, _, _ = orc.update_indexes(rk, rd, 240, sort_mode=1)
+        assert np.array_equal(xys(k), xys(rk)) and np.array_equal(d, rd)
+    finally:
+        ctx.close()
+
+
+def test_detect_min_distance_grid(golden):
+    # min_distance = 10 -> 5-px cells: the greedy occupancy path (S2:331-369) is exercised
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, min_distance=10)
+    try:
+        frames, _ = synth.make_sequence("c1", seed=2, n_frames=1)
+        img = frames[0][0]
+        k, d = ctx.detect(img)
+        rk, rd = orc.orb_compute(img, orc.fast9(img, 20))
+        rk, rd, _ = orc.non_max_sup(200, rk, rd, 10, 240, 320)
+        rk, rd, _, _ = orc.update_indexes(rk, rd, 240)
+        assert np.array_equal(xys(k), xys(rk)) and np.array_equal(d, rd)
+    finally:
+        ctx.close()
+
+
+# ------------------------------------------------------------------------------------ stage 3
+def test_match_lr_stage_entry(ctx_c1):
+    frames, _ = synth.make_sequence("c1", seed=7, n_frames=1)
+    kL, dL = ctx_c1.detect(frames[0][0])
+    kR, dR = ctx_c1.detect(frames[0][1])
+    got = ctx_c1.match_lr(kL, dL, kR, dR)
+    ref = orc.lr_filter(orc.bf_match(dL, dR), kL, kR, False, 1.0, 40, 320)
+    assert np.array_equal(mtuple(got), mtuple(ref)) and len(got) > 50
+    assert len(ctx_c1.match_lr(kL, dL, kR[:0], dR[:0])) == 0
+    assert len(ctx_c1.match_lr(kL[:0], dL[:0], kR, dR)) == 0
+
+
+def test_match_lr_robust_1to1():
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, enable_robust_1to1_match=1, max_y_diff=2.0,
+                       orb_threshold=60)
+    try:
+        frames, _ = synth.make_sequence("c1", seed=8, n_frames=1)
+        kL, dL = ctx.detect(frames[0][0])
+        kR, dR = ctx.detect(frames[0][1])
+        got = ctx.match_lr(kL, dL, kR, dR)
+        ref = orc.lr_filter(orc.bf_match(dL, dR), kL, kR, True, 2.0, 60, 320)
+        assert np.array_equal(mtuple(got), mtuple(ref))
+        assert len(np.unique(got["trainIdx"])) == len(got)
+    finally:
+        ctx.close()
+
+
+# ------------------------------------------------------------------------------------ F-matrix RANSAC
+def _two_views(rng, n, outl, integer=True):
+    X = np.stack([rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(3, 12, n)], 1)
+    f, c = 500.0, np.array([320.0, 240.0])
+    w = rng.normal(0, 0.02, 3)
+    t = rng.normal(0, 0.1, 3)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    R = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+    Y = X @ R.T + t
+    p1 = f * X[:, :2] / X[:, 2:] + c
+    p2 = f * Y[:, :2] / Y[:, 2:] + c + rng.normal(0, 0.3, (n, 2))
+    k = int(outl * n)
+    p2[:k] += rng.uniform(-50, 50, (k, 2))
+    if integer:
+        p1, p2 = np.rint(p1), np.rint(p2)
+    return p1.astype(np.float32), p2.astype(np.float32)
+
+
+def test_fundmat_ransac_matches_opencv():
+    cv2 = pytest.importorskip("cv2")
+    ctx = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=1)
+    try:
+        rng = np.random.default_rng(0)
+        total = bad = 0
+        for n in (14, 15, 16, 30, 100, 300, 700, 1000):
+            for outl in (0.0, 0.1, 0.3, 0.6):
+                for integer in (True, False):
+                    p1, p2 = _two_views(rng, n, outl, integer)
+                    F, m = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+                    m = np.zeros(n, np.uint8) if m is None else m.ravel()
+                    cnt, mine = ctx.fundmat_ransac(p1, p2)
+                    total += 1
+                    bad += int(not np.array_equal(m, mine))
+                    assert cnt == int(mine.sum())
+        assert bad == 0, f"{bad}/{total} masks differ from cv2.findFundamentalMat"
+        # small inputs: n == 7 -> all ones, n < 7 -> no mask
+        p1, p2 = _two_views(rng, 7, 0.0)
+        assert ctx.fundmat_ransac(p1, p2)[0] == 7
+        assert ctx.fundmat_ransac(p1[:6], p2[:6])[0] == 0
+        # 8..13 points: OpenCV's LMedS keeps exactly the 7 sample points (median error ~ 0), which the
+        # reference then ignores (< 8 inliers, S4:205,240); which 7 is decided by rounding noise
+        p1, p2 = _two_views(rng, 11, 0.2)
+        assert ctx.fundmat_ransac(p1, p2)[0] == 7
+    finally:
+        ctx.close()
+
+
+def test_fundmat_ransac_golden(golden):
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1)
+    try:
+        for i in (1, 2):
+            for side in "LR":
+                cnt, m = ctx.fundmat_ransac(golden[f"c1_f{i}_p1{side}"], golden[f"c1_f{i}_p2{side}"])
+                assert np.array_equal(m, golden[f"c1_f{i}_inl{side}"])
+    finally:
+        ctx.close()
+
+
+# ------------------------------------------------------------------------------------ stage 5 alone
+def test_get_change_in_pose_kat():
+    from tests.test_oracle_pins import _kat_inputs
+    for noise in (False, True):
+        a, cam, N = _kat_inputs(noise)
+        ctx = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=1)
+        try:
+            kp = [np.zeros(N, capi.KEYPOINT) for _ in range(4)]
+            for k, v in zip(kp, a):
+                k["x"], k["y"], k["response"] = v[:, 0], v[:, 1], 1.0
+            m = np.zeros(N, capi.DMATCH)
+            m["queryIdx"] = m["trainIdx"] = np.arange(N)
+            tp = np.stack([np.arange(N), np.arange(N)], 1)
+            g = capi.make_camera(500, 500, 320, 240, 0.12)
+            res = ctx.get_change_in_pose(tp, m, m, kp[0], kp[1], kp[2], kp[3], g)
+            ores, oresid, oinl = orc.stage5(*a, np.ones(N, np.float32), np.arange(N), 480, 640, 3, cam,
+                                            orc.LSParams.defaults(), np.zeros(6))
+            assert (res.valid, res.error_code, res.num_it, res.num_it_final) == (ores.valid, ores.error_code, ores.num_it, ores.num_it_final)
+            assert res.n_outliers == len(oinl)
+            assert np.array_equal(ctx.outliers(0), oinl)
+            np.testing.assert_allclose(res.delta_pose[:3], ores.delta_pose[:3], atol=POSE_TOL_RAD * 1e-3)
+            np.testing.assert_allclose(res.delta_pose[3:], ores.delta_pose[3:], atol=POSE_TOL_M * 1e-3)
+            np.testing.assert_allclose(res.out_pose_t[:], ores.out_pose_t[:], atol=1e-7)
+            np.testing.assert_allclose(np.array(res.out_pose[:]).reshape(4, 4), np.array(ores.out_pose_mat[:]).reshape(4, 4), atol=1e-7)
+            np.testing.assert_allclose(ctx.residuals(0), oresid, rtol=1e-6)
+        finally:
+            ctx.close()
+
+
+def test_get_change_in_pose_degenerate():
+    from tests.test_oracle_pins import _kat_inputs
+    a, cam, N = _kat_inputs(False)
+    ctx = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=1)
+    try:
+        def run(arrs):
+            n = len(arrs[0])
+            kp = [np.zeros(n, capi.KEYPOINT) for _ in range(4)]
+            for k, v in zip(kp, arrs):
+                k["x"], k["y"], k["response"] = v[:, 0], v[:, 1], 1.0
+            m = np.zeros(n, capi.DMATCH)
+            m["queryIdx"] = m["trainIdx"] = np.arange(n)
+            tp = np.stack([np.arange(n), np.arange(n)], 1)
+            return ctx.get_change_in_pose(tp, m, m, *kp, capi.make_camera(500, 500, 320, 240, 0.12))
+        r = run([v[:7] for v in a])                    # fewer than 8 points: invalid, no iterations
+        assert r.valid == 0 and r.num_it == 0 and r.n_residuals == 0
+        c = [v[:20].copy() for v in a]
+        c[1][:, 0] = c[0][:, 0]                        # zero disparity: every Jacobian rejected, H = 0 -> NaN cond
+        r = run(c)
+        assert r.valid == 0 and r.error_code == capi.VOEC["voecBadCondNumber"]
+    finally:
+        ctx.close()
+
+
+# ------------------------------------------------------------------------------------ whole pipeline
+def _run_sequence(ctx, est, frames, cam, slot=0, check_golden=None, golden=None):
+    out = []
+    for i, (L, R) in enumerate(frames):
+        o = est.process_new_image_pair(L, R, ocam(cam))
+        r = ctx.process_batch([L], [R], [gcam(cam)], slots=[slot])[0]
+        f = o["frame"]
+        assert np.array_equal(xys(ctx.keypoints(slot, 0, 0)), xys(f.kpsL)), f"frame {i}: left keypoints"
+        assert np.array_equal(xys(ctx.keypoints(slot, 0, 1)), xys(f.kpsR)), f"frame {i}: right keypoints"
+        assert np.array_equal(ctx.descriptors(slot, 0, 0), f.descL) and np.array_equal(ctx.descriptors(slot, 0, 1), f.descR)
+        assert np.array_equal(mtuple(ctx.matches(slot, 0)), mtuple(f.matches)), f"frame {i}: stereo matches"
+        assert (r.detected_left, r.detected_right, r.stereo_matches) == (len(f.kpsL), len(f.kpsR), len(f.matches))
+        assert r.error_code == o["error_code"] and bool(r.valid) == o["valid"], f"frame {i}: status"
+        if i > 0 and "track_dbg" in o:
+            q, tl, tr, il, ir = ctx.track_candidates(slot)
+            t = o["track_dbg"]
+            assert np.array_equal(q, t["matL"]["queryIdx"]) and np.array_equal(tl, t["matL"]["trainIdx"])
+            assert np.array_equal(tr, t["matR"]["trainIdx"])
+            if t["inlL"] is not None and est.ransac != "off":
+                assert np.array_equal(il, t["inlL"]) and np.array_equal(ir, t["inlR"]), f"frame {i}: RANSAC masks"
+            assert np.array_equal(ctx.tracked_pairs(slot), o["tracked"]), f"frame {i}: tracked pairs"
+            assert r.tracked_feats_from_last_frame == len(o["tracked"])
+        if o["pose"] is not None:
+            assert (r.num_it, r.num_it_final) == (o["num_it"], o["num_it_final"]), f"frame {i}: GN iterations"
+            np.testing.assert_allclose(r.delta_pose[:3], o["pose"]["delta"][:3], atol=POSE_TOL_RAD)
+            np.testing.assert_allclose(r.delta_pose[3:], o["pose"]["delta"][3:], atol=POSE_TOL_M)
+            np.testing.assert_allclose(r.out_pose_rotvec[:], o["pose"]["rotvec"], atol=POSE_TOL_RAD)
+            np.testing.assert_allclose(r.out_pose_t[:], o["pose"]["t"], atol=POSE_TOL_M)
+            np.testing.assert_allclose(r.out_pose_ypr[:], o["pose"]["ypr"], atol=POSE_TOL_RAD)
+            assert np.array_equal(ctx.outliers(slot), o["outliers"])
+            np.testing.assert_allclose(ctx.residuals(slot), o["out_residual"], rtol=1e-6, atol=1e-9)
+        if check_golden is not None:
+            g = golden
+            assert np.array_equal(xys(ctx.keypoints(slot, 0, 0)), g[f"{check_golden}_f{i}_kpsL"])
+            assert np.array_equal(mtuple(ctx.matches(slot, 0)), g[f"{check_golden}_f{i}_matches"])
+            assert np.array_equal(ctx.tracked_pairs(slot) if i > 0 else np.zeros((0, 2), np.int64), g[f"{check_golden}_f{i}_tracked"])
+            if i > 0:
+                np.testing.assert_allclose(r.delta_pose[:], g[f"{check_golden}_f{i}_delta"], atol=POSE_TOL_RAD)
+        out.append((o, r))
+    return out
+
+
+def test_pipeline_c1_vs_oracle_and_opencv_golden(ctx_c1, golden):
+    """BASELINE config 1 (320x240 / 200 kp): every stage boundary against the oracle and the
+    OpenCV-generated golden sequence, including the two F-matrix RANSAC masks."""
+    frames, cam = synth.make_sequence("c1", seed=3, n_frames=3)
+    ctx_c1.reset_slot(0)
+    masks = []
+
+    def golden_ransac(p1, p2):
+        return masks.pop(0)
+
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend="port", ransac=golden_ransac)
+    # feed the oracle with the OpenCV masks of the golden run, frame by frame
+    orig = est.process_new_image_pair
+
+    def wrapped(L, R, camo, _i=[0]):
+        i = _i[0]
+        _i[0] += 1
+        if i > 0:
+            masks[:] = [golden[f"c1_f{i}_inlL"], golden[f"c1_f{i}_inlR"]]
+        return orig(L, R, camo)
+    est.process_new_image_pair = wrapped
+    res = _run_sequence(ctx_c1, est, frames, cam, slot=0, check_golden="c1", golden=golden)
+    assert res[-1][1].valid and abs(res[-1][1].out_pose_t[0] - 0.05) < 5e-3
+
+
+def test_pipeline_ransac_off_matches_oracle(golden):
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, fundmat_filter=0)
+    try:
+        frames, cam = synth.make_sequence("c1", seed=11, n_frames=4)
+        est = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend="port", ransac="off")
+        _run_sequence(ctx, est, frames, cam)
+    finally:
+        ctx.close()
+
+
+def test_pipeline_c2_full_size_vs_oracle():
+    """BASELINE config 2 (640x480 / 1000 kp), the configuration the metric is quoted on."""
+    cv2 = pytest.importorskip("cv2")
+    ctx = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=2)
+    try:
+        frames, cam = synth.make_sequence("c2", seed=0, n_frames=3)
+        est = orc.OracleEstimator(orc.Params(orb_nfeats=500), backend="port", ransac="cv2")
+        res = _run_sequence(ctx, est, frames, cam, slot=1)
+        assert res[-1][1].detected_left == 1000 and res[-1][1].tracked_feats_from_last_frame > 300
+    finally:
+        ctx.close()
+
+
+def test_pipeline_c3_kitti_shape_vs_oracle():
+    """BASELINE config 3 (1242x375 / 2000 kp, RANSAC on)."""
+    cv2 = pytest.importorskip("cv2")
+    ctx = capi.Context(width=1242, height=375, orb_nfeats=1000, max_seqs=1, max_corners=32768)
+    try:
+        frames, cam = synth.make_sequence("c3", seed=1, n_frames=2)
+        est = orc.OracleEstimator(orc.Params(orb_nfeats=1000), backend="port", ransac="cv2")
+        res = _run_sequence(ctx, est, frames, cam)
+        assert res[-1][1].detected_left == 2000 and res[-1][1].valid
+    finally:
+        ctx.close()
+
+
+def test_batch_of_sequences_equals_sequences_alone(ctx_c1):
+    """BASELINE config 4 in miniature: independent sequences advanced together in one batch give the
+    results each gives alone (no cross-talk between slots)."""
+    seqs = [synth.make_sequence("c1", seed=20 + s, n_frames=3) for s in range(4)]
+    alone = []
+    for s, (frames, cam) in enumerate(seqs):
+        ctx_c1.reset_slot(0)
+        rs = [ctx_c1.process_batch([L], [R], [gcam(cam)], slots=[0])[0] for (L, R) in frames]
+        alone.append([(tuple(r.delta_pose), r.num_it, r.num_it_final, r.stereo_matches, r.tracked_feats_from_last_frame,
+                       r.error_code, r.valid) for r in rs])
+    for s in range(4):
+        ctx_c1.reset_slot(4 + s)
+    for f in range(3):
+        Ls = [seqs[s][0][f][0] for s in range(4)]
+        Rs = [seqs[s][0][f][1] for s in range(4)]
+        rs = ctx_c1.process_batch(Ls, Rs, [gcam(seqs[s][1]) for s in range(4)], slots=[4, 5, 6, 7])
+        for s, r in enumerate(rs):
+            got = (tuple(r.delta_pose), r.num_it, r.num_it_final, r.stereo_matches, r.tracked_feats_from_last_frame,
+                   r.error_code, r.valid)
+            assert got == alone[s][f]
+
+
+def test_state_machine_first_frame_bad_tracking_and_repeat(ctx_c1):
+    frames, cam = synth.make_sequence("c1", seed=4, n_frames=2)
+    ctx_c1.reset_slot(2)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend="port", ransac="off")
+    rng = np.random.default_rng(99)
+    junk = (synth.make_texture(rng, 240, 320), synth.make_texture(rng, 240, 320))
+    seq = [frames[0], junk, frames[1]]
+    expect = ["voecFirstIteration", "voecBadTracking", "voecNone"]
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, fundmat_filter=0)
+    try:
+        for (L, R), code in zip(seq, expect):
+            o = est.process_new_image_pair(L, R, ocam(cam))
+            r = ctx.process_pair(L, R, gcam(cam))
+            assert r.error_code == o["error_code"] == capi.VOEC[code]
+            assert bool(r.valid) == o["valid"]
+        # after voecBadTracking the previous frame was retained (P:86-89): frame 1 was matched against frame 0
+        assert r.valid and np.array_equal(xys(ctx.keypoints(0, 1, 0)), xys(est.prev.kpsL))
+        # request.repeat: no shift, same previous frame, same answer
+        o2 = est.process_new_image_pair(*frames[1], ocam(cam), repeat=True)
+        r2 = ctx.process_pair(*frames[1], gcam(cam), repeat=True)
+        assert r2.error_code == o2["error_code"] and bool(r2.valid) == o2["valid"]
+        assert r2.tracked_feats_from_last_frame == len(o2["tracked"]) == r.tracked_feats_from_last_frame
+    finally:
+        ctx.close()
+
+
+def test_match_ids_bookkeeping():
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, vo_use_matches_ids=1, fundmat_filter=0)
+    try:
+        frames, cam = synth.make_sequence("c1", seed=6, n_frames=3)
+        est = orc.OracleEstimator(orc.Params(orb_nfeats=100, vo_use_matches_ids=True), backend="port", ransac="off")
+        for (L, R) in frames:
+            o = est.process_new_image_pair(L, R, ocam(cam))
+            ctx.process_pair(L, R, gcam(cam))
+            assert np.array_equal(ctx.match_ids(0, 0), o["frame"].ids)
+    finally:
+        ctx.close()
+
+
+def test_argument_errors(ctx_c1):
+    frames, cam = synth.make_sequence("c1", seed=0, n_frames=1)
+    with pytest.raises(capi.SvoError):
+        ctx_c1.process_batch([frames[0][0]] * 2, [frames[0][1]] * 2, [gcam(cam)] * 2, slots=[1, 1])   # duplicate slot
+    with pytest.raises(capi.SvoError):
+        ctx_c1.process_batch([frames[0][0]], [frames[0][1]], [gcam(cam)], slots=[99])
+    with pytest.raises(capi.SvoError):
+        capi.Context(width=320, height=240, min_distance=1)
+    with pytest.raises(capi.SvoError):
+        capi.Context(width=16, height=16)
