@@ -200,6 +200,11 @@ int svo_get_change_in_pose(svo_ctx* ctx, int32_t slot,
  * when no model was found or n < 7. */
 int svo_fundmat_ransac(svo_ctx* ctx, const float* p1, const float* p2, int32_t n, uint8_t* mask);
 
+/* parity seam inside stage 2: the intermediate image planes of the last step for (slot, side).
+ * plane 0 = the 7x7 sigma=2 blur cv::ORB::compute applies (stage2_detect.cpp:512), plane 1 = FAST score
+ * after 3x3 NMS and the 31-px border filter (0 = no corner).  out: height*width bytes, tightly packed. */
+int svo_get_plane(svo_ctx* ctx, int32_t slot, int32_t side, int32_t plane, uint8_t* out);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 int svo_abi_version(void);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */

@@ -741,7 +741,7 @@ void orc_stage5(const float* l1l, const float* l1r, const float* l2l, const floa
         const bool cond = eval_rgn(l2l, l2r, nL, survivors, lmks, deltaPose, cam, ls, newPose, grad, residual, cCost, ec);
         res->error_code = ec;  // S5:564 writes result.error_code
         if (!cond) { res->valid = 0; res->bad_cond = 1; res->last_cost = cCost; return; }  // S5:569-573 (residuals NOT swapped out)
-        for (int k = 0; k < 6; ++k) deltaPose[k] += newPose[k];
+        for (int k = 0; k < 6; ++k) { deltaPose[k] += newPose[k]; res->delta_pose[k] = deltaPose[k]; }
         if (res->num_it > 0) {
             double m = 0;
             for (int c = 0; c < 6; ++c) m += newPose[c] * newPose[c];
@@ -778,7 +778,7 @@ void orc_stage5(const float* l1l, const float* l1r, const float* l2l, const floa
             res->bad_cond = 1;  // m_error = voecBadCondNumber is set inside m_evalRGN (S5:384)
             return;
         }
-        for (int k = 0; k < 6; ++k) deltaPose[k] += newPose[k];
+        for (int k = 0; k < 6; ++k) { deltaPose[k] += newPose[k]; res->delta_pose[k] = deltaPose[k]; }
         if (res->num_it_final > 0) {
             double m = 0;
             for (int c = 0; c < 6; ++c) m += newPose[c] * newPose[c];

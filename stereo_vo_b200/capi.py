@@ -28,7 +28,7 @@ EXPORTS = [
     "svo_default_config", "svo_create", "svo_destroy", "svo_last_error", "svo_reset_slot",
     "svo_process_batch", "svo_process_batch_device", "svo_fetch_results", "svo_synchronize", "svo_process_pair",
     "svo_get_keypoints", "svo_get_descriptors", "svo_get_matches", "svo_get_match_ids", "svo_get_tracked_pairs",
-    "svo_get_residuals", "svo_get_outliers", "svo_get_track_candidates",
+    "svo_get_residuals", "svo_get_outliers", "svo_get_track_candidates", "svo_get_plane",
     "svo_detect", "svo_match_hamming", "svo_match_hamming_device", "svo_match_lr", "svo_get_change_in_pose",
     "svo_fundmat_ransac", "svo_abi_version", "svo_kernel_launches", "svo_stream",
     "svo_enable_stage_timing", "svo_get_stage_times",
@@ -237,6 +237,11 @@ class Context:
         ir = np.zeros(self.kp_cap, np.uint8)
         n = self._check(lib().svo_get_track_candidates(self._h, slot, _vp(q), _vp(tl), _vp(tr), _vp(il), _vp(ir), self.kp_cap))
         return q[:n].copy(), tl[:n].copy(), tr[:n].copy(), il[:n].copy(), ir[:n].copy()
+
+    def plane(self, slot=0, side=0, plane=0):
+        out = np.zeros((self.cfg.height, self.cfg.width), np.uint8)
+        self._check(lib().svo_get_plane(self._h, slot, side, plane, _vp(out)))
+        return out
 
     # ---- per-stage entries --------------------------------------------------------------------------
     def detect(self, img):

@@ -564,6 +564,16 @@ int svo_get_track_candidates(svo_ctx* c, int32_t slot, int32_t* out_query, int32
     return n;
 }
 
+int svo_get_plane(svo_ctx* c, int32_t slot, int32_t side, int32_t plane, uint8_t* out) {
+    if (!c || !out) return SVO_ERR_ARG;
+    if (slot == -1) slot = c->hidden_slot;   // the scratch slot used by svo_detect
+    if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (side | 1) != 1 || (plane | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/side/plane");
+    CU(c, cudaStreamSynchronize(c->stream));
+    const uint8_t* src = (plane ? c->P.score : c->P.blur) + img_idx(slot, side) * (size_t)c->pitch * c->cfg.height;
+    CU(c, cudaMemcpy2D(out, c->cfg.width, src, c->pitch, c->cfg.width, c->cfg.height, cudaMemcpyDeviceToHost));
+    return SVO_OK;
+}
+
 // ---- per-stage entries ---------------------------------------------------------------------------
 int svo_detect(svo_ctx* c, const uint8_t* img, size_t stride, svo_keypoint* out_kps, uint8_t* out_desc, int32_t cap) {
     if (!c) return SVO_ERR_ARG;

@@ -61,21 +61,25 @@ __device__ __forceinline__ int fast9_score(const uint8_t* __restrict__ s, int th
     unsigned u = bright & (bright >> 1);
     u &= u >> 2; u &= u >> 4; u &= bright >> 8;
     if (((t | u) & 0xFFFFu) == 0) return 0;
-    // score = max over the 16 arcs of length 9 of min(d) and of min(-d), minus 1
-    int lo2[16], hi2[16];
+    // score = max over the 16 arcs of length 9 of min(d) and of min(-d), minus 1.
+    // Both polarities ride in one register as signed 16-bit lanes {d, -d} (|d| <= 255), so the sliding
+    // 9-window minima need 16-bit SIMD min/max only (DPX: VIMNMX.S16x2 / VIMNMX3.S16x2).
+    // NOTE: the obvious scalar form `best = max(best, max(lo9, -hi9))` is miscompiled by ptxas 12.9
+    // (-O1 and above, also by the driver JIT): wrong scores on sm_100a, correct with -Xptxas -O0.
+    // This formulation was checked on the device against the scalar definition (tests/test_gpu_parity.py).
+    unsigned p[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
-    int lo4[16], hi4[16];
+    for (int k = 0; k < 16; ++k) p[k] = ((unsigned)d[k] & 0xFFFFu) | ((unsigned)(-d[k]) << 16);
+    unsigned lo2[16], lo4[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
-    int best = -1024;
+    for (int k = 0; k < 16; ++k) lo2[k] = __vmins2(p[k], p[(k + 1) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(lo9, -hi9));
-    }
-    return best - 1;
+    for (int k = 0; k < 16; ++k) lo4[k] = __vmins2(lo2[k], lo2[(k + 2) & 15]);
+    unsigned best = 0x80008000u;   // (-32768, -32768)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) best = __vmaxs2(best, __vimin3_s16x2(lo4[k], lo4[(k + 4) & 15], p[(k + 8) & 15]));
+    const int a = (short)(best & 0xFFFFu), b = (short)(best >> 16);
+    return max(a, b) - 1;
 }
 
 __global__ void __launch_bounds__(K1_THREADS)

@@ -92,58 +92,69 @@ __device__ void rot_and_derivs(const double* dp, RotDeriv& o) {
 // Symmetric 6x6 eigen-decomposition by cyclic Jacobi; stands in for Eigen::JacobiSVD on the
 // (symmetric positive semi-definite) Hessian: singular values = |eigenvalues|.
 // Returns false when the condition number sigma_max/sigma_min would be NaN (S5:379-386).
+// The rotation is applied with the classic symmetric update (only the upper triangle is live):
+//   a_pp -= t a_pq, a_qq += t a_pq, a_pq = 0, a_rp -= s (a_rq + tau a_rp), a_rq += s (a_rp - tau a_rq).
+// A two-pass "columns then rows" update on a double[6][6] was observed to be miscompiled by nvcc 12.9
+// for sm_100a (the column pass acted on rows); this form was validated on the device.
+__device__ __forceinline__ double& sym(double* A, int i, int j) { return i <= j ? A[6 * i + j] : A[6 * j + i]; }
+
 __device__ bool solve6(const double* Hu /* 21 upper-triangle entries, row-major */, const double* g, double* x) {
-    double A[6][6], V[6][6];
+    double A[36], V[36];
     bool finite = true;
     {
         int k = 0;
         for (int i = 0; i < 6; ++i)
-            for (int j = i; j < 6; ++j) {
-                A[i][j] = A[j][i] = Hu[k++];
-                finite = finite && isfinite(A[i][j]);
+            for (int j = 0; j < 6; ++j) {
+                V[6 * i + j] = (i == j) ? 1.0 : 0.0;
+                if (j >= i) { A[6 * i + j] = Hu[k++]; finite = finite && isfinite(A[6 * i + j]); }
+                else A[6 * i + j] = 0.0;
             }
     }
     if (!finite) return false;
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0, diag = 0;
-        for (int i = 0; i < 6; ++i) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < 6; ++j) off += A[i][j] * A[i][j]; }
-        if (off <= diag * 1e-34 || off == 0.0) break;
+        for (int i = 0; i < 6; ++i) {
+            diag += A[6 * i + i] * A[6 * i + i];
+            for (int j = i + 1; j < 6; ++j) off += A[6 * i + j] * A[6 * i + j];
+        }
+        if (off <= diag * 1e-32) break;
         for (int p = 0; p < 5; ++p)
             for (int q = p + 1; q < 6; ++q) {
-                const double apq = A[p][q];
+                const double apq = A[6 * p + q];
                 if (apq == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double theta = (A[6 * q + q] - A[6 * p + p]) / (2.0 * apq);
                 const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 6; ++k) {   // columns p,q
-                    const double akp = A[k][p], akq = A[k][q];
-                    A[k][p] = c * akp - s * akq;
-                    A[k][q] = s * akp + c * akq;
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c, tau = sn / (1.0 + c);
+                A[6 * p + p] -= t * apq;
+                A[6 * q + q] += t * apq;
+                A[6 * p + q] = 0.0;
+                for (int r = 0; r < 6; ++r) {
+                    if (r == p || r == q) continue;
+                    double& arp = sym(A, r, p);
+                    double& arq = sym(A, r, q);
+                    const double vp = arp, vq = arq;
+                    arp = vp - sn * (vq + tau * vp);
+                    arq = vq + sn * (vp - tau * vq);
                 }
-                for (int k = 0; k < 6; ++k) {   // rows p,q
-                    const double apk = A[p][k], aqk = A[q][k];
-                    A[p][k] = c * apk - s * aqk;
-                    A[q][k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < 6; ++k) {
-                    const double vkp = V[k][p], vkq = V[k][q];
-                    V[k][p] = c * vkp - s * vkq;
-                    V[k][q] = s * vkp + c * vkq;
+                for (int r = 0; r < 6; ++r) {
+                    const double vp = V[6 * r + p], vq = V[6 * r + q];
+                    V[6 * r + p] = vp - sn * (vq + tau * vp);
+                    V[6 * r + q] = vq + sn * (vp - tau * vq);
                 }
             }
     }
     double smax = 0, smin = DBL_MAX;
-    for (int i = 0; i < 6; ++i) { const double s = fabs(A[i][i]); smax = fmax(smax, s); smin = fmin(smin, s); }
+    for (int i = 0; i < 6; ++i) { const double sv = fabs(A[6 * i + i]); smax = fmax(smax, sv); smin = fmin(smin, sv); }
     if (smax == 0.0 && smin == 0.0) return false;          // 0/0 = NaN
     const double thr = fmax(smax * 6.0 * DBL_EPSILON, DBL_MIN);   // Eigen SVDBase::rank() threshold
     for (int i = 0; i < 6; ++i) x[i] = 0;
     for (int k = 0; k < 6; ++k) {
-        if (!(fabs(A[k][k]) > thr)) continue;
+        const double lam = A[6 * k + k];
+        if (!(fabs(lam) > thr)) continue;
         double proj = 0;
-        for (int i = 0; i < 6; ++i) proj += V[i][k] * g[i];
-        proj /= A[k][k];
-        for (int i = 0; i < 6; ++i) x[i] += V[i][k] * proj;
+        for (int i = 0; i < 6; ++i) proj += V[6 * i + k] * g[i];
+        proj /= lam;
+        for (int i = 0; i < 6; ++i) x[i] += V[6 * i + k] * proj;
     }
     return true;
 }
@@ -169,6 +180,9 @@ struct GNShared {
     double step[6];
     double cCost, pCost;
     int done, abort, fail;
+#ifdef SVO_GN_DEBUG
+    int dbg_once; Result* dbg_res;
+#endif
     unsigned timesInc;
     int n_non_masked;
 };
@@ -262,6 +276,14 @@ __device__ void eval_rgn(const GnScratch& G, size_t base, int T, const Camera& c
         }
         sh.cCost = tot[27];
         sh.fail = solve6(tot, tot + 21, sh.step) ? 0 : 1;
+#ifdef SVO_GN_DEBUG
+        if (sh.dbg_once == 0) {
+            sh.dbg_once = 1;
+            Result& rr = *sh.dbg_res;
+            for (int i = 0; i < 16; ++i) rr.out_pose[i] = tot[i];
+            for (int i = 0; i < 3; ++i) { rr.out_pose_rotvec[i] = tot[16 + i]; rr.out_pose_t[i] = tot[19 + i]; rr.out_pose_ypr[i] = tot[22 + i]; }
+        }
+#endif
     }
     __syncthreads();
 }
@@ -378,6 +400,9 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
             sh.pose[i] = v;
         }
         sh.cCost = 0; sh.pCost = 0; sh.done = 0; sh.abort = 0; sh.fail = 0; sh.timesInc = 0;
+#ifdef SVO_GN_DEBUG
+        sh.dbg_once = 0; sh.dbg_res = &res;
+#endif
         res.n_outliers = 0;
         res.n_residuals = 0;
     }
@@ -402,7 +427,7 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
         }
         if (tid == 0) {
             double m = 0;
-            for (int k = 0; k < 6; ++k) { sh.pose[k] += sh.step[k]; m += sh.step[k] * sh.step[k]; }
+            for (int k = 0; k < 6; ++k) { sh.pose[k] += sh.step[k]; m += sh.step[k] * sh.step[k]; res.delta_pose[k] = sh.pose[k]; }
             if (num_it > 0) {
                 sh.done = sqrt(m) < p.min_mod_out_vector;
                 if (sh.pCost < sh.cCost) {
@@ -460,7 +485,7 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
         }
         if (tid == 0) {
             double m = 0;
-            for (int k = 0; k < 6; ++k) { sh.pose[k] += sh.step[k]; m += sh.step[k] * sh.step[k]; }
+            for (int k = 0; k < 6; ++k) { sh.pose[k] += sh.step[k]; m += sh.step[k] * sh.step[k]; res.delta_pose[k] = sh.pose[k]; }
             if (num_it_final > 0) {
                 sh.done = sqrt(m) < p.min_mod_out_vector;
                 if (sh.pCost < sh.cCost) {
