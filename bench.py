@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- stereo pairs/s of the B200 hot path at BASELINE.json config 2 (640x480, 1000 ORB kp,
+full detect + L/R match + tracking + F-matrix RANSAC + Gauss-Newton), one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     the reference's CPU path (oracle: real OpenCV
+                                                           calls + C++ restatement of the reference's glue)
+
+A "step" advances B independent stereo sequences (one slot each) by one frame.  Rank 0 prints ONE JSON line.
+  value  : pairs/s, inputs resident in HBM, timed with CUDA events on the library's stream
+  e2e    : pairs/s through svo_process_batch with pinned HOST images (H2D + results D2H inside the timing)
+  roofline : the dominant kernel's algorithmic HBM bytes / measured time vs the measured HBM peak
+  cpu_baseline : the CPU oracle on the host cores, bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "stereo_pairs_per_s"
+UNIT = "pairs/s"
+CONFIG = "c2"
+N_SEQ = 8            # distinct synthetic sequences (seeds 0..7), replicated over the slots with phase offsets
+N_FRAMES = 4         # frames per sequence, played back and forth so consecutive steps are adjacent frames
+
+
+def pingpong(t, n):
+    period = 2 * (n - 1)
+    t %= period
+    return t if t < n else period - t
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json (of measured)"
+    return 6650.0, "fallback 6.65 TB/s of /opt/skills/guides/B200_PROFILING.md (of fallback)"
+
+
+def make_frames(n_seq=N_SEQ, n_frames=N_FRAMES, config=CONFIG):
+    from stereo_vo_b200 import synth
+    seqs = []
+    cam = None
+    for s in range(n_seq):
+        frames, cam = synth.make_sequence(config, seed=s, n_frames=n_frames)
+        seqs.append(frames)
+    return seqs, cam
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device = device
+        self.stop_flag = False
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nme in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle with the real OpenCV calls, one process per core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    frames, cam, n_pairs, backend = args
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+    except Exception:
+        backend = "port"
+    from oracle import oracle as orc
+    camo = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=500), backend=backend, ransac="cv2" if backend == "cv2" else "off")
+    est.process_new_image_pair(*frames[0], camo)          # first frame (untimed: no tracking / GN yet)
+    t0 = time.perf_counter()
+    valid = 0
+    for t in range(1, n_pairs + 1):
+        o = est.process_new_image_pair(*frames[pingpong(t, len(frames))], camo)
+        valid += int(o["valid"])
+    return time.perf_counter() - t0, valid
+
+
+def cpu_throughput(seqs, cam, pairs_per_proc, procs):
+    """pairs/s of the CPU oracle with `procs` processes x 1 OpenCV thread, one sequence each."""
+    import multiprocessing as mp
+    try:
+        import cv2  # noqa: F401
+        backend = "cv2"
+    except Exception:
+        backend = "port"
+    from oracle import oracle as orc
+    orc.build()
+    ctxmp = mp.get_context("fork")
+    jobs = [(seqs[i % len(seqs)], cam, pairs_per_proc, backend) for i in range(procs)]
+    t0 = time.perf_counter()
+    with ctxmp.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    total = pairs_per_proc * procs
+    return total / busy, dict(kind="port", cores=procs, backend=backend,
+                              sample=f"{procs} processes x {pairs_per_proc} consecutive {CONFIG} pairs "
+                                     f"({total} pairs, {busy:.1f} s busy, {wall:.1f} s wall); "
+                                     f"third-party calls via {'cv2 ' + __import__('cv2').__version__ if backend == 'cv2' else 'the C++ port'}",
+                              valid=int(sum(r[1] for r in res)))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    seqs, cam = make_frames()
+    procs = os.cpu_count() or 1
+    per = max(2, args.ref_pairs)
+    vals = []
+    info = None
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_throughput(seqs, cam, 2, procs)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, info = cpu_throughput(seqs, cam, per, procs)
+        vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
+        "config": {"workload": "c2: 640x480 synthetic stereo sequences, 1000 ORB kp, FAST+ORB / BF L-R match / BF "
+                               "tracking + F-matrix RANSAC / robust Gauss-Newton (CPU: OpenCV + C++ restatement of the "
+                               "reference's glue; the reference itself cannot be built in this image)"},
+        "cpu_baseline": dict(info, value=value, unit=UNIT),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic HBM bytes per kernel launch (no re-reads counted)
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(B, W, H, N, M, T):
+    img = W * H
+    return {
+        "fast_blur_kernel": 2 * B * (img + 2 * img),          # image in, blur + score planes out
+        "select_kernel": 2 * B * (img + 12 * N),               # score plane in, keypoints out
+        "brief_kernel": 2 * B * (img + 12 * N + 32 * N),       # blur plane + keypoints in, descriptors out
+        "hamming_kernel(lr)": B * (32 * (N + N) + 8 * N),      # SURVEY: 32(NL+NR) + 8 NL
+        "lr_filter_kernel": B * (4 * N + 16 * N + 16 * M + 2 * 64 * M),
+        "hamming_kernel(track)": 2 * B * (32 * (M + M) + 8 * M),
+        "track_filter_kernel": B * (8 * M + 16 * M),
+        "ransac_prepare_kernel": B * (16 * M + 2 * 16 * M),
+        "fundmat_kernel": 2 * B * (16 * M + M),
+        "consistency_kernel": B * (16 * M + 2 * M + 8 * T),
+        "gn_kernel": B * (32 * T + 8 * T + 96),                # SURVEY: 32 T + 8 T + 96
+        "begin_step": B * 64,
+    }
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from stereo_vo_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = args.batch
+    cfgd = dict(c1=(320, 240, 100), c2=(640, 480, 500), c3=(1242, 375, 1000))[CONFIG]
+    W, H, nfeats = cfgd
+    seqs, cam = make_frames()
+    gc = capi.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    period = 2 * (N_FRAMES - 1)
+
+    # batch tensors for every phase of the playback: slot i plays sequence (i + rank) % N_SEQ with phase offset i
+    host = [[torch.empty((B, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(period)]
+    for t in range(period):
+        for i in range(B):
+            fr = seqs[(i + rank) % N_SEQ][pingpong(t + i, N_FRAMES)]
+            host[t][0][i].copy_(torch.from_numpy(fr[0]))
+            host[t][1][i].copy_(torch.from_numpy(fr[1]))
+    dev = [[h.cuda(non_blocking=True) for h in pair] for pair in host]
+    torch.cuda.synchronize()
+
+    ctx = capi.Context(width=W, height=H, orb_nfeats=nfeats, max_seqs=B, device=local)
+    cams = [gc] * B
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def step_device(t):
+        L, R = dev[t % period]
+        ctx.process_batch_device(L.data_ptr(), R.data_ptr(), B, W, W * H, cams)
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ---------------------------------------------------------------------
+    for t in range(args.warmup):
+        step_device(t)
+    ctx.synchronize()
+    ctx.enable_stage_timing(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.kernel_launches()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        step_device(args.warmup + k)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches() - launches0
+    sampler.stop_flag = True
+    kernel_ms = ctx.stage_times()
+    ctx.enable_stage_timing(False)
+    res = ctx.fetch_results(B)
+    n_valid = sum(int(r.valid) for r in res)
+    Nkp = float(np.mean([r.detected_left for r in res]))
+    M = float(np.mean([r.stereo_matches for r in res]))
+    T = float(np.mean([r.tracked_feats_from_last_frame for r in res]))
+
+    # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
+    ptrs = []
+    for t in range(period):
+        lp = (C.c_void_p * B)(*[host[t][0][i].data_ptr() for i in range(B)])
+        rp = (C.c_void_p * B)(*[host[t][1][i].data_ptr() for i in range(B)])
+        ptrs.append((lp, rp))
+    cam_arr = (capi.Camera * B)(*cams)
+    out = (capi.Result * B)()
+    lib = capi.lib()
+
+    def step_host(t):
+        lp, rp = ptrs[t % period]
+        rc = lib.svo_process_batch(ctx._h, B, None, lp, rp, C.c_size_t(W), cam_arr, None, out)
+        if rc < 0:
+            raise RuntimeError(lib.svo_last_error(ctx._h).decode())
+
+    for t in range(max(2, args.warmup)):
+        step_host(args.warmup + args.steps + t)
+    barrier()
+    t0 = time.perf_counter()
+    e2 = torch.cuda.Event(enable_timing=True)
+    e3 = torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for k in range(args.steps):
+        step_host(args.warmup + args.steps + 2 + k)
+    e3.record(stream)
+    barrier()
+    e2e_ms = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+    e2e_valid = sum(int(r.valid) for r in out)
+
+    # ---- max over ranks + the end-of-batch gather (the only collective on this path) ------------------------
+    pairs = B * args.steps
+    if world > 1:
+        tm = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tm[0]), float(tm[1])
+        cnt = torch.tensor([pairs, n_valid, launches], dtype=torch.int64, device="cuda")
+        gathered = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(gathered, cnt)
+        pairs_all = int(sum(int(g[0]) for g in gathered))
+        n_valid_all = int(sum(int(g[1]) for g in gathered))
+        launches_all = int(sum(int(g[2]) for g in gathered))
+    else:
+        pairs_all, n_valid_all, launches_all = pairs, n_valid, launches
+
+    if rank == 0:
+        value = pairs_all / (ms * 1e-3)
+        e2e_value = pairs_all / (e2e_ms * 1e-3)
+        peak, peak_src = load_peaks()
+        ab = algorithmic_bytes(B, W, H, Nkp, M, T)
+        total_kernel_ms = sum(kernel_ms.values()) or 1.0
+        kernels = {}
+        for name, kms in kernel_ms.items():
+            gbs = ab.get(name, 0) / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+            kernels[name] = {"ms": round(kms, 4), "share": round(kms / total_kernel_ms, 4),
+                             "algo_bytes": int(ab.get(name, 0)), "gbs": round(gbs, 2)}
+        dom = max(kernel_ms, key=kernel_ms.get)
+        dom_gbs = kernels[dom]["gbs"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(dom)
+            except Exception:
+                traffic = None
+        # Hamming stage: pair-distances/s against the POPC issue roof (16 lanes/clk/SM x 148 SMs), reported beside HBM
+        hm_ms = kernel_ms.get("hamming_kernel(lr)", 0) + kernel_ms.get("hamming_kernel(track)", 0)
+        pairdist = B * (Nkp * Nkp + 2 * M * M)
+        clocks = sampler.summary()
+        sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        popc_roof = 148 * 16 * sm_clk / 8.0          # pair-distances/s at 8 POPC each
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8+f64", "data": "synthetic",
+            "config": {"workload": "c2: 640x480 synthetic stereo sequences, 1000 ORB kp, full FAST+ORB detect / L-R match / "
+                                   "tracking + F-matrix RANSAC / Gauss-Newton path",
+                       "pairs_per_step_per_gpu": B, "distinct_sequences": N_SEQ,
+                       "l2": f"inputs larger than L2: {2 * B * W * H / 1e6:.0f} MB of images per step per GPU, "
+                             f"{period} distinct batches cycled",
+                       "keypoints_per_image": Nkp, "stereo_matches": M, "tracked_pairs": T,
+                       "valid_results": f"{n_valid_all}/{B * world}"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * W * H,
+                    "d2h_bytes_per_step": B * C.sizeof(capi.Result), "ms_per_step": e2e_ms / args.steps,
+                    "valid_results": f"{e2e_valid}/{B}"},
+            "gpu_launches": launches_all,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": dom_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                         "note": "the dominant kernel is integer-ALU bound (FAST ring test + arc min/max), not HBM bound; "
+                                 "frac is reported against HBM as the contract asks"},
+            "kernels": kernels,
+            "match_stage": {"pair_distances_per_s": pairdist / (hm_ms * 1e-3) if hm_ms else None,
+                            "popc_roof_pair_distances_per_s": popc_roof,
+                            "frac_of_popc_roof": (pairdist / (hm_ms * 1e-3) / popc_roof) if hm_ms else None,
+                            "hbm_gbs": (ab["hamming_kernel(lr)"] + ab["hamming_kernel(track)"]) / (hm_ms * 1e-3) / 1e9 if hm_ms else None},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            seqs_cpu = seqs
+            procs = os.cpu_count() or 1
+            v, info = cpu_throughput(seqs_cpu, cam, args.cpu_pairs, procs)
+            line["cpu_baseline"] = dict(info, value=v, unit=UNIT)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="stereo pairs (sequence slots) per step per GPU")
+    ap.add_argument("--cpu-pairs", type=int, default=12, help="cpu_baseline: pairs per process")
+    ap.add_argument("--ref-pairs", type=int, default=12, help="--impl reference: pairs per process per step")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -303,7 +303,7 @@ class Context:
         self._check(lib().svo_enable_stage_timing(self._h, int(on)))
 
     def stage_times(self):
-        names = (C.c_char_p * 16)()
-        ms = (C.c_float * 16)()
-        n = self._check(lib().svo_get_stage_times(self._h, names, ms, 16))
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        n = self._check(lib().svo_get_stage_times(self._h, names, ms, 32))
         return {names[i].decode(): float(ms[i]) for i in range(n)}

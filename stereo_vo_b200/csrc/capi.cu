@@ -23,9 +23,12 @@ static_assert(sizeof(svo_keypoint) == 28 && sizeof(svo_dmatch) == 16, "cv::KeyPo
 
 static thread_local std::string g_create_error;
 
-enum { ST_H2D = 0, ST_DETECT, ST_MATCH_LR, ST_TRACK, ST_RANSAC, ST_CONSIST, ST_GN, ST_COUNT };
-static const char* kStageNames[ST_COUNT] = {"h2d", "stg2.detect", "stg3.match_lr", "stg4.track_match",
-                                            "stg4.fundmat_ransac", "stg4.consistency", "stg5.optimize"};
+// one timed interval per kernel of a step, in launch order (see run_step)
+enum { KT_COUNT = 12, KT_DEPTH = 64 };
+static const char* kKernelNames[KT_COUNT] = {
+    "begin_step", "fast_blur_kernel", "select_kernel", "brief_kernel", "hamming_kernel(lr)", "lr_filter_kernel",
+    "hamming_kernel(track)", "track_filter_kernel", "ransac_prepare_kernel", "fundmat_kernel", "consistency_kernel",
+    "gn_kernel"};
 
 struct svo_ctx {
     svo_config cfg;
@@ -54,9 +57,9 @@ struct svo_ctx {
     int launches_i = 0;
     int64_t launches = 0;
     int timing = 0;
-    cudaEvent_t ev[ST_COUNT + 1] = {};
-    float stage_ms[ST_COUNT] = {};
-    bool have_times = false;
+    std::vector<cudaEvent_t> ev;      // KT_DEPTH sets of KT_COUNT+1 events
+    int timed_steps = 0;              // steps recorded since timing was enabled
+    int marks_last = 0;
 };
 
 namespace {
@@ -107,7 +110,6 @@ __global__ void reset_slot_kernel(Pools P, int slot) {
 
 bool valid_slot(const svo_ctx* c, int slot) { return slot >= 0 && slot < c->cfg.max_seqs; }
 
-void record(svo_ctx* c, int i) { if (c->timing) cudaEventRecord(c->ev[i], c->stream); }
 
 // enqueue one pipeline step on device images
 int run_step(svo_ctx* c, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride, size_t image_pitch,
@@ -115,25 +117,24 @@ int run_step(svo_ctx* c, int n, const uint8_t* d_left, const uint8_t* d_right, s
     Pools& P = c->P;
     int& L = c->launches_i;
     L = 0;
+    StepTimer tm;
+    if (c->timing && !c->ev.empty()) tm.ev = c->ev.data() + (size_t)(c->timed_steps % KT_DEPTH) * (KT_COUNT + 1);
+    StepTimer* t = tm.ev ? &tm : nullptr;
+    if (t) t->mark(c->stream);
     scatter_cams_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(P, c->d_cams_batch, n);
     CU(c, launch_begin_step(P, n, have_repeat ? c->d_repeat : nullptr, c->stream));
+    if (t) t->mark(c->stream);
     L += 2;
-    record(c, ST_DETECT);
     CU(c, launch_detect(P, n, d_left, d_right, stride, image_pitch, c->pitch, c->d_occ, c->occ_words,
-                        c->d_sort_scratch, c->stream, &L));
-    record(c, ST_MATCH_LR);
-    CU(c, launch_match_lr(P, n, c->stream, &L));
-    record(c, ST_TRACK);
-    CU(c, launch_track_match(P, n, c->stream, &L));
-    record(c, ST_RANSAC);
-    if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, c->RS, n, c->stream, &L));
-    record(c, ST_CONSIST);
-    CU(c, launch_consistency(P, n, c->stream, &L));
-    record(c, ST_GN);
-    CU(c, launch_gn(P, c->G, n, /*external=*/0, /*custom pose=*/0, /*assume_fast_kps=*/1, c->stream, &L));
-    record(c, ST_COUNT);
+                        c->d_sort_scratch, c->stream, &L, t));
+    CU(c, launch_match_lr(P, n, c->stream, &L, t));
+    CU(c, launch_track_match(P, n, c->stream, &L, t));
+    if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, c->RS, n, c->stream, &L, t));
+    else if (t) { t->mark(c->stream); t->mark(c->stream); }
+    CU(c, launch_consistency(P, n, c->stream, &L, t));
+    CU(c, launch_gn(P, c->G, n, /*external=*/0, /*custom pose=*/0, /*assume_fast_kps=*/1, c->stream, &L, t));
+    if (t) { c->marks_last = tm.next; ++c->timed_steps; }
     c->launches += L;
-    c->have_times = c->timing != 0;
     return SVO_OK;
 }
 
@@ -291,7 +292,6 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
 #undef HA
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { int rc = cuda_fail(nullptr, e, "cudaStreamCreate"); svo_destroy(c); return rc; }
-    for (int i = 0; i <= ST_COUNT; ++i) cudaEventCreate(&c->ev[i]);
     if ((e = configure_detect(p)) != cudaSuccess || (e = configure_match(p)) != cudaSuccess ||
         (e = configure_gn(p)) != cudaSuccess || (e = configure_ransac(kp_cap)) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "kernel configuration (shared memory)");
@@ -308,7 +308,7 @@ void svo_destroy(svo_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-    for (int i = 0; i <= ST_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (void* p : c->dev_allocs) cudaFree(p);
     for (void* p : c->host_allocs) cudaFreeHost(p);
     delete c;
@@ -333,20 +333,31 @@ int64_t svo_kernel_launches(const svo_ctx* c) { return c ? c->launches : 0; }
 
 int svo_enable_stage_timing(svo_ctx* c, int32_t on) {
     if (!c) return SVO_ERR_ARG;
+    if (on && c->ev.empty()) {
+        c->ev.resize((size_t)KT_DEPTH * (KT_COUNT + 1));
+        for (cudaEvent_t& e : c->ev) CU(c, cudaEventCreate(&e));
+    }
     c->timing = on;
+    c->timed_steps = 0;
     return SVO_OK;
 }
 
+// mean device time per kernel over the steps recorded since timing was enabled (at most the last KT_DEPTH)
 int svo_get_stage_times(svo_ctx* c, const char** names, float* ms, int32_t cap) {
     if (!c) return SVO_ERR_ARG;
-    if (!c->have_times) return 0;
+    if (c->ev.empty() || c->timed_steps == 0) return 0;
     CU(c, cudaStreamSynchronize(c->stream));
+    const int steps = std::min(c->timed_steps, (int)KT_DEPTH);
     int n = 0;
-    for (int i = 0; i < ST_COUNT && n < cap; ++i) {
-        float t = 0;
-        if (cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]) != cudaSuccess) t = 0;
-        if (names) names[n] = kStageNames[i];
-        if (ms) ms[n] = t;
+    for (int i = 0; i < KT_COUNT && n < cap; ++i) {
+        double acc = 0;
+        for (int s = 0; s < steps; ++s) {
+            const cudaEvent_t* e = c->ev.data() + (size_t)s * (KT_COUNT + 1);
+            float t = 0;
+            if (cudaEventElapsedTime(&t, e[i], e[i + 1]) == cudaSuccess) acc += t;
+        }
+        if (names) names[n] = kKernelNames[i];
+        if (ms) ms[n] = (float)(acc / steps);
         ++n;
     }
     return n;
@@ -360,7 +371,6 @@ int svo_process_batch_device(svo_ctx* c, int32_t n, const int32_t* slots, const 
     CU(c, cudaSetDevice(c->cfg.device));
     int rc = upload_batch_meta(c, n, slots, cams, repeat);
     if (rc != SVO_OK) return rc;
-    record(c, ST_H2D);
     return run_step(c, n, d_left, d_right, stride, image_pitch, repeat != nullptr);
 }
 
@@ -402,7 +412,6 @@ int svo_process_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t
     CU(c, cudaSetDevice(c->cfg.device));
     int rc = upload_batch_meta(c, n, slots, cams, repeat);
     if (rc != SVO_OK) return rc;
-    record(c, ST_H2D);
     const int W = c->cfg.width, H = c->cfg.height;
     const size_t plane = (size_t)c->pitch * H;
     // contiguous batches go up in one copy per side

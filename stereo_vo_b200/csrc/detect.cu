@@ -432,13 +432,16 @@ cudaError_t launch_begin_step(const Pools& P, int n, const uint8_t* d_repeat, cu
 
 cudaError_t launch_detect(const Pools& P, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
                           size_t image_pitch, int pitch_out, uint32_t* occ_scratch, int occ_words_per_img,
-                          uint32_t* sort_scratch, cudaStream_t st, int* launches) {
+                          uint32_t* sort_scratch, cudaStream_t st, int* launches, StepTimer* tm) {
     const dim3 g1((P.p.W + TW - 1) / TW, (P.p.H + TH - 1) / TH, 2 * n);
     fast_blur_kernel<<<g1, K1_THREADS, 0, st>>>(P, d_left, d_right, stride, image_pitch, pitch_out);
+    if (tm) tm->mark(st);
     const int smem = detect_smem_bytes(P.p);
     select_kernel<<<2 * n, K2_THREADS, smem, st>>>(P, pitch_out, occ_scratch, occ_words_per_img, sort_scratch);
+    if (tm) tm->mark(st);
     const dim3 g3((P.p.kp_cap + K3_WARPS - 1) / K3_WARPS, 2 * n);
     brief_kernel<<<g3, K3_WARPS * 32, 0, st>>>(P, pitch_out);
+    if (tm) tm->mark(st);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }

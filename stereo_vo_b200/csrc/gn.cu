@@ -529,8 +529,9 @@ cudaError_t configure_gn(const Params& p) {
 }
 
 cudaError_t launch_gn(const Pools& P, const GnScratch& G, int n, int external, int use_custom_pose,
-                      int assume_fast_kps, cudaStream_t st, int* launches) {
+                      int assume_fast_kps, cudaStream_t st, int* launches, StepTimer* tm) {
     gn_kernel<<<n, GN_THREADS, P.p.kp_cap * 8, st>>>(P, G, external, use_custom_pose, assume_fast_kps);
+    if (tm) tm->mark(st);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

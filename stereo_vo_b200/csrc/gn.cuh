@@ -18,5 +18,5 @@ struct GnScratch {            // per-slot scratch, [max_seqs][kp_cap] unless not
 
 cudaError_t configure_gn(const Params& p);
 cudaError_t launch_gn(const Pools& P, const GnScratch& G, int n, int external, int use_custom_pose,
-                      int assume_fast_kps, cudaStream_t st, int* launches);
+                      int assume_fast_kps, cudaStream_t st, int* launches, StepTimer* tm = nullptr);
 }  // namespace svo

@@ -339,27 +339,32 @@ consistency_kernel(Pools P) {
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_match_lr(const Pools& P, int n, cudaStream_t st, int* launches) {
+cudaError_t launch_match_lr(const Pools& P, int n, cudaStream_t st, int* launches, StepTimer* tm) {
     const int per = HM_THREADS * HM_QPT;
     dim3 g((P.p.kp_cap + per - 1) / per, n);
     hamming_pipeline_kernel<<<g, HM_THREADS, 0, st>>>(P, 0, 1);
+    if (tm) tm->mark(st);
     lr_filter_kernel<<<n, FT, P.p.kp_cap * sizeof(uint32_t), st>>>(P);
+    if (tm) tm->mark(st);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }
 
-cudaError_t launch_track_match(const Pools& P, int n, cudaStream_t st, int* launches) {
+cudaError_t launch_track_match(const Pools& P, int n, cudaStream_t st, int* launches, StepTimer* tm) {
     const int per = HM_THREADS * HM_QPT;
     dim3 g((P.p.kp_cap + per - 1) / per, 2 * n);
     hamming_pipeline_kernel<<<g, HM_THREADS, 0, st>>>(P, 1, 2);
+    if (tm) tm->mark(st);
     const int bw = (P.p.kp_cap + 31) / 32;
     track_filter_kernel<<<n, 32, (2 * P.p.kp_cap + 2 * bw) * sizeof(uint32_t), st>>>(P);
+    if (tm) tm->mark(st);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }
 
-cudaError_t launch_consistency(const Pools& P, int n, cudaStream_t st, int* launches) {
+cudaError_t launch_consistency(const Pools& P, int n, cudaStream_t st, int* launches, StepTimer* tm) {
     consistency_kernel<<<n, FT, P.p.kp_cap * sizeof(uint32_t), st>>>(P);
+    if (tm) tm->mark(st);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

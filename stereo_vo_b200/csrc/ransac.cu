@@ -212,9 +212,12 @@ cudaError_t configure_ransac(int kp_cap) {
     return cudaFuncSetAttribute(fundmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ransac_smem(kp_cap));
 }
 
-cudaError_t launch_ransac(const Pools& P, const RansacScratch& R, int n, cudaStream_t st, int* launches) {
+cudaError_t launch_ransac(const Pools& P, const RansacScratch& R, int n, cudaStream_t st, int* launches,
+                          StepTimer* tm) {
     ransac_prepare_kernel<<<n, 256, 0, st>>>(P, R);
+    if (tm) tm->mark(st);
     fundmat_kernel<<<2 * n, RS_THREADS, ransac_smem(R.kp_cap), st>>>(R);
+    if (tm) tm->mark(st);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

@@ -18,7 +18,8 @@ struct RansacScratch {
 cudaError_t alloc_ransac(RansacScratch& R, int n_slots, int kp_cap, std::vector<void*>& allocs);
 cudaError_t configure_ransac(int kp_cap);
 // masks for every slot of the running batch: P.inl / P.n_inl (stage4_match_consecutive.cpp:171-241)
-cudaError_t launch_ransac(const Pools& P, const RansacScratch& R, int n, cudaStream_t st, int* launches);
+cudaError_t launch_ransac(const Pools& P, const RansacScratch& R, int n, cudaStream_t st, int* launches,
+                          StepTimer* tm = nullptr);
 // stand-alone: host points -> host mask (svo_fundmat_ransac)
 cudaError_t ransac_host_points(const RansacScratch& R, int scratch_slot, const float* p1, const float* p2, int n,
                                uint8_t* mask, int* n_inliers, cudaStream_t st);

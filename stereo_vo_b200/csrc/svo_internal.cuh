@@ -100,6 +100,14 @@ struct Pools {
     int32_t* slots;        // [max_seqs] slot index of batch item i
 };
 
+// Optional per-kernel timing: one CUDA event is recorded on the launching stream after every kernel
+// of a step (bench.py derives the per-kernel roofline numbers from these).
+struct StepTimer {
+    cudaEvent_t* ev = nullptr;   // events of the running step, or nullptr when timing is off
+    int next = 0;
+    void mark(cudaStream_t st) { if (ev) cudaEventRecord(ev[next++], st); }
+};
+
 __host__ __device__ inline size_t img_idx(int slot, int side) { return (size_t)slot * 2 + side; }
 __host__ __device__ inline size_t frame_idx(int slot, int buf, int side) { return ((size_t)slot * 2 + buf) * 2 + side; }
 __host__ __device__ inline size_t pair_idx(int slot, int buf) { return (size_t)slot * 2 + buf; }
