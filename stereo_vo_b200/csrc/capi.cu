@@ -275,7 +275,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
         c->occ_words = (int)((glx * gly + 31) / 32) + 1;
     }
     DA(c->d_occ, (size_t)S * 2 * c->occ_words);
-    DA(c->d_sort_scratch, cfg->sort_mode ? (size_t)S * 2 * cfg->max_corners : 16);
+    DA(c->d_sort_scratch, (size_t)S * 2 * cfg->max_corners);
     GnScratch& G = c->G;
     DA(G.prev, S * cap); DA(G.obs, S * cap); DA(G.lmk, S * cap * 3); DA(G.mask, S * cap);
     DA(G.cur_idx, S * cap); DA(G.ini_pose, S * 6);

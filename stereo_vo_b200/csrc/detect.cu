@@ -215,8 +215,13 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* s_a = smem;                          // [max_corners]
     uint32_t* s_b = smem + P.p.max_corners;        // [kp_cap]
+    const int list_cap = P.p.max_corners / 16 + 2;
+    uint2* s_listA = reinterpret_cast<uint2*>(smem + ((P.p.max_corners + P.p.kp_cap + 1) & ~1));
+    uint2* s_listB = s_listA + list_cap;
     __shared__ int s_warp[K2_THREADS / 32];
-    __shared__ int s_n, s_nsel;
+    __shared__ int s_nsel;
+    __shared__ int s_cnt2[2];
+    uint32_t* tmp = sort_scratch + (size_t)blockIdx.x * P.p.max_corners;
 
     const int W = P.p.W, H = P.p.H;
     const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
@@ -282,12 +287,8 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
 
     if (P.p.nms) {
         // ---- B. sort by response, descending (KeypointResponseSorter) ------------------------------
-        if (P.p.sort_mode == 0) {
-            if (tid == 0) introsort_seq<true, 24>(s_a, n);
-            __syncthreads();
-        } else {
-            block_stable_sort<true, 24>(s_a, sort_scratch + (size_t)blockIdx.x * P.p.max_corners, n);
-        }
+        if (P.p.sort_mode == 0) introsort_block(KeyComp<true, 24>(), s_a, n, s_listA, s_listB, s_cnt2, tmp);
+        else block_stable_sort<true, 24>(s_a, tmp, n);
         // ---- C. greedy occupancy grid ---------------------------------------------------------------
         const unsigned cell = (unsigned)(P.p.min_distance / 2.0);     // S2:331
         if (cell == 1) {
@@ -331,12 +332,8 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
         s_b[k] = (pos & 0xFFFF0000u) | (uint32_t)k;   // y << 16 | position in the selection order
     }
     __syncthreads();
-    if (P.p.sort_mode == 0) {
-        if (tid == 0) introsort_seq<false, 16>(s_b, n_sel);
-        __syncthreads();
-    } else {
-        block_stable_sort<false, 16>(s_b, sort_scratch + (size_t)blockIdx.x * P.p.max_corners, n_sel);
-    }
+    if (P.p.sort_mode == 0) introsort_block(KeyComp<false, 16>(), s_b, n_sel, s_listA, s_listB, s_cnt2, tmp);
+    else block_stable_sort<false, 16>(s_b, tmp, n_sel);
     // ---- E. emit ------------------------------------------------------------------------------------
     for (int i = tid; i < n_sel; i += K2_THREADS) {
         const uint32_t wd = s_a[s_b[i] & 0xFFFFu];
@@ -419,7 +416,9 @@ __global__ void begin_step_kernel(Pools P, int n, const uint8_t* __restrict__ re
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-int detect_smem_bytes(const Params& p) { return (p.max_corners + p.kp_cap) * (int)sizeof(uint32_t); }
+int detect_smem_bytes(const Params& p) {
+    return ((p.max_corners + p.kp_cap + 1) & ~1) * (int)sizeof(uint32_t) + 2 * (p.max_corners / 16 + 2) * (int)sizeof(uint2);
+}
 
 cudaError_t configure_detect(const Params& p) {
     return cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, detect_smem_bytes(p));

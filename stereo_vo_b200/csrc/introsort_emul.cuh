@@ -178,6 +178,127 @@ SVO_HD void introsort_seq(uint32_t* a, int n) {
     introsort_seq_c(KeyComp<Desc, KeyShift>(), a, n);
 }
 
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------------------------
+// Block-cooperative emulation (device only): identical result to introsort_seq.
+//
+//  * The recursion tree is walked level by level: all segments of one level are independent, each is
+//    handled by one warp, the children (> 16 elements) go to the next level's list.  Both children of a
+//    partition inherit depth-1, exactly like the recursion on [cut,last) + loop on [first,cut).
+//  * The unguarded Hoare partition is executed 32 elements at a time: the warp loads a chunk from each
+//    end, ballots the "stoppers" (left: !comp(x,pivot), right: !comp(pivot,x)), pairs the k-th left
+//    stopper with the k-th right stopper and swaps the pairs with i < j in one step.  The pairing
+//    sequence, and therefore every swap and the returned cut, is the one the sequential loop produces
+//    (validated exhaustively against the sequential partition, tests/test_host_cpu.py + GPU tests).
+//  * The final insertion sort is a stable sort that only moves elements inside their <= 16-element
+//    leaf segment, so an element's final position is  i - #{j in [i-15,i): comp(a[i],a[j])}
+//    + #{j in (i,i+15]: comp(a[j],a[i])}: computed by all threads at once.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned clear_lowest_set_bits(unsigned mask, int c) {
+    if (c <= 0) return mask;
+    const unsigned pos = __fns(mask, 0, c);          // position of the c-th set bit (1-based)
+    return pos >= 31u ? 0u : (mask & (0xFFFFFFFFu << (pos + 1)));
+}
+
+// Partition a[seg_first .. seg_last) around the pivot already placed at a[seg_first]; all 32 lanes call it.
+template <class C>
+__device__ int warp_unguarded_partition(const C& c, uint32_t* a, int seg_first, int seg_last) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t pivot = a[seg_first];
+    int lb = seg_first + 1 - 32, rb = seg_last - 1 + 32;
+    unsigned lmask = 0, rmask = 0;
+    int lastR = 0x7FFFFFFF;
+    while (true) {
+        if (lmask == 0) {
+            lb += 32;
+            const int x = lb + lane;
+            const bool stop = (x >= seg_last) ? true : !c.lt(a[x], pivot);
+            lmask = __ballot_sync(0xffffffffu, stop);
+        }
+        if (rmask == 0) {
+            rb -= 32;
+            const int x = rb - lane;
+            const bool stop = (x < seg_first) ? true : !c.lt(pivot, a[x]);
+            rmask = __ballot_sync(0xffffffffu, stop);
+        }
+        if (lmask == 0 || rmask == 0) continue;
+        const int cnt = min(__popc(lmask), __popc(rmask));
+        int i = 0, j = 0;
+        bool ok = false;
+        if (lane < cnt) {
+            i = lb + (int)__fns(lmask, 0, lane + 1);
+            j = rb - (int)__fns(rmask, 0, lane + 1);
+            ok = i < j;
+        }
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        const int m = __popc(okmask);            // the pairs with i < j form a prefix
+        if (ok) { const uint32_t t = a[i]; a[i] = a[j]; a[j] = t; }
+        __syncwarp();
+        if (m > 0) lastR = rb - (int)__fns(rmask, 0, m);
+        if (m < cnt) {
+            const int Lm = lb + (int)__fns(lmask, 0, m + 1);
+            return min(Lm, lastR);
+        }
+        lmask = clear_lowest_set_bits(lmask, cnt);
+        rmask = clear_lowest_set_bits(rmask, cnt);
+    }
+}
+
+// Sort a[0..n) (shared memory) with all threads of the block.  listA/listB: room for n/16 + 2 entries each
+// (shared memory), s_cnt: 2 ints (shared), tmp: n words of scratch (global or shared).
+template <class C>
+__device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, uint2* listB, int* s_cnt, uint32_t* tmp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (tid == 0) {
+        s_cnt[0] = 0;
+        if (n > kSortThreshold) { listA[0] = make_uint2(0u, (unsigned)n | ((unsigned)(2 * floor_log2(n)) << 24)); s_cnt[0] = 1; }
+        s_cnt[1] = 0;
+    }
+    __syncthreads();
+    int cur = 0;
+    while (true) {
+        const int cntA = s_cnt[cur];
+        if (cntA == 0) break;
+        uint2* in = cur ? listB : listA;
+        uint2* out = cur ? listA : listB;
+        for (int sidx = warp; sidx < cntA; sidx += nwarps) {
+            const uint2 e = in[sidx];
+            const int first = (int)e.x, last = (int)(e.y & 0xFFFFFFu);
+            int depth = (int)(e.y >> 24);
+            if (depth == 0) {                          // depth limit hit: heap sort, no children
+                if (lane == 0) heap_sort_(c, a + first, last - first);
+                __syncwarp();
+                continue;
+            }
+            --depth;
+            if (lane == 0) median_to_first_(c, a, first, first + 1, first + (last - first) / 2, last - 1);
+            __syncwarp();
+            const int cut = warp_unguarded_partition(c, a, first, last);
+            if (lane == 0) {
+                if (last - cut > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)cut, (unsigned)last | ((unsigned)depth << 24));
+                if (cut - first > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)first, (unsigned)cut | ((unsigned)depth << 24));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_cnt[cur] = 0;
+        cur ^= 1;
+        __syncthreads();
+    }
+    // final insertion sort == stable placement inside the <= 16-element leaves
+    for (int i = tid; i < n; i += blockDim.x) {
+        const uint32_t v = a[i];
+        int pos = i;
+        const int lo = max(0, i - (kSortThreshold - 1)), hi = min(n - 1, i + (kSortThreshold - 1));
+        for (int j = lo; j < i; ++j) pos -= c.lt(v, a[j]) ? 1 : 0;
+        for (int j = i + 1; j <= hi; ++j) pos += c.lt(a[j], v) ? 1 : 0;
+        tmp[pos] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) a[i] = tmp[i];
+    __syncthreads();
+}
+#endif  // __CUDACC__
+
 // Stable order (sort_mode = 1): plain insertion-free reference used for diagnostics.
 template <bool Desc, int KeyShift>
 SVO_HD void stable_sort_seq(uint32_t* a, int n) {

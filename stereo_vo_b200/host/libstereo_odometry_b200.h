@@ -1,0 +1,196 @@
+// libstereo_odometry_b200.h -- C++ host shim with the reference's API shape
+// (libstereo-odometry/include/libstereo-odometry.h:147-1047) on top of the C-ABI include/svo_b200.h.
+//
+// The reference's public boundary is the class rso::CStereoOdometryEstimator with
+//   processNewImagePair(TStereoOdometryRequest&, TStereoOdometryResult&)      H:157-159
+//   getChangeInPose(...)                                                       H:162-172
+//   getValues(...)                                                             H:704-724
+// plus its parameter structs.  This header mirrors those names, members and defaults for the
+// FAST+ORB / smDescBF / ifmDescBF / Gauss-Newton path, but is MRPT- and OpenCV-free: this image has
+// neither.  The stand-in types below keep the field names and layouts the path
+// touches (cv::KeyPoint 28 B, cv::DMatch 16 B, TStereoCamera's fx()/cx()/rightCameraPose[0], CPose3D's
+// x()/yaw()/...), so that code written against the reference compiles against this header after
+// replacing the include; INTEGRATION.md shows the binding inside the real MRPT/OpenCV class.
+//
+// All arithmetic of the path runs in the sm_100a kernels of libsvo_b200.so; there is no CPU path here.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/svo_b200.h"
+
+namespace rso {
+
+// ---- stand-ins for the OpenCV / MRPT types the path touches ------------------------------------------
+struct Point2f { float x, y; };
+struct KeyPoint {                 // == cv::KeyPoint (28 bytes)
+    Point2f pt; float size, angle, response; int octave, class_id;
+};
+struct DMatch {                   // == cv::DMatch (16 bytes)
+    int queryIdx, trainIdx, imgIdx; float distance;
+};
+static_assert(sizeof(KeyPoint) == sizeof(svo_keypoint) && sizeof(DMatch) == sizeof(svo_dmatch), "layout");
+
+struct Mat {                      // descriptor matrix: rows x 32 bytes, CV_8U, continuous
+    int rows = 0, cols = 32;
+    std::vector<uint8_t> data;
+    const uint8_t* ptr(int r) const { return data.data() + (size_t)r * cols; }
+};
+
+struct TCamera {                  // mrpt::utils::TCamera: the accessors the path uses
+    double fx_ = 0, fy_ = 0, cx_ = 0, cy_ = 0;
+    uint32_t ncols = 0, nrows = 0;
+    double fx() const { return fx_; }
+    double fy() const { return fy_; }
+    double cx() const { return cx_; }
+    double cy() const { return cy_; }
+};
+struct TStereoCamera {            // mrpt::utils::TStereoCamera
+    TCamera leftCamera, rightCamera;
+    double rightCameraPose[7] = {0, 0, 0, 1, 0, 0, 0};   // [0] = baseline (S5:185,515)
+};
+
+struct CPose3D {                  // mrpt::poses::CPose3D: what the demo reads (demo-main.cpp:235-253)
+    double m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   // row-major homogeneous matrix
+    double ypr[3] = {0, 0, 0};
+    double x() const { return m[3]; }
+    double y() const { return m[7]; }
+    double z() const { return m[11]; }
+    double yaw() const { return ypr[0]; }
+    double pitch() const { return ypr[1]; }
+    double roll() const { return ypr[2]; }
+};
+
+struct CImage {                   // 8-bit gray view; the shim never owns or frees pixels
+    const uint8_t* data = nullptr;
+    int width = 0, height = 0;
+    size_t stride = 0;
+    size_t getRowStride() const { return stride; }
+    int getWidth() const { return width; }
+    int getHeight() const { return height; }
+};
+struct CObservationStereoImages { CImage imageLeft, imageRight; double timestamp = 0; };
+
+typedef std::vector<KeyPoint> TKeyPointList;
+typedef std::vector<DMatch> TDMatchList;
+typedef std::vector<std::pair<size_t, size_t> > vector_index_pairs_t;
+
+enum VOErrorCode { voecNone, voecBadCondNumber, voecIncrFuncCostStg1, voecIncrFuncCostStg2, voecFirstIteration, voecBadTracking };  // H:142
+
+class CStereoOdometryEstimator {
+public:
+    struct TStereoOdometryRequest {                 // H:205-233
+        const CObservationStereoImages* stereo_imgs = nullptr;
+        TStereoCamera stereo_cam;
+        bool use_precomputed_data = false;          // the reference's precomputed-data seam is broken at this commit (SURVEY B-11)
+        bool repeat = false;
+    };
+    struct TStereoOdometryResult {                  // H:235-264
+        CPose3D outPose;
+        std::vector<size_t> outliers;               // holds the INLIERS' current-match indices (S5:601-610)
+        std::vector<double> out_residual;
+        int num_it = 0, num_it_final = 0;
+        bool valid = false;
+        VOErrorCode error_code = voecNone;
+        size_t tracked_feats_from_last_KF = 0, tracked_feats_from_last_frame = 0;
+        std::vector<std::pair<size_t, size_t> > detected_feats;
+        std::vector<size_t> stereo_matches;
+    };
+    struct TGeneralParams {                         // H:266-283, process_new_image_pair.cpp:34-35
+        bool vo_use_matches_ids = false, vo_save_files = false, vo_debug = false, vo_pause_it = false;
+        std::string vo_out_dir = "out";
+    };
+    struct TInterFrameMatchingParams {              // H:285-310
+        enum TIFMMethod { ifmDescBF = 0, ifmDescWin, ifmSAD, ifmOpticalFlow };
+        TIFMMethod ifm_method = ifmDescBF;
+        bool filter_fund_matrix = true;             // the DescBF branch always filters (S4:171-259)
+    };
+    struct TLeastSquaresParams {                    // H:313-350, common.cpp:69-82
+        bool use_robust_kernel = true;
+        double kernel_param = 3.;
+        size_t max_iters = 100, initial_max_iters = 10;
+        double min_mod_out_vector = 1e-3, std_noise_pixels = 1.;
+        size_t max_incr_cost = 3;
+        double residual_threshold = 10.;
+        size_t bad_tracking_th = 5;
+        bool use_previous_pose_as_initial = true, use_custom_initial_pose = false;
+    };
+    struct TRectifyParams { int nOctaves = 1; };    // the path runs with one octave
+    struct TDetectParams {                          // H:383-447, stage2_detect.cpp:44-58
+        enum NMSMethod { nmsmStandard, nmsmAdaptive };
+        enum TDMethod { dmORB, dmFAST_ORB, dmFASTER, dmKLT };
+        TDMethod detect_method = dmFAST_ORB;        // the reference's ctor default is dmFASTER; this shim only has the hot path
+        bool non_maximal_suppression = true;
+        NMSMethod nmsMethod = nmsmStandard;
+        size_t min_distance = 3;
+        size_t orb_nfeats = 500, orb_nlevels = 8;
+        int fast_min_th = 5, fast_max_th = 30, initial_FAST_threshold = 20;
+    };
+    struct TLeftRightMatchParams {                  // H:449-499, stage3_match_left_right.cpp:46-57
+        enum TSMMethod { smDescBF = 0, smDescRbR, smSAD };
+        TSMMethod match_method = smDescBF;          // ctor default smSAD; this shim only has the hot path
+        double orb_max_distance = 40;
+        int orb_min_th = 30, orb_max_th = 100;
+        bool enable_robust_1to1_match = false, rectified_images = true;
+        double max_y_diff = 1;                      // SURVEY Appendix C (ctor default 0)
+    };
+
+    TRectifyParams params_rectify;
+    TDetectParams params_detect;
+    TLeftRightMatchParams params_lr_match;
+    TInterFrameMatchingParams params_if_match;
+    TLeastSquaresParams params_least_squares;
+    TGeneralParams params_general;
+
+    CStereoOdometryEstimator();
+    ~CStereoOdometryEstimator();
+    CStereoOdometryEstimator(const CStereoOdometryEstimator&) = delete;
+    CStereoOdometryEstimator& operator=(const CStereoOdometryEstimator&) = delete;
+
+    /** The main entry point (H:157-159).  Throws std::runtime_error on argument / device errors
+      * (the reference throws through MRPT's THROW_EXCEPTION); VO failures travel in result.error_code. */
+    void processNewImagePair(TStereoOdometryRequest& request_data, TStereoOdometryResult& result);
+
+    /** Stage 5 alone on caller data (H:162-172, common.cpp:355-413). */
+    bool getChangeInPose(const vector_index_pairs_t& tracked_pairs, const std::vector<DMatch>& pre_matches,
+                         const std::vector<DMatch>& cur_matches, const std::vector<KeyPoint>& pre_left_feats,
+                         const std::vector<KeyPoint>& pre_right_feats, const std::vector<KeyPoint>& cur_left_feats,
+                         const std::vector<KeyPoint>& cur_right_feats, const TStereoCamera& stereo_camera,
+                         TStereoOdometryResult& result, const std::vector<double>& ini_estimation = std::vector<double>(6, 0));
+
+    /** Copies of the current frame's data (H:704-724). */
+    void getValues(std::vector<KeyPoint>& leftKP, std::vector<KeyPoint>& rightKP, Mat& leftDesc, Mat& rightDesc,
+                   std::vector<DMatch>& matches, std::vector<size_t>& matches_id);
+
+    // H:529-541
+    int getFASTThreshold() const { return m_current_fast_th; }
+    void setFASTThreshold(int v) { m_current_fast_th = std::min(params_detect.fast_max_th, std::max(params_detect.fast_min_th, v)); m_dirty = true; }
+    void resetFASTThreshold() { m_current_fast_th = params_detect.initial_FAST_threshold; m_dirty = true; }
+    int getORBThreshold() const { return m_current_orb_th; }
+    void setORBThreshold(int v) { m_current_orb_th = std::min(params_lr_match.orb_max_th, std::max(params_lr_match.orb_min_th, v)); m_dirty = true; }
+    void resetORBThreshold() { m_current_orb_th = (int)params_lr_match.orb_max_distance; m_dirty = true; }
+    void setVerbosityLevel(int level) { m_verbose_level = level; }
+
+    /** Apply the param structs (what loadParamsFromConfigFile does at H:554-663, minus the INI parsing):
+      * re-reads every params_* member and resets both thresholds (H:661-662). */
+    void applyParams() { resetFASTThreshold(); resetORBThreshold(); m_dirty = true; }
+
+    /** CUDA device ordinal used by this estimator (default 0); must be set before the first call. */
+    void setDevice(int device) { m_device = device; m_dirty = true; }
+
+private:
+    void ensure_context(int width, int height);
+    static void throw_last(svo_ctx* c, const char* what);
+    svo_ctx* m_ctx = nullptr;
+    int m_w = 0, m_h = 0, m_device = 0;
+    bool m_dirty = true;
+    int m_current_fast_th = 20, m_current_orb_th = 60;   // ctor values, common.cpp:35-36
+    int m_verbose_level = 1;
+    unsigned int m_it_counter = 0;
+};
+
+}  // namespace rso
