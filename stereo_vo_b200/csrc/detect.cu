@@ -26,12 +26,10 @@ constexpr int SIN_W = TW + 2 * HALO;   // 72
 constexpr int SIN_H = TH + 2 * HALO;   // 40
 constexpr int SSC_W = TW + 4;          // score tile with halo 1, padded to 68
 constexpr int K1_THREADS = 256;
+constexpr int K1_NCAND = (TH + 2) * (TW + 2);
 
-__device__ __forceinline__ int reflect101(int i, int n) {
-    if (n == 1) return 0;
-    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
-    return i;
-}
+// one-step REFLECT_101 (|offset| <= 4 < n)
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
 // cv::getGaussianKernel(7, 2, CV_32F) bit patterns
 __device__ __forceinline__ float gk(int i) {
@@ -40,88 +38,131 @@ __device__ __forceinline__ float gk(int i) {
 }
 
 // FAST-9/16 score of the pixel at s (shared memory, row pitch SIN_W); 0 if it is not a corner.
+//   score = max over the 16 arcs of length 9 of min(d) and of min(-d), minus 1, d_k = I(p) - I(ring_k);
+//   the pixel is a corner iff score >= th (cv::FAST_t<16> + cornerScore<16>).
+// Both polarities ride in one register as 16-bit lanes {256 + d, 256 - d} (always positive, so one IMAD
+// per ring pixel builds the pair: r * -K + (v * K + C) with K = 1 - 65536); the sliding 9-window minima
+// then need 16-bit SIMD min/max only (DPX: VIMNMX.S16x2 / VIMNMX3.S16x2).
+// NOTE: the obvious scalar form `best = max(best, max(lo9, -hi9))` is miscompiled by ptxas 12.9
+// (-O1 and above, also by the driver JIT): wrong scores on sm_100a, correct with -Xptxas -O0.
 __device__ __forceinline__ int fast9_score(const uint8_t* __restrict__ s, int th) {
-    const int v = s[0];
-    int d[16];
-    d[0] = v - s[3 * SIN_W + 0];   d[1] = v - s[3 * SIN_W + 1];   d[2] = v - s[2 * SIN_W + 2];   d[3] = v - s[1 * SIN_W + 3];
-    d[4] = v - s[3];               d[5] = v - s[-1 * SIN_W + 3];  d[6] = v - s[-2 * SIN_W + 2];  d[7] = v - s[-3 * SIN_W + 1];
-    d[8] = v - s[-3 * SIN_W + 0];  d[9] = v - s[-3 * SIN_W - 1];  d[10] = v - s[-2 * SIN_W - 2]; d[11] = v - s[-1 * SIN_W - 3];
-    d[12] = v - s[-3];             d[13] = v - s[1 * SIN_W - 3];  d[14] = v - s[2 * SIN_W - 2];  d[15] = v - s[3 * SIN_W - 1];
-    unsigned dark = 0, bright = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        dark |= (unsigned)(d[k] > th) << k;
-        bright |= (unsigned)(d[k] < -th) << k;
-    }
-    // 9 contiguous set bits on the 16-ring
-    dark |= dark << 16;
-    bright |= bright << 16;
-    unsigned t = dark & (dark >> 1);
-    t &= t >> 2; t &= t >> 4; t &= dark >> 8;
-    unsigned u = bright & (bright >> 1);
-    u &= u >> 2; u &= u >> 4; u &= bright >> 8;
-    if (((t | u) & 0xFFFFu) == 0) return 0;
-    // score = max over the 16 arcs of length 9 of min(d) and of min(-d), minus 1.
-    // Both polarities ride in one register as signed 16-bit lanes {d, -d} (|d| <= 255), so the sliding
-    // 9-window minima need 16-bit SIMD min/max only (DPX: VIMNMX.S16x2 / VIMNMX3.S16x2).
-    // NOTE: the obvious scalar form `best = max(best, max(lo9, -hi9))` is miscompiled by ptxas 12.9
-    // (-O1 and above, also by the driver JIT): wrong scores on sm_100a, correct with -Xptxas -O0.
-    // This formulation was checked on the device against the scalar definition (tests/test_gpu_parity.py).
+    constexpr unsigned K = 0xFFFF0001u;                      // 1 - 65536
+    const unsigned cv = (unsigned)s[0] * K + 0x01000100u;    // {256 + v, 256 - v}
     unsigned p[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) p[k] = ((unsigned)d[k] & 0xFFFFu) | ((unsigned)(-d[k]) << 16);
+    p[0] = cv - (unsigned)s[3 * SIN_W + 0] * K;   p[1] = cv - (unsigned)s[3 * SIN_W + 1] * K;
+    p[2] = cv - (unsigned)s[2 * SIN_W + 2] * K;   p[3] = cv - (unsigned)s[1 * SIN_W + 3] * K;
+    p[4] = cv - (unsigned)s[3] * K;               p[5] = cv - (unsigned)s[-1 * SIN_W + 3] * K;
+    p[6] = cv - (unsigned)s[-2 * SIN_W + 2] * K;  p[7] = cv - (unsigned)s[-3 * SIN_W + 1] * K;
+    p[8] = cv - (unsigned)s[-3 * SIN_W + 0] * K;  p[9] = cv - (unsigned)s[-3 * SIN_W - 1] * K;
+    p[10] = cv - (unsigned)s[-2 * SIN_W - 2] * K; p[11] = cv - (unsigned)s[-1 * SIN_W - 3] * K;
+    p[12] = cv - (unsigned)s[-3] * K;             p[13] = cv - (unsigned)s[1 * SIN_W - 3] * K;
+    p[14] = cv - (unsigned)s[2 * SIN_W - 2] * K;  p[15] = cv - (unsigned)s[3 * SIN_W - 1] * K;
     unsigned lo2[16], lo4[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) lo2[k] = __vmins2(p[k], p[(k + 1) & 15]);
 #pragma unroll
     for (int k = 0; k < 16; ++k) lo4[k] = __vmins2(lo2[k], lo2[(k + 2) & 15]);
-    unsigned best = 0x80008000u;   // (-32768, -32768)
+    unsigned best = 0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) best = __vmaxs2(best, __vimin3_s16x2(lo4[k], lo4[(k + 4) & 15], p[(k + 8) & 15]));
-    const int a = (short)(best & 0xFFFFu), b = (short)(best >> 16);
-    return max(a, b) - 1;
+    const int sc = max((int)(best & 0xFFFFu), (int)(best >> 16)) - 257;
+    return sc >= th ? sc : 0;
+}
+
+// Necessary condition for a FAST-9 corner: every arc of 9 contains two adjacent compass points
+// (ring 0,4,8,12), so two adjacent compass points must both be darker (or both brighter) than the centre
+// by more than th.  Only pixels passing this test get the full score.
+__device__ __forceinline__ bool fast_pretest(const uint8_t* __restrict__ s, int th) {
+    const int v = s[0];
+    const int d0 = v - s[3 * SIN_W], d4 = v - s[3], d8 = v - s[-3 * SIN_W], d12 = v - s[-3];
+    const bool a0 = d0 > th, a4 = d4 > th, a8 = d8 > th, a12 = d12 > th;
+    const bool b0 = d0 < -th, b4 = d4 < -th, b8 = d8 < -th, b12 = d12 < -th;
+    return (a0 && a4) || (a4 && a8) || (a8 && a12) || (a12 && a0) || (b0 && b4) || (b4 && b8) || (b8 && b12) || (b12 && b0);
 }
 
 __global__ void __launch_bounds__(K1_THREADS)
 fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __restrict__ imgR,
                  size_t stride, size_t image_pitch, int pitch_out) {
     __shared__ __align__(16) uint8_t s_in[SIN_H * SIN_W];
-    __shared__ float s_row[(TH + 6) * TW];
-    __shared__ __align__(4) uint8_t s_sc[(TH + 2) * SSC_W];
+    __shared__ __align__(16) float s_row[(TH + 6) * TW];
+    __shared__ __align__(16) uint8_t s_sc[(TH + 2) * SSC_W];
+    __shared__ uint16_t s_list[K1_NCAND];
+    __shared__ int s_nlist;
 
     const int W = P.p.W, H = P.p.H;
     const int item = blockIdx.z >> 1, side = blockIdx.z & 1;
     const int slot = P.slots[item];
     const uint8_t* __restrict__ img = (side ? imgR : imgL) + (size_t)item * image_pitch;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
 
-    // 1. stage the tile with halo 4 (REFLECT_101 outside the image, only the blur looks there)
-    for (int i = tid; i < SIN_H * SIN_W; i += K1_THREADS) {
-        const int r = i / SIN_W, c = i - r * SIN_W;
-        const int gy = reflect101(y0 - HALO + r, H), gx = reflect101(x0 - HALO + c, W);
-        s_in[i] = __ldg(img + (size_t)gy * stride + gx);
+    // 1. stage the tile with halo 4 as 32-bit words (REFLECT_101 outside the image: only the blur looks there)
+    {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(img) | stride) & 3) == 0;
+        uint32_t* s_w = reinterpret_cast<uint32_t*>(s_in);
+        for (int w = tid; w < SIN_H * (SIN_W / 4); w += K1_THREADS) {
+            const int r = w / (SIN_W / 4), cw = w - r * (SIN_W / 4);
+            const int gy = reflect1(y0 - HALO + r, H), gx0 = x0 - HALO + 4 * cw;
+            const uint8_t* row = img + (size_t)gy * stride;
+            uint32_t v;
+            if (aligned && gx0 >= 0 && gx0 + 3 < W) {
+                v = __ldg(reinterpret_cast<const uint32_t*>(row + gx0));
+            } else {
+                v = (uint32_t)__ldg(row + reflect1(gx0, W)) | ((uint32_t)__ldg(row + reflect1(gx0 + 1, W)) << 8) |
+                    ((uint32_t)__ldg(row + reflect1(gx0 + 2, W)) << 16) | ((uint32_t)__ldg(row + reflect1(gx0 + 3, W)) << 24);
+            }
+            s_w[w] = v;
+        }
+        uint32_t* s_z = reinterpret_cast<uint32_t*>(s_sc);
+        for (int w = tid; w < (TH + 2) * SSC_W / 4; w += K1_THREADS) s_z[w] = 0;
+        if (tid == 0) s_nlist = 0;
     }
     __syncthreads();
 
-    // 2. blur, row pass: rows y0-3 .. y0+TH+2  (float32, sequential FMA left to right)
-    for (int i = tid; i < (TH + 6) * TW; i += K1_THREADS) {
-        const int r = i / TW, c = i - r * TW;
-        const uint8_t* p = s_in + (r + 1) * SIN_W + c + 1;   // column x-3
-        float acc = __fmul_rn(gk(0), (float)p[0]);
+    // 2. blur, row pass: rows y0-3 .. y0+TH+2, four outputs per work item (float32, sequential FMA left to right)
+    for (int i = tid; i < (TH + 6) * (TW / 4); i += K1_THREADS) {
+        const int r = i / (TW / 4), c = (i - r * (TW / 4)) * 4;
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(s_in + (r + 1) * SIN_W + c);   // bytes c .. c+11
+        const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
+        float f[10];                                   // columns c+1 .. c+10  (x-3 .. x+6 of the first output)
+        f[0] = (float)((w0 >> 8) & 0xFF); f[1] = (float)((w0 >> 16) & 0xFF); f[2] = (float)(w0 >> 24);
+        f[3] = (float)(w1 & 0xFF); f[4] = (float)((w1 >> 8) & 0xFF); f[5] = (float)((w1 >> 16) & 0xFF); f[6] = (float)(w1 >> 24);
+        f[7] = (float)(w2 & 0xFF); f[8] = (float)((w2 >> 8) & 0xFF); f[9] = (float)((w2 >> 16) & 0xFF);
+        float4 o;
+        float* op = &o.x;
 #pragma unroll
-        for (int t = 1; t < 7; ++t) acc = __fmaf_rn(gk(t), (float)p[t], acc);
-        s_row[i] = acc;
+        for (int q = 0; q < 4; ++q) {
+            float acc = __fmul_rn(gk(0), f[q]);
+#pragma unroll
+            for (int t = 1; t < 7; ++t) acc = __fmaf_rn(gk(t), f[q + t], acc);
+            op[q] = acc;
+        }
+        *reinterpret_cast<float4*>(s_row + r * TW + c) = o;
     }
-    // 3. FAST score on the tile plus a 1-px ring (needed by the 3x3 NMS)
+    // 3a. FAST pre-test on the tile plus a 1-px ring (needed by the 3x3 NMS): collect candidates
     const int th = P.p.fast_th;
-    for (int i = tid; i < (TH + 2) * (TW + 2); i += K1_THREADS) {
+    for (int i0 = 0; i0 < K1_NCAND; i0 += K1_THREADS) {
+        const int i = i0 + tid;
+        bool cand = false;
+        if (i < K1_NCAND) {
+            const int r = i / (TW + 2), c = i - r * (TW + 2);
+            const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+            if (gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3)
+                cand = fast_pretest(s_in + (r + HALO - 1) * SIN_W + (c + HALO - 1), th);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_nlist, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (cand) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+    }
+    __syncthreads();
+    // 3b. full score for the candidates only (dense over the CTA)
+    const int nlist = s_nlist;
+    for (int q = tid; q < nlist; q += K1_THREADS) {
+        const int i = s_list[q];
         const int r = i / (TW + 2), c = i - r * (TW + 2);
-        const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-        int sc = 0;
-        if (gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3)
-            sc = fast9_score(s_in + (r + HALO - 1) * SIN_W + (c + HALO - 1), th);
-        s_sc[r * SSC_W + c] = (uint8_t)sc;
+        s_sc[r * SSC_W + c] = (uint8_t)fast9_score(s_in + (r + HALO - 1) * SIN_W + (c + HALO - 1), th);
     }
     __syncthreads();
 
@@ -133,25 +174,36 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
         const int gy = y0 + r, gx = x0 + c4;
         if (gy >= H || gx >= pitch_out) continue;
         uint32_t bw = 0, sw = 0;
+        const float* rr0 = s_row + (r + 3) * TW + c4;
+        const float4 m0 = *reinterpret_cast<const float4*>(rr0);
+        const float4 p1 = *reinterpret_cast<const float4*>(rr0 + TW), n1 = *reinterpret_cast<const float4*>(rr0 - TW);
+        const float4 p2 = *reinterpret_cast<const float4*>(rr0 + 2 * TW), n2 = *reinterpret_cast<const float4*>(rr0 - 2 * TW);
+        const float4 p3 = *reinterpret_cast<const float4*>(rr0 + 3 * TW), n3 = *reinterpret_cast<const float4*>(rr0 - 3 * TW);
+        const float c0[4] = {m0.x, m0.y, m0.z, m0.w};
+        const float a1[4] = {p1.x, p1.y, p1.z, p1.w}, b1[4] = {n1.x, n1.y, n1.z, n1.w};
+        const float a2[4] = {p2.x, p2.y, p2.z, p2.w}, b2[4] = {n2.x, n2.y, n2.z, n2.w};
+        const float a3[4] = {p3.x, p3.y, p3.z, p3.w}, b3[4] = {n3.x, n3.y, n3.z, n3.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int c = c4 + q;
-            const float* rr = s_row + (r + 3) * TW + c;
-            float acc = __fmul_rn(gk(3), rr[0]);
-#pragma unroll
-            for (int j = 1; j <= 3; ++j) acc = __fmaf_rn(gk(3 + j), __fadd_rn(rr[j * TW], rr[-j * TW]), acc);
+            float acc = __fmul_rn(gk(3), c0[q]);
+            acc = __fmaf_rn(gk(4), __fadd_rn(a1[q], b1[q]), acc);
+            acc = __fmaf_rn(gk(5), __fadd_rn(a2[q], b2[q]), acc);
+            acc = __fmaf_rn(gk(6), __fadd_rn(a3[q], b3[q]), acc);
             int v = __float2int_rn(acc);   // round half to even
             v = min(255, max(0, v));
             bw |= (uint32_t)v << (8 * q);
+            const int c = c4 + q;
             const uint8_t* sp = s_sc + (r + 1) * SSC_W + (c + 1);
             const int s = sp[0];
-            const int x = gx + q;
-            bool keep = s > 0 && x >= kOrbEdge && x < W - kOrbEdge && gy >= kOrbEdge && gy < H - kOrbEdge;
-            if (keep) {
-                keep = s > sp[-SSC_W - 1] && s > sp[-SSC_W] && s > sp[-SSC_W + 1] && s > sp[-1] && s > sp[1] &&
-                       s > sp[SSC_W - 1] && s > sp[SSC_W] && s > sp[SSC_W + 1];
+            if (s > 0) {
+                const int x = gx + q;
+                bool keep = x >= kOrbEdge && x < W - kOrbEdge && gy >= kOrbEdge && gy < H - kOrbEdge;
+                if (keep) {
+                    keep = s > sp[-SSC_W - 1] && s > sp[-SSC_W] && s > sp[-SSC_W + 1] && s > sp[-1] && s > sp[1] &&
+                           s > sp[SSC_W - 1] && s > sp[SSC_W] && s > sp[SSC_W + 1];
+                }
+                sw |= (uint32_t)(keep ? s : 0) << (8 * q);
             }
-            sw |= (uint32_t)(keep ? s : 0) << (8 * q);
         }
         *reinterpret_cast<uint32_t*>(blur_out + (size_t)gy * pitch_out + gx) = bw;
         *reinterpret_cast<uint32_t*>(score_out + (size_t)gy * pitch_out + gx) = sw;
@@ -221,6 +273,7 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
     __shared__ int s_warp[K2_THREADS / 32];
     __shared__ int s_nsel;
     __shared__ int s_cnt2[2];
+    __shared__ int s_pos[64 * (K2_THREADS / 32)];
     uint32_t* tmp = sort_scratch + (size_t)blockIdx.x * P.p.max_corners;
 
     const int W = P.p.W, H = P.p.H;
@@ -287,7 +340,7 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
 
     if (P.p.nms) {
         // ---- B. sort by response, descending (KeypointResponseSorter) ------------------------------
-        if (P.p.sort_mode == 0) introsort_block(KeyComp<true, 24>(), s_a, n, s_listA, s_listB, s_cnt2, tmp);
+        if (P.p.sort_mode == 0) introsort_block(KeyComp<true, 24>(), s_a, n, s_listA, s_listB, s_cnt2, tmp, s_pos);
         else block_stable_sort<true, 24>(s_a, tmp, n);
         // ---- C. greedy occupancy grid ---------------------------------------------------------------
         const unsigned cell = (unsigned)(P.p.min_distance / 2.0);     // S2:331
@@ -332,7 +385,7 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
         s_b[k] = (pos & 0xFFFF0000u) | (uint32_t)k;   // y << 16 | position in the selection order
     }
     __syncthreads();
-    if (P.p.sort_mode == 0) introsort_block(KeyComp<false, 16>(), s_b, n_sel, s_listA, s_listB, s_cnt2, tmp);
+    if (P.p.sort_mode == 0) introsort_block(KeyComp<false, 16>(), s_b, n_sel, s_listA, s_listB, s_cnt2, tmp, s_pos);
     else block_stable_sort<false, 16>(s_b, tmp, n_sel);
     // ---- E. emit ------------------------------------------------------------------------------------
     for (int i = tid; i < n_sel; i += K2_THREADS) {

@@ -194,60 +194,68 @@ SVO_HD void introsort_seq(uint32_t* a, int n) {
 //    leaf segment, so an element's final position is  i - #{j in [i-15,i): comp(a[i],a[j])}
 //    + #{j in (i,i+15]: comp(a[j],a[i])}: computed by all threads at once.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned clear_lowest_set_bits(unsigned mask, int c) {
-    if (c <= 0) return mask;
-    const unsigned pos = __fns(mask, 0, c);          // position of the c-th set bit (1-based)
-    return pos >= 31u ? 0u : (mask & (0xFFFFFFFFu << (pos + 1)));
-}
-
 // Partition a[seg_first .. seg_last) around the pivot already placed at a[seg_first]; all 32 lanes call it.
+// s_pos: 64 ints of shared scratch private to the calling warp (rank -> position tables of one chunk pair).
 template <class C>
-__device__ int warp_unguarded_partition(const C& c, uint32_t* a, int seg_first, int seg_last) {
+__device__ int warp_unguarded_partition(const C& c, uint32_t* a, int seg_first, int seg_last, int* s_pos) {
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t pivot = a[seg_first];
+    int* posL = s_pos;          // posL[k] = position of the k-th pending left stopper
+    int* posR = s_pos + 32;     // posR[k] = position of the k-th pending right stopper
+    int nl = 0, nr = 0;         // pending stoppers; the tables are consumed from index kl / kr upwards
+    int kl = 0, kr = 0;
     int lb = seg_first + 1 - 32, rb = seg_last - 1 + 32;
-    unsigned lmask = 0, rmask = 0;
     int lastR = 0x7FFFFFFF;
     while (true) {
-        if (lmask == 0) {
+        if (kl == nl) {          // left table exhausted: next chunk
             lb += 32;
             const int x = lb + lane;
             const bool stop = (x >= seg_last) ? true : !c.lt(a[x], pivot);
-            lmask = __ballot_sync(0xffffffffu, stop);
+            const unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (stop) posL[__popc(m & lt_mask)] = x;
+            nl = __popc(m);
+            kl = 0;
         }
-        if (rmask == 0) {
+        if (kr == nr) {
             rb -= 32;
             const int x = rb - lane;
             const bool stop = (x < seg_first) ? true : !c.lt(pivot, a[x]);
-            rmask = __ballot_sync(0xffffffffu, stop);
+            const unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (stop) posR[__popc(m & lt_mask)] = x;
+            nr = __popc(m);
+            kr = 0;
         }
-        if (lmask == 0 || rmask == 0) continue;
-        const int cnt = min(__popc(lmask), __popc(rmask));
+        __syncwarp();
+        if (nl == 0 || nr == 0) continue;
+        const int cnt = min(nl - kl, nr - kr);
         int i = 0, j = 0;
         bool ok = false;
         if (lane < cnt) {
-            i = lb + (int)__fns(lmask, 0, lane + 1);
-            j = rb - (int)__fns(rmask, 0, lane + 1);
+            i = posL[kl + lane];
+            j = posR[kr + lane];
             ok = i < j;
         }
         const unsigned okmask = __ballot_sync(0xffffffffu, ok);
         const int m = __popc(okmask);            // the pairs with i < j form a prefix
         if (ok) { const uint32_t t = a[i]; a[i] = a[j]; a[j] = t; }
-        __syncwarp();
-        if (m > 0) lastR = rb - (int)__fns(rmask, 0, m);
+        if (m > 0) lastR = posR[kr + m - 1];
         if (m < cnt) {
-            const int Lm = lb + (int)__fns(lmask, 0, m + 1);
+            const int Lm = posL[kl + m];
+            __syncwarp();
             return min(Lm, lastR);
         }
-        lmask = clear_lowest_set_bits(lmask, cnt);
-        rmask = clear_lowest_set_bits(rmask, cnt);
+        kl += cnt;
+        kr += cnt;
+        __syncwarp();
     }
 }
 
 // Sort a[0..n) (shared memory) with all threads of the block.  listA/listB: room for n/16 + 2 entries each
-// (shared memory), s_cnt: 2 ints (shared), tmp: n words of scratch (global or shared).
+// (shared memory), s_cnt: 2 ints (shared), tmp: n words of scratch (global or shared), s_pos: 64 ints per warp.
 template <class C>
-__device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, uint2* listB, int* s_cnt, uint32_t* tmp) {
+__device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, uint2* listB, int* s_cnt, uint32_t* tmp,
+                                int* s_pos /* 64 ints per warp, shared */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     if (tid == 0) {
         s_cnt[0] = 0;
@@ -273,7 +281,7 @@ __device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, ui
             --depth;
             if (lane == 0) median_to_first_(c, a, first, first + 1, first + (last - first) / 2, last - 1);
             __syncwarp();
-            const int cut = warp_unguarded_partition(c, a, first, last);
+            const int cut = warp_unguarded_partition(c, a, first, last, s_pos + 64 * warp);
             if (lane == 0) {
                 if (last - cut > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)cut, (unsigned)last | ((unsigned)depth << 24));
                 if (cut - first > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)first, (unsigned)cut | ((unsigned)depth << 24));
