@@ -134,6 +134,16 @@ int svo_process_batch(svo_ctx* ctx, int32_t n, const int32_t* slots,
                       const uint8_t* const* left, const uint8_t* const* right, size_t stride_bytes,
                       const svo_camera* cams, const uint8_t* repeat, svo_result* results);
 
+/* The same step split in two for pipelining: svo_submit_batch enqueues the host->device copies (on a
+ * copy stream), the kernels and the device->host copy of the results and returns at once; svo_wait_batch
+ * blocks until the OLDEST submitted batch is complete and writes its results (in the order of that
+ * batch's slot list).  At most two batches may be in flight, so the copies of batch t+1 overlap the
+ * kernels of batch t.  The host image buffers must stay valid (and should be pinned) until the wait. */
+int svo_submit_batch(svo_ctx* ctx, int32_t n, const int32_t* slots,
+                     const uint8_t* const* left, const uint8_t* const* right, size_t stride_bytes,
+                     const svo_camera* cams, const uint8_t* repeat);
+int svo_wait_batch(svo_ctx* ctx, svo_result* results);
+
 /* Same, images already resident in device memory (HBM): d_left/d_right point to n images each,
  * image i at d_left + i*image_pitch_bytes, rows `stride_bytes` apart.  Results stay on the device
  * until svo_fetch_results(); the call only enqueues work on the context's stream. */

@@ -26,7 +26,7 @@ VOEC = {"voecNone": 0, "voecBadCondNumber": 1, "voecIncrFuncCostStg1": 2, "voecI
 # every symbol declared in include/svo_b200.h (checked by tests/test_capi_symbols.py)
 EXPORTS = [
     "svo_default_config", "svo_create", "svo_destroy", "svo_last_error", "svo_reset_slot",
-    "svo_process_batch", "svo_process_batch_device", "svo_fetch_results", "svo_synchronize", "svo_process_pair",
+    "svo_process_batch", "svo_submit_batch", "svo_wait_batch", "svo_process_batch_device", "svo_fetch_results", "svo_synchronize", "svo_process_pair",
     "svo_get_keypoints", "svo_get_descriptors", "svo_get_matches", "svo_get_match_ids", "svo_get_tracked_pairs",
     "svo_get_residuals", "svo_get_outliers", "svo_get_track_candidates", "svo_get_plane",
     "svo_detect", "svo_match_hamming", "svo_match_hamming_device", "svo_match_lr", "svo_get_change_in_pose",
@@ -68,6 +68,9 @@ def build(verbose=False):
         raise RuntimeError("building libsvo_b200.so failed:\n" + out.stdout + out.stderr)
     if verbose:
         print(out.stdout)
+    host = subprocess.run(["make", "-C", os.path.join(_HERE, "host")], capture_output=True, text=True)
+    if host.returncode != 0:
+        raise RuntimeError("building the host shim failed:\n" + host.stdout + host.stderr)
     return LIB_PATH
 
 
@@ -164,6 +167,26 @@ class Context:
         rep = None if repeat is None else (C.c_uint8 * n)(*[1 if r else 0 for r in repeat])
         res = (Result * n)()
         self._check(lib().svo_process_batch(self._h, n, sl, lp, rp, C.c_size_t(W), cam_arr, rep, res))
+        return list(res)
+
+    def submit_batch(self, left, right, cams, slots=None, repeat=None):
+        """Asynchronous half of process_batch; keeps the host arrays alive until wait_batch."""
+        L = [np.ascontiguousarray(a, np.uint8) for a in left]
+        R = [np.ascontiguousarray(a, np.uint8) for a in right]
+        n = len(L)
+        W = L[0].shape[1]
+        lp = (C.c_void_p * n)(*[a.ctypes.data for a in L])
+        rp = (C.c_void_p * n)(*[a.ctypes.data for a in R])
+        cam_arr = (Camera * n)(*cams)
+        sl = None if slots is None else (C.c_int32 * n)(*slots)
+        rep = None if repeat is None else (C.c_uint8 * n)(*[1 if r else 0 for r in repeat])
+        self._check(lib().svo_submit_batch(self._h, n, sl, lp, rp, C.c_size_t(W), cam_arr, rep))
+        self._inflight = getattr(self, "_inflight", []) + [(L, R, n)]
+
+    def wait_batch(self):
+        L, R, n = self._inflight.pop(0)
+        res = (Result * n)()
+        self._check(lib().svo_wait_batch(self._h, res))
         return list(res)
 
     def process_pair(self, left, right, cam, repeat=False):

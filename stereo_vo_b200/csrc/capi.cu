@@ -41,8 +41,20 @@ struct svo_ctx {
     int n_slots_alloc = 0;      // max_seqs + 1 (the last slot serves the per-stage entry points)
     int hidden_slot = 0;
     int pitch = 0;              // row pitch of the internal image planes (W rounded up to 16)
-    uint8_t* d_stageL = nullptr;
+    uint8_t* d_stageL = nullptr;      // == d_stL[0] (used by the synchronous per-stage entries)
     uint8_t* d_stageR = nullptr;
+    // two-deep submit/wait pipeline: staging images, pinned meta/result rings, events
+    cudaStream_t copy_stream = nullptr;
+    uint8_t* d_stL[2] = {nullptr, nullptr};
+    uint8_t* d_stR[2] = {nullptr, nullptr};
+    int32_t* r_slots[2] = {nullptr, nullptr};
+    uint8_t* r_repeat[2] = {nullptr, nullptr};
+    Camera* r_cams[2] = {nullptr, nullptr};
+    Result* r_res[2] = {nullptr, nullptr};
+    SlotState* r_state[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    int pend_n[2] = {0, 0}, pend_lo[2] = {0, 0}, pend_hi[2] = {0, 0};
+    int pend_head = 0, pend_count = 0;
     uint8_t* d_repeat = nullptr;
     Camera* d_cams_batch = nullptr;
     uint32_t* d_occ = nullptr;
@@ -265,7 +277,8 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     DA(P.lr_best, S * cap); DA(P.tr_best, S * 2 * cap); DA(P.tcand, S * cap); DA(P.n_tcand, S);
     DA(P.inl, S * 2 * cap); DA(P.n_inl, S * 2); DA(P.tracked, S * cap); DA(P.n_tracked, S);
     DA(P.residual, S * cap); DA(P.outliers, S * cap); DA(P.slots, S);
-    DA(c->d_stageL, (size_t)S * plane); DA(c->d_stageR, (size_t)S * plane);
+    for (int b = 0; b < 2; ++b) { DA(c->d_stL[b], (size_t)S * plane); DA(c->d_stR[b], (size_t)S * plane); }
+    c->d_stageL = c->d_stL[0]; c->d_stageR = c->d_stR[0];
     DA(c->d_repeat, S); DA(c->d_cams_batch, S);
     // occupancy grids (only touched when uint(min_distance/2) != 1): worst case 1-px... cells >= 2 px
     {
@@ -288,9 +301,15 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
         c->RS.slots = P.slots; c->RS.inl = P.inl; c->RS.n_inl = P.n_inl;
     }
     HA(c->h_slots, S); HA(c->h_repeat, S); HA(c->h_cams, S); HA(c->h_results, S);
+    for (int b = 0; b < 2; ++b) { HA(c->r_slots[b], S); HA(c->r_repeat[b], S); HA(c->r_cams[b], S); HA(c->r_res[b], S); HA(c->r_state[b], S); }
 #undef DA
 #undef HA
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { int rc = cuda_fail(nullptr, e, "cudaStreamCreate"); svo_destroy(c); return rc; }
     if ((e = configure_detect(p)) != cudaSuccess || (e = configure_match(p)) != cudaSuccess ||
         (e = configure_gn(p)) != cudaSuccess || (e = configure_ransac(kp_cap)) != cudaSuccess) {
@@ -308,6 +327,8 @@ void svo_destroy(svo_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int b = 0; b < 2; ++b) { if (c->ev_h2d[b]) cudaEventDestroy(c->ev_h2d[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (void* p : c->dev_allocs) cudaFree(p);
     for (void* p : c->host_allocs) cudaFreeHost(p);
@@ -403,34 +424,86 @@ int svo_fetch_results(svo_ctx* c, int32_t n, const int32_t* slots, svo_result* r
     return rc;
 }
 
-int svo_process_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t* const* left,
-                      const uint8_t* const* right, size_t stride, const svo_camera* cams, const uint8_t* repeat,
-                      svo_result* results) {
+int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t* const* left,
+                     const uint8_t* const* right, size_t stride, const svo_camera* cams, const uint8_t* repeat) {
     if (!c) return SVO_ERR_ARG;
-    if (!left || !right || !results) return fail(c, SVO_ERR_ARG, "NULL argument");
+    if (!left || !right || !cams) return fail(c, SVO_ERR_ARG, "NULL argument");
     if (stride < (size_t)c->cfg.width) return fail(c, SVO_ERR_ARG, "stride smaller than the image width");
+    if (n <= 0 || n > c->cfg.max_seqs) return fail(c, SVO_ERR_ARG, "batch size out of range");
+    if (c->pend_count == 2) return fail(c, SVO_ERR_STATE, "two batches are already in flight: call svo_wait_batch first");
     CU(c, cudaSetDevice(c->cfg.device));
-    int rc = upload_batch_meta(c, n, slots, cams, repeat);
-    if (rc != SVO_OK) return rc;
+    const int b = (c->pend_head + c->pend_count) & 1;
+    std::vector<char> seen(c->cfg.max_seqs, 0);
+    int lo = c->cfg.max_seqs, hi = -1;
+    for (int i = 0; i < n; ++i) {
+        const int s = slots ? slots[i] : i;
+        if (!valid_slot(c, s)) return fail(c, SVO_ERR_ARG, "slot index out of range");
+        if (seen[s]) return fail(c, SVO_ERR_ARG, "duplicate slot in one batch");
+        if (!left[i] || !right[i]) return fail(c, SVO_ERR_ARG, "image pointer is NULL");
+        seen[s] = 1;
+        c->r_slots[b][i] = s;
+        memcpy(&c->r_cams[b][i], &cams[i], sizeof(Camera));
+        c->r_repeat[b][i] = repeat ? repeat[i] : 0;
+        lo = std::min(lo, s); hi = std::max(hi, s);
+    }
     const int W = c->cfg.width, H = c->cfg.height;
     const size_t plane = (size_t)c->pitch * H;
-    // contiguous batches go up in one copy per side
+    // images: host -> staging buffer b on the copy stream (overlaps the kernels of the previous batch)
     bool contig = true;
     for (int i = 1; i < n && contig; ++i)
         contig = left[i] == left[0] + (size_t)i * stride * H && right[i] == right[0] + (size_t)i * stride * H;
     if (contig && stride == (size_t)c->pitch) {
-        CU(c, cudaMemcpyAsync(c->d_stageL, left[0], plane * n, cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemcpyAsync(c->d_stageR, right[0], plane * n, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_stL[b], left[0], plane * n, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaMemcpyAsync(c->d_stR[b], right[0], plane * n, cudaMemcpyHostToDevice, c->copy_stream));
     } else {
         for (int i = 0; i < n; ++i) {
-            if (!left[i] || !right[i]) return fail(c, SVO_ERR_ARG, "image pointer is NULL");
-            CU(c, cudaMemcpy2DAsync(c->d_stageL + i * plane, c->pitch, left[i], stride, W, H, cudaMemcpyHostToDevice, c->stream));
-            CU(c, cudaMemcpy2DAsync(c->d_stageR + i * plane, c->pitch, right[i], stride, W, H, cudaMemcpyHostToDevice, c->stream));
+            CU(c, cudaMemcpy2DAsync(c->d_stL[b] + i * plane, c->pitch, left[i], stride, W, H, cudaMemcpyHostToDevice, c->copy_stream));
+            CU(c, cudaMemcpy2DAsync(c->d_stR[b] + i * plane, c->pitch, right[i], stride, W, H, cudaMemcpyHostToDevice, c->copy_stream));
         }
     }
-    rc = run_step(c, n, c->d_stageL, c->d_stageR, c->pitch, plane, repeat != nullptr);
+    CU(c, cudaEventRecord(c->ev_h2d[b], c->copy_stream));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+    CU(c, cudaMemcpyAsync(c->P.slots, c->r_slots[b], n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_cams_batch, c->r_cams[b], n * sizeof(Camera), cudaMemcpyHostToDevice, c->stream));
+    if (repeat) CU(c, cudaMemcpyAsync(c->d_repeat, c->r_repeat[b], n, cudaMemcpyHostToDevice, c->stream));
+    int rc = run_step(c, n, c->d_stL[b], c->d_stR[b], c->pitch, plane, repeat != nullptr);
     if (rc != SVO_OK) return rc;
-    return svo_fetch_results(c, n, slots, results);
+    CU(c, cudaMemcpyAsync(c->r_res[b] + lo, c->P.result + lo, (size_t)(hi - lo + 1) * sizeof(Result), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(c->r_state[b] + lo, c->P.state + lo, (size_t)(hi - lo + 1) * sizeof(SlotState), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaEventRecord(c->ev_done[b], c->stream));
+    c->pend_n[b] = n; c->pend_lo[b] = lo; c->pend_hi[b] = hi;
+    ++c->pend_count;
+    return SVO_OK;
+}
+
+int svo_wait_batch(svo_ctx* c, svo_result* results) {
+    if (!c || !results) return SVO_ERR_ARG;
+    if (c->pend_count == 0) return fail(c, SVO_ERR_STATE, "no batch in flight");
+    const int b = c->pend_head;
+    CU(c, cudaEventSynchronize(c->ev_done[b]));
+    int rc = SVO_OK;
+    for (int i = 0; i < c->pend_n[b]; ++i) {
+        const int s = c->r_slots[b][i];
+        memcpy(&results[i], &c->r_res[b][s], sizeof(svo_result));
+        const int st = c->r_state[b][s].status;
+        results[i].status = st;
+        if (st != 0) { results[i].valid = 0; rc = st; }
+    }
+    c->pend_head ^= 1;
+    --c->pend_count;
+    if (rc == SVO_ERR_CAPACITY) return fail(c, rc, "max_corners exceeded for at least one image (raise svo_config.max_corners)");
+    return rc;
+}
+
+int svo_process_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t* const* left,
+                      const uint8_t* const* right, size_t stride, const svo_camera* cams, const uint8_t* repeat,
+                      svo_result* results) {
+    if (!c) return SVO_ERR_ARG;
+    if (!results) return fail(c, SVO_ERR_ARG, "NULL argument");
+    if (c->pend_count != 0) return fail(c, SVO_ERR_STATE, "batches submitted with svo_submit_batch are still in flight");
+    const int rc = svo_submit_batch(c, n, slots, left, right, stride, cams, repeat);
+    if (rc != SVO_OK) return rc;
+    return svo_wait_batch(c, results);
 }
 
 int svo_process_pair(svo_ctx* c, const uint8_t* left, const uint8_t* right, size_t stride, const svo_camera* cam,

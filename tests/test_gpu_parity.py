@@ -428,6 +428,24 @@ def test_batch_of_sequences_equals_sequences_alone(ctx_c1):
             assert got == alone[s][f]
 
 
+def test_submit_wait_pipeline_equals_synchronous_calls(ctx_c1):
+    """svo_submit_batch / svo_wait_batch with two batches in flight give the results of svo_process_batch."""
+    frames, cam = synth.make_sequence("c1", seed=31, n_frames=4)
+    key = lambda r: (tuple(r.delta_pose), r.num_it, r.num_it_final, r.stereo_matches, r.tracked_feats_from_last_frame, r.error_code, r.valid)
+    ctx_c1.reset_slot(3)
+    ref = [key(ctx_c1.process_batch([L], [R], [gcam(cam)], slots=[3])[0]) for (L, R) in frames]
+    ctx_c1.reset_slot(3)
+    got = []
+    ctx_c1.submit_batch([frames[0][0]], [frames[0][1]], [gcam(cam)], slots=[3])
+    for k in range(1, 4):
+        ctx_c1.submit_batch([frames[k][0]], [frames[k][1]], [gcam(cam)], slots=[3])
+        got.append(key(ctx_c1.wait_batch()[0]))
+    got.append(key(ctx_c1.wait_batch()[0]))
+    assert got == ref
+    res = (capi.Result * 1)()
+    assert capi.lib().svo_wait_batch(ctx_c1._h, res) == capi.SVO_ERR_STATE      # nothing in flight
+
+
 def test_state_machine_first_frame_bad_tracking_and_repeat(ctx_c1):
     frames, cam = synth.make_sequence("c1", seed=4, n_frames=2)
     ctx_c1.reset_slot(2)
@@ -477,3 +495,37 @@ def test_argument_errors(ctx_c1):
         capi.Context(width=320, height=240, min_distance=1)
     with pytest.raises(capi.SvoError):
         capi.Context(width=16, height=16)
+
+
+def test_host_shim_demo_loop_matches_oracle(tmp_path):
+    """The C++ host shim (reference API shape: processNewImagePair / TStereoOdometryResult) driven by the
+    demo loop of demo-main.cpp:210-253 reproduces the oracle's composed camera poses."""
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    demo = os.path.join(root, "stereo_vo_b200", "host", "svo_demo")
+    assert os.path.exists(demo), "host shim not built (run __graft_entry__.build())"
+    frames, cam = synth.make_sequence("c1", seed=9, n_frames=4)
+    seq = tmp_path / "seq.bin"
+    with open(seq, "wb") as f:
+        f.write(struct.pack("<3i5d", 320, 240, len(frames), cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"]))
+        for (L, R) in frames:
+            f.write(L.tobytes())
+            f.write(R.tobytes())
+    out = tmp_path / "camera_pose.txt"
+    p = subprocess.run([demo, str(seq), str(out), "100"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    got = np.loadtxt(out).reshape(-1, 6)
+    cv2 = pytest.importorskip("cv2")
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend="port", ransac="cv2")
+    pose = np.eye(4)
+    exp = []
+    for (L, R) in frames:
+        o = est.process_new_image_pair(L, R, ocam(cam))
+        if o["valid"]:
+            pose = pose @ o["pose"]["mat"]
+        ypr = [np.arctan2(pose[1, 0], pose[0, 0]), np.arctan2(-pose[2, 0], np.hypot(pose[0, 0], pose[1, 0])), np.arctan2(pose[2, 1], pose[2, 2])]
+        exp.append([pose[0, 3], pose[1, 3], pose[2, 3]] + ypr)
+    np.testing.assert_allclose(got, np.array(exp), atol=1.5e-3)     # the file holds %.3f values
+    assert abs(got[-1, 0] - 0.15) < 0.02                            # 3 steps of 0.05 m

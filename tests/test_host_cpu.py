@@ -138,3 +138,18 @@ def test_fundmat_core_small_inputs(fundmat_host):
     assert fundmat_host(p1, p2)[0] == 7 and fundmat_host(p1[:6], p2[:6])[0] == -1
     p1, p2 = _two_views(rng, 11, 0.2)
     assert fundmat_host(p1, p2)[0] == 7     # LMedS on 8..13 points keeps exactly its 7 sample points
+
+
+def test_host_shim_builds_and_fails_loudly_without_gpu(built_lib, tmp_path):
+    import struct
+    import torch
+    demo = os.path.join(ROOT, "stereo_vo_b200", "host", "svo_demo")
+    assert os.path.exists(demo) and os.path.exists(os.path.join(ROOT, "stereo_vo_b200", "host", "libstereo_odometry_b200.so"))
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    seq = tmp_path / "seq.bin"
+    with open(seq, "wb") as f:
+        f.write(struct.pack("<3i5d", 320, 240, 1, 250.0, 250.0, 160.0, 120.0, 0.12))
+        f.write(bytes(320 * 240 * 2))
+    p = subprocess.run([demo, str(seq), str(tmp_path / "pose.txt"), "100"], capture_output=True, text=True)
+    assert p.returncode == 1 and "no CUDA device" in p.stderr
