@@ -192,6 +192,22 @@ def algorithmic_bytes(B, W, H, N, M, T):
     }
 
 
+def reduce_over_ranks(ms, e2e_ms, pairs, n_valid, launches, device):
+    """max over ranks of the elapsed times + the end-of-batch gather of the per-rank counters: the only
+    collectives on this path (NCCL on the GPU box; gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return ms, e2e_ms, pairs, n_valid, launches
+    tm = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([pairs, n_valid, launches], dtype=torch.int64, device=device)
+    gathered = [torch.zeros_like(cnt) for _ in range(dist.get_world_size())]
+    dist.all_gather(gathered, cnt)
+    return (float(tm[0]), float(tm[1]), int(sum(int(g[0]) for g in gathered)), int(sum(int(g[1]) for g in gathered)),
+            int(sum(int(g[2]) for g in gathered)))
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -308,18 +324,7 @@ def run_gpu(args):
 
     # ---- max over ranks + the end-of-batch gather (the only collective on this path) ------------------------
     pairs = B * args.steps
-    if world > 1:
-        tm = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(tm[0]), float(tm[1])
-        cnt = torch.tensor([pairs, n_valid, launches], dtype=torch.int64, device="cuda")
-        gathered = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(gathered, cnt)
-        pairs_all = int(sum(int(g[0]) for g in gathered))
-        n_valid_all = int(sum(int(g[1]) for g in gathered))
-        launches_all = int(sum(int(g[2]) for g in gathered))
-    else:
-        pairs_all, n_valid_all, launches_all = pairs, n_valid, launches
+    ms, e2e_ms, pairs_all, n_valid_all, launches_all = reduce_over_ranks(ms, e2e_ms, pairs, n_valid, launches, "cuda")
 
     if rank == 0:
         value = pairs_all / (ms * 1e-3)
