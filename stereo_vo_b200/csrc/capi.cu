@@ -60,6 +60,7 @@ struct svo_ctx {
     uint32_t* d_occ = nullptr;
     int occ_words = 0;
     uint32_t* d_sort_scratch = nullptr;
+    uint2* d_list_scratch = nullptr;
     // pinned host staging
     int32_t* h_slots = nullptr;
     uint8_t* h_repeat = nullptr;
@@ -138,7 +139,7 @@ int run_step(svo_ctx* c, int n, const uint8_t* d_left, const uint8_t* d_right, s
     if (t) t->mark(c->stream);
     L += 2;
     CU(c, launch_detect(P, n, d_left, d_right, stride, image_pitch, c->pitch, c->d_occ, c->occ_words,
-                        c->d_sort_scratch, c->stream, &L, t));
+                        c->d_sort_scratch, c->d_list_scratch, c->stream, &L, t));
     CU(c, launch_match_lr(P, n, c->stream, &L, t));
     CU(c, launch_track_match(P, n, c->stream, &L, t));
     if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, c->RS, n, c->stream, &L, t));
@@ -289,6 +290,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     }
     DA(c->d_occ, (size_t)S * 2 * c->occ_words);
     DA(c->d_sort_scratch, (size_t)S * 2 * cfg->max_corners);
+    DA(c->d_list_scratch, (size_t)S * 2 * 2 * (cfg->max_corners / 16 + 2));
     GnScratch& G = c->G;
     DA(G.prev, S * cap); DA(G.obs, S * cap); DA(G.lmk, S * cap * 3); DA(G.mask, S * cap);
     DA(G.cur_idx, S * cap); DA(G.ini_pose, S * 6);
@@ -672,7 +674,7 @@ int svo_detect(svo_ctx* c, const uint8_t* img, size_t stride, svo_keypoint* out_
     CU(c, launch_begin_step(c->P, 1, nullptr, c->stream));
     int L = 1;
     CU(c, launch_detect(c->P, 1, c->d_stageL, c->d_stageR, c->pitch, plane, c->pitch, c->d_occ, c->occ_words,
-                        c->d_sort_scratch, c->stream, &L));
+                        c->d_sort_scratch, c->d_list_scratch, c->stream, &L));
     c->launches += L;
     const int n = svo_get_keypoints(c, hs, 0, 0, out_kps, cap);
     if (n < 0) return n;

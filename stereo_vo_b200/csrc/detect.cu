@@ -27,6 +27,7 @@ constexpr int SIN_H = TH + 2 * HALO;   // 40
 constexpr int SSC_W = TW + 4;          // score tile with halo 1, padded to 68
 constexpr int K1_THREADS = 256;
 constexpr int K1_NCAND = (TH + 2) * (TW + 2);
+constexpr int K1_WLIST = ((K1_NCAND + K1_THREADS - 1) / K1_THREADS) * 32;   // candidates one warp can collect
 
 // one-step REFLECT_101 (|offset| <= 4 < n)
 __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
@@ -86,8 +87,8 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
     __shared__ __align__(16) uint8_t s_in[SIN_H * SIN_W];
     __shared__ __align__(16) float s_row[(TH + 6) * TW];
     __shared__ __align__(16) uint8_t s_sc[(TH + 2) * SSC_W];
-    __shared__ uint16_t s_list[K1_NCAND];
-    __shared__ int s_nlist;
+    __shared__ uint16_t s_list[(K1_THREADS / 32) * K1_WLIST];
+    __shared__ int s_wcnt[K1_THREADS / 32];
 
     const int W = P.p.W, H = P.p.H;
     const int item = blockIdx.z >> 1, side = blockIdx.z & 1;
@@ -115,7 +116,6 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
         }
         uint32_t* s_z = reinterpret_cast<uint32_t*>(s_sc);
         for (int w = tid; w < (TH + 2) * SSC_W / 4; w += K1_THREADS) s_z[w] = 0;
-        if (tid == 0) s_nlist = 0;
     }
     __syncthreads();
 
@@ -139,8 +139,11 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
         }
         *reinterpret_cast<float4*>(s_row + r * TW + c) = o;
     }
-    // 3a. FAST pre-test on the tile plus a 1-px ring (needed by the 3x3 NMS): collect candidates
+    // 3a. FAST pre-test on the tile plus a 1-px ring (needed by the 3x3 NMS): every warp collects its
+    //     candidates in its own segment of s_list (ballot + popc, no atomics)
     const int th = P.p.fast_th;
+    const int wid = tid >> 5;
+    int wcount = 0;
     for (int i0 = 0; i0 < K1_NCAND; i0 += K1_THREADS) {
         const int i = i0 + tid;
         bool cand = false;
@@ -151,16 +154,22 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
                 cand = fast_pretest(s_in + (r + HALO - 1) * SIN_W + (c + HALO - 1), th);
         }
         const unsigned m = __ballot_sync(0xffffffffu, cand);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(&s_nlist, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (cand) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        if (cand) s_list[wid * K1_WLIST + wcount + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        wcount += __popc(m);
     }
+    if (lane == 0) s_wcnt[wid] = wcount;
     __syncthreads();
     // 3b. full score for the candidates only (dense over the CTA)
-    const int nlist = s_nlist;
+    int pre[K1_THREADS / 32 + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int w = 0; w < K1_THREADS / 32; ++w) pre[w + 1] = pre[w] + s_wcnt[w];
+    const int nlist = pre[K1_THREADS / 32];
     for (int q = tid; q < nlist; q += K1_THREADS) {
-        const int i = s_list[q];
+        int w = 0;
+#pragma unroll
+        for (int k = 1; k < K1_THREADS / 32; ++k) w += (q >= pre[k]) ? 1 : 0;
+        const int i = s_list[w * K1_WLIST + (q - pre[w])];
         const int r = i / (TW + 2), c = i - r * (TW + 2);
         s_sc[r * SSC_W + c] = (uint8_t)fast9_score(s_in + (r + HALO - 1) * SIN_W + (c + HALO - 1), th);
     }
@@ -263,12 +272,14 @@ __device__ void block_stable_sort(uint32_t* a, uint32_t* tmp, int n) {
 
 __global__ void __launch_bounds__(K2_THREADS)
 select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_words_per_img,
-              uint32_t* __restrict__ sort_scratch) {
+              uint32_t* __restrict__ sort_scratch, uint2* __restrict__ list_scratch) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* s_a = smem;                          // [max_corners]
     uint32_t* s_b = smem + P.p.max_corners;        // [kp_cap]
+    // segment lists of the sort emulation live in global memory (one read + one write per segment): keeps the
+    // shared-memory footprint at 4 B per candidate so that three CTAs fit on an SM
     const int list_cap = P.p.max_corners / 16 + 2;
-    uint2* s_listA = reinterpret_cast<uint2*>(smem + ((P.p.max_corners + P.p.kp_cap + 1) & ~1));
+    uint2* s_listA = list_scratch + (size_t)blockIdx.x * 2 * list_cap;
     uint2* s_listB = s_listA + list_cap;
     __shared__ int s_warp[K2_THREADS / 32];
     __shared__ int s_nsel;
@@ -299,30 +310,32 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
             v = *reinterpret_cast<const uint4*>(score + (size_t)y * pitch + x);
         }
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        // bit 7 of every non-zero byte
+        uint32_t nzw[4];
         int cnt = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            // number of non-zero bytes in w[q]
-            const uint32_t nz = ((w[q] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w[q]) & 0x80808080u;
-            cnt += __popc(nz);
+            nzw[q] = ((w[q] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w[q]) & 0x80808080u;
+            cnt += __popc(nzw[q]);
         }
         int total;
         const int off = block_exclusive_scan(cnt, s_warp, total);
         if (cnt) {
             int o = base + off;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t s = (w[q] >> (8 * b)) & 0xFFu;
-                    if (s) {
-                        if (o < P.p.max_corners) {
-                            s_a[o] = (s << 24) | (uint32_t)o;
-                            cand_pos[o] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * q + b);
-                        }
-                        ++o;
+            for (int q = 0; q < 4; ++q) {
+                uint32_t m = nzw[q];
+                while (m) {                              // corners are sparse: visit only the non-zero bytes, in x order
+                    const int bit = __ffs(m) - 1;        // 7, 15, 23 or 31
+                    m &= m - 1;
+                    const uint32_t sc = (w[q] >> (bit - 7)) & 0xFFu;
+                    if (o < P.p.max_corners) {
+                        s_a[o] = (sc << 24) | (uint32_t)o;
+                        cand_pos[o] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * q + (bit >> 3));
                     }
+                    ++o;
                 }
+            }
         }
         base += total;
     }
@@ -402,39 +415,76 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
 // K3  brief_kernel: one warp per keypoint, lane l produces descriptor byte l (tests 8l..8l+7).
 //   bit i = blur[y+ay_i][x+ax_i] < blur[y+by_i][x+bx_i]      (cv::ORB::compute, S2:512)
 // ------------------------------------------------------------------------------------------------
-__constant__ int8_t c_orb_pattern[256][4] = {
-#include "orb_pattern.inc"
-};
-
 constexpr int K3_WARPS = 8;
+constexpr int K3_ITERS = 8;         // keypoints per warp
+constexpr int K3_PITCH = 40;        // patch row pitch in bytes: 9 aligned words (36 B) + pad
 
+// Sample offsets inside the staged patch, built at compile time from the ORB pattern and stored transposed
+// ([test-in-byte][lane]) so that the 32 lanes of a warp read consecutive words.
+struct BriefOffsets { uint32_t v[8 * 32]; };
+constexpr BriefOffsets make_brief_offsets() {
+    constexpr int pat[256][4] = {
+#include "orb_pattern.inc"
+    };
+    BriefOffsets t{};
+    for (int lane = 0; lane < 32; ++lane)
+        for (int k = 0; k < 8; ++k) {
+            const int i = lane * 8 + k;
+            const uint32_t a = (uint32_t)((pat[i][1] + 15) * K3_PITCH + pat[i][0] + 15);
+            const uint32_t b = (uint32_t)((pat[i][3] + 15) * K3_PITCH + pat[i][2] + 15);
+            t.v[k * 32 + lane] = a | (b << 16);
+        }
+    return t;
+}
+__device__ const BriefOffsets g_brief_offsets = make_brief_offsets();
+
+// The 512 samples of one keypoint lie within |offset| <= 13 of it.  The warp first copies the 31-row patch
+// around the keypoint into shared memory with aligned 32-bit loads (3 rows x 9 words per instruction, ~55 L1
+// sectors per keypoint), then every lane reads its 16 samples from there -- instead of 16 global byte gathers
+// per lane that touch ~20 sectors each.
 __global__ void __launch_bounds__(K3_WARPS * 32)
 brief_kernel(Pools P, int pitch) {
-    __shared__ int s_off[512];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        s_off[2 * i] = c_orb_pattern[i][1] * pitch + c_orb_pattern[i][0];
-        s_off[2 * i + 1] = c_orb_pattern[i][3] * pitch + c_orb_pattern[i][2];
-    }
-    __syncthreads();
+    __shared__ __align__(16) uint8_t s_patch[K3_WARPS][31 * K3_PITCH];
     const int item = blockIdx.y >> 1, side = blockIdx.y & 1;
     const int slot = P.slots[item];
     const int cur = P.state[slot].cur;
     const size_t f = frame_idx(slot, cur, side);
     const int n = P.n_kp[f];
-    const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * K3_WARPS + (threadIdx.x >> 5);
-    if (k >= n) return;
-    const int2 kp = P.kp[f * P.p.kp_cap + k];
-    const int x = kp.x & 0xFFFF, y = (unsigned)kp.x >> 16;
-    const uint8_t* __restrict__ c = P.blur + img_idx(slot, side) * (size_t)pitch * P.p.H + (size_t)y * pitch + x;
-    unsigned v = 0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t off[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const int i = lane * 8 + t;
-        const int a = c[s_off[2 * i]], b = c[s_off[2 * i + 1]];
-        v |= (unsigned)(a < b) << t;
+    for (int t = 0; t < 8; ++t) off[t] = g_brief_offsets.v[t * 32 + lane];
+    const int lr = lane / 9, lw = lane - lr * 9;
+    uint32_t* patchw = reinterpret_cast<uint32_t*>(s_patch[w]);
+    const uint8_t* __restrict__ plane = P.blur + img_idx(slot, side) * (size_t)pitch * P.p.H;
+    const int k0 = (blockIdx.x * K3_WARPS + w) * K3_ITERS;
+    for (int it = 0; it < K3_ITERS; ++it) {
+        const int k = k0 + it;
+        if (k >= n) break;
+        const int2 kp = P.kp[f * P.p.kp_cap + k];
+        const int x = kp.x & 0xFFFF, y = (unsigned)kp.x >> 16;
+        // rows y-15 .. y+15; columns from (x-15) rounded down to a multiple of 4 (planes are 16-byte aligned with a
+        // pitch that is a multiple of 16; keypoints are >= 31 px inside the image, so the patch never leaves it)
+        const int xs = x - 15, a = xs & 3;
+        const uint8_t* __restrict__ src = plane + (size_t)(y - 15) * pitch + (xs - a);
+        __syncwarp();
+        if (lane < 27) {
+#pragma unroll
+            for (int r3 = 0; r3 < 11; ++r3) {
+                const int row = r3 * 3 + lr;
+                if (row < 31) patchw[row * (K3_PITCH / 4) + lw] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)row * pitch) + lw);
+            }
+        }
+        __syncwarp();
+        const uint8_t* patch = s_patch[w] + a;
+        unsigned v = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int pa = patch[off[t] & 0xFFFFu], pb = patch[off[t] >> 16];
+            v |= (unsigned)(pa < pb) << t;
+        }
+        reinterpret_cast<uint8_t*>(P.desc + (f * P.p.kp_cap + k) * 2)[lane] = (uint8_t)v;
     }
-    reinterpret_cast<uint8_t*>(P.desc + (f * P.p.kp_cap + k) * 2)[lane] = (uint8_t)v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -470,7 +520,7 @@ __global__ void begin_step_kernel(Pools P, int n, const uint8_t* __restrict__ re
 // host launchers
 // ------------------------------------------------------------------------------------------------
 int detect_smem_bytes(const Params& p) {
-    return ((p.max_corners + p.kp_cap + 1) & ~1) * (int)sizeof(uint32_t) + 2 * (p.max_corners / 16 + 2) * (int)sizeof(uint2);
+    return ((p.max_corners + p.kp_cap + 1) & ~1) * (int)sizeof(uint32_t);
 }
 
 cudaError_t configure_detect(const Params& p) {
@@ -484,14 +534,14 @@ cudaError_t launch_begin_step(const Pools& P, int n, const uint8_t* d_repeat, cu
 
 cudaError_t launch_detect(const Pools& P, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
                           size_t image_pitch, int pitch_out, uint32_t* occ_scratch, int occ_words_per_img,
-                          uint32_t* sort_scratch, cudaStream_t st, int* launches, StepTimer* tm) {
+                          uint32_t* sort_scratch, uint2* list_scratch, cudaStream_t st, int* launches, StepTimer* tm) {
     const dim3 g1((P.p.W + TW - 1) / TW, (P.p.H + TH - 1) / TH, 2 * n);
     fast_blur_kernel<<<g1, K1_THREADS, 0, st>>>(P, d_left, d_right, stride, image_pitch, pitch_out);
     if (tm) tm->mark(st);
     const int smem = detect_smem_bytes(P.p);
-    select_kernel<<<2 * n, K2_THREADS, smem, st>>>(P, pitch_out, occ_scratch, occ_words_per_img, sort_scratch);
+    select_kernel<<<2 * n, K2_THREADS, smem, st>>>(P, pitch_out, occ_scratch, occ_words_per_img, sort_scratch, list_scratch);
     if (tm) tm->mark(st);
-    const dim3 g3((P.p.kp_cap + K3_WARPS - 1) / K3_WARPS, 2 * n);
+    const dim3 g3((P.p.kp_cap + K3_WARPS * K3_ITERS - 1) / (K3_WARPS * K3_ITERS), 2 * n);
     brief_kernel<<<g3, K3_WARPS * 32, 0, st>>>(P, pitch_out);
     if (tm) tm->mark(st);
     if (launches) *launches += 3;

@@ -22,7 +22,7 @@
 
 namespace svo {
 
-constexpr int GN_THREADS = 256;
+constexpr int GN_THREADS = 64;    // 254 registers/thread: 4 CTAs (stereo pairs) per SM overlap each other's serial 6x6 solves
 constexpr int NACC = 28;   // 21 (H upper triangle) + 6 (g) + 1 (cost)
 
 struct RotDeriv {
