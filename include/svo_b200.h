@@ -224,6 +224,9 @@ void* svo_stream(svo_ctx* ctx);
 /* per-stage device times of the last svo_process_batch* call, in ms, measured with CUDA events on
  * the context's stream when enabled with svo_enable_stage_timing(ctx, 1).  names: static strings. */
 int svo_enable_stage_timing(svo_ctx* ctx, int32_t on);
+/* register-only probes of the POPC and LOP3 issue rates (lane operations per second) on this device: the measured
+ * denominators of the Hamming stage's integer-pipe roofline (bench.py) */
+int svo_measure_pipe_peaks(svo_ctx* ctx, double* popc_per_s, double* lop3_per_s);
 int svo_get_stage_times(svo_ctx* ctx, const char** names, float* ms, int32_t cap);
 
 #ifdef __cplusplus

@@ -31,7 +31,7 @@ EXPORTS = [
     "svo_get_residuals", "svo_get_outliers", "svo_get_track_candidates", "svo_get_plane",
     "svo_detect", "svo_match_hamming", "svo_match_hamming_device", "svo_match_lr", "svo_get_change_in_pose",
     "svo_fundmat_ransac", "svo_abi_version", "svo_kernel_launches", "svo_stream",
-    "svo_enable_stage_timing", "svo_get_stage_times",
+    "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks",
 ]
 
 
@@ -324,6 +324,11 @@ class Context:
 
     def enable_stage_timing(self, on=True):
         self._check(lib().svo_enable_stage_timing(self._h, int(on)))
+
+    def pipe_peaks(self):
+        p, l = C.c_double(0), C.c_double(0)
+        self._check(lib().svo_measure_pipe_peaks(self._h, C.byref(p), C.byref(l)))
+        return {"popc_per_s": p.value, "lop3_per_s": l.value}
 
     def stage_times(self):
         names = (C.c_char_p * 32)()

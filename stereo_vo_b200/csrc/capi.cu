@@ -5,6 +5,7 @@
 #include "detect.cuh"
 #include "gn.cuh"
 #include "match.cuh"
+#include "microbench.cuh"
 #include "ransac.cuh"
 #include "svo_internal.cuh"
 
@@ -353,6 +354,14 @@ int svo_synchronize(svo_ctx* c) {
 
 void* svo_stream(svo_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int64_t svo_kernel_launches(const svo_ctx* c) { return c ? c->launches : 0; }
+
+int svo_measure_pipe_peaks(svo_ctx* c, double* popc_per_s, double* lop3_per_s) {
+    if (!c || !popc_per_s || !lop3_per_s) return SVO_ERR_ARG;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, measure_pipe_peaks(popc_per_s, lop3_per_s, c->stream));
+    return SVO_OK;
+}
 
 int svo_enable_stage_timing(svo_ctx* c, int32_t on) {
     if (!c) return SVO_ERR_ARG;

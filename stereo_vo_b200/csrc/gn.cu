@@ -159,6 +159,63 @@ __device__ bool solve6(const double* Hu /* 21 upper-triangle entries, row-major 
     return true;
 }
 
+// Fast path of the 6x6 solve: Cholesky in registers (fully unrolled, static indices).  Taken only when every
+// pivot is far above the rank threshold Eigen's JacobiSVD::solve applies (sigma_i > 6 eps sigma_max), i.e. when the
+// pseudo-inverse is the inverse; otherwise (near-singular or non-finite H) the Jacobi path below decides, so the
+// degenerate cases keep the reference's semantics.  ~150 flops instead of ~5000 on local-memory arrays.
+__device__ __forceinline__ bool chol6_solve(const double* Hu, const double* g, double* x) {
+    double L[6][6];
+    double dmax = 0;
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) { L[j][i] = Hu[k++]; }   // lower triangle = H
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dmax = fmax(dmax, L[i][i]);
+    if (!(dmax > 0) || !isfinite(dmax)) return false;
+    const double tiny = dmax * 1e-9;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = L[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+        ok = ok && (d > tiny);
+        const double r = sqrt(d), inv = 1.0 / r;
+        L[j][j] = r;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double v = L[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+            L[i][j] = v * inv;
+        }
+    }
+    if (!ok) return false;
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = g[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
+        y[i] = v / L[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k];
+        x[i] = v / L[i][i];
+    }
+    bool fin = true;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) fin = fin && isfinite(x[i]);
+    return fin;
+}
+
 __device__ void rodrigues(const double* w, double R[3][3]) {
     const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
     double a, b;
@@ -275,7 +332,13 @@ __device__ void eval_rgn(const GnScratch& G, size_t base, int T, const Camera& c
             tot[i] = v;
         }
         sh.cCost = tot[27];
-        sh.fail = solve6(tot, tot + 21, sh.step) ? 0 : 1;
+        double stepv[6];
+        if (chol6_solve(tot, tot + 21, stepv)) {
+            for (int i = 0; i < 6; ++i) sh.step[i] = stepv[i];
+            sh.fail = 0;
+        } else {
+            sh.fail = solve6(tot, tot + 21, sh.step) ? 0 : 1;
+        }
 #ifdef SVO_GN_DEBUG
         if (sh.dbg_once == 0) {
             sh.dbg_once = 1;

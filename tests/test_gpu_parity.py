@@ -529,3 +529,134 @@ def test_host_shim_demo_loop_matches_oracle(tmp_path):
         exp.append([pose[0, 3], pose[1, 3], pose[2, 3]] + ypr)
     np.testing.assert_allclose(got, np.array(exp), atol=1.5e-3)     # the file holds %.3f values
     assert abs(got[-1, 0] - 0.15) < 0.02                            # 3 steps of 0.05 m
+
+
+# ------------------------------------------------------------------------------------ edge cases
+def _oracle_frame(est_params, img_pairs, cam, **kw):
+    est = orc.OracleEstimator(orc.Params(**est_params), backend="port", ransac=kw.get("ransac", "off"))
+    return est, [est.process_new_image_pair(L, R, ocam(cam)) for (L, R) in img_pairs]
+
+
+def test_empty_right_image_and_sparse_content():
+    """No keypoints on one side: BFMatcher returns no matches, nothing tracks, voecBadTracking from frame 1 on."""
+    frames, cam = synth.make_sequence("c1", seed=12, n_frames=2)
+    flat = np.full((240, 320), 90, np.uint8)
+    seq = [(frames[0][0], flat), (frames[1][0], flat)]
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, fundmat_filter=0)
+    try:
+        est, outs = _oracle_frame(dict(orb_nfeats=100), seq, cam)
+        for (L, R), o in zip(seq, outs):
+            r = ctx.process_pair(L, R, gcam(cam))
+            assert (r.detected_left, r.detected_right, r.stereo_matches) == (len(o["frame"].kpsL), 0, 0)
+            assert r.error_code == o["error_code"] and not r.valid
+        assert r.error_code == capi.VOEC["voecBadTracking"]
+        # sparse content: fewer corners than the quota, no cap -> all kept, still bit-exact
+        sparse = flat.copy()
+        rng = np.random.default_rng(5)
+        tex = synth.make_texture(rng, 240, 320)
+        for _ in range(12):                               # a dozen textured 14x14 patches on a flat background
+            y, x = rng.integers(40, 180), rng.integers(40, 260)
+            sparse[y:y + 14, x:x + 14] = tex[y:y + 14, x:x + 14]
+        k, d = ctx.detect(sparse)
+        rk, rd = orc.orb_compute(sparse, orc.fast9(sparse, 20))
+        rk, rd, _ = orc.non_max_sup(200, rk, rd, 3, 240, 320)
+        rk, rd, _, _ = orc.update_indexes(rk, rd, 240)
+        assert 0 < len(k) < 200 and np.array_equal(xys(k), xys(rk)) and np.array_equal(d, rd)
+    finally:
+        ctx.close()
+
+
+def test_padded_host_stride_and_small_image():
+    """Row stride larger than the width (cudaMemcpy2D path) and the smallest supported image (64x64)."""
+    frames, cam = synth.make_sequence("c1", seed=13, n_frames=2)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, fundmat_filter=0)
+    try:
+        ref = []
+        for (L, R) in frames:
+            r = ctx.process_pair(L, R, gcam(cam))
+            ref.append((r.stereo_matches, r.tracked_feats_from_last_frame, tuple(r.delta_pose)))
+        ctx.reset_slot(0)
+        got = []
+        for (L, R) in frames:
+            Lp = np.zeros((240, 352), np.uint8)
+            Rp = np.zeros((240, 352), np.uint8)
+            Lp[:, :320], Rp[:, :320] = L, R
+            res = capi.Result()
+            rc = capi.lib().svo_process_pair(ctx._h, Lp.ctypes.data_as(capi.C.c_void_p), Rp.ctypes.data_as(capi.C.c_void_p),
+                                             capi.C.c_size_t(352), capi.C.byref(gcam(cam)), 0, capi.C.byref(res))
+            assert rc == 0
+            got.append((res.stereo_matches, res.tracked_feats_from_last_frame, tuple(res.delta_pose)))
+        assert got == ref
+    finally:
+        ctx.close()
+    small = capi.Context(width=64, height=64, orb_nfeats=20, max_seqs=1)
+    try:
+        img = synth.make_texture(np.random.default_rng(3), 64, 64)
+        k, d = small.detect(img)
+        rk, rd = orc.orb_compute(img, orc.fast9(img, 20))     # only x,y in [31,33) survive the ORB border
+        rk, rd, _ = orc.non_max_sup(40, rk, rd, 3, 64, 64)
+        rk, rd, _, _ = orc.update_indexes(rk, rd, 64)
+        assert np.array_equal(xys(k), xys(rk)) and np.array_equal(d, rd)
+    finally:
+        small.close()
+
+
+@pytest.mark.parametrize("th", [5, 30])
+def test_detect_other_fast_thresholds(th):
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, fast_threshold=th)
+    try:
+        frames, _ = synth.make_sequence("c1", seed=14, n_frames=1)
+        img = frames[0][1]
+        k, d = ctx.detect(img)
+        rk, rd = orc.orb_compute(img, orc.fast9(img, th))
+        rk, rd, _ = orc.non_max_sup(200, rk, rd, 3, 240, 320)
+        rk, rd, _, _ = orc.update_indexes(rk, rd, 240)
+        assert np.array_equal(xys(k), xys(rk)) and np.array_equal(d, rd)
+    finally:
+        ctx.close()
+
+
+def test_no_nms_keeps_every_corner():
+    """non_maximal_suppression = false: feats_vector is swapped in unchanged (S2:613) and only row-sorted."""
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, non_maximal_suppression=0, max_corners=4096)
+    try:
+        frames, _ = synth.make_sequence("c1", seed=15, n_frames=1)
+        img = frames[0][0]
+        k, d = ctx.detect(img)
+        rk, rd = orc.orb_compute(img, orc.fast9(img, 20))
+        rk, rd, _, _ = orc.update_indexes(rk, rd, 240)
+        assert len(k) == len(rk) > 1000 and np.array_equal(xys(k), xys(rk)) and np.array_equal(d, rd)
+    finally:
+        ctx.close()
+
+
+def test_ls_param_variants_match_oracle():
+    """Plain least squares (no robust kernel), no warm start, fewer iterations."""
+    frames, cam = synth.make_sequence("c1", seed=16, n_frames=3)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, fundmat_filter=0, use_robust_kernel=0,
+                       use_previous_pose_as_initial=0, initial_max_iters=4, max_iters=7, residual_threshold=6.0)
+    try:
+        est = orc.OracleEstimator(orc.Params(orb_nfeats=100, use_robust_kernel=False, use_previous_pose_as_initial=False,
+                                             initial_max_iters=4, max_iters=7, residual_threshold=6.0),
+                                  backend="port", ransac="off")
+        _run_sequence(ctx, est, frames, cam)
+    finally:
+        ctx.close()
+
+
+def test_device_resident_entry_matches_host_entry(ctx_c1):
+    """svo_process_batch_device (images already in HBM, the path bench.py's `value` uses) == svo_process_batch."""
+    torch = pytest.importorskip("torch")
+    frames, cam = synth.make_sequence("c1", seed=17, n_frames=3)
+    key = lambda r: (tuple(r.delta_pose), r.num_it, r.num_it_final, r.stereo_matches, r.tracked_feats_from_last_frame, r.error_code, r.valid)
+    ctx_c1.reset_slot(0)
+    ctx_c1.reset_slot(1)
+    for (L, R) in frames:
+        a = ctx_c1.process_batch([L], [R], [gcam(cam)], slots=[0])[0]
+        dL = torch.from_numpy(L).cuda()
+        dR = torch.from_numpy(R).cuda()
+        torch.cuda.synchronize()
+        ctx_c1.process_batch_device(dL.data_ptr(), dR.data_ptr(), 1, 320, 320 * 240, [gcam(cam)], slots=[1])
+        b = ctx_c1.fetch_results(1, slots=[1])[0]
+        assert key(a) == key(b)
+        assert np.array_equal(ctx_c1.tracked_pairs(0), ctx_c1.tracked_pairs(1))
