@@ -32,6 +32,7 @@ UNIT = "pairs/s"
 CONFIG = "c2"
 N_SEQ = 8            # distinct synthetic sequences (seeds 0..7), replicated over the slots with phase offsets
 N_FRAMES = 4         # frames per sequence, played back and forth so consecutive steps are adjacent frames
+HM_POPC, HM_ALU = 4, 17   # per pair-distance: POPC-pipe and ALU-pipe (16 LOP3 + 1 min) instructions (SASS of hamming_*_kernel)
 
 
 def pingpong(t, n):
@@ -208,6 +209,150 @@ def reduce_over_ranks(ms, e2e_ms, pairs, n_valid, launches, device):
             int(sum(int(g[2]) for g in gathered)))
 
 
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 5: descriptor-match microbench (4096 L x 4096 R, 256-bit Hamming brute force) and the
+# NR sweep across the roofline ridge: small NR = HBM-bound streaming of the queries,
+# large NR = integer-pipe bound.
+# ------------------------------------------------------------------------------------------------
+C5_N = 4096
+
+
+def hamming_algo_bytes(nq, nt, reps):
+    return reps * (32 * (nq + nt) + 4 * nq)        # every descriptor once in, one packed (dist<<16|idx) word out
+
+
+def time_hamming(ctx, torch, stream, d_q, nq, d_t, nt, reps, d_out, iters, warm=3, flush=None):
+    """mean milliseconds per svo_match_hamming_device launch (CUDA events on the library stream)."""
+    for _ in range(warm):
+        ctx.match_hamming_device(d_q.data_ptr(), nq, d_t.data_ptr(), nt, reps, d_out.data_ptr())
+    ctx.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.add_(1)                      # > L2: the next launch reads its inputs from HBM
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.match_hamming_device(d_q.data_ptr(), nq, d_t.data_ptr(), nt, reps, d_out.data_ptr())
+        e1.record(stream)
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def c5_microbench(ctx, torch, stream, device, pipe, peak, reps=64, iters=10, sweep=True, seed=5):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    q = torch.randint(0, 256, (reps, C5_N, 32), dtype=torch.uint8, generator=g).to(device)
+    t = torch.randint(0, 256, (reps, C5_N, 32), dtype=torch.uint8, generator=g).to(device)
+    out = torch.zeros((reps, C5_N), dtype=torch.int32, device=device)
+    flush = torch.zeros(64 << 20, dtype=torch.int32, device=device)       # 256 MB > 126 MB L2
+    ms = time_hamming(ctx, torch, stream, q, C5_N, t, C5_N, reps, out, iters, flush=flush)
+    pd = reps * C5_N * C5_N / (ms * 1e-3)
+    int_roof = 1.0 / max(HM_POPC / pipe["popc_per_s"], HM_ALU / pipe["lop3_per_s"])
+    res = {"problem": f"{reps} independent {C5_N}x{C5_N} problems per launch", "ms": ms, "pair_distances_per_s": pd,
+           "frac_of_int_pipe_roof": pd / int_roof, "algo_bytes": hamming_algo_bytes(C5_N, C5_N, reps),
+           "hbm_gbs": hamming_algo_bytes(C5_N, C5_N, reps) / (ms * 1e-3) / 1e9}
+    res["hbm_frac"] = res["hbm_gbs"] / peak
+    if sweep:
+        # one problem, NL = 8 Mi queries (256 MB of descriptors, larger than L2) against NR train rows: crosses the
+        # ridge (NR ~ 8); below it the kernel streams the queries once and "fraction of HBM peak" is the figure
+        nq = 8 << 20
+        qb = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=device)
+        ob = torch.zeros((nq,), dtype=torch.int32, device=device)
+        rows = []
+        for nt in (1, 2, 4, 8, 16, 64, 256, 1024):
+            m = time_hamming(ctx, torch, stream, qb, nq, t, nt, 1, ob, 3, warm=1)
+            ab = hamming_algo_bytes(nq, nt, 1)
+            rows.append({"nr": nt, "nl": nq, "us": round(m * 1e3, 2), "hbm_gbs": round(ab / (m * 1e-3) / 1e9, 1),
+                         "hbm_frac": round(ab / (m * 1e-3) / 1e9 / peak, 4),
+                         "int_frac": round(nq * nt / (m * 1e-3) / int_roof, 4)})
+        res["sweep"] = rows
+        del qb, ob
+    return res, (q, t, out)
+
+
+def run_c5(args):
+    """--workload c5: the microbench on N GPUs.  Query rows are sharded across the ranks, the train set is
+    replicated (broadcast from rank 0), the packed results are all-gathered (the one exchange step, NCCL)."""
+    import torch
+    import torch.distributed as dist
+    from stereo_vo_b200 import capi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, device=local)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+    pipe = ctx.pipe_peaks()
+    peak, peak_src = load_peaks()
+    reps = args.c5_reps
+    micro, (q, t, out) = c5_microbench(ctx, torch, stream, device, pipe, peak, reps=reps, iters=5, sweep=(rank == 0), seed=5 + rank)
+    if world > 1:
+        dist.broadcast(t, src=0)                       # replicated train set
+    gathered = torch.zeros((world,) + tuple(out.shape), dtype=out.dtype, device=device)
+    flush = torch.zeros(64 << 20, dtype=torch.int32, device=device)
+
+    def step():
+        with torch.cuda.stream(stream):
+            flush.add_(1)
+        ctx.match_hamming_device(q.data_ptr(), C5_N, t.data_ptr(), C5_N, reps, out.data_ptr())
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tm = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm[0])
+        assert torch.equal(gathered[rank], out)
+    if rank == 0:
+        pd = world * reps * C5_N * C5_N * args.steps / (ms * 1e-3)
+        ab = hamming_algo_bytes(C5_N, C5_N, reps)
+        kms = micro["ms"]
+        line = {"metric": "hamming_pair_distances_per_s", "value": pd, "unit": "pair-distances/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"c5: {reps} x ({C5_N} L x {C5_N} R) 256-bit Hamming brute force per GPU per step; "
+                                       "query rows sharded over the ranks, train set replicated, results all-gathered",
+                           "l2": "256 MB flush buffer written between launches"},
+                "gpu_launches": args.steps * world,
+                "roofline": {"bound": "hbm", "kernel": "hamming_raw_kernel", "achieved": ab / (kms * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": ab / (kms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "note": "N x N brute force is integer-pipe bound (ridge at NR ~ 8); see sweep for the HBM-bound regime"},
+                "match_microbench": micro, "clocks": sampler.summary()}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -348,12 +493,13 @@ def run_gpu(args):
             except Exception:
                 traffic = None
         # Hamming stage against its binding (integer-pipe) roof.  Per pair-distance the kernel issues 4 POPC and
-        # 26 ALU-pipe ops (25 LOP3 of the carry-save tree + 1 min; SASS of hamming_*_kernel); the denominators are
+        # 17 ALU-pipe ops (16 LOP3 of the carry-save tree + 1 min; SASS of hamming_*_kernel); the denominators are
         # the POPC and LOP3 lane rates measured on this GPU by register-only probes (svo_measure_pipe_peaks).
         hm_ms = kernel_ms.get("hamming_kernel(lr)", 0) + kernel_ms.get("hamming_kernel(track)", 0)
         pairdist = B * (Nkp * Nkp + 2 * M * M)
         clocks = sampler.summary()
-        int_roof = 1.0 / max(4.0 / pipe["popc_per_s"], 26.0 / pipe["lop3_per_s"])
+        int_roof = 1.0 / max(HM_POPC / pipe["popc_per_s"], HM_ALU / pipe["lop3_per_s"])
+        micro, _ = c5_microbench(ctx, torch, stream, torch.device("cuda", local), pipe, peak, reps=32, iters=5)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -378,8 +524,9 @@ def run_gpu(args):
                             "int_pipe_roof_pair_distances_per_s": int_roof,
                             "frac_of_int_pipe_roof": (pairdist / (hm_ms * 1e-3) / int_roof) if hm_ms else None,
                             "measured_popc_lane_ops_per_s": pipe["popc_per_s"], "measured_lop3_lane_ops_per_s": pipe["lop3_per_s"],
-                            "ops_per_pair_distance": {"popc": 4, "alu": 26},
+                            "ops_per_pair_distance": {"popc": HM_POPC, "alu": HM_ALU},
                             "hbm_gbs": (ab["hamming_kernel(lr)"] + ab["hamming_kernel(track)"]) / (hm_ms * 1e-3) / 1e9 if hm_ms else None},
+            "match_microbench": micro,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -401,14 +548,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="stereo pairs (sequence slots) per step per GPU")
-    ap.add_argument("--cpu-pairs", type=int, default=12, help="cpu_baseline: pairs per process")
-    ap.add_argument("--ref-pairs", type=int, default=12, help="--impl reference: pairs per process per step")
+    ap.add_argument("--cpu-pairs", type=int, default=300, help="cpu_baseline: pairs per process")
+    ap.add_argument("--ref-pairs", type=int, default=100, help="--impl reference: pairs per process per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = the headline pipeline; c5 = Hamming microbench")
+    ap.add_argument("--c5-reps", type=int, default=64, help="c5: independent 4096x4096 problems per GPU per step")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_gpu(args)
 

@@ -18,16 +18,23 @@ namespace svo {
 //   in : 8-bit image (HBM, read once through shared memory, halo 4)
 //   out: blur  (7x7 sigma=2, OpenCV float32 FMA order, rint, saturate)        1 B / px
 //        score (FAST-9/16 corner score after strict 3x3 NMS and the 31-px ORB border filter) 1 B / px
-// Roofline: algorithmic HBM traffic 3 B / px; the kernel is integer-ALU bound (about 250 lane-ops
-// per pixel for the ring test and the arc min/max network), not HBM bound.
+// Roofline: algorithmic HBM traffic 3 B / px; the kernel is instruction-issue bound (ring pre-test, arc
+// min/max network, float blur), not HBM bound.  Stages, all on shared memory:
+//   1  stage the tile (+ halo 4) as 32-bit words
+//   2  blur row pass (float32)
+//   3a FAST pre-test, 4 pixels per work item on 16-bit SIMD lanes (DPX VIMNMX.S16x2), candidates -> list
+//   3b full score for the listed candidates (dense), corners -> second list
+//   3c strict 3x3 NMS + ORB border filter over the corner list (dense)
+//   4  blur column pass + stores, 4 pixels per work item
 // ------------------------------------------------------------------------------------------------
 constexpr int TW = 64, TH = 32, HALO = 4;
-constexpr int SIN_W = TW + 2 * HALO;   // 72
+constexpr int SIN_W = TW + 2 * HALO;   // 72 bytes per staged row
+constexpr int SIN_WW = SIN_W / 4;      // 18 words
 constexpr int SIN_H = TH + 2 * HALO;   // 40
-constexpr int SSC_W = TW + 4;          // score tile with halo 1, padded to 68
+constexpr int SC_H = TH + 2;           // score rows: tile rows -1 .. TH (row r <-> tile row r-1); columns as in s_in
 constexpr int K1_THREADS = 256;
-constexpr int K1_NCAND = (TH + 2) * (TW + 2);
-constexpr int K1_WLIST = ((K1_NCAND + K1_THREADS - 1) / K1_THREADS) * 32;   // candidates one warp can collect
+constexpr int K1_NCAND = SC_H * (TW + 2);
+constexpr int K1_ITEMS3 = SC_H * SIN_WW;   // pre-test work items (row, word)
 
 // one-step REFLECT_101 (|offset| <= 4 < n)
 __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
@@ -58,37 +65,53 @@ __device__ __forceinline__ int fast9_score(const uint8_t* __restrict__ s, int th
     p[10] = cv - (unsigned)s[-2 * SIN_W - 2] * K; p[11] = cv - (unsigned)s[-1 * SIN_W - 3] * K;
     p[12] = cv - (unsigned)s[-3] * K;             p[13] = cv - (unsigned)s[1 * SIN_W - 3] * K;
     p[14] = cv - (unsigned)s[2 * SIN_W - 2] * K;  p[15] = cv - (unsigned)s[3 * SIN_W - 1] * K;
-    unsigned lo2[16], lo4[16];
+    unsigned lo2[16], lo4[16], lo9[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) lo2[k] = __vmins2(p[k], p[(k + 1) & 15]);
 #pragma unroll
     for (int k = 0; k < 16; ++k) lo4[k] = __vmins2(lo2[k], lo2[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) lo9[k] = __vimin3_s16x2(lo4[k], lo4[(k + 4) & 15], p[(k + 8) & 15]);
     unsigned best = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) best = __vmaxs2(best, __vimin3_s16x2(lo4[k], lo4[(k + 4) & 15], p[(k + 8) & 15]));
+    for (int k = 0; k < 16; k += 2) best = __vimax3_s16x2(best, lo9[k], lo9[k + 1]);
     const int sc = max((int)(best & 0xFFFFu), (int)(best >> 16)) - 257;
     return sc >= th ? sc : 0;
 }
 
-// Necessary condition for a FAST-9 corner: every arc of 9 contains two adjacent compass points
-// (ring 0,4,8,12), so two adjacent compass points must both be darker (or both brighter) than the centre
-// by more than th.  Only pixels passing this test get the full score.
-__device__ __forceinline__ bool fast_pretest(const uint8_t* __restrict__ s, int th) {
-    const int v = s[0];
-    const int d0 = v - s[3 * SIN_W], d4 = v - s[3], d8 = v - s[-3 * SIN_W], d12 = v - s[-3];
-    const bool a0 = d0 > th, a4 = d4 > th, a8 = d8 > th, a12 = d12 > th;
-    const bool b0 = d0 < -th, b4 = d4 < -th, b8 = d8 < -th, b12 = d12 < -th;
-    return (a0 && a4) || (a4 && a8) || (a8 && a12) || (a12 && a0) || (b0 && b4) || (b4 && b8) || (b8 && b12) || (b12 && b0);
+// FAST pre-test for two horizontally adjacent pixels held in the 16-bit lanes of one register.
+// Necessary condition for a FAST-9 corner: every arc of 9 contains two adjacent compass points (ring 0, 4, 8, 12),
+// so two adjacent compass points must both be darker (or both brighter) than the centre by more than th.
+//   c2        {256 + v} per lane;  down/right/up/left: the compass pixels, one per lane
+//   t_hi = 257 + th, t_lo = 255 - th (replicated): with d = 256 + v - ring,  v - ring > th <=> d >= t_hi,
+//   v - ring < -th <=> d <= t_lo
+__device__ __forceinline__ void fast_pretest2(unsigned c2, unsigned down, unsigned right, unsigned up, unsigned left,
+                                              unsigned t_hi, unsigned t_lo, bool& cand_lo, bool& cand_hi) {
+    const unsigned d0 = c2 - down, d4 = c2 - right, d8 = c2 - up, d12 = c2 - left;   // lanes stay in 1..511: no borrow
+    const unsigned mn = __vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8), __vmaxs2(__vmins2(d8, d12), __vmins2(d12, d0)));
+    const unsigned mx = __vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmins2(__vmaxs2(d8, d12), __vmaxs2(d12, d0)));
+    bool ph, pl, qh, ql;
+    (void)__vibmax_s16x2(mn, t_hi, &ph, &pl);    // pred = (mn >= t_hi) per lane
+    (void)__vibmin_s16x2(mx, t_lo, &qh, &ql);    // pred = (mx <= t_lo) per lane
+    cand_lo = pl || ql;
+    cand_hi = ph || qh;
 }
+
+__device__ __forceinline__ unsigned widen_lo(unsigned w) { return __byte_perm(w, 0u, 0x4140); }   // bytes 0,1 -> 16-bit lanes
+__device__ __forceinline__ unsigned widen_hi(unsigned w) { return __byte_perm(w, 0u, 0x4342); }   // bytes 2,3 -> 16-bit lanes
 
 __global__ void __launch_bounds__(K1_THREADS)
 fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __restrict__ imgR,
                  size_t stride, size_t image_pitch, int pitch_out) {
-    __shared__ __align__(16) uint8_t s_in[SIN_H * SIN_W];
+    __shared__ __align__(16) uint32_t s_inw[SIN_H * SIN_WW];
     __shared__ __align__(16) float s_row[(TH + 6) * TW];
-    __shared__ __align__(16) uint8_t s_sc[(TH + 2) * SSC_W];
-    __shared__ uint16_t s_list[(K1_THREADS / 32) * K1_WLIST];
-    __shared__ int s_wcnt[K1_THREADS / 32];
+    __shared__ __align__(16) uint32_t s_scw[SC_H * SIN_WW];       // scores of the candidates (tile + 1-px ring)
+    __shared__ __align__(16) uint32_t s_nmsw[TH * (TW / 4)];      // scores after NMS + border filter (tile only)
+    __shared__ uint16_t s_list[K1_NCAND];                         // pre-test survivors  (row * SIN_W + column)
+    __shared__ uint16_t s_corner[K1_NCAND];                       // corners (score > 0)
+    __shared__ int s_n[2];
+    const uint8_t* s_in = reinterpret_cast<const uint8_t*>(s_inw);
+    uint8_t* s_sc = reinterpret_cast<uint8_t*>(s_scw);
 
     const int W = P.p.W, H = P.p.H;
     const int item = blockIdx.z >> 1, side = blockIdx.z & 1;
@@ -96,33 +119,42 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
     const uint8_t* __restrict__ img = (side ? imgR : imgL) + (size_t)item * image_pitch;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     // 1. stage the tile with halo 4 as 32-bit words (REFLECT_101 outside the image: only the blur looks there)
     {
         const bool aligned = ((reinterpret_cast<uintptr_t>(img) | stride) & 3) == 0;
-        uint32_t* s_w = reinterpret_cast<uint32_t*>(s_in);
-        for (int w = tid; w < SIN_H * (SIN_W / 4); w += K1_THREADS) {
-            const int r = w / (SIN_W / 4), cw = w - r * (SIN_W / 4);
-            const int gy = reflect1(y0 - HALO + r, H), gx0 = x0 - HALO + 4 * cw;
-            const uint8_t* row = img + (size_t)gy * stride;
-            uint32_t v;
-            if (aligned && gx0 >= 0 && gx0 + 3 < W) {
-                v = __ldg(reinterpret_cast<const uint32_t*>(row + gx0));
-            } else {
-                v = (uint32_t)__ldg(row + reflect1(gx0, W)) | ((uint32_t)__ldg(row + reflect1(gx0 + 1, W)) << 8) |
-                    ((uint32_t)__ldg(row + reflect1(gx0 + 2, W)) << 16) | ((uint32_t)__ldg(row + reflect1(gx0 + 3, W)) << 24);
+        if (aligned && x0 >= HALO && x0 + TW + HALO <= W && y0 >= HALO && y0 + TH + HALO <= H) {
+            const uint8_t* base = img + (size_t)(y0 - HALO) * stride + (x0 - HALO);      // interior tile: plain word copies
+            for (int w = tid; w < SIN_H * SIN_WW; w += K1_THREADS) {
+                const int r = w / SIN_WW, cw = w - r * SIN_WW;
+                s_inw[w] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * stride) + cw);
             }
-            s_w[w] = v;
+        } else {
+            for (int w = tid; w < SIN_H * SIN_WW; w += K1_THREADS) {
+                const int r = w / SIN_WW, cw = w - r * SIN_WW;
+                const int gy = reflect1(y0 - HALO + r, H), gx0 = x0 - HALO + 4 * cw;
+                const uint8_t* row = img + (size_t)gy * stride;
+                uint32_t v;
+                if (aligned && gx0 >= 0 && gx0 + 3 < W) {
+                    v = __ldg(reinterpret_cast<const uint32_t*>(row + gx0));
+                } else {
+                    v = (uint32_t)__ldg(row + reflect1(gx0, W)) | ((uint32_t)__ldg(row + reflect1(gx0 + 1, W)) << 8) |
+                        ((uint32_t)__ldg(row + reflect1(gx0 + 2, W)) << 16) | ((uint32_t)__ldg(row + reflect1(gx0 + 3, W)) << 24);
+                }
+                s_inw[w] = v;
+            }
         }
-        uint32_t* s_z = reinterpret_cast<uint32_t*>(s_sc);
-        for (int w = tid; w < (TH + 2) * SSC_W / 4; w += K1_THREADS) s_z[w] = 0;
+        for (int w = tid; w < SC_H * SIN_WW; w += K1_THREADS) s_scw[w] = 0;
+        for (int w = tid; w < TH * (TW / 4); w += K1_THREADS) s_nmsw[w] = 0;
+        if (tid < 2) s_n[tid] = 0;
     }
     __syncthreads();
 
     // 2. blur, row pass: rows y0-3 .. y0+TH+2, four outputs per work item (float32, sequential FMA left to right)
     for (int i = tid; i < (TH + 6) * (TW / 4); i += K1_THREADS) {
         const int r = i / (TW / 4), c = (i - r * (TW / 4)) * 4;
-        const uint32_t* pw = reinterpret_cast<const uint32_t*>(s_in + (r + 1) * SIN_W + c);   // bytes c .. c+11
+        const uint32_t* pw = s_inw + (r + 1) * SIN_WW + (c >> 2);   // bytes c .. c+11
         const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
         float f[10];                                   // columns c+1 .. c+10  (x-3 .. x+6 of the first output)
         f[0] = (float)((w0 >> 8) & 0xFF); f[1] = (float)((w0 >> 16) & 0xFF); f[2] = (float)(w0 >> 24);
@@ -139,50 +171,95 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
         }
         *reinterpret_cast<float4*>(s_row + r * TW + c) = o;
     }
-    // 3a. FAST pre-test on the tile plus a 1-px ring (needed by the 3x3 NMS): every warp collects its
-    //     candidates in its own segment of s_list (ballot + popc, no atomics)
+
+    // 3a. FAST pre-test on the tile plus a 1-px ring (needed by the 3x3 NMS): one work item = one staged word
+    //     (4 pixels) of rows -1 .. TH; survivors are appended to s_list (order is irrelevant)
     const int th = P.p.fast_th;
-    const int wid = tid >> 5;
-    int wcount = 0;
-    for (int i0 = 0; i0 < K1_NCAND; i0 += K1_THREADS) {
-        const int i = i0 + tid;
-        bool cand = false;
-        if (i < K1_NCAND) {
-            const int r = i / (TW + 2), c = i - r * (TW + 2);
-            const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-            if (gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3)
-                cand = fast_pretest(s_in + (r + HALO - 1) * SIN_W + (c + HALO - 1), th);
+    {
+        const unsigned t_hi = (unsigned)(257 + th) * 0x00010001u;
+        const unsigned t_lo = ((unsigned)(255 - th) & 0xFFFFu) * 0x00010001u;
+        // candidate columns: FAST is evaluated for 3 <= x < W-3, the tile needs x0-1 .. x0+TW
+        const int cx_lo = max(3, x0 - 1) - (x0 - HALO), cx_hi = min(W - 3, x0 + TW + 1) - (x0 - HALO);   // staged columns [cx_lo, cx_hi)
+        for (int i0 = 0; i0 < K1_ITEMS3; i0 += K1_THREADS) {
+            const int i = i0 + tid;
+            bool c0 = false, c1 = false, c2 = false, c3 = false;
+            int r = 0, cw = 0;
+            if (i < K1_ITEMS3) {
+                r = i / SIN_WW; cw = i - r * SIN_WW;
+                const int gy = y0 - 1 + r;
+                const int jlo = cx_lo - 4 * cw, jhi = cx_hi - 4 * cw;      // valid pixels of this word: jlo <= j < jhi
+                if (gy >= 3 && gy < H - 3 && jlo < 4 && jhi > 0) {
+                    const uint32_t* rp = s_inw + (r + 3) * SIN_WW + cw;
+                    const uint32_t C = rp[0], Cm = rp[-1], Cp = rp[1], U = rp[-3 * SIN_WW], D = rp[3 * SIN_WW];
+                    const uint32_t L = __funnelshift_r(Cm, C, 8);      // pixels x-3
+                    const uint32_t R = __funnelshift_r(C, Cp, 24);     // pixels x+3
+                    fast_pretest2(widen_lo(C) + 0x01000100u, widen_lo(D), widen_lo(R), widen_lo(U), widen_lo(L), t_hi, t_lo, c0, c1);
+                    fast_pretest2(widen_hi(C) + 0x01000100u, widen_hi(D), widen_hi(R), widen_hi(U), widen_hi(L), t_hi, t_lo, c2, c3);
+                    c0 = c0 && jlo <= 0 && jhi > 0;
+                    c1 = c1 && jlo <= 1 && jhi > 1;
+                    c2 = c2 && jlo <= 2 && jhi > 2;
+                    c3 = c3 && jlo <= 3 && jhi > 3;
+                }
+            }
+            const unsigned b0 = __ballot_sync(0xffffffffu, c0), b1 = __ballot_sync(0xffffffffu, c1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, c2), b3 = __ballot_sync(0xffffffffu, c3);
+            const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+            int base = 0;
+            if (lane == 0 && (n0 + n1 + n2 + n3) > 0) base = atomicAdd(&s_n[0], n0 + n1 + n2 + n3);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int e = r * SIN_W + 4 * cw;
+            if (c0) s_list[base + __popc(b0 & lt_mask)] = (uint16_t)e;
+            if (c1) s_list[base + n0 + __popc(b1 & lt_mask)] = (uint16_t)(e + 1);
+            if (c2) s_list[base + n0 + n1 + __popc(b2 & lt_mask)] = (uint16_t)(e + 2);
+            if (c3) s_list[base + n0 + n1 + n2 + __popc(b3 & lt_mask)] = (uint16_t)(e + 3);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (cand) s_list[wid * K1_WLIST + wcount + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
-        wcount += __popc(m);
     }
-    if (lane == 0) s_wcnt[wid] = wcount;
     __syncthreads();
-    // 3b. full score for the candidates only (dense over the CTA)
-    int pre[K1_THREADS / 32 + 1];
-    pre[0] = 0;
-#pragma unroll
-    for (int w = 0; w < K1_THREADS / 32; ++w) pre[w + 1] = pre[w] + s_wcnt[w];
-    const int nlist = pre[K1_THREADS / 32];
-    for (int q = tid; q < nlist; q += K1_THREADS) {
-        int w = 0;
-#pragma unroll
-        for (int k = 1; k < K1_THREADS / 32; ++k) w += (q >= pre[k]) ? 1 : 0;
-        const int i = s_list[w * K1_WLIST + (q - pre[w])];
-        const int r = i / (TW + 2), c = i - r * (TW + 2);
-        s_sc[r * SSC_W + c] = (uint8_t)fast9_score(s_in + (r + HALO - 1) * SIN_W + (c + HALO - 1), th);
+    // 3b. full score for the candidates only (dense over the CTA); corners go to a second list
+    {
+        const int nlist = s_n[0];
+        for (int q0 = 0; q0 < nlist; q0 += K1_THREADS) {
+            const int q = q0 + tid;
+            int sc = 0, e = 0;
+            if (q < nlist) {
+                e = s_list[q];
+                sc = fast9_score(s_in + e + 3 * SIN_W, th);
+                if (sc > 0) s_sc[e] = (uint8_t)sc;
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, sc > 0);
+            int base = 0;
+            if (lane == 0 && b) base = atomicAdd(&s_n[1], __popc(b));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (sc > 0) s_corner[base + __popc(b & lt_mask)] = (uint16_t)e;
+        }
+    }
+    __syncthreads();
+    // 3c. strict 3x3 NMS (cv::FAST, nonmaxSuppression = true) + the 31-px border filter of ORB::compute, tile pixels only
+    {
+        const int ncorner = s_n[1];
+        uint8_t* s_nms = reinterpret_cast<uint8_t*>(s_nmsw);
+        for (int q = tid; q < ncorner; q += K1_THREADS) {
+            const int e = s_corner[q];
+            const int r = e / SIN_W, c = e - r * SIN_W;           // r: 1 .. TH inside the tile, c: HALO .. HALO+TW-1
+            const int gx = x0 - HALO + c, gy = y0 - 1 + r;
+            if (r < 1 || r > TH || c < HALO || c >= HALO + TW) continue;
+            if (gx < kOrbEdge || gx >= W - kOrbEdge || gy < kOrbEdge || gy >= H - kOrbEdge) continue;
+            const uint8_t* sp = s_sc + e;
+            const int sv = sp[0];
+            const bool keep = sv > sp[-SIN_W - 1] && sv > sp[-SIN_W] && sv > sp[-SIN_W + 1] && sv > sp[-1] && sv > sp[1] &&
+                              sv > sp[SIN_W - 1] && sv > sp[SIN_W] && sv > sp[SIN_W + 1];
+            if (keep) s_nms[(r - 1) * TW + (c - HALO)] = (uint8_t)sv;
+        }
     }
     __syncthreads();
 
-    // 4. blur column pass + NMS / border filter; 4 pixels per thread, 32-bit stores
+    // 4. blur column pass + stores; 4 pixels per work item, 32-bit stores
     uint8_t* __restrict__ blur_out = P.blur + img_idx(slot, side) * (size_t)pitch_out * H;
     uint8_t* __restrict__ score_out = P.score + img_idx(slot, side) * (size_t)pitch_out * H;
     for (int i = tid; i < TH * TW / 4; i += K1_THREADS) {
         const int r = i / (TW / 4), c4 = (i - r * (TW / 4)) * 4;
         const int gy = y0 + r, gx = x0 + c4;
         if (gy >= H || gx >= pitch_out) continue;
-        uint32_t bw = 0, sw = 0;
         const float* rr0 = s_row + (r + 3) * TW + c4;
         const float4 m0 = *reinterpret_cast<const float4*>(rr0);
         const float4 p1 = *reinterpret_cast<const float4*>(rr0 + TW), n1 = *reinterpret_cast<const float4*>(rr0 - TW);
@@ -192,30 +269,19 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
         const float a1[4] = {p1.x, p1.y, p1.z, p1.w}, b1[4] = {n1.x, n1.y, n1.z, n1.w};
         const float a2[4] = {p2.x, p2.y, p2.z, p2.w}, b2[4] = {n2.x, n2.y, n2.z, n2.w};
         const float a3[4] = {p3.x, p3.y, p3.z, p3.w}, b3[4] = {n3.x, n3.y, n3.z, n3.w};
+        uint32_t bw = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float acc = __fmul_rn(gk(3), c0[q]);
             acc = __fmaf_rn(gk(4), __fadd_rn(a1[q], b1[q]), acc);
             acc = __fmaf_rn(gk(5), __fadd_rn(a2[q], b2[q]), acc);
             acc = __fmaf_rn(gk(6), __fadd_rn(a3[q], b3[q]), acc);
-            int v = __float2int_rn(acc);   // round half to even
-            v = min(255, max(0, v));
-            bw |= (uint32_t)v << (8 * q);
-            const int c = c4 + q;
-            const uint8_t* sp = s_sc + (r + 1) * SSC_W + (c + 1);
-            const int s = sp[0];
-            if (s > 0) {
-                const int x = gx + q;
-                bool keep = x >= kOrbEdge && x < W - kOrbEdge && gy >= kOrbEdge && gy < H - kOrbEdge;
-                if (keep) {
-                    keep = s > sp[-SSC_W - 1] && s > sp[-SSC_W] && s > sp[-SSC_W + 1] && s > sp[-1] && s > sp[1] &&
-                           s > sp[SSC_W - 1] && s > sp[SSC_W] && s > sp[SSC_W + 1];
-                }
-                sw |= (uint32_t)(keep ? s : 0) << (8 * q);
-            }
+            uint32_t v;                                  // round half to even, saturate to 0..255
+            asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(v) : "f"(acc));
+            bw |= v << (8 * q);
         }
         *reinterpret_cast<uint32_t*>(blur_out + (size_t)gy * pitch_out + gx) = bw;
-        *reinterpret_cast<uint32_t*>(score_out + (size_t)gy * pitch_out + gx) = sw;
+        *reinterpret_cast<uint32_t*>(score_out + (size_t)gy * pitch_out + gx) = s_nmsw[i];
     }
 }
 
@@ -228,6 +294,10 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
 //   E. write keypoints in final order
 // ------------------------------------------------------------------------------------------------
 constexpr int K2_THREADS = 256;
+constexpr int K2_SEGS = 4;          // 16-pixel score segments per thread per compaction round
+
+// bit 7 of every non-zero byte
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t w) { return ((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w) & 0x80808080u; }
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -300,40 +370,46 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
     const int total_segs = rows * segs;
     int base = 0;
     bool overflow = false;
-    for (int g0 = 0; g0 < total_segs; g0 += K2_THREADS) {
-        const int g = g0 + tid;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        int y = 0, x = 0;
-        if (g < total_segs) {
-            y = kOrbEdge + g / segs;
-            x = (g % segs) * 16;
-            v = *reinterpret_cast<const uint4*>(score + (size_t)y * pitch + x);
-        }
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        // bit 7 of every non-zero byte
-        uint32_t nzw[4];
+    for (int g0 = 0; g0 < total_segs; g0 += K2_THREADS * K2_SEGS) {
+        // K2_SEGS consecutive 16-pixel segments per thread, all loads in flight before the block scan
+        uint4 v[K2_SEGS];
         int cnt = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            nzw[q] = ((w[q] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w[q]) & 0x80808080u;
-            cnt += __popc(nzw[q]);
+        for (int u = 0; u < K2_SEGS; ++u) {
+            const int g = g0 + tid * K2_SEGS + u;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (g < total_segs) {
+                const int r = g / segs;
+                v[u] = *reinterpret_cast<const uint4*>(score + (size_t)(kOrbEdge + r) * pitch + (g - r * segs) * 16);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < K2_SEGS; ++u)
+            cnt += __popc(nonzero_bytes(v[u].x)) + __popc(nonzero_bytes(v[u].y)) + __popc(nonzero_bytes(v[u].z)) +
+                   __popc(nonzero_bytes(v[u].w));
         int total;
         const int off = block_exclusive_scan(cnt, s_warp, total);
         if (cnt) {
             int o = base + off;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t m = nzw[q];
-                while (m) {                              // corners are sparse: visit only the non-zero bytes, in x order
-                    const int bit = __ffs(m) - 1;        // 7, 15, 23 or 31
-                    m &= m - 1;
-                    const uint32_t sc = (w[q] >> (bit - 7)) & 0xFFu;
-                    if (o < P.p.max_corners) {
-                        s_a[o] = (sc << 24) | (uint32_t)o;
-                        cand_pos[o] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * q + (bit >> 3));
+            for (int u = 0; u < K2_SEGS; ++u) {
+                const int g = g0 + tid * K2_SEGS + u;
+                const int r = g / segs;
+                const int y = kOrbEdge + r, x = (g - r * segs) * 16;
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t m = nonzero_bytes(w[q]);
+                    while (m) {                              // corners are sparse: visit only the non-zero bytes, in x order
+                        const int bit = __ffs(m) - 1;        // 7, 15, 23 or 31
+                        m &= m - 1;
+                        const uint32_t sc = (w[q] >> (bit - 7)) & 0xFFu;
+                        if (o < P.p.max_corners) {
+                            s_a[o] = (sc << 24) | (uint32_t)o;
+                            cand_pos[o] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * q + (bit >> 3));
+                        }
+                        ++o;
                     }
-                    ++o;
                 }
             }
         }

@@ -173,6 +173,56 @@ SVO_HD void introsort_seq_c(const C& c, uint32_t* a, int n) {
     insertion_sort_(c, a, 0, n);
 }
 
+
+// Rank-table formulation of the unguarded Hoare partition of a[first..last) around the pivot at a[first]
+// (what the warp- and block-cooperative versions below compute, kept sequential here so that the host unit
+// test can pin it against unguarded_partition_):
+//   L = positions x in (first, last), ascending,  with !comp(a[x], pivot)       ("left stoppers")
+//   R = positions x in [first, last), descending, with !comp(pivot, a[x])       ("right stoppers"; x = first always is)
+//   K = #{k : L[k] < R[k]}  (a prefix, L ascends and R descends);  the pairs k < K are swapped;
+//   cut = min(L[K], R[K-1])  (the left scan of the last round stops at the next original stopper or at the
+//   stopper the previous swap moved to R[K-1], whichever comes first).
+template <class C>
+SVO_HD int ranked_partition_seq(const C& c, uint32_t* a, int first, int last, int* posL, int* posR) {
+    const uint32_t pivot = a[first];
+    int nl = 0, nr = 0;
+    for (int x = first + 1; x < last; ++x) if (!c.lt(a[x], pivot)) posL[nl++] = x;
+    for (int x = last - 1; x >= first; --x) if (!c.lt(pivot, a[x])) posR[nr++] = x;
+    int K = 0;
+    const int kmax = nl < nr ? nl : nr;
+    while (K < kmax && posL[K] < posR[K]) {
+        const uint32_t t = a[posL[K]]; a[posL[K]] = a[posR[K]]; a[posR[K]] = t;
+        ++K;
+    }
+    int cut = (K < nl) ? posL[K] : last;
+    if (K > 0 && posR[K - 1] < cut) cut = posR[K - 1];
+    return cut;
+}
+
+// introsort_seq_c with the partition in its rank-table formulation (host unit test only)
+template <class C>
+SVO_HD void introsort_seq_ranked_c(const C& c, uint32_t* a, int n, int* posL, int* posR) {
+    if (n <= 1) return;
+    int st_first[64], st_last[64], st_depth[64];
+    int sp = 0;
+    st_first[0] = 0; st_last[0] = n; st_depth[0] = 2 * floor_log2(n);
+    sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+        while (last - first > kSortThreshold) {
+            if (depth == 0) { heap_sort_(c, a + first, last - first); break; }
+            --depth;
+            median_to_first_(c, a, first, first + 1, first + (last - first) / 2, last - 1);
+            const int cut = ranked_partition_seq(c, a, first, last, posL, posR);
+            st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth;
+            ++sp;
+            last = cut;
+        }
+    }
+    insertion_sort_(c, a, 0, n);
+}
+
 template <bool Desc, int KeyShift>
 SVO_HD void introsort_seq(uint32_t* a, int n) {
     introsort_seq_c(KeyComp<Desc, KeyShift>(), a, n);
@@ -251,6 +301,81 @@ __device__ int warp_unguarded_partition(const C& c, uint32_t* a, int seg_first, 
     }
 }
 
+
+// Block-wide partition for the few large segments at the top of the recursion (one warp would walk them 32
+// elements at a time while the other warps wait): every thread classifies elements, the stoppers are ranked with
+// ballots + per-warp counts, the rank -> position tables go to scratch (16-bit positions) and the pairs k < K are
+// swapped in parallel.  Same result as ranked_partition_seq.  All threads of the block must call it.
+//   posL / posR: room for (last - first) uint16 each;  s_blk: 2 * nwarps + 1 ints of shared memory.
+constexpr int kBlockPartMin = 1024;      // segments at least this long are partitioned by the whole block
+constexpr int kBlockPartMaxList = 16;    // ... on levels with at most this many segments
+
+template <class C>
+__device__ int block_unguarded_partition(const C& c, uint32_t* a, int first, int last, uint16_t* posL, uint16_t* posR,
+                                         int* s_blk) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int* s_cl = s_blk;
+    int* s_cr = s_blk + nwarps;
+    int* s_K = s_blk + 2 * nwarps;
+    const uint32_t pivot = a[first];
+    const int per = ((last - first + nwarps * 32 - 1) / (nwarps * 32)) * 32;   // elements per warp, multiple of 32
+    const int wbeg = first + warp * per, wend = min(last, wbeg + per);
+    // A. count the stoppers of this warp's range
+    int cl = 0, cr = 0;
+    for (int x0 = wbeg; x0 < wend; x0 += 32) {
+        const int x = x0 + lane;
+        const bool in = x < wend;
+        const uint32_t v = in ? a[x] : 0u;
+        cl += __popc(__ballot_sync(0xffffffffu, in && x > first && !c.lt(v, pivot)));
+        cr += __popc(__ballot_sync(0xffffffffu, in && !c.lt(pivot, v)));
+    }
+    if (lane == 0) { s_cl[warp] = cl; s_cr[warp] = cr; }
+    if (tid == 0) *s_K = 0;
+    __syncthreads();
+    int offL = 0, offR = 0, nl = 0, nr = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int l = s_cl[w], r = s_cr[w];
+        if (w < warp) offL += l;
+        if (w > warp) offR += r;
+        nl += l; nr += r;
+    }
+    // B. rank -> position tables: left stoppers ascending, right stoppers descending
+    for (int x0 = wbeg; x0 < wend; x0 += 32) {
+        const int x = x0 + lane;
+        const bool stop = x < wend && x > first && !c.lt(a[x], pivot);
+        const unsigned m = __ballot_sync(0xffffffffu, stop);
+        if (stop) posL[offL + __popc(m & lt_mask)] = (uint16_t)x;
+        offL += __popc(m);
+    }
+    for (int x0 = wend - 1; x0 >= wbeg; x0 -= 32) {
+        const int x = x0 - lane;
+        const bool stop = x >= wbeg && !c.lt(pivot, a[x]);
+        const unsigned m = __ballot_sync(0xffffffffu, stop);
+        if (stop) posR[offR + __popc(m & lt_mask)] = (uint16_t)x;
+        offR += __popc(m);
+    }
+    __syncthreads();
+    // C. swap the pairs with L[k] < R[k] (a prefix of the pair list); no position takes part in two swaps
+    const int kmax = min(nl, nr);
+    int cnt = 0;
+    for (int k0 = 0; k0 < kmax; k0 += blockDim.x) {
+        const int k = k0 + tid;
+        bool ok = false;
+        int i = 0, j = 0;
+        if (k < kmax) { i = posL[k]; j = posR[k]; ok = i < j; }
+        if (ok) { const uint32_t t = a[i]; a[i] = a[j]; a[j] = t; }
+        cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0 && cnt) atomicAdd(s_K, cnt);
+    __syncthreads();
+    const int K = *s_K;
+    int cut = (K < nl) ? (int)posL[K] : last;
+    if (K > 0) cut = min(cut, (int)posR[K - 1]);
+    __syncthreads();       // s_blk is reused by the next call
+    return cut;
+}
+
 // Sort a[0..n) (shared memory) with all threads of the block.  listA/listB: room for n/16 + 2 entries each
 // (shared memory), s_cnt: 2 ints (shared), tmp: n words of scratch (global or shared), s_pos: 64 ints per warp.
 template <class C>
@@ -269,10 +394,33 @@ __device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, ui
         if (cntA == 0) break;
         uint2* in = cur ? listB : listA;
         uint2* out = cur ? listA : listB;
-        for (int sidx = warp; sidx < cntA; sidx += nwarps) {
+        // the few large segments at the top of the recursion: whole block, one after the other
+        const bool top = cntA <= kBlockPartMaxList && n < 65536;
+        if (top) {
+            for (int sidx = 0; sidx < cntA; ++sidx) {
+                const uint2 e = in[sidx];
+                const int first = (int)e.x, last = (int)(e.y & 0xFFFFFFu);
+                const int depth = (int)(e.y >> 24);
+                if (depth == 0 || last - first < kBlockPartMin) continue;
+                if (tid == 0) median_to_first_(c, a, first, first + 1, first + (last - first) / 2, last - 1);
+                __syncthreads();
+                uint16_t* pos16 = reinterpret_cast<uint16_t*>(tmp);
+                const int cut = block_unguarded_partition(c, a, first, last, pos16, pos16 + n, s_pos);
+                if (tid == 0) {
+                    if (last - cut > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)cut, (unsigned)last | ((unsigned)(depth - 1) << 24));
+                    if (cut - first > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)first, (unsigned)cut | ((unsigned)(depth - 1) << 24));
+                }
+            }
+        }
+        int small_idx = 0;
+        for (int sidx = top ? 0 : warp; sidx < cntA; sidx += top ? 1 : nwarps) {
             const uint2 e = in[sidx];
             const int first = (int)e.x, last = (int)(e.y & 0xFFFFFFu);
             int depth = (int)(e.y >> 24);
+            if (top) {
+                if (depth != 0 && last - first >= kBlockPartMin) continue;      // done by the block above
+                if ((small_idx++ % nwarps) != warp) continue;
+            }
             if (depth == 0) {                          // depth limit hit: heap sort, no children
                 if (lane == 0) heap_sort_(c, a + first, last - first);
                 __syncwarp();

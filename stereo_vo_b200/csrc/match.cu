@@ -24,21 +24,29 @@ constexpr int HM_THREADS = 128;
 constexpr int HM_QPT = 2;
 constexpr int HM_TILE = 512;   // train rows per shared-memory tile (16 KB)
 
-// 256-bit Hamming distance with a carry-save (Harley-Seal) adder tree: the eight XOR words are compressed
-// bit-sliced into ones/twos/fours/eights planes with LOP3 full adders, so only 4 POPC are needed instead of 8
-// (POPC issues at a quarter of the LOP3 rate).
-__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
-__device__ __forceinline__ int hamming256(const uint4& qa, const uint4& qb, const uint4& ta, const uint4& tb) {
+// 256-bit Hamming distance with a carry-save adder tree: four LOP3 full adders compress the eight XOR words
+// into two weight-1 planes (s3, w7), one weight-2 plane (t1) and one weight-4 plane (f1), so 4 POPC are needed
+// instead of 8 (POPC issues at a quarter of the LOP3 rate) for 16 LOP3 in total; the weighted sum and the
+// (distance << 16 | index) packing are IMADs (FMA pipe), leaving the ALU pipe 16 LOP3 + 1 min per pair-distance.
+// The full adders are written as explicit LOP3s (sum = 0x96, carry = 0xE8): left to itself nvcc re-associates the
+// query XORs into the adders and ends up with 19 LOP3 per pair-distance instead of 16.
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ uint32_t hamming256_packed(const uint4& qa, const uint4& qb, const uint4& ta, const uint4& tb,
+                                                      uint32_t idx) {
     const uint32_t w0 = qa.x ^ ta.x, w1 = qa.y ^ ta.y, w2 = qa.z ^ ta.z, w3 = qa.w ^ ta.w;
     const uint32_t w4 = qb.x ^ tb.x, w5 = qb.y ^ tb.y, w6 = qb.z ^ tb.z, w7 = qb.w ^ tb.w;
-    const uint32_t s1 = w0 ^ w1 ^ w2, c1 = maj3(w0, w1, w2);
-    const uint32_t s2 = w3 ^ w4 ^ w5, c2 = maj3(w3, w4, w5);
-    const uint32_t s3 = s1 ^ s2 ^ w6, c3 = maj3(s1, s2, w6);
-    const uint32_t ones = s3 ^ w7, c4 = s3 & w7;
-    const uint32_t t1 = c1 ^ c2 ^ c3, f1 = maj3(c1, c2, c3);
-    const uint32_t twos = t1 ^ c4, f2 = t1 & c4;
-    const uint32_t fours = f1 ^ f2, eights = f1 & f2;
-    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+    const uint32_t s1 = lop3_xor3(w0, w1, w2), c1 = lop3_maj3(w0, w1, w2);
+    const uint32_t s2 = lop3_xor3(w3, w4, w5), c2 = lop3_maj3(w3, w4, w5);
+    const uint32_t s3 = lop3_xor3(s1, s2, w6), c3 = lop3_maj3(s1, s2, w6);
+    const uint32_t t1 = lop3_xor3(c1, c2, c3), f1 = lop3_maj3(c1, c2, c3);
+    const uint32_t x = (uint32_t)__popc(t1) * 2u + (uint32_t)__popc(s3);
+    const uint32_t y = (uint32_t)__popc(f1) * 4u + (uint32_t)__popc(w7);
+    return y * 65536u + (x * 65536u + idx);
 }
 
 struct HammingProblem {
@@ -91,8 +99,7 @@ __device__ __forceinline__ void hamming_body(const HammingProblem& h, uint4* s_t
             const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
 #pragma unroll
             for (int r = 0; r < HM_QPT; ++r) {
-                const int d = hamming256(qa[r], qb[r], ta, tb);
-                best[r] = min(best[r], ((uint32_t)d << 16) | (uint32_t)(t0 + j));
+                best[r] = min(best[r], hamming256_packed(qa[r], qb[r], ta, tb, (uint32_t)(t0 + j)));
             }
         }
     }

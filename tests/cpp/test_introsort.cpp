@@ -21,6 +21,16 @@ static void check(const std::vector<uint32_t>& keys, const char* what) {
     std::vector<uint32_t> w(n);
     for (int i = 0; i < n; ++i) w[i] = (keys[i] << Shift) | (uint32_t)i;
     svo::introsort_seq<Desc, Shift>(w.data(), n);
+    // the rank-table formulation of the partition (what the warp / block kernels compute) must agree too
+    std::vector<uint32_t> w2(n);
+    for (int i = 0; i < n; ++i) w2[i] = (keys[i] << Shift) | (uint32_t)i;
+    std::vector<int> pl(n + 1), pr(n + 1);
+    svo::introsort_seq_ranked_c(svo::KeyComp<Desc, Shift>(), w2.data(), n, pl.data(), pr.data());
+    if (w2 != w) {
+        if (g_fail < 5) std::printf("MISMATCH (ranked partition) %s n=%d\n", what, n);
+        ++g_fail;
+        return;
+    }
     ++g_cases;
     for (int i = 0; i < n; ++i)
         if ((w[i] & ((1u << Shift) - 1)) != idx[i]) {
