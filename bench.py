@@ -400,10 +400,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ---------------------------------------------------------------------
+    if args.chunks:
+        ctx.set_concurrency(args.chunks)
     for t in range(args.warmup):
         step_device(t)
     ctx.synchronize()
-    ctx.enable_stage_timing(True)
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ctx.kernel_launches()
@@ -418,6 +419,16 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     launches = ctx.kernel_launches() - launches0
     sampler.stop_flag = True
+    # ---- per-kernel times: the same steps once more with one CUDA event after every kernel.  In this pass the
+    #      library keeps the whole batch on one stream, so each kernel is timed alone (in the headline pass above,
+    #      groups of slots run on concurrent streams and their kernels overlap) ------------------------------
+    n_kt = min(args.steps, 8)
+    ctx.enable_stage_timing(True)
+    t_ser0 = time.perf_counter()
+    for k in range(n_kt):
+        step_device(args.warmup + args.steps + k)
+    ctx.synchronize()
+    serial_ms = 1e3 * (time.perf_counter() - t_ser0) / n_kt
     kernel_ms = ctx.stage_times()
     pipe = ctx.pipe_peaks()
     ctx.enable_stage_timing(False)
@@ -449,7 +460,7 @@ def run_gpu(args):
         if rc < 0:
             raise RuntimeError(lib.svo_last_error(ctx._h).decode())
 
-    base_t = args.warmup + args.steps
+    base_t = args.warmup + args.steps + n_kt
     for t in range(max(2, args.warmup)):            # warm-up through the same public calls
         submit(base_t + t)
         wait(t)
@@ -507,6 +518,9 @@ def run_gpu(args):
             "config": {"workload": "c2: 640x480 synthetic stereo sequences, 1000 ORB kp, full FAST+ORB detect / L-R match / "
                                    "tracking + F-matrix RANSAC / Gauss-Newton path",
                        "pairs_per_step_per_gpu": B, "distinct_sequences": N_SEQ,
+                       "streams": "slots of a step run in %s groups on concurrent streams (value, e2e); the per-kernel times "
+                                  "and the roofline come from a serialised pass of the same steps (%.3f ms per step)"
+                                  % (args.chunks or "the library's default (4)", serial_ms),
                        "l2": f"inputs larger than L2: {2 * B * W * H / 1e6:.0f} MB of images per step per GPU, "
                              f"{period} distinct batches cycled",
                        "keypoints_per_image": Nkp, "stereo_matches": M, "tracked_pairs": T,
@@ -551,6 +565,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=300, help="cpu_baseline: pairs per process")
     ap.add_argument("--ref-pairs", type=int, default=100, help="--impl reference: pairs per process per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--chunks", type=int, default=0, help="groups of slots on concurrent streams (0 = library default)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = the headline pipeline; c5 = Hamming microbench")
     ap.add_argument("--c5-reps", type=int, default=64, help="c5: independent 4096x4096 problems per GPU per step")
     args = ap.parse_args()

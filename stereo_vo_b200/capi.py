@@ -31,7 +31,7 @@ EXPORTS = [
     "svo_get_residuals", "svo_get_outliers", "svo_get_track_candidates", "svo_get_plane",
     "svo_detect", "svo_match_hamming", "svo_match_hamming_device", "svo_match_lr", "svo_get_change_in_pose",
     "svo_fundmat_ransac", "svo_abi_version", "svo_kernel_launches", "svo_stream",
-    "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks",
+    "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks", "svo_set_concurrency",
 ]
 
 
@@ -321,6 +321,9 @@ class Context:
 
     def stream(self):
         return lib().svo_stream(self._h)
+
+    def set_concurrency(self, chunks):
+        self._check(lib().svo_set_concurrency(self._h, int(chunks)))
 
     def enable_stage_timing(self, on=True):
         self._check(lib().svo_enable_stage_timing(self._h, int(on)))

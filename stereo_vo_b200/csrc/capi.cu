@@ -31,6 +31,8 @@ static const char* kKernelNames[KT_COUNT] = {
     "hamming_kernel(track)", "track_filter_kernel", "ransac_prepare_kernel", "fundmat_kernel", "consistency_kernel",
     "gn_kernel"};
 
+enum { kMaxChunks = 8, kDefaultChunks = 4, kMinChunkItems = 32 };
+
 struct svo_ctx {
     svo_config cfg;
     Pools P;
@@ -70,6 +72,10 @@ struct svo_ctx {
     std::string err;
     int launches_i = 0;
     int64_t launches = 0;
+    // concurrency inside one step: groups of batch items on their own streams (see run_step)
+    int chunks = kDefaultChunks;
+    cudaStream_t aux[kMaxChunks] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {};
     int timing = 0;
     std::vector<cudaEvent_t> ev;      // KT_DEPTH sets of KT_COUNT+1 events
     int timed_steps = 0;              // steps recorded since timing was enabled
@@ -125,29 +131,59 @@ __global__ void reset_slot_kernel(Pools P, int slot) {
 bool valid_slot(const svo_ctx* c, int slot) { return slot >= 0 && slot < c->cfg.max_seqs; }
 
 
-// enqueue one pipeline step on device images
+// enqueue the kernels of one pipeline step for the batch items [a, a + n) on stream st
+int enqueue_items(svo_ctx* c, int a, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride, size_t image_pitch,
+                  bool have_repeat, cudaStream_t st, int& L, StepTimer* t) {
+    Pools P = c->P;
+    P.slots += a;                                   // batch item i of this chunk = item a + i of the step
+    RansacScratch RS = c->RS;
+    RS.slots = P.slots;
+    if (t) t->mark(st);
+    scatter_cams_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, c->d_cams_batch + a, n);
+    CU(c, launch_begin_step(P, n, have_repeat ? c->d_repeat + a : nullptr, st));
+    if (t) t->mark(st);
+    L += 2;
+    const size_t img2 = 2 * (size_t)a;              // scratch indexed by (item, side)
+    CU(c, launch_detect(P, n, d_left + a * image_pitch, d_right + a * image_pitch, stride, image_pitch, c->pitch,
+                        c->d_occ + img2 * c->occ_words, c->occ_words, c->d_sort_scratch + img2 * c->cfg.max_corners,
+                        c->d_list_scratch + img2 * 2 * (c->cfg.max_corners / 16 + 2), st, &L, t));
+    CU(c, launch_match_lr(P, n, st, &L, t));
+    CU(c, launch_track_match(P, n, st, &L, t));
+    if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, RS, n, st, &L, t));
+    else if (t) { t->mark(st); t->mark(st); }
+    CU(c, launch_consistency(P, n, st, &L, t));
+    CU(c, launch_gn(P, c->G, n, /*external=*/0, /*custom pose=*/0, /*assume_fast_kps=*/1, st, &L, t));
+    return SVO_OK;
+}
+
+// enqueue one pipeline step on device images.  Large batches are split into `chunks` groups of slots that run
+// the same kernel sequence on their own streams (forked from / joined into the context's stream): the
+// latency-bound kernels of one group (sort emulation, RANSAC, Gauss-Newton) then share the SMs with the
+// issue-bound kernels of another (FAST, Hamming) instead of leaving them idle.  With per-kernel timing on, the
+// step runs on the one stream so that every kernel is timed alone.
 int run_step(svo_ctx* c, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride, size_t image_pitch,
              bool have_repeat) {
-    Pools& P = c->P;
     int& L = c->launches_i;
     L = 0;
     StepTimer tm;
     if (c->timing && !c->ev.empty()) tm.ev = c->ev.data() + (size_t)(c->timed_steps % KT_DEPTH) * (KT_COUNT + 1);
     StepTimer* t = tm.ev ? &tm : nullptr;
-    if (t) t->mark(c->stream);
-    scatter_cams_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(P, c->d_cams_batch, n);
-    CU(c, launch_begin_step(P, n, have_repeat ? c->d_repeat : nullptr, c->stream));
-    if (t) t->mark(c->stream);
-    L += 2;
-    CU(c, launch_detect(P, n, d_left, d_right, stride, image_pitch, c->pitch, c->d_occ, c->occ_words,
-                        c->d_sort_scratch, c->d_list_scratch, c->stream, &L, t));
-    CU(c, launch_match_lr(P, n, c->stream, &L, t));
-    CU(c, launch_track_match(P, n, c->stream, &L, t));
-    if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, c->RS, n, c->stream, &L, t));
-    else if (t) { t->mark(c->stream); t->mark(c->stream); }
-    CU(c, launch_consistency(P, n, c->stream, &L, t));
-    CU(c, launch_gn(P, c->G, n, /*external=*/0, /*custom pose=*/0, /*assume_fast_kps=*/1, c->stream, &L, t));
-    if (t) { c->marks_last = tm.next; ++c->timed_steps; }
+    int chunks = std::min(c->chunks, n / kMinChunkItems);
+    if (t || chunks < 2) {
+        int rc = enqueue_items(c, 0, n, d_left, d_right, stride, image_pitch, have_repeat, c->stream, L, t);
+        if (rc != SVO_OK) return rc;
+        if (t) { c->marks_last = tm.next; ++c->timed_steps; }
+    } else {
+        CU(c, cudaEventRecord(c->ev_fork, c->stream));
+        for (int j = 0; j < chunks; ++j) {
+            const int a = (int)((long long)n * j / chunks), b = (int)((long long)n * (j + 1) / chunks);
+            CU(c, cudaStreamWaitEvent(c->aux[j], c->ev_fork, 0));
+            int rc = enqueue_items(c, a, b - a, d_left, d_right, stride, image_pitch, have_repeat, c->aux[j], L, nullptr);
+            if (rc != SVO_OK) return rc;
+            CU(c, cudaEventRecord(c->ev_join[j], c->aux[j]));
+            CU(c, cudaStreamWaitEvent(c->stream, c->ev_join[j], 0));
+        }
+    }
     c->launches += L;
     return SVO_OK;
 }
@@ -309,6 +345,11 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
 #undef HA
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    for (int j = 0; j < kMaxChunks && e == cudaSuccess; ++j) {
+        e = cudaStreamCreateWithFlags(&c->aux[j], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[j], cudaEventDisableTiming);
+    }
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
         e = cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming);
@@ -332,6 +373,11 @@ void svo_destroy(svo_ctx* c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int b = 0; b < 2; ++b) { if (c->ev_h2d[b]) cudaEventDestroy(c->ev_h2d[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
+    for (int j = 0; j < kMaxChunks; ++j) {
+        if (c->aux[j]) { cudaStreamSynchronize(c->aux[j]); cudaStreamDestroy(c->aux[j]); }
+        if (c->ev_join[j]) cudaEventDestroy(c->ev_join[j]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (void* p : c->dev_allocs) cudaFree(p);
     for (void* p : c->host_allocs) cudaFreeHost(p);
@@ -353,6 +399,13 @@ int svo_synchronize(svo_ctx* c) {
 }
 
 void* svo_stream(svo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int svo_set_concurrency(svo_ctx* c, int32_t chunks) {
+    if (!c) return SVO_ERR_ARG;
+    if (chunks < 1 || chunks > kMaxChunks) return fail(c, SVO_ERR_ARG, "chunks must be within [1, 8]");
+    c->chunks = chunks;
+    return SVO_OK;
+}
 int64_t svo_kernel_launches(const svo_ctx* c) { return c ? c->launches : 0; }
 
 int svo_measure_pipe_peaks(svo_ctx* c, double* popc_per_s, double* lop3_per_s) {

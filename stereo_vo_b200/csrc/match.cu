@@ -21,7 +21,7 @@ namespace svo {
 // 32 B per descriptor once (L2 serves the re-reads of the train tile by the other CTAs).
 // ------------------------------------------------------------------------------------------------
 constexpr int HM_THREADS = 128;
-constexpr int HM_QPT = 2;
+constexpr int HM_QPT = 2;     // queries per thread (hamming_body dispatches on 1 or 2 live groups per warp)
 constexpr int HM_TILE = 512;   // train rows per shared-memory tile (16 KB)
 
 // 256-bit Hamming distance with a carry-save adder tree: four LOP3 full adders compress the eight XOR words
@@ -76,16 +76,33 @@ __device__ __forceinline__ HammingProblem pipeline_problem(const Pools& P, int m
     return h;
 }
 
+// inner loop over one staged train tile for NQ queries per thread (NQ is warp-uniform)
+template <int NQ>
+__device__ __forceinline__ void hamming_tile(const uint4* __restrict__ s_t, int rows, int t0, const uint4* qa, const uint4* qb,
+                                             uint32_t* best) {
+#pragma unroll 4
+    for (int j = 0; j < rows; ++j) {
+        const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
+#pragma unroll
+        for (int r = 0; r < NQ; ++r) best[r] = min(best[r], hamming256_packed(qa[r], qb[r], ta, tb, (uint32_t)(t0 + j)));
+    }
+}
+
 __device__ __forceinline__ void hamming_body(const HammingProblem& h, uint4* s_t) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q0 = blockIdx.x * (HM_THREADS * HM_QPT);
     if (q0 >= h.nq) return;
+    // a warp owns 32 * HM_QPT consecutive queries; groups of 32 that lie beyond nq are skipped by the whole warp
+    // (a ragged last CTA then costs what its queries cost, not a full CTA)
+    const int wq0 = q0 + warp * (32 * HM_QPT);
+    int nq_w = 0;                                   // query groups of this warp with at least one valid query
     uint4 qa[HM_QPT], qb[HM_QPT];
     uint32_t best[HM_QPT];
 #pragma unroll
     for (int r = 0; r < HM_QPT; ++r) {
-        const int qi = q0 + r * HM_THREADS + tid;
+        const int qi = wq0 + r * 32 + lane;
         best[r] = 0xFFFFFFFFu;
+        if (wq0 + r * 32 < h.nq) nq_w = r + 1;
         if (qi < h.nq) { qa[r] = h.q[2 * (size_t)qi]; qb[r] = h.q[2 * (size_t)qi + 1]; }
         else { qa[r] = make_uint4(0, 0, 0, 0); qb[r] = qa[r]; }
     }
@@ -94,18 +111,12 @@ __device__ __forceinline__ void hamming_body(const HammingProblem& h, uint4* s_t
         __syncthreads();
         for (int i = tid; i < rows * 2; i += HM_THREADS) s_t[i] = h.t[2 * (size_t)t0 + i];
         __syncthreads();
-#pragma unroll 4
-        for (int j = 0; j < rows; ++j) {
-            const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
-#pragma unroll
-            for (int r = 0; r < HM_QPT; ++r) {
-                best[r] = min(best[r], hamming256_packed(qa[r], qb[r], ta, tb, (uint32_t)(t0 + j)));
-            }
-        }
+        if (nq_w == HM_QPT) hamming_tile<HM_QPT>(s_t, rows, t0, qa, qb, best);
+        else if (nq_w == 1) hamming_tile<1>(s_t, rows, t0, qa, qb, best);
     }
 #pragma unroll
     for (int r = 0; r < HM_QPT; ++r) {
-        const int qi = q0 + r * HM_THREADS + tid;
+        const int qi = wq0 + r * 32 + lane;
         if (qi < h.nq) h.out[qi] = best[r];
     }
 }
