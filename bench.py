@@ -169,7 +169,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -273,6 +273,45 @@ def c5_microbench(ctx, torch, stream, device, pipe, peak, reps=64, iters=10, swe
     return res, (q, t, out)
 
 
+
+def stage1_microbench(ctx, torch, stream, device, W, H, peak, n=128, iters=5):
+    """stage 1 on the device (gray conversion + rectification, csrc/prepare.cu): HBM-bound streaming kernels, timed
+    alone on n stereo pairs (inputs larger than L2).  Algorithmic bytes per output pixel: channels (source) + 1."""
+    pitch = (W + 15) & ~15
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+    r2 = ((xs - W / 2) / W) ** 2 + ((ys - H / 2) / W) ** 2
+    maps = []
+    for side in (0, 1):          # mild radial distortion, CV_16SC2 + CV_16UC1 layout of cv::initUndistortRectifyMap
+        fx = np.rint((xs + (xs - W / 2) * (-0.06 + 0.02 * side) * r2) * 32).astype(np.int64)
+        fy = np.rint((ys + (ys - H / 2) * (-0.06 + 0.02 * side) * r2) * 32).astype(np.int64)
+        maps.append((np.stack([fx >> 5, fy >> 5], -1).astype(np.int16), ((fy & 31) * 32 + (fx & 31)).astype(np.uint16)))
+    out = {}
+    dst = [torch.zeros((n, H, pitch), dtype=torch.uint8, device=device) for _ in range(2)]
+    for ch, rect in ((3, True), (1, True), (3, False)):
+        if rect:
+            ctx.set_rectify_maps(maps[0][0], maps[0][1], maps[1][0], maps[1][1])
+        else:
+            ctx.set_rectify_maps()
+        src = [torch.randint(0, 256, (n, H, W * ch), dtype=torch.uint8, device=device) for _ in range(2)]
+        tot = 0.0
+        for it in range(iters + 2):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.prepare_rectify_device(src[0].data_ptr(), src[1].data_ptr(), n, W * ch, H * W * ch, ch, dst[0].data_ptr(), dst[1].data_ptr())
+            e1.record(stream)
+            e1.synchronize()
+            if it >= 2:
+                tot += e0.elapsed_time(e1)
+        ms = tot / iters
+        ab = 2 * n * W * H * (ch + 1)
+        out["%s%s" % ("bgr" if ch == 3 else "gray", "+rectify" if rect else "->gray")] = {
+            "ms": round(ms, 4), "pairs": n, "algo_bytes": ab, "hbm_gbs": round(ab / (ms * 1e-3) / 1e9, 1),
+            "hbm_frac": round(ab / (ms * 1e-3) / 1e9 / peak, 4)}
+        del src
+    ctx.set_rectify_maps()
+    return out
+
 def run_c5(args):
     """--workload c5: the microbench on N GPUs.  Query rows are sharded across the ranks, the train set is
     replicated (broadcast from rank 0), the packed results are all-gathered (the one exchange step, NCCL)."""
@@ -347,7 +386,7 @@ def run_c5(args):
                              "unit": "GB/s", "frac": ab / (kms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                              "note": "N x N brute force is integer-pipe bound (ridge at NR ~ 8); see sweep for the HBM-bound regime"},
                 "match_microbench": micro, "clocks": sampler.summary()}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -510,7 +549,8 @@ def run_gpu(args):
         pairdist = B * (Nkp * Nkp + 2 * M * M)
         clocks = sampler.summary()
         int_roof = 1.0 / max(HM_POPC / pipe["popc_per_s"], HM_ALU / pipe["lop3_per_s"])
-        micro, _ = c5_microbench(ctx, torch, stream, torch.device("cuda", local), pipe, peak, reps=32, iters=5)
+        micro, _ = c5_microbench(ctx, torch, stream, torch.device("cuda", local), pipe, peak, reps=64, iters=5)
+        stage1 = stage1_microbench(ctx, torch, stream, torch.device("cuda", local), W, H, peak)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -541,6 +581,7 @@ def run_gpu(args):
                             "ops_per_pair_distance": {"popc": HM_POPC, "alu": HM_ALU},
                             "hbm_gbs": (ab["hamming_kernel(lr)"] + ab["hamming_kernel(track)"]) / (hm_ms * 1e-3) / 1e9 if hm_ms else None},
             "match_microbench": micro,
+            "stage1": stage1,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -548,14 +589,31 @@ def run_gpu(args):
             procs = os.cpu_count() or 1
             v, info = cpu_throughput(seqs_cpu, cam, args.cpu_pairs, procs)
             line["cpu_baseline"] = dict(info, value=v, unit=UNIT)
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line on the real stdout (everything else, NCCL's version banner included, goes to stderr)"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                    # libraries that print to stdout (NCCL banner) must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

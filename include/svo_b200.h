@@ -127,7 +127,8 @@ int  svo_reset_slot(svo_ctx* ctx, int32_t slot);                /* fresh estimat
 
 /* ---- the pipeline: processNewImagePair (process_new_image_pair.cpp:41-385) ----------------- */
 /* One call == one processNewImagePair per listed slot, all slots advanced together on the GPU.
- * left/right: n pointers to 8-bit gray, rectified images (host memory), row stride in bytes.
+ * left/right: n pointers to 8-bit images (host memory), row stride in bytes: gray and rectified unless
+ * svo_set_input_format / svo_set_rectify_maps say otherwise (stage 1 then runs on the device).
  * slots: n distinct slot indices (NULL = 0..n-1).  cams: n cameras (one per slot).
  * repeat: request_data.repeat per slot (NULL = all false).  results: n entries (host). */
 int svo_process_batch(svo_ctx* ctx, int32_t n, const int32_t* slots,
@@ -171,6 +172,30 @@ int svo_get_outliers(svo_ctx* ctx, int32_t slot, int64_t* out, int32_t cap);
  * and the two RANSAC inlier masks (stage4_match_consecutive.cpp:145-160, 202, 237) */
 int svo_get_track_candidates(svo_ctx* ctx, int32_t slot, int32_t* out_query, int32_t* out_trainL,
                              int32_t* out_trainR, uint8_t* out_inlL, uint8_t* out_inlR, int32_t cap);
+
+/* ---- stage 1: stage1_prepare_rectify (stage1_rectify.cpp:37-93), nOctaves = 1 ---------------- */
+/* Input format of svo_process_batch / svo_submit_batch / svo_process_pair: channels = 1 (8-bit gray, the default)
+ * or 3 (8-bit BGR, as MRPT / OpenCV hold colour images; row stride in bytes).  Colour input is converted on the
+ * device like mrpt::utils::CImage(img, FAST_REF_OR_CONVERT_TO_GRAY) = cv::cvtColor(BGR2GRAY)
+ * (stage1_rectify.cpp:51-52). */
+int svo_set_input_format(svo_ctx* ctx, int32_t channels);
+/* Rectification maps of the stereo camera: what mrpt::vision::CStereoRectifyMap::setFromCamParams precomputes on
+ * first use (stage1_rectify.cpp:69-70) with cv::initUndistortRectifyMap(..., CV_16SC2): map_xy = H*W int16 pairs
+ * (x, y), map_a = H*W uint16 interpolation-table indices, per side.  Once set, every image given to
+ * svo_process_batch / svo_submit_batch / svo_process_pair is rectified on the device like
+ * CStereoRectifyMap::rectify = cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) (stage1_rectify.cpp:72-74).
+ * Four NULLs: images are rectified already (obs->areImagesRectified(), stage1_rectify.cpp:61-65). */
+int svo_set_rectify_maps(svo_ctx* ctx, const int16_t* map_xy_left, const uint16_t* map_a_left,
+                         const int16_t* map_xy_right, const uint16_t* map_a_right);
+/* stage 1 alone on one host stereo pair: out_left / out_right receive height*width gray (rectified) bytes */
+int svo_prepare_rectify(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t stride_bytes, int32_t channels,
+                        uint8_t* out_left, uint8_t* out_right);
+/* device-resident variant for n pairs (source image i at d_left + i*image_pitch); the outputs are planes with a
+ * row pitch of width rounded up to 16 and height*pitch bytes per image: the layout svo_process_batch_device takes
+ * with stride = pitch, image_pitch = height*pitch.  Only enqueues work on the context's stream. */
+int svo_prepare_rectify_device(svo_ctx* ctx, int32_t n, const uint8_t* d_left, const uint8_t* d_right,
+                               size_t stride_bytes, size_t image_pitch, int32_t channels,
+                               uint8_t* d_out_left, uint8_t* d_out_right);
 
 /* ---- per-stage entries (the internal seams, usable on their own) ---------------------------- */
 /* FAST + ORB::compute + m_non_max_sup + m_update_indexes for one host image

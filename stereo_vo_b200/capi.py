@@ -32,6 +32,7 @@ EXPORTS = [
     "svo_detect", "svo_match_hamming", "svo_match_hamming_device", "svo_match_lr", "svo_get_change_in_pose",
     "svo_fundmat_ransac", "svo_abi_version", "svo_kernel_launches", "svo_stream",
     "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks", "svo_set_concurrency",
+    "svo_set_input_format", "svo_set_rectify_maps", "svo_prepare_rectify", "svo_prepare_rectify_device",
 ]
 
 
@@ -158,7 +159,7 @@ class Context:
         L = [np.ascontiguousarray(a, np.uint8) for a in left]
         R = [np.ascontiguousarray(a, np.uint8) for a in right]
         n = len(L)
-        H, W = L[0].shape
+        H, W = L[0].shape[:2]
         assert (H, W) == (self.cfg.height, self.cfg.width)
         lp = (C.c_void_p * n)(*[a.ctypes.data for a in L])
         rp = (C.c_void_p * n)(*[a.ctypes.data for a in R])
@@ -166,7 +167,7 @@ class Context:
         sl = None if slots is None else (C.c_int32 * n)(*slots)
         rep = None if repeat is None else (C.c_uint8 * n)(*[1 if r else 0 for r in repeat])
         res = (Result * n)()
-        self._check(lib().svo_process_batch(self._h, n, sl, lp, rp, C.c_size_t(W), cam_arr, rep, res))
+        self._check(lib().svo_process_batch(self._h, n, sl, lp, rp, C.c_size_t(L[0].strides[0]), cam_arr, rep, res))
         return list(res)
 
     def submit_batch(self, left, right, cams, slots=None, repeat=None):
@@ -174,13 +175,12 @@ class Context:
         L = [np.ascontiguousarray(a, np.uint8) for a in left]
         R = [np.ascontiguousarray(a, np.uint8) for a in right]
         n = len(L)
-        W = L[0].shape[1]
         lp = (C.c_void_p * n)(*[a.ctypes.data for a in L])
         rp = (C.c_void_p * n)(*[a.ctypes.data for a in R])
         cam_arr = (Camera * n)(*cams)
         sl = None if slots is None else (C.c_int32 * n)(*slots)
         rep = None if repeat is None else (C.c_uint8 * n)(*[1 if r else 0 for r in repeat])
-        self._check(lib().svo_submit_batch(self._h, n, sl, lp, rp, C.c_size_t(W), cam_arr, rep))
+        self._check(lib().svo_submit_batch(self._h, n, sl, lp, rp, C.c_size_t(L[0].strides[0]), cam_arr, rep))
         self._inflight = getattr(self, "_inflight", []) + [(L, R, n)]
 
     def wait_batch(self):
@@ -193,7 +193,7 @@ class Context:
         left = np.ascontiguousarray(left, np.uint8)
         right = np.ascontiguousarray(right, np.uint8)
         res = Result()
-        self._check(lib().svo_process_pair(self._h, _vp(left), _vp(right), C.c_size_t(left.shape[1]), C.byref(cam),
+        self._check(lib().svo_process_pair(self._h, _vp(left), _vp(right), C.c_size_t(left.strides[0]), C.byref(cam),
                                            int(bool(repeat)), C.byref(res)))
         return res
 
@@ -321,6 +321,35 @@ class Context:
 
     def stream(self):
         return lib().svo_stream(self._h)
+
+    # ---- stage 1 ----------------------------------------------------------------------------------------
+    def set_input_format(self, channels):
+        self._check(lib().svo_set_input_format(self._h, int(channels)))
+
+    def set_rectify_maps(self, map_xy_left=None, map_a_left=None, map_xy_right=None, map_a_right=None):
+        if map_xy_left is None:
+            self._check(lib().svo_set_rectify_maps(self._h, None, None, None, None))
+            return
+        H, W = self.cfg.height, self.cfg.width
+        mx = [np.ascontiguousarray(m, np.int16).reshape(H, W, 2) for m in (map_xy_left, map_xy_right)]
+        ma = [np.ascontiguousarray(m, np.uint16).reshape(H, W) for m in (map_a_left, map_a_right)]
+        self._check(lib().svo_set_rectify_maps(self._h, _vp(mx[0]), _vp(ma[0]), _vp(mx[1]), _vp(ma[1])))
+
+    def prepare_rectify(self, left, right):
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        ch = 1 if left.ndim == 2 else left.shape[2]
+        H, W = self.cfg.height, self.cfg.width
+        assert left.shape[:2] == (H, W) and right.shape == left.shape
+        oL = np.zeros((H, W), np.uint8)
+        oR = np.zeros((H, W), np.uint8)
+        self._check(lib().svo_prepare_rectify(self._h, _vp(left), _vp(right), C.c_size_t(W * ch), ch, _vp(oL), _vp(oR)))
+        return oL, oR
+
+    def prepare_rectify_device(self, d_left, d_right, n, stride, image_pitch, channels, d_out_left, d_out_right):
+        self._check(lib().svo_prepare_rectify_device(self._h, n, C.c_void_p(d_left), C.c_void_p(d_right), C.c_size_t(stride),
+                                                     C.c_size_t(image_pitch), channels, C.c_void_p(d_out_left),
+                                                     C.c_void_p(d_out_right)))
 
     def set_concurrency(self, chunks):
         self._check(lib().svo_set_concurrency(self._h, int(chunks)))

@@ -6,6 +6,7 @@
 #include "gn.cuh"
 #include "match.cuh"
 #include "microbench.cuh"
+#include "prepare.cuh"
 #include "ransac.cuh"
 #include "svo_internal.cuh"
 
@@ -72,6 +73,15 @@ struct svo_ctx {
     std::string err;
     int launches_i = 0;
     int64_t launches = 0;
+    // stage 1 on the device (gray conversion / rectification): input format, maps, raw staging (allocated on demand)
+    int in_channels = 1;
+    bool rectify = false;
+    short2* d_map_xy[2] = {nullptr, nullptr};
+    uint16_t* d_map_a[2] = {nullptr, nullptr};
+    uint8_t* d_raw[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][side]
+    uint8_t* d_gray[2] = {nullptr, nullptr};                           // gray planes between conversion and rectification
+    size_t raw_pitch = 0;             // bytes per row of the raw staging images
+    int raw_channels = 0;
     // concurrency inside one step: groups of batch items on their own streams (see run_step)
     int chunks = kDefaultChunks;
     cudaStream_t aux[kMaxChunks] = {};
@@ -221,6 +231,37 @@ int get_state(svo_ctx* c, int slot, SlotState* s) {
 }
 
 int frame_buf(const SlotState& s, int which) { return which == 0 ? s.cur : (s.cur ^ 1); }
+
+bool needs_stage1(const svo_ctx* c) { return c->in_channels != 1 || c->rectify; }
+
+// raw staging for inputs that go through stage 1 on the device (colour and / or unrectified images)
+int ensure_raw_staging(svo_ctx* c) {
+    if (c->d_raw[0][0] && c->raw_channels >= c->in_channels) return SVO_OK;
+    for (int b = 0; b < 2; ++b) for (int sd = 0; sd < 2; ++sd) c->d_raw[b][sd] = nullptr;   // old buffers stay in dev_allocs
+    c->raw_channels = c->in_channels;
+    c->raw_pitch = ((size_t)c->cfg.width * c->raw_channels + 15) & ~(size_t)15;
+    for (int b = 0; b < 2; ++b)
+        for (int sd = 0; sd < 2; ++sd) {
+            cudaError_t e = dalloc(c, &c->d_raw[b][sd], (size_t)c->n_slots_alloc * c->raw_pitch * c->cfg.height);
+            if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc raw staging");
+        }
+    for (int sd = 0; sd < 2 && c->raw_channels == 3 && !c->d_gray[sd]; ++sd) {
+        cudaError_t e = dalloc(c, &c->d_gray[sd], (size_t)c->n_slots_alloc * c->pitch * c->cfg.height);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc gray planes");
+    }
+    return SVO_OK;
+}
+
+PrepareArgs prepare_args(const svo_ctx* c, const uint8_t* srcL, const uint8_t* srcR, size_t stride, size_t image_pitch,
+                         uint8_t* dstL, uint8_t* dstR) {
+    PrepareArgs A;
+    A.srcL = srcL; A.srcR = srcR; A.src_stride = stride; A.src_image_pitch = image_pitch;
+    A.dstL = dstL; A.dstR = dstR; A.dst_image_pitch = (size_t)c->pitch * c->cfg.height;
+    A.W = c->cfg.width; A.H = c->cfg.height; A.pitch_out = c->pitch;
+    for (int sd = 0; sd < 2; ++sd) { A.map_xy[sd] = c->d_map_xy[sd]; A.map_a[sd] = c->d_map_a[sd]; }
+    A.tmpL = c->d_gray[0]; A.tmpR = c->d_gray[1];     // room for max_seqs + 1 images (callers with more pass NULL)
+    return A;
+}
 
 }  // namespace
 
@@ -448,6 +489,88 @@ int svo_get_stage_times(svo_ctx* c, const char** names, float* ms, int32_t cap) 
     return n;
 }
 
+int svo_set_input_format(svo_ctx* c, int32_t channels) {
+    if (!c) return SVO_ERR_ARG;
+    if (channels != 1 && channels != 3) return fail(c, SVO_ERR_ARG, "channels must be 1 (gray) or 3 (BGR)");
+    if (c->pend_count != 0) return fail(c, SVO_ERR_STATE, "batches are in flight");
+    c->in_channels = channels;
+    return SVO_OK;
+}
+
+int svo_set_rectify_maps(svo_ctx* c, const int16_t* map_xy_left, const uint16_t* map_a_left, const int16_t* map_xy_right,
+                         const uint16_t* map_a_right) {
+    if (!c) return SVO_ERR_ARG;
+    if (c->pend_count != 0) return fail(c, SVO_ERR_STATE, "batches are in flight");
+    const int16_t* mxy[2] = {map_xy_left, map_xy_right};
+    const uint16_t* ma[2] = {map_a_left, map_a_right};
+    const int nnull = (!mxy[0]) + (!mxy[1]) + (!ma[0]) + (!ma[1]);
+    if (nnull == 4) { c->rectify = false; return SVO_OK; }          // obs->areImagesRectified()
+    if (nnull != 0) return fail(c, SVO_ERR_ARG, "all four maps or none");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const size_t npx = (size_t)c->cfg.width * c->cfg.height;
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!c->d_map_xy[sd]) {
+            cudaError_t e = dalloc(c, &c->d_map_xy[sd], npx);
+            if (e == cudaSuccess) e = dalloc(c, &c->d_map_a[sd], npx);
+            if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc rectification maps");
+        }
+        CU(c, cudaMemcpyAsync(c->d_map_xy[sd], mxy[sd], npx * sizeof(short2), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_map_a[sd], ma[sd], npx * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->rectify = true;
+    return SVO_OK;
+}
+
+int svo_prepare_rectify_device(svo_ctx* c, int32_t n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
+                               size_t image_pitch, int32_t channels, uint8_t* d_out_left, uint8_t* d_out_right) {
+    if (!c) return SVO_ERR_ARG;
+    if (n <= 0 || !d_left || !d_right || !d_out_left || !d_out_right) return fail(c, SVO_ERR_ARG, "bad argument");
+    if (channels != 1 && channels != 3) return fail(c, SVO_ERR_ARG, "channels must be 1 (gray) or 3 (BGR)");
+    if (stride < (size_t)c->cfg.width * channels) return fail(c, SVO_ERR_ARG, "stride smaller than one image row");
+    CU(c, cudaSetDevice(c->cfg.device));
+    PrepareArgs A = prepare_args(c, d_left, d_right, stride, image_pitch, d_out_left, d_out_right);
+    if (channels == 3 && c->rectify && !c->d_gray[0]) {      // scratch for the two-pass colour path
+        for (int sd = 0; sd < 2; ++sd) {
+            cudaError_t e = dalloc(c, &c->d_gray[sd], (size_t)c->n_slots_alloc * c->pitch * c->cfg.height);
+            if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc gray planes");
+        }
+        A.tmpL = c->d_gray[0]; A.tmpR = c->d_gray[1];
+    }
+    if (n > c->n_slots_alloc) A.tmpL = A.tmpR = nullptr;      // larger than the scratch: fused single pass
+    int L1 = 0;
+    CU(c, launch_prepare(A, n, channels, c->rectify, c->stream, &L1));
+    c->launches += L1;
+    return SVO_OK;
+}
+
+int svo_prepare_rectify(svo_ctx* c, const uint8_t* left, const uint8_t* right, size_t stride, int32_t channels,
+                        uint8_t* out_left, uint8_t* out_right) {
+    if (!c) return SVO_ERR_ARG;
+    if (!left || !right || !out_left || !out_right) return fail(c, SVO_ERR_ARG, "NULL argument");
+    if (channels != 1 && channels != 3) return fail(c, SVO_ERR_ARG, "channels must be 1 (gray) or 3 (BGR)");
+    const int W = c->cfg.width, H = c->cfg.height;
+    if (stride < (size_t)W * channels) return fail(c, SVO_ERR_ARG, "stride smaller than one image row");
+    if (c->pend_count != 0) return fail(c, SVO_ERR_STATE, "batches are in flight");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const int keep = c->in_channels;
+    c->in_channels = std::max(c->in_channels, channels);
+    int rc = ensure_raw_staging(c);
+    c->in_channels = keep;
+    if (rc != SVO_OK) return rc;
+    const size_t rp = c->raw_pitch;
+    CU(c, cudaMemcpy2DAsync(c->d_raw[0][0], rp, left, stride, (size_t)W * channels, H, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpy2DAsync(c->d_raw[0][1], rp, right, stride, (size_t)W * channels, H, cudaMemcpyHostToDevice, c->stream));
+    int L1 = 0;
+    CU(c, launch_prepare(prepare_args(c, c->d_raw[0][0], c->d_raw[0][1], rp, rp * H, c->d_stL[0], c->d_stR[0]), 1, channels,
+                         c->rectify, c->stream, &L1));
+    c->launches += L1;
+    CU(c, cudaMemcpy2DAsync(out_left, W, c->d_stL[0], c->pitch, W, H, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpy2DAsync(out_right, W, c->d_stR[0], c->pitch, W, H, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}
+
 int svo_process_batch_device(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t* d_left, const uint8_t* d_right,
                              size_t stride, size_t image_pitch, const svo_camera* cams, const uint8_t* repeat) {
     if (!c) return SVO_ERR_ARG;
@@ -492,7 +615,6 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
                      const uint8_t* const* right, size_t stride, const svo_camera* cams, const uint8_t* repeat) {
     if (!c) return SVO_ERR_ARG;
     if (!left || !right || !cams) return fail(c, SVO_ERR_ARG, "NULL argument");
-    if (stride < (size_t)c->cfg.width) return fail(c, SVO_ERR_ARG, "stride smaller than the image width");
     if (n <= 0 || n > c->cfg.max_seqs) return fail(c, SVO_ERR_ARG, "batch size out of range");
     if (c->pend_count == 2) return fail(c, SVO_ERR_STATE, "two batches are already in flight: call svo_wait_batch first");
     CU(c, cudaSetDevice(c->cfg.device));
@@ -512,17 +634,29 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
     }
     const int W = c->cfg.width, H = c->cfg.height;
     const size_t plane = (size_t)c->pitch * H;
-    // images: host -> staging buffer b on the copy stream (overlaps the kernels of the previous batch)
+    const bool stage1 = needs_stage1(c);
+    if (stage1) {
+        int rc1 = ensure_raw_staging(c);
+        if (rc1 != SVO_OK) return rc1;
+    }
+    // images: host -> staging buffer b on the copy stream (overlaps the kernels of the previous batch); inputs that
+    // need stage 1 (colour / unrectified) land in the raw staging buffer and are converted on the device
+    uint8_t* upL = stage1 ? c->d_raw[b][0] : c->d_stL[b];
+    uint8_t* upR = stage1 ? c->d_raw[b][1] : c->d_stR[b];
+    const size_t up_pitch = stage1 ? c->raw_pitch : (size_t)c->pitch;
+    const size_t up_plane = up_pitch * H;
+    const size_t row_bytes = (size_t)W * (stage1 ? c->in_channels : 1);
+    if (stride < row_bytes) return fail(c, SVO_ERR_ARG, "stride smaller than one image row");
     bool contig = true;
     for (int i = 1; i < n && contig; ++i)
         contig = left[i] == left[0] + (size_t)i * stride * H && right[i] == right[0] + (size_t)i * stride * H;
-    if (contig && stride == (size_t)c->pitch) {
-        CU(c, cudaMemcpyAsync(c->d_stL[b], left[0], plane * n, cudaMemcpyHostToDevice, c->copy_stream));
-        CU(c, cudaMemcpyAsync(c->d_stR[b], right[0], plane * n, cudaMemcpyHostToDevice, c->copy_stream));
+    if (contig && stride == up_pitch) {
+        CU(c, cudaMemcpyAsync(upL, left[0], up_plane * n, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaMemcpyAsync(upR, right[0], up_plane * n, cudaMemcpyHostToDevice, c->copy_stream));
     } else {
         for (int i = 0; i < n; ++i) {
-            CU(c, cudaMemcpy2DAsync(c->d_stL[b] + i * plane, c->pitch, left[i], stride, W, H, cudaMemcpyHostToDevice, c->copy_stream));
-            CU(c, cudaMemcpy2DAsync(c->d_stR[b] + i * plane, c->pitch, right[i], stride, W, H, cudaMemcpyHostToDevice, c->copy_stream));
+            CU(c, cudaMemcpy2DAsync(upL + i * up_plane, up_pitch, left[i], stride, row_bytes, H, cudaMemcpyHostToDevice, c->copy_stream));
+            CU(c, cudaMemcpy2DAsync(upR + i * up_plane, up_pitch, right[i], stride, row_bytes, H, cudaMemcpyHostToDevice, c->copy_stream));
         }
     }
     CU(c, cudaEventRecord(c->ev_h2d[b], c->copy_stream));
@@ -530,6 +664,12 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
     CU(c, cudaMemcpyAsync(c->P.slots, c->r_slots[b], n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_cams_batch, c->r_cams[b], n * sizeof(Camera), cudaMemcpyHostToDevice, c->stream));
     if (repeat) CU(c, cudaMemcpyAsync(c->d_repeat, c->r_repeat[b], n, cudaMemcpyHostToDevice, c->stream));
+    if (stage1) {   // stage1_prepare_rectify on the device: raw staging -> gray, rectified planes
+        int L1 = 0;
+        CU(c, launch_prepare(prepare_args(c, upL, upR, up_pitch, up_plane, c->d_stL[b], c->d_stR[b]), n, c->in_channels,
+                             c->rectify, c->stream, &L1));
+        c->launches += L1;
+    }
     int rc = run_step(c, n, c->d_stL[b], c->d_stR[b], c->pitch, plane, repeat != nullptr);
     if (rc != SVO_OK) return rc;
     CU(c, cudaMemcpyAsync(c->r_res[b] + lo, c->P.result + lo, (size_t)(hi - lo + 1) * sizeof(Result), cudaMemcpyDeviceToHost, c->stream));

@@ -1,0 +1,20 @@
+// prepare.cuh -- stage 1 (grayscale conversion + stereo rectification), see prepare.cu
+#pragma once
+#include "svo_internal.cuh"
+
+namespace svo {
+
+struct PrepareArgs {
+    const uint8_t* srcL; const uint8_t* srcR;   // source images of the batch, item i at + i * src_image_pitch
+    size_t src_stride, src_image_pitch;         // bytes per source row / per source image
+    uint8_t* dstL; uint8_t* dstR;               // gray (rectified) planes, item i at + i * dst_image_pitch
+    size_t dst_image_pitch;
+    int W, H, pitch_out;                        // pitch_out: row pitch of the output planes (multiple of 16)
+    const short2* map_xy[2];                    // CV_16SC2 map of cv::initUndistortRectifyMap, per side (rectify only)
+    const uint16_t* map_a[2];                   // CV_16UC1 interpolation-table indices, per side
+    uint8_t* tmpL; uint8_t* tmpR;               // optional scratch planes (layout of dst) for colour + rectification
+};
+
+cudaError_t launch_prepare(const PrepareArgs& A, int n, int channels, bool rectify, cudaStream_t st, int* launches);
+
+}  // namespace svo

@@ -16,3 +16,9 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_stage1():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_stage1.npz"), allow_pickle=False)

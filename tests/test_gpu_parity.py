@@ -660,3 +660,83 @@ def test_device_resident_entry_matches_host_entry(ctx_c1):
         b = ctx_c1.fetch_results(1, slots=[1])[0]
         assert key(a) == key(b)
         assert np.array_equal(ctx_c1.tracked_pairs(0), ctx_c1.tracked_pairs(1))
+
+
+# ------------------------------------------------------------------------------------ stage 1 (gray + rectify)
+def test_stage1_gray_and_rectify_bit_exact(golden_stage1):
+    """svo_prepare_rectify against the cv2-generated goldens (cv::cvtColor BGR2GRAY, cv::remap INTER_LINEAR with
+    CV_16SC2 maps, BORDER_CONSTANT) and against the numpy oracle (stage1_rectify.cpp:51-52, :68-74)."""
+    from oracle import pyoracle as po
+    g = golden_stage1
+    H, W = g["gray_L"].shape
+    ctx = capi.Context(width=W, height=H, orb_nfeats=100, max_seqs=1)
+    try:
+        # colour -> gray only (images flagged as rectified)
+        oL, oR = ctx.prepare_rectify(g["bgr_L"], g["bgr_R"])
+        assert np.array_equal(oL, g["gray_L"]) and np.array_equal(oR, g["gray_R"])
+        # gray passes through untouched
+        oL, oR = ctx.prepare_rectify(g["gray_L"], g["gray_R"])
+        assert np.array_equal(oL, g["gray_L"]) and np.array_equal(oR, g["gray_R"])
+        ctx.set_rectify_maps(g["map_xy_L"], g["map_a_L"], g["map_xy_R"], g["map_a_R"])
+        # gray -> rectified, colour -> gray -> rectified
+        for src in ("gray", "bgr"):
+            oL, oR = ctx.prepare_rectify(g[src + "_L"], g[src + "_R"])
+            assert np.array_equal(oL, g["rect_L"]) and np.array_equal(oR, g["rect_R"])
+            assert np.array_equal(oL, po.stage1(g[src + "_L"], g["map_xy_L"], g["map_a_L"]))
+        # maps cleared: back to pass-through
+        ctx.set_rectify_maps()
+        oL, _ = ctx.prepare_rectify(g["gray_L"], g["gray_R"])
+        assert np.array_equal(oL, g["gray_L"])
+    finally:
+        ctx.close()
+
+
+def _mild_maps(W, H, side):
+    """smooth, nearly-identity CV_16SC2 maps built without cv2 (the GPU box test must not depend on it)"""
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+    u = (xs - W / 2) / W
+    v = (ys - H / 2) / W
+    r2 = u * u + v * v
+    k = -0.06 + 0.02 * side
+    fx = (xs + (xs - W / 2) * k * r2 + 0.7 * side) * 32.0
+    fy = (ys + (ys - H / 2) * k * r2 - 0.4 * side) * 32.0
+    ix = np.rint(fx).astype(np.int64)
+    iy = np.rint(fy).astype(np.int64)
+    mxy = np.stack([ix >> 5, iy >> 5], -1).astype(np.int16)
+    ma = ((iy & 31) * 32 + (ix & 31)).astype(np.uint16)
+    return mxy, ma
+
+
+def test_pipeline_with_stage1_on_device_equals_preprocessed_input():
+    """processNewImagePair on colour, unrectified input (stage 1 on the device, then stages 2-5) must give what the
+    pipeline gives on the images the stage-1 oracle prepares (stage1_rectify.cpp:37-93 + process_new_image_pair.cpp)."""
+    from oracle import pyoracle as po
+    frames, cam = synth.make_sequence("c1", seed=5, n_frames=3)
+    H, W = frames[0][0].shape
+    rng = np.random.default_rng(3)
+    maps = [_mild_maps(W, H, 0), _mild_maps(W, H, 1)]
+
+    def colourise(g):      # a BGR image whose channels differ (so that the conversion matters)
+        n = rng.integers(-20, 21, g.shape + (3,))
+        return np.clip(g[..., None].astype(np.int64) + n, 0, 255).astype(np.uint8)
+
+    a = capi.Context(width=W, height=H, orb_nfeats=100, max_seqs=2)
+    b = capi.Context(width=W, height=H, orb_nfeats=100, max_seqs=2)
+    try:
+        a.set_input_format(3)
+        a.set_rectify_maps(maps[0][0], maps[0][1], maps[1][0], maps[1][1])
+        for (L, R) in frames:
+            cL, cR = colourise(L), colourise(R)
+            ra = a.process_batch([cL, cL], [cR, cR], [gcam(cam)] * 2)
+            pL, pR = po.stage1(cL, *maps[0]), po.stage1(cR, *maps[1])
+            rb = b.process_batch([pL, pL], [pR, pR], [gcam(cam)] * 2)
+            for s in range(2):
+                assert np.array_equal(xys(a.keypoints(s, 0, 0)), xys(b.keypoints(s, 0, 0)))
+                assert np.array_equal(a.descriptors(s, 0, 1), b.descriptors(s, 0, 1))
+                assert np.array_equal(mtuple(a.matches(s, 0)), mtuple(b.matches(s, 0)))
+                assert ra[s].error_code == rb[s].error_code and ra[s].valid == rb[s].valid
+                assert np.array_equal(np.array(ra[s].delta_pose[:]), np.array(rb[s].delta_pose[:]))
+        assert ra[0].valid and ra[0].stereo_matches > 20
+    finally:
+        a.close()
+        b.close()

@@ -362,3 +362,37 @@ def test_first_frame_and_bad_tracking_state_machine():
     o = est.process_new_image_pair(*frames[1], camo)
     assert est.prev is first                       # matched against the older frame
     assert o["valid"] and o["error_code"] == orc.VOEC["voecNone"]
+
+
+# ---------------------------------------------------------------- stage 1 (stage1_rectify.cpp:51-52, :68-74)
+@pytest.mark.parametrize("side", ["L", "R"])
+def test_stage1_oracle_matches_cv2_goldens(golden_stage1, side):
+    g = golden_stage1
+    assert np.array_equal(po.gray_bgr(g["bgr_" + side]), g["gray_" + side])
+    assert np.array_equal(po.remap_bilinear(g["gray_" + side], g["map_xy_" + side], g["map_a_" + side]), g["rect_" + side])
+    assert np.array_equal(po.stage1(g["bgr_" + side], g["map_xy_" + side], g["map_a_" + side]), g["rect_" + side])
+    m = g["map_xy_" + side].astype(np.int64)
+    H, W = g["gray_" + side].shape
+    outside = (m[..., 0] < 0) | (m[..., 0] >= W - 1) | (m[..., 1] < 0) | (m[..., 1] >= H - 1)
+    assert outside.sum() > 50                                                     # the border path is exercised
+
+
+@needs_cv2
+def test_stage1_oracle_matches_cv2_live():
+    rng = np.random.default_rng(11)
+    # every (B, G, R) on a coarse lattice + random triples: the fixed-point gray conversion
+    v = np.arange(0, 256, 5, dtype=np.uint8)
+    lattice = np.stack(np.meshgrid(v, v, v, indexing="ij"), -1).reshape(-1, 1, 3)
+    rnd = rng.integers(0, 256, (4096, 64, 3), dtype=np.uint8)
+    for img in (lattice, rnd):
+        assert np.array_equal(po.gray_bgr(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    # remap with strongly distorted maps (large out-of-image regions)
+    H, W = 120, 160
+    src = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    K = np.array([[130.0, 0, 80], [0, 130, 60], [0, 0, 1]])
+    D = np.array([-0.4, 0.15, 0.002, -0.001, 0.0])
+    R = cv2.Rodrigues(np.array([0.03, -0.05, 0.02]))[0]
+    P = np.array([[100.0, 0, 70, 0], [0, 100, 65, 0], [0, 0, 1, 0]])
+    mxy, ma = cv2.initUndistortRectifyMap(K, D, R, P, (W, H), cv2.CV_16SC2)
+    ref = cv2.remap(src, mxy, ma, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    assert np.array_equal(po.remap_bilinear(src, mxy, ma), ref)
