@@ -173,6 +173,12 @@ int svo_get_outliers(svo_ctx* ctx, int32_t slot, int64_t* out, int32_t cap);
 int svo_get_track_candidates(svo_ctx* ctx, int32_t slot, int32_t* out_query, int32_t* out_trainL,
                              int32_t* out_trainR, uint8_t* out_inlL, uint8_t* out_inlR, int32_t cap);
 
+/* ---- match-ID / key-frame control (libstereo-odometry.h:675-726); need vo_use_matches_ids ----- */
+int svo_set_this_frame_as_kf(svo_ctx* ctx, int32_t slot);         /* setThisFrameAsKF(): m_last_kf_max_id = max current ID, H:675-683 */
+int svo_reset_ids(svo_ctx* ctx, int32_t slot);                    /* resetIds(): m_reset, applied at the next step (P:254-267), H:684 */
+int svo_set_ids(svo_ctx* ctx, int32_t slot, const int64_t* ids, int32_t n);   /* setIds(), H:685-694 */
+int svo_set_max_match_id(svo_ctx* ctx, int32_t slot, int64_t id); /* setMaxMatchID(), H:726 */
+
 /* ---- stage 1: stage1_prepare_rectify (stage1_rectify.cpp:37-93), nOctaves = 1 ---------------- */
 /* Input format of svo_process_batch / svo_submit_batch / svo_process_pair: channels = 1 (8-bit gray, the default)
  * or 3 (8-bit BGR, as MRPT / OpenCV hold colour images; row stride in bytes).  Colour input is converted on the

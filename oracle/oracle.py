@@ -338,10 +338,26 @@ class OracleEstimator:
         self.m_last_computed_pose = np.zeros(6)
         self.m_last_match_ID = 0
         self.m_last_kf_max_id = 0
+        self.m_reset = False
         self.m_it_counter = 0
         self.prev = None
         self.cur = None
         self.trace = {}
+
+    # -- match-ID / key-frame control (libstereo-odometry.h:675-726) --------------------------------
+    def set_this_frame_as_kf(self):                  # H:675-683
+        assert self.cur is not None and self.cur.ids is not None and len(self.cur.ids) > 0
+        self.m_last_kf_max_id = int(self.cur.ids.max())
+
+    def reset_ids(self):                             # H:684
+        self.m_reset = True
+
+    def set_ids(self, ids):                          # H:685-694
+        f = self.cur if self.cur is not None else self.prev
+        f.ids = np.array(ids, np.int64)
+
+    def set_max_match_id(self, id_):                 # H:726
+        self.m_last_match_ID = int(id_)
 
     # -- stage 2 (stage2_detect.cpp:385-671, FAST_ORB branch) --------------------------------------
     def detect(self, img):
@@ -439,6 +455,13 @@ class OracleEstimator:
         f.kpsR, f.descR, rawR = self.detect(imgR)   # P:167
         out["detected_feats"] = (len(f.kpsL), len(f.kpsR))
         first = self.prev is None
+        if self.m_reset and self.prev is not None:    # P:254-267 (the reference crashes without a previous frame)
+            n_ids = len(self.prev.ids) if self.prev.ids is not None else 0
+            if n_ids:
+                self.prev.ids = np.arange(n_ids, dtype=np.int64)
+            self.m_last_match_ID = n_ids
+            self.m_last_kf_max_id = self.m_last_match_ID - 1
+            self.m_reset = False
         f.matches, raw_m = self.match_lr(f)           # P:269
         f.ids = None
         if self.p.vo_use_matches_ids and first:       # S3:67,172-173
@@ -464,6 +487,8 @@ class OracleEstimator:
                         self.m_last_match_ID += 1
                 f.ids = ids
             out["tracked_feats_from_last_frame"] = len(tracked)
+            # S4:743-752
+            out["tracked_feats_from_last_KF"] = int((f.ids <= self.m_last_kf_max_id).sum()) if self.p.vo_use_matches_ids else 0
             if len(tracked) < self.p.bad_tracking_th:  # P:326-330
                 self.m_error = out["error_code"] = VOEC["voecBadTracking"]
             if self.m_error != VOEC["voecBadTracking"]:

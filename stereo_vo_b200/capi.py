@@ -33,6 +33,7 @@ EXPORTS = [
     "svo_fundmat_ransac", "svo_abi_version", "svo_kernel_launches", "svo_stream",
     "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks", "svo_set_concurrency",
     "svo_set_input_format", "svo_set_rectify_maps", "svo_prepare_rectify", "svo_prepare_rectify_device",
+    "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
 ]
 
 
@@ -321,6 +322,20 @@ class Context:
 
     def stream(self):
         return lib().svo_stream(self._h)
+
+    # ---- match IDs / key frames (libstereo-odometry.h:675-726) ---------------------------------------------
+    def set_this_frame_as_kf(self, slot=0):
+        self._check(lib().svo_set_this_frame_as_kf(self._h, slot))
+
+    def reset_ids(self, slot=0):
+        self._check(lib().svo_reset_ids(self._h, slot))
+
+    def set_ids(self, ids, slot=0):
+        ids = np.ascontiguousarray(ids, np.int64)
+        self._check(lib().svo_set_ids(self._h, slot, _vp(ids), len(ids)))
+
+    def set_max_match_id(self, id_, slot=0):
+        self._check(lib().svo_set_max_match_id(self._h, slot, C.c_int64(id_)))
 
     # ---- stage 1 ----------------------------------------------------------------------------------------
     def set_input_format(self, channels):

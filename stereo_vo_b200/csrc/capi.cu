@@ -790,6 +790,69 @@ int svo_get_match_ids(svo_ctx* c, int32_t slot, int32_t which, int64_t* out, int
     return n;
 }
 
+// ---- match-ID / key-frame control (libstereo-odometry.h:675-726) ------------------------------------
+static int put_state(svo_ctx* c, int slot, const SlotState& s) {
+    CU(c, cudaMemcpy(c->P.state + slot, &s, sizeof(SlotState), cudaMemcpyHostToDevice));
+    return SVO_OK;
+}
+
+int svo_set_this_frame_as_kf(svo_ctx* c, int32_t slot) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    if (!c->cfg.vo_use_matches_ids) return fail(c, SVO_ERR_STATE, "vo_use_matches_ids is off: there are no match IDs");
+    SlotState s;
+    int rc = get_state(c, slot, &s);
+    if (rc) return rc;
+    if (!s.has_cur) return fail(c, SVO_ERR_STATE, "[VO Error -- setThisFrameAsKF] Current frame does not exist");
+    const size_t pi = pair_idx(slot, s.cur);
+    int n = 0;
+    CU(c, cudaMemcpy(&n, c->P.n_match + pi, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n <= 0) return fail(c, SVO_ERR_STATE, "[VO Error -- setThisFrameAsKF] No existing lr_pairing_data");
+    std::vector<long long> ids(n);
+    CU(c, cudaMemcpy(ids.data(), c->P.match_id + pi * c->P.p.kp_cap, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    long long mx = ids[0];
+    for (long long v : ids) mx = std::max(mx, v);
+    s.last_kf_max_id = mx;                           // *std::max_element(v.begin(), v.end())
+    return put_state(c, slot, s);
+}
+
+int svo_reset_ids(svo_ctx* c, int32_t slot) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    SlotState s;
+    int rc = get_state(c, slot, &s);
+    if (rc) return rc;
+    s.reset_ids = 1;                                 // m_reset = true
+    return put_state(c, slot, s);
+}
+
+int svo_set_ids(svo_ctx* c, int32_t slot, const int64_t* ids, int32_t n) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot) || n < 0 || (n > 0 && !ids)) return fail(c, SVO_ERR_ARG, "bad argument");
+    if (!c->cfg.vo_use_matches_ids) return fail(c, SVO_ERR_STATE, "vo_use_matches_ids is off: there are no match IDs");
+    SlotState s;
+    int rc = get_state(c, slot, &s);
+    if (rc) return rc;
+    if (!s.has_cur && !s.has_prev) return fail(c, SVO_ERR_STATE, "no frame present");
+    // H:685-694: the current frame's IDs if there is one, else the previous frame's
+    const size_t pi = pair_idx(slot, s.has_cur ? s.cur : (s.cur ^ 1));
+    int nm = 0;
+    CU(c, cudaMemcpy(&nm, c->P.n_match + pi, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n != nm) return fail(c, SVO_ERR_ARG, "setIds: one ID per stereo match of the frame is required");
+    if (n) CU(c, cudaMemcpy(c->P.match_id + pi * c->P.p.kp_cap, ids, (size_t)n * 8, cudaMemcpyHostToDevice));
+    return SVO_OK;
+}
+
+int svo_set_max_match_id(svo_ctx* c, int32_t slot, int64_t id) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    SlotState s;
+    int rc = get_state(c, slot, &s);
+    if (rc) return rc;
+    s.last_match_id = id;                            // m_last_match_ID = id
+    return put_state(c, slot, s);
+}
+
 int svo_get_tracked_pairs(svo_ctx* c, int32_t slot, int64_t* out_pairs, int32_t cap) {
     if (!c) return SVO_ERR_ARG;
     if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");

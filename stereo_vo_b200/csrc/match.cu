@@ -186,6 +186,18 @@ lr_filter_kernel(Pools P) {
     const int tid = threadIdx.x;
     const int n_in = (nR > 0) ? nL : 0;   // BFMatcher returns no matches for an empty train set
 
+    // P:254-267 (resetIds()): before stage 3 the previous frame's IDs are renumbered 0..N-1, the ID generator
+    // restarts behind them and the previous frame becomes the key frame.  (The reference dereferences a null
+    // m_prev_imgpair when there is no previous frame; here the flag simply stays pending.)
+    if (st.reset_ids && st.has_prev) {
+        const int Mp = P.p.use_ids ? P.n_match[pair_idx(slot, cur ^ 1)] : 0;   // matches_IDs is empty without ID control
+        long long* idp = P.match_id + pair_idx(slot, cur ^ 1) * cap;
+        for (int m = tid; m < Mp; m += FT) idp[m] = m;
+        __syncthreads();
+        if (tid == 0) { st.last_match_id = Mp; st.last_kf_max_id = (long long)Mp - 1; st.reset_ids = 0; }
+        __syncthreads();
+    }
+
     if (P.p.robust_1to1) {   // S3:124-148: per right keypoint the left one with the smallest distance
         for (int i = tid; i < nR; i += FT) s_rc[i] = 0xFFFFFFFFu;
         __syncthreads();

@@ -24,7 +24,7 @@ struct SlotState {                  // mutable members of the estimator (libster
     int32_t repeat;                 // request_data.repeat of the step being processed
     int32_t status;                 // svo_status of the step (capacity overflow ...)
     uint32_t it_counter;            // m_it_counter
-    int32_t  pad;
+    int32_t  reset_ids;             // m_reset: renumber the previous frame's match IDs at the next step (P:254-267)
     long long last_match_id;        // m_last_match_ID
     long long last_kf_max_id;       // m_last_kf_max_id
     double last_pose[6];            // m_last_computed_pose

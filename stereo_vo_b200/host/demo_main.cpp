@@ -6,9 +6,13 @@
 // Sequence file (written by tests / tools, little endian):
 //   int32 width, height, n_frames; double fx, fy, cx, cy, baseline; then n_frames x (left, right) images.
 //
-// usage: svo_demo <sequence.bin> <camera_pose.txt> [orb_nfeats]
+// usage: svo_demo <sequence.bin> <camera_pose.txt> [orb_nfeats | config.ini]
+//   config.ini: the 7 sections RECTIFY, DETECT, MATCH, IF-MATCH, LEAST_SQUARES, GUI, GENERAL (demo-main.cpp:155-167),
+//   GENERAL/vo_verbosity and GENERAL/camera_pose_on_robot = [x y z yaw pitch roll] in metres / degrees (:168-172, :182)
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <sstream>
 #include <vector>
 
 #include "libstereo_odometry_b200.h"
@@ -24,6 +28,23 @@ static void matmul4(const double* a, const double* b, double* c) {
         }
 }
 
+// mrpt::poses::CPose3D(x, y, z, yaw, pitch, roll): R = Rz(yaw) * Ry(pitch) * Rx(roll)
+static void pose_matrix(const double* v, double* m) {
+    const double cy = std::cos(v[3]), sy = std::sin(v[3]), cp = std::cos(v[4]), sp = std::sin(v[4]), cr = std::cos(v[5]), sr = std::sin(v[5]);
+    const double r[16] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr, v[0],
+                          sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr, v[1],
+                          -sp,     cp * sr,                cp * cr,                v[2],
+                          0, 0, 0, 1};
+    std::memcpy(m, r, sizeof(r));
+}
+static void rigid_inverse(const double* a, double* inv) {
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) inv[4 * i + j] = a[4 * j + i];
+        inv[4 * i + 3] = -(a[i] * a[3] + a[4 + i] * a[7] + a[8 + i] * a[11]);
+    }
+    inv[12] = inv[13] = inv[14] = 0; inv[15] = 1;
+}
+
 int main(int argc, char** argv) {
     if (argc < 3) { std::fprintf(stderr, "usage: %s <sequence.bin> <camera_pose.txt> [orb_nfeats]\n", argv[0]); return 2; }
     FILE* f = std::fopen(argv[1], "rb");
@@ -34,9 +55,26 @@ int main(int argc, char** argv) {
     const int W = hdr[0], H = hdr[1], N = hdr[2];
     try {
         CStereoOdometryEstimator engine;
-        if (argc > 3) engine.params_detect.orb_nfeats = (size_t)std::atoi(argv[3]);
-        engine.applyParams();                     // what loadParamsFromConfigFile ends with (H:661-662)
-        engine.setVerbosityLevel(0);
+        double K[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, Kinv[16];   // camera pose on the robot
+        const bool have_ini = argc > 3 && std::strlen(argv[3]) > 4 && !std::strcmp(argv[3] + std::strlen(argv[3]) - 4, ".ini");
+        if (have_ini) {
+            const std::vector<std::string> sections = {"RECTIFY", "DETECT", "MATCH", "IF-MATCH", "LEAST_SQUARES", "GUI", "GENERAL"};
+            engine.loadParamsFromConfigFileName(argv[3], sections);                     // demo-main.cpp:167
+            CConfigFile ini(argv[3]);
+            engine.setVerbosityLevel(ini.read_int("GENERAL", "vo_verbosity", 0));       // :168
+            std::string vp = ini.read_string("GENERAL", "camera_pose_on_robot", "");    // :171-172, :182
+            for (char& ch : vp) if (ch == '[' || ch == ']' || ch == ',') ch = ' ';
+            std::istringstream is(vp);
+            double v[6] = {0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < 6 && (is >> v[k]); ++k) {}
+            for (int k = 3; k < 6; ++k) v[k] *= M_PI / 180.0;
+            pose_matrix(v, K);
+        } else {
+            if (argc > 3) engine.params_detect.orb_nfeats = (size_t)std::atoi(argv[3]);
+            engine.applyParams();                     // what loadParamsFromConfigFile ends with (H:661-662)
+            engine.setVerbosityLevel(0);
+        }
+        rigid_inverse(K, Kinv);
         CStereoOdometryEstimator::TStereoOdometryRequest req;
         req.stereo_cam.leftCamera.fx_ = req.stereo_cam.rightCamera.fx_ = cam[0];
         req.stereo_cam.leftCamera.fy_ = req.stereo_cam.rightCamera.fy_ = cam[1];
@@ -63,8 +101,10 @@ int main(int argc, char** argv) {
             CStereoOdometryEstimator::TStereoOdometryResult res;
             engine.processNewImagePair(req, res);
             if (res.valid) {
-                double next[16];
-                matmul4(pose, res.outPose.m, next);   // K = identity
+                double kd[16], kdk[16], next[16];     // pose <- pose * (K * delta * K^-1), demo-main.cpp:235-242
+                matmul4(K, res.outPose.m, kd);
+                matmul4(kd, Kinv, kdk);
+                matmul4(pose, kdk, next);
                 for (int k = 0; k < 16; ++k) pose[k] = next[k];
                 ypr[1] = std::atan2(-pose[8], std::hypot(pose[0], pose[4]));
                 ypr[0] = std::atan2(pose[4], pose[0]);

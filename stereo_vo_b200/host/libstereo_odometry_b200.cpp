@@ -3,9 +3,185 @@
 #include "libstereo_odometry_b200.h"
 
 #include <algorithm>
+#include <cctype>
+#include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <sstream>
 
 namespace rso {
+
+// ---- CConfigFile ---------------------------------------------------------------------------------------
+static std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && std::isspace((unsigned char)s[a])) ++a;
+    while (b > a && std::isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+static std::string lower(std::string s) {
+    for (char& c : s) c = (char)std::tolower((unsigned char)c);
+    return s;
+}
+
+void CConfigFile::parse(const std::string& text) {
+    std::istringstream in(text);
+    std::string line, section;
+    while (std::getline(in, line)) {
+        size_t cut = line.size();
+        for (size_t i = 0; i < line.size(); ++i)
+            if (line[i] == ';' || line[i] == '#' || (line[i] == '/' && i + 1 < line.size() && line[i + 1] == '/')) { cut = i; break; }
+        line = trim(line.substr(0, cut));
+        if (line.empty()) continue;
+        if (line.front() == '[' && line.back() == ']') { section = lower(trim(line.substr(1, line.size() - 2))); m_data[section]; continue; }
+        const size_t eq = line.find('=');
+        if (eq == std::string::npos) continue;
+        m_data[section][lower(trim(line.substr(0, eq)))] = trim(line.substr(eq + 1));
+    }
+}
+
+CConfigFile::CConfigFile(const std::string& fileName) {
+    std::ifstream f(fileName.c_str());
+    if (!f) throw std::runtime_error("CConfigFile: cannot open '" + fileName + "'");
+    std::stringstream ss;
+    ss << f.rdbuf();
+    parse(ss.str());
+}
+
+CConfigFile CConfigFile::fromString(const std::string& text) {
+    CConfigFile c;
+    c.parse(text);
+    return c;
+}
+
+bool CConfigFile::sectionExists(const std::string& section) const { return m_data.count(lower(section)) != 0; }
+
+bool CConfigFile::find(const std::string& section, const std::string& name, std::string& out, bool failIfNotFound) const {
+    auto s = m_data.find(lower(section));
+    if (s != m_data.end()) {
+        auto k = s->second.find(lower(name));
+        if (k != s->second.end()) { out = k->second; return true; }
+    }
+    if (failIfNotFound) throw std::runtime_error("Value '" + name + "' not found in section '" + section + "' of the configuration file");
+    return false;
+}
+
+int CConfigFile::read_int(const std::string& section, const std::string& name, int def, bool fail) const {
+    std::string v;
+    return find(section, name, v, fail) ? (int)std::strtol(v.c_str(), nullptr, 0) : def;
+}
+double CConfigFile::read_double(const std::string& section, const std::string& name, double def, bool fail) const {
+    std::string v;
+    return find(section, name, v, fail) ? std::strtod(v.c_str(), nullptr) : def;
+}
+bool CConfigFile::read_bool(const std::string& section, const std::string& name, bool def, bool fail) const {
+    std::string v;
+    if (!find(section, name, v, fail)) return def;
+    v = lower(v);
+    if (v == "true" || v == "yes" || v == "on") return true;
+    if (v == "false" || v == "no" || v == "off") return false;
+    return std::strtol(v.c_str(), nullptr, 0) != 0;
+}
+std::string CConfigFile::read_string(const std::string& section, const std::string& name, const std::string& def, bool fail) const {
+    std::string v;
+    return find(section, name, v, fail) ? v : def;
+}
+
+// ---- loadParamsFromConfigFile (H:554-672) ------------------------------------------------------------------
+void CStereoOdometryEstimator::loadParamsFromConfigFile(const CConfigFile& ini, const std::vector<std::string>& sections) {
+    if (sections.size() != 7) throw std::runtime_error("Assert condition failed: sections.size() == 7");   // ASSERT_, H:556
+    if (!sections[0].empty())   // rectify
+        params_rectify.nOctaves = ini.read_int(sections[0], "nOctaves", params_rectify.nOctaves);
+    if (!sections[1].empty()) { // detection
+        TDetectParams& d = params_detect;
+        d.detect_method = static_cast<TDetectParams::TDMethod>(ini.read_int(sections[1], "detect_method", d.detect_method));
+        d.min_distance = (size_t)ini.read_int(sections[1], "min_distance", (int)d.min_distance);
+        d.initial_FAST_threshold = ini.read_int(sections[1], "initial_FAST_threshold", d.initial_FAST_threshold);
+        d.fast_min_th = ini.read_int(sections[1], "fast_min_th", d.fast_min_th);
+        d.fast_max_th = ini.read_int(sections[1], "fast_max_th", d.fast_max_th);
+        d.orb_nfeats = (size_t)ini.read_int(sections[1], "orb_nfeats", (int)d.orb_nfeats);
+        d.orb_nlevels = (size_t)ini.read_int(sections[1], "orb_nlevels", (int)d.orb_nlevels);
+        d.non_maximal_suppression = ini.read_bool(sections[1], "non_maximal_suppression", d.non_maximal_suppression);
+        d.nmsMethod = static_cast<TDetectParams::NMSMethod>(ini.read_int(sections[1], "non_max_supp_method", d.nmsMethod));
+    }
+    if (!sections[2].empty()) { // left right matching
+        TLeftRightMatchParams& m = params_lr_match;
+        m.match_method = static_cast<TLeftRightMatchParams::TSMMethod>(ini.read_int(sections[2], "match_method", m.match_method));
+        m.max_y_diff = ini.read_double(sections[2], "max_y_diff", m.max_y_diff);
+        m.enable_robust_1to1_match = ini.read_bool(sections[2], "enable_robust_1to1_match", m.enable_robust_1to1_match);
+        m.rectified_images = ini.read_bool(sections[2], "rectified_images", m.rectified_images);
+        m.orb_min_th = ini.read_int(sections[2], "orb_min_th", m.orb_min_th);
+        m.orb_max_th = ini.read_int(sections[2], "orb_max_th", m.orb_max_th);
+        m.orb_max_distance = ini.read_double(sections[2], "orb_max_distance", m.orb_max_distance);
+    }
+    if (!sections[3].empty()) { // inter-frame matching (default 0 when the key is missing, H:610)
+        params_if_match.ifm_method = static_cast<TInterFrameMatchingParams::TIFMMethod>(ini.read_int(sections[3], "if_match_method", 0));
+        params_if_match.filter_fund_matrix = ini.read_bool(sections[3], "filter_fund_matrix", params_if_match.filter_fund_matrix);
+    }
+    if (!sections[4].empty()) { // least squares
+        TLeastSquaresParams& l = params_least_squares;
+        l.std_noise_pixels = ini.read_double(sections[4], "std_noise_pixels", l.std_noise_pixels);
+        l.use_previous_pose_as_initial = ini.read_bool(sections[4], "use_previous_pose_as_initial", l.use_previous_pose_as_initial);
+        l.initial_max_iters = (size_t)ini.read_int(sections[4], "initial_max_iters", (int)l.initial_max_iters);
+        l.max_iters = (size_t)ini.read_int(sections[4], "max_iters", (int)l.max_iters);
+        l.min_mod_out_vector = ini.read_double(sections[4], "min_mod_out_vector", l.min_mod_out_vector);
+        l.max_incr_cost = (size_t)ini.read_int(sections[4], "max_incr_cost", (int)l.max_incr_cost);
+        l.residual_threshold = ini.read_double(sections[4], "residual_threshold", l.residual_threshold);
+        l.bad_tracking_th = (size_t)ini.read_int(sections[4], "bad_tracking_th", (int)l.bad_tracking_th);
+        l.use_robust_kernel = ini.read_bool(sections[4], "use_robust_kernel", l.use_robust_kernel);
+        l.kernel_param = ini.read_double(sections[4], "kernel_param", l.kernel_param);
+    }
+    // sections[5] (GUI): there is no GUI in this build, its keys are ignored
+    if (!sections[6].empty()) { // GENERAL
+        TGeneralParams& g = params_general;
+        g.vo_use_matches_ids = ini.read_bool(sections[6], "vo_use_matches_ids", g.vo_use_matches_ids);
+        g.vo_save_files = ini.read_bool(sections[6], "vo_save_files", g.vo_save_files);
+        g.vo_debug = ini.read_bool(sections[6], "vo_debug", g.vo_debug);
+        g.vo_pause_it = ini.read_bool(sections[6], "vo_pause_it", g.vo_pause_it);
+        g.vo_out_dir = ini.read_string(sections[6], "vo_out_dir", g.vo_out_dir);
+    }
+    resetFASTThreshold();       // H:661-662
+    resetORBThreshold();
+}
+
+void CStereoOdometryEstimator::loadParamsFromConfigFileName(const std::string& fileName, const std::vector<std::string>& sections) {
+    CConfigFile ini(fileName);  // ASSERT_(fileExists(fileName)), H:669
+    loadParamsFromConfigFile(ini, sections);
+}
+
+// ---- match IDs / key frames (H:675-726) ---------------------------------------------------------------------
+void CStereoOdometryEstimator::setThisFrameAsKF() {
+    if (!m_ctx) throw std::runtime_error("[VO Error -- setThisFrameAsKF] Current frame does not exist");
+    if (svo_set_this_frame_as_kf(m_ctx, 0) != SVO_OK) throw_last(m_ctx, "setThisFrameAsKF");
+}
+void CStereoOdometryEstimator::resetIds() {
+    if (!m_ctx) throw std::runtime_error("[Visual Odometry Error] no frame has been processed yet.");
+    if (svo_reset_ids(m_ctx, 0) != SVO_OK) throw_last(m_ctx, "resetIds");
+}
+void CStereoOdometryEstimator::setIds(const std::vector<size_t>& ids) {
+    if (!m_ctx) throw std::runtime_error("[Visual Odometry Error] no frame has been processed yet.");
+    std::vector<int64_t> v(ids.begin(), ids.end());
+    if (svo_set_ids(m_ctx, 0, v.data(), (int32_t)v.size()) != SVO_OK) throw_last(m_ctx, "setIds");
+}
+void CStereoOdometryEstimator::setMaxMatchID(size_t id) {
+    if (!m_ctx) throw std::runtime_error("[Visual Odometry Error] no frame has been processed yet.");
+    if (svo_set_max_match_id(m_ctx, 0, (int64_t)id) != SVO_OK) throw_last(m_ctx, "setMaxMatchID");
+}
+std::vector<size_t> CStereoOdometryEstimator::getCopyCurrentIDs(size_t octave) {
+    if (octave != 0 || !m_ctx) return std::vector<size_t>();
+    const int cap = 2 * (int)params_detect.orb_nfeats + 16;
+    std::vector<int64_t> ids(cap);
+    const int n = svo_get_match_ids(m_ctx, 0, 0, ids.data(), cap);
+    if (n < 0) throw_last(m_ctx, "svo_get_match_ids");
+    return std::vector<size_t>(ids.begin(), ids.begin() + n);
+}
+
+void CStereoOdometryEstimator::setRectifyMaps(const std::vector<int16_t>& xyL, const std::vector<uint16_t>& aL,
+                                              const std::vector<int16_t>& xyR, const std::vector<uint16_t>& aR) {
+    if (xyL.size() != 2 * aL.size() || xyR.size() != 2 * aR.size() || aL.size() != aR.size() || aL.empty())
+        throw std::runtime_error("[Visual Odometry Error] setRectifyMaps: map_xy needs 2 and map_a 1 entry per pixel, both sides.");
+    m_map_xy[0] = xyL; m_map_a[0] = aL; m_map_xy[1] = xyR; m_map_a[1] = aR;
+    m_maps_on_device = false;
+}
 
 CStereoOdometryEstimator::CStereoOdometryEstimator() {}
 
@@ -62,6 +238,9 @@ void CStereoOdometryEstimator::ensure_context(int width, int height) {
     m_w = width;
     m_h = height;
     m_dirty = false;
+    m_in_channels = 1;          // a fresh context takes gray, rectified images
+    m_maps_on_device = false;
+    m_rectify_active = false;
 }
 
 static svo_camera to_cam(const TStereoCamera& s) {
@@ -97,9 +276,25 @@ void CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& reque
         throw std::runtime_error("[Visual Odometry Error] use_precomputed_data is not supported (unusable in the reference too).");
     const CImage& L = request_data.stereo_imgs->imageLeft;
     const CImage& R = request_data.stereo_imgs->imageRight;
-    if (!L.data || !R.data || L.width != R.width || L.height != R.height || L.stride != R.stride)
-        throw std::runtime_error("[Visual Odometry Error] left/right images must be 8-bit gray with equal geometry.");
+    if (!L.data || !R.data || L.width != R.width || L.height != R.height || L.stride != R.stride || L.channels != R.channels ||
+        (L.channels != 1 && L.channels != 3))
+        throw std::runtime_error("[Visual Odometry Error] left/right images must be 8-bit gray or BGR with equal geometry.");
     ensure_context(L.width, L.height);
+    // stage 1 (stage1_rectify.cpp:37-93) runs on the device: tell the context what the images are
+    if (L.channels != m_in_channels) {
+        if (svo_set_input_format(m_ctx, L.channels) != SVO_OK) throw_last(m_ctx, "svo_set_input_format");
+        m_in_channels = L.channels;
+    }
+    const bool rectify = !request_data.stereo_imgs->areImagesRectified();
+    if (rectify && m_map_a[0].size() != (size_t)L.width * L.height)
+        throw std::runtime_error("[Visual Odometry Error] unrectified images need setRectifyMaps() with maps of the image size.");
+    if (rectify != m_rectify_active || (rectify && !m_maps_on_device)) {
+        const int rc1 = rectify ? svo_set_rectify_maps(m_ctx, m_map_xy[0].data(), m_map_a[0].data(), m_map_xy[1].data(), m_map_a[1].data())
+                                : svo_set_rectify_maps(m_ctx, nullptr, nullptr, nullptr, nullptr);
+        if (rc1 != SVO_OK) throw_last(m_ctx, "svo_set_rectify_maps");
+        m_rectify_active = rectify;
+        m_maps_on_device = rectify;
+    }
     result.error_code = voecNone;                         // P:50
     const svo_camera cam = to_cam(request_data.stereo_cam);
     svo_result r;

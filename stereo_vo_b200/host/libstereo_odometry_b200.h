@@ -16,6 +16,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -65,15 +66,41 @@ struct CPose3D {                  // mrpt::poses::CPose3D: what the demo reads (
     double roll() const { return ypr[2]; }
 };
 
-struct CImage {                   // 8-bit gray view; the shim never owns or frees pixels
+struct CImage {                   // 8-bit view (gray or BGR); the shim never owns or frees pixels
     const uint8_t* data = nullptr;
     int width = 0, height = 0;
     size_t stride = 0;
+    int channels = 1;             // 1 = gray, 3 = BGR (converted on the device like FAST_REF_OR_CONVERT_TO_GRAY, S1:51-52)
     size_t getRowStride() const { return stride; }
     int getWidth() const { return width; }
     int getHeight() const { return height; }
+    bool isColor() const { return channels == 3; }
 };
-struct CObservationStereoImages { CImage imageLeft, imageRight; double timestamp = 0; };
+struct CObservationStereoImages {
+    CImage imageLeft, imageRight;
+    double timestamp = 0;
+    bool rectified = true;        // areImagesRectified() (S1:61): false = rectify with the maps given to setRectifyMaps()
+    bool areImagesRectified() const { return rectified; }
+};
+
+/** Minimal stand-in for mrpt::utils::CConfigFile: "[SECTION]" headers, "key = value" lines, comments starting with
+  * ';', '#' or "//" (anywhere on the line), case-insensitive section and key names, values trimmed. */
+class CConfigFile {
+public:
+    CConfigFile() {}
+    explicit CConfigFile(const std::string& fileName);      // throws std::runtime_error when the file cannot be read
+    static CConfigFile fromString(const std::string& text);
+    bool sectionExists(const std::string& section) const;
+    int read_int(const std::string& section, const std::string& name, int defaultValue, bool failIfNotFound = false) const;
+    double read_double(const std::string& section, const std::string& name, double defaultValue, bool failIfNotFound = false) const;
+    bool read_bool(const std::string& section, const std::string& name, bool defaultValue, bool failIfNotFound = false) const;
+    std::string read_string(const std::string& section, const std::string& name, const std::string& defaultValue,
+                            bool failIfNotFound = false) const;
+private:
+    void parse(const std::string& text);
+    bool find(const std::string& section, const std::string& name, std::string& out, bool failIfNotFound) const;
+    std::map<std::string, std::map<std::string, std::string> > m_data;
+};
 
 typedef std::vector<KeyPoint> TKeyPointList;
 typedef std::vector<DMatch> TDMatchList;
@@ -175,6 +202,27 @@ public:
     void resetORBThreshold() { m_current_orb_th = (int)params_lr_match.orb_max_distance; m_dirty = true; }
     void setVerbosityLevel(int level) { m_verbose_level = level; }
 
+    /** Loads configuration from an INI file (H:554-663).  Sections must be (in this order) related to:
+      * RECTIFY, DETECT, MATCH, IF-MATCH, LEAST_SQUARES, GUI, GENERAL; empty names are skipped.  Keys of methods this
+      * build does not have (KLT, SAD, window trackers, GUI) are accepted and ignored.  Ends with
+      * resetFASTThreshold() + resetORBThreshold() like the reference (H:661-662). */
+    void loadParamsFromConfigFile(const CConfigFile& iniFile, const std::vector<std::string>& sections);
+    /** Loads configuration from an INI file from its name (H:666-672). */
+    void loadParamsFromConfigFileName(const std::string& fileName, const std::vector<std::string>& sections);
+
+    // Match-ID / key-frame control (H:675-726); IDs exist only with params_general.vo_use_matches_ids
+    void setThisFrameAsKF();
+    void resetIds();
+    void setIds(const std::vector<size_t>& ids);
+    void setMaxMatchID(size_t id);
+    std::vector<size_t> getCopyCurrentIDs(size_t octave = 0);   // getRefCurrentIDs(octave) by value (state lives on the device)
+
+    /** Rectification maps for observations with rectified == false: what CStereoRectifyMap::setFromCamParams computes
+      * on first use (S1:69-70) with cv::initUndistortRectifyMap(..., CV_16SC2): per side H*W (x, y) int16 pairs and
+      * H*W uint16 interpolation indices.  The rectification itself (cv::remap) runs on the device. */
+    void setRectifyMaps(const std::vector<int16_t>& map_xy_left, const std::vector<uint16_t>& map_a_left,
+                        const std::vector<int16_t>& map_xy_right, const std::vector<uint16_t>& map_a_right);
+
     /** Apply the param structs (what loadParamsFromConfigFile does at H:554-663, minus the INI parsing):
       * re-reads every params_* member and resets both thresholds (H:661-662). */
     void applyParams() { resetFASTThreshold(); resetORBThreshold(); m_dirty = true; }
@@ -191,6 +239,10 @@ private:
     int m_current_fast_th = 20, m_current_orb_th = 60;   // ctor values, common.cpp:35-36
     int m_verbose_level = 1;
     unsigned int m_it_counter = 0;
+    int m_in_channels = 1;
+    bool m_maps_on_device = false, m_rectify_active = false;
+    std::vector<int16_t> m_map_xy[2];
+    std::vector<uint16_t> m_map_a[2];
 };
 
 }  // namespace rso

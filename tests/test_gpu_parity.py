@@ -531,6 +531,50 @@ def test_host_shim_demo_loop_matches_oracle(tmp_path):
     assert abs(got[-1, 0] - 0.15) < 0.02                            # 3 steps of 0.05 m
 
 
+def test_host_shim_demo_with_ini_and_camera_pose_on_robot(tmp_path):
+    """demo loop configured through an INI file (demo-main.cpp:155-172): parameters from the 7 sections and the
+    composition pose <- pose * K * delta * K^-1 with K = camera pose on the robot (demo-main.cpp:235-242)."""
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    demo = os.path.join(root, "stereo_vo_b200", "host", "svo_demo")
+    frames, cam = synth.make_sequence("c1", seed=4, n_frames=4)
+    seq = tmp_path / "seq.bin"
+    with open(seq, "wb") as f:
+        f.write(struct.pack("<3i5d", 320, 240, len(frames), cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"]))
+        for (L, R) in frames:
+            f.write(L.tobytes())
+            f.write(R.tobytes())
+    ini = tmp_path / "cfg.ini"
+    text = open(os.path.join(root, "stereo_vo_b200", "host", "hot_path.ini")).read()
+    text = text.replace("orb_nfeats = 500", "orb_nfeats = 100").replace("max_y_diff = 1", "max_y_diff = 2")
+    text = text.replace("camera_pose_on_robot = [0 0 0 0 0 0]", "camera_pose_on_robot = [0.1 -0.2 0.3 -90 0 -100]")
+    ini.write_text(text)
+    out = tmp_path / "camera_pose.txt"
+    p = subprocess.run([demo, str(seq), str(out), str(ini)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    got = np.loadtxt(out).reshape(-1, 6)
+    pytest.importorskip("cv2")
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100, max_y_diff=2.0), backend="port", ransac="cv2")
+    yaw, pitch, roll = np.deg2rad([-90.0, 0.0, -100.0])
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    K = np.eye(4)
+    K[:3, :3] = [[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                 [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr], [-sp, cp * sr, cp * cr]]
+    K[:3, 3] = [0.1, -0.2, 0.3]
+    pose = np.eye(4)
+    exp = []
+    for (L, R) in frames:
+        o = est.process_new_image_pair(L, R, ocam(cam))
+        if o["valid"]:
+            pose = pose @ (K @ o["pose"]["mat"] @ np.linalg.inv(K))
+        ypr = [np.arctan2(pose[1, 0], pose[0, 0]), np.arctan2(-pose[2, 0], np.hypot(pose[0, 0], pose[1, 0])), np.arctan2(pose[2, 1], pose[2, 2])]
+        exp.append([pose[0, 3], pose[1, 3], pose[2, 3]] + ypr)
+    np.testing.assert_allclose(got, np.array(exp), atol=1.5e-3)
+    assert np.abs(got[-1, :3]).max() > 0.05
+
+
 # ------------------------------------------------------------------------------------ edge cases
 def _oracle_frame(est_params, img_pairs, cam, **kw):
     est = orc.OracleEstimator(orc.Params(**est_params), backend="port", ransac=kw.get("ransac", "off"))
@@ -740,3 +784,40 @@ def test_pipeline_with_stage1_on_device_equals_preprocessed_input():
     finally:
         a.close()
         b.close()
+
+
+def test_match_id_and_keyframe_control():
+    """setThisFrameAsKF / resetIds / setIds / setMaxMatchID (libstereo-odometry.h:675-726, process_new_image_pair.cpp:
+    254-267, stage4_match_consecutive.cpp:743-752) against the oracle's restatement."""
+    frames, cam = synth.make_sequence("c1", seed=9, n_frames=6)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, vo_use_matches_ids=1, fundmat_filter=0)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100, vo_use_matches_ids=True), backend="port", ransac="off")
+    kf_counts = []
+    try:
+        for i, (L, R) in enumerate(frames):
+            o = est.process_new_image_pair(L, R, ocam(cam))
+            r = ctx.process_pair(L, R, gcam(cam))
+            assert np.array_equal(ctx.match_ids(0, 0), o["frame"].ids), i
+            if i > 0:
+                kf_counts.append(o["tracked_feats_from_last_KF"])
+                assert r.tracked_feats_from_last_KF == o["tracked_feats_from_last_KF"], i
+                assert r.tracked_feats_from_last_frame == o["tracked_feats_from_last_frame"], i
+            if i == 1:                                  # key frame: later frames count the IDs that existed here
+                est.set_this_frame_as_kf()
+                ctx.set_this_frame_as_kf()
+            if i == 2:                                  # renumber at the next step, previous frame becomes the key frame
+                est.reset_ids()
+                ctx.reset_ids()
+            if i == 3:                                  # caller-assigned IDs + generator restart
+                ids = np.arange(len(o["frame"].ids), dtype=np.int64) * 3 + 1000
+                est.set_ids(ids)
+                ctx.set_ids(ids)
+                est.set_max_match_id(5000)
+                ctx.set_max_match_id(5000)
+                assert np.array_equal(ctx.match_ids(0, 0), ids)
+        # frame 2 counts against the key frame set at frame 1, frame 3 against the renumbered frame 2
+        assert kf_counts[1] > 0 and kf_counts[2] > 0 and ctx.match_ids(0, 0).max() >= 5000
+        with pytest.raises(capi.SvoError):
+            ctx.set_ids(np.arange(3))                   # wrong length
+    finally:
+        ctx.close()

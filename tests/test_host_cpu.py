@@ -153,3 +153,14 @@ def test_host_shim_builds_and_fails_loudly_without_gpu(built_lib, tmp_path):
         f.write(bytes(320 * 240 * 2))
     p = subprocess.run([demo, str(seq), str(tmp_path / "pose.txt"), "100"], capture_output=True, text=True)
     assert p.returncode == 1 and "no CUDA device" in p.stderr
+
+
+def test_host_shim_ini_loader(built_lib, tmp_path):
+    """loadParamsFromConfigFile / loadParamsFromConfigFileName of the host shim (libstereo-odometry.h:554-672)."""
+    exe = tmp_path / "test_config"
+    host = os.path.join(ROOT, "stereo_vo_b200", "host")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "cpp", "test_config.cpp"),
+                           "-L" + host, "-lstereo_odometry_b200", "-L" + os.path.join(ROOT, "stereo_vo_b200"), "-lsvo_b200",
+                           "-Wl,-rpath," + host, "-Wl,-rpath," + os.path.join(ROOT, "stereo_vo_b200")])
+    p = subprocess.run([str(exe), os.path.join(host, "hot_path.ini")], capture_output=True, text=True)
+    assert p.returncode == 0 and "failures=0" in p.stdout, p.stdout + p.stderr
