@@ -517,6 +517,19 @@ def run_gpu(args):
     barrier()
     out = outs[(args.steps - 1) & 1]
     e2e_valid = sum(int(r.valid) for r in out)
+    # the host->device link alone: the same pinned image batches copied with nothing else running.  e2e cannot be
+    # faster than this copy (it moves h2d_bytes_per_step every step)
+    h2d_ms = []
+    for t in range(4):
+        c0 = torch.cuda.Event(enable_timing=True)
+        c1 = torch.cuda.Event(enable_timing=True)
+        c0.record()
+        dev[t % period][0].copy_(host[t % period][0], non_blocking=True)
+        dev[t % period][1].copy_(host[t % period][1], non_blocking=True)
+        c1.record()
+        c1.synchronize()
+        h2d_ms.append(c0.elapsed_time(c1))
+    h2d_ms = float(np.median(h2d_ms[1:]))
 
     # ---- max over ranks + the end-of-batch gather (the only collective on this path) ------------------------
     pairs = B * args.steps
@@ -567,7 +580,10 @@ def run_gpu(args):
                        "valid_results": f"{n_valid_all}/{B * world}"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * W * H,
                     "d2h_bytes_per_step": B * C.sizeof(capi.Result), "ms_per_step": e2e_ms / args.steps,
-                    "valid_results": f"{e2e_valid}/{B}"},
+                    "valid_results": f"{e2e_valid}/{B}",
+                    "h2d_link": {"ms_per_step_copy_only": round(h2d_ms, 3), "gbs": round(2 * B * W * H / (h2d_ms * 1e-3) / 1e9, 1),
+                                 "pairs_per_s_ceiling": round(B / (h2d_ms * 1e-3)),
+                                 "note": "pinned host -> device copy of one step's images, measured alone on this rank"}},
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                          "frac": dom_gbs / peak, "traffic": traffic, "peak_source": peak_src,
