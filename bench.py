@@ -423,7 +423,8 @@ def run_gpu(args):
     dev = [[h.cuda(non_blocking=True) for h in pair] for pair in host]
     torch.cuda.synchronize()
 
-    ctx = capi.Context(width=W, height=H, orb_nfeats=nfeats, max_seqs=B, device=local)
+    ctx = capi.Context(width=W, height=H, orb_nfeats=nfeats, max_seqs=B, device=local, match_method=args.match_method,
+                       if_match_method=args.if_match_method)
     cams = [gc] * B
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
 
@@ -571,6 +572,8 @@ def run_gpu(args):
             "config": {"workload": "c2: 640x480 synthetic stereo sequences, 1000 ORB kp, full FAST+ORB detect / L-R match / "
                                    "tracking + F-matrix RANSAC / Gauss-Newton path",
                        "pairs_per_step_per_gpu": B, "distinct_sequences": N_SEQ,
+                       "matchers": {"match_method": ["smDescBF", "smDescRbR"][args.match_method],
+                                    "if_match_method": ["ifmDescBF", "ifmDescWin"][args.if_match_method]},
                        "streams": "slots of a step run in %s groups on concurrent streams (value, e2e); the per-kernel times "
                                   "and the roofline come from a serialised pass of the same steps (%.3f ms per step)"
                                   % (args.chunks or "the library's default (4)", serial_ms),
@@ -639,6 +642,8 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=300, help="cpu_baseline: pairs per process")
     ap.add_argument("--ref-pairs", type=int, default=100, help="--impl reference: pairs per process per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--match-method", type=int, default=0, help="0 = smDescBF (headline), 1 = smDescRbR (row-by-row band matcher)")
+    ap.add_argument("--if-match-method", type=int, default=0, help="0 = ifmDescBF (headline), 1 = ifmDescWin (windowed tracker)")
     ap.add_argument("--chunks", type=int, default=0, help="groups of slots on concurrent streams (0 = library default)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = the headline pipeline; c5 = Hamming microbench")
     ap.add_argument("--c5-reps", type=int, default=64, help="c5: independent 4096x4096 problems per GPU per step")

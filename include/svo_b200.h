@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SVO_B200_ABI_VERSION 1
+#define SVO_B200_ABI_VERSION 2
 
 typedef enum svo_status {
     SVO_OK = 0,
@@ -95,6 +95,14 @@ typedef struct svo_config {
     /* 0 = reproduce libstdc++ std::sort's permutation (stage2_detect.cpp:89,242,324) exactly;
      * 1 = stable order (diagnostic; compare with the oracle's sort_mode=1) */
     int32_t sort_mode;
+    /* alternative matchers (ABI version 2) */
+    int32_t match_method;         /* TLeftRightMatchParams::TSMMethod: 0 = smDescBF (stage3_match_left_right.cpp:83-178),
+                                     1 = smDescRbR, the row-by-row / epipolar-band matcher (:185-419) */
+    int32_t if_match_method;      /* TInterFrameMatchingParams::TIFMMethod: 0 = ifmDescBF (stage4_match_consecutive.cpp:88-329),
+                                     1 = ifmDescWin, the windowed descriptor tracker (:435-738) */
+    int32_t ifm_win_w, ifm_win_h; /* window of ifmDescWin (INI keys window_width / window_height; no default in the
+                                     reference, 20 / 20 here) */
+    double  orb_max_distance;     /* params_lr_match.orb_max_distance, the threshold smDescRbR reads (:206); 40 */
 } svo_config;
 
 /* POD mirror of TStereoOdometryResult (libstereo-odometry.h:235-264) for nOctaves == 1.

@@ -79,6 +79,8 @@ def lib():
         _lib.orc_bf_match.restype = C.c_int
         _lib.orc_lr_filter.restype = C.c_int
         _lib.orc_track_filter.restype = C.c_int
+        _lib.orc_match_rbr.restype = C.c_int
+        _lib.orc_track_win.restype = C.c_int
         _lib.orc_track_consistency.restype = C.c_int
         _lib.orc_eval_rgn.restype = C.c_int
         assert _lib.orc_sizeof_keypoint() == KEYPOINT.itemsize
@@ -177,6 +179,38 @@ def track_filter(matL, matR, cur_n, orb_th):
     assert len(l) == len(r)
     n = lib().orc_track_filter(_p(l), _p(r), len(l), int(cur_n), int(orb_th))
     return l[:n].copy(), r[:n].copy()
+
+
+def match_rbr(kpsL, descL, idxL, kpsR, descR, idxR, H, W, max_y_diff, orb_max_distance, robust_1to1):
+    """stage 3, smDescRbR branch (stage3_match_left_right.cpp:185-419)."""
+    kl = np.ascontiguousarray(kpsL, KEYPOINT)
+    kr = np.ascontiguousarray(kpsR, KEYPOINT)
+    dl = np.ascontiguousarray(descL, np.uint8).reshape(-1, 32)
+    dr = np.ascontiguousarray(descR, np.uint8).reshape(-1, 32)
+    il = np.ascontiguousarray(idxL, np.int64)
+    ir = np.ascontiguousarray(idxR, np.int64)
+    assert len(il) == H and len(ir) == H
+    out = np.zeros(max(len(kl), 1), DMATCH)
+    n = lib().orc_match_rbr(_p(kl), _p(dl), len(kl), _p(il), _p(kr), _p(dr), len(kr), _p(ir), int(H), int(W),
+                            C.c_double(max_y_diff), C.c_double(orb_max_distance), int(bool(robust_1to1)), _p(out))
+    return out[:n].copy()
+
+
+def track_win(prev, cur, win_w, win_h):
+    """stage 4, ifmDescWin branch (stage4_match_consecutive.cpp:435-640) up to the candidate list: (n, 2) array of
+    (previous match index, current match index) in current-match order."""
+    pm = np.ascontiguousarray(prev.matches, DMATCH)
+    cm = np.ascontiguousarray(cur.matches, DMATCH)
+    pri = lr_row_index(pm, prev.kpsL, prev.H)
+    cri = lr_row_index(cm, cur.kpsL, cur.H)
+    op = np.zeros(max(len(cm), 1), np.int32)
+    oc = np.zeros(max(len(cm), 1), np.int32)
+    a = [np.ascontiguousarray(x, KEYPOINT) for x in (prev.kpsL, prev.kpsR, cur.kpsL, cur.kpsR)]
+    pd = np.ascontiguousarray(prev.descL, np.uint8).reshape(-1, 32)
+    cd = np.ascontiguousarray(cur.descL, np.uint8).reshape(-1, 32)
+    n = lib().orc_track_win(_p(pm), len(pm), _p(a[0]), _p(a[1]), _p(pd), _p(pri), _p(cm), len(cm), _p(a[2]), _p(a[3]),
+                            _p(cd), _p(cri), int(cur.H), int(cur.W), int(win_w), int(win_h), _p(op), _p(oc))
+    return np.stack([op[:n], oc[:n]], 1).astype(np.int64)
 
 
 def track_consistency(matL, matR, inlL, inlR):
@@ -290,6 +324,11 @@ class Params:
         self.max_y_diff = 1.0
         self.orb_max_distance = 40.0
         self.enable_robust_1to1_match = False
+        self.match_method = 0                 # TSMMethod: 0 = smDescBF, 1 = smDescRbR (H:454)
+        # TInterFrameMatchingParams (H:285-310); the window sizes have no default in the reference (empty ctor, C:84)
+        self.ifm_method = 0                   # TIFMMethod: 0 = ifmDescBF, 1 = ifmDescWin (H:291)
+        self.ifm_win_w = 20
+        self.ifm_win_h = 20
         # TLeastSquaresParams (H:313-350)
         self.use_robust_kernel = True
         self.kernel_param = 3.0
@@ -320,7 +359,7 @@ def make_camera(fx, fy, cx, cy, baseline):
 
 class FrameData:
     """TImagePairData (libstereo-odometry.h:756-811) for nOctaves == 1."""
-    __slots__ = ("kpsL", "descL", "kpsR", "descR", "matches", "ids", "H", "W")
+    __slots__ = ("kpsL", "descL", "kpsR", "descR", "matches", "ids", "H", "W", "idxL", "idxR")
 
 
 class OracleEstimator:
@@ -374,10 +413,15 @@ class OracleEstimator:
         if self.p.non_maximal_suppression:
             kps, desc, sel = non_max_sup(quota, kps, desc, self.p.min_distance, H, W, self.sort_mode)
         kps, desc, perm, row_index = update_indexes(kps, desc, H, self.sort_mode)
+        self._last_row_index = row_index           # pyr_feats_index (only the row-by-row matcher reads it)
         return kps, desc, raw
 
     # -- stage 3 (stage3_match_left_right.cpp:83-178) ------------------------------------------------
     def match_lr(self, f):
+        if self.p.match_method == 1:               # smDescRbR, S3:185-419 (no BF post-filter on this branch)
+            m = match_rbr(f.kpsL, f.descL, f.idxL, f.kpsR, f.descR, f.idxR, f.H, f.W, self.p.max_y_diff,
+                          self.p.orb_max_distance, self.p.enable_robust_1to1_match)
+            return m, m.copy()
         m = (cv2_bf_match if self.backend == "cv2" else bf_match)(f.descL, f.descR)
         raw = m.copy()
         m = lr_filter(m, f.kpsL, f.kpsR, self.p.enable_robust_1to1_match, self.p.max_y_diff,
@@ -386,6 +430,8 @@ class OracleEstimator:
 
     # -- stage 4 (stage4_match_consecutive.cpp:88-329) -----------------------------------------------
     def track(self, prev, cur):
+        if self.p.ifm_method == 1:                 # ifmDescWin, S4:435-738
+            return self.track_window(prev, cur)
         bf = cv2_bf_match if self.backend == "cv2" else bf_match
         preL = prev.descL[prev.matches["queryIdx"]]
         preR = prev.descR[prev.matches["trainIdx"]]
@@ -416,6 +462,26 @@ class OracleEstimator:
         tracked = track_consistency(matL, matR, inlL, inlR)
         return tracked, dict(matL_raw=raw[0], matR_raw=raw[1], matL=matL, matR=matR, inlL=inlL, inlR=inlR,
                              p1L=p1L, p2L=p2L, p1R=p1R, p2R=p2R)
+
+    def track_window(self, prev, cur):
+        cand = track_win(prev, cur, self.p.ifm_win_w, self.p.ifm_win_h)
+        pm = prev.matches[cand[:, 0]]
+        cm = cur.matches[cand[:, 1]]
+        def xy(k, idx):
+            return np.stack([k["x"][idx], k["y"][idx]], 1).astype(np.float32)
+        p1L, p1R = xy(prev.kpsL, pm["queryIdx"]), xy(prev.kpsR, pm["trainIdx"])
+        p2L, p2R = xy(cur.kpsL, cm["queryIdx"]), xy(cur.kpsR, cm["trainIdx"])
+        keep = np.ones(len(cand), bool)
+        inlL = inlR = None
+        if self.ransac != "off" and len(cand):
+            fn = cv2_fmat_mask if self.ransac == "cv2" else self.ransac
+            inlL = fn(p1L, p2L)                    # S4:693-713: the right filter only runs when the left one found >= 8
+            if inlL is not None and int(np.count_nonzero(inlL)) >= 8:
+                inlR = fn(p1R, p2R)
+                if inlR is not None and int(np.count_nonzero(inlR)) >= 8:
+                    keep = (np.asarray(inlL).ravel() != 0) & (np.asarray(inlR).ravel() != 0)
+        tracked = cand[keep]
+        return tracked, dict(cand=cand, inlL=inlL, inlR=inlR, p1L=p1L, p2L=p2L, p1R=p1R, p2R=p2R)
 
     # -- stage 5 (stage5_optimization.cpp:392-736) via the tracked pairs ------------------------------
     def optimize(self, prev, cur, tracked, cam, initial_estimation=None):
@@ -452,7 +518,9 @@ class OracleEstimator:
         f = FrameData()
         f.H, f.W = imgL.shape
         f.kpsL, f.descL, rawL = self.detect(imgL)   # P:166
+        f.idxL = self._last_row_index
         f.kpsR, f.descR, rawR = self.detect(imgR)   # P:167
+        f.idxR = self._last_row_index
         out["detected_feats"] = (len(f.kpsL), len(f.kpsR))
         first = self.prev is None
         if self.m_reset and self.prev is not None:    # P:254-267 (the reference crashes without a previous frame)

@@ -623,6 +623,116 @@ void orc_lr_row_index(const OrcDMatch* matches, int n, const OrcKeyPoint* leftKp
     row_index[imgH] = n_left;  // sic: number of left FEATURES (S3:443)
 }
 
+// ---- stage 3, row-by-row descriptor branch (smDescRbR)  S3:185-419 ----------------------------------------
+// Hamming distance the way that branch computes it: byte-wise Kernighan popcount summed in a uint8_t (S3:321-331),
+// i.e. modulo 256 (identical to the true distance except for 256 -> 0).
+static inline unsigned rbr_hamming_u8(const uint8_t* a, const uint8_t* b) {
+    uint8_t d = 0;
+    for (int k = 0; k < 32; ++k) d = (uint8_t)(d + __builtin_popcount((unsigned)(a[k] ^ b[k])));
+    return d;
+}
+
+// idxL / idxR: pyr_feats_index of the two images as m_update_indexes leaves them (orc_update_indexes), imgH entries.
+// out: at most nL matches in left-index order.  Returns the number of matches.
+// Notes kept from the reference: candidate rows come from the quirky row index (so the loop at row y works on the
+// left features of row y+1 and on the right rows y-r+1 .. y+r; the last feature row of either image is never
+// matched), disparity window [1, int(0.7 W)] on int-truncated coordinates, threshold size_t(orb_max_distance) (the
+// parameter, not m_current_orb_th), ratio test inert for descriptors (max_ratio = 1), no epipolar post-filter.
+int orc_match_rbr(const OrcKeyPoint* kpsL, const uint8_t* descL, int nL, const int64_t* idxL,
+                  const OrcKeyPoint* kpsR, const uint8_t* descR, int nR, const int64_t* idxR,
+                  int imgH, int imgW, double max_y_diff, double orb_max_distance, int robust_1to1, OrcDMatch* out) {
+    const size_t max_distance = (size_t)orb_max_distance;                  // S3:206
+    const int INVALID = -1;
+    const uint32_t MAX_D = 0xFFFFFFFFu;
+    std::vector<int> left_match(nL, INVALID);                             // S3:231
+    std::vector<std::pair<int, uint32_t> > right_assign(nR, std::make_pair(INVALID, MAX_D));
+    const int max_disparity = (int)(imgW * 0.7);                           // S3:249
+    const size_t nRowsMax = (size_t)imgH;                                  // idxL.size()
+    const int tol = (int)std::round(max_y_diff);
+    for (size_t y = 0; y + 1 < nRowsMax; ++y) {                            // S3:252
+        const size_t L0 = (size_t)idxL[y], L1 = (size_t)idxL[y + 1];
+        const size_t rmin = (size_t)std::max(0, (int)y - tol);
+        const size_t rmax = std::min((size_t)(imgH - 1), y + (size_t)tol);
+        const size_t R0 = (size_t)idxR[rmin], R1 = (size_t)idxR[rmax];
+        if (L1 - L0 == 0 || R1 - R0 == 0) continue;                        // size_t differences (S3:261-265)
+        for (size_t i = L0; i < L1; ++i) {
+            uint32_t min_1 = MAX_D, min_2 = MAX_D;
+            int min_idx = INVALID;
+            for (size_t j = R0; j < R1; ++j) {
+                const int disparity = (int)(kpsL[i].x - kpsR[j].x);        // S3:285
+                if (disparity < 1 || disparity > max_disparity) continue;
+                const size_t dist = rbr_hamming_u8(descL + i * 32, descR + j * 32);
+                if (dist > max_distance) continue;                         // S3:335
+                if (dist < min_1) { min_2 = min_1; min_1 = (uint32_t)dist; min_idx = (int)j; }
+                else if (dist < min_2) min_2 = (uint32_t)dist;
+            }
+            if (min_idx == INVALID) continue;
+            std::pair<int, uint32_t>& ra = right_assign[min_idx];
+            if (ra.first == INVALID) {                                     // both modes: first claim
+                left_match[i] = min_idx; ra.first = (int)i; ra.second = min_1;
+            } else if (robust_1to1 && min_1 < ra.second) {                 // S3:370-377: keep the BEST, undo the previous one
+                left_match[ra.first] = INVALID;
+                left_match[i] = min_idx; ra.first = (int)i; ra.second = min_1;
+            }
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < nL; ++i)                                           // S3:398-410
+        if (left_match[i] != INVALID) {
+            OrcDMatch d = {i, left_match[i], 0, (float)right_assign[left_match[i]].second};
+            out[m++] = d;
+        }
+    return m;
+}
+
+// ---- stage 4, windowed descriptor branch (ifmDescWin)  S4:435-640 -------------------------------------------
+// prev/cur: stereo matches, left/right keypoints, LEFT descriptors and matches_lr_row_index (imgH+1 entries) of the
+// two frames.  out_prev / out_cur: candidate pairs (index into the previous / current match list) in current-match
+// order, before the F-matrix filter.  Returns their number.
+// Notes kept from the reference: only the left descriptors are compared (S4:585-603), distance in a uint8_t, a
+// candidate must beat 255 strictly, no distance threshold, windows |dy| <= ifm_win_w (sic) and |dx| <= ifm_win_h on
+// both the left and the right keypoint.  One deviation: matches_lr_row_index[imgH] holds the number of left FEATURES
+// (S3:443), so a window that reaches the last image row makes the reference read past the match list; the window end
+// is clamped to the list here.
+int orc_track_win(const OrcDMatch* pm, int nPm, const OrcKeyPoint* pL, const OrcKeyPoint* pR, const uint8_t* pDescL,
+                  const int64_t* pRowIdx, const OrcDMatch* cm, int nCm, const OrcKeyPoint* cL, const OrcKeyPoint* cR,
+                  const uint8_t* cDescL, const int64_t* cRowIdx, int imgH, int imgW, int win_w, int win_h,
+                  int32_t* out_prev, int32_t* out_cur) {
+    const int INVALID = -1;
+    std::vector<std::pair<int, uint32_t> > current(nCm, std::make_pair(INVALID, 0xFFFFFFFFu));
+    const int abs_wx_max = imgW - 1, abs_wy_max = imgH - 1;                // S4:491-492 (descriptor variant)
+    for (int y = 0; y < imgH - 1; ++y) {
+        const size_t p0 = (size_t)pRowIdx[y], p1 = std::min((size_t)pRowIdx[y + 1], (size_t)nPm);
+        if (p1 - p0 == 0 || p1 < p0) continue;
+        const int wy_min = std::max(0, y - win_w), wy_max = std::min(abs_wy_max, y + win_w);
+        const size_t c0 = (size_t)cRowIdx[wy_min], c1 = std::min((size_t)cRowIdx[wy_max + 1], (size_t)nCm);
+        if (c1 - c0 == 0 || c1 < c0) continue;
+        for (size_t pi = p0; pi < p1; ++pi) {
+            const OrcKeyPoint& a = pL[pm[pi].queryIdx];
+            const OrcKeyPoint& b = pR[pm[pi].trainIdx];
+            const int xl0 = std::max(0, (int)(a.x - win_h)), xl1 = std::min(abs_wx_max, (int)(a.x + win_h));
+            const int xr0 = std::max(0, (int)(b.x - win_h)), xr1 = std::min(abs_wx_max, (int)(b.x + win_h));
+            int best_ci = INVALID;
+            uint8_t best = 255;
+            for (size_t ci = c0; ci < c1; ++ci) {
+                const OrcKeyPoint& fl = cL[cm[ci].queryIdx];
+                const OrcKeyPoint& fr = cR[cm[ci].trainIdx];
+                if (fl.x < xl0 || fl.x > xl1 || fr.x < xr0 || fr.x > xr1) continue;
+                const unsigned orb = rbr_hamming_u8(pDescL + (size_t)pm[pi].queryIdx * 32, cDescL + (size_t)cm[ci].queryIdx * 32);
+                if (orb < best) { best = (uint8_t)orb; best_ci = (int)ci; }
+            }
+            if (best_ci == INVALID) continue;
+            std::pair<int, uint32_t>& cur = current[best_ci];              // S4:622-634
+            if (cur.first == INVALID) { cur.first = (int)pi; cur.second = best; }
+            if (cur.first != INVALID && best < cur.second) { cur.first = (int)pi; cur.second = best; }
+        }
+    }
+    int n = 0;
+    for (int ci = 0; ci < nCm; ++ci)
+        if (current[ci].first != INVALID) { out_prev[n] = current[ci].first; out_cur[n] = ci; ++n; }
+    return n;
+}
+
 // ---- stage4 greedy distance / collision filter  S4:145-160 ------------------------------
 // matL / matR compacted in place in lockstep; returns number kept.
 int orc_track_filter(OrcDMatch* matL, OrcDMatch* matR, int n, int curNMatches, int orb_th) {

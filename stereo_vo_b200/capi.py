@@ -47,7 +47,9 @@ class Config(C.Structure):
                 ("use_robust_kernel", C.c_int32), ("kernel_param", C.c_double), ("max_iters", C.c_int32),
                 ("initial_max_iters", C.c_int32), ("min_mod_out_vector", C.c_double), ("max_incr_cost", C.c_int32),
                 ("residual_threshold", C.c_double), ("bad_tracking_th", C.c_int32),
-                ("use_previous_pose_as_initial", C.c_int32), ("vo_use_matches_ids", C.c_int32), ("sort_mode", C.c_int32)]
+                ("use_previous_pose_as_initial", C.c_int32), ("vo_use_matches_ids", C.c_int32), ("sort_mode", C.c_int32),
+                ("match_method", C.c_int32), ("if_match_method", C.c_int32), ("ifm_win_w", C.c_int32),
+                ("ifm_win_h", C.c_int32), ("orb_max_distance", C.c_double)]
 
 
 class Camera(C.Structure):

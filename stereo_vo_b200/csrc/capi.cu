@@ -296,6 +296,11 @@ void svo_default_config(svo_config* cfg) {
     cfg->use_previous_pose_as_initial = 1;
     cfg->vo_use_matches_ids = 0;
     cfg->sort_mode = 0;
+    cfg->match_method = 0;               // smDescBF
+    cfg->if_match_method = 0;            // ifmDescBF
+    cfg->ifm_win_w = 20;
+    cfg->ifm_win_h = 20;
+    cfg->orb_max_distance = 40.0;
 }
 
 const char* svo_last_error(const svo_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -311,6 +316,11 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     if (cfg->min_distance < 2) return fail(nullptr, SVO_ERR_ARG, "min_distance must be >= 2 (the reference divides by uint(min_distance/2))");
     if (cfg->fast_threshold < 1 || cfg->fast_threshold > 254) return fail(nullptr, SVO_ERR_ARG, "fast_threshold out of range");
     if (cfg->max_corners < 16) return fail(nullptr, SVO_ERR_ARG, "max_corners too small");
+    if ((cfg->match_method | 1) != 1) return fail(nullptr, SVO_ERR_ARG, "Stereo matching method not correct (smDescBF = 0 or smDescRbR = 1)");
+    if ((cfg->if_match_method | 1) != 1) return fail(nullptr, SVO_ERR_ARG, "Interframe matching method not correct (ifmDescBF = 0 or ifmDescWin = 1)");
+    if (cfg->ifm_win_w < 0 || cfg->ifm_win_h < 0 || cfg->ifm_win_w > kMaxImgDim || cfg->ifm_win_h > kMaxImgDim)
+        return fail(nullptr, SVO_ERR_ARG, "ifm_win_w / ifm_win_h out of range");
+    if (!(cfg->orb_max_distance >= 0 && cfg->orb_max_distance < 65536)) return fail(nullptr, SVO_ERR_ARG, "orb_max_distance out of range");
     const int quota = 2 * cfg->orb_nfeats;    // size_t(orb_nfeats*(2*nOctaves)/(2^nOctaves-1)), nOctaves = 1
     const int kp_cap = cfg->non_maximal_suppression ? std::min(quota, cfg->max_corners) : cfg->max_corners;
     if (kp_cap > 65535) return fail(nullptr, SVO_ERR_ARG, "more than 65535 keypoints per image are not supported");
@@ -338,6 +348,9 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     p.max_incr_cost = cfg->max_incr_cost; p.residual_threshold = cfg->residual_threshold;
     p.bad_tracking_th = cfg->bad_tracking_th; p.use_prev_pose = cfg->use_previous_pose_as_initial;
     p.use_ids = cfg->vo_use_matches_ids; p.sort_mode = cfg->sort_mode;
+    p.match_method = cfg->match_method; p.ifm_method = cfg->if_match_method;
+    p.ifm_win_w = cfg->ifm_win_w; p.ifm_win_h = cfg->ifm_win_h;
+    p.rbr_max_distance = (int32_t)(size_t)cfg->orb_max_distance;
 
     const int S = cfg->max_seqs + 1;
     c->n_slots_alloc = S;

@@ -299,6 +299,220 @@ track_filter_kernel(Pools P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Alternative matchers of the reference, restated with their quirks.
+// Both are band-limited: a few candidates per query instead of the full N x N brute force.
+// ------------------------------------------------------------------------------------------------
+// Hamming distance as those branches compute it: byte-wise popcounts summed in a uint8_t (S3:321-331, S4:590-603),
+// i.e. the true distance modulo 256.
+__device__ __forceinline__ unsigned hamming256_u8(const uint4* __restrict__ a, const uint4* __restrict__ b) {
+    const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+    const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                  __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+    return (unsigned)d & 0xFFu;
+}
+
+// number of entries of the ascending row list rows[0..n) that are <= r  (rows(i) reads the row of entry i)
+template <class RowOf>
+__device__ __forceinline__ int count_rows_le(RowOf rows, int n, int r) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (rows(mid) <= r) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// pyr_feats_index as m_update_indexes leaves it (S2:103-129): rows before the first feature row and from the last
+// feature row on hold 0, the others the number of features with row <= r.
+__device__ void build_feats_index(const int2* __restrict__ kp, int n, int H, int* idx) {
+    const int y_first = n ? (int)((unsigned)kp[0].x >> 16) : 0, y_last = n ? (int)((unsigned)kp[n - 1].x >> 16) : 0;
+    for (int r = threadIdx.x; r < H; r += blockDim.x)
+        idx[r] = (n && r >= y_first && r < y_last) ? count_rows_le([&](int i) { return (int)((unsigned)kp[i].x >> 16); }, n, r) : 0;
+}
+
+// K5b  rbr_match_kernel: stage 3, smDescRbR branch (S3:185-419), one CTA per slot.
+//   shared: idxL[H] idxR[H] | cand[kp_cap] (min_1 << 16 | right index, or ~0) | assign[kp_cap]
+__global__ void __launch_bounds__(FT)
+rbr_match_kernel(Pools P) {
+    extern __shared__ uint32_t s_dyn[];
+    __shared__ int s_warp[FT / 32];
+    const int H = P.p.H, W = P.p.W;
+    int* idxL = reinterpret_cast<int*>(s_dyn);
+    int* idxR = idxL + H;
+    uint32_t* cand = s_dyn + 2 * H;
+    uint32_t* assign = cand + P.p.kp_cap;
+    const int slot = P.slots[blockIdx.x];
+    SlotState& st = P.state[slot];
+    const int cur = st.cur;
+    const size_t cap = (size_t)P.p.kp_cap;
+    const size_t fL = frame_idx(slot, cur, 0), fR = frame_idx(slot, cur, 1);
+    const int nL = P.n_kp[fL], nR = P.n_kp[fR];
+    const int2* __restrict__ kpL = P.kp + fL * cap;
+    const int2* __restrict__ kpR = P.kp + fR * cap;
+    const uint4* __restrict__ dL = P.desc + fL * cap * 2;
+    const uint4* __restrict__ dR = P.desc + fR * cap * 2;
+    const int tid = threadIdx.x;
+
+    if (st.reset_ids && st.has_prev) {           // P:254-267, see lr_filter_kernel
+        const int Mp = P.p.use_ids ? P.n_match[pair_idx(slot, cur ^ 1)] : 0;
+        long long* idp = P.match_id + pair_idx(slot, cur ^ 1) * cap;
+        for (int m = tid; m < Mp; m += FT) idp[m] = m;
+        __syncthreads();
+        if (tid == 0) { st.last_match_id = Mp; st.last_kf_max_id = (long long)Mp - 1; st.reset_ids = 0; }
+    }
+    build_feats_index(kpL, nL, H, idxL);
+    build_feats_index(kpR, nR, H, idxR);
+    for (int j = tid; j < nR; j += FT) assign[j] = 0xFFFFFFFFu;
+    __syncthreads();
+
+    // best right candidate of every left feature (S3:252-352): the loop at row y works on the left features
+    // [idxL[y], idxL[y+1]) and the right features [idxR[max(0,y-tol)], idxR[min(H-1,y+tol)])
+    const int tol = (int)round(P.p.max_y_diff);
+    const int max_disparity = (int)(W * 0.7);
+    const unsigned max_distance = (unsigned)P.p.rbr_max_distance;
+    const bool robust = P.p.robust_1to1 != 0;
+    for (int i = tid; i < nL; i += FT) {
+        uint32_t best = 0xFFFFFFFFu;
+        const int2 l = kpL[i];
+        const int y = (int)((unsigned)l.x >> 16) - 1;
+        if (y >= 0 && y + 1 < H) {
+            const int L0 = idxL[y], L1 = idxL[y + 1];
+            const int R0 = idxR[max(0, y - tol)], R1 = idxR[min(H - 1, y + tol)];
+            if (i >= L0 && i < L1 && R1 != R0) {
+                const float xl = (float)(l.x & 0xFFFF);
+                for (int j = R0; j < R1; ++j) {
+                    const int disparity = (int)(xl - (float)(kpR[j].x & 0xFFFF));
+                    if (disparity < 1 || disparity > max_disparity) continue;
+                    const unsigned d = hamming256_u8(dL + 2 * (size_t)i, dR + 2 * (size_t)j);
+                    if (d > max_distance) continue;
+                    best = min(best, (d << 16) | (unsigned)j);        // strict '<' in the reference: first index wins ties
+                }
+            }
+        }
+        cand[i] = best;
+        // S3:355-392: a right feature keeps its FIRST claimant, or with enable_robust_1to1_match the BEST one
+        // (strictly smaller distance replaces): both are a minimum over the claimants, walked in index order
+        if (best != 0xFFFFFFFFu) atomicMin(&assign[best & 0xFFFFu], robust ? ((best & 0xFFFF0000u) | (unsigned)i) : (unsigned)i);
+    }
+    __syncthreads();
+
+    // S3:398-410: matches in left-index order; distance = the winning claimant's
+    int4* __restrict__ mout = P.match + pair_idx(slot, cur) * cap;
+    uint4* __restrict__ mdL = P.mdesc + frame_idx(slot, cur, 0) * cap * 2;
+    uint4* __restrict__ mdR = P.mdesc + frame_idx(slot, cur, 1) * cap * 2;
+    int base = 0;
+    for (int i0 = 0; i0 < nL; i0 += FT) {
+        const int i = i0 + tid;
+        int keep = 0, t = 0, dist = 0;
+        if (i < nL && cand[i] != 0xFFFFFFFFu) {
+            t = (int)(cand[i] & 0xFFFFu);
+            dist = (int)(cand[i] >> 16);
+            keep = (int)(assign[t] & 0xFFFFu) == i;
+        }
+        int total;
+        const int off = scan256(keep, s_warp, total);
+        if (keep) {
+            const int m = base + off;
+            mout[m] = make_int4(i, t, dist, 0);
+            mdL[2 * m] = dL[2 * i]; mdL[2 * m + 1] = dL[2 * i + 1];
+            mdR[2 * m] = dR[2 * t]; mdR[2 * m + 1] = dR[2 * t + 1];
+        }
+        base += total;
+    }
+    if (tid == 0) {
+        P.n_match[pair_idx(slot, cur)] = base;
+        P.result[slot].stereo_matches = base;
+    }
+    if (P.p.use_ids && !st.has_prev) {           // S3:67,406-407
+        long long* ids = P.match_id + pair_idx(slot, cur) * cap;
+        const long long b0 = st.last_match_id;
+        for (int m = tid; m < base; m += FT) ids[m] = b0 + m;
+        __syncthreads();
+        if (tid == 0) st.last_match_id = b0 + base;
+    }
+}
+
+// K7b  win_track_kernel: stage 4, ifmDescWin branch up to the candidate list (S4:435-640), one CTA per slot.
+//   shared: pidx[H+1] cidx[H+1] (matches_lr_row_index of the previous / current frame, S3:425-445) | cur[kp_cap]
+// Deviation: matches_lr_row_index[H] holds the number of left FEATURES (S3:443), so a window reaching the last image
+// row makes the reference read past the current match list; the window end is clamped to the list here.
+__global__ void __launch_bounds__(FT)
+win_track_kernel(Pools P) {
+    extern __shared__ uint32_t s_dyn[];
+    __shared__ int s_warp[FT / 32];
+    const int H = P.p.H, W = P.p.W;
+    int* pidx = reinterpret_cast<int*>(s_dyn);
+    int* cidx = pidx + (H + 1);
+    uint32_t* curm = s_dyn + 2 * (H + 1);
+    const int slot = P.slots[blockIdx.x];
+    const SlotState& st = P.state[slot];
+    const int cur = st.cur, prev = cur ^ 1;
+    const size_t cap = (size_t)P.p.kp_cap;
+    const int tid = threadIdx.x;
+    const int Mc = P.n_match[pair_idx(slot, cur)];
+    const int Mp = st.has_prev ? P.n_match[pair_idx(slot, prev)] : 0;
+    const int4* __restrict__ mp = P.match + pair_idx(slot, prev) * cap;
+    const int4* __restrict__ mc = P.match + pair_idx(slot, cur) * cap;
+    const int2* __restrict__ pL = P.kp + frame_idx(slot, prev, 0) * cap;
+    const int2* __restrict__ pR = P.kp + frame_idx(slot, prev, 1) * cap;
+    const int2* __restrict__ cL = P.kp + frame_idx(slot, cur, 0) * cap;
+    const int2* __restrict__ cR = P.kp + frame_idx(slot, cur, 1) * cap;
+    const uint4* __restrict__ pD = P.desc + frame_idx(slot, prev, 0) * cap * 2;
+    const uint4* __restrict__ cD = P.desc + frame_idx(slot, cur, 0) * cap * 2;
+
+    // matches_lr_row_index[y] = number of matches whose left keypoint lies above row y; [H] = number of left features
+    for (int y = tid; y <= H; y += FT) {
+        pidx[y] = y == H ? P.n_kp[frame_idx(slot, prev, 0)]
+                         : count_rows_le([&](int k) { return (int)((unsigned)pL[mp[k].x].x >> 16); }, Mp, y - 1);
+        cidx[y] = y == H ? P.n_kp[frame_idx(slot, cur, 0)]
+                         : count_rows_le([&](int k) { return (int)((unsigned)cL[mc[k].x].x >> 16); }, Mc, y - 1);
+    }
+    for (int k = tid; k < Mc; k += FT) curm[k] = 0xFFFFFFFFu;
+    __syncthreads();
+
+    const int win_w = P.p.ifm_win_w, win_h = P.p.ifm_win_h;
+    for (int pi = tid; pi < Mp; pi += FT) {
+        const int4 m = mp[pi];
+        const int2 a = pL[m.x], b = pR[m.y];
+        const int y = (int)((unsigned)a.x >> 16);
+        if (y >= H - 1) continue;                                         // S4:512: rows 0 .. H-2
+        const int p0 = pidx[y], p1 = pidx[y + 1];
+        if (pi < p0 || pi >= p1) continue;
+        const int wy_min = max(0, y - win_w), wy_max = min(H - 1, y + win_w);     // sic: the vertical window uses win_w
+        const int c0 = cidx[wy_min], c1 = min(cidx[wy_max + 1], Mc);
+        if (c1 <= c0) continue;
+        const float axf = (float)(a.x & 0xFFFF), bxf = (float)(b.x & 0xFFFF);
+        const int xl0 = max(0, (int)(axf - (float)win_h)), xl1 = min(W - 1, (int)(axf + (float)win_h));
+        const int xr0 = max(0, (int)(bxf - (float)win_h)), xr1 = min(W - 1, (int)(bxf + (float)win_h));
+        unsigned best = 255u, best_ci = 0xFFFFu;
+        for (int ci = c0; ci < c1; ++ci) {
+            const int4 c = mc[ci];
+            const int fx = cL[c.x].x & 0xFFFF, gx = cR[c.y].x & 0xFFFF;
+            if (fx < xl0 || fx > xl1 || gx < xr0 || gx > xr1) continue;
+            const unsigned d = hamming256_u8(pD + 2 * (size_t)m.x, cD + 2 * (size_t)c.x);   // left descriptors only (S4:585-603)
+            if (d < best) { best = d; best_ci = (unsigned)ci; }
+        }
+        // S4:620-634: a current match keeps the previous match with the smallest distance, the first one among equals
+        if (best_ci != 0xFFFFu) atomicMin(&curm[best_ci], (best << 16) | (unsigned)pi);
+    }
+    __syncthreads();
+
+    // S4:638-670: candidates in current-match order
+    int4* __restrict__ out = P.tcand + (size_t)slot * cap;
+    int base = 0;
+    for (int c0 = 0; c0 < Mc; c0 += FT) {
+        const int ci = c0 + tid;
+        const int keep = (ci < Mc && curm[ci] != 0xFFFFFFFFu) ? 1 : 0;
+        int total;
+        const int off = scan256(keep, s_warp, total);
+        if (keep) out[base + off] = make_int4((int)(curm[ci] & 0xFFFFu), ci, ci, 0);
+        base += total;
+    }
+    if (tid == 0) {
+        P.n_tcand[slot] = base;
+        P.n_inl[slot * 2 + 0] = 0;     // masks default to "not computed" (S4:693-713)
+        P.n_inl[slot * 2 + 1] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K9  consistency_kernel: one CTA per slot.  S4:243-305, S4:743-752, P:326-330, P:348-352.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FT)
@@ -385,7 +599,16 @@ consistency_kernel(Pools P) {
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
+static int rbr_smem(const Params& p) { return (2 * p.H + 2 * p.kp_cap) * (int)sizeof(uint32_t); }
+static int win_smem(const Params& p) { return (2 * (p.H + 1) + p.kp_cap) * (int)sizeof(uint32_t); }
+
 cudaError_t launch_match_lr(const Pools& P, int n, cudaStream_t st, int* launches, StepTimer* tm) {
+    if (P.p.match_method == 1) {            // smDescRbR: one band-limited kernel instead of brute force + filter
+        rbr_match_kernel<<<n, FT, rbr_smem(P.p), st>>>(P);
+        if (tm) { tm->mark(st); tm->mark(st); }
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     const int per = HM_THREADS * HM_QPT;
     dim3 g((P.p.kp_cap + per - 1) / per, n);
     hamming_pipeline_kernel<<<g, HM_THREADS, 0, st>>>(P, 0, 1);
@@ -397,6 +620,12 @@ cudaError_t launch_match_lr(const Pools& P, int n, cudaStream_t st, int* launche
 }
 
 cudaError_t launch_track_match(const Pools& P, int n, cudaStream_t st, int* launches, StepTimer* tm) {
+    if (P.p.ifm_method == 1) {              // ifmDescWin
+        win_track_kernel<<<n, FT, win_smem(P.p), st>>>(P);
+        if (tm) { tm->mark(st); tm->mark(st); }
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     const int per = HM_THREADS * HM_QPT;
     dim3 g((P.p.kp_cap + per - 1) / per, 2 * n);
     hamming_pipeline_kernel<<<g, HM_THREADS, 0, st>>>(P, 1, 2);
@@ -430,6 +659,10 @@ cudaError_t configure_match(const Params& p) {
                                          (int)((2 * p.kp_cap + 2 * ((p.kp_cap + 31) / 32)) * sizeof(uint32_t)));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lr_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * sizeof(uint32_t)));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rbr_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rbr_smem(p));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(win_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, win_smem(p));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(consistency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * sizeof(uint32_t)));
 }

@@ -45,6 +45,10 @@ struct Params {                     // device copy of svo_config (see include/sv
     int32_t max_incr_cost;
     double  residual_threshold;
     int32_t bad_tracking_th, use_prev_pose, use_ids, sort_mode;
+    int32_t match_method;           // TSMMethod: 0 = smDescBF, 1 = smDescRbR (libstereo-odometry.h:454)
+    int32_t ifm_method;             // TIFMMethod: 0 = ifmDescBF, 1 = ifmDescWin (libstereo-odometry.h:291)
+    int32_t ifm_win_w, ifm_win_h;   // inter-frame search window (libstereo-odometry.h:294)
+    int32_t rbr_max_distance;       // size_t(params_lr_match.orb_max_distance) (stage3_match_left_right.cpp:206)
 };
 
 // Device result record: same layout as svo_result in include/svo_b200.h (static_assert in capi.cu).

@@ -116,6 +116,8 @@ void CStereoOdometryEstimator::loadParamsFromConfigFile(const CConfigFile& ini, 
     if (!sections[3].empty()) { // inter-frame matching (default 0 when the key is missing, H:610)
         params_if_match.ifm_method = static_cast<TInterFrameMatchingParams::TIFMMethod>(ini.read_int(sections[3], "if_match_method", 0));
         params_if_match.filter_fund_matrix = ini.read_bool(sections[3], "filter_fund_matrix", params_if_match.filter_fund_matrix);
+        params_if_match.ifm_win_h = ini.read_int(sections[3], "window_height", params_if_match.ifm_win_h);   // H:614-615
+        params_if_match.ifm_win_w = ini.read_int(sections[3], "window_width", params_if_match.ifm_win_w);
     }
     if (!sections[4].empty()) { // least squares
         TLeastSquaresParams& l = params_least_squares;
@@ -201,10 +203,10 @@ void CStereoOdometryEstimator::ensure_context(int width, int height) {
     // process_new_image_pair.cpp:54-76: only the FAST+ORB / DescBF / DescBF path exists here
     if (params_detect.detect_method != TDetectParams::dmFAST_ORB)
         throw std::runtime_error("[Visual Odometry Error] Detect method not correct (this build has dmFAST_ORB only).");
-    if (params_lr_match.match_method != TLeftRightMatchParams::smDescBF)
-        throw std::runtime_error("[Visual Odometry Error] Stereo matching method not correct (this build has smDescBF only).");
-    if (params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescBF)
-        throw std::runtime_error("[Visual Odometry Error] Interframe matching method not correct (this build has ifmDescBF only).");
+    if (params_lr_match.match_method != TLeftRightMatchParams::smDescBF && params_lr_match.match_method != TLeftRightMatchParams::smDescRbR)
+        throw std::runtime_error("[Visual Odometry Error] Stereo matching method not correct (this build has smDescBF and smDescRbR).");
+    if (params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescBF && params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescWin)
+        throw std::runtime_error("[Visual Odometry Error] Interframe matching method not correct (this build has ifmDescBF and ifmDescWin).");
     if (params_rectify.nOctaves != 1)
         throw std::runtime_error("[Visual Odometry Error] nOctaves must be 1 on this path.");
     if (params_detect.nmsMethod != TDetectParams::nmsmStandard)
@@ -234,6 +236,11 @@ void CStereoOdometryEstimator::ensure_context(int width, int height) {
     cfg.bad_tracking_th = (int32_t)params_least_squares.bad_tracking_th;
     cfg.use_previous_pose_as_initial = params_least_squares.use_previous_pose_as_initial ? 1 : 0;
     cfg.vo_use_matches_ids = params_general.vo_use_matches_ids ? 1 : 0;
+    cfg.match_method = (int32_t)params_lr_match.match_method;
+    cfg.if_match_method = (int32_t)params_if_match.ifm_method;
+    cfg.ifm_win_w = params_if_match.ifm_win_w;
+    cfg.ifm_win_h = params_if_match.ifm_win_h;
+    cfg.orb_max_distance = params_lr_match.orb_max_distance;
     if (svo_create(&cfg, &m_ctx) != SVO_OK) throw_last(nullptr, "svo_create");
     m_w = width;
     m_h = height;

@@ -133,8 +133,9 @@ public:
     };
     struct TInterFrameMatchingParams {              // H:285-310
         enum TIFMMethod { ifmDescBF = 0, ifmDescWin, ifmSAD, ifmOpticalFlow };
-        TIFMMethod ifm_method = ifmDescBF;
-        bool filter_fund_matrix = true;             // the DescBF branch always filters (S4:171-259)
+        TIFMMethod ifm_method = ifmDescBF;          // ifmDescBF and ifmDescWin are built
+        int ifm_win_w = 20, ifm_win_h = 20;         // window of ifmDescWin (uninitialised in the reference, C:84)
+        bool filter_fund_matrix = true;             // both descriptor branches always filter (S4:171-259, :673-713)
     };
     struct TLeastSquaresParams {                    // H:313-350, common.cpp:69-82
         bool use_robust_kernel = true;
@@ -159,7 +160,7 @@ public:
     };
     struct TLeftRightMatchParams {                  // H:449-499, stage3_match_left_right.cpp:46-57
         enum TSMMethod { smDescBF = 0, smDescRbR, smSAD };
-        TSMMethod match_method = smDescBF;          // ctor default smSAD; this shim only has the hot path
+        TSMMethod match_method = smDescBF;          // ctor default smSAD; smDescBF and smDescRbR are built
         double orb_max_distance = 40;
         int orb_min_th = 30, orb_max_th = 100;
         bool enable_robust_1to1_match = false, rectified_images = true;

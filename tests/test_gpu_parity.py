@@ -821,3 +821,60 @@ def test_match_id_and_keyframe_control():
             ctx.set_ids(np.arange(3))                   # wrong length
     finally:
         ctx.close()
+
+
+# ------------------------------------------------------------------------------------ alternative matchers
+@pytest.mark.parametrize("mm,im", [(1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("robust", [0, 1])
+def test_alternative_matchers_bit_exact(mm, im, robust):
+    """smDescRbR (stage3_match_left_right.cpp:185-419) and ifmDescWin (stage4_match_consecutive.cpp:435-738) against the
+    oracle's restatement: stereo matches, tracked pairs, inlier lists and iteration counts bit-exact, pose within the
+    north_star tolerance."""
+    pytest.importorskip("cv2")
+    frames, cam = synth.make_sequence("c1", seed=6, n_frames=4)
+    kw = dict(match_method=mm, ifm_win_w=15, ifm_win_h=25, max_y_diff=2.0, orb_max_distance=50.0)
+    # orb_threshold = m_current_orb_th, which an INI load sets to orb_max_distance (libstereo-odometry.h:539,662)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, if_match_method=im, enable_robust_1to1_match=robust,
+                       orb_threshold=50, **kw)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100, ifm_method=im, enable_robust_1to1_match=bool(robust), **kw),
+                              backend="port", ransac="cv2")
+    try:
+        for i, (L, R) in enumerate(frames):
+            o = est.process_new_image_pair(L, R, ocam(cam))
+            r = ctx.process_pair(L, R, gcam(cam))
+            assert np.array_equal(mtuple(ctx.matches(0, 0)), mtuple(o["frame"].matches)), i
+            assert r.stereo_matches == o["stereo_matches"]
+            assert r.error_code == o["error_code"] and bool(r.valid) == o["valid"], i
+            if i > 0:
+                assert np.array_equal(ctx.tracked_pairs(0), o["tracked"]), i
+                assert (r.num_it, r.num_it_final) == (o["num_it"], o["num_it_final"])
+                assert np.array_equal(ctx.outliers(0), o["outliers"])
+                assert np.allclose(np.array(r.delta_pose[:3]), o["pose"]["delta"][:3], atol=POSE_TOL_RAD)
+                assert np.allclose(np.array(r.delta_pose[3:]), o["pose"]["delta"][3:], atol=POSE_TOL_M)
+        assert r.valid and r.stereo_matches > 50 and r.tracked_feats_from_last_frame > 30
+    finally:
+        ctx.close()
+
+
+def test_alternative_matchers_batch_c2_with_ids():
+    """config-2 size, several slots per step, match IDs on: the band-limited matchers through the batched entry."""
+    pytest.importorskip("cv2")
+    seqs = [synth.make_sequence("c2", seed=s, n_frames=3) for s in (0, 1, 2)]
+    cam = seqs[0][1]
+    kw = dict(match_method=1, ifm_win_w=20, ifm_win_h=30)
+    ctx = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=3, if_match_method=1, vo_use_matches_ids=1, **kw)
+    ests = [orc.OracleEstimator(orc.Params(orb_nfeats=500, ifm_method=1, vo_use_matches_ids=True, **kw), backend="port", ransac="cv2")
+            for _ in seqs]
+    try:
+        for t in range(3):
+            res = ctx.process_batch([s[0][t][0] for s in seqs], [s[0][t][1] for s in seqs], [gcam(cam)] * 3)
+            for k, est in enumerate(ests):
+                o = est.process_new_image_pair(seqs[k][0][t][0], seqs[k][0][t][1], ocam(cam))
+                assert np.array_equal(mtuple(ctx.matches(k, 0)), mtuple(o["frame"].matches)), (t, k)
+                assert np.array_equal(ctx.match_ids(k, 0), o["frame"].ids), (t, k)
+                if t > 0:
+                    assert np.array_equal(ctx.tracked_pairs(k), o["tracked"]), (t, k)
+                    assert bool(res[k].valid) == o["valid"] and res[k].valid
+                    assert np.allclose(np.array(res[k].delta_pose[:]), o["pose"]["delta"], atol=1e-4)
+    finally:
+        ctx.close()

@@ -29,7 +29,7 @@ def test_library_exports_every_header_symbol(built_lib):
     for name in declared:
         assert hasattr(L, name), f"{name} is declared in svo_b200.h but not exported"
     assert sorted(capi.EXPORTS) == declared
-    assert L.svo_abi_version() == 1
+    assert L.svo_abi_version() == 2
 
 
 def test_struct_layouts_match_header(built_lib):
@@ -41,6 +41,7 @@ def test_struct_layouts_match_header(built_lib):
     assert (cfg.orb_nfeats, cfg.fast_threshold, cfg.min_distance, cfg.orb_threshold) == (500, 20, 3, 40)
     assert (cfg.max_iters, cfg.initial_max_iters, cfg.max_incr_cost, cfg.bad_tracking_th) == (100, 10, 3, 5)
     assert cfg.kernel_param == 3.0 and cfg.residual_threshold == 10.0 and cfg.min_mod_out_vector == 1e-3
+    assert (cfg.match_method, cfg.if_match_method, cfg.ifm_win_w, cfg.ifm_win_h, cfg.orb_max_distance) == (0, 0, 20, 20, 40.0)
 
 
 def test_no_cpu_fallback_without_device(built_lib):

@@ -396,3 +396,70 @@ def test_stage1_oracle_matches_cv2_live():
     mxy, ma = cv2.initUndistortRectifyMap(K, D, R, P, (W, H), cv2.CV_16SC2)
     ref = cv2.remap(src, mxy, ma, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
     assert np.array_equal(po.remap_bilinear(src, mxy, ma), ref)
+
+
+# ---------------------------------------------------------------- alternative matchers (S3:185-419, S4:435-738)
+def _brute_rbr(kL, dL, kR, dR, H, W, tol, max_d, robust):
+    """independent numpy/py restatement of what smDescRbR computes, written from its effect rather than its loop:
+    left feature of row ry (not the last feature row) sees right features of rows ry-tol .. ry+tol-1 (not the last
+    right feature row), disparity in [1, int(0.7 W)], u8 Hamming <= max_d, first minimum; a right feature keeps its
+    first (or, robust, its best) claimant."""
+    yL = kL["y"].astype(int); yR = kR["y"].astype(int)
+    last_L = yL.max() if len(yL) else -1
+    last_R = yR.max() if len(yR) else -1
+    first_R = yR.min() if len(yR) else 0
+    claim = {}
+    cand = {}
+    for i in range(len(kL)):
+        ry = yL[i]
+        if ry >= last_L:
+            continue
+        y = ry - 1
+        lo_row, hi_row = max(0, y - tol), min(H - 1, y + tol)
+        def idxR(r):
+            return int((yR <= r).sum()) if (first_R <= r < last_R) else 0
+        R0, R1 = idxR(lo_row), idxR(hi_row)
+        best = None
+        for j in range(R0, R1):
+            disp = int(kL["x"][i] - kR["x"][j])
+            if disp < 1 or disp > int(W * 0.7):
+                continue
+            d = int(np.unpackbits(dL[i] ^ dR[j]).sum()) & 0xFF
+            if d > max_d:
+                continue
+            if best is None or d < best[0]:
+                best = (d, j)
+        if best is not None:
+            cand[i] = best
+            d, j = best
+            if j not in claim or (robust and d < claim[j][0]):
+                claim[j] = (d, i)
+    return [(i, j, claim[j][0]) for i, (d, j) in sorted(cand.items()) if claim[j][1] == i]
+
+
+@pytest.mark.parametrize("robust", [False, True])
+def test_rbr_oracle_matches_independent_restatement(robust):
+    frames, cam = synth.make_sequence("c1", seed=8, n_frames=1)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100, match_method=1, max_y_diff=2.0, orb_max_distance=60.0,
+                                         enable_robust_1to1_match=robust), backend="port", ransac="off")
+    o = est.process_new_image_pair(frames[0][0], frames[0][1], orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"]))
+    f = o["frame"]
+    exp = _brute_rbr(f.kpsL, f.descL, f.kpsR, f.descR, f.H, f.W, 2, 60, robust)
+    got = [(int(m["queryIdx"]), int(m["trainIdx"]), int(m["distance"])) for m in f.matches]
+    assert got == exp and len(got) > 50
+
+
+def test_window_tracker_oracle_properties():
+    """ifmDescWin candidates: every pair respects both windows, each current match is used once, the chosen previous
+    match has the smallest left-descriptor distance among the previous matches that picked this current match."""
+    frames, cam = synth.make_sequence("c1", seed=8, n_frames=2)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100, ifm_method=1, ifm_win_w=12, ifm_win_h=30), backend="port", ransac="off")
+    camo = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    o0 = est.process_new_image_pair(frames[0][0], frames[0][1], camo)
+    o1 = est.process_new_image_pair(frames[1][0], frames[1][1], camo)
+    prev, cur, cand = o0["frame"], o1["frame"], o1["track_dbg"]["cand"]
+    assert len(cand) > 40 and len(set(cand[:, 1].tolist())) == len(cand) and np.all(np.diff(cand[:, 1]) > 0)
+    for pi, ci in cand:
+        a = prev.kpsL[prev.matches["queryIdx"][pi]]; b = prev.kpsR[prev.matches["trainIdx"][pi]]
+        c = cur.kpsL[cur.matches["queryIdx"][ci]]; d = cur.kpsR[cur.matches["trainIdx"][ci]]
+        assert abs(int(c["y"]) - int(a["y"])) <= 12 and abs(int(c["x"]) - int(a["x"])) <= 30 and abs(int(d["x"]) - int(b["x"])) <= 30
