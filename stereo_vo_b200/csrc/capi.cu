@@ -65,6 +65,7 @@ struct svo_ctx {
     int occ_words = 0;
     uint32_t* d_sort_scratch = nullptr;
     uint2* d_list_scratch = nullptr;
+    uint32_t* d_key_scratch = nullptr;
     // pinned host staging
     int32_t* h_slots = nullptr;
     uint8_t* h_repeat = nullptr;
@@ -156,7 +157,8 @@ int enqueue_items(svo_ctx* c, int a, int n, const uint8_t* d_left, const uint8_t
     const size_t img2 = 2 * (size_t)a;              // scratch indexed by (item, side)
     CU(c, launch_detect(P, n, d_left + a * image_pitch, d_right + a * image_pitch, stride, image_pitch, c->pitch,
                         c->d_occ + img2 * c->occ_words, c->occ_words, c->d_sort_scratch + img2 * c->cfg.max_corners,
-                        c->d_list_scratch + img2 * 2 * (c->cfg.max_corners / 16 + 2), st, &L, t));
+                        c->d_list_scratch + img2 * 3 * (c->cfg.max_corners / 16 + 2),
+                        c->d_key_scratch + img2 * c->cfg.max_corners, st, &L, t));
     CU(c, launch_match_lr(P, n, st, &L, t));
     CU(c, launch_track_match(P, n, st, &L, t));
     if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, RS, n, st, &L, t));
@@ -381,7 +383,8 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     }
     DA(c->d_occ, (size_t)S * 2 * c->occ_words);
     DA(c->d_sort_scratch, (size_t)S * 2 * cfg->max_corners);
-    DA(c->d_list_scratch, (size_t)S * 2 * 2 * (cfg->max_corners / 16 + 2));
+    DA(c->d_list_scratch, (size_t)S * 2 * 3 * (cfg->max_corners / 16 + 2));
+    DA(c->d_key_scratch, (size_t)S * 2 * cfg->max_corners);
     GnScratch& G = c->G;
     DA(G.prev, S * cap); DA(G.obs, S * cap); DA(G.lmk, S * cap * 3); DA(G.mask, S * cap);
     DA(G.cur_idx, S * cap); DA(G.ini_pose, S * 6);
@@ -952,7 +955,7 @@ int svo_detect(svo_ctx* c, const uint8_t* img, size_t stride, svo_keypoint* out_
     CU(c, launch_begin_step(c->P, 1, nullptr, c->stream));
     int L = 1;
     CU(c, launch_detect(c->P, 1, c->d_stageL, c->d_stageR, c->pitch, plane, c->pitch, c->d_occ, c->occ_words,
-                        c->d_sort_scratch, c->d_list_scratch, c->stream, &L));
+                        c->d_sort_scratch, c->d_list_scratch, c->d_key_scratch, c->stream, &L));
     c->launches += L;
     const int n = svo_get_keypoints(c, hs, 0, 0, out_kps, cap);
     if (n < 0) return n;

@@ -342,18 +342,22 @@ __device__ void block_stable_sort(uint32_t* a, uint32_t* tmp, int n) {
 
 __global__ void __launch_bounds__(K2_THREADS)
 select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_words_per_img,
-              uint32_t* __restrict__ sort_scratch, uint2* __restrict__ list_scratch) {
+              uint32_t* __restrict__ sort_scratch, uint2* __restrict__ list_scratch, uint32_t* __restrict__ key_scratch,
+              int smem_corners) {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t* s_a = smem;                          // [max_corners]
-    uint32_t* s_b = smem + P.p.max_corners;        // [kp_cap]
+    // The candidate words are compacted into global scratch first; they are sorted in shared memory when they fit
+    // into smem_corners words (4 CTAs per SM at the default sizes), in the global array otherwise (same code, slower).
+    uint32_t* g_a = key_scratch + (size_t)blockIdx.x * P.p.max_corners;
+    uint32_t* s_b = smem + smem_corners;           // [kp_cap]
     // segment lists of the sort emulation live in global memory (one read + one write per segment): keeps the
     // shared-memory footprint at 4 B per candidate so that three CTAs fit on an SM
     const int list_cap = P.p.max_corners / 16 + 2;
-    uint2* s_listA = list_scratch + (size_t)blockIdx.x * 2 * list_cap;
+    uint2* s_listA = list_scratch + (size_t)blockIdx.x * 3 * list_cap;
     uint2* s_listB = s_listA + list_cap;
+    uint2* s_listS = s_listB + list_cap;
     __shared__ int s_warp[K2_THREADS / 32];
     __shared__ int s_nsel;
-    __shared__ int s_cnt2[2];
+    __shared__ int s_cnt2[3];
     __shared__ int s_pos[64 * (K2_THREADS / 32)];
     uint32_t* tmp = sort_scratch + (size_t)blockIdx.x * P.p.max_corners;
 
@@ -405,7 +409,7 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
                         m &= m - 1;
                         const uint32_t sc = (w[q] >> (bit - 7)) & 0xFFu;
                         if (o < P.p.max_corners) {
-                            s_a[o] = (sc << 24) | (uint32_t)o;
+                            g_a[o] = (sc << 24) | (uint32_t)o;
                             cand_pos[o] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * q + (bit >> 3));
                         }
                         ++o;
@@ -417,6 +421,12 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
     }
     if (base > P.p.max_corners) { overflow = true; base = P.p.max_corners; }
     const int n = base;
+    uint32_t* s_a = g_a;
+    __syncthreads();
+    if (n <= smem_corners) {
+        s_a = smem;
+        for (int i = tid; i < n; i += K2_THREADS) s_a[i] = g_a[i];
+    }
     if (tid == 0) {
         P.n_cand[img_idx(slot, side)] = n;
         if (overflow) P.state[slot].status = -3;  // SVO_ERR_CAPACITY
@@ -429,7 +439,7 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
 
     if (P.p.nms) {
         // ---- B. sort by response, descending (KeypointResponseSorter) ------------------------------
-        if (P.p.sort_mode == 0) introsort_block(KeyComp<true, 24>(), s_a, n, s_listA, s_listB, s_cnt2, tmp, s_pos);
+        if (P.p.sort_mode == 0) introsort_block(KeyComp<true, 24>(), s_a, n, s_listA, s_listB, s_listS, s_cnt2, tmp, s_pos);
         else block_stable_sort<true, 24>(s_a, tmp, n);
         // ---- C. greedy occupancy grid ---------------------------------------------------------------
         const unsigned cell = (unsigned)(P.p.min_distance / 2.0);     // S2:331
@@ -474,7 +484,7 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
         s_b[k] = (pos & 0xFFFF0000u) | (uint32_t)k;   // y << 16 | position in the selection order
     }
     __syncthreads();
-    if (P.p.sort_mode == 0) introsort_block(KeyComp<false, 16>(), s_b, n_sel, s_listA, s_listB, s_cnt2, tmp, s_pos);
+    if (P.p.sort_mode == 0) introsort_block(KeyComp<false, 16>(), s_b, n_sel, s_listA, s_listB, s_listS, s_cnt2, tmp, s_pos);
     else block_stable_sort<false, 16>(s_b, tmp, n_sel);
     // ---- E. emit ------------------------------------------------------------------------------------
     for (int i = tid; i < n_sel; i += K2_THREADS) {
@@ -595,8 +605,10 @@ __global__ void begin_step_kernel(Pools P, int n, const uint8_t* __restrict__ re
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
+// candidate words sorted in shared memory: at most 12288 (48 KB) so that four CTAs share an SM
+int detect_smem_corners(const Params& p) { return p.max_corners < 12288 ? p.max_corners : 12288; }
 int detect_smem_bytes(const Params& p) {
-    return ((p.max_corners + p.kp_cap + 1) & ~1) * (int)sizeof(uint32_t);
+    return ((detect_smem_corners(p) + p.kp_cap + 1) & ~1) * (int)sizeof(uint32_t);
 }
 
 cudaError_t configure_detect(const Params& p) {
@@ -610,12 +622,14 @@ cudaError_t launch_begin_step(const Pools& P, int n, const uint8_t* d_repeat, cu
 
 cudaError_t launch_detect(const Pools& P, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
                           size_t image_pitch, int pitch_out, uint32_t* occ_scratch, int occ_words_per_img,
-                          uint32_t* sort_scratch, uint2* list_scratch, cudaStream_t st, int* launches, StepTimer* tm) {
+                          uint32_t* sort_scratch, uint2* list_scratch, uint32_t* key_scratch, cudaStream_t st, int* launches,
+                          StepTimer* tm) {
     const dim3 g1((P.p.W + TW - 1) / TW, (P.p.H + TH - 1) / TH, 2 * n);
     fast_blur_kernel<<<g1, K1_THREADS, 0, st>>>(P, d_left, d_right, stride, image_pitch, pitch_out);
     if (tm) tm->mark(st);
     const int smem = detect_smem_bytes(P.p);
-    select_kernel<<<2 * n, K2_THREADS, smem, st>>>(P, pitch_out, occ_scratch, occ_words_per_img, sort_scratch, list_scratch);
+    select_kernel<<<2 * n, K2_THREADS, smem, st>>>(P, pitch_out, occ_scratch, occ_words_per_img, sort_scratch, list_scratch,
+                                                   key_scratch, detect_smem_corners(P.p));
     if (tm) tm->mark(st);
     const dim3 g3((P.p.kp_cap + K3_WARPS * K3_ITERS - 1) / (K3_WARPS * K3_ITERS), 2 * n);
     brief_kernel<<<g3, K3_WARPS * 32, 0, st>>>(P, pitch_out);

@@ -20,6 +20,10 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef SVO_THREAD_SEG_MAX
+#define SVO_THREAD_SEG_MAX 32
+#endif
+
 #if defined(__CUDACC__)
 #define SVO_HD __host__ __device__ __forceinline__
 #else
@@ -143,15 +147,13 @@ SVO_HD void insertion_sort_(const C& c, uint32_t* a, int first, int last) {
     }
 }
 
-// Sequential emulation.  `stack` needs room for 2*64 ints (ranges pending on the explicit stack).
+// std::__introsort_loop on a[first..last) with the given remaining depth, one thread: explicit stack of
+// (first, last, depth) replacing the recursion on the right part.  Leaves segments of <= 16 elements unsorted.
 template <class C>
-SVO_HD void introsort_seq_c(const C& c, uint32_t* a, int n) {
-    if (n <= 1) return;
-    // explicit stack of (first, last, depth) replacing the recursion on the right part
+SVO_HD void introsort_loop_seq(const C& c, uint32_t* a, int first0, int last0, int depth0) {
     int st_first[64], st_last[64], st_depth[64];
-    int sp = 0;
-    st_first[0] = 0; st_last[0] = n; st_depth[0] = 2 * floor_log2(n);
-    sp = 1;
+    int sp = 1;
+    st_first[0] = first0; st_last[0] = last0; st_depth[0] = depth0;
     while (sp > 0) {
         --sp;
         int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
@@ -170,9 +172,15 @@ SVO_HD void introsort_seq_c(const C& c, uint32_t* a, int n) {
             last = cut;
         }
     }
-    insertion_sort_(c, a, 0, n);
 }
 
+// Sequential emulation of std::sort.
+template <class C>
+SVO_HD void introsort_seq_c(const C& c, uint32_t* a, int n) {
+    if (n <= 1) return;
+    introsort_loop_seq(c, a, 0, n, 2 * floor_log2(n));
+    insertion_sort_(c, a, 0, n);
+}
 
 // Rank-table formulation of the unguarded Hoare partition of a[first..last) around the pivot at a[first]
 // (what the warp- and block-cooperative versions below compute, kept sequential here so that the host unit
@@ -309,6 +317,9 @@ __device__ int warp_unguarded_partition(const C& c, uint32_t* a, int seg_first, 
 //   posL / posR: room for (last - first) uint16 each;  s_blk: 2 * nwarps + 1 ints of shared memory.
 constexpr int kBlockPartMin = 1024;      // segments at least this long are partitioned by the whole block
 constexpr int kBlockPartMaxList = 16;    // ... on levels with at most this many segments
+constexpr int kThreadSegMax = SVO_THREAD_SEG_MAX;   // segments up to this long are finished by ONE thread each (sequential
+                                         // std::__introsort_loop): near the leaves there are hundreds of independent
+                                         // segments, and a warp per 20..100 elements wastes most of its lanes
 
 template <class C>
 __device__ int block_unguarded_partition(const C& c, uint32_t* a, int first, int last, uint16_t* posL, uint16_t* posR,
@@ -376,16 +387,23 @@ __device__ int block_unguarded_partition(const C& c, uint32_t* a, int first, int
     return cut;
 }
 
-// Sort a[0..n) (shared memory) with all threads of the block.  listA/listB: room for n/16 + 2 entries each
-// (shared memory), s_cnt: 2 ints (shared), tmp: n words of scratch (global or shared), s_pos: 64 ints per warp.
+// children of a partition: short ones go to the per-thread list, the others to the next level
+__device__ __forceinline__ void push_segment(int first, int last, int depth, uint2* out, int* cnt_out, uint2* small, int* cnt_small) {
+    if (last - first <= kSortThreshold) return;
+    const uint2 e = make_uint2((unsigned)first, (unsigned)last | ((unsigned)depth << 24));
+    if (last - first <= kThreadSegMax) small[atomicAdd(cnt_small, 1)] = e;
+    else out[atomicAdd(cnt_out, 1)] = e;
+}
+
+// Sort a[0..n) (shared memory) with all threads of the block.  listA/listB/listS: room for n/16 + 2 entries each,
+// s_cnt: 3 ints (shared), tmp: n words of scratch (global or shared), s_pos: 64 ints per warp.
 template <class C>
-__device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, uint2* listB, int* s_cnt, uint32_t* tmp,
+__device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, uint2* listB, uint2* listS, int* s_cnt, uint32_t* tmp,
                                 int* s_pos /* 64 ints per warp, shared */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     if (tid == 0) {
-        s_cnt[0] = 0;
-        if (n > kSortThreshold) { listA[0] = make_uint2(0u, (unsigned)n | ((unsigned)(2 * floor_log2(n)) << 24)); s_cnt[0] = 1; }
-        s_cnt[1] = 0;
+        s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+        push_segment(0, n, 2 * floor_log2(max(n, 1)), listA, &s_cnt[0], listS, &s_cnt[2]);
     }
     __syncthreads();
     int cur = 0;
@@ -407,8 +425,8 @@ __device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, ui
                 uint16_t* pos16 = reinterpret_cast<uint16_t*>(tmp);
                 const int cut = block_unguarded_partition(c, a, first, last, pos16, pos16 + n, s_pos);
                 if (tid == 0) {
-                    if (last - cut > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)cut, (unsigned)last | ((unsigned)(depth - 1) << 24));
-                    if (cut - first > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)first, (unsigned)cut | ((unsigned)(depth - 1) << 24));
+                    push_segment(cut, last, depth - 1, out, &s_cnt[cur ^ 1], listS, &s_cnt[2]);
+                    push_segment(first, cut, depth - 1, out, &s_cnt[cur ^ 1], listS, &s_cnt[2]);
                 }
             }
         }
@@ -431,13 +449,22 @@ __device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, ui
             __syncwarp();
             const int cut = warp_unguarded_partition(c, a, first, last, s_pos + 64 * warp);
             if (lane == 0) {
-                if (last - cut > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)cut, (unsigned)last | ((unsigned)depth << 24));
-                if (cut - first > kSortThreshold) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = make_uint2((unsigned)first, (unsigned)cut | ((unsigned)depth << 24));
+                push_segment(cut, last, depth, out, &s_cnt[cur ^ 1], listS, &s_cnt[2]);
+                push_segment(first, cut, depth, out, &s_cnt[cur ^ 1], listS, &s_cnt[2]);
             }
         }
         __syncthreads();
         if (tid == 0) s_cnt[cur] = 0;
         cur ^= 1;
+        __syncthreads();
+    }
+    // the short segments: one thread each, sequential std::__introsort_loop
+    {
+        const int ns = s_cnt[2];
+        for (int sidx = tid; sidx < ns; sidx += blockDim.x) {
+            const uint2 e = listS[sidx];
+            introsort_loop_seq(c, a, (int)e.x, (int)(e.y & 0xFFFFFFu), (int)(e.y >> 24));
+        }
         __syncthreads();
     }
     // final insertion sort == stable placement inside the <= 16-element leaves

@@ -123,6 +123,23 @@ def test_detect_flat_and_tiny_content(ctx_c1):
     _check_detect(ctx_c1, one, 200)
 
 
+def test_detect_more_candidates_than_the_shared_memory_sort_holds():
+    """FAST threshold 7 on the config-2 texture gives ~12.9k corners inside the ORB border: more than the 12288 words the
+    sort emulation keeps in shared memory, so select_kernel sorts in its global scratch; results must not change."""
+    ctx = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=1, fast_threshold=7)
+    try:
+        frames, _ = synth.make_sequence("c2", seed=1, n_frames=1)
+        img = frames[0][0]
+        k, d = ctx.detect(img)
+        rk, rd = orc.orb_compute(img, orc.fast9(img, 7))
+        assert len(rk) > 12288
+        rk, rd, _ = orc.non_max_sup(1000, rk, rd, 3, 480, 640)
+        rk, rd, _, _ = orc.update_indexes(rk, rd, 480)
+        assert np.array_equal(xys(k), xys(rk)) and np.array_equal(d, rd) and len(k) == 1000
+    finally:
+        ctx.close()
+
+
 def test_detect_capacity_overflow_is_reported():
     ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, max_corners=64)
     try:
