@@ -244,6 +244,16 @@ int svo_get_change_in_pose(svo_ctx* ctx, int32_t slot,
                            const svo_camera* cam, int32_t use_custom_initial_pose, const double* ini_estimation,
                            svo_result* result);
 
+/* getProjectedCoords (libstereo-odometry.h:175-182, common.cpp:415-470): the stereo matches of the previous key frame
+ * whose other_matches_tracked entry is -1 are triangulated and projected into the left and right image with
+ * delta_pose = [w1 w2 w3 t1 t2 t3], the rotation-vector form of the INVERSE of change_pose the reference derives at
+ * common.cpp:459-464 (MRPT pose algebra stays with the caller).  out_pixels: 4 floats (xl, yl, xr, yr) per projected
+ * match, in match order.  Returns their number. */
+int svo_get_projected_coords(svo_ctx* ctx, const svo_dmatch* pre_matches, int32_t n_matches,
+                             const svo_keypoint* pre_left, int32_t n_pl, const svo_keypoint* pre_right, int32_t n_pr,
+                             const int32_t* other_matches_tracked, const svo_camera* cam, const double* delta_pose,
+                             float* out_pixels, int32_t cap);
+
 /* cv::findFundamentalMat(p1, p2, FM_RANSAC, 1.0, 0.99, mask) (stage4_match_consecutive.cpp:202,237):
  * n x 2 float32 points (host), mask n bytes.  Returns the inlier count, 0 (and an all-zero mask)
  * when no model was found or n < 7. */

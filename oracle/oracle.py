@@ -79,6 +79,7 @@ def lib():
         _lib.orc_bf_match.restype = C.c_int
         _lib.orc_lr_filter.restype = C.c_int
         _lib.orc_track_filter.restype = C.c_int
+        _lib.orc_projected_coords.restype = C.c_int
         _lib.orc_match_rbr.restype = C.c_int
         _lib.orc_track_win.restype = C.c_int
         _lib.orc_track_consistency.restype = C.c_int
@@ -211,6 +212,18 @@ def track_win(prev, cur, win_w, win_h):
     n = lib().orc_track_win(_p(pm), len(pm), _p(a[0]), _p(a[1]), _p(pd), _p(pri), _p(cm), len(cm), _p(a[2]), _p(a[3]),
                             _p(cd), _p(cri), int(cur.H), int(cur.W), int(win_w), int(win_h), _p(op), _p(oc))
     return np.stack([op[:n], oc[:n]], 1).astype(np.int64)
+
+
+def projected_coords(pre_matches, pre_left, pre_right, other_matches_tracked, cam, delta_pose):
+    """getProjectedCoords (common.cpp:415-470) for delta_pose = [w t] of the inverse of change_pose."""
+    pm = np.ascontiguousarray(pre_matches, DMATCH)
+    kl = np.ascontiguousarray(pre_left, KEYPOINT)
+    kr = np.ascontiguousarray(pre_right, KEYPOINT)
+    fl = np.ascontiguousarray(other_matches_tracked, np.int32)
+    dp = np.ascontiguousarray(delta_pose, np.float64)
+    out = np.zeros((max(len(pm), 1), 4), np.float32)
+    n = lib().orc_projected_coords(_p(pm), len(pm), _p(kl), _p(kr), _p(fl), C.byref(cam), _p(dp), _p(out))
+    return out[:n].copy()
 
 
 def track_consistency(matL, matR, inlL, inlR):

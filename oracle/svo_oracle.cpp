@@ -925,6 +925,35 @@ void orc_stage5(const float* l1l, const float* l1r, const float* l2l, const floa
     res->last_cost = cCost;
 }
 
+// ---- getProjectedCoords  C:415-470 --------------------------------------------------------------------------
+// The matches flagged -1 are triangulated (C:428-455, same formula as S5:537-542) and projected with
+// m_pinhole_stereo_projection (S5:165-193) for delta_pose = [w t] of the inverse of change_pose (C:459-464; that MRPT
+// pose algebra is the caller's).  out: 4 floats per projected match.  Returns their number.
+int orc_projected_coords(const OrcDMatch* pre_matches, int n_matches, const OrcKeyPoint* pre_left, const OrcKeyPoint* pre_right,
+                         const int32_t* other_matches_tracked, const OrcCamera* cam, const double* delta_pose, float* out) {
+    RotDeriv R;
+    rot_and_derivs(delta_pose, R);
+    int n = 0;
+    for (int m = 0; m < n_matches; ++m) {
+        if (other_matches_tracked[m] != -1) continue;
+        const double ul = pre_left[pre_matches[m].queryIdx].x, vl = pre_left[pre_matches[m].queryIdx].y;
+        const double ur = pre_right[pre_matches[m].trainIdx].x;
+        const double disparity = cam->fxl * (cam->cxr - ur) + cam->fxr * (ul - cam->cxl);
+        const double b_d = cam->baseline / disparity;
+        const double X1p = b_d * cam->fxr * (ul - cam->cxl), Y1p = b_d * cam->fxr * (vl - cam->cyl), Z1p = b_d * cam->fxl * cam->fxr;
+        const double X1c = R.r[0][0] * X1p + R.r[0][1] * Y1p + R.r[0][2] * Z1p + delta_pose[3];
+        const double Y1c = R.r[1][0] * X1p + R.r[1][1] * Y1p + R.r[1][2] * Z1p + delta_pose[4];
+        const double Z1c = R.r[2][0] * X1p + R.r[2][1] * Y1p + R.r[2][2] * Z1p + delta_pose[5];
+        const double X2c = X1c - cam->baseline;
+        out[4 * n + 0] = (float)(cam->fxl * X1c / Z1c + cam->cxl);
+        out[4 * n + 1] = (float)(cam->fyl * Y1c / Z1c + cam->cyl);
+        out[4 * n + 2] = (float)(cam->fxr * X2c / Z1c + cam->cxr);
+        out[4 * n + 3] = (float)(cam->fyr * Y1c / Z1c + cam->cyr);
+        ++n;
+    }
+    return n;
+}
+
 int orc_sizeof_keypoint() { return (int)sizeof(OrcKeyPoint); }
 int orc_sizeof_dmatch() { return (int)sizeof(OrcDMatch); }
 

@@ -33,7 +33,7 @@ EXPORTS = [
     "svo_fundmat_ransac", "svo_abi_version", "svo_kernel_launches", "svo_stream",
     "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks", "svo_set_concurrency",
     "svo_set_input_format", "svo_set_rectify_maps", "svo_prepare_rectify", "svo_prepare_rectify_device",
-    "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
+    "svo_get_projected_coords", "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
 ]
 
 
@@ -310,6 +310,18 @@ class Context:
                                                  _vp(kl[3]), len(kl[3]), C.byref(cam), int(ini is not None), _vp(ini),
                                                  C.byref(res)))
         return res
+
+    def get_projected_coords(self, pre_matches, pre_left, pre_right, other_matches_tracked, cam, delta_pose):
+        pm = np.ascontiguousarray(pre_matches, DMATCH)
+        kl = np.ascontiguousarray(pre_left, KEYPOINT)
+        kr = np.ascontiguousarray(pre_right, KEYPOINT)
+        fl = np.ascontiguousarray(other_matches_tracked, np.int32)
+        dp = np.ascontiguousarray(delta_pose, np.float64)
+        assert len(fl) == len(pm) and len(dp) == 6
+        out = np.zeros((max(len(pm), 1), 4), np.float32)
+        n = self._check(lib().svo_get_projected_coords(self._h, _vp(pm), len(pm), _vp(kl), len(kl), _vp(kr), len(kr), _vp(fl),
+                                                       C.byref(cam), _vp(dp), _vp(out), len(out)))
+        return out[:n].copy()
 
     def fundmat_ransac(self, p1, p2):
         p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)

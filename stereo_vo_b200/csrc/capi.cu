@@ -1100,6 +1100,52 @@ int svo_get_change_in_pose(svo_ctx* c, int32_t slot, const int64_t* tracked_pair
     return result->valid;
 }
 
+int svo_get_projected_coords(svo_ctx* c, const svo_dmatch* pre_matches, int32_t n_matches, const svo_keypoint* pre_left,
+                             int32_t n_pl, const svo_keypoint* pre_right, int32_t n_pr, const int32_t* other_matches_tracked,
+                             const svo_camera* cam, const double* delta_pose, float* out_pixels, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (n_matches < 0 || n_pl < 0 || n_pr < 0 || !cam || !delta_pose || (n_matches > 0 && (!pre_matches || !other_matches_tracked)))
+        return fail(c, SVO_ERR_ARG, "bad argument");
+    std::vector<int32_t> order;
+    std::vector<int4> hm((size_t)n_matches);
+    for (int m = 0; m < n_matches; ++m) {
+        hm[m] = make_int4(pre_matches[m].queryIdx, pre_matches[m].trainIdx, 0, 0);
+        if (other_matches_tracked[m] != -1) continue;                 // C:430-431
+        if (pre_matches[m].queryIdx < 0 || pre_matches[m].queryIdx >= n_pl || pre_matches[m].trainIdx < 0 || pre_matches[m].trainIdx >= n_pr)
+            return fail(c, SVO_ERR_ARG, "match index outside the keypoint lists");
+        order.push_back(m);
+    }
+    const int n = (int)order.size();
+    if (n > cap) return fail(c, SVO_ERR_ARG, "output capacity too small");
+    if (n == 0) return 0;
+    if (!out_pixels || !pre_left || !pre_right) return fail(c, SVO_ERR_ARG, "NULL argument");
+    CU(c, cudaSetDevice(c->cfg.device));
+    std::vector<float2> hl((size_t)n_pl), hr((size_t)n_pr);
+    for (int i = 0; i < n_pl; ++i) hl[i] = make_float2(pre_left[i].x, pre_left[i].y);
+    for (int i = 0; i < n_pr; ++i) hr[i] = make_float2(pre_right[i].x, pre_right[i].y);
+    int4* dm = nullptr; float2* dl = nullptr; float2* dr = nullptr; int32_t* dord = nullptr; double* dpose = nullptr; float4* dout = nullptr;
+    cudaError_t e = cudaMalloc(&dm, hm.size() * sizeof(int4));
+    if (e == cudaSuccess) e = cudaMalloc(&dl, std::max<size_t>(1, hl.size()) * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&dr, std::max<size_t>(1, hr.size()) * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&dord, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&dpose, 6 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)n * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dm, hm.data(), hm.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && n_pl) e = cudaMemcpyAsync(dl, hl.data(), hl.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && n_pr) e = cudaMemcpyAsync(dr, hr.data(), hr.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dord, order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dpose, delta_pose, 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    Camera cm;
+    memcpy(&cm, cam, sizeof(Camera));
+    if (e == cudaSuccess) e = launch_project(dm, dl, dr, dord, n, cm, dpose, dout, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_pixels, dout, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dm); cudaFree(dl); cudaFree(dr); cudaFree(dord); cudaFree(dpose); cudaFree(dout);
+    if (e != cudaSuccess) return cuda_fail(c, e, "svo_get_projected_coords");
+    c->launches += 1;
+    return n;
+}
+
 int svo_fundmat_ransac(svo_ctx* c, const float* p1, const float* p2, int32_t n, uint8_t* mask) {
     if (!c) return SVO_ERR_ARG;
     if (n < 0 || (n > 0 && (!p1 || !p2 || !mask))) return fail(c, SVO_ERR_ARG, "bad arguments");

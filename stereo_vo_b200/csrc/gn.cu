@@ -591,6 +591,41 @@ cudaError_t configure_gn(const Params& p) {
     return cudaFuncSetAttribute(gn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * 8));
 }
 
+// getProjectedCoords (common.cpp:415-470): triangulate the stereo matches flagged "not tracked" (flag == -1) in the
+// previous frame (S5:537-542 formula) and project them with the pose [w1 w2 w3 t1 t2 t3] (m_pinhole_stereo_projection,
+// S5:165-193, pixels as float32 TPixelCoordf).  One thread per flagged match; `order` lists their match indices.
+__global__ void project_kernel(const int4* __restrict__ matches, const float2* __restrict__ left, const float2* __restrict__ right,
+                               const int32_t* __restrict__ order, int n, Camera cam, const double* __restrict__ pose,
+                               float4* __restrict__ out) {
+    __shared__ RotDeriv R;
+    __shared__ double dp[6];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 6; ++i) dp[i] = pose[i];
+        rot_and_derivs(dp, R);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 m = matches[order[i]];
+    const double ul = left[m.x].x, vl = left[m.x].y, ur = right[m.y].x;
+    const double disparity = cam.fxl * (cam.cxr - ur) + cam.fxr * (ul - cam.cxl);
+    const double b_d = cam.baseline / disparity;
+    const double X1p = b_d * cam.fxr * (ul - cam.cxl), Y1p = b_d * cam.fxr * (vl - cam.cyl), Z1p = b_d * cam.fxl * cam.fxr;
+    const double X1c = R.r[0][0] * X1p + R.r[0][1] * Y1p + R.r[0][2] * Z1p + dp[3];
+    const double Y1c = R.r[1][0] * X1p + R.r[1][1] * Y1p + R.r[1][2] * Z1p + dp[4];
+    const double Z1c = R.r[2][0] * X1p + R.r[2][1] * Y1p + R.r[2][2] * Z1p + dp[5];
+    const double X2c = X1c - cam.baseline;
+    out[i] = make_float4((float)(cam.fxl * X1c / Z1c + cam.cxl), (float)(cam.fyl * Y1c / Z1c + cam.cyl),
+                         (float)(cam.fxr * X2c / Z1c + cam.cxr), (float)(cam.fyr * Y1c / Z1c + cam.cyr));
+}
+
+cudaError_t launch_project(const int4* d_matches, const float2* d_left, const float2* d_right, const int32_t* d_order, int n,
+                           const Camera& cam, const double* d_pose, float4* d_out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    project_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_matches, d_left, d_right, d_order, n, cam, d_pose, d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gn(const Pools& P, const GnScratch& G, int n, int external, int use_custom_pose,
                       int assume_fast_kps, cudaStream_t st, int* launches, StepTimer* tm) {
     gn_kernel<<<n, GN_THREADS, P.p.kp_cap * 8, st>>>(P, G, external, use_custom_pose, assume_fast_kps);

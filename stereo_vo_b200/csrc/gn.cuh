@@ -17,6 +17,9 @@ struct GnScratch {            // per-slot scratch, [max_seqs][kp_cap] unless not
 };
 
 cudaError_t configure_gn(const Params& p);
+// getProjectedCoords (common.cpp:415-470) on device arrays
+cudaError_t launch_project(const int4* d_matches, const float2* d_left, const float2* d_right, const int32_t* d_order, int n,
+                           const Camera& cam, const double* d_pose, float4* d_out, cudaStream_t st);
 cudaError_t launch_gn(const Pools& P, const GnScratch& G, int n, int external, int use_custom_pose,
                       int assume_fast_kps, cudaStream_t st, int* launches, StepTimer* tm = nullptr);
 }  // namespace svo

@@ -342,6 +342,52 @@ bool CStereoOdometryEstimator::getChangeInPose(const vector_index_pairs_t& track
     return result.valid;
 }
 
+void CStereoOdometryEstimator::getProjectedCoords(const std::vector<DMatch>& pre_matches, const std::vector<KeyPoint>& pre_left_feats,
+                                                  const std::vector<KeyPoint>& pre_right_feats,
+                                                  const std::vector<std::pair<int, float> >& other_matches_tracked,
+                                                  const TStereoCamera& stereo_camera, const CPose3D& change_pose,
+                                                  std::vector<std::pair<Point2f, Point2f> >& pro_pre_feats) {
+    if (other_matches_tracked.size() > pre_matches.size())
+        throw std::runtime_error("[Visual Odometry Error] getProjectedCoords: more tracking flags than matches.");
+    const int w = stereo_camera.leftCamera.ncols ? (int)stereo_camera.leftCamera.ncols : (m_w ? m_w : 640);
+    const int h = stereo_camera.leftCamera.nrows ? (int)stereo_camera.leftCamera.nrows : (m_h ? m_h : 480);
+    ensure_context(w, h);
+    // C:459-464: auxPose = change_pose^-1, then its rotation-vector form [w1 w2 w3 t1 t2 t3]
+    const double* M = change_pose.m;
+    double Ri[9], ti[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Ri[3 * i + j] = M[4 * j + i];
+        ti[i] = -(M[i] * M[3] + M[4 + i] * M[7] + M[8 + i] * M[11]);
+    }
+    double dp[6] = {0, 0, 0, ti[0], ti[1], ti[2]};
+    const double tr = std::max(-1.0, std::min(3.0, Ri[0] + Ri[4] + Ri[8]));
+    const double angle = std::acos(std::max(-1.0, std::min(1.0, (tr - 1.0) / 2.0)));
+    const double vx = Ri[7] - Ri[5], vy = Ri[2] - Ri[6], vz = Ri[3] - Ri[1];      // 2 sin(angle) * axis
+    if (angle > 1e-12) {
+        const double s = std::sin(angle);
+        if (std::fabs(s) > 1e-9) { const double k = angle / (2.0 * s); dp[0] = k * vx; dp[1] = k * vy; dp[2] = k * vz; }
+        else {   // angle ~ pi: axis from the diagonal
+            const double ax = std::sqrt(std::max(0.0, (Ri[0] + 1) / 2)), ay = std::sqrt(std::max(0.0, (Ri[4] + 1) / 2)),
+                         az = std::sqrt(std::max(0.0, (Ri[8] + 1) / 2));
+            dp[0] = angle * ax; dp[1] = angle * (Ri[1] + Ri[3] < 0 ? -ay : ay); dp[2] = angle * (Ri[2] + Ri[6] < 0 ? -az : az);
+        }
+    }
+    std::vector<int32_t> flags(pre_matches.size(), 0);          // entries beyond other_matches_tracked are not visited (C:428)
+    for (size_t m = 0; m < other_matches_tracked.size(); ++m) flags[m] = other_matches_tracked[m].first;
+    const svo_camera cam = to_cam(stereo_camera);
+    std::vector<float> out(4 * std::max<size_t>(1, pre_matches.size()));
+    const int n = svo_get_projected_coords(m_ctx, reinterpret_cast<const svo_dmatch*>(pre_matches.data()), (int32_t)pre_matches.size(),
+                                           reinterpret_cast<const svo_keypoint*>(pre_left_feats.data()), (int32_t)pre_left_feats.size(),
+                                           reinterpret_cast<const svo_keypoint*>(pre_right_feats.data()), (int32_t)pre_right_feats.size(),
+                                           flags.data(), &cam, dp, out.data(), (int32_t)pre_matches.size());
+    if (n < 0) throw_last(m_ctx, "svo_get_projected_coords");
+    pro_pre_feats.resize((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        pro_pre_feats[i].first = Point2f{out[4 * i], out[4 * i + 1]};
+        pro_pre_feats[i].second = Point2f{out[4 * i + 2], out[4 * i + 3]};
+    }
+}
+
 void CStereoOdometryEstimator::getValues(std::vector<KeyPoint>& leftKP, std::vector<KeyPoint>& rightKP, Mat& leftDesc, Mat& rightDesc,
                                          std::vector<DMatch>& matches, std::vector<size_t>& matches_id) {
     if (!m_ctx) throw std::runtime_error("[Visual Odometry Error] no current frame.");

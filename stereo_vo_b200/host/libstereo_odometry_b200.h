@@ -190,6 +190,15 @@ public:
                          const std::vector<KeyPoint>& cur_right_feats, const TStereoCamera& stereo_camera,
                          TStereoOdometryResult& result, const std::vector<double>& ini_estimation = std::vector<double>(6, 0));
 
+    /** Projects the stereo matches of the previous key frame that were NOT tracked (other_matches_tracked[m].first == -1)
+      * into the current left / right images for the given change in pose (H:175-182, common.cpp:415-470).  The inverse
+      * of change_pose is turned into [w t] here (MRPT's CPose3D::inverse + CPose3DRotVec(CPose3D), restated with the
+      * standard SO(3) logarithm); triangulation and projection run on the device. */
+    void getProjectedCoords(const std::vector<DMatch>& pre_matches, const std::vector<KeyPoint>& pre_left_feats,
+                            const std::vector<KeyPoint>& pre_right_feats, const std::vector<std::pair<int, float> >& other_matches_tracked,
+                            const TStereoCamera& stereo_camera, const CPose3D& change_pose,
+                            std::vector<std::pair<Point2f, Point2f> >& pro_pre_feats);
+
     /** Copies of the current frame's data (H:704-724). */
     void getValues(std::vector<KeyPoint>& leftKP, std::vector<KeyPoint>& rightKP, Mat& leftDesc, Mat& rightDesc,
                    std::vector<DMatch>& matches, std::vector<size_t>& matches_id);

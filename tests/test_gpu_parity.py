@@ -895,3 +895,27 @@ def test_alternative_matchers_batch_c2_with_ids():
                     assert np.allclose(np.array(res[k].delta_pose[:]), o["pose"]["delta"], atol=1e-4)
     finally:
         ctx.close()
+
+
+def test_get_projected_coords(ctx_c1):
+    """getProjectedCoords (common.cpp:415-470): untracked stereo matches of the previous frame projected into the
+    current one; float32 pixels, compared with the oracle bit for bit up to 1 ulp and against the geometry."""
+    frames, cam = synth.make_sequence("c1", seed=2, n_frames=2)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend="port", ransac="off")
+    o0 = est.process_new_image_pair(frames[0][0], frames[0][1], ocam(cam))
+    o1 = est.process_new_image_pair(frames[1][0], frames[1][1], ocam(cam))
+    f0 = o0["frame"]
+    flags = np.full(len(f0.matches), -1, np.int32)
+    flags[o1["tracked"][:, 0]] = o1["tracked"][:, 1]          # tracked ones are skipped
+    delta = o1["pose"]["delta"]                               # [w t] of the inverse of outPose
+    exp = orc.projected_coords(f0.matches, f0.kpsL, f0.kpsR, flags, ocam(cam), delta)
+    got = ctx_c1.get_projected_coords(f0.matches, f0.kpsL, f0.kpsR, flags, gcam(cam), delta)
+    assert got.shape == exp.shape and len(got) == int((flags == -1).sum()) > 10
+    assert np.allclose(got, exp, rtol=0, atol=2e-4)           # float32 pixels; FMA contraction may differ in the last ulp
+    # geometry: the scene moves 0.05 m laterally between frames -> projections stay on the same rows, right = left - disparity
+    assert np.abs(got[:, 1] - got[:, 3]).max() < 1e-3 and (got[:, 0] > got[:, 2]).all()
+    # zero pose: the projection reproduces the measured keypoints of the untracked matches
+    got0 = ctx_c1.get_projected_coords(f0.matches, f0.kpsL, f0.kpsR, flags, gcam(cam), np.zeros(6))
+    sel = f0.matches[flags == -1]
+    assert np.allclose(got0[:, 0], f0.kpsL["x"][sel["queryIdx"]], atol=1e-3) and np.allclose(got0[:, 2], f0.kpsR["x"][sel["trainIdx"]], atol=1e-3)
+    assert len(ctx_c1.get_projected_coords(f0.matches, f0.kpsL, f0.kpsR, np.zeros(len(f0.matches), np.int32), gcam(cam), delta)) == 0
