@@ -312,6 +312,27 @@ def stage1_microbench(ctx, torch, stream, device, W, H, peak, n=128, iters=5):
     ctx.set_rectify_maps()
     return out
 
+def single_pair_latency(capi, seqs, gc, W, H, nfeats, device_index, n=60):
+    """what one caller with ONE sequence sees: svo_process_pair per frame (host images in, result out, synchronous)"""
+    ctx = capi.Context(width=W, height=H, orb_nfeats=nfeats, max_seqs=1, device=device_index)
+    frames = seqs[0]
+    ts = []
+    valid = 0
+    for t in range(n + 5):
+        L, R = frames[pingpong(t, len(frames))]
+        t0 = time.perf_counter()
+        r = ctx.process_pair(L, R, gc)
+        dt = time.perf_counter() - t0
+        if t >= 5:
+            ts.append(dt)
+            valid += int(r.valid)
+    ctx.close()
+    ts = np.array(ts) * 1e3
+    return {"median_ms": round(float(np.median(ts)), 3), "p90_ms": round(float(np.percentile(ts, 90)), 3),
+            "pairs_per_s": round(1e3 / float(np.median(ts)), 1), "valid": f"{valid}/{n}",
+            "note": "batch of one: the kernels are latency-bound here, throughput needs many sequences per step"}
+
+
 def run_c5(args):
     """--workload c5: the microbench on N GPUs.  Query rows are sharded across the ranks, the train set is
     replicated (broadcast from rank 0), the packed results are all-gathered (the one exchange step, NCCL)."""
@@ -565,6 +586,7 @@ def run_gpu(args):
         int_roof = 1.0 / max(HM_POPC / pipe["popc_per_s"], HM_ALU / pipe["lop3_per_s"])
         micro, _ = c5_microbench(ctx, torch, stream, torch.device("cuda", local), pipe, peak, reps=64, iters=5)
         stage1 = stage1_microbench(ctx, torch, stream, torch.device("cuda", local), W, H, peak)
+        latency = single_pair_latency(capi, seqs, gc, W, H, nfeats, local)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -601,6 +623,7 @@ def run_gpu(args):
                             "hbm_gbs": (ab["hamming_kernel(lr)"] + ab["hamming_kernel(track)"]) / (hm_ms * 1e-3) / 1e9 if hm_ms else None},
             "match_microbench": micro,
             "stage1": stage1,
+            "single_pair": latency,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -919,3 +919,33 @@ def test_get_projected_coords(ctx_c1):
     sel = f0.matches[flags == -1]
     assert np.allclose(got0[:, 0], f0.kpsL["x"][sel["queryIdx"]], atol=1e-3) and np.allclose(got0[:, 2], f0.kpsR["x"][sel["trainIdx"]], atol=1e-3)
     assert len(ctx_c1.get_projected_coords(f0.matches, f0.kpsL, f0.kpsR, np.zeros(len(f0.matches), np.int32), gcam(cam), delta)) == 0
+
+
+@pytest.mark.parametrize("W,H", [(250, 130), (333, 97), (64, 64)])
+def test_stage1_odd_sizes_against_oracle(W, H):
+    """widths that are not multiples of 4 / 16 (scalar map loads, ragged last work items), strongly distorted maps
+    (large out-of-image regions, footprints spanning several rows), padded source strides."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(W * 1000 + H)
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+    maps = []
+    for side in (0, 1):
+        a = 0.15 * (1 + side)
+        fx = np.rint((xs * (1.2 + 0.1 * side) - 0.1 * W + a * ys + 3 * np.sin(ys / 7.0)) * 32).astype(np.int64)
+        fy = np.rint((ys * 0.9 + 0.05 * H - a * xs * 0.5 + 2 * np.cos(xs / 9.0)) * 32).astype(np.int64)
+        maps.append((np.stack([fx >> 5, fy >> 5], -1).astype(np.int16), ((fy & 31) * 32 + (fx & 31)).astype(np.uint16)))
+    ctx = capi.Context(width=W, height=H, orb_nfeats=50, max_seqs=1)
+    try:
+        for ch in (1, 3):
+            shape = (H, W) if ch == 1 else (H, W, 3)
+            L = rng.integers(0, 256, shape, dtype=np.uint8)
+            R = rng.integers(0, 256, shape, dtype=np.uint8)
+            ctx.set_rectify_maps()
+            oL, oR = ctx.prepare_rectify(L, R)
+            assert np.array_equal(oL, po.gray_bgr(L)) and np.array_equal(oR, po.gray_bgr(R))
+            ctx.set_rectify_maps(maps[0][0], maps[0][1], maps[1][0], maps[1][1])
+            oL, oR = ctx.prepare_rectify(L, R)
+            assert np.array_equal(oL, po.stage1(L, *maps[0])) and np.array_equal(oR, po.stage1(R, *maps[1]))
+            assert (oL == 0).sum() > 10          # the constant border was reached
+    finally:
+        ctx.close()
