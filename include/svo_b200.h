@@ -146,7 +146,7 @@ int svo_process_batch(svo_ctx* ctx, int32_t n, const int32_t* slots,
 /* The same step split in two for pipelining: svo_submit_batch enqueues the host->device copies (on a
  * copy stream), the kernels and the device->host copy of the results and returns at once; svo_wait_batch
  * blocks until the OLDEST submitted batch is complete and writes its results (in the order of that
- * batch's slot list).  At most two batches may be in flight, so the copies of batch t+1 overlap the
+ * batch's slot list).  At most three batches may be in flight, so the copies of batches t+1, t+2 overlap the
  * kernels of batch t.  The host image buffers must stay valid (and should be pinned) until the wait. */
 int svo_submit_batch(svo_ctx* ctx, int32_t n, const int32_t* slots,
                      const uint8_t* const* left, const uint8_t* const* right, size_t stride_bytes,

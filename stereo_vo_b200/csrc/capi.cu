@@ -33,6 +33,8 @@ static const char* kKernelNames[KT_COUNT] = {
     "gn_kernel"};
 
 enum { kMaxChunks = 8, kDefaultChunks = 4, kMinChunkItems = 32 };
+enum { kDepth = 3 };   // batches in flight (svo_submit_batch / svo_wait_batch): with three staging buffers the copy stream
+                       // never waits for the host to see a batch finish before the next upload can start
 
 struct svo_ctx {
     svo_config cfg;
@@ -47,17 +49,17 @@ struct svo_ctx {
     int pitch = 0;              // row pitch of the internal image planes (W rounded up to 16)
     uint8_t* d_stageL = nullptr;      // == d_stL[0] (used by the synchronous per-stage entries)
     uint8_t* d_stageR = nullptr;
-    // two-deep submit/wait pipeline: staging images, pinned meta/result rings, events
+    // kDepth-deep submit/wait pipeline: staging images, pinned meta/result rings, events
     cudaStream_t copy_stream = nullptr;
-    uint8_t* d_stL[2] = {nullptr, nullptr};
-    uint8_t* d_stR[2] = {nullptr, nullptr};
-    int32_t* r_slots[2] = {nullptr, nullptr};
-    uint8_t* r_repeat[2] = {nullptr, nullptr};
-    Camera* r_cams[2] = {nullptr, nullptr};
-    Result* r_res[2] = {nullptr, nullptr};
-    SlotState* r_state[2] = {nullptr, nullptr};
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    int pend_n[2] = {0, 0}, pend_lo[2] = {0, 0}, pend_hi[2] = {0, 0};
+    uint8_t* d_stL[kDepth] = {};
+    uint8_t* d_stR[kDepth] = {};
+    int32_t* r_slots[kDepth] = {};
+    uint8_t* r_repeat[kDepth] = {};
+    Camera* r_cams[kDepth] = {};
+    Result* r_res[kDepth] = {};
+    SlotState* r_state[kDepth] = {};
+    cudaEvent_t ev_h2d[kDepth] = {}, ev_done[kDepth] = {};
+    int pend_n[kDepth] = {}, pend_lo[kDepth] = {}, pend_hi[kDepth] = {};
     int pend_head = 0, pend_count = 0;
     uint8_t* d_repeat = nullptr;
     Camera* d_cams_batch = nullptr;
@@ -79,7 +81,7 @@ struct svo_ctx {
     bool rectify = false;
     short2* d_map_xy[2] = {nullptr, nullptr};
     uint16_t* d_map_a[2] = {nullptr, nullptr};
-    uint8_t* d_raw[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][side]
+    uint8_t* d_raw[kDepth][2] = {};                                    // [buffer][side]
     uint8_t* d_gray[2] = {nullptr, nullptr};                           // gray planes between conversion and rectification
     size_t raw_pitch = 0;             // bytes per row of the raw staging images
     int raw_channels = 0;
@@ -128,6 +130,19 @@ cudaError_t halloc(svo_ctx* c, T** p, size_t count) {
 __global__ void scatter_cams_kernel(Pools P, const Camera* cams, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) P.cam[P.slots[i]] = cams[i];
+}
+
+// Batch description from pinned host memory (read by the kernel over PCIe, a few KB) into the device arrays.
+// A kernel instead of cudaMemcpyAsync: small H2D copies issued on the compute stream would queue on the host->device
+// copy engine BEHIND the image uploads of the following batches and delay this batch's kernels by a whole upload.
+__global__ void upload_meta_kernel(int32_t* __restrict__ d_slots, Camera* __restrict__ d_cams, uint8_t* __restrict__ d_repeat,
+                                   const int32_t* __restrict__ h_slots, const Camera* __restrict__ h_cams,
+                                   const uint8_t* __restrict__ h_repeat, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d_slots[i] = h_slots[i];
+    d_cams[i] = h_cams[i];
+    if (h_repeat) d_repeat[i] = h_repeat[i];
 }
 
 __global__ void reset_slot_kernel(Pools P, int slot) {
@@ -239,10 +254,10 @@ bool needs_stage1(const svo_ctx* c) { return c->in_channels != 1 || c->rectify; 
 // raw staging for inputs that go through stage 1 on the device (colour and / or unrectified images)
 int ensure_raw_staging(svo_ctx* c) {
     if (c->d_raw[0][0] && c->raw_channels >= c->in_channels) return SVO_OK;
-    for (int b = 0; b < 2; ++b) for (int sd = 0; sd < 2; ++sd) c->d_raw[b][sd] = nullptr;   // old buffers stay in dev_allocs
+    for (int b = 0; b < kDepth; ++b) for (int sd = 0; sd < 2; ++sd) c->d_raw[b][sd] = nullptr;   // old buffers stay in dev_allocs
     c->raw_channels = c->in_channels;
     c->raw_pitch = ((size_t)c->cfg.width * c->raw_channels + 15) & ~(size_t)15;
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < kDepth; ++b)
         for (int sd = 0; sd < 2; ++sd) {
             cudaError_t e = dalloc(c, &c->d_raw[b][sd], (size_t)c->n_slots_alloc * c->raw_pitch * c->cfg.height);
             if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc raw staging");
@@ -371,7 +386,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     DA(P.lr_best, S * cap); DA(P.tr_best, S * 2 * cap); DA(P.tcand, S * cap); DA(P.n_tcand, S);
     DA(P.inl, S * 2 * cap); DA(P.n_inl, S * 2); DA(P.tracked, S * cap); DA(P.n_tracked, S);
     DA(P.residual, S * cap); DA(P.outliers, S * cap); DA(P.slots, S);
-    for (int b = 0; b < 2; ++b) { DA(c->d_stL[b], (size_t)S * plane); DA(c->d_stR[b], (size_t)S * plane); }
+    for (int b = 0; b < kDepth; ++b) { DA(c->d_stL[b], (size_t)S * plane); DA(c->d_stR[b], (size_t)S * plane); }
     c->d_stageL = c->d_stL[0]; c->d_stageR = c->d_stR[0];
     DA(c->d_repeat, S); DA(c->d_cams_batch, S);
     // occupancy grids (only touched when uint(min_distance/2) != 1): worst case 1-px... cells >= 2 px
@@ -397,7 +412,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
         c->RS.slots = P.slots; c->RS.inl = P.inl; c->RS.n_inl = P.n_inl;
     }
     HA(c->h_slots, S); HA(c->h_repeat, S); HA(c->h_cams, S); HA(c->h_results, S);
-    for (int b = 0; b < 2; ++b) { HA(c->r_slots[b], S); HA(c->r_repeat[b], S); HA(c->r_cams[b], S); HA(c->r_res[b], S); HA(c->r_state[b], S); }
+    for (int b = 0; b < kDepth; ++b) { HA(c->r_slots[b], S); HA(c->r_repeat[b], S); HA(c->r_cams[b], S); HA(c->r_res[b], S); HA(c->r_state[b], S); }
 #undef DA
 #undef HA
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -407,7 +422,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
         e = cudaStreamCreateWithFlags(&c->aux[j], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[j], cudaEventDisableTiming);
     }
-    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    for (int b = 0; b < kDepth && e == cudaSuccess; ++b) {
         e = cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming);
     }
@@ -429,7 +444,7 @@ void svo_destroy(svo_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
-    for (int b = 0; b < 2; ++b) { if (c->ev_h2d[b]) cudaEventDestroy(c->ev_h2d[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
+    for (int b = 0; b < kDepth; ++b) { if (c->ev_h2d[b]) cudaEventDestroy(c->ev_h2d[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
     for (int j = 0; j < kMaxChunks; ++j) {
         if (c->aux[j]) { cudaStreamSynchronize(c->aux[j]); cudaStreamDestroy(c->aux[j]); }
         if (c->ev_join[j]) cudaEventDestroy(c->ev_join[j]);
@@ -632,9 +647,9 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
     if (!c) return SVO_ERR_ARG;
     if (!left || !right || !cams) return fail(c, SVO_ERR_ARG, "NULL argument");
     if (n <= 0 || n > c->cfg.max_seqs) return fail(c, SVO_ERR_ARG, "batch size out of range");
-    if (c->pend_count == 2) return fail(c, SVO_ERR_STATE, "two batches are already in flight: call svo_wait_batch first");
+    if (c->pend_count == kDepth) return fail(c, SVO_ERR_STATE, "three batches are already in flight: call svo_wait_batch first");
     CU(c, cudaSetDevice(c->cfg.device));
-    const int b = (c->pend_head + c->pend_count) & 1;
+    const int b = (c->pend_head + c->pend_count) % kDepth;
     std::vector<char> seen(c->cfg.max_seqs, 0);
     int lo = c->cfg.max_seqs, hi = -1;
     for (int i = 0; i < n; ++i) {
@@ -677,9 +692,16 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
     }
     CU(c, cudaEventRecord(c->ev_h2d[b], c->copy_stream));
     CU(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
-    CU(c, cudaMemcpyAsync(c->P.slots, c->r_slots[b], n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_cams_batch, c->r_cams[b], n * sizeof(Camera), cudaMemcpyHostToDevice, c->stream));
-    if (repeat) CU(c, cudaMemcpyAsync(c->d_repeat, c->r_repeat[b], n, cudaMemcpyHostToDevice, c->stream));
+    {
+        void *ds = nullptr, *dc = nullptr, *dr = nullptr;      // device views of the pinned rings (identical under UVA)
+        CU(c, cudaHostGetDevicePointer(&ds, c->r_slots[b], 0));
+        CU(c, cudaHostGetDevicePointer(&dc, c->r_cams[b], 0));
+        CU(c, cudaHostGetDevicePointer(&dr, c->r_repeat[b], 0));
+        upload_meta_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->P.slots, c->d_cams_batch, c->d_repeat, (const int32_t*)ds,
+                                                                   (const Camera*)dc, repeat ? (const uint8_t*)dr : nullptr, n);
+        CU(c, cudaGetLastError());
+        c->launches += 1;
+    }
     if (stage1) {   // stage1_prepare_rectify on the device: raw staging -> gray, rectified planes
         int L1 = 0;
         CU(c, launch_prepare(prepare_args(c, upL, upR, up_pitch, up_plane, c->d_stL[b], c->d_stR[b]), n, c->in_channels,
@@ -709,7 +731,7 @@ int svo_wait_batch(svo_ctx* c, svo_result* results) {
         results[i].status = st;
         if (st != 0) { results[i].valid = 0; rc = st; }
     }
-    c->pend_head ^= 1;
+    c->pend_head = (c->pend_head + 1) % kDepth;
     --c->pend_count;
     if (rc == SVO_ERR_CAPACITY) return fail(c, rc, "max_corners exceeded for at least one image (raise svo_config.max_corners)");
     return rc;

@@ -461,6 +461,15 @@ def test_submit_wait_pipeline_equals_synchronous_calls(ctx_c1):
     assert got == ref
     res = (capi.Result * 1)()
     assert capi.lib().svo_wait_batch(ctx_c1._h, res) == capi.SVO_ERR_STATE      # nothing in flight
+    # three batches in flight (the pipeline depth); a fourth submit is refused until a wait
+    ctx_c1.reset_slot(3)
+    for k in range(3):
+        ctx_c1.submit_batch([frames[k][0]], [frames[k][1]], [gcam(cam)], slots=[3])
+    with pytest.raises(capi.SvoError) as e:
+        ctx_c1.submit_batch([frames[3][0]], [frames[3][1]], [gcam(cam)], slots=[3])
+    assert e.value.code == capi.SVO_ERR_STATE
+    got3 = [key(ctx_c1.wait_batch()[0]) for _ in range(3)]
+    assert got3 == ref[:3]
 
 
 def test_state_machine_first_frame_bad_tracking_and_repeat(ctx_c1):
