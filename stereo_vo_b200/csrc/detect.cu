@@ -65,13 +65,12 @@ __device__ __forceinline__ int fast9_score(const uint8_t* __restrict__ s, int th
     p[10] = cv - (unsigned)s[-2 * SIN_W - 2] * K; p[11] = cv - (unsigned)s[-1 * SIN_W - 3] * K;
     p[12] = cv - (unsigned)s[-3] * K;             p[13] = cv - (unsigned)s[1 * SIN_W - 3] * K;
     p[14] = cv - (unsigned)s[2 * SIN_W - 2] * K;  p[15] = cv - (unsigned)s[3 * SIN_W - 1] * K;
-    unsigned lo2[16], lo4[16], lo9[16];
+    // minima over the 16 arcs of 9: lo3[k] = min(p[k..k+2]), lo9[k] = min(lo3[k], lo3[k+3], lo3[k+6]); 3-input DPX ops
+    unsigned lo3[16], lo9[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) lo2[k] = __vmins2(p[k], p[(k + 1) & 15]);
+    for (int k = 0; k < 16; ++k) lo3[k] = __vimin3_s16x2(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) lo4[k] = __vmins2(lo2[k], lo2[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) lo9[k] = __vimin3_s16x2(lo4[k], lo4[(k + 4) & 15], p[(k + 8) & 15]);
+    for (int k = 0; k < 16; ++k) lo9[k] = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
     unsigned best = 0;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) best = __vimax3_s16x2(best, lo9[k], lo9[k + 1]);
@@ -88,8 +87,10 @@ __device__ __forceinline__ int fast9_score(const uint8_t* __restrict__ s, int th
 __device__ __forceinline__ void fast_pretest2(unsigned c2, unsigned down, unsigned right, unsigned up, unsigned left,
                                               unsigned t_hi, unsigned t_lo, bool& cand_lo, bool& cand_hi) {
     const unsigned d0 = c2 - down, d4 = c2 - right, d8 = c2 - up, d12 = c2 - left;   // lanes stay in 1..511: no borrow
-    const unsigned mn = __vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8), __vmaxs2(__vmins2(d8, d12), __vmins2(d12, d0)));
-    const unsigned mx = __vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmins2(__vmaxs2(d8, d12), __vmaxs2(d12, d0)));
+    // an adjacent compass pair is (0 or 8) with (4 or 12): "both beyond the threshold" for some adjacent pair
+    // <=> (d0 or d8 beyond) and (d4 or d12 beyond) <=> min(max(d0,d8), max(d4,d12)) >= t_hi, resp. max(min, min) <= t_lo
+    const unsigned mn = __vmins2(__vmaxs2(d0, d8), __vmaxs2(d4, d12));
+    const unsigned mx = __vmaxs2(__vmins2(d0, d8), __vmins2(d4, d12));
     bool ph, pl, qh, ql;
     (void)__vibmax_s16x2(mn, t_hi, &ph, &pl);    // pred = (mn >= t_hi) per lane
     (void)__vibmin_s16x2(mx, t_lo, &qh, &ql);    // pred = (mx <= t_lo) per lane
@@ -100,13 +101,22 @@ __device__ __forceinline__ void fast_pretest2(unsigned c2, unsigned down, unsign
 __device__ __forceinline__ unsigned widen_lo(unsigned w) { return __byte_perm(w, 0u, 0x4140); }   // bytes 0,1 -> 16-bit lanes
 __device__ __forceinline__ unsigned widen_hi(unsigned w) { return __byte_perm(w, 0u, 0x4342); }   // bytes 2,3 -> 16-bit lanes
 
+// a staged word that straddles the image border (or an unaligned image): byte loads with REFLECT_101; kept out of
+// line so that the common word path of border tiles stays lean
+__device__ __noinline__ uint32_t load_border_word(const uint8_t* __restrict__ row, int gx0, int W) {
+    return (uint32_t)__ldg(row + reflect1(gx0, W)) | ((uint32_t)__ldg(row + reflect1(gx0 + 1, W)) << 8) |
+           ((uint32_t)__ldg(row + reflect1(gx0 + 2, W)) << 16) | ((uint32_t)__ldg(row + reflect1(gx0 + 3, W)) << 24);
+}
+
 __global__ void __launch_bounds__(K1_THREADS)
 fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __restrict__ imgR,
                  size_t stride, size_t image_pitch, int pitch_out) {
     __shared__ __align__(16) uint32_t s_inw[SIN_H * SIN_WW];
     __shared__ __align__(16) float s_row[(TH + 6) * TW];
-    __shared__ __align__(16) uint32_t s_scw[SC_H * SIN_WW];       // scores of the candidates (tile + 1-px ring)
-    __shared__ __align__(16) uint32_t s_nmsw[TH * (TW / 4)];      // scores after NMS + border filter (tile only)
+    __shared__ __align__(16) uint32_t s_zero[SC_H * SIN_WW + TH * (TW / 4)];   // zero-initialised planes:
+    uint32_t* s_scw = s_zero;                                     //   scores of the candidates (tile + 1-px ring)
+    uint32_t* s_nmsw = s_zero + SC_H * SIN_WW;                    //   scores after NMS + border filter (tile only)
+    static_assert((SC_H * SIN_WW + TH * (TW / 4)) % 4 == 0 && (SC_H * SIN_WW) % 4 == 0, "uint4 zeroing / aligned planes");
     __shared__ uint16_t s_list[K1_NCAND];                         // pre-test survivors  (row * SIN_W + column)
     __shared__ uint16_t s_corner[K1_NCAND];                       // corners (score > 0)
     __shared__ int s_n[2];
@@ -135,18 +145,12 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
                 const int r = w / SIN_WW, cw = w - r * SIN_WW;
                 const int gy = reflect1(y0 - HALO + r, H), gx0 = x0 - HALO + 4 * cw;
                 const uint8_t* row = img + (size_t)gy * stride;
-                uint32_t v;
-                if (aligned && gx0 >= 0 && gx0 + 3 < W) {
-                    v = __ldg(reinterpret_cast<const uint32_t*>(row + gx0));
-                } else {
-                    v = (uint32_t)__ldg(row + reflect1(gx0, W)) | ((uint32_t)__ldg(row + reflect1(gx0 + 1, W)) << 8) |
-                        ((uint32_t)__ldg(row + reflect1(gx0 + 2, W)) << 16) | ((uint32_t)__ldg(row + reflect1(gx0 + 3, W)) << 24);
-                }
-                s_inw[w] = v;
+                s_inw[w] = (aligned && gx0 >= 0 && gx0 + 3 < W) ? __ldg(reinterpret_cast<const uint32_t*>(row + gx0))
+                                                                 : load_border_word(row, gx0, W);
             }
         }
-        for (int w = tid; w < SC_H * SIN_WW; w += K1_THREADS) s_scw[w] = 0;
-        for (int w = tid; w < TH * (TW / 4); w += K1_THREADS) s_nmsw[w] = 0;
+        for (int w = tid; w < (SC_H * SIN_WW + TH * (TW / 4)) / 4; w += K1_THREADS)
+            reinterpret_cast<uint4*>(s_zero)[w] = make_uint4(0, 0, 0, 0);
         if (tid < 2) s_n[tid] = 0;
     }
     __syncthreads();
@@ -181,6 +185,7 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
         // candidate columns: FAST is evaluated for 3 <= x < W-3, the tile needs x0-1 .. x0+TW
         const int cx_lo = max(3, x0 - 1) - (x0 - HALO), cx_hi = min(W - 3, x0 + TW + 1) - (x0 - HALO);   // staged columns [cx_lo, cx_hi)
         for (int i0 = 0; i0 < K1_ITEMS3; i0 += K1_THREADS) {
+            if (i0 + (tid & ~31) >= K1_ITEMS3) break;      // whole warp beyond the work items
             const int i = i0 + tid;
             bool c0 = false, c1 = false, c2 = false, c3 = false;
             int r = 0, cw = 0;
@@ -219,6 +224,7 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
     {
         const int nlist = s_n[0];
         for (int q0 = 0; q0 < nlist; q0 += K1_THREADS) {
+            if (q0 + (tid & ~31) >= nlist) break;          // whole warp beyond the list
             const int q = q0 + tid;
             int sc = 0, e = 0;
             if (q < nlist) {
