@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -586,9 +586,11 @@ def run_gpu(args):
         pairdist = B * (Nkp * Nkp + 2 * M * M)
         clocks = sampler.summary()
         int_roof = 1.0 / max(HM_POPC / pipe["popc_per_s"], HM_ALU / pipe["lop3_per_s"])
-        micro, _ = c5_microbench(ctx, torch, stream, torch.device("cuda", local), pipe, peak, reps=64, iters=5)
-        stage1 = stage1_microbench(ctx, torch, stream, torch.device("cuda", local), W, H, peak)
-        latency = single_pair_latency(capi, seqs, gc, W, H, nfeats, local)
+        micro = stage1 = latency = None
+        if not args.no_micro:
+            micro, _ = c5_microbench(ctx, torch, stream, torch.device("cuda", local), pipe, peak, reps=64, iters=5)
+            stage1 = stage1_microbench(ctx, torch, stream, torch.device("cuda", local), W, H, peak)
+            latency = single_pair_latency(capi, seqs, gc, W, H, nfeats, local)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -660,13 +662,14 @@ def main():
     os.dup2(2, 1)                    # libraries that print to stdout (NCCL banner) must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="stereo pairs (sequence slots) per step per GPU")
     ap.add_argument("--cpu-pairs", type=int, default=300, help="cpu_baseline: pairs per process")
     ap.add_argument("--ref-pairs", type=int, default=100, help="--impl reference: pairs per process per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-micro", action="store_true", help="skip the microbenches (match c5 + sweep, stage 1, single-pair latency)")
     ap.add_argument("--match-method", type=int, default=0, help="0 = smDescBF (headline), 1 = smDescRbR (row-by-row band matcher)")
     ap.add_argument("--if-match-method", type=int, default=0, help="0 = ifmDescBF (headline), 1 = ifmDescWin (windowed tracker)")
     ap.add_argument("--chunks", type=int, default=0, help="groups of slots on concurrent streams (0 = library default)")

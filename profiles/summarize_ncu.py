@@ -27,6 +27,11 @@ KEYS = [
 ]
 
 
+PIPELINE = ("fast_blur_kernel", "select_kernel", "brief_kernel", "hamming_pipeline_kernel", "lr_filter_kernel", "track_filter_kernel",
+            "ransac_prepare_kernel", "fundmat_kernel", "consistency_kernel", "gn_kernel", "begin_step_kernel", "scatter_cams_kernel",
+            "rbr_match_kernel", "win_track_kernel", "upload_meta_kernel")
+
+
 def launches(src, dst):
     rows = list(csv.DictReader(l for l in open(src) if l.startswith('"')))
     per = defaultdict(list)
@@ -46,6 +51,13 @@ def launches(src, dst):
         for k in sorted(per, key=lambda k: -sum(per[k])):
             v = per[k]
             f.write(f"| `{k}` | {len(v)} | {sum(v)/len(v):.1f} | {sum(v):.1f} | {sum(v)/total:.3f} |\n")
+        # the kernels of one pipeline step only (the microbenches of bench.py launch others)
+        step = [k for k in per if any(t in k for t in PIPELINE)]
+        tot2 = sum(sum(per[k]) for k in step) or 1.0
+        f.write("\n## pipeline kernels only (share of a step)\n\n| kernel | launches | mean us | share of step |\n|---|---:|---:|---:|\n")
+        for k in sorted(step, key=lambda k: -sum(per[k])):
+            v = per[k]
+            f.write(f"| `{k}` | {len(v)} | {sum(v)/len(v):.1f} | {sum(v)/tot2:.3f} |\n")
     print(open(dst).read())
 
 
