@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Parity soak on a GPU box: many seeded config-2 sequences, every frame compared with the CPU oracle (real OpenCV
+calls for FAST / ORB / BFMatcher / findFundamentalMat + the C++ restatement of the reference's glue).
+Test infrastructure, not product code.  usage: python tools/soak_parity.py [n_seeds] [n_frames] [config]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as orc          # noqa: E402
+from stereo_vo_b200 import capi, synth    # noqa: E402
+
+
+def main():
+    n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+    cfg = sys.argv[3] if len(sys.argv) > 3 else "c2"
+    W, H, nf = dict(c1=(320, 240, 100), c2=(640, 480, 500), c3=(1242, 375, 1000))[cfg]
+    ctx = capi.Context(width=W, height=H, orb_nfeats=nf, max_seqs=n_seeds, max_corners=32768 if cfg == "c3" else 16384)
+    seqs = [synth.make_sequence(cfg, seed=100 + s, n_frames=n_frames) for s in range(n_seeds)]
+    cam = seqs[0][1]
+    gc = capi.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    oc = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    ests = [orc.OracleEstimator(orc.Params(orb_nfeats=nf), backend="cv2", ransac="cv2") for _ in range(n_seeds)]
+    bad = 0
+    worst_rot = worst_t = 0.0
+    t0 = time.time()
+    dead = set()            # sequences whose oracle stopped (cv2.findFundamentalMat raises an internal assertion on some inputs)
+    n_cmp = 0
+    for t in range(n_frames):
+        res = ctx.process_batch([s[0][t][0] for s in seqs], [s[0][t][1] for s in seqs], [gc] * n_seeds)
+        for k in range(n_seeds):
+            if k in dead:
+                continue
+            try:
+                o = ests[k].process_new_image_pair(seqs[k][0][t][0], seqs[k][0][t][1], oc)
+            except Exception as e:          # noqa: BLE001
+                print(f"ORACLE FAILED seed {100 + k} frame {t}: {str(e).splitlines()[0][:120]}")
+                dead.add(k)
+                continue
+            n_cmp += 1
+            f = o["frame"]
+            kp = ctx.keypoints(k, 0, 0)
+            checks = {"keypoints": np.array_equal(kp["x"], f.kpsL["x"]) and np.array_equal(kp["y"], f.kpsL["y"]),
+                      "descriptors": np.array_equal(ctx.descriptors(k, 0, 1), f.descR)}
+            m = ctx.matches(k, 0)
+            checks["matches"] = np.array_equal(m["trainIdx"], f.matches["trainIdx"]) and np.array_equal(m["queryIdx"], f.matches["queryIdx"])
+            checks["status"] = res[k].error_code == o["error_code"] and bool(res[k].valid) == o["valid"]
+            if t > 0:
+                q, tl, tr, il, ir = ctx.track_candidates(k)
+                dbg = o["track_dbg"]
+                checks["greedy list"] = np.array_equal(q, dbg["matL"]["queryIdx"]) and np.array_equal(tl, dbg["matL"]["trainIdx"])
+                if dbg["inlL"] is not None:
+                    checks["mask L"] = np.array_equal(il, dbg["inlL"])
+                    checks["mask R"] = np.array_equal(ir, dbg["inlR"])
+                checks["tracked"] = np.array_equal(ctx.tracked_pairs(k), o["tracked"])
+                checks["iterations"] = (res[k].num_it, res[k].num_it_final) == (o["num_it"], o["num_it_final"])
+                if o["pose"] is not None:
+                    d = np.array(res[k].delta_pose[:]) - o["pose"]["delta"]
+                    worst_rot = max(worst_rot, float(np.abs(d[:3]).max()))
+                    worst_t = max(worst_t, float(np.abs(d[3:]).max()))
+                    checks["pose"] = bool(np.abs(d[:3]).max() < 1e-4 and np.abs(d[3:]).max() < 1e-3)
+            failed = [n for n, v in checks.items() if not v]
+            if failed:
+                bad += 1
+                extra = ""
+                if "mask L" in failed or "mask R" in failed:
+                    extra = f" (inliers L {int(il.sum())}/{int(np.sum(dbg['inlL']))} R {int(ir.sum())}/{int(np.sum(dbg['inlR']))} of {len(il)})"
+                print(f"MISMATCH seed {100 + k} frame {t}: {failed}{extra}")
+    print(f"soak {cfg}: {n_seeds} sequences x {n_frames} frames, {n_cmp} stereo pairs compared, {bad} mismatching frames, "
+          f"{len(dead)} sequences cut short by an OpenCV assertion in the oracle; "
+          f"max |d rot| = {worst_rot:.2e} rad, max |d t| = {worst_t:.2e} m; {time.time() - t0:.1f} s")
+    ctx.close()
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
