@@ -148,11 +148,13 @@ def run_reference(args):
         return
     seqs, cam = make_frames()
     procs = os.cpu_count() or 1
-    per = max(2, args.ref_pairs)
+    # warm-up doubles as a rate probe: the per-step sample is sized so that the whole run stays near one minute
+    rate, _ = cpu_throughput(seqs, cam, 4, procs)
+    budget_s = 60.0
+    per = int(budget_s * rate / max(1, args.steps) / procs)
+    per = max(2, min(args.ref_pairs, per))
     vals = []
     info = None
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_throughput(seqs, cam, 2, procs)
     t_all = time.perf_counter()
     for _ in range(args.steps):
         v, info = cpu_throughput(seqs, cam, per, procs)
