@@ -958,3 +958,29 @@ def test_stage1_odd_sizes_against_oracle(W, H):
             assert (oL == 0).sum() > 10          # the constant border was reached
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("n", [64, 101, 200])
+def test_concurrent_groups_give_identical_results(n):
+    """svo_set_concurrency: a step split into 1, 3, 4 or 8 groups of slots on concurrent streams must produce the same
+    results, bit for bit (the groups only share read-only data); n = 101 exercises uneven groups, slot lists are shuffled."""
+    seqs = [synth.make_sequence("c1", seed=40 + s, n_frames=3) for s in range(4)]
+    cam = seqs[0][1]
+    rng = np.random.default_rng(n)
+    slots = rng.permutation(n).tolist()
+    key = lambda r: (tuple(r.delta_pose), r.num_it, r.num_it_final, r.stereo_matches, r.tracked_feats_from_last_frame,
+                     r.detected_left, r.detected_right, r.error_code, r.valid)
+    outs = {}
+    for chunks in (1, 3, 4, 8):
+        ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=n)
+        try:
+            ctx.set_concurrency(chunks)
+            for t in range(3):
+                L = [seqs[i % 4][0][t][0] for i in range(n)]
+                R = [seqs[i % 4][0][t][1] for i in range(n)]
+                res = ctx.process_batch(L, R, [gcam(cam)] * n, slots=slots)
+            outs[chunks] = ([key(r) for r in res], mtuple(ctx.matches(slots[7], 0)).tobytes(), ctx.tracked_pairs(slots[-1]).tobytes())
+        finally:
+            ctx.close()
+    assert outs[1] == outs[3] == outs[4] == outs[8]
+    assert sum(k[-1] for k in outs[1][0]) == n               # every slot produced a valid pose
