@@ -137,7 +137,12 @@ SVO_HD2 int solve_cubic(const double* c, double* r) {
 }
 
 // run7Point: up to three candidate fundamental matrices (row-major 3x3 each) from 7 correspondences.
-SVO_HD2 int run_7point(const Pt2f* m1, const Pt2f* m2, double* F /* 27 */) {
+// ---- the 7-point solver in three steps (run_7point below chains them; the CUDA kernel runs the middle one
+//      cooperatively in a warp, see run_7point_warp in ransac.cu) -------------------------------------------------
+struct Fm7Norm { double m1cx, m1cy, m2cx, m2cy, scale1, scale2; };
+
+// Hartley normalisation of the 7 correspondences; false if the points coincide
+SVO_HD2 bool fm7_normalise(const Pt2f* m1, const Pt2f* m2, Fm7Norm& nm) {
     double m1cx = 0, m1cy = 0, m2cx = 0, m2cy = 0;
     for (int i = 0; i < 7; ++i) { m1cx += m1[i].x; m1cy += m1[i].y; m2cx += m2[i].x; m2cy += m2[i].y; }
     const double t = 1. / 7;
@@ -149,53 +154,26 @@ SVO_HD2 int run_7point(const Pt2f* m1, const Pt2f* m2, double* F /* 27 */) {
         scale2 += sqrt(bx * bx + by * by);
     }
     scale1 *= t; scale2 *= t;
-    if (scale1 < FLT_EPSILON || scale2 < FLT_EPSILON) return 0;
-    scale1 = sqrt(2.) / scale1;
-    scale2 = sqrt(2.) / scale2;
-    double a[7][9];
-    for (int i = 0; i < 7; ++i) {
-        const double x0 = (m1[i].x - m1cx) * scale1, y0 = (m1[i].y - m1cy) * scale1;
-        const double x1 = (m2[i].x - m2cx) * scale2, y1 = (m2[i].y - m2cy) * scale2;
-        a[i][0] = x1 * x0; a[i][1] = x1 * y0; a[i][2] = x1;
-        a[i][3] = y1 * x0; a[i][4] = y1 * y0; a[i][5] = y1;
-        a[i][6] = x0;      a[i][7] = y0;      a[i][8] = 1;
-    }
-    // null space of the 7x9 system: Gauss-Jordan with complete pivoting
-    int pivcol[7];
-    bool used[9];
-    for (int j = 0; j < 9; ++j) used[j] = false;
-    int rank = 0;
-    for (int r = 0; r < 7; ++r) {
-        int pr = -1, pc = -1;
-        double best = 0;
-        for (int i = r; i < 7; ++i)
-            for (int j = 0; j < 9; ++j)
-                if (!used[j] && fabs(a[i][j]) > best) { best = fabs(a[i][j]); pr = i; pc = j; }
-        if (pr < 0 || best < 1e-13) break;
-        if (pr != r) for (int j = 0; j < 9; ++j) { const double tmp = a[r][j]; a[r][j] = a[pr][j]; a[pr][j] = tmp; }
-        const double inv = 1. / a[r][pc];
-        for (int j = 0; j < 9; ++j) a[r][j] *= inv;
-        for (int i = 0; i < 7; ++i) {
-            if (i == r) continue;
-            const double f = a[i][pc];
-            if (f != 0) for (int j = 0; j < 9; ++j) a[i][j] -= f * a[r][j];
-        }
-        used[pc] = true;
-        pivcol[r] = pc;
-        ++rank;
-    }
-    // basis vectors of the null space for the two (or more) free columns; use the last two free columns
-    double f1[9], f2[9];
-    int freec[9], nfree = 0;
-    for (int j = 0; j < 9; ++j) if (!used[j]) freec[nfree++] = j;
-    if (nfree < 2) return 0;
-    for (int v = 0; v < 2; ++v) {
-        double* f = v == 0 ? f1 : f2;
-        const int fc = freec[v];
-        for (int j = 0; j < 9; ++j) f[j] = 0;
-        f[fc] = 1;
-        for (int r = 0; r < rank; ++r) f[pivcol[r]] = -a[r][fc];
-    }
+    if (scale1 < FLT_EPSILON || scale2 < FLT_EPSILON) return false;
+    nm.m1cx = m1cx; nm.m1cy = m1cy; nm.m2cx = m2cx; nm.m2cy = m2cy;
+    nm.scale1 = sqrt(2.) / scale1;
+    nm.scale2 = sqrt(2.) / scale2;
+    return true;
+}
+
+// entry (i, j) of the 7x9 system: rows [x1*x0, x1*y0, x1, y1*x0, y1*y0, y1, x0, y0, 1]
+SVO_HD2 double fm7_entry(const Pt2f* m1, const Pt2f* m2, const Fm7Norm& nm, int i, int j) {
+    const double x0 = (m1[i].x - nm.m1cx) * nm.scale1, y0 = (m1[i].y - nm.m1cy) * nm.scale1;
+    const double x1 = (m2[i].x - nm.m2cx) * nm.scale2, y1 = (m2[i].y - nm.m2cy) * nm.scale2;
+    const double p = j < 3 ? x1 : (j < 6 ? y1 : 1.0);
+    const int jj = j % 3;
+    const double q = jj == 0 ? x0 : (jj == 1 ? y0 : 1.0);
+    return (j < 6 && jj < 2) ? p * q : (j < 6 ? p : q);          // the products only where the reference form has them
+}
+
+// cubic in the pencil f1 + (1 - lambda) ... , roots -> up to 3 de-normalised F matrices.  f1, f2: null-space basis.
+SVO_HD2 int fm7_finish(double* f1, double* f2, const Fm7Norm& nm, double* F /* 27 */) {
+    const double m1cx = nm.m1cx, m1cy = nm.m1cy, m2cx = nm.m2cx, m2cy = nm.m2cy, scale1 = nm.scale1, scale2 = nm.scale2;
     // orthonormalise (the parametrisation below is basis independent; this only helps conditioning)
     double n1 = 0;
     for (int j = 0; j < 9; ++j) n1 += f1[j] * f1[j];
@@ -253,6 +231,51 @@ SVO_HD2 int run_7point(const Pt2f* m1, const Pt2f* m2, double* F /* 27 */) {
         if (fabs(fm[8]) > FLT_EPSILON) { const double inv = 1. / fm[8]; for (int i = 0; i < 9; ++i) fm[i] *= inv; }
     }
     return n;
+}
+
+SVO_HD2 int run_7point(const Pt2f* m1, const Pt2f* m2, double* F /* 27 */) {
+    Fm7Norm nm;
+    if (!fm7_normalise(m1, m2, nm)) return 0;
+    double a[7][9];
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 9; ++j) a[i][j] = fm7_entry(m1, m2, nm, i, j);
+    // null space of the 7x9 system: Gauss-Jordan with complete pivoting
+    int pivcol[7];
+    bool used[9];
+    for (int j = 0; j < 9; ++j) used[j] = false;
+    int rank = 0;
+    for (int r = 0; r < 7; ++r) {
+        int pr = -1, pc = -1;
+        double best = 0;
+        for (int i = r; i < 7; ++i)
+            for (int j = 0; j < 9; ++j)
+                if (!used[j] && fabs(a[i][j]) > best) { best = fabs(a[i][j]); pr = i; pc = j; }
+        if (pr < 0 || best < 1e-13) break;
+        if (pr != r) for (int j = 0; j < 9; ++j) { const double tmp = a[r][j]; a[r][j] = a[pr][j]; a[pr][j] = tmp; }
+        const double inv = 1. / a[r][pc];
+        for (int j = 0; j < 9; ++j) a[r][j] *= inv;
+        for (int i = 0; i < 7; ++i) {
+            if (i == r) continue;
+            const double f = a[i][pc];
+            if (f != 0) for (int j = 0; j < 9; ++j) a[i][j] -= f * a[r][j];
+        }
+        used[pc] = true;
+        pivcol[r] = pc;
+        ++rank;
+    }
+    // basis vectors of the null space for the two (or more) free columns; use the first two free columns
+    double f1[9], f2[9];
+    int freec[9], nfree = 0;
+    for (int j = 0; j < 9; ++j) if (!used[j]) freec[nfree++] = j;
+    if (nfree < 2) return 0;
+    for (int v = 0; v < 2; ++v) {
+        double* f = v == 0 ? f1 : f2;
+        const int fc = freec[v];
+        for (int j = 0; j < 9; ++j) f[j] = 0;
+        f[fc] = 1;
+        for (int r = 0; r < rank; ++r) f[pivcol[r]] = -a[r][fc];
+    }
+    return fm7_finish(f1, f2, nm, F);
 }
 
 // FMEstimatorCallback::computeError for one correspondence (float32 result)

@@ -57,6 +57,85 @@ ransac_prepare_kernel(Pools P, RansacScratch R) {
     }
 }
 
+
+// run_7point with the null-space step (Gauss-Jordan with complete pivoting on the 7x9 system) spread over the warp:
+// lane j < 9 owns column j in registers, the pivot search is a warp arg-max with the sequential scan's tie order
+// (largest |a|, then smallest row, then smallest column), row swaps / scaling / elimination touch each element with
+// exactly the operations of the sequential loop, so the models are bit-identical to run_7point's.  All 32 lanes must
+// call it; F and the return value are valid on lane 0.  (On one lane the dynamically indexed 7x9 array lives in local
+// memory and this step was more than half of fundmat_kernel's time.)
+__device__ int run_7point_warp(const Pt2f* m1, const Pt2f* m2, double* F /* 27, lane 0 */) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    Fm7Norm nm;
+    if (!fm7_normalise(m1, m2, nm)) return 0;          // same inputs on every lane: uniform
+    const bool colv = lane < 9;
+    double col[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) col[i] = colv ? fm7_entry(m1, m2, nm, i, lane) : 0.0;
+    bool used = !colv;                                 // lanes >= 9 never offer a pivot
+    int pivcol[7];
+    int rank = 0;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        // this column's best candidate among rows r..6 (strict '>' keeps the smallest row among equals)
+        double bv = 0;
+        int bi = -1;
+        if (!used) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                if (i < r) continue;
+                const double v = fabs(col[i]);
+                if (v > bv) { bv = v; bi = i; }
+            }
+        }
+        int bl = lane;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {              // arg-max over lanes 0..15: value, then smaller row, then smaller column
+            const double ov = __shfl_xor_sync(full, bv, o);
+            const int oi = __shfl_xor_sync(full, bi, o);
+            const int ol = __shfl_xor_sync(full, bl, o);
+            const bool take = oi >= 0 && (bi < 0 || ov > bv || (ov == bv && (oi < bi || (oi == bi && ol < bl))));
+            if (take) { bv = ov; bi = oi; bl = ol; }
+        }
+        const double best = __shfl_sync(full, bv, 0);
+        const int pr = __shfl_sync(full, bi, 0), pc = __shfl_sync(full, bl, 0);
+        if (pr < 0 || best < 1e-13) break;
+        if (pr != r) {                                 // swap rows r and pr (pr > r)
+            double tmp = col[r];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) if (i == pr) { col[r] = col[i]; col[i] = tmp; }
+        }
+        const double inv = 1. / __shfl_sync(full, col[r], pc);
+        col[r] *= inv;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            if (i == r) continue;
+            const double f = __shfl_sync(full, col[i], pc);
+            if (f != 0) col[i] -= f * col[r];
+        }
+        if (lane == pc) used = true;
+        pivcol[r] = pc;
+        ++rank;
+    }
+    // the first two free columns span the null-space basis: f[fc] = 1, f[pivcol[r]] = -a[r][fc]
+    const unsigned freem = __ballot_sync(full, !used);
+    if (__popc(freem) < 2) return 0;
+    const int fc0 = __ffs(freem) - 1, fc1 = __ffs(freem & (freem - 1)) - 1;
+    double e1 = lane == fc0 ? 1.0 : 0.0, e2 = lane == fc1 ? 1.0 : 0.0;      // this lane's entries of f1 / f2
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const double v1 = __shfl_sync(full, col[r], fc0), v2 = __shfl_sync(full, col[r], fc1);
+        if (r < rank && pivcol[r] == lane) { e1 = -v1; e2 = -v2; }
+    }
+    double f1[9], f2[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { f1[j] = __shfl_sync(full, e1, j); f2[j] = __shfl_sync(full, e2, j); }
+    int n = 0;
+    if (lane == 0) n = fm7_finish(f1, f2, nm, F);
+    return __shfl_sync(full, n, 0);
+}
+
 __global__ void __launch_bounds__(RS_THREADS)
 fundmat_kernel(RansacScratch R) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -114,7 +193,10 @@ fundmat_kernel(RansacScratch R) {
         __syncthreads();
         // ---- every warp: solve and score its sample -------------------------------------------------
         if (sh.found[wid] == 1) {
-            if (lane == 0) sh.nmodels[wid] = run_7point(sh.ms1[wid], sh.ms2[wid], sh.F[wid]);
+            {
+                const int nm7 = run_7point_warp(sh.ms1[wid], sh.ms2[wid], sh.F[wid]);
+                if (lane == 0) sh.nmodels[wid] = nm7;
+            }
             __syncwarp();
             const int nm = sh.nmodels[wid];
             for (int i = 0; i < nm; ++i) {
