@@ -270,6 +270,7 @@ __device__ void eval_rgn(const GnScratch& G, size_t base, int T, const Camera& c
         const float px3 = (float)(cam.fyr * Y1c / Z1c + cam.cyr);
         double J[4][6];
         bool good = true;
+        const double iz2 = 1.0 / (Z1c * Z1c);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             double X1cd, Y1cd, Z1cd;
@@ -286,10 +287,13 @@ __device__ void eval_rgn(const GnScratch& G, size_t base, int T, const Camera& c
             } else {
                 X1cd = (j == 3); Y1cd = (j == 4); Z1cd = (j == 5);
             }
-            J[0][j] = cam.fxl * (X1cd * Z1c - X1c * Z1cd) / (Z1c * Z1c);
-            J[1][j] = cam.fyl * (Y1cd * Z1c - Y1c * Z1cd) / (Z1c * Z1c);
-            J[2][j] = cam.fxr * (X1cd * Z1c - X2c * Z1cd) / (Z1c * Z1c);
-            J[3][j] = cam.fyr * (Y1cd * Z1c - Y1c * Z1cd) / (Z1c * Z1c);
+            // the reference divides each of the 24 entries by Z1c^2 (S5:251-254); one reciprocal and 24 products differ
+            // from that by at most 2 ulp per entry (observed pose differences vs the oracle stay below 1e-12), and
+            // FP64 division was 40 % of this kernel
+            J[0][j] = cam.fxl * (X1cd * Z1c - X1c * Z1cd) * iz2;
+            J[1][j] = cam.fyl * (Y1cd * Z1c - Y1c * Z1cd) * iz2;
+            J[2][j] = cam.fxr * (X1cd * Z1c - X2c * Z1cd) * iz2;
+            J[3][j] = cam.fyr * (Y1cd * Z1c - Y1c * Z1cd) * iz2;
             good = good && isfinite(J[0][j]) && isfinite(J[1][j]) && isfinite(J[2][j]) && isfinite(J[3][j]);
         }
         if (!good) continue;   // m_jacobian_is_good, S5:322
