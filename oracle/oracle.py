@@ -14,6 +14,9 @@ ifmDescBF configuration on the CPU:
 `ransac` selects how the two cv::findFundamentalMat masks of stage4_match_consecutive.cpp:202,237
 are obtained: "cv2" (real OpenCV), "off" (masks absent => filter skipped, as the reference does when
 fewer than 8 inliers are found, :243-259) or a callable (p1, p2) -> mask.
+
+Parity status: PARITY UNPINNED BY THE REFERENCE (it ships no vectors for this path and cannot be built in this
+image); pinned against the real OpenCV (cv2) goldens, libstdc++'s std::sort and SURVEY.md A.7's known answers instead.
 """
 import ctypes as C
 import os
