@@ -76,19 +76,42 @@ __device__ __forceinline__ HammingProblem pipeline_problem(const Pools& P, int m
     return h;
 }
 
-// inner loop over one staged train tile for NQ queries per thread (NQ is warp-uniform)
-template <int NQ>
+// 128-bit prefix of the distance (the first four words): a lower bound of the full distance, 3 POPC + 6 LOP3
+__device__ __forceinline__ uint32_t hamming128(const uint4& q, const uint4& t) {
+    const uint32_t w0 = q.x ^ t.x, w1 = q.y ^ t.y, w2 = q.z ^ t.z, w3 = q.w ^ t.w;
+    const uint32_t s1 = lop3_xor3(w0, w1, w2), c1 = lop3_maj3(w0, w1, w2);
+    return (uint32_t)__popc(c1) * 2u + (uint32_t)__popc(s1) + (uint32_t)__popc(w3);
+}
+
+// inner loop over one staged train tile for NQ queries per thread (NQ is warp-uniform).
+// PRUNE (pipeline only): every consumer of the pipeline's matches discards distances above orb_th (S3:164, S4:148),
+// so `best` starts at (orb_th + 1) << 16 and a pair is finished only when its 128-bit prefix distance is below the
+// best distance so far -- otherwise the full distance cannot win (train indices only grow, so an equal distance loses
+// the lowest-index tie-break too).  On ORB descriptors the prefix of a non-matching pair is below 41 in 0.4 % of the
+// pairs: the second half of the distance is computed for a few percent of the warp-instructions.
+template <int NQ, bool PRUNE>
 __device__ __forceinline__ void hamming_tile(const uint4* __restrict__ s_t, int rows, int t0, const uint4* qa, const uint4* qb,
                                              uint32_t* best) {
 #pragma unroll 4
     for (int j = 0; j < rows; ++j) {
         const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
 #pragma unroll
-        for (int r = 0; r < NQ; ++r) best[r] = min(best[r], hamming256_packed(qa[r], qb[r], ta, tb, (uint32_t)(t0 + j)));
+        for (int r = 0; r < NQ; ++r) {
+            if (PRUNE) {
+                const uint32_t d1 = hamming128(qa[r], ta);
+                if (d1 < (best[r] >> 16)) {
+                    const uint32_t d = d1 + hamming128(qb[r], tb);
+                    best[r] = min(best[r], (d << 16) | (uint32_t)(t0 + j));
+                }
+            } else {
+                best[r] = min(best[r], hamming256_packed(qa[r], qb[r], ta, tb, (uint32_t)(t0 + j)));
+            }
+        }
     }
 }
 
-__device__ __forceinline__ void hamming_body(const HammingProblem& h, uint4* s_t) {
+template <bool PRUNE>
+__device__ __forceinline__ void hamming_body(const HammingProblem& h, uint4* s_t, uint32_t best_init) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q0 = blockIdx.x * (HM_THREADS * HM_QPT);
     if (q0 >= h.nq) return;
@@ -101,7 +124,7 @@ __device__ __forceinline__ void hamming_body(const HammingProblem& h, uint4* s_t
 #pragma unroll
     for (int r = 0; r < HM_QPT; ++r) {
         const int qi = wq0 + r * 32 + lane;
-        best[r] = 0xFFFFFFFFu;
+        best[r] = best_init;
         if (wq0 + r * 32 < h.nq) nq_w = r + 1;
         if (qi < h.nq) { qa[r] = h.q[2 * (size_t)qi]; qb[r] = h.q[2 * (size_t)qi + 1]; }
         else { qa[r] = make_uint4(0, 0, 0, 0); qb[r] = qa[r]; }
@@ -111,8 +134,8 @@ __device__ __forceinline__ void hamming_body(const HammingProblem& h, uint4* s_t
         __syncthreads();
         for (int i = tid; i < rows * 2; i += HM_THREADS) s_t[i] = h.t[2 * (size_t)t0 + i];
         __syncthreads();
-        if (nq_w == HM_QPT) hamming_tile<HM_QPT>(s_t, rows, t0, qa, qb, best);
-        else if (nq_w == 1) hamming_tile<1>(s_t, rows, t0, qa, qb, best);
+        if (nq_w == HM_QPT) hamming_tile<HM_QPT, PRUNE>(s_t, rows, t0, qa, qb, best);
+        else if (nq_w == 1) hamming_tile<1, PRUNE>(s_t, rows, t0, qa, qb, best);
     }
 #pragma unroll
     for (int r = 0; r < HM_QPT; ++r) {
@@ -126,7 +149,9 @@ hamming_pipeline_kernel(Pools P, int mode_base, int n_modes) {
     __shared__ uint4 s_t[HM_TILE * 2];
     const int item = blockIdx.y / n_modes, mode = mode_base + blockIdx.y % n_modes;
     const HammingProblem h = pipeline_problem(P, mode, item);
-    hamming_body(h, s_t);
+    // distances above orb_th are dropped by lr_filter_kernel / track_filter_kernel: (orb_th + 1, index 0) stands for them
+    const uint32_t cut = (uint32_t)min(max(P.p.orb_th, 0) + 1, 0x7FFF);
+    hamming_body<true>(h, s_t, cut << 16);
 }
 
 __global__ void __launch_bounds__(HM_THREADS)
@@ -137,7 +162,7 @@ hamming_raw_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict_
     h.t = t + (size_t)blockIdx.y * nt * 2;
     h.out = out + (size_t)blockIdx.y * nq;
     h.nq = nq; h.nt = nt;
-    hamming_body(h, s_t);
+    hamming_body<false>(h, s_t, 0xFFFFFFFFu);
 }
 
 // ------------------------------------------------------------------------------------------------
