@@ -207,6 +207,53 @@ def test_match_lr_robust_1to1():
         ctx.close()
 
 
+@pytest.mark.parametrize("robust", [0, 1])
+def test_match_lr_prefix_pruning_adversarial(robust):
+    """The pipeline's Hamming kernels finish a distance only if its 128-bit prefix beats the best so far (best starts at
+    orb_th + 1).  Crafted descriptors: differences only in the second half (prefix distance 0 everywhere), only in the
+    first half, distances of exactly orb_th and orb_th + 1, exact duplicates (lowest index must win), several left
+    descriptors claiming one right descriptor."""
+    rng = np.random.default_rng(5)
+    th, n = 40, 192
+    base = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+
+    def flip(d, bits):                       # flip the given bit positions (0..255) of one descriptor
+        d = d.copy()
+        for b in bits:
+            d[b >> 3] ^= np.uint8(1 << (b & 7))
+        return d
+    dL = base.copy()
+    dR = np.zeros_like(base)
+    for i in range(n):
+        k = i % 8
+        if k == 0:   dR[i] = flip(base[i], rng.choice(np.arange(128, 256), th, replace=False))        # d = th, all in the 2nd half
+        elif k == 1: dR[i] = flip(base[i], rng.choice(np.arange(128, 256), th + 1, replace=False))    # d = th + 1: must be dropped
+        elif k == 2: dR[i] = flip(base[i], rng.choice(np.arange(0, 128), th, replace=False))          # d = th, all in the 1st half
+        elif k == 3: dR[i] = flip(base[i], rng.choice(np.arange(0, 128), th + 1, replace=False))
+        elif k == 4: dR[i] = base[i]                                                                  # exact copy
+        elif k == 5: dR[i] = dR[i - 1]                                                                # duplicate of the copy: index i-1 wins for both
+        elif k == 6: dR[i] = flip(base[i], rng.choice(256, 10, replace=False))
+        else:        dR[i] = rng.integers(0, 256, 32, dtype=np.uint8)                                 # unrelated
+    dL[5::8] = dL[4::8]                      # two left descriptors claim the same right one (robust 1-to-1 path)
+    kL = np.zeros(n, capi.KEYPOINT)
+    kR = np.zeros(n, capi.KEYPOINT)
+    for k in (kL, kR):
+        k["size"], k["angle"], k["class_id"], k["response"] = 7, -1, -1, 30
+    kL["y"] = kR["y"] = 40 + np.arange(n) // 2          # sorted rows, inside the image
+    kL["x"] = 150 + (np.arange(n) % 2) * 40
+    kR["x"] = kL["x"] - 7                                # disparity 7
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, enable_robust_1to1_match=robust, max_y_diff=300.0,
+                       orb_threshold=th)
+    try:
+        got = ctx.match_lr(kL, dL, kR, dR)
+        ref = orc.lr_filter(orc.bf_match(dL, dR), kL, kR, bool(robust), 300.0, th, 320)
+        assert np.array_equal(mtuple(got), mtuple(ref))
+        d = dict(zip(got["queryIdx"].tolist(), got["distance"].tolist()))
+        assert d.get(0) == th and 1 not in d and d.get(2) == th and 3 not in d and d.get(4) == 0
+    finally:
+        ctx.close()
+
+
 # ------------------------------------------------------------------------------------ F-matrix RANSAC
 def _two_views(rng, n, outl, integer=True):
     X = np.stack([rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(3, 12, n)], 1)
