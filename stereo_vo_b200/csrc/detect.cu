@@ -445,10 +445,13 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
 
     if (P.p.nms) {
         // ---- B. sort by response, descending (KeypointResponseSorter) ------------------------------
-        if (P.p.sort_mode == 0) introsort_block(KeyComp<true, 24>(), s_a, n, s_listA, s_listB, s_listS, s_cnt2, tmp, s_pos);
+        const unsigned cell = (unsigned)(P.p.min_distance / 2.0);     // S2:331
+        // with 1-px cells the selection is the first `quota` entries of the sorted order (see C below): only that prefix
+        // of std::sort's result is computed; the greedy grid walks further down the list and needs all of it
+        const int keep = cell == 1 ? min(n, P.p.quota) : n;
+        if (P.p.sort_mode == 0) introsort_block(KeyComp<true, 24>(), s_a, n, s_listA, s_listB, s_listS, s_cnt2, tmp, s_pos, keep);
         else block_stable_sort<true, 24>(s_a, tmp, n);
         // ---- C. greedy occupancy grid ---------------------------------------------------------------
-        const unsigned cell = (unsigned)(P.p.min_distance / 2.0);     // S2:331
         if (cell == 1) {
             // FAST's strict 3x3 NMS leaves no two corners in 8-adjacent pixels, and with 1-px cells a
             // corner only blocks its own pixel and the 4 neighbours: nothing is ever rejected.
@@ -490,7 +493,7 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
         s_b[k] = (pos & 0xFFFF0000u) | (uint32_t)k;   // y << 16 | position in the selection order
     }
     __syncthreads();
-    if (P.p.sort_mode == 0) introsort_block(KeyComp<false, 16>(), s_b, n_sel, s_listA, s_listB, s_listS, s_cnt2, tmp, s_pos);
+    if (P.p.sort_mode == 0) introsort_block(KeyComp<false, 16>(), s_b, n_sel, s_listA, s_listB, s_listS, s_cnt2, tmp, s_pos, n_sel);
     else block_stable_sort<false, 16>(s_b, tmp, n_sel);
     // ---- E. emit ------------------------------------------------------------------------------------
     for (int i = tid; i < n_sel; i += K2_THREADS) {

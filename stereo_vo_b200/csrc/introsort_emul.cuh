@@ -149,11 +149,16 @@ SVO_HD void insertion_sort_(const C& c, uint32_t* a, int first, int last) {
 
 // std::__introsort_loop on a[first..last) with the given remaining depth, one thread: explicit stack of
 // (first, last, depth) replacing the recursion on the right part.  Leaves segments of <= 16 elements unsorted.
+// `keep`: only the final positions [0, keep) are wanted (top-K selection).  A segment that starts at or beyond `keep`
+// can be left unsorted: partitions never move an element across a segment boundary again, and the final insertion sort
+// cannot either (everything right of a boundary is not smaller than everything left of it), so the first `keep`
+// positions end up exactly as in the full sort.
 template <class C>
-SVO_HD void introsort_loop_seq(const C& c, uint32_t* a, int first0, int last0, int depth0) {
+SVO_HD void introsort_loop_seq(const C& c, uint32_t* a, int first0, int last0, int depth0, int keep = 0x7FFFFFFF) {
     int st_first[64], st_last[64], st_depth[64];
     int sp = 1;
     st_first[0] = first0; st_last[0] = last0; st_depth[0] = depth0;
+    if (first0 >= keep) return;
     while (sp > 0) {
         --sp;
         int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
@@ -166,9 +171,8 @@ SVO_HD void introsort_loop_seq(const C& c, uint32_t* a, int first0, int last0, i
             const int mid = first + (last - first) / 2;
             median_to_first_(c, a, first, first + 1, mid, last - 1);
             const int cut = unguarded_partition_(c, a, first + 1, last, a[first]);
-            // recurse on [cut, last), continue with [first, cut)
-            st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth;
-            ++sp;
+            // recurse on [cut, last) (unless it lies beyond the wanted prefix), continue with [first, cut)
+            if (cut < keep) { st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth; ++sp; }
             last = cut;
         }
     }
@@ -180,6 +184,16 @@ SVO_HD void introsort_seq_c(const C& c, uint32_t* a, int n) {
     if (n <= 1) return;
     introsort_loop_seq(c, a, 0, n, 2 * floor_log2(n));
     insertion_sort_(c, a, 0, n);
+}
+
+// The first `keep` positions of std::sort's result (the rest of the array is left in an unspecified order).
+template <class C>
+SVO_HD void introsort_prefix_seq_c(const C& c, uint32_t* a, int n, int keep) {
+    if (n <= 1) return;
+    introsort_loop_seq(c, a, 0, n, 2 * floor_log2(n), keep);
+    // final insertion sort restricted to the leaves that reach into the prefix: an element moves at most 15 places
+    const int lim = keep < n - kSortThreshold ? keep + kSortThreshold : n;
+    insertion_sort_(c, a, 0, lim);
 }
 
 // Rank-table formulation of the unguarded Hoare partition of a[first..last) around the pivot at a[first]
@@ -388,8 +402,9 @@ __device__ int block_unguarded_partition(const C& c, uint32_t* a, int first, int
 }
 
 // children of a partition: short ones go to the per-thread list, the others to the next level
-__device__ __forceinline__ void push_segment(int first, int last, int depth, uint2* out, int* cnt_out, uint2* small, int* cnt_small) {
-    if (last - first <= kSortThreshold) return;
+__device__ __forceinline__ void push_segment(int first, int last, int depth, uint2* out, int* cnt_out, uint2* small, int* cnt_small,
+                                             int keep) {
+    if (last - first <= kSortThreshold || first >= keep) return;     // beyond the wanted prefix: see introsort_loop_seq
     const uint2 e = make_uint2((unsigned)first, (unsigned)last | ((unsigned)depth << 24));
     if (last - first <= kThreadSegMax) small[atomicAdd(cnt_small, 1)] = e;
     else out[atomicAdd(cnt_out, 1)] = e;
@@ -397,13 +412,14 @@ __device__ __forceinline__ void push_segment(int first, int last, int depth, uin
 
 // Sort a[0..n) (shared memory) with all threads of the block.  listA/listB/listS: room for n/16 + 2 entries each,
 // s_cnt: 3 ints (shared), tmp: n words of scratch (global or shared), s_pos: 64 ints per warp.
+// keep: only positions [0, keep) of the result are needed (pass n for a full sort); the rest of a[] is left unspecified.
 template <class C>
 __device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, uint2* listB, uint2* listS, int* s_cnt, uint32_t* tmp,
-                                int* s_pos /* 64 ints per warp, shared */) {
+                                int* s_pos /* 64 ints per warp, shared */, int keep) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     if (tid == 0) {
         s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
-        push_segment(0, n, 2 * floor_log2(max(n, 1)), listA, &s_cnt[0], listS, &s_cnt[2]);
+        push_segment(0, n, 2 * floor_log2(max(n, 1)), listA, &s_cnt[0], listS, &s_cnt[2], keep);
     }
     __syncthreads();
     int cur = 0;
@@ -425,8 +441,8 @@ __device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, ui
                 uint16_t* pos16 = reinterpret_cast<uint16_t*>(tmp);
                 const int cut = block_unguarded_partition(c, a, first, last, pos16, pos16 + n, s_pos);
                 if (tid == 0) {
-                    push_segment(cut, last, depth - 1, out, &s_cnt[cur ^ 1], listS, &s_cnt[2]);
-                    push_segment(first, cut, depth - 1, out, &s_cnt[cur ^ 1], listS, &s_cnt[2]);
+                    push_segment(cut, last, depth - 1, out, &s_cnt[cur ^ 1], listS, &s_cnt[2], keep);
+                    push_segment(first, cut, depth - 1, out, &s_cnt[cur ^ 1], listS, &s_cnt[2], keep);
                 }
             }
         }
@@ -449,8 +465,8 @@ __device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, ui
             __syncwarp();
             const int cut = warp_unguarded_partition(c, a, first, last, s_pos + 64 * warp);
             if (lane == 0) {
-                push_segment(cut, last, depth, out, &s_cnt[cur ^ 1], listS, &s_cnt[2]);
-                push_segment(first, cut, depth, out, &s_cnt[cur ^ 1], listS, &s_cnt[2]);
+                push_segment(cut, last, depth, out, &s_cnt[cur ^ 1], listS, &s_cnt[2], keep);
+                push_segment(first, cut, depth, out, &s_cnt[cur ^ 1], listS, &s_cnt[2], keep);
             }
         }
         __syncthreads();
@@ -467,8 +483,9 @@ __device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, ui
         }
         __syncthreads();
     }
-    // final insertion sort == stable placement inside the <= 16-element leaves
-    for (int i = tid; i < n; i += blockDim.x) {
+    // final insertion sort == stable placement inside the <= 16-element leaves (those that reach into the prefix)
+    const int lim = keep < n - kSortThreshold ? keep + kSortThreshold : n;
+    for (int i = tid; i < lim; i += blockDim.x) {
         const uint32_t v = a[i];
         int pos = i;
         const int lo = max(0, i - (kSortThreshold - 1)), hi = min(n - 1, i + (kSortThreshold - 1));
@@ -477,7 +494,7 @@ __device__ void introsort_block(const C& c, uint32_t* a, int n, uint2* listA, ui
         tmp[pos] = v;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) a[i] = tmp[i];
+    for (int i = tid; i < min(lim, keep); i += blockDim.x) a[i] = tmp[i];
     __syncthreads();
 }
 #endif  // __CUDACC__

@@ -31,6 +31,18 @@ static void check(const std::vector<uint32_t>& keys, const char* what) {
         ++g_fail;
         return;
     }
+    // top-K variant: the first `keep` positions must equal the full sort's for every keep
+    for (int keep : {1, 7, 16, 17, n / 3, n / 2, n - 1, n}) {
+        if (keep < 1 || keep > n) continue;
+        std::vector<uint32_t> w3(n);
+        for (int i = 0; i < n; ++i) w3[i] = (keys[i] << Shift) | (uint32_t)i;
+        svo::introsort_prefix_seq_c(svo::KeyComp<Desc, Shift>(), w3.data(), n, keep);
+        if (!std::equal(w3.begin(), w3.begin() + keep, w.begin())) {
+            if (g_fail < 5) std::printf("MISMATCH (prefix %d) %s n=%d\n", keep, what, n);
+            ++g_fail;
+            return;
+        }
+    }
     ++g_cases;
     for (int i = 0; i < n; ++i)
         if ((w[i] & ((1u << Shift) - 1)) != idx[i]) {
