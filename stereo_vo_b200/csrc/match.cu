@@ -279,44 +279,86 @@ lr_filter_kernel(Pools P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K7  track_filter_kernel: one warp per slot; the filter is order dependent (a pair only claims its
-// train indices if it is itself kept), so lane 0 walks the list while the warp stages the inputs.
+// K7  track_filter_kernel: one CTA per slot.  S4:145-160: pair k is erased if one of its two distances exceeds the
+// threshold or if its left or right train index was already claimed by an EARLIER pair that was itself kept.  The
+// reference walks the list sequentially; here the same fixed point is reached in parallel rounds:
+//   minL[v] / minR[v] = earliest pair not (yet) rejected among those whose left / right train index is v;
+//   a pair that is the earliest in both of its chains is KEPT (everything before it in those chains is rejected for
+//   good, so at its turn the sequential walk finds both indices unclaimed); a pair whose chain head is an earlier KEPT
+//   pair is REJECTED.  The smallest undecided pair is always decided, so the rounds end; real lists need 2-3 rounds
+//   (collisions are rare).  After kTfMaxRounds a single thread finishes the undecided rest sequentially.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+constexpr int kTfMaxRounds = 12;
+enum : uint8_t { TF_UNDECIDED = 0, TF_KEPT = 1, TF_REJECTED = 2 };
+
+__global__ void __launch_bounds__(FT)
 track_filter_kernel(Pools P) {
-    extern __shared__ uint32_t s_mem[];   // [2*cap] packed best + [2*ceil(cap/32)] bitmaps
+    extern __shared__ uint32_t s_mem[];   // [cap] packed (trainL << 16 | trainR) | [cap] minL | [cap] minR | [cap] states (bytes)
+    __shared__ int s_warp[FT / 32];
+    __shared__ int s_undecided;
     const int slot = P.slots[blockIdx.x];
     const SlotState& st = P.state[slot];
     const int cur = st.cur, prev = cur ^ 1;
     const int cap = P.p.kp_cap;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x;
     const int Mp = st.has_prev ? P.n_match[pair_idx(slot, prev)] : 0;
     const int Mc = P.n_match[pair_idx(slot, cur)];
     const int n_in = (Mc > 0) ? Mp : 0;
-    uint32_t* s_l = s_mem;
-    uint32_t* s_r = s_mem + cap;
-    uint32_t* bmL = s_mem + 2 * cap;
-    const int bw = (cap + 31) / 32;
-    uint32_t* bmR = bmL + bw;
+    uint32_t* s_ab = s_mem;
+    uint32_t* minL = s_mem + cap;
+    uint32_t* minR = s_mem + 2 * cap;
+    uint8_t* state = reinterpret_cast<uint8_t*>(s_mem + 3 * cap);
     const uint32_t* __restrict__ bl = P.tr_best + ((size_t)slot * 2 + 0) * cap;
     const uint32_t* __restrict__ br = P.tr_best + ((size_t)slot * 2 + 1) * cap;
-    for (int i = lane; i < n_in; i += 32) { s_l[i] = bl[i]; s_r[i] = br[i]; }
-    for (int i = lane; i < 2 * bw; i += 32) bmL[i] = 0;
-    __syncwarp();
-    int4* __restrict__ out = P.tcand + (size_t)slot * cap;
-    if (lane == 0) {
-        int m = 0;
-        const uint32_t th = (uint32_t)P.p.orb_th;
+    const uint32_t th = (uint32_t)P.p.orb_th;
+    for (int k = tid; k < n_in; k += FT) {
+        const uint32_t a = bl[k], b = br[k];
+        s_ab[k] = (a << 16) | (b & 0xFFFFu);
+        state[k] = ((a >> 16) > th || (b >> 16) > th) ? TF_REJECTED : TF_UNDECIDED;
+    }
+    __syncthreads();
+    for (int round = 0; round < kTfMaxRounds; ++round) {
+        for (int v = tid; v < Mc; v += FT) { minL[v] = 0xFFFFFFFFu; minR[v] = 0xFFFFFFFFu; }
+        if (tid == 0) s_undecided = 0;
+        __syncthreads();
+        for (int k = tid; k < n_in; k += FT)
+            if (state[k] != TF_REJECTED) { atomicMin(&minL[s_ab[k] >> 16], (uint32_t)k); atomicMin(&minR[s_ab[k] & 0xFFFFu], (uint32_t)k); }
+        __syncthreads();
+        for (int k = tid; k < n_in; k += FT)
+            if (state[k] == TF_UNDECIDED && minL[s_ab[k] >> 16] == (uint32_t)k && minR[s_ab[k] & 0xFFFFu] == (uint32_t)k) state[k] = TF_KEPT;
+        __syncthreads();
+        for (int k = tid; k < n_in; k += FT)
+            if (state[k] == TF_UNDECIDED) {
+                const uint32_t hl = minL[s_ab[k] >> 16], hr = minR[s_ab[k] & 0xFFFFu];     // chain heads, <= k
+                if ((hl < (uint32_t)k && state[hl] == TF_KEPT) || (hr < (uint32_t)k && state[hr] == TF_KEPT)) state[k] = TF_REJECTED;
+                else s_undecided = 1;
+            }
+        __syncthreads();
+        const int undecided = s_undecided;
+        __syncthreads();                       // thread 0 clears the flag at the top of the next round
+        if (!undecided) break;
+    }
+    if (s_undecided && tid == 0) {            // pathological collision chains: finish sequentially (decided states are final)
+        for (int v = 0; v < Mc; ++v) { minL[v] = 0; minR[v] = 0; }      // reused as "claimed" flags
         for (int k = 0; k < n_in; ++k) {
-            const uint32_t a = s_l[k], b = s_r[k];
-            const uint32_t tl = a & 0xFFFFu, tr = b & 0xFFFFu;
-            if ((a >> 16) > th || (b >> 16) > th) continue;
-            if (((bmL[tl >> 5] >> (tl & 31)) & 1u) || ((bmR[tr >> 5] >> (tr & 31)) & 1u)) continue;
-            bmL[tl >> 5] |= 1u << (tl & 31);
-            bmR[tr >> 5] |= 1u << (tr & 31);
-            out[m++] = make_int4(k, (int)tl, (int)tr, 0);
+            const uint32_t tl = s_ab[k] >> 16, tr = s_ab[k] & 0xFFFFu;
+            if (state[k] == TF_UNDECIDED) state[k] = (minL[tl] || minR[tr]) ? TF_REJECTED : TF_KEPT;
+            if (state[k] == TF_KEPT) { minL[tl] = 1; minR[tr] = 1; }
         }
-        P.n_tcand[slot] = m;
+    }
+    __syncthreads();
+    int4* __restrict__ out = P.tcand + (size_t)slot * cap;
+    int base = 0;
+    for (int k0 = 0; k0 < n_in; k0 += FT) {
+        const int k = k0 + tid;
+        const int keep = (k < n_in && state[k] == TF_KEPT) ? 1 : 0;
+        int total;
+        const int off = scan256(keep, s_warp, total);
+        if (keep) out[base + off] = make_int4(k, (int)(s_ab[k] >> 16), (int)(s_ab[k] & 0xFFFFu), 0);
+        base += total;
+    }
+    if (tid == 0) {
+        P.n_tcand[slot] = base;
         // masks default to "not computed": zero inliers => filter skipped (S4:243-259)
         P.n_inl[slot * 2 + 0] = 0;
         P.n_inl[slot * 2 + 1] = 0;
@@ -624,6 +666,7 @@ consistency_kernel(Pools P) {
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
+static int tf_smem(const Params& p) { return 3 * p.kp_cap * (int)sizeof(uint32_t) + ((p.kp_cap + 3) & ~3); }
 static int rbr_smem(const Params& p) { return (2 * p.H + 2 * p.kp_cap) * (int)sizeof(uint32_t); }
 static int win_smem(const Params& p) { return (2 * (p.H + 1) + p.kp_cap) * (int)sizeof(uint32_t); }
 
@@ -655,8 +698,7 @@ cudaError_t launch_track_match(const Pools& P, int n, cudaStream_t st, int* laun
     dim3 g((P.p.kp_cap + per - 1) / per, 2 * n);
     hamming_pipeline_kernel<<<g, HM_THREADS, 0, st>>>(P, 1, 2);
     if (tm) tm->mark(st);
-    const int bw = (P.p.kp_cap + 31) / 32;
-    track_filter_kernel<<<n, 32, (2 * P.p.kp_cap + 2 * bw) * sizeof(uint32_t), st>>>(P);
+    track_filter_kernel<<<n, FT, tf_smem(P.p), st>>>(P);
     if (tm) tm->mark(st);
     if (launches) *launches += 2;
     return cudaGetLastError();
@@ -680,8 +722,7 @@ cudaError_t launch_hamming_raw(const uint8_t* d_q, int nq, const uint8_t* d_t, i
 }
 
 cudaError_t configure_match(const Params& p) {
-    cudaError_t e = cudaFuncSetAttribute(track_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((2 * p.kp_cap + 2 * ((p.kp_cap + 31) / 32)) * sizeof(uint32_t)));
+    cudaError_t e = cudaFuncSetAttribute(track_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tf_smem(p));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lr_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * sizeof(uint32_t)));
     if (e != cudaSuccess) return e;
