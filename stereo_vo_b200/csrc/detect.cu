@@ -10,6 +10,10 @@
 // filter of ORB::compute is applied before the selection, so the results are identical.
 #include "detect.cuh"
 #include "introsort_emul.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cstdlib>
+#include <cstring>
 
 namespace svo {
 
@@ -28,8 +32,13 @@ namespace svo {
 //   4  blur column pass + stores, 4 pixels per work item
 // ------------------------------------------------------------------------------------------------
 constexpr int TW = 64, TH = 32, HALO = 4;
-constexpr int SIN_W = TW + 2 * HALO;   // 72 bytes per staged row
-constexpr int SIN_WW = SIN_W / 4;      // 18 words
+constexpr int SIN_W = TW + 2 * HALO;   // 72 bytes per staged row ...
+constexpr int SIN_WW = SIN_W / 4;      // ... = 18 words
+// TMA wants the box to start at a multiple of 16 bytes in x and to be a multiple of 16 bytes wide: the staged box begins
+// SIN_XOFF = 12 columns left of the halo (x0 - 16) and is 96 bytes wide; logical column c lives at byte SIN_XOFF + c.
+constexpr int SIN_P = 96;              // row pitch of the staged tile and of the score plane in bytes
+constexpr int SIN_PW = SIN_P / 4;      // 24 words
+constexpr int SIN_XOFF = 12;           // bytes; a multiple of 4, so staged words stay aligned
 constexpr int SIN_H = TH + 2 * HALO;   // 40
 constexpr int SC_H = TH + 2;           // score rows: tile rows -1 .. TH (row r <-> tile row r-1); columns as in s_in
 constexpr int K1_THREADS = 256;
@@ -57,14 +66,14 @@ __device__ __forceinline__ int fast9_score(const uint8_t* __restrict__ s, int th
     constexpr unsigned K = 0xFFFF0001u;                      // 1 - 65536
     const unsigned cv = (unsigned)s[0] * K + 0x01000100u;    // {256 + v, 256 - v}
     unsigned p[16];
-    p[0] = cv - (unsigned)s[3 * SIN_W + 0] * K;   p[1] = cv - (unsigned)s[3 * SIN_W + 1] * K;
-    p[2] = cv - (unsigned)s[2 * SIN_W + 2] * K;   p[3] = cv - (unsigned)s[1 * SIN_W + 3] * K;
-    p[4] = cv - (unsigned)s[3] * K;               p[5] = cv - (unsigned)s[-1 * SIN_W + 3] * K;
-    p[6] = cv - (unsigned)s[-2 * SIN_W + 2] * K;  p[7] = cv - (unsigned)s[-3 * SIN_W + 1] * K;
-    p[8] = cv - (unsigned)s[-3 * SIN_W + 0] * K;  p[9] = cv - (unsigned)s[-3 * SIN_W - 1] * K;
-    p[10] = cv - (unsigned)s[-2 * SIN_W - 2] * K; p[11] = cv - (unsigned)s[-1 * SIN_W - 3] * K;
-    p[12] = cv - (unsigned)s[-3] * K;             p[13] = cv - (unsigned)s[1 * SIN_W - 3] * K;
-    p[14] = cv - (unsigned)s[2 * SIN_W - 2] * K;  p[15] = cv - (unsigned)s[3 * SIN_W - 1] * K;
+    p[0] = cv - (unsigned)s[3 * SIN_P + 0] * K;   p[1] = cv - (unsigned)s[3 * SIN_P + 1] * K;
+    p[2] = cv - (unsigned)s[2 * SIN_P + 2] * K;   p[3] = cv - (unsigned)s[1 * SIN_P + 3] * K;
+    p[4] = cv - (unsigned)s[3] * K;               p[5] = cv - (unsigned)s[-1 * SIN_P + 3] * K;
+    p[6] = cv - (unsigned)s[-2 * SIN_P + 2] * K;  p[7] = cv - (unsigned)s[-3 * SIN_P + 1] * K;
+    p[8] = cv - (unsigned)s[-3 * SIN_P + 0] * K;  p[9] = cv - (unsigned)s[-3 * SIN_P - 1] * K;
+    p[10] = cv - (unsigned)s[-2 * SIN_P - 2] * K; p[11] = cv - (unsigned)s[-1 * SIN_P - 3] * K;
+    p[12] = cv - (unsigned)s[-3] * K;             p[13] = cv - (unsigned)s[1 * SIN_P - 3] * K;
+    p[14] = cv - (unsigned)s[2 * SIN_P - 2] * K;  p[15] = cv - (unsigned)s[3 * SIN_P - 1] * K;
     // minima over the 16 arcs of 9: lo3[k] = min(p[k..k+2]), lo9[k] = min(lo3[k], lo3[k+3], lo3[k+6]); 3-input DPX ops
     unsigned lo3[16], lo9[16];
 #pragma unroll
@@ -108,19 +117,48 @@ __device__ __noinline__ uint32_t load_border_word(const uint8_t* __restrict__ ro
            ((uint32_t)__ldg(row + reflect1(gx0 + 2, W)) << 16) | ((uint32_t)__ldg(row + reflect1(gx0 + 3, W)) << 24);
 }
 
+// ---- TMA helpers (sm_100a): one thread arms an mbarrier with the byte count and issues a 3-D tiled bulk copy
+//      global -> shared; every thread waits on the barrier's phase before reading the tile -------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // make the initialised barrier visible to the async proxy
+}
+__device__ __forceinline__ void tma_load_tile3d(void* smem_dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar, unsigned bytes) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// USE_TMA: the tile (+ halo) comes in with one cp.async.bulk.tensor per CTA from a tensor map over the batch's images
+// (zero fill outside the image; the few halo bytes that REFLECT_101 needs are patched afterwards, border tiles only).
+// Needs 16-byte aligned images / strides; launch_detect falls back to the load loop otherwise.
+template <bool USE_TMA>
 __global__ void __launch_bounds__(K1_THREADS)
 fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __restrict__ imgR,
-                 size_t stride, size_t image_pitch, int pitch_out) {
-    __shared__ __align__(16) uint32_t s_inw[SIN_H * SIN_WW];
+                 size_t stride, size_t image_pitch, int pitch_out, const __grid_constant__ CUtensorMap tmL,
+                 const __grid_constant__ CUtensorMap tmR) {
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(128) uint32_t s_inw[SIN_H * SIN_PW];
     __shared__ __align__(16) float s_row[(TH + 6) * TW];
-    __shared__ __align__(16) uint32_t s_zero[SC_H * SIN_WW + TH * (TW / 4)];   // zero-initialised planes:
+    __shared__ __align__(16) uint32_t s_zero[SC_H * SIN_PW + TH * (TW / 4)];   // zero-initialised planes:
     uint32_t* s_scw = s_zero;                                     //   scores of the candidates (tile + 1-px ring)
-    uint32_t* s_nmsw = s_zero + SC_H * SIN_WW;                    //   scores after NMS + border filter (tile only)
-    static_assert((SC_H * SIN_WW + TH * (TW / 4)) % 4 == 0 && (SC_H * SIN_WW) % 4 == 0, "uint4 zeroing / aligned planes");
-    __shared__ uint16_t s_list[K1_NCAND];                         // pre-test survivors  (row * SIN_W + column)
+    uint32_t* s_nmsw = s_zero + SC_H * SIN_PW;                    //   scores after NMS + border filter (tile only)
+    static_assert((SC_H * SIN_PW + TH * (TW / 4)) % 4 == 0 && (SC_H * SIN_PW) % 4 == 0, "uint4 zeroing / aligned planes");
+    __shared__ uint16_t s_list[K1_NCAND];                         // pre-test survivors  (row * SIN_P + column)
     __shared__ uint16_t s_corner[K1_NCAND];                       // corners (score > 0)
     __shared__ int s_n[2];
-    const uint8_t* s_in = reinterpret_cast<const uint8_t*>(s_inw);
+    uint32_t* s_inl = s_inw + SIN_XOFF / 4;                       // logical origin of the staged tile (column x0 - HALO)
+    const uint8_t* s_in = reinterpret_cast<const uint8_t*>(s_inl);
     uint8_t* s_sc = reinterpret_cast<uint8_t*>(s_scw);
 
     const int W = P.p.W, H = P.p.H;
@@ -131,25 +169,48 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // 1. stage the tile with halo 4 as 32-bit words (REFLECT_101 outside the image: only the blur looks there)
-    {
+    // 1. stage the tile with halo 4 (REFLECT_101 outside the image: only the blur looks there)
+    if (USE_TMA) {
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {      // (no pointer select between the two __grid_constant__ maps: each branch names its parameter)
+            if (side) tma_load_tile3d(s_inw, &tmR, x0 - HALO - SIN_XOFF, y0 - HALO, item, &s_bar, SIN_H * SIN_P);
+            else tma_load_tile3d(s_inw, &tmL, x0 - HALO - SIN_XOFF, y0 - HALO, item, &s_bar, SIN_H * SIN_P);
+        }
+        for (int w = tid; w < (SC_H * SIN_PW + TH * (TW / 4)) / 4; w += K1_THREADS)      // overlaps the copy
+            reinterpret_cast<uint4*>(s_zero)[w] = make_uint4(0, 0, 0, 0);
+        if (tid < 2) s_n[tid] = 0;
+        mbar_wait(&s_bar, 0);
+        // staged rows / columns outside the image arrived as zeros: patch them with the reflected pixels
+        const int c_lo = max(0, HALO - x0), c_hi = min(SIN_W, W - (x0 - HALO));
+        const int r_lo = max(0, HALO - y0), r_hi = min(SIN_H, H - (y0 - HALO));
+        if (c_lo > 0 || c_hi < SIN_W || r_lo > 0 || r_hi < SIN_H) {
+            __syncthreads();
+            uint8_t* s_inb = reinterpret_cast<uint8_t*>(s_inl);
+            for (int i = tid; i < SIN_H * SIN_W; i += K1_THREADS) {
+                const int r = i / SIN_W, c = i - r * SIN_W;
+                if (r < r_lo || r >= r_hi || c < c_lo || c >= c_hi)
+                    s_inb[r * SIN_P + c] = __ldg(img + (size_t)reflect1(y0 - HALO + r, H) * stride + reflect1(x0 - HALO + c, W));
+            }
+        }
+    } else {
         const bool aligned = ((reinterpret_cast<uintptr_t>(img) | stride) & 3) == 0;
         if (aligned && x0 >= HALO && x0 + TW + HALO <= W && y0 >= HALO && y0 + TH + HALO <= H) {
             const uint8_t* base = img + (size_t)(y0 - HALO) * stride + (x0 - HALO);      // interior tile: plain word copies
             for (int w = tid; w < SIN_H * SIN_WW; w += K1_THREADS) {
                 const int r = w / SIN_WW, cw = w - r * SIN_WW;
-                s_inw[w] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * stride) + cw);
+                s_inl[r * SIN_PW + cw] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * stride) + cw);
             }
         } else {
             for (int w = tid; w < SIN_H * SIN_WW; w += K1_THREADS) {
                 const int r = w / SIN_WW, cw = w - r * SIN_WW;
                 const int gy = reflect1(y0 - HALO + r, H), gx0 = x0 - HALO + 4 * cw;
                 const uint8_t* row = img + (size_t)gy * stride;
-                s_inw[w] = (aligned && gx0 >= 0 && gx0 + 3 < W) ? __ldg(reinterpret_cast<const uint32_t*>(row + gx0))
-                                                                 : load_border_word(row, gx0, W);
+                s_inl[r * SIN_PW + cw] = (aligned && gx0 >= 0 && gx0 + 3 < W) ? __ldg(reinterpret_cast<const uint32_t*>(row + gx0))
+                                                                               : load_border_word(row, gx0, W);
             }
         }
-        for (int w = tid; w < (SC_H * SIN_WW + TH * (TW / 4)) / 4; w += K1_THREADS)
+        for (int w = tid; w < (SC_H * SIN_PW + TH * (TW / 4)) / 4; w += K1_THREADS)
             reinterpret_cast<uint4*>(s_zero)[w] = make_uint4(0, 0, 0, 0);
         if (tid < 2) s_n[tid] = 0;
     }
@@ -158,7 +219,7 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
     // 2. blur, row pass: rows y0-3 .. y0+TH+2, four outputs per work item (float32, sequential FMA left to right)
     for (int i = tid; i < (TH + 6) * (TW / 4); i += K1_THREADS) {
         const int r = i / (TW / 4), c = (i - r * (TW / 4)) * 4;
-        const uint32_t* pw = s_inw + (r + 1) * SIN_WW + (c >> 2);   // bytes c .. c+11
+        const uint32_t* pw = s_inl + (r + 1) * SIN_PW + (c >> 2);   // bytes c .. c+11
         const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
         float f[10];                                   // columns c+1 .. c+10  (x-3 .. x+6 of the first output)
         f[0] = (float)((w0 >> 8) & 0xFF); f[1] = (float)((w0 >> 16) & 0xFF); f[2] = (float)(w0 >> 24);
@@ -194,8 +255,8 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
                 const int gy = y0 - 1 + r;
                 const int jlo = cx_lo - 4 * cw, jhi = cx_hi - 4 * cw;      // valid pixels of this word: jlo <= j < jhi
                 if (gy >= 3 && gy < H - 3 && jlo < 4 && jhi > 0) {
-                    const uint32_t* rp = s_inw + (r + 3) * SIN_WW + cw;
-                    const uint32_t C = rp[0], Cm = rp[-1], Cp = rp[1], U = rp[-3 * SIN_WW], D = rp[3 * SIN_WW];
+                    const uint32_t* rp = s_inl + (r + 3) * SIN_PW + cw;
+                    const uint32_t C = rp[0], Cm = rp[-1], Cp = rp[1], U = rp[-3 * SIN_PW], D = rp[3 * SIN_PW];
                     const uint32_t L = __funnelshift_r(Cm, C, 8);      // pixels x-3
                     const uint32_t R = __funnelshift_r(C, Cp, 24);     // pixels x+3
                     fast_pretest2(widen_lo(C) + 0x01000100u, widen_lo(D), widen_lo(R), widen_lo(U), widen_lo(L), t_hi, t_lo, c0, c1);
@@ -212,7 +273,7 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
             int base = 0;
             if (lane == 0 && (n0 + n1 + n2 + n3) > 0) base = atomicAdd(&s_n[0], n0 + n1 + n2 + n3);
             base = __shfl_sync(0xffffffffu, base, 0);
-            const int e = r * SIN_W + 4 * cw;
+            const int e = r * SIN_P + 4 * cw;
             if (c0) s_list[base + __popc(b0 & lt_mask)] = (uint16_t)e;
             if (c1) s_list[base + n0 + __popc(b1 & lt_mask)] = (uint16_t)(e + 1);
             if (c2) s_list[base + n0 + n1 + __popc(b2 & lt_mask)] = (uint16_t)(e + 2);
@@ -229,7 +290,7 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
             int sc = 0, e = 0;
             if (q < nlist) {
                 e = s_list[q];
-                sc = fast9_score(s_in + e + 3 * SIN_W, th);
+                sc = fast9_score(s_in + e + 3 * SIN_P, th);
                 if (sc > 0) s_sc[e] = (uint8_t)sc;
             }
             const unsigned b = __ballot_sync(0xffffffffu, sc > 0);
@@ -246,14 +307,14 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
         uint8_t* s_nms = reinterpret_cast<uint8_t*>(s_nmsw);
         for (int q = tid; q < ncorner; q += K1_THREADS) {
             const int e = s_corner[q];
-            const int r = e / SIN_W, c = e - r * SIN_W;           // r: 1 .. TH inside the tile, c: HALO .. HALO+TW-1
+            const int r = e / SIN_P, c = e - r * SIN_P;           // r: 1 .. TH inside the tile, c: HALO .. HALO+TW-1
             const int gx = x0 - HALO + c, gy = y0 - 1 + r;
             if (r < 1 || r > TH || c < HALO || c >= HALO + TW) continue;
             if (gx < kOrbEdge || gx >= W - kOrbEdge || gy < kOrbEdge || gy >= H - kOrbEdge) continue;
             const uint8_t* sp = s_sc + e;
             const int sv = sp[0];
-            const bool keep = sv > sp[-SIN_W - 1] && sv > sp[-SIN_W] && sv > sp[-SIN_W + 1] && sv > sp[-1] && sv > sp[1] &&
-                              sv > sp[SIN_W - 1] && sv > sp[SIN_W] && sv > sp[SIN_W + 1];
+            const bool keep = sv > sp[-SIN_P - 1] && sv > sp[-SIN_P] && sv > sp[-SIN_P + 1] && sv > sp[-1] && sv > sp[1] &&
+                              sv > sp[SIN_P - 1] && sv > sp[SIN_P] && sv > sp[SIN_P + 1];
             if (keep) s_nms[(r - 1) * TW + (c - HALO)] = (uint8_t)sv;
         }
     }
@@ -629,12 +690,41 @@ cudaError_t launch_begin_step(const Pools& P, int n, const uint8_t* d_repeat, cu
     return cudaGetLastError();
 }
 
+// Tensor map over the n images of one side: dims (x, y, image) of 8-bit pixels, box = one staged tile (SIN_P x SIN_H x 1),
+// no swizzle, out-of-bounds elements read as 0.  false if TMA's alignment rules do not hold (or the driver entry point
+// is missing): the caller then uses the load-loop kernel.
+static bool make_image_map(CUtensorMap* tm, const uint8_t* d_img, int W, int H, int n, size_t stride, size_t image_pitch) {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    if (!encode || getenv("SVO_NO_TMA")) return false;
+    if ((reinterpret_cast<uintptr_t>(d_img) & 15) || (stride & 15) || (image_pitch & 15) || n < 1) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)image_pitch};      // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)SIN_P, (cuuint32_t)SIN_H, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t launch_detect(const Pools& P, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
                           size_t image_pitch, int pitch_out, uint32_t* occ_scratch, int occ_words_per_img,
                           uint32_t* sort_scratch, uint2* list_scratch, uint32_t* key_scratch, cudaStream_t st, int* launches,
                           StepTimer* tm) {
     const dim3 g1((P.p.W + TW - 1) / TW, (P.p.H + TH - 1) / TH, 2 * n);
-    fast_blur_kernel<<<g1, K1_THREADS, 0, st>>>(P, d_left, d_right, stride, image_pitch, pitch_out);
+    CUtensorMap tmL, tmR;
+    if (make_image_map(&tmL, d_left, P.p.W, P.p.H, n, stride, image_pitch) && make_image_map(&tmR, d_right, P.p.W, P.p.H, n, stride, image_pitch))
+        fast_blur_kernel<true><<<g1, K1_THREADS, 0, st>>>(P, d_left, d_right, stride, image_pitch, pitch_out, tmL, tmR);
+    else {
+        memset(&tmL, 0, sizeof(tmL));
+        fast_blur_kernel<false><<<g1, K1_THREADS, 0, st>>>(P, d_left, d_right, stride, image_pitch, pitch_out, tmL, tmL);
+    }
     if (tm) tm->mark(st);
     const int smem = detect_smem_bytes(P.p);
     select_kernel<<<2 * n, K2_THREADS, smem, st>>>(P, pitch_out, occ_scratch, occ_words_per_img, sort_scratch, list_scratch,
