@@ -573,7 +573,9 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
 // ------------------------------------------------------------------------------------------------
 constexpr int K3_WARPS = 8;
 constexpr int K3_ITERS = 8;         // keypoints per warp
-constexpr int K3_PITCH = 40;        // patch row pitch in bytes: 9 aligned words (36 B) + pad
+constexpr int K3_PITCH = 48;        // patch row pitch in bytes: a 48-byte TMA box row (x origin rounded down to 16 bytes)
+constexpr int K3_PBYTES = 31 * K3_PITCH;             // 1488 bytes per staged patch
+constexpr int K3_PSLOT = (K3_PBYTES + 127) & ~127;   // 1536: TMA destinations are 128-byte aligned
 
 // Sample offsets inside the staged patch, built at compile time from the ORB pattern and stored transposed
 // ([test-in-byte][lane]) so that the 32 lanes of a warp read consecutive words.
@@ -594,13 +596,16 @@ constexpr BriefOffsets make_brief_offsets() {
 }
 __device__ const BriefOffsets g_brief_offsets = make_brief_offsets();
 
-// The 512 samples of one keypoint lie within |offset| <= 13 of it.  The warp first copies the 31-row patch
-// around the keypoint into shared memory with aligned 32-bit loads (3 rows x 9 words per instruction, ~55 L1
-// sectors per keypoint), then every lane reads its 16 samples from there -- instead of 16 global byte gathers
-// per lane that touch ~20 sectors each.
+// The 512 samples of one keypoint lie within |offset| <= 13 of it.  The 31-row patch around the keypoint is staged in
+// shared memory and every lane reads its 16 samples from there (instead of 16 global byte gathers per lane).
+//   USE_TMA : lane 0 issues one cp.async.bulk.tensor.3d per keypoint (48 x 31 box of the blur plane, x origin rounded
+//             down to 16 bytes) into one of two buffers, one keypoint ahead of the warp; all lanes wait on the mbarrier.
+//   else    : the warp copies the patch with aligned 32-bit loads (3 rows x 9 words per instruction).
+template <bool USE_TMA>
 __global__ void __launch_bounds__(K3_WARPS * 32)
-brief_kernel(Pools P, int pitch) {
-    __shared__ __align__(16) uint8_t s_patch[K3_WARPS][31 * K3_PITCH];
+brief_kernel(Pools P, int pitch, const __grid_constant__ CUtensorMap tmBlur) {
+    __shared__ __align__(128) uint8_t s_patch[K3_WARPS][2][K3_PSLOT];
+    __shared__ __align__(8) uint64_t s_bar[K3_WARPS][2];
     const int item = blockIdx.y >> 1, side = blockIdx.y & 1;
     const int slot = P.slots[item];
     const int cur = P.state[slot].cur;
@@ -610,36 +615,67 @@ brief_kernel(Pools P, int pitch) {
     uint32_t off[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) off[t] = g_brief_offsets.v[t * 32 + lane];
-    const int lr = lane / 9, lw = lane - lr * 9;
-    uint32_t* patchw = reinterpret_cast<uint32_t*>(s_patch[w]);
-    const uint8_t* __restrict__ plane = P.blur + img_idx(slot, side) * (size_t)pitch * P.p.H;
     const int k0 = (blockIdx.x * K3_WARPS + w) * K3_ITERS;
-    for (int it = 0; it < K3_ITERS; ++it) {
-        const int k = k0 + it;
-        if (k >= n) break;
-        const int2 kp = P.kp[f * P.p.kp_cap + k];
-        const int x = kp.x & 0xFFFF, y = (unsigned)kp.x >> 16;
-        // rows y-15 .. y+15; columns from (x-15) rounded down to a multiple of 4 (planes are 16-byte aligned with a
-        // pitch that is a multiple of 16; keypoints are >= 31 px inside the image, so the patch never leaves it)
-        const int xs = x - 15, a = xs & 3;
-        const uint8_t* __restrict__ src = plane + (size_t)(y - 15) * pitch + (xs - a);
+    const int2* __restrict__ kps = P.kp + f * P.p.kp_cap;
+    uint8_t* __restrict__ desc = reinterpret_cast<uint8_t*>(P.desc + f * P.p.kp_cap * 2);
+    if (USE_TMA) {
+        const int img = (int)img_idx(slot, side);
+        if (lane == 0) { mbar_init(&s_bar[w][0], 1); mbar_init(&s_bar[w][1], 1); }
         __syncwarp();
-        if (lane < 27) {
+        auto issue = [&](int k, int buf) {              // lane 0: patch of keypoint k -> buffer buf
+            const int2 kp = kps[k];
+            const int xs = (kp.x & 0xFFFF) - 15, y = (int)((unsigned)kp.x >> 16);
+            tma_load_tile3d(s_patch[w][buf], &tmBlur, xs & ~15, y - 15, img, &s_bar[w][buf], K3_PBYTES);
+        };
+        if (lane == 0 && k0 < n) issue(k0, 0);
+        for (int it = 0; it < K3_ITERS; ++it) {
+            const int k = k0 + it;
+            if (k >= n) break;
+            const int buf = it & 1;
+            if (lane == 0 && it + 1 < K3_ITERS && k + 1 < n) issue(k + 1, buf ^ 1);     // its last readers passed the __syncwarp below
+            const int xs = (kps[k].x & 0xFFFF) - 15;
+            mbar_wait(&s_bar[w][buf], (unsigned)(it >> 1) & 1u);
+            const uint8_t* patch = s_patch[w][buf] + (xs & 15);
+            unsigned v = 0;
 #pragma unroll
-            for (int r3 = 0; r3 < 11; ++r3) {
-                const int row = r3 * 3 + lr;
-                if (row < 31) patchw[row * (K3_PITCH / 4) + lw] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)row * pitch) + lw);
+            for (int t = 0; t < 8; ++t) {
+                const int pa = patch[off[t] & 0xFFFFu], pb = patch[off[t] >> 16];
+                v |= (unsigned)(pa < pb) << t;
             }
+            desc[(size_t)k * 32 + lane] = (uint8_t)v;
+            __syncwarp();
         }
-        __syncwarp();
-        const uint8_t* patch = s_patch[w] + a;
-        unsigned v = 0;
+    } else {
+        const int lr = lane / 9, lw = lane - lr * 9;
+        uint32_t* patchw = reinterpret_cast<uint32_t*>(s_patch[w][0]);
+        const uint8_t* __restrict__ plane = P.blur + img_idx(slot, side) * (size_t)pitch * P.p.H;
+        for (int it = 0; it < K3_ITERS; ++it) {
+            const int k = k0 + it;
+            if (k >= n) break;
+            const int2 kp = kps[k];
+            const int x = kp.x & 0xFFFF, y = (unsigned)kp.x >> 16;
+            // rows y-15 .. y+15; columns from (x-15) rounded down to a multiple of 4 (planes are 16-byte aligned with a
+            // pitch that is a multiple of 16; keypoints are >= 31 px inside the image, so the patch never leaves it)
+            const int xs = x - 15, a = xs & 3;
+            const uint8_t* __restrict__ src = plane + (size_t)(y - 15) * pitch + (xs - a);
+            __syncwarp();
+            if (lane < 27) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int pa = patch[off[t] & 0xFFFFu], pb = patch[off[t] >> 16];
-            v |= (unsigned)(pa < pb) << t;
+                for (int r3 = 0; r3 < 11; ++r3) {
+                    const int row = r3 * 3 + lr;
+                    if (row < 31) patchw[row * (K3_PITCH / 4) + lw] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)row * pitch) + lw);
+                }
+            }
+            __syncwarp();
+            const uint8_t* patch = s_patch[w][0] + a;
+            unsigned v = 0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int pa = patch[off[t] & 0xFFFFu], pb = patch[off[t] >> 16];
+                v |= (unsigned)(pa < pb) << t;
+            }
+            desc[(size_t)k * 32 + lane] = (uint8_t)v;
         }
-        reinterpret_cast<uint8_t*>(P.desc + (f * P.p.kp_cap + k) * 2)[lane] = (uint8_t)v;
     }
 }
 
@@ -693,7 +729,8 @@ cudaError_t launch_begin_step(const Pools& P, int n, const uint8_t* d_repeat, cu
 // Tensor map over the n images of one side: dims (x, y, image) of 8-bit pixels, box = one staged tile (SIN_P x SIN_H x 1),
 // no swizzle, out-of-bounds elements read as 0.  false if TMA's alignment rules do not hold (or the driver entry point
 // is missing): the caller then uses the load-loop kernel.
-static bool make_image_map(CUtensorMap* tm, const uint8_t* d_img, int W, int H, int n, size_t stride, size_t image_pitch) {
+static bool make_plane_map(CUtensorMap* tm, const uint8_t* d_img, int W, int H, int n, size_t stride, size_t image_pitch, int box_w,
+                           int box_h) {
     static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     static bool looked = false;
     if (!looked) {
@@ -707,10 +744,17 @@ static bool make_image_map(CUtensorMap* tm, const uint8_t* d_img, int W, int H, 
     if ((reinterpret_cast<uintptr_t>(d_img) & 15) || (stride & 15) || (image_pitch & 15) || n < 1) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
     const cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)image_pitch};      // bytes, dims 1 and 2
-    const cuuint32_t box[3] = {(cuuint32_t)SIN_P, (cuuint32_t)SIN_H, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool make_image_map(CUtensorMap* tm, const uint8_t* d_img, int W, int H, int n, size_t stride, size_t image_pitch) {
+    return make_plane_map(tm, d_img, W, H, n, stride, image_pitch, SIN_P, SIN_H);
+}
+// the pitched internal planes (blur): all (slot, side) images of the context
+static bool make_plane_map(CUtensorMap* tm, const uint8_t* d_plane, int pitch, int H, int n_images, int box_w, int box_h) {
+    return make_plane_map(tm, d_plane, pitch, H, n_images, (size_t)pitch, (size_t)pitch * H, box_w, box_h);
 }
 
 cudaError_t launch_detect(const Pools& P, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
@@ -731,7 +775,13 @@ cudaError_t launch_detect(const Pools& P, int n, const uint8_t* d_left, const ui
                                                    key_scratch, detect_smem_corners(P.p));
     if (tm) tm->mark(st);
     const dim3 g3((P.p.kp_cap + K3_WARPS * K3_ITERS - 1) / (K3_WARPS * K3_ITERS), 2 * n);
-    brief_kernel<<<g3, K3_WARPS * 32, 0, st>>>(P, pitch_out);
+    CUtensorMap tmB;
+    if (!getenv("SVO_NO_TMA_BRIEF") && make_plane_map(&tmB, P.blur, pitch_out, P.p.H, 2 * (P.p.max_seqs + 1), K3_PITCH, 31))
+        brief_kernel<true><<<g3, K3_WARPS * 32, 0, st>>>(P, pitch_out, tmB);
+    else {
+        memset(&tmB, 0, sizeof(tmB));
+        brief_kernel<false><<<g3, K3_WARPS * 32, 0, st>>>(P, pitch_out, tmB);
+    }
     if (tm) tm->mark(st);
     if (launches) *launches += 3;
     return cudaGetLastError();
