@@ -606,7 +606,7 @@ def run_gpu(args):
                                     "if_match_method": ["ifmDescBF", "ifmDescWin"][args.if_match_method]},
                        "streams": "slots of a step run in %s groups on concurrent streams (value, e2e); the per-kernel times "
                                   "and the roofline come from a serialised pass of the same steps (%.3f ms per step)"
-                                  % (args.chunks or "the library's default (4)", serial_ms),
+                                  % (args.chunks or "the library's default (2)", serial_ms),
                        "l2": f"inputs larger than L2: {2 * B * W * H / 1e6:.0f} MB of images per step per GPU, "
                              f"{period} distinct batches cycled",
                        "keypoints_per_image": Nkp, "stereo_matches": M, "tracked_pairs": T,

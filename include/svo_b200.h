@@ -271,7 +271,7 @@ int64_t svo_kernel_launches(const svo_ctx* ctx);
 /* raw CUDA stream of the context (cudaStream_t as void*), for event timing on the launching stream */
 void* svo_stream(svo_ctx* ctx);
 /* Concurrency inside one batched step (no counterpart in the reference, which is single-threaded): batches of
- * >= 64 slots are split into `chunks` groups (1..8, default 4) whose kernel sequences run on separate streams,
+ * >= 64 slots are split into `chunks` groups (1..8, default 2) whose kernel sequences run on separate streams,
  * forked from and joined into the context's stream.  Results do not depend on the setting. */
 int svo_set_concurrency(svo_ctx* ctx, int32_t chunks);
 /* per-stage device times of the last svo_process_batch* call, in ms, measured with CUDA events on

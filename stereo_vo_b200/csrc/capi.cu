@@ -32,7 +32,7 @@ static const char* kKernelNames[KT_COUNT] = {
     "hamming_kernel(track)", "track_filter_kernel", "ransac_prepare_kernel", "fundmat_kernel", "consistency_kernel",
     "gn_kernel"};
 
-enum { kMaxChunks = 8, kDefaultChunks = 4, kMinChunkItems = 32 };
+enum { kMaxChunks = 8, kDefaultChunks = 2, kMinChunkItems = 32 };
 enum { kDepth = 3 };   // batches in flight (svo_submit_batch / svo_wait_batch): with three staging buffers the copy stream
                        // never waits for the host to see a batch finish before the next upload can start
 
