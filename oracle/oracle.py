@@ -595,3 +595,196 @@ class OracleEstimator:
         if not repeat:
             self.m_it_counter += 1
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Multi-octave path (params_rectify.nOctaves > 1; the reference's ctor default is 3, stage1_rectify.cpp:28)
+# ------------------------------------------------------------------------------------------------
+PYR_MRPT_AUTO, PYR_AVG2X2, PYR_PYRDOWN = 0, 1, 2
+
+
+def pyr_half_avg(img):
+    """MRPT 1.x CImage::scaleHalfSmooth, SSE2 path (image_SSE2_scale_half_smooth_1c8u): two rows are averaged with
+    _mm_avg_epu8 (rounding up), then horizontal neighbours with _mm_avg_epu16.  MRPT's source is not in this image:
+    restated from its published implementation, UNPINNED."""
+    img = _img(img)
+    h2, w2 = img.shape[0] >> 1, img.shape[1] >> 1
+    a = img[0:2 * h2:2, :2 * w2].astype(np.uint16)
+    b = img[1:2 * h2:2, :2 * w2].astype(np.uint16)
+    v = (a + b + 1) >> 1
+    return ((v[:, 0::2] + v[:, 1::2] + 1) >> 1).astype(np.uint8)
+
+
+def _reflect101(i, n):
+    if n == 1:
+        return 0
+    while i < 0 or i >= n:
+        i = -i if i < 0 else 2 * (n - 1) - i
+    return i
+
+
+def pyr_down5(img):
+    """cv::pyrDown / cvPyrDown (MRPT's fallback in scaleHalfSmooth when the SSE2 conditions do not hold) into a
+    (w>>1) x (h>>1) image: separable [1 4 6 4 1], integer accumulation, (sum + 128) >> 8, BORDER_REFLECT_101.
+    Pinned against cv2.pyrDown in tests/test_octaves_cpu.py."""
+    img = _img(img)
+    h, w = img.shape
+    h2, w2 = h >> 1, w >> 1
+    k = (1, 4, 6, 4, 1)
+    cols = [np.array([_reflect101(2 * x + d, w) for x in range(w2)]) for d in range(-2, 3)]
+    rows = [np.array([_reflect101(2 * y + d, h) for y in range(h2)]) for d in range(-2, 3)]
+    src = img.astype(np.int32)
+    hor = sum(kk * src[:, c] for kk, c in zip(k, cols))          # (h, w2)
+    ver = sum(kk * hor[r, :] for kk, r in zip(k, rows))          # (h2, w2)
+    return ((ver + 128) >> 8).astype(np.uint8)
+
+
+def pyr_half(img, mode=PYR_MRPT_AUTO):
+    if mode == PYR_AVG2X2 or (mode == PYR_MRPT_AUTO and img.shape[1] % 16 == 0):
+        return pyr_half_avg(img)
+    return pyr_down5(img)
+
+
+def build_pyramid(img, n_octaves, mode=PYR_MRPT_AUTO):
+    """CImagePyramid::buildPyramidFast(img, nOctaves) (stage1_rectify.cpp:82-83; smooth_halves defaults to true)."""
+    out = [_img(img)]
+    for _ in range(1, n_octaves):
+        out.append(pyr_half(out[-1], mode))
+    return out
+
+
+def kps_to_detect(orb_nfeats, n_octaves):
+    """stage2_detect.cpp:404-407."""
+    q0 = int(orb_nfeats * (2 * n_octaves) / (2.0 ** n_octaves - 1))
+    return [q0] + [int(np.floor(q0 / 2.0 ** k + 0.5)) for k in range(1, n_octaves)]
+
+
+class OracleEstimatorOctaves(OracleEstimator):
+    """processNewImagePair with params_rectify.nOctaves >= 1 on the FAST+ORB / smDescBF / ifmDescBF path: stage 2-4
+    run per octave (stage2_detect.cpp:423-624, stage3_match_left_right.cpp:87-177, stage4_match_consecutive.cpp:91-328),
+    the match-ID generator and the tracking counters run through the octaves in order, stage 5 flattens all octaves with
+    the x 2^octave rescale (stage5_optimization.cpp:419-461)."""
+
+    def __init__(self, params=None, backend="cv2", ransac="cv2", sort_mode=0, pyr_mode=PYR_MRPT_AUTO):
+        super().__init__(params, backend, ransac, sort_mode)
+        assert self.p.match_method == 0 and self.p.ifm_method == 0
+        self.pyr_mode = pyr_mode
+
+    def detect_octave(self, img, quota):
+        H, W = img.shape
+        th = self.m_current_fast_th
+        if self.backend == "cv2":
+            kps, desc = cv2_fast_orb(img, th)
+        else:
+            kps = fast9(img, th)
+            kps, desc = orb_compute(img, kps)
+        if self.p.non_maximal_suppression:
+            kps, desc, _ = non_max_sup(quota, kps, desc, self.p.min_distance, H, W, self.sort_mode)
+        kps, desc, _, row_index = update_indexes(kps, desc, H, self.sort_mode)
+        return kps, desc, row_index
+
+    def process_new_image_pair(self, imgL, imgR, cam, repeat=False):
+        nOct = int(self.p.nOctaves)
+        out = dict(error_code=VOEC["voecNone"], valid=False, num_it=0, num_it_final=0, outliers=np.zeros(0, np.int64),
+                   out_residual=np.zeros(0), tracked=[np.zeros((0, 2), np.int64)] * nOct, pose=None)
+        if (not repeat) and self.m_error not in (VOEC["voecBadTracking"], VOEC["voecBadCondNumber"]):
+            self.prev = self.cur
+        self.m_error = VOEC["voecNone"]
+        pyrL = build_pyramid(imgL, nOct, self.pyr_mode)
+        pyrR = build_pyramid(imgR, nOct, self.pyr_mode)
+        quotas = kps_to_detect(self.p.orb_nfeats, nOct)
+        frames = []
+        for k in range(nOct):
+            f = FrameData()
+            f.H, f.W = pyrL[k].shape
+            f.kpsL, f.descL, f.idxL = self.detect_octave(pyrL[k], quotas[k])
+            f.kpsR, f.descR, f.idxR = self.detect_octave(pyrR[k], quotas[k])
+            f.ids = None
+            frames.append(f)
+        out["detected_feats"] = [(len(f.kpsL), len(f.kpsR)) for f in frames]
+        first = self.prev is None
+        if self.m_reset and self.prev is not None:    # P:254-267
+            self.m_last_match_ID = 0
+            for pf in self.prev:
+                n_ids = len(pf.ids) if pf.ids is not None else 0
+                if n_ids:
+                    pf.ids = np.arange(self.m_last_match_ID, self.m_last_match_ID + n_ids, dtype=np.int64)
+                self.m_last_match_ID += n_ids
+            self.m_reset = False
+            self.m_last_kf_max_id = self.m_last_match_ID - 1
+        for f in frames:                              # S3:87-177
+            f.matches, _ = self.match_lr(f)
+            if self.p.vo_use_matches_ids and first:
+                f.ids = np.arange(self.m_last_match_ID, self.m_last_match_ID + len(f.matches), dtype=np.int64)
+                self.m_last_match_ID += len(f.matches)
+        out["stereo_matches"] = [len(f.matches) for f in frames]
+        self.cur = frames
+        out["frames"] = frames
+        out["pyramid"] = (pyrL, pyrR)
+        if self.prev is None:
+            out["error_code"] = VOEC["voecFirstIteration"]
+            if not repeat:
+                self.m_it_counter += 1
+            return out
+        tracked_all, dbg_all = [], []
+        for k in range(nOct):                         # S4:91-328
+            pf, f = self.prev[k], frames[k]
+            tracked, tr = self.track(pf, f)
+            tracked_all.append(tracked)
+            dbg_all.append(tr)
+            if self.p.vo_use_matches_ids:
+                ids = np.zeros(len(f.matches), np.int64)
+                got = np.zeros(len(f.matches), bool)
+                for a, b in tracked:
+                    ids[b] = pf.ids[a]
+                    got[b] = True
+                for m in range(len(ids)):
+                    if not got[m]:
+                        ids[m] = self.m_last_match_ID
+                        self.m_last_match_ID += 1
+                f.ids = ids
+        out["tracked"] = tracked_all
+        out["track_dbg"] = dbg_all
+        total = sum(len(t) for t in tracked_all)      # S4:743-752
+        out["tracked_feats_from_last_frame"] = total
+        out["tracked_feats_from_last_KF"] = (sum(int((f.ids <= self.m_last_kf_max_id).sum()) for f in frames)
+                                             if self.p.vo_use_matches_ids else 0)
+        if total < self.p.bad_tracking_th:            # P:326-330
+            self.m_error = out["error_code"] = VOEC["voecBadTracking"]
+            if not repeat:
+                self.m_it_counter += 1
+            return out
+        # S5:419-461: all octaves into four flat lists at the scale of octave 0
+        def xy(kp, idx, s):
+            return (np.stack([kp["x"][idx], kp["y"][idx]], 1).astype(np.float32) * np.float32(s)).astype(np.float32)
+        L = dict(l1l=[], l1r=[], l2l=[], l2r=[], resp=[], cmi=[])
+        for k in range(nOct):
+            s = float(2 ** k) if nOct > 1 else 1.0
+            pf, f, tp = self.prev[k], frames[k], tracked_all[k]
+            pm = pf.matches[tp[:, 0]]
+            cm = f.matches[tp[:, 1]]
+            L["l1l"].append(xy(pf.kpsL, pm["queryIdx"], s)); L["l1r"].append(xy(pf.kpsR, pm["trainIdx"], s))
+            L["l2l"].append(xy(f.kpsL, cm["queryIdx"], s)); L["l2r"].append(xy(f.kpsR, cm["trainIdx"], s))
+            L["resp"].append(pf.kpsL["response"][pm["queryIdx"]].astype(np.float32))
+            L["cmi"].append(tp[:, 1].astype(np.int64))
+        flat = {k: np.concatenate(v) for k, v in L.items()}
+        if self.p.use_previous_pose_as_initial:
+            ini = self.m_last_computed_pose.copy()
+        else:
+            ini = np.zeros(6)
+        H0, W0 = self.prev[0].H, self.prev[0].W
+        res, residual, inl = stage5(flat["l1l"], flat["l1r"], flat["l2l"], flat["l2r"], flat["resp"], flat["cmi"], H0, W0,
+                                    self.p.min_distance, cam, self.p.ls(), ini, self.sort_mode)
+        if res.bad_cond:
+            self.m_error = VOEC["voecBadCondNumber"]
+        if res.reached_end and self.p.use_previous_pose_as_initial:
+            self.m_last_computed_pose = np.array(res.delta_pose[:])
+        out.update(gn=res, gn_dbg=dict(flat, ini=ini), error_code=res.error_code, valid=bool(res.valid), num_it=res.num_it,
+                   num_it_final=res.num_it_final, out_residual=residual, outliers=inl)
+        if res.reached_end:
+            out["pose"] = dict(rotvec=np.array(res.out_pose_rotvec[:]), t=np.array(res.out_pose_t[:]),
+                               mat=np.array(res.out_pose_mat[:]).reshape(4, 4), ypr=np.array(res.out_pose_ypr[:]),
+                               delta=np.array(res.delta_pose[:]))
+        if not repeat:
+            self.m_it_counter += 1
+        return out
