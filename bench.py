@@ -336,6 +336,44 @@ def single_pair_latency(capi, seqs, gc, W, H, nfeats, device_index, n=60):
             "note": "batch of one: the kernels are latency-bound here, throughput needs many sequences per step"}
 
 
+def octaves_throughput(capi, torch, dev, gc, W, H, nfeats, device_index, n_octaves=3, batch=256, steps=20, warmup=3):
+    """params_rectify.nOctaves = 3, the reference's ctor default (stage1_rectify.cpp:28): the pyramid is built on the
+    device and stages 2-4 run per octave before one flattened stage 5.  Device-resident images, CUDA events on the
+    library's stream; a second line beside the headline (which runs the one-octave INI of SURVEY Appendix C)."""
+    batch = min(batch, dev[0][0].shape[0])
+    ctx = capi.Context(width=W, height=H, orb_nfeats=nfeats, max_seqs=batch, device=device_index, n_octaves=n_octaves)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", device_index))
+    cams = [gc] * batch
+
+    def step(t):
+        L, R = dev[t % len(dev)]
+        ctx.process_batch_device(L.data_ptr(), R.data_ptr(), batch, W, W * H, cams)
+    for t in range(warmup):
+        step(t)
+    ctx.synchronize()
+    l0 = ctx.kernel_launches()
+    with torch.cuda.stream(stream):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(steps):
+            step(warmup + t)
+        e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res = ctx.fetch_results(batch)
+    stats = np.mean([ctx.octave_stats(s) for s in range(0, batch, max(1, batch // 16))], axis=0)
+    out = {"n_octaves": n_octaves, "pairs_per_step": batch, "ms_per_step": round(ms, 4),
+           "pairs_per_s": round(batch / ms * 1e3, 1), "valid_results": f"{sum(int(r.valid) for r in res)}/{batch}",
+           "launches_per_step": (ctx.kernel_launches() - l0) // steps,
+           "per_octave_mean": {"keypoints_left": [round(float(v), 1) for v in stats[:, 0]],
+                               "stereo_matches": [round(float(v), 1) for v in stats[:, 2]],
+                               "tracked_pairs": [round(float(v), 1) for v in stats[:, 3]]},
+           "octave_sizes": [list(o[:2]) for o in ctx.octave_info], "quotas": [o[2] for o in ctx.octave_info]}
+    ctx.close()
+    return out
+
+
 def run_c5(args):
     """--workload c5: the microbench on N GPUs.  Query rows are sharded across the ranks, the train set is
     replicated (broadcast from rank 0), the packed results are all-gathered (the one exchange step, NCCL)."""
@@ -590,8 +628,9 @@ def run_gpu(args):
         pairdist = B * (Nkp * Nkp + 2 * M * M)
         clocks = sampler.summary()
         int_roof = 1.0 / max(HM_POPC_PFX / pipe["popc_per_s"], HM_ALU_PFX / pipe["lop3_per_s"])
-        micro = stage1 = latency = None
+        micro = stage1 = latency = octaves = None
         if not args.no_micro:
+            octaves = octaves_throughput(capi, torch, dev, gc, W, H, nfeats, local)
             micro, _ = c5_microbench(ctx, torch, stream, torch.device("cuda", local), pipe, peak, reps=64, iters=5)
             stage1 = stage1_microbench(ctx, torch, stream, torch.device("cuda", local), W, H, peak)
             latency = single_pair_latency(capi, seqs, gc, W, H, nfeats, local)
@@ -634,6 +673,7 @@ def run_gpu(args):
             "match_microbench": micro,
             "stage1": stage1,
             "single_pair": latency,
+            "octaves": octaves,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

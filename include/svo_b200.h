@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SVO_B200_ABI_VERSION 2
+#define SVO_B200_ABI_VERSION 3
 
 typedef enum svo_status {
     SVO_OK = 0,
@@ -103,9 +103,16 @@ typedef struct svo_config {
     int32_t ifm_win_w, ifm_win_h; /* window of ifmDescWin (INI keys window_width / window_height; no default in the
                                      reference, 20 / 20 here) */
     double  orb_max_distance;     /* params_lr_match.orb_max_distance, the threshold smDescRbR reads (:206); 40 */
+    /* image pyramid (ABI version 3) */
+    int32_t n_octaves;            /* params_rectify.nOctaves (stage1_rectify.cpp:28,80): 1..4.  1 here;
+                                     the reference's ctor default is 3.  > 1 needs smDescBF / ifmDescBF */
+    int32_t pyr_mode;             /* how CImagePyramid::buildPyramidFast halves an octave (stage1_rectify.cpp:82-83):
+                                     0 = as MRPT 1.x picks (2x2 rounded average when the width is a multiple of 16,
+                                     cvPyrDown otherwise), 1 = always the 2x2 average, 2 = always cv::pyrDown */
 } svo_config;
 
-/* POD mirror of TStereoOdometryResult (libstereo-odometry.h:235-264) for nOctaves == 1.
+/* POD mirror of TStereoOdometryResult (libstereo-odometry.h:235-264).  detected_* / stereo_matches describe octave 0
+ * (svo_get_octave_stats has every octave); the tracked counters run over all octaves as in the reference.
  * The variable-length members (outliers, out_residual) are fetched with svo_get_* below. */
 typedef struct svo_result {
     double  out_pose[16];         /* outPose as row-major 4x4 (pose of the current frame wrt the previous) */
@@ -176,6 +183,24 @@ int svo_get_match_ids(svo_ctx* ctx, int32_t slot, int32_t which, int64_t* out, i
 int svo_get_tracked_pairs(svo_ctx* ctx, int32_t slot, int64_t* out_pairs /* cap x 2 */, int32_t cap);
 int svo_get_residuals(svo_ctx* ctx, int32_t slot, double* out, int32_t cap);
 int svo_get_outliers(svo_ctx* ctx, int32_t slot, int64_t* out, int32_t cap);
+/* ---- octaves (params_rectify.nOctaves > 1; per-octave vectors of TImagePairData, libstereo-odometry.h:756-811) ---- */
+/* The readers above address octave 0; these take the octave.  svo_get_tracked_pairs_oct = tracked_pairs[octave]
+ * (stage4_match_consecutive.cpp:262-287); residuals / outliers cover the flattened list of all octaves in octave order
+ * (stage5_optimization.cpp:419-461, 601-610). */
+int svo_get_keypoints_oct(svo_ctx* ctx, int32_t slot, int32_t octave, int32_t which, int32_t side, svo_keypoint* out, int32_t cap);
+int svo_get_descriptors_oct(svo_ctx* ctx, int32_t slot, int32_t octave, int32_t which, int32_t side, uint8_t* out, int32_t cap_rows);
+int svo_get_matches_oct(svo_ctx* ctx, int32_t slot, int32_t octave, int32_t which, svo_dmatch* out, int32_t cap);
+int svo_get_match_ids_oct(svo_ctx* ctx, int32_t slot, int32_t octave, int32_t which, int64_t* out, int32_t cap);
+int svo_get_tracked_pairs_oct(svo_ctx* ctx, int32_t slot, int32_t octave, int64_t* out_pairs /* cap x 2 */, int32_t cap);
+/* out4 = {width, height, kps_to_detect[octave] (stage2_detect.cpp:404-407), keypoint capacity}; returns n_octaves */
+int svo_get_octave_info(svo_ctx* ctx, int32_t octave, int32_t* out4);
+/* per octave {detected left, detected right, stereo matches, tracked pairs} of the slot's last step (result.detected_feats,
+ * result.stereo_matches, tracked_pairs[octave].size()); out holds cap_octaves x 4 values; returns n_octaves */
+int svo_get_octave_stats(svo_ctx* ctx, int32_t slot, int32_t* out, int32_t cap_octaves);
+/* parity seam of the pyramid: the image of octave >= 1 built for batch item `item` (position in the slot list) of the
+ * last step, (height >> octave) x (width >> octave) bytes, tightly packed */
+int svo_get_pyramid_plane(svo_ctx* ctx, int32_t item, int32_t octave, int32_t side, uint8_t* out);
+
 /* debugging / parity seams inside stage 4: the greedy-filtered matL/matR lists (train indices)
  * and the two RANSAC inlier masks (stage4_match_consecutive.cpp:145-160, 202, 237) */
 int svo_get_track_candidates(svo_ctx* ctx, int32_t slot, int32_t* out_query, int32_t* out_trainL,
@@ -187,7 +212,7 @@ int svo_reset_ids(svo_ctx* ctx, int32_t slot);                    /* resetIds():
 int svo_set_ids(svo_ctx* ctx, int32_t slot, const int64_t* ids, int32_t n);   /* setIds(), H:685-694 */
 int svo_set_max_match_id(svo_ctx* ctx, int32_t slot, int64_t id); /* setMaxMatchID(), H:726 */
 
-/* ---- stage 1: stage1_prepare_rectify (stage1_rectify.cpp:37-93), nOctaves = 1 ---------------- */
+/* ---- stage 1: stage1_prepare_rectify (stage1_rectify.cpp:37-93); the pyramid (:80-83) is built inside the step -- */
 /* Input format of svo_process_batch / svo_submit_batch / svo_process_pair: channels = 1 (8-bit gray, the default)
  * or 3 (8-bit BGR, as MRPT / OpenCV hold colour images; row stride in bytes).  Colour input is converted on the
  * device like mrpt::utils::CImage(img, FAST_REF_OR_CONVERT_TO_GRAY) = cv::cvtColor(BGR2GRAY)

@@ -34,6 +34,8 @@ EXPORTS = [
     "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks", "svo_set_concurrency",
     "svo_set_input_format", "svo_set_rectify_maps", "svo_prepare_rectify", "svo_prepare_rectify_device",
     "svo_get_projected_coords", "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
+    "svo_get_keypoints_oct", "svo_get_descriptors_oct", "svo_get_matches_oct", "svo_get_match_ids_oct",
+    "svo_get_tracked_pairs_oct", "svo_get_octave_info", "svo_get_octave_stats", "svo_get_pyramid_plane",
 ]
 
 
@@ -49,7 +51,8 @@ class Config(C.Structure):
                 ("residual_threshold", C.c_double), ("bad_tracking_th", C.c_int32),
                 ("use_previous_pose_as_initial", C.c_int32), ("vo_use_matches_ids", C.c_int32), ("sort_mode", C.c_int32),
                 ("match_method", C.c_int32), ("if_match_method", C.c_int32), ("ifm_win_w", C.c_int32),
-                ("ifm_win_h", C.c_int32), ("orb_max_distance", C.c_double)]
+                ("ifm_win_h", C.c_int32), ("orb_max_distance", C.c_double),
+                ("n_octaves", C.c_int32), ("pyr_mode", C.c_int32)]
 
 
 class Camera(C.Structure):
@@ -137,8 +140,9 @@ class Context:
         rc = lib().svo_create(C.byref(self.cfg), C.byref(self._h))
         if rc != SVO_OK:
             raise SvoError(rc, lib().svo_last_error(None).decode())
-        quota = 2 * self.cfg.orb_nfeats
-        self.kp_cap = min(quota, self.cfg.max_corners) if self.cfg.non_maximal_suppression else self.cfg.max_corners
+        self.n_octaves = int(self.cfg.n_octaves)
+        self.octave_info = [self._octave_info(k) for k in range(self.n_octaves)]   # (W, H, quota, kp_cap) per octave
+        self.kp_cap = sum(o[3] for o in self.octave_info)      # room for any per-octave or flattened list
 
     def close(self):
         if getattr(self, "_h", None):
@@ -219,30 +223,47 @@ class Context:
     def reset_slot(self, slot):
         self._check(lib().svo_reset_slot(self._h, slot))
 
-    # ---- readers ----------------------------------------------------------------------------------
-    def keypoints(self, slot=0, which=0, side=0):
+    # ---- readers (octave = index into the image pyramid, params_rectify.nOctaves) ------------------
+    def _octave_info(self, octave):
+        out = (C.c_int32 * 4)()
+        self._check(lib().svo_get_octave_info(self._h, octave, out))
+        return tuple(out)
+
+    def octave_stats(self, slot=0):
+        """(n_octaves, 4) array: detected left, detected right, stereo matches, tracked pairs of the last step."""
+        out = np.zeros((self.n_octaves, 4), np.int32)
+        self._check(lib().svo_get_octave_stats(self._h, slot, _vp(out), self.n_octaves))
+        return out
+
+    def pyramid_plane(self, item=0, octave=1, side=0):
+        w, h = self.octave_info[octave][:2]
+        out = np.zeros((h, w), np.uint8)
+        self._check(lib().svo_get_pyramid_plane(self._h, item, octave, side, _vp(out)))
+        return out
+
+    def keypoints(self, slot=0, which=0, side=0, octave=0):
         out = np.zeros(self.kp_cap, KEYPOINT)
-        n = self._check(lib().svo_get_keypoints(self._h, slot, which, side, _vp(out), self.kp_cap))
+        n = self._check(lib().svo_get_keypoints_oct(self._h, slot, octave, which, side, _vp(out), self.kp_cap))
         return out[:n].copy()
 
-    def descriptors(self, slot=0, which=0, side=0):
+    def descriptors(self, slot=0, which=0, side=0, octave=0):
         out = np.zeros((self.kp_cap, 32), np.uint8)
-        n = self._check(lib().svo_get_descriptors(self._h, slot, which, side, _vp(out), self.kp_cap))
+        n = self._check(lib().svo_get_descriptors_oct(self._h, slot, octave, which, side, _vp(out), self.kp_cap))
         return out[:n].copy()
 
-    def matches(self, slot=0, which=0):
+    def matches(self, slot=0, which=0, octave=0):
         out = np.zeros(self.kp_cap, DMATCH)
-        n = self._check(lib().svo_get_matches(self._h, slot, which, _vp(out), self.kp_cap))
+        n = self._check(lib().svo_get_matches_oct(self._h, slot, octave, which, _vp(out), self.kp_cap))
         return out[:n].copy()
 
-    def match_ids(self, slot=0, which=0):
+    def match_ids(self, slot=0, which=0, octave=0):
         out = np.zeros(self.kp_cap, np.int64)
-        n = self._check(lib().svo_get_match_ids(self._h, slot, which, _vp(out), self.kp_cap))
+        n = self._check(lib().svo_get_match_ids_oct(self._h, slot, octave, which, _vp(out), self.kp_cap))
         return out[:n].copy()
 
-    def tracked_pairs(self, slot=0):
+    def tracked_pairs(self, slot=0, octave=0):
         out = np.zeros((self.kp_cap, 2), np.int64)
-        n = self._check(lib().svo_get_tracked_pairs(self._h, slot, _vp(out), self.kp_cap))
+        n = self._check(lib().svo_get_tracked_pairs_oct(self._h, slot, octave, _vp(out), self.kp_cap))
         return out[:n].copy()
 
     def residuals(self, slot=0):

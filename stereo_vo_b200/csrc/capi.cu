@@ -36,11 +36,27 @@ enum { kMaxChunks = 8, kDefaultChunks = 2, kMinChunkItems = 32 };
 enum { kDepth = 3 };   // batches in flight (svo_submit_batch / svo_wait_batch): with three staging buffers the copy stream
                        // never waits for the host to see a batch finish before the next upload can start
 
+// octave k >= 1 of a multi-octave context (octave 0 lives in svo_ctx::P / RS and reads the caller's images)
+struct OctaveCtx {
+    Pools P;
+    RansacScratch RS;
+    int W = 0, H = 0, pitch = 0;
+    uint8_t* imgL = nullptr;      // [n_slots_alloc][pitch * H] pyramid planes of the running step
+    uint8_t* imgR = nullptr;
+};
+
 struct svo_ctx {
     svo_config cfg;
     Pools P;
     GnScratch G;
     RansacScratch RS;
+    // params_rectify.nOctaves > 1: per-octave pools, and the pools / scratch of the flattened stage-5 problem
+    // (kp_cap = sum of the octaves' capacities).  With one octave PG == P and GG == G.
+    int n_oct = 1;
+    OctaveCtx oct[kMaxOctaves];
+    Pools PG;
+    GnScratch GG;
+    OctaveList OL;
     cudaStream_t stream = nullptr;
     std::vector<void*> dev_allocs;
     std::vector<void*> host_allocs;
@@ -157,6 +173,54 @@ __global__ void reset_slot_kernel(Pools P, int slot) {
 bool valid_slot(const svo_ctx* c, int slot) { return slot >= 0 && slot < c->cfg.max_seqs; }
 
 
+// nOctaves > 1 (stage1_rectify.cpp:80-83, stage2_detect.cpp:423-624, stage3_match_left_right.cpp:87-177,
+// stage4_match_consecutive.cpp:91-328): after the prev/cur shift and the cross-octave ID renumbering, stages 2-4 run
+// octave by octave -- octave k > 0 on the image the pyramid kernel derives from octave k-1 -- with the match-ID
+// generator and the tracking counters carried through the shared slot state in octave order; the last octave's
+// consistency kernel applies the bad-tracking gate to the total; stage 5 then runs once on the flattened lists.
+// P0 / RS0: octave 0's pools with the slot list already advanced to item a.
+int enqueue_octaves(svo_ctx* c, const Pools& P0, const RansacScratch& RS0, int a, int n, const uint8_t* d_left,
+                    const uint8_t* d_right, size_t stride, size_t image_pitch, cudaStream_t st, int& L) {
+    CU(c, launch_reset_ids_octaves(P0, c->OL, n, st, &L));
+    const size_t img2 = 2 * (size_t)a;
+    const uint8_t* srcL = d_left + a * image_pitch;
+    const uint8_t* srcR = d_right + a * image_pitch;
+    size_t src_stride = stride, src_pitch = image_pitch;
+    int sw = c->cfg.width, sh = c->cfg.height;
+    for (int k = 0; k < c->n_oct; ++k) {
+        Pools P = k == 0 ? P0 : c->oct[k].P;
+        RansacScratch RS = k == 0 ? RS0 : c->oct[k].RS;
+        P.slots = P0.slots;
+        RS.slots = P0.slots;
+        int pitch_k = c->pitch;
+        if (k > 0) {
+            OctaveCtx& o = c->oct[k];
+            const size_t plane = (size_t)o.pitch * o.H;
+            PyramidArgs A;
+            A.srcL = srcL; A.srcR = srcR; A.src_stride = src_stride; A.src_image_pitch = src_pitch;
+            A.dstL = o.imgL + a * plane; A.dstR = o.imgR + a * plane; A.dst_stride = (size_t)o.pitch; A.dst_image_pitch = plane;
+            A.sw = sw; A.sh = sh;
+            CU(c, launch_pyramid_level(A, n, pyramid_method(c->cfg.pyr_mode, sw), st, &L));
+            srcL = A.dstL; srcR = A.dstR; src_stride = (size_t)o.pitch; src_pitch = plane;
+            sw = o.W; sh = o.H;
+            pitch_k = o.pitch;
+        }
+        CU(c, launch_detect(P, n, srcL, srcR, src_stride, src_pitch, pitch_k, c->d_occ + img2 * c->occ_words, c->occ_words,
+                            c->d_sort_scratch + img2 * c->cfg.max_corners,
+                            c->d_list_scratch + img2 * 3 * (c->cfg.max_corners / 16 + 2),
+                            c->d_key_scratch + img2 * c->cfg.max_corners, st, &L, nullptr));
+        CU(c, launch_match_lr(P, n, st, &L, nullptr));
+        CU(c, launch_track_match(P, n, st, &L, nullptr));
+        if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, RS, n, st, &L, nullptr));
+        CU(c, launch_consistency(P, n, st, &L, nullptr));
+    }
+    Pools PG = c->PG;
+    PG.slots = P0.slots;
+    CU(c, launch_flatten_octaves(PG, c->GG, c->OL, n, st, &L));
+    CU(c, launch_gn(PG, c->GG, n, GN_FLATTENED, /*custom pose=*/0, /*assume_fast_kps=*/0, st, &L, nullptr));
+    return SVO_OK;
+}
+
 // enqueue the kernels of one pipeline step for the batch items [a, a + n) on stream st
 int enqueue_items(svo_ctx* c, int a, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride, size_t image_pitch,
                   bool have_repeat, cudaStream_t st, int& L, StepTimer* t) {
@@ -170,6 +234,7 @@ int enqueue_items(svo_ctx* c, int a, int n, const uint8_t* d_left, const uint8_t
     if (t) t->mark(st);
     L += 2;
     const size_t img2 = 2 * (size_t)a;              // scratch indexed by (item, side)
+    if (c->n_oct > 1) return enqueue_octaves(c, P, RS, a, n, d_left, d_right, stride, image_pitch, st, L);
     CU(c, launch_detect(P, n, d_left + a * image_pitch, d_right + a * image_pitch, stride, image_pitch, c->pitch,
                         c->d_occ + img2 * c->occ_words, c->occ_words, c->d_sort_scratch + img2 * c->cfg.max_corners,
                         c->d_list_scratch + img2 * 3 * (c->cfg.max_corners / 16 + 2),
@@ -179,7 +244,7 @@ int enqueue_items(svo_ctx* c, int a, int n, const uint8_t* d_left, const uint8_t
     if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, RS, n, st, &L, t));
     else if (t) { t->mark(st); t->mark(st); }
     CU(c, launch_consistency(P, n, st, &L, t));
-    CU(c, launch_gn(P, c->G, n, /*external=*/0, /*custom pose=*/0, /*assume_fast_kps=*/1, st, &L, t));
+    CU(c, launch_gn(P, c->G, n, GN_FROM_TRACKED, /*custom pose=*/0, /*assume_fast_kps=*/1, st, &L, t));
     return SVO_OK;
 }
 
@@ -194,7 +259,7 @@ int run_step(svo_ctx* c, int n, const uint8_t* d_left, const uint8_t* d_right, s
     L = 0;
     StepTimer tm;
     if (c->timing && !c->ev.empty()) tm.ev = c->ev.data() + (size_t)(c->timed_steps % KT_DEPTH) * (KT_COUNT + 1);
-    StepTimer* t = tm.ev ? &tm : nullptr;
+    StepTimer* t = (tm.ev && c->n_oct == 1) ? &tm : nullptr;      // the per-kernel event set describes the one-octave step
     int chunks = std::min(c->chunks, n / kMinChunkItems);
     if (t || chunks < 2) {
         int rc = enqueue_items(c, 0, n, d_left, d_right, stride, image_pitch, have_repeat, c->stream, L, t);
@@ -280,6 +345,31 @@ PrepareArgs prepare_args(const svo_ctx* c, const uint8_t* srcL, const uint8_t* s
     return A;
 }
 
+// kps_to_detect[] of stage2_detect.cpp:404-407
+void octave_quotas(int orb_nfeats, int n_oct, int* q) {
+    q[0] = (int)(size_t)((double)((size_t)orb_nfeats * (2 * (size_t)n_oct)) / (std::pow(2.0, n_oct) - 1.0));
+    for (int k = 1; k < n_oct; ++k) q[k] = (int)(size_t)std::round((double)q[0] / std::pow(2.0, k));
+}
+
+// the per-(slot, buffer, side) arrays of one octave k >= 1 (octave 0's are allocated in svo_create)
+cudaError_t alloc_octave_arrays(svo_ctx* c, Pools& P, size_t S, size_t plane, size_t cap) {
+    cudaError_t e;
+#define OA(ptr, count) do { if ((e = dalloc(c, &(ptr), (count))) != cudaSuccess) return e; } while (0)
+    OA(P.blur, S * 2 * plane); OA(P.score, S * 2 * plane);
+    OA(P.cand_pos, S * 2 * (size_t)P.p.max_corners); OA(P.n_cand, S * 2);
+    OA(P.kp, S * 4 * cap); OA(P.desc, S * 4 * cap * 2); OA(P.n_kp, S * 4);
+    OA(P.match, S * 2 * cap); OA(P.n_match, S * 2); OA(P.mdesc, S * 4 * cap * 2); OA(P.match_id, S * 2 * cap);
+    OA(P.lr_best, S * cap); OA(P.tr_best, S * 2 * cap); OA(P.tcand, S * cap); OA(P.n_tcand, S);
+    OA(P.inl, S * 2 * cap); OA(P.n_inl, S * 2); OA(P.tracked, S * cap); OA(P.n_tracked, S);
+#undef OA
+    return cudaSuccess;
+}
+
+const Pools* octave_pools(const svo_ctx* c, int octave) {
+    if (octave < 0 || octave >= c->n_oct) return nullptr;
+    return octave == 0 ? &c->P : &c->oct[octave].P;
+}
+
 }  // namespace
 
 extern "C" {
@@ -318,6 +408,8 @@ void svo_default_config(svo_config* cfg) {
     cfg->ifm_win_w = 20;
     cfg->ifm_win_h = 20;
     cfg->orb_max_distance = 40.0;
+    cfg->n_octaves = 1;                  // SURVEY Appendix C (the reference's ctor default is 3, stage1_rectify.cpp:28)
+    cfg->pyr_mode = 0;                   // as MRPT picks: 2x2 average when width % 16 == 0, cvPyrDown otherwise
 }
 
 const char* svo_last_error(const svo_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -338,7 +430,17 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     if (cfg->ifm_win_w < 0 || cfg->ifm_win_h < 0 || cfg->ifm_win_w > kMaxImgDim || cfg->ifm_win_h > kMaxImgDim)
         return fail(nullptr, SVO_ERR_ARG, "ifm_win_w / ifm_win_h out of range");
     if (!(cfg->orb_max_distance >= 0 && cfg->orb_max_distance < 65536)) return fail(nullptr, SVO_ERR_ARG, "orb_max_distance out of range");
-    const int quota = 2 * cfg->orb_nfeats;    // size_t(orb_nfeats*(2*nOctaves)/(2^nOctaves-1)), nOctaves = 1
+    const int n_oct = cfg->n_octaves;
+    if (n_oct < 1 || n_oct > kMaxOctaves) return fail(nullptr, SVO_ERR_ARG, "n_octaves must be within [1, 4]");
+    if (cfg->pyr_mode < 0 || cfg->pyr_mode > 2) return fail(nullptr, SVO_ERR_ARG, "pyr_mode must be 0 (as MRPT), 1 (2x2 average) or 2 (pyrDown)");
+    if (n_oct > 1 && (cfg->match_method != 0 || cfg->if_match_method != 0))
+        return fail(nullptr, SVO_ERR_ARG, "n_octaves > 1 is built for smDescBF / ifmDescBF only");
+    if ((cfg->width >> (n_oct - 1)) < 64 || (cfg->height >> (n_oct - 1)) < 64)
+        return fail(nullptr, SVO_ERR_ARG, "the smallest octave must be at least 64 x 64");
+    int quotas[kMaxOctaves];
+    octave_quotas(cfg->orb_nfeats, n_oct, quotas);    // kps_to_detect[], stage2_detect.cpp:404-407
+    const int quota = quotas[0];                      // 2 * orb_nfeats for nOctaves = 1
+    if (quota < 1 || quotas[n_oct - 1] < 1) return fail(nullptr, SVO_ERR_ARG, "orb_nfeats too small for n_octaves");
     const int kp_cap = cfg->non_maximal_suppression ? std::min(quota, cfg->max_corners) : cfg->max_corners;
     if (kp_cap > 65535) return fail(nullptr, SVO_ERR_ARG, "more than 65535 keypoints per image are not supported");
     if (cfg->max_corners >= (1 << 24)) return fail(nullptr, SVO_ERR_ARG, "max_corners too large");
@@ -386,6 +488,9 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     DA(P.lr_best, S * cap); DA(P.tr_best, S * 2 * cap); DA(P.tcand, S * cap); DA(P.n_tcand, S);
     DA(P.inl, S * 2 * cap); DA(P.n_inl, S * 2); DA(P.tracked, S * cap); DA(P.n_tracked, S);
     DA(P.residual, S * cap); DA(P.outliers, S * cap); DA(P.slots, S);
+    DA(P.oct_stats, (size_t)S * kMaxOctaves * 4);
+    P.octave = 0; P.n_octaves = n_oct;
+    c->n_oct = n_oct;
     for (int b = 0; b < kDepth; ++b) { DA(c->d_stL[b], (size_t)S * plane); DA(c->d_stR[b], (size_t)S * plane); }
     c->d_stageL = c->d_stL[0]; c->d_stageR = c->d_stR[0];
     DA(c->d_repeat, S); DA(c->d_cams_batch, S);
@@ -411,6 +516,48 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
         if (e2 != cudaSuccess) { int rc = cuda_fail(nullptr, e2, "alloc_ransac"); svo_destroy(c); return rc; }
         c->RS.slots = P.slots; c->RS.inl = P.inl; c->RS.n_inl = P.n_inl;
     }
+    // octaves 1..n-1: own frame arrays and pyramid planes; state / result / cam / slots / stats are shared with octave 0
+    c->PG = c->P; c->GG = c->G;
+    {
+        OctaveList& OL = c->OL;
+        memset(&OL, 0, sizeof(OL));
+        OL.n = n_oct;
+        size_t total_cap = cap;
+        for (int k = 1; k < n_oct; ++k) {
+            OctaveCtx& o = c->oct[k];
+            o.W = cfg->width >> k; o.H = cfg->height >> k; o.pitch = (o.W + 15) & ~15;
+            o.P = c->P;
+            o.P.octave = k;
+            o.P.p.W = o.W; o.P.p.H = o.H; o.P.p.quota = quotas[k];
+            o.P.p.kp_cap = cfg->non_maximal_suppression ? std::min(quotas[k], cfg->max_corners) : cfg->max_corners;
+            o.P.residual = nullptr; o.P.outliers = nullptr;        // stage 5 runs on the flattened problem only
+            const size_t plane_k = (size_t)o.pitch * o.H;
+            cudaError_t e2 = alloc_octave_arrays(c, o.P, S, plane_k, (size_t)o.P.p.kp_cap);
+            if (e2 == cudaSuccess) e2 = dalloc(c, &o.imgL, (size_t)S * plane_k);
+            if (e2 == cudaSuccess) e2 = dalloc(c, &o.imgR, (size_t)S * plane_k);
+            if (e2 != cudaSuccess) { int rc = cuda_fail(nullptr, e2, "cudaMalloc octave arrays"); svo_destroy(c); return rc; }
+            o.RS = c->RS;
+            o.RS.kp_cap = o.P.p.kp_cap; o.RS.inl = o.P.inl; o.RS.n_inl = o.P.n_inl;
+            total_cap += (size_t)o.P.p.kp_cap;
+        }
+        for (int k = 0; k < n_oct; ++k) {
+            const Pools& Pk = *octave_pools(c, k);
+            OL.cap[k] = Pk.p.kp_cap; OL.kp[k] = Pk.kp; OL.match[k] = Pk.match; OL.n_match[k] = Pk.n_match;
+            OL.match_id[k] = Pk.match_id; OL.tracked[k] = Pk.tracked; OL.n_tracked[k] = Pk.n_tracked;
+        }
+        if (n_oct > 1) {
+            if (total_cap > 65535) { svo_destroy(c); return fail(nullptr, SVO_ERR_ARG, "more than 65535 keypoints over all octaves are not supported"); }
+            Pools& PG = c->PG;
+            GnScratch& GG = c->GG;
+            PG.p.kp_cap = (int)total_cap;
+            PG.tracked = nullptr;                      // GN_FLATTENED reads GnScratch::cur_idx instead
+            DA(PG.n_tracked, S); DA(PG.residual, S * total_cap); DA(PG.outliers, S * total_cap);
+            DA(GG.prev, S * total_cap); DA(GG.obs, S * total_cap); DA(GG.lmk, S * total_cap * 3); DA(GG.mask, S * total_cap);
+            DA(GG.cur_idx, S * total_cap); DA(GG.ini_pose, S * 6);
+            DA(GG.occ, (size_t)S * 2 * c->occ_words);      // own grid: stage 5 of one group may overlap stage 2 of another
+            GG.residual = PG.residual;
+        }
+    }
     HA(c->h_slots, S); HA(c->h_repeat, S); HA(c->h_cams, S); HA(c->h_results, S);
     for (int b = 0; b < kDepth; ++b) { HA(c->r_slots[b], S); HA(c->r_repeat[b], S); HA(c->r_cams[b], S); HA(c->r_res[b], S); HA(c->r_state[b], S); }
 #undef DA
@@ -428,7 +575,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     }
     if (e != cudaSuccess) { int rc = cuda_fail(nullptr, e, "cudaStreamCreate"); svo_destroy(c); return rc; }
     if ((e = configure_detect(p)) != cudaSuccess || (e = configure_match(p)) != cudaSuccess ||
-        (e = configure_gn(p)) != cudaSuccess || (e = configure_ransac(kp_cap)) != cudaSuccess) {
+        (e = configure_gn(c->PG.p)) != cudaSuccess || (e = configure_ransac(kp_cap)) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "kernel configuration (shared memory)");
         svo_destroy(c);
         return rc;
@@ -757,17 +904,23 @@ int svo_process_pair(svo_ctx* c, const uint8_t* left, const uint8_t* right, size
 
 // ---- readers -------------------------------------------------------------------------------------
 int svo_get_keypoints(svo_ctx* c, int32_t slot, int32_t which, int32_t side, svo_keypoint* out, int32_t cap) {
+    return svo_get_keypoints_oct(c, slot, 0, which, side, out, cap);
+}
+
+int svo_get_keypoints_oct(svo_ctx* c, int32_t slot, int32_t octave, int32_t which, int32_t side, svo_keypoint* out, int32_t cap) {
     if (!c) return SVO_ERR_ARG;
     if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (which | 1) != 1 || (side | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/which/side");
+    const Pools* Pk = octave_pools(c, octave);
+    if (!Pk) return fail(c, SVO_ERR_ARG, "octave out of range");
     SlotState s;
     int rc = get_state(c, slot, &s);
     if (rc) return rc;
     if (which == 0 ? !s.has_cur : !s.has_prev) return fail(c, SVO_ERR_STATE, "frame not present");
     const size_t f = frame_idx(slot, frame_buf(s, which), side);
     int n = 0;
-    CU(c, cudaMemcpy(&n, c->P.n_kp + f, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&n, Pk->n_kp + f, sizeof(int), cudaMemcpyDeviceToHost));
     std::vector<int2> tmp(n);
-    if (n) CU(c, cudaMemcpy(tmp.data(), c->P.kp + f * c->P.p.kp_cap, n * sizeof(int2), cudaMemcpyDeviceToHost));
+    if (n) CU(c, cudaMemcpy(tmp.data(), Pk->kp + f * Pk->p.kp_cap, n * sizeof(int2), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n && i < cap; ++i) {
         svo_keypoint k;
         k.x = (float)(tmp[i].x & 0xFFFF); k.y = (float)((unsigned)tmp[i].x >> 16);
@@ -778,32 +931,44 @@ int svo_get_keypoints(svo_ctx* c, int32_t slot, int32_t which, int32_t side, svo
 }
 
 int svo_get_descriptors(svo_ctx* c, int32_t slot, int32_t which, int32_t side, uint8_t* out, int32_t cap_rows) {
+    return svo_get_descriptors_oct(c, slot, 0, which, side, out, cap_rows);
+}
+
+int svo_get_descriptors_oct(svo_ctx* c, int32_t slot, int32_t octave, int32_t which, int32_t side, uint8_t* out, int32_t cap_rows) {
     if (!c) return SVO_ERR_ARG;
     if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (which | 1) != 1 || (side | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/which/side");
+    const Pools* Pk = octave_pools(c, octave);
+    if (!Pk) return fail(c, SVO_ERR_ARG, "octave out of range");
     SlotState s;
     int rc = get_state(c, slot, &s);
     if (rc) return rc;
     if (which == 0 ? !s.has_cur : !s.has_prev) return fail(c, SVO_ERR_STATE, "frame not present");
     const size_t f = frame_idx(slot, frame_buf(s, which), side);
     int n = 0;
-    CU(c, cudaMemcpy(&n, c->P.n_kp + f, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&n, Pk->n_kp + f, sizeof(int), cudaMemcpyDeviceToHost));
     const int m = std::min(n, cap_rows);
-    if (m > 0) CU(c, cudaMemcpy(out, c->P.desc + f * c->P.p.kp_cap * 2, (size_t)m * 32, cudaMemcpyDeviceToHost));
+    if (m > 0) CU(c, cudaMemcpy(out, Pk->desc + f * Pk->p.kp_cap * 2, (size_t)m * 32, cudaMemcpyDeviceToHost));
     return n;
 }
 
 int svo_get_matches(svo_ctx* c, int32_t slot, int32_t which, svo_dmatch* out, int32_t cap) {
+    return svo_get_matches_oct(c, slot, 0, which, out, cap);
+}
+
+int svo_get_matches_oct(svo_ctx* c, int32_t slot, int32_t octave, int32_t which, svo_dmatch* out, int32_t cap) {
     if (!c) return SVO_ERR_ARG;
     if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (which | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/which");
+    const Pools* Pk = octave_pools(c, octave);
+    if (!Pk) return fail(c, SVO_ERR_ARG, "octave out of range");
     SlotState s;
     int rc = get_state(c, slot, &s);
     if (rc) return rc;
     if (which == 0 ? !s.has_cur : !s.has_prev) return fail(c, SVO_ERR_STATE, "frame not present");
     const size_t pi = pair_idx(slot, frame_buf(s, which));
     int n = 0;
-    CU(c, cudaMemcpy(&n, c->P.n_match + pi, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&n, Pk->n_match + pi, sizeof(int), cudaMemcpyDeviceToHost));
     std::vector<int4> tmp(n);
-    if (n) CU(c, cudaMemcpy(tmp.data(), c->P.match + pi * c->P.p.kp_cap, n * sizeof(int4), cudaMemcpyDeviceToHost));
+    if (n) CU(c, cudaMemcpy(tmp.data(), Pk->match + pi * Pk->p.kp_cap, n * sizeof(int4), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n && i < cap; ++i) {
         svo_dmatch m = {tmp[i].x, tmp[i].y, 0, (float)tmp[i].z};
         out[i] = m;
@@ -812,8 +977,14 @@ int svo_get_matches(svo_ctx* c, int32_t slot, int32_t which, svo_dmatch* out, in
 }
 
 int svo_get_match_ids(svo_ctx* c, int32_t slot, int32_t which, int64_t* out, int32_t cap) {
+    return svo_get_match_ids_oct(c, slot, 0, which, out, cap);
+}
+
+int svo_get_match_ids_oct(svo_ctx* c, int32_t slot, int32_t octave, int32_t which, int64_t* out, int32_t cap) {
     if (!c) return SVO_ERR_ARG;
     if (!valid_slot(c, slot) || (which | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/which");
+    const Pools* Pk = octave_pools(c, octave);
+    if (!Pk) return fail(c, SVO_ERR_ARG, "octave out of range");
     if (!c->cfg.vo_use_matches_ids) return 0;
     SlotState s;
     int rc = get_state(c, slot, &s);
@@ -821,10 +992,10 @@ int svo_get_match_ids(svo_ctx* c, int32_t slot, int32_t which, int64_t* out, int
     if (which == 0 ? !s.has_cur : !s.has_prev) return fail(c, SVO_ERR_STATE, "frame not present");
     const size_t pi = pair_idx(slot, frame_buf(s, which));
     int n = 0;
-    CU(c, cudaMemcpy(&n, c->P.n_match + pi, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&n, Pk->n_match + pi, sizeof(int), cudaMemcpyDeviceToHost));
     const int m = std::min(n, cap);
     static_assert(sizeof(long long) == sizeof(int64_t), "");
-    if (m > 0) CU(c, cudaMemcpy(out, c->P.match_id + pi * c->P.p.kp_cap, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    if (m > 0) CU(c, cudaMemcpy(out, Pk->match_id + pi * Pk->p.kp_cap, (size_t)m * 8, cudaMemcpyDeviceToHost));
     return n;
 }
 
@@ -892,13 +1063,19 @@ int svo_set_max_match_id(svo_ctx* c, int32_t slot, int64_t id) {
 }
 
 int svo_get_tracked_pairs(svo_ctx* c, int32_t slot, int64_t* out_pairs, int32_t cap) {
+    return svo_get_tracked_pairs_oct(c, slot, 0, out_pairs, cap);
+}
+
+int svo_get_tracked_pairs_oct(svo_ctx* c, int32_t slot, int32_t octave, int64_t* out_pairs, int32_t cap) {
     if (!c) return SVO_ERR_ARG;
     if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    const Pools* Pk = octave_pools(c, octave);
+    if (!Pk) return fail(c, SVO_ERR_ARG, "octave out of range");
     CU(c, cudaStreamSynchronize(c->stream));
     int n = 0;
-    CU(c, cudaMemcpy(&n, c->P.n_tracked + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(&n, Pk->n_tracked + slot, sizeof(int), cudaMemcpyDeviceToHost));
     std::vector<int2> tmp(n);
-    if (n) CU(c, cudaMemcpy(tmp.data(), c->P.tracked + (size_t)slot * c->P.p.kp_cap, n * sizeof(int2), cudaMemcpyDeviceToHost));
+    if (n) CU(c, cudaMemcpy(tmp.data(), Pk->tracked + (size_t)slot * Pk->p.kp_cap, n * sizeof(int2), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n && i < cap; ++i) { out_pairs[2 * i] = tmp[i].x; out_pairs[2 * i + 1] = tmp[i].y; }
     return n;
 }
@@ -910,7 +1087,7 @@ int svo_get_residuals(svo_ctx* c, int32_t slot, double* out, int32_t cap) {
     Result r;
     CU(c, cudaMemcpy(&r, c->P.result + slot, sizeof(Result), cudaMemcpyDeviceToHost));
     const int m = std::min(r.n_residuals, cap);
-    if (m > 0) CU(c, cudaMemcpy(out, c->P.residual + (size_t)slot * c->P.p.kp_cap, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    if (m > 0) CU(c, cudaMemcpy(out, c->PG.residual + (size_t)slot * c->PG.p.kp_cap, (size_t)m * 8, cudaMemcpyDeviceToHost));
     return r.n_residuals;
 }
 
@@ -921,7 +1098,7 @@ int svo_get_outliers(svo_ctx* c, int32_t slot, int64_t* out, int32_t cap) {
     Result r;
     CU(c, cudaMemcpy(&r, c->P.result + slot, sizeof(Result), cudaMemcpyDeviceToHost));
     std::vector<int32_t> tmp(r.n_outliers);
-    if (r.n_outliers) CU(c, cudaMemcpy(tmp.data(), c->P.outliers + (size_t)slot * c->P.p.kp_cap, r.n_outliers * 4, cudaMemcpyDeviceToHost));
+    if (r.n_outliers) CU(c, cudaMemcpy(tmp.data(), c->PG.outliers + (size_t)slot * c->PG.p.kp_cap, r.n_outliers * 4, cudaMemcpyDeviceToHost));
     for (int i = 0; i < r.n_outliers && i < cap; ++i) out[i] = tmp[i];
     return r.n_outliers;
 }
@@ -949,6 +1126,35 @@ int svo_get_track_candidates(svo_ctx* c, int32_t slot, int32_t* out_query, int32
         if (out_inlR) out_inlR[i] = ir[i];
     }
     return n;
+}
+
+int svo_get_octave_info(svo_ctx* c, int32_t octave, int32_t* out4) {
+    if (!c || !out4) return SVO_ERR_ARG;
+    const Pools* Pk = octave_pools(c, octave);
+    if (!Pk) return fail(c, SVO_ERR_ARG, "octave out of range");
+    out4[0] = Pk->p.W; out4[1] = Pk->p.H; out4[2] = Pk->p.quota; out4[3] = Pk->p.kp_cap;
+    return c->n_oct;
+}
+
+int svo_get_octave_stats(svo_ctx* c, int32_t slot, int32_t* out, int32_t cap_octaves) {
+    if (!c || !out) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    CU(c, cudaStreamSynchronize(c->stream));
+    int32_t tmp[kMaxOctaves * 4];
+    CU(c, cudaMemcpy(tmp, c->P.oct_stats + stat_idx(slot, 0, 0), sizeof(tmp), cudaMemcpyDeviceToHost));
+    const int n = std::min(c->n_oct, (int)cap_octaves);
+    for (int i = 0; i < n * 4; ++i) out[i] = tmp[i];
+    return c->n_oct;
+}
+
+int svo_get_pyramid_plane(svo_ctx* c, int32_t item, int32_t octave, int32_t side, uint8_t* out) {
+    if (!c || !out) return SVO_ERR_ARG;
+    if (octave < 1 || octave >= c->n_oct || item < 0 || item >= c->cfg.max_seqs || (side | 1) != 1) return fail(c, SVO_ERR_ARG, "bad item/octave/side");
+    CU(c, cudaStreamSynchronize(c->stream));
+    const OctaveCtx& o = c->oct[octave];
+    const uint8_t* src = (side ? o.imgR : o.imgL) + (size_t)item * o.pitch * o.H;
+    CU(c, cudaMemcpy2D(out, o.W, src, o.pitch, o.W, o.H, cudaMemcpyDeviceToHost));
+    return SVO_OK;
 }
 
 int svo_get_plane(svo_ctx* c, int32_t slot, int32_t side, int32_t plane, uint8_t* out) {
@@ -1075,8 +1281,8 @@ int svo_get_change_in_pose(svo_ctx* c, int32_t slot, const int64_t* tracked_pair
     if (!c) return SVO_ERR_ARG;
     if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
     if (!cam || !result || n_tracked < 0) return fail(c, SVO_ERR_ARG, "NULL argument");
-    const int kc = c->P.p.kp_cap;
-    if (n_tracked > kc) return fail(c, SVO_ERR_ARG, "more tracked pairs than the context's capacity (2*orb_nfeats)");
+    const int kc = c->PG.p.kp_cap;      // with n_octaves > 1: the capacity of the flattened problem
+    if (n_tracked > kc) return fail(c, SVO_ERR_ARG, "more tracked pairs than the context's capacity");
     CU(c, cudaSetDevice(c->cfg.device));
     // S5:419-461 on the host side of the seam: flatten the index chains into four point lists
     std::vector<float4> prev(n_tracked), obs(n_tracked);
@@ -1100,22 +1306,22 @@ int svo_get_change_in_pose(svo_ctx* c, int32_t slot, const int64_t* tracked_pair
     if (rc) return rc;
     const size_t base = (size_t)slot * kc;
     if (n_tracked) {
-        CU(c, cudaMemcpyAsync(c->G.prev + base, prev.data(), n_tracked * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemcpyAsync(c->G.obs + base, obs.data(), n_tracked * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemcpyAsync(c->G.cur_idx + base, cur_idx.data(), n_tracked * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->GG.prev + base, prev.data(), n_tracked * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->GG.obs + base, obs.data(), n_tracked * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->GG.cur_idx + base, cur_idx.data(), n_tracked * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    CU(c, cudaMemcpyAsync(c->P.n_tracked + slot, &n_tracked, 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->PG.n_tracked + slot, &n_tracked, 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->P.cam + slot, cam, sizeof(Camera), cudaMemcpyHostToDevice, c->stream));
     double ini[6] = {0, 0, 0, 0, 0, 0};
     if (use_custom_initial_pose && ini_estimation) memcpy(ini, ini_estimation, sizeof(ini));
-    CU(c, cudaMemcpyAsync(c->G.ini_pose + (size_t)slot * 6, ini, sizeof(ini), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->GG.ini_pose + (size_t)slot * 6, ini, sizeof(ini), cudaMemcpyHostToDevice, c->stream));
     // a fresh TStereoOdometryResult (libstereo-odometry.h:251-263)
     Result zero;
     memset(&zero, 0, sizeof(zero));
     CU(c, cudaMemcpyAsync(c->P.result + slot, &zero, sizeof(zero), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     int L = 0;
-    CU(c, launch_gn(c->P, c->G, 1, /*external=*/1, use_custom_initial_pose ? 1 : 0, /*assume_fast_kps=*/0, c->stream, &L));
+    CU(c, launch_gn(c->PG, c->GG, 1, GN_EXTERNAL, use_custom_initial_pose ? 1 : 0, /*assume_fast_kps=*/0, c->stream, &L));
     c->launches += L;
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaMemcpy(result, c->P.result + slot, sizeof(Result), cudaMemcpyDeviceToHost));

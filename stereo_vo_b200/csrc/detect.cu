@@ -563,7 +563,10 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
     }
     if (tid == 0) {
         P.n_kp[frame_idx(slot, cur, side)] = n_sel;
-        if (side == 0) P.result[slot].detected_left = n_sel; else P.result[slot].detected_right = n_sel;
+        P.oct_stats[stat_idx(slot, P.octave, side)] = n_sel;
+        if (P.octave == 0) {                     // svo_result mirrors detected_feats[0]
+            if (side == 0) P.result[slot].detected_left = n_sel; else P.result[slot].detected_right = n_sel;
+        }
     }
 }
 

@@ -392,7 +392,7 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
     const size_t base = (size_t)slot * cap;
     const Camera cam = P.cam[slot];
 
-    if (!external) {
+    if (external != GN_EXTERNAL) {
         if (!st.has_prev) return;               // voecFirstIteration already reported (P:348-352)
         if (st.m_error == 5) return;            // voecBadTracking: stage 5 is skipped (P:332)
     }
@@ -400,7 +400,7 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
     const int cur = st.cur, prev = cur ^ 1;
 
     // ---- S5:419-461: gather the four point lists ----------------------------------------------------
-    if (!external) {
+    if (external == GN_FROM_TRACKED) {
         const int4* mp = P.match + pair_idx(slot, prev) * cap;
         const int4* mc = P.match + pair_idx(slot, cur) * cap;
         const int2* kpl = P.kp + frame_idx(slot, prev, 0) * cap;
@@ -627,6 +627,48 @@ cudaError_t launch_project(const int4* d_matches, const float2* d_left, const fl
                            const Camera& cam, const double* d_pose, float4* d_out, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     project_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_matches, d_left, d_right, d_order, n, cam, d_pose, d_out);
+    return cudaGetLastError();
+}
+
+// S5:419-461 for nOctaves > 1: one CTA per slot walks the octaves in order and appends their tracked pairs, keypoint
+// coordinates multiplied by scale_norm = 2^octave (float x size_t, exact for FAST's integer coordinates).
+__global__ void __launch_bounds__(256)
+flatten_octaves_kernel(Pools PG, GnScratch G, OctaveList O) {
+    const int slot = PG.slots[blockIdx.x];
+    const SlotState& st = PG.state[slot];
+    if (!st.has_prev) { if (threadIdx.x == 0) PG.n_tracked[slot] = 0; return; }
+    const int cur = st.cur, prev = cur ^ 1;
+    const size_t base = (size_t)slot * PG.p.kp_cap;
+    int off = 0;
+    for (int k = 0; k < O.n; ++k) {
+        const size_t cap = (size_t)O.cap[k];
+        const int T = O.n_tracked[k][slot];
+        const int2* __restrict__ tr = O.tracked[k] + (size_t)slot * cap;
+        const int4* __restrict__ mp = O.match[k] + pair_idx(slot, prev) * cap;
+        const int4* __restrict__ mc = O.match[k] + pair_idx(slot, cur) * cap;
+        const int2* __restrict__ kpl = O.kp[k] + frame_idx(slot, prev, 0) * cap;
+        const int2* __restrict__ kpr = O.kp[k] + frame_idx(slot, prev, 1) * cap;
+        const int2* __restrict__ kcl = O.kp[k] + frame_idx(slot, cur, 0) * cap;
+        const int2* __restrict__ kcr = O.kp[k] + frame_idx(slot, cur, 1) * cap;
+        const float s = (float)(1u << k);
+        for (int i = threadIdx.x; i < T; i += blockDim.x) {
+            const int2 tp = tr[i];
+            const int4 a = mp[tp.x], b = mc[tp.y];
+            const int2 pl = kpl[a.x], pr = kpr[a.y], cl = kcl[b.x], cr = kcr[b.y];
+            G.prev[base + off + i] = make_float4((float)(pl.x & 0xFFFF) * s, (float)((unsigned)pl.x >> 16) * s,
+                                                 (float)(pr.x & 0xFFFF) * s, (float)pl.y);
+            G.obs[base + off + i] = make_float4((float)(cl.x & 0xFFFF) * s, (float)((unsigned)cl.x >> 16) * s,
+                                                (float)(cr.x & 0xFFFF) * s, (float)((unsigned)cr.x >> 16) * s);
+            G.cur_idx[base + off + i] = tp.y;   // result.outliers receives tracked_pairs[octave][i].second (S5:601-610)
+        }
+        off += T;
+    }
+    if (threadIdx.x == 0) PG.n_tracked[slot] = off;
+}
+
+cudaError_t launch_flatten_octaves(const Pools& PG, const GnScratch& G, const OctaveList& O, int n, cudaStream_t st, int* launches) {
+    flatten_octaves_kernel<<<n, 256, 0, st>>>(PG, G, O);
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

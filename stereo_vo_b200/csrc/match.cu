@@ -266,7 +266,8 @@ lr_filter_kernel(Pools P) {
     }
     if (tid == 0) {
         P.n_match[pair_idx(slot, cur)] = base;
-        P.result[slot].stereo_matches = base;
+        P.oct_stats[stat_idx(slot, P.octave, 2)] = base;
+        if (P.octave == 0) P.result[slot].stereo_matches = base;   // svo_result mirrors stereo_matches[0]
     }
     // S3:67,172-173: on the first frame every kept match receives a fresh ID
     if (P.p.use_ids && !st.has_prev) {
@@ -485,7 +486,8 @@ rbr_match_kernel(Pools P) {
     }
     if (tid == 0) {
         P.n_match[pair_idx(slot, cur)] = base;
-        P.result[slot].stereo_matches = base;
+        P.oct_stats[stat_idx(slot, P.octave, 2)] = base;
+        if (P.octave == 0) P.result[slot].stereo_matches = base;   // svo_result mirrors stereo_matches[0]
     }
     if (P.p.use_ids && !st.has_prev) {           // S3:67,406-407
         long long* ids = P.match_id + pair_idx(slot, cur) * cap;
@@ -593,7 +595,7 @@ consistency_kernel(Pools P) {
     const size_t cap = (size_t)P.p.kp_cap;
     const int tid = threadIdx.x;
     if (!st.has_prev) {                      // first iteration (P:348-352)
-        if (tid == 0) { res.error_code = 4; res.valid = 0; P.n_tracked[slot] = 0; }
+        if (tid == 0) { res.error_code = 4; res.valid = 0; P.n_tracked[slot] = 0; P.oct_stats[stat_idx(slot, P.octave, 3)] = 0; }
         return;
     }
     const int n = P.n_tcand[slot];
@@ -654,13 +656,38 @@ consistency_kernel(Pools P) {
     }
     if (tid == 0) {
         P.n_tracked[slot] = base;
-        res.tracked_frame = base;
-        res.tracked_kf = kf;
-        if (base < P.p.bad_tracking_th) {    // P:326-330
+        P.oct_stats[stat_idx(slot, P.octave, 3)] = base;
+        // S4:743-752: both counters run over all octaves; begin_step_kernel zeroed them
+        const int total = res.tracked_frame + base;
+        res.tracked_frame = total;
+        res.tracked_kf += kf;
+        if (P.octave == P.n_octaves - 1 && total < P.p.bad_tracking_th) {    // P:326-330, after the last octave
             st.m_error = 5;
             res.error_code = 5;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b  reset_ids_octaves_kernel (nOctaves > 1 only): P:254-267.  After resetIds() the previous frame's match IDs of
+// ALL octaves are renumbered 0..N-1 in octave order, the generator restarts behind them and the previous frame becomes
+// the key frame.  Runs before the per-octave stage 3, so lr_filter_kernel never sees the flag in a multi-octave step.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT)
+reset_ids_octaves_kernel(Pools P, OctaveList O) {
+    const int slot = P.slots[blockIdx.x];
+    SlotState& st = P.state[slot];
+    if (!(st.reset_ids && st.has_prev)) return;          // the whole CTA decides alike: the flag is written after the barrier
+    const int prev = st.cur ^ 1;
+    long long base = 0;
+    for (int k = 0; k < O.n; ++k) {
+        const int Mp = P.p.use_ids ? O.n_match[k][pair_idx(slot, prev)] : 0;   // matches_IDs is empty without ID control
+        long long* idp = O.match_id[k] + pair_idx(slot, prev) * (size_t)O.cap[k];
+        for (int m = threadIdx.x; m < Mp; m += FT) idp[m] = base + m;
+        base += Mp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { st.last_match_id = base; st.last_kf_max_id = base - 1; st.reset_ids = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -707,6 +734,12 @@ cudaError_t launch_track_match(const Pools& P, int n, cudaStream_t st, int* laun
 cudaError_t launch_consistency(const Pools& P, int n, cudaStream_t st, int* launches, StepTimer* tm) {
     consistency_kernel<<<n, FT, P.p.kp_cap * sizeof(uint32_t), st>>>(P);
     if (tm) tm->mark(st);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reset_ids_octaves(const Pools& P, const OctaveList& O, int n, cudaStream_t st, int* launches) {
+    reset_ids_octaves_kernel<<<n, FT, 0, st>>>(P, O);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -16,6 +16,7 @@ namespace svo {
 
 constexpr int kOrbEdge = 31;        // cv::ORB edgeThreshold (border filter inside ORB::compute)
 constexpr int kMaxImgDim = 4096;    // x and y are packed in 16 bits each, grid occupancy bitmaps sized from it
+constexpr int kMaxOctaves = 4;      // params_rectify.nOctaves (reference default 3, stage1_rectify.cpp:28)
 
 struct SlotState {                  // mutable members of the estimator (libstereo-odometry.h:733-754)
     int32_t cur;                    // buffer index holding m_current_imgpair
@@ -102,6 +103,23 @@ struct Pools {
     int32_t* outliers;     // [max_seqs][kp_cap]
     // batch description of the running step
     int32_t* slots;        // [max_seqs] slot index of batch item i
+    // Octaves (params_rectify.nOctaves > 1): stages 2-4 run once per octave, each with its own Pools (own W, H, quota,
+    // kp_cap and frame arrays); state / result / cam / slots are shared by the octaves of a slot.
+    int32_t octave, n_octaves;
+    int32_t* oct_stats;    // [max_seqs][kMaxOctaves][4] detected left, detected right, stereo matches, tracked pairs
+};
+
+// The arrays of all octaves of a context, for the kernels that cross octaves: the ID renumbering of
+// process_new_image_pair.cpp:254-267 and the flattening of stage5_optimization.cpp:419-461.
+struct OctaveList {
+    int32_t n;
+    int32_t cap[kMaxOctaves];
+    const int2* kp[kMaxOctaves];
+    const int4* match[kMaxOctaves];
+    const int32_t* n_match[kMaxOctaves];
+    long long* match_id[kMaxOctaves];
+    const int2* tracked[kMaxOctaves];
+    const int32_t* n_tracked[kMaxOctaves];
 };
 
 // Optional per-kernel timing: one CUDA event is recorded on the launching stream after every kernel
@@ -115,5 +133,6 @@ struct StepTimer {
 __host__ __device__ inline size_t img_idx(int slot, int side) { return (size_t)slot * 2 + side; }
 __host__ __device__ inline size_t frame_idx(int slot, int buf, int side) { return ((size_t)slot * 2 + buf) * 2 + side; }
 __host__ __device__ inline size_t pair_idx(int slot, int buf) { return (size_t)slot * 2 + buf; }
+__host__ __device__ inline size_t stat_idx(int slot, int octave, int what) { return ((size_t)slot * kMaxOctaves + octave) * 4 + what; }
 
 }  // namespace svo

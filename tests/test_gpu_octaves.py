@@ -1,0 +1,190 @@
+"""GPU parity of the multi-octave path (params_rectify.nOctaves > 1; the reference's ctor default is 3,
+stage1_rectify.cpp:28,80-83) against the octave-aware oracle: pyramid planes, per-octave keypoints / descriptors /
+stereo matches / match IDs / tracked pairs bit-exact, the flattened stage-5 problem (x 2^octave rescale,
+stage5_optimization.cpp:419-461) within the pose tolerance north_star states (1e-4 rad, 1e-3 m)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from stereo_vo_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_RAD = 1e-4
+POSE_TOL_M = 1e-3
+
+
+def xys(k):
+    return np.stack([k["x"], k["y"], k["response"]], 1).astype(np.int32)
+
+
+def mtuple(m):
+    return np.stack([m["queryIdx"], m["trainIdx"], m["distance"].astype(np.int32)], 1)
+
+
+def ocam(cam):
+    return orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+
+
+def gcam(cam):
+    return capi.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+
+
+def device_masks(ctx):
+    """The oracle takes its two findFundamentalMat masks from the device kernel (whose bit-exactness against OpenCV is
+    the subject of tests/test_gpu_parity.py): these tests are about the octave plumbing around it."""
+    def fn(p1, p2):
+        if len(p1) < 7:
+            return None
+        return ctx.fundmat_ransac(p1, p2)[1]
+    return fn
+
+
+def check_frame(ctx, o, r, slot, i, ids):
+    n_oct = ctx.n_octaves
+    stats = ctx.octave_stats(slot)
+    for k in range(n_oct):
+        f = o["frames"][k]
+        assert np.array_equal(xys(ctx.keypoints(slot, 0, 0, octave=k)), xys(f.kpsL)), f"frame {i} octave {k}: left keypoints"
+        assert np.array_equal(xys(ctx.keypoints(slot, 0, 1, octave=k)), xys(f.kpsR)), f"frame {i} octave {k}: right keypoints"
+        assert np.array_equal(ctx.descriptors(slot, 0, 0, octave=k), f.descL), f"frame {i} octave {k}: left descriptors"
+        assert np.array_equal(ctx.descriptors(slot, 0, 1, octave=k), f.descR), f"frame {i} octave {k}: right descriptors"
+        assert np.array_equal(mtuple(ctx.matches(slot, 0, octave=k)), mtuple(f.matches)), f"frame {i} octave {k}: stereo matches"
+        assert tuple(stats[k][:3]) == (len(f.kpsL), len(f.kpsR), len(f.matches))
+        if ids:
+            assert np.array_equal(ctx.match_ids(slot, 0, octave=k), f.ids), f"frame {i} octave {k}: match IDs"
+        if "track_dbg" in o:
+            assert np.array_equal(ctx.tracked_pairs(slot, octave=k), o["tracked"][k]), f"frame {i} octave {k}: tracked pairs"
+            assert stats[k][3] == len(o["tracked"][k])
+    f0 = o["frames"][0]
+    assert (r.detected_left, r.detected_right, r.stereo_matches) == (len(f0.kpsL), len(f0.kpsR), len(f0.matches))
+    if "track_dbg" in o:
+        assert r.tracked_feats_from_last_frame == o["tracked_feats_from_last_frame"]
+        assert r.tracked_feats_from_last_KF == o["tracked_feats_from_last_KF"]
+    assert (r.error_code, bool(r.valid), r.num_it, r.num_it_final) == (o["error_code"], o["valid"], o["num_it"], o["num_it_final"]), \
+        f"frame {i}: status {list(r.delta_pose)} vs {None if o['pose'] is None else o['pose']['delta']}"
+    if o["pose"] is not None:
+        np.testing.assert_allclose(r.delta_pose[:3], o["pose"]["delta"][:3], atol=POSE_TOL_RAD)
+        np.testing.assert_allclose(r.delta_pose[3:], o["pose"]["delta"][3:], atol=POSE_TOL_M)
+        np.testing.assert_allclose(r.out_pose_rotvec[:], o["pose"]["rotvec"], atol=POSE_TOL_RAD)
+        np.testing.assert_allclose(r.out_pose_t[:], o["pose"]["t"], atol=POSE_TOL_M)
+        assert np.array_equal(ctx.outliers(slot), o["outliers"]), f"frame {i}: inlier list"
+        np.testing.assert_allclose(ctx.residuals(slot), o["out_residual"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("config,n_oct,pyr_mode", [("c1", 2, 0), ("c1", 2, 2), ("c2", 3, 0), ("c3", 2, 0), ("c3", 2, 1)])
+def test_pyramid_planes_bit_exact(config, n_oct, pyr_mode):
+    cfg = synth.CONFIGS[config]
+    frames, cam = synth.make_sequence(config, seed=2, n_frames=1)
+    ctx = capi.Context(width=cfg["W"], height=cfg["H"], orb_nfeats=cfg["orb_nfeats"], max_seqs=2, max_corners=32768,
+                       n_octaves=n_oct, pyr_mode=pyr_mode)
+    try:
+        L, R = frames[0]
+        ctx.process_batch([L, R], [R, L], [gcam(cam)] * 2)          # two items: the second one's planes sit behind the first's
+        pyrL = orc.build_pyramid(L, n_oct, pyr_mode)
+        pyrR = orc.build_pyramid(R, n_oct, pyr_mode)
+        for k in range(1, n_oct):
+            assert ctx.octave_info[k][:2] == (cfg["W"] >> k, cfg["H"] >> k)
+            assert np.array_equal(ctx.pyramid_plane(0, k, 0), pyrL[k]), f"octave {k} left"
+            assert np.array_equal(ctx.pyramid_plane(0, k, 1), pyrR[k]), f"octave {k} right"
+            assert np.array_equal(ctx.pyramid_plane(1, k, 0), pyrR[k]) and np.array_equal(ctx.pyramid_plane(1, k, 1), pyrL[k])
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("config,n_oct,ids,n_frames", [("c2", 3, True, 4), ("c1", 2, False, 3), ("c3", 2, True, 2)])
+def test_pipeline_octaves_vs_oracle(config, n_oct, ids, n_frames):
+    cfg = synth.CONFIGS[config]
+    frames, cam = synth.make_sequence(config, seed=4, n_frames=n_frames)
+    ctx = capi.Context(width=cfg["W"], height=cfg["H"], orb_nfeats=cfg["orb_nfeats"], max_seqs=2, max_corners=32768,
+                       n_octaves=n_oct, vo_use_matches_ids=int(ids))
+    try:
+        assert [o[2] for o in ctx.octave_info] == orc.kps_to_detect(cfg["orb_nfeats"], n_oct)
+        est = orc.OracleEstimatorOctaves(orc.Params(orb_nfeats=cfg["orb_nfeats"], nOctaves=n_oct, vo_use_matches_ids=ids),
+                                         backend="port", ransac=device_masks(ctx))
+        last = None
+        for i, (L, R) in enumerate(frames):
+            if ids and i == 2:                     # resetIds(): renumbering across all octaves (P:254-267)
+                est.reset_ids()
+                ctx.reset_ids(1)
+            o = est.process_new_image_pair(L, R, ocam(cam))
+            r = ctx.process_batch([L], [R], [gcam(cam)], slots=[1])[0]
+            check_frame(ctx, o, r, 1, i, ids)
+            if ids and i > 0:
+                for k in range(n_oct):             # previous frame's IDs (renumbered after the reset)
+                    assert np.array_equal(ctx.match_ids(1, 1, octave=k), est.prev[k].ids)
+            last = (o, r)
+        o, r = last
+        assert r.valid and all(len(t) > 10 for t in o["tracked"])
+        assert abs(r.out_pose_t[0] - 0.05) < 5e-3
+        assert len(ctx.residuals(1)) == sum(len(t) for t in o["tracked"])
+    finally:
+        ctx.close()
+
+
+def test_bad_tracking_gate_counts_all_octaves():
+    """P:326-330 compares the TOTAL over the octaves with bad_tracking_th; an unrelated second frame trips it, the
+    frame after that is matched against the kept previous frame (P:86-89)."""
+    a, cam = synth.make_sequence("c1", seed=7, n_frames=3)
+    b, _ = synth.make_sequence("c1", seed=8, n_frames=1)
+    frames = [a[0], b[0], a[1], a[2]]
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, n_octaves=2)
+    try:
+        est = orc.OracleEstimatorOctaves(orc.Params(orb_nfeats=100, nOctaves=2), backend="port", ransac=device_masks(ctx))
+        codes = []
+        for i, (L, R) in enumerate(frames):
+            o = est.process_new_image_pair(L, R, ocam(cam))
+            r = ctx.process_batch([L], [R], [gcam(cam)])[0]
+            check_frame(ctx, o, r, 0, i, False)
+            codes.append(r.error_code)
+        assert codes[0] == capi.VOEC["voecFirstIteration"] and codes[1] == capi.VOEC["voecBadTracking"]
+        assert codes[2] == capi.VOEC["voecNone"]
+    finally:
+        ctx.close()
+
+
+def test_octave_batch_in_concurrent_groups_equals_slots_alone():
+    """64 slots (two groups on two streams) over 4 distinct sequences: every slot gets what the sequence gets alone."""
+    seqs = [synth.make_sequence("c1", seed=40 + s, n_frames=3) for s in range(4)]
+    key = lambda r: (tuple(r.delta_pose), r.num_it, r.num_it_final, r.stereo_matches, r.tracked_feats_from_last_frame,
+                     r.error_code, r.valid)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=64, n_octaves=2)
+    try:
+        alone = []
+        for s, (frames, cam) in enumerate(seqs):
+            ctx.reset_slot(0)
+            alone.append([(key(ctx.process_batch([L], [R], [gcam(cam)], slots=[0])[0]), ctx.octave_stats(0).tolist())
+                          for (L, R) in frames])
+        for s in range(64):
+            ctx.reset_slot(s)
+        order = list(range(63, -1, -1))            # slot list in reverse: item i is slot 63 - i
+        for f in range(3):
+            Ls = [seqs[i % 4][0][f][0] for i in range(64)]
+            Rs = [seqs[i % 4][0][f][1] for i in range(64)]
+            rs = ctx.process_batch(Ls, Rs, [gcam(seqs[i % 4][1]) for i in range(64)], slots=order)
+            for i, r in enumerate(rs):
+                assert key(r) == alone[i % 4][f][0], f"frame {f} item {i}"
+                assert ctx.octave_stats(order[i]).tolist() == alone[i % 4][f][1]
+        assert any(a[0][6] for a in alone[0][1:])   # the sequences do produce valid poses
+    finally:
+        ctx.close()
+
+
+def test_get_change_in_pose_on_a_multi_octave_context():
+    """getChangeInPose (C:355-413) is single-octave by construction (`const size_t octave = 0`); on a context with
+    octaves it must give what a one-octave context gives."""
+    frames, cam = synth.make_sequence("c1", seed=9, n_frames=2)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend="port", ransac="off")
+    est.process_new_image_pair(*frames[0], ocam(cam))
+    o = est.process_new_image_pair(*frames[1], ocam(cam))
+    prev, cur = est.prev, est.cur
+    got = []
+    for n_oct in (1, 2):
+        ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, n_octaves=n_oct)
+        try:
+            r = ctx.get_change_in_pose(o["tracked"], prev.matches, cur.matches, prev.kpsL, prev.kpsR, cur.kpsL, cur.kpsR, gcam(cam))
+            got.append((tuple(r.delta_pose), r.num_it, r.num_it_final, r.valid, tuple(ctx.outliers(0)), tuple(ctx.residuals(0))))
+        finally:
+            ctx.close()
+    assert got[0] == got[1] and got[0][3] == 1
+    np.testing.assert_allclose(got[0][0][3:], o["pose"]["delta"][3:], atol=POSE_TOL_M)

@@ -29,7 +29,7 @@ def test_library_exports_every_header_symbol(built_lib):
     for name in declared:
         assert hasattr(L, name), f"{name} is declared in svo_b200.h but not exported"
     assert sorted(capi.EXPORTS) == declared
-    assert L.svo_abi_version() == 2
+    assert L.svo_abi_version() == 3
 
 
 def test_struct_layouts_match_header(built_lib):
@@ -42,6 +42,18 @@ def test_struct_layouts_match_header(built_lib):
     assert (cfg.max_iters, cfg.initial_max_iters, cfg.max_incr_cost, cfg.bad_tracking_th) == (100, 10, 3, 5)
     assert cfg.kernel_param == 3.0 and cfg.residual_threshold == 10.0 and cfg.min_mod_out_vector == 1e-3
     assert (cfg.match_method, cfg.if_match_method, cfg.ifm_win_w, cfg.ifm_win_h, cfg.orb_max_distance) == (0, 0, 20, 20, 40.0)
+    assert (cfg.n_octaves, cfg.pyr_mode) == (1, 0)
+
+
+def test_octave_configuration_is_validated_before_any_device_work(built_lib):
+    """Argument errors of svo_create (the reference throws via ASSERT_) do not need a device."""
+    capi = built_lib
+    for kw, text in ((dict(n_octaves=0), "n_octaves"), (dict(n_octaves=5), "n_octaves"), (dict(pyr_mode=3), "pyr_mode"),
+                     (dict(n_octaves=2, match_method=1), "smDescBF"), (dict(n_octaves=2, if_match_method=1), "smDescBF"),
+                     (dict(width=320, height=240, n_octaves=3), "64 x 64"), (dict(width=1024, height=1024, orb_nfeats=1, n_octaves=4), "orb_nfeats")):
+        with pytest.raises(capi.SvoError) as e:
+            capi.Context(**kw)
+        assert e.value.code == capi.SVO_ERR_ARG and text in str(e.value), kw
 
 
 def test_no_cpu_fallback_without_device(built_lib):
