@@ -6,7 +6,7 @@
 // Sequence file (written by tests / tools, little endian):
 //   int32 width, height, n_frames; double fx, fy, cx, cy, baseline; then n_frames x (left, right) images.
 //
-// usage: svo_demo <sequence.bin> <camera_pose.txt> [orb_nfeats | config.ini]
+// usage: svo_demo <sequence.bin> <camera_pose.txt> [orb_nfeats [nOctaves] | config.ini]
 //   config.ini: the 7 sections RECTIFY, DETECT, MATCH, IF-MATCH, LEAST_SQUARES, GUI, GENERAL (demo-main.cpp:155-167),
 //   GENERAL/vo_verbosity and GENERAL/camera_pose_on_robot = [x y z yaw pitch roll] in metres / degrees (:168-172, :182)
 #include <cstdio>
@@ -71,6 +71,7 @@ int main(int argc, char** argv) {
             pose_matrix(v, K);
         } else {
             if (argc > 3) engine.params_detect.orb_nfeats = (size_t)std::atoi(argv[3]);
+            engine.params_rectify.nOctaves = argc > 4 ? std::atoi(argv[4]) : 1;        // the hot-path INI runs one octave
             engine.applyParams();                     // what loadParamsFromConfigFile ends with (H:661-662)
             engine.setVerbosityLevel(0);
         }

@@ -8,6 +8,8 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <sys/stat.h>
+#include <sys/types.h>
 
 namespace rso {
 
@@ -169,11 +171,11 @@ void CStereoOdometryEstimator::setMaxMatchID(size_t id) {
     if (svo_set_max_match_id(m_ctx, 0, (int64_t)id) != SVO_OK) throw_last(m_ctx, "setMaxMatchID");
 }
 std::vector<size_t> CStereoOdometryEstimator::getCopyCurrentIDs(size_t octave) {
-    if (octave != 0 || !m_ctx) return std::vector<size_t>();
+    if (!m_ctx || octave >= (size_t)params_rectify.nOctaves) return std::vector<size_t>();
     const int cap = 2 * (int)params_detect.orb_nfeats + 16;
     std::vector<int64_t> ids(cap);
-    const int n = svo_get_match_ids(m_ctx, 0, 0, ids.data(), cap);
-    if (n < 0) throw_last(m_ctx, "svo_get_match_ids");
+    const int n = svo_get_match_ids_oct(m_ctx, 0, (int32_t)octave, 0, ids.data(), cap);
+    if (n < 0) throw_last(m_ctx, "svo_get_match_ids_oct");
     return std::vector<size_t>(ids.begin(), ids.begin() + n);
 }
 
@@ -207,8 +209,8 @@ void CStereoOdometryEstimator::ensure_context(int width, int height) {
         throw std::runtime_error("[Visual Odometry Error] Stereo matching method not correct (this build has smDescBF and smDescRbR).");
     if (params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescBF && params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescWin)
         throw std::runtime_error("[Visual Odometry Error] Interframe matching method not correct (this build has ifmDescBF and ifmDescWin).");
-    if (params_rectify.nOctaves != 1)
-        throw std::runtime_error("[Visual Odometry Error] nOctaves must be 1 on this path.");
+    if (params_rectify.nOctaves < 1 || params_rectify.nOctaves > 4)
+        throw std::runtime_error("[Visual Odometry Error] nOctaves must be within [1, 4].");
     if (params_detect.nmsMethod != TDetectParams::nmsmStandard)
         throw std::runtime_error("[Visual Odometry Error] Invalid non-maximal-suppression method (nmsmStandard only).");
     if (m_ctx) { svo_destroy(m_ctx); m_ctx = nullptr; }
@@ -241,6 +243,8 @@ void CStereoOdometryEstimator::ensure_context(int width, int height) {
     cfg.ifm_win_w = params_if_match.ifm_win_w;
     cfg.ifm_win_h = params_if_match.ifm_win_h;
     cfg.orb_max_distance = params_lr_match.orb_max_distance;
+    cfg.n_octaves = params_rectify.nOctaves;      // stage1_rectify.cpp:80 (dmORB, which forces one octave, is not built)
+    cfg.pyr_mode = params_rectify.pyr_mode;
     if (svo_create(&cfg, &m_ctx) != SVO_OK) throw_last(nullptr, "svo_create");
     m_w = width;
     m_h = height;
@@ -276,6 +280,90 @@ static void fill_result(svo_ctx* ctx, const svo_result& r, CStereoOdometryEstima
     if (r.n_residuals > 0) svo_get_residuals(ctx, 0, out.out_residual.data(), r.n_residuals);
 }
 
+// ---- params_general.vo_save_files: the per-frame text dumps of the reference ---------------------------------
+// Written from the device state after the step, file names and line formats as in process_new_image_pair.cpp:179-203
+// (left/right_feats_%04d.txt, left/right_desc_o%02d_%04d.yml in cv::FileStorage's YAML layout), :278-287
+// (matches_%04d.txt), stage4_match_consecutive.cpp:81-82,308-328 (inter_frame_matching_%04d.txt) and
+// stage5_optimization.cpp:703-713 (out_residual_%04d.txt and out_residual_final_%04d.txt: the reference writes the
+// final residual vector to both).  Not written: l-l / r-r_%04d.txt (S4:176-232) and optimization.txt (S5:477-490).
+static FILE* open_dump(const std::string& dir, const char* fmt, int a, int b = -1) {
+    char name[128];
+    if (b < 0) std::snprintf(name, sizeof(name), fmt, a);
+    else std::snprintf(name, sizeof(name), fmt, a, b);
+    FILE* f = std::fopen((dir + "/" + name).c_str(), "wt");
+    if (!f) throw std::runtime_error("[Visual Odometry Error] cannot write '" + dir + "/" + name + "'");
+    return f;
+}
+
+void CStereoOdometryEstimator::save_files(const TStereoOdometryResult& result, bool have_prev) {
+    const std::string& dir = params_general.vo_out_dir;
+    const int it = (int)m_it_counter;
+    const int n_oct = (int)result.detected_feats.size();
+    const int cap = 2 * (int)params_detect.orb_nfeats + 16;
+    struct Oct { std::vector<KeyPoint> kp[2][2]; std::vector<DMatch> m[2]; };      // [which][side], [which]
+    std::vector<Oct> oc((size_t)n_oct);
+    auto kps = [&](int octave, int which, int side, std::vector<KeyPoint>& out) {
+        out.resize((size_t)cap);
+        const int n = svo_get_keypoints_oct(m_ctx, 0, octave, which, side, reinterpret_cast<svo_keypoint*>(out.data()), cap);
+        if (n < 0) throw_last(m_ctx, "svo_get_keypoints_oct");
+        out.resize((size_t)n);
+    };
+    auto matches = [&](int octave, int which, std::vector<DMatch>& out) {
+        out.resize((size_t)cap);
+        const int n = svo_get_matches_oct(m_ctx, 0, octave, which, reinterpret_cast<svo_dmatch*>(out.data()), cap);
+        if (n < 0) throw_last(m_ctx, "svo_get_matches_oct");
+        out.resize((size_t)n);
+    };
+    for (int k = 0; k < n_oct; ++k) {
+        for (int which = 0; which < (have_prev ? 2 : 1); ++which) {
+            kps(k, which, 0, oc[k].kp[which][0]);
+            kps(k, which, 1, oc[k].kp[which][1]);
+            matches(k, which, oc[k].m[which]);
+        }
+    }
+    for (int side = 0; side < 2; ++side) {
+        FILE* f = open_dump(dir, side ? "right_feats_%04d.txt" : "left_feats_%04d.txt", it);
+        for (int k = 0; k < n_oct; ++k) {
+            const std::vector<KeyPoint>& v = oc[k].kp[0][side];
+            for (const KeyPoint& p : v) std::fprintf(f, "%d %.2f %.2f %.8f\n", k, p.pt.x, p.pt.y, p.response);
+            std::vector<uint8_t> desc(v.size() * 32);
+            if (!v.empty() && svo_get_descriptors_oct(m_ctx, 0, k, 0, side, desc.data(), (int32_t)v.size()) < 0) throw_last(m_ctx, "svo_get_descriptors_oct");
+            FILE* y = open_dump(dir, side ? "right_desc_o%02d_%04d.yml" : "left_desc_o%02d_%04d.yml", k, it);
+            std::fprintf(y, "%%YAML:1.0\n---\n%s: !!opencv-matrix\n   rows: %d\n   cols: 32\n   dt: u\n   data: [ ", side ? "rightDescMat" : "leftDescMat", (int)v.size());
+            for (size_t i = 0; i < desc.size(); ++i) std::fprintf(y, "%s%d", i ? (i % 16 ? ", " : ",\n       ") : "", (int)desc[i]);
+            std::fprintf(y, " ]\n");
+            std::fclose(y);
+        }
+        std::fclose(f);
+    }
+    FILE* f = open_dump(dir, "matches_%04d.txt", it);
+    for (int k = 0; k < n_oct; ++k)
+        for (const DMatch& m : oc[k].m[0]) std::fprintf(f, "%d %d %d %.2f\n", k, m.queryIdx, m.trainIdx, m.distance);
+    std::fclose(f);
+    if (!have_prev) return;
+    f = open_dump(dir, "inter_frame_matching_%04d.txt", it);
+    for (int k = 0; k < n_oct; ++k) {
+        std::vector<int64_t> tp((size_t)2 * cap);
+        const int n = svo_get_tracked_pairs_oct(m_ctx, 0, k, tp.data(), cap);
+        if (n < 0) throw_last(m_ctx, "svo_get_tracked_pairs_oct");
+        for (int i = 0; i < n; ++i) {
+            const DMatch& pm = oc[k].m[1][(size_t)tp[2 * i]];
+            const DMatch& cm = oc[k].m[0][(size_t)tp[2 * i + 1]];
+            const KeyPoint &pl = oc[k].kp[1][0][pm.queryIdx], &pr = oc[k].kp[1][1][pm.trainIdx];
+            const KeyPoint &cl = oc[k].kp[0][0][cm.queryIdx], &cr = oc[k].kp[0][1][cm.trainIdx];
+            std::fprintf(f, "%d %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %d %d\n", k, pl.pt.x, pl.pt.y, pr.pt.x, pr.pt.y, cl.pt.x, cl.pt.y,
+                         cr.pt.x, cr.pt.y, (int)tp[2 * i], (int)tp[2 * i + 1]);
+        }
+    }
+    std::fclose(f);
+    if (result.error_code == voecBadTracking) return;       // stage 5 did not run (P:332)
+    for (const char* fmt : {"out_residual_%04d.txt", "out_residual_final_%04d.txt"}) {
+        FILE* fr = open_dump(dir, fmt, it);
+        for (double v : result.out_residual) std::fprintf(fr, "%.3f\n", v);
+        std::fclose(fr);
+    }
+}
+
 void CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& request_data, TStereoOdometryResult& result) {
     if (!request_data.stereo_imgs)   // process_new_image_pair.cpp:81
         throw std::runtime_error("Pointer 'request_data.stereo_imgs' must be set to stereo observation data!");
@@ -307,9 +395,22 @@ void CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& reque
     svo_result r;
     const int rc = svo_process_pair(m_ctx, L.data, R.data, L.stride, &cam, request_data.repeat ? 1 : 0, &r);
     if (rc != SVO_OK) throw_last(m_ctx, "svo_process_pair");
-    result.detected_feats.assign(1, std::make_pair((size_t)r.detected_left, (size_t)r.detected_right));   // P:171-176
-    result.stereo_matches.assign(1, (size_t)r.stereo_matches);                                            // P:274-276
+    int32_t stats[4 * 4];
+    const int n_oct = svo_get_octave_stats(m_ctx, 0, stats, 4);
+    if (n_oct < 1) throw_last(m_ctx, "svo_get_octave_stats");
+    result.detected_feats.resize((size_t)n_oct);                                                           // P:171-176
+    result.stereo_matches.resize((size_t)n_oct);                                                           // P:274-276
+    for (int k = 0; k < n_oct; ++k) {
+        result.detected_feats[k] = std::make_pair((size_t)stats[4 * k], (size_t)stats[4 * k + 1]);
+        result.stereo_matches[k] = (size_t)stats[4 * k + 2];
+    }
     fill_result(m_ctx, r, result, r.n_residuals > 0 && (r.valid || r.error_code == voecIncrFuncCostStg2 || r.error_code == voecIncrFuncCostStg1));
+    if (params_general.vo_save_files) {
+        struct stat sb;                                     // P:46-47: the output directory is created on demand
+        if (stat(params_general.vo_out_dir.c_str(), &sb) != 0 && mkdir(params_general.vo_out_dir.c_str(), 0777) != 0)
+            throw std::runtime_error("[Visual Odometry Error] cannot create '" + params_general.vo_out_dir + "'");
+        save_files(result, r.error_code != voecFirstIteration);
+    }
     if (!request_data.repeat) ++m_it_counter;              // P:380-381
 }
 

@@ -124,8 +124,8 @@ public:
         bool valid = false;
         VOErrorCode error_code = voecNone;
         size_t tracked_feats_from_last_KF = 0, tracked_feats_from_last_frame = 0;
-        std::vector<std::pair<size_t, size_t> > detected_feats;
-        std::vector<size_t> stereo_matches;
+        std::vector<std::pair<size_t, size_t> > detected_feats;   // one entry per octave (P:171-176)
+        std::vector<size_t> stereo_matches;                       // one entry per octave (P:274-276)
     };
     struct TGeneralParams {                         // H:266-283, process_new_image_pair.cpp:34-35
         bool vo_use_matches_ids = false, vo_save_files = false, vo_debug = false, vo_pause_it = false;
@@ -147,7 +147,12 @@ public:
         size_t bad_tracking_th = 5;
         bool use_previous_pose_as_initial = true, use_custom_initial_pose = false;
     };
-    struct TRectifyParams { int nOctaves = 1; };    // the path runs with one octave
+    struct TRectifyParams {                         // H:352-381, stage1_rectify.cpp:26-30
+        int nOctaves = 3;                           // ctor default of the reference; 1..4 here
+        // how CImagePyramid::buildPyramidFast halves an octave (MRPT is absent here): 0 = as MRPT 1.x picks (2x2 rounded
+        // average when the width is a multiple of 16, cvPyrDown otherwise), 1 = always the average, 2 = always pyrDown
+        int pyr_mode = 0;
+    };
     struct TDetectParams {                          // H:383-447, stage2_detect.cpp:44-58
         enum NMSMethod { nmsmStandard, nmsmAdaptive };
         enum TDMethod { dmORB, dmFAST_ORB, dmFASTER, dmKLT };
@@ -242,6 +247,7 @@ public:
 
 private:
     void ensure_context(int width, int height);
+    void save_files(const TStereoOdometryResult& result, bool have_prev);   // params_general.vo_save_files
     static void throw_last(svo_ctx* c, const char* what);
     svo_ctx* m_ctx = nullptr;
     int m_w = 0, m_h = 0, m_device = 0;

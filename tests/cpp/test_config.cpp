@@ -34,6 +34,7 @@ int main(int argc, char** argv) {
     CStereoOdometryEstimator e2;
     e2.loadParamsFromConfigFile(CConfigFile::fromString(text), {"", "", "", "", "", "", ""});
     CHECK(e2.params_detect.orb_nfeats == 500 && e2.getORBThreshold() == 40);
+    CHECK(e2.params_rectify.nOctaves == 3);                                                      // ctor default, stage1_rectify.cpp:28
     bool threw = false;
     try { e2.loadParamsFromConfigFile(CConfigFile::fromString(text), {"RECTIFY"}); } catch (const std::exception&) { threw = true; }
     CHECK(threw);

@@ -188,3 +188,99 @@ def test_get_change_in_pose_on_a_multi_octave_context():
             ctx.close()
     assert got[0] == got[1] and got[0][3] == 1
     np.testing.assert_allclose(got[0][0][3:], o["pose"]["delta"][3:], atol=POSE_TOL_M)
+
+
+def test_host_shim_demo_with_two_octaves(tmp_path):
+    """The C++ host shim with params_rectify.nOctaves = 2 (demo loop of demo-main.cpp:210-253): composed camera poses
+    equal the octave-aware oracle's, and the per-octave result vectors have one entry per octave."""
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    demo = os.path.join(root, "stereo_vo_b200", "host", "svo_demo")
+    assert os.path.exists(demo), "host shim not built (run __graft_entry__.build())"
+    frames, cam = synth.make_sequence("c1", seed=9, n_frames=4)
+    seq = tmp_path / "seq.bin"
+    with open(seq, "wb") as f:
+        f.write(struct.pack("<3i5d", 320, 240, len(frames), cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"]))
+        for (L, R) in frames:
+            f.write(L.tobytes())
+            f.write(R.tobytes())
+    out = tmp_path / "camera_pose.txt"
+    p = subprocess.run([demo, str(seq), str(out), "100", "2"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    got = np.loadtxt(out).reshape(-1, 6)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, n_octaves=2)
+    try:
+        est = orc.OracleEstimatorOctaves(orc.Params(orb_nfeats=100, nOctaves=2), backend="port", ransac=device_masks(ctx))
+        pose = np.eye(4)
+        exp = []
+        for (L, R) in frames:
+            o = est.process_new_image_pair(L, R, ocam(cam))
+            if o["valid"]:
+                pose = pose @ o["pose"]["mat"]
+            ypr = [np.arctan2(pose[1, 0], pose[0, 0]), np.arctan2(-pose[2, 0], np.hypot(pose[0, 0], pose[1, 0])),
+                   np.arctan2(pose[2, 1], pose[2, 2])]
+            exp.append([pose[0, 3], pose[1, 3], pose[2, 3]] + ypr)
+    finally:
+        ctx.close()
+    np.testing.assert_allclose(got, np.array(exp), atol=1.5e-3)     # the file holds %.3f values
+    assert abs(got[-1, 0] - 0.15) < 0.02
+
+
+def test_host_shim_vo_save_files_dumps(tmp_path):
+    """params_general.vo_save_files (P:179-203, 278-287; S4:81-82, 308-328; S5:703-713): the per-frame text dumps of the
+    reference, written by the shim from the device state, two octaves; the descriptor .yml must parse with
+    cv::FileStorage (cv2) and hold the descriptors the C-ABI readers return."""
+    import os
+    import struct
+    import subprocess
+    cv2 = pytest.importorskip("cv2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    demo = os.path.join(root, "stereo_vo_b200", "host", "svo_demo")
+    frames, cam = synth.make_sequence("c1", seed=6, n_frames=3)
+    seq = tmp_path / "seq.bin"
+    with open(seq, "wb") as f:
+        f.write(struct.pack("<3i5d", 320, 240, len(frames), cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"]))
+        for (L, R) in frames:
+            f.write(L.tobytes())
+            f.write(R.tobytes())
+    outdir = tmp_path / "dumps"
+    text = open(os.path.join(root, "stereo_vo_b200", "host", "hot_path.ini")).read()
+    text = text.replace("orb_nfeats = 500", "orb_nfeats = 100").replace("nOctaves = 1", "nOctaves = 2")
+    text = text.replace("vo_save_files = false", f"vo_save_files = true\nvo_out_dir = {outdir}")
+    ini = tmp_path / "cfg.ini"
+    ini.write_text(text)
+    p = subprocess.run([demo, str(seq), str(tmp_path / "camera_pose.txt"), str(ini)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, n_octaves=2)
+    try:
+        for i, (L, R) in enumerate(frames):
+            r = ctx.process_batch([L], [R], [gcam(cam)])[0]
+            kl = [ctx.keypoints(0, 0, 0, octave=k) for k in range(2)]
+            feats = np.loadtxt(outdir / f"left_feats_{i:04d}.txt").reshape(-1, 4)
+            exp = np.concatenate([np.stack([np.full(len(k), o), k["x"], k["y"], k["response"]], 1) for o, k in enumerate(kl)])
+            assert np.array_equal(feats, exp)
+            assert len(np.loadtxt(outdir / f"right_feats_{i:04d}.txt").reshape(-1, 4)) == ctx.octave_stats(0)[:, 1].sum()
+            for k in range(2):
+                for side, name in ((0, "left"), (1, "right")):
+                    fs = cv2.FileStorage(str(outdir / f"{name}_desc_o{k:02d}_{i:04d}.yml"), cv2.FILE_STORAGE_READ)
+                    assert np.array_equal(fs.getNode(f"{name}DescMat").mat(), ctx.descriptors(0, 0, side, octave=k))
+            m = np.loadtxt(outdir / f"matches_{i:04d}.txt").reshape(-1, 4)
+            expm = np.concatenate([np.stack([np.full(len(mm), o), mm["queryIdx"], mm["trainIdx"], mm["distance"]], 1)
+                                   for o, mm in enumerate(ctx.matches(0, 0, octave=k) for k in range(2))])
+            assert np.array_equal(m, expm)
+            if i == 0:
+                assert not (outdir / "inter_frame_matching_0000.txt").exists()
+                continue
+            ifm = np.loadtxt(outdir / f"inter_frame_matching_{i:04d}.txt").reshape(-1, 11)
+            tps = [ctx.tracked_pairs(0, octave=k) for k in range(2)]
+            assert len(ifm) == r.tracked_feats_from_last_frame == sum(len(t) for t in tps)
+            assert np.array_equal(ifm[:, [0, 9, 10]], np.concatenate([np.column_stack([np.full(len(t), o), t]) for o, t in enumerate(tps)]))
+            cl = kl[0][ctx.matches(0, 0, octave=0)["queryIdx"][tps[0][:, 1]]]
+            assert np.array_equal(ifm[:len(tps[0]), 5], cl["x"]) and np.array_equal(ifm[:len(tps[0]), 6], cl["y"])
+            res = np.loadtxt(outdir / f"out_residual_{i:04d}.txt").reshape(-1)
+            np.testing.assert_allclose(res, ctx.residuals(0), atol=5.1e-4)          # %.3f
+            assert np.array_equal(res, np.loadtxt(outdir / f"out_residual_final_{i:04d}.txt").reshape(-1))
+    finally:
+        ctx.close()
