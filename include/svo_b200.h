@@ -105,7 +105,7 @@ typedef struct svo_config {
     double  orb_max_distance;     /* params_lr_match.orb_max_distance, the threshold smDescRbR reads (:206); 40 */
     /* image pyramid (ABI version 3) */
     int32_t n_octaves;            /* params_rectify.nOctaves (stage1_rectify.cpp:28,80): 1..4.  1 here;
-                                     the reference's ctor default is 3.  > 1 needs smDescBF / ifmDescBF */
+                                     the reference's ctor default is 3 */
     int32_t pyr_mode;             /* how CImagePyramid::buildPyramidFast halves an octave (stage1_rectify.cpp:82-83):
                                      0 = as MRPT 1.x picks (2x2 rounded average when the width is a multiple of 16,
                                      cvPyrDown otherwise), 1 = always the 2x2 average, 2 = always cv::pyrDown */

@@ -660,14 +660,14 @@ def kps_to_detect(orb_nfeats, n_octaves):
 
 
 class OracleEstimatorOctaves(OracleEstimator):
-    """processNewImagePair with params_rectify.nOctaves >= 1 on the FAST+ORB / smDescBF / ifmDescBF path: stage 2-4
-    run per octave (stage2_detect.cpp:423-624, stage3_match_left_right.cpp:87-177, stage4_match_consecutive.cpp:91-328),
+    """processNewImagePair with params_rectify.nOctaves >= 1 on the FAST+ORB path with either stereo matcher and either
+    tracker: stage 2-4 run per octave (stage2_detect.cpp:423-624, stage3_match_left_right.cpp:87-177 / :208-408,
+    stage4_match_consecutive.cpp:91-328 / :458-735),
     the match-ID generator and the tracking counters run through the octaves in order, stage 5 flattens all octaves with
     the x 2^octave rescale (stage5_optimization.cpp:419-461)."""
 
     def __init__(self, params=None, backend="cv2", ransac="cv2", sort_mode=0, pyr_mode=PYR_MRPT_AUTO):
         super().__init__(params, backend, ransac, sort_mode)
-        assert self.p.match_method == 0 and self.p.ifm_method == 0
         self.pyr_mode = pyr_mode
 
     def detect_octave(self, img, quota):

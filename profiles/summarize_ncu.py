@@ -29,7 +29,8 @@ KEYS = [
 
 PIPELINE = ("fast_blur_kernel", "select_kernel", "brief_kernel", "hamming_pipeline_kernel", "lr_filter_kernel", "track_filter_kernel",
             "ransac_prepare_kernel", "fundmat_kernel", "consistency_kernel", "gn_kernel", "begin_step_kernel", "scatter_cams_kernel",
-            "rbr_match_kernel", "win_track_kernel", "upload_meta_kernel")
+            "rbr_match_kernel", "win_track_kernel", "upload_meta_kernel", "pyramid_kernel", "flatten_octaves_kernel",
+            "reset_ids_octaves_kernel")
 
 
 def launches(src, dst):

@@ -433,8 +433,6 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     const int n_oct = cfg->n_octaves;
     if (n_oct < 1 || n_oct > kMaxOctaves) return fail(nullptr, SVO_ERR_ARG, "n_octaves must be within [1, 4]");
     if (cfg->pyr_mode < 0 || cfg->pyr_mode > 2) return fail(nullptr, SVO_ERR_ARG, "pyr_mode must be 0 (as MRPT), 1 (2x2 average) or 2 (pyrDown)");
-    if (n_oct > 1 && (cfg->match_method != 0 || cfg->if_match_method != 0))
-        return fail(nullptr, SVO_ERR_ARG, "n_octaves > 1 is built for smDescBF / ifmDescBF only");
     if ((cfg->width >> (n_oct - 1)) < 64 || (cfg->height >> (n_oct - 1)) < 64)
         return fail(nullptr, SVO_ERR_ARG, "the smallest octave must be at least 64 x 64");
     int quotas[kMaxOctaves];

@@ -721,7 +721,7 @@ int detect_smem_bytes(const Params& p) {
 }
 
 cudaError_t configure_detect(const Params& p) {
-    return cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, detect_smem_bytes(p));
+    return SVO_RAISE_DYN_SMEM(select_kernel, detect_smem_bytes(p));
 }
 
 cudaError_t launch_begin_step(const Pools& P, int n, const uint8_t* d_repeat, cudaStream_t st) {

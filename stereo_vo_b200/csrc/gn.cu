@@ -421,7 +421,9 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
 
     // ---- S5:465-474: aux non-max-suppression on the previous-left points ----------------------------
     const unsigned cell = (unsigned)(p.min_distance / 2.0);
-    if (assume_fast_kps && cell == 1) {
+    if (assume_fast_kps == GN_MASK_READY) {
+        // G.mask was written by aux_nms_kernel (launch_gn runs it first for lists that do not come from stage 2)
+    } else if (assume_fast_kps && cell == 1) {
         // keypoints produced by stage 2 are distinct and never 8-adjacent: with 1-px cells all survive
         for (int i = tid; i < T; i += GN_THREADS) G.mask[base + i] = 1;
     } else {
@@ -591,8 +593,96 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// aux_nms_kernel: the auxiliary non-maximal suppression of stage 5 (S5:465-474 -> m_non_max_sup, S2:225-283) for point
+// lists that are not stage 2's own keypoints: the flattened octaves (rescaled points of different octaves collide) and
+// getChangeInPose's caller data.  One CTA per slot: the indices are ordered by response with the block-cooperative
+// emulation of std::sort (introsort_block: same permutation as the reference's std::sort, ties included), the occupancy
+// grid lives in shared memory when it fits, one thread then walks the sorted list (the greedy rule is sequential).
+// gn_kernel keeps a one-thread version of the same steps for the remaining case (stage-2 keypoints with cells > 1 px).
+// ------------------------------------------------------------------------------------------------
+constexpr int AUX_THREADS = 128;
+struct AuxLayout { int tmp, lists, pos, occ, words; };      // offsets in 32-bit words of the dynamic shared memory
+static __host__ __device__ AuxLayout aux_layout(int cap, int occ_words_smem) {
+    AuxLayout L;
+    L.tmp = 2 * cap;                                   // [cap] idx | [cap] key | [cap] tmp
+    L.lists = 3 * cap + (cap & 1);                     // 8-byte aligned: 3 lists of (cap/16 + 2) uint2
+    L.pos = L.lists + 6 * (cap / 16 + 2);              // 64 ints per warp
+    L.occ = L.pos + 64 * (AUX_THREADS / 32);
+    L.words = L.occ + occ_words_smem;
+    return L;
+}
+
+__global__ void __launch_bounds__(AUX_THREADS)
+aux_nms_kernel(Pools P, GnScratch G, int occ_in_smem) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ int s_sortcnt[3];
+    const int slot = P.slots[blockIdx.x];
+    const Params& p = P.p;
+    const int tid = threadIdx.x;
+    const int cap = p.kp_cap;
+    const size_t base = (size_t)slot * cap;
+    const int T = min(P.n_tracked[slot], cap);
+    const unsigned cell = (unsigned)(p.min_distance / 2.0);
+    const float cell_inv = 1.0f / (float)cell;
+    const unsigned glx = (unsigned)(1 + p.W * cell_inv), gly = (unsigned)(1 + p.H * cell_inv);
+    const unsigned occ_n = (glx * gly + 31) / 32;
+    const AuxLayout L = aux_layout(cap, 0);
+    uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_dyn);
+    float* s_key = reinterpret_cast<float*>(s_dyn) + cap;
+    uint32_t* s_tmp = s_idx + L.tmp;
+    uint2* s_list = reinterpret_cast<uint2*>(s_idx + L.lists);
+    int* s_pos = reinterpret_cast<int*>(s_idx + L.pos);
+    uint32_t* occ = occ_in_smem ? s_idx + L.occ : G.occ + (size_t)slot * G.occ_words;
+    for (int i = tid; i < T; i += AUX_THREADS) { s_idx[i] = i; s_key[i] = G.prev[base + i].w; G.mask[base + i] = 0; }
+    for (unsigned i = tid; i < occ_n; i += AUX_THREADS) occ[i] = 0;
+    __syncthreads();
+    IndexedDescComp c{s_key};
+    if (p.sort_mode == 0) {
+        const int nl = cap / 16 + 2;
+        introsort_block(c, s_idx, T, s_list, s_list + nl, s_list + 2 * nl, s_sortcnt, s_tmp, s_pos, T);
+    } else {
+        if (tid == 0) insertion_sort_(c, s_idx, 0, T);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        auto get = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; return (occ[b >> 5] >> (b & 31)) & 1u; };
+        auto set = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; occ[b >> 5] |= 1u << (b & 31); };
+        for (int k = 0; k < T; ++k) {                  // num_out == T: the quota never ends the walk early (S5:468-473)
+            const uint32_t idx = s_idx[k];
+            const float4 pp = G.prev[base + idx];
+            const unsigned sx = (unsigned)(pp.x * cell_inv), sy = (unsigned)(pp.y * cell_inv);
+            if (sx >= glx || sy >= gly) continue;      // outside the image: the reference would index out of bounds
+            if (get(sx, sy)) continue;
+            set(sx, sy);
+            if (sx > 0) set(sx - 1, sy);
+            if (sy > 0) set(sx, sy - 1);
+            if (sx < glx - 1) set(sx + 1, sy);
+            if (sy < gly - 1) set(sx, sy + 1);
+            G.mask[base + idx] = 1;
+        }
+    }
+}
+
+// dynamic shared memory of aux_nms_kernel; *occ_in_smem = whether the occupancy grid fits beside the sort scratch
+static int aux_smem_bytes(const Params& p, int* occ_in_smem) {
+    const unsigned cell = (unsigned)(p.min_distance / 2.0);
+    const float cell_inv = 1.0f / (float)cell;
+    const unsigned glx = (unsigned)(1 + p.W * cell_inv), gly = (unsigned)(1 + p.H * cell_inv);
+    const int occ_n = (int)((glx * gly + 31) / 32);
+    const int without = aux_layout(p.kp_cap, 0).words * 4, with = aux_layout(p.kp_cap, occ_n).words * 4;
+    *occ_in_smem = with <= 160 * 1024 ? 1 : 0;
+    return *occ_in_smem ? with : without;
+}
+static bool aux_kernel_usable(const Params& p) { int o; return aux_smem_bytes(p, &o) <= 200 * 1024; }
+
 cudaError_t configure_gn(const Params& p) {
-    return cudaFuncSetAttribute(gn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * 8));
+    if (aux_kernel_usable(p)) {
+        int o;
+        cudaError_t e = SVO_RAISE_DYN_SMEM(aux_nms_kernel, aux_smem_bytes(p, &o));
+        if (e != cudaSuccess) return e;
+    }
+    return SVO_RAISE_DYN_SMEM(gn_kernel, (int)(p.kp_cap * 8));
 }
 
 // getProjectedCoords (common.cpp:415-470): triangulate the stereo matches flagged "not tracked" (flag == -1) in the
@@ -674,6 +764,14 @@ cudaError_t launch_flatten_octaves(const Pools& PG, const GnScratch& G, const Oc
 
 cudaError_t launch_gn(const Pools& P, const GnScratch& G, int n, int external, int use_custom_pose,
                       int assume_fast_kps, cudaStream_t st, int* launches, StepTimer* tm) {
+    // point lists that are not stage 2's keypoints: the aux NMS runs in its own block-parallel kernel first
+    if (external != GN_FROM_TRACKED && !assume_fast_kps && aux_kernel_usable(P.p)) {
+        int occ_in_smem = 0;
+        const int smem = aux_smem_bytes(P.p, &occ_in_smem);
+        aux_nms_kernel<<<n, AUX_THREADS, smem, st>>>(P, G, occ_in_smem);
+        if (launches) *launches += 1;
+        assume_fast_kps = GN_MASK_READY;
+    }
     gn_kernel<<<n, GN_THREADS, P.p.kp_cap * 8, st>>>(P, G, external, use_custom_pose, assume_fast_kps);
     if (tm) tm->mark(st);
     if (launches) *launches += 1;

@@ -24,6 +24,9 @@ cudaError_t launch_project(const int4* d_matches, const float2* d_left, const fl
 enum { GN_FROM_TRACKED = 0,     // gathered by the kernel from the slot's tracked pairs (nOctaves == 1)
        GN_EXTERNAL = 1,         // written to GnScratch by the caller: getChangeInPose, no processNewImagePair gating
        GN_FLATTENED = 2 };      // written to GnScratch by launch_flatten_octaves (nOctaves > 1), gating as GN_FROM_TRACKED
+// `assume_fast_kps` of launch_gn: 1 = the points are stage 2's keypoints (distinct, never 8-adjacent: with 1-px cells the
+// aux NMS of S5:465-474 keeps them all), 0 = run the aux NMS; GN_MASK_READY is set internally once aux_nms_kernel ran
+enum { GN_MASK_READY = 2 };
 // nOctaves > 1: the tracked pairs of all octaves into G.prev / G.obs / G.cur_idx at the scale of octave 0
 // (x 2^octave, stage5_optimization.cpp:422-456); PG = the Pools of the flattened problem (kp_cap = sum over the octaves)
 cudaError_t launch_flatten_octaves(const Pools& PG, const GnScratch& G, const OctaveList& O, int n, cudaStream_t st, int* launches);

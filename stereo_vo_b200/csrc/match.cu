@@ -755,15 +755,15 @@ cudaError_t launch_hamming_raw(const uint8_t* d_q, int nq, const uint8_t* d_t, i
 }
 
 cudaError_t configure_match(const Params& p) {
-    cudaError_t e = cudaFuncSetAttribute(track_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tf_smem(p));
+    cudaError_t e = SVO_RAISE_DYN_SMEM(track_filter_kernel, tf_smem(p));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lr_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * sizeof(uint32_t)));
+    e = SVO_RAISE_DYN_SMEM(lr_filter_kernel, (int)(p.kp_cap * sizeof(uint32_t)));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rbr_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rbr_smem(p));
+    e = SVO_RAISE_DYN_SMEM(rbr_match_kernel, rbr_smem(p));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(win_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, win_smem(p));
+    e = SVO_RAISE_DYN_SMEM(win_track_kernel, win_smem(p));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(consistency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.kp_cap * sizeof(uint32_t)));
+    return SVO_RAISE_DYN_SMEM(consistency_kernel, (int)(p.kp_cap * sizeof(uint32_t)));
 }
 
 }  // namespace svo

@@ -184,8 +184,8 @@ cudaError_t launch_prepare(const PrepareArgs& A, int n, int channels, bool recti
 //     _mm_avg_epu8, then horizontal neighbours with _mm_avg_epu16, both rounding half up  (restated from MRPT 1.x:
 //     its source is not in this image, UNPINNED);
 //   * cvPyrDown otherwise: separable [1 4 6 4 1], (sum + 128) >> 8, BORDER_REFLECT_101 (pinned against cv2.pyrDown).
-// One thread = 4 output pixels (one 32-bit store); blockIdx.z = 2 * item + side.  Streaming: reads sw*sh, writes a
-// quarter of it; the kernel exists to keep the pyramid on the device, it is not a hot spot (< 2 % of a step).
+// One thread = 8 output pixels (two 16-byte loads, one 8-byte store); blockIdx.z = 2 * item + side.  Streaming and
+// HBM-bound: algorithmic bytes = sw*sh read + a quarter of it written per image; < 2 % of a step.
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
@@ -195,29 +195,29 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 template <int METHOD>
 __global__ void __launch_bounds__(256)
 pyramid_kernel(PyramidArgs A) {
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int x8 = (blockIdx.x * 8 + threadIdx.x) * 8;       // CTA = 64 x 32 output pixels: a warp covers 4 rows of 64
+    const int y = blockIdx.y * 32 + threadIdx.y;
     const int dw = A.sw >> 1, dh = A.sh >> 1;
-    if (x4 >= (int)A.dst_stride || y >= dh) return;
+    if (x8 >= (int)A.dst_stride || y >= dh) return;
     const int item = blockIdx.z >> 1, side = blockIdx.z & 1;
     const uint8_t* __restrict__ src = (side ? A.srcR : A.srcL) + (size_t)item * A.src_image_pitch;
     uint8_t* __restrict__ dst = (side ? A.dstR : A.dstL) + (size_t)item * A.dst_image_pitch;
-    uint32_t out = 0;
+    uint32_t out[2] = {0u, 0u};
     if (METHOD == PYR_AVG2X2) {
-        const uint8_t* r0 = src + (size_t)(2 * y) * A.src_stride + 2 * x4;
+        const uint8_t* r0 = src + (size_t)(2 * y) * A.src_stride + 2 * x8;
         const uint8_t* r1 = r0 + A.src_stride;
-        if (x4 + 3 < dw && ((reinterpret_cast<uintptr_t>(r0) | A.src_stride) & 7) == 0) {
-            const uint2 a = __ldg(reinterpret_cast<const uint2*>(r0)), b = __ldg(reinterpret_cast<const uint2*>(r1));
-            const uint32_t v0 = __vavgu4(a.x, b.x), v1 = __vavgu4(a.y, b.y);          // vertical, (p + q + 1) >> 1 per byte
-            const uint32_t ev = __byte_perm(v0, v1, 0x6420), od = __byte_perm(v0, v1, 0x7531);
-            out = __vavgu4(ev, od);                                                    // horizontal
+        if (x8 + 7 < dw && ((reinterpret_cast<uintptr_t>(r0) | A.src_stride) & 15) == 0) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(r0)), b = __ldg(reinterpret_cast<const uint4*>(r1));
+            // vertical, (p + q + 1) >> 1 per byte; then even / odd columns apart and the horizontal average
+            const uint32_t v0 = __vavgu4(a.x, b.x), v1 = __vavgu4(a.y, b.y), v2 = __vavgu4(a.z, b.z), v3 = __vavgu4(a.w, b.w);
+            out[0] = __vavgu4(__byte_perm(v0, v1, 0x6420), __byte_perm(v0, v1, 0x7531));
+            out[1] = __vavgu4(__byte_perm(v2, v3, 0x6420), __byte_perm(v2, v3, 0x7531));
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int x = x4 + j;
-                if (x >= dw) break;
+            for (int j = 0; j < 8; ++j) {
+                if (x8 + j >= dw) break;
                 const uint32_t va = (r0[2 * j] + r1[2 * j] + 1u) >> 1, vb = (r0[2 * j + 1] + r1[2 * j + 1] + 1u) >> 1;
-                out |= ((va + vb + 1u) >> 1) << (8 * j);
+                out[j >> 2] |= ((va + vb + 1u) >> 1) << (8 * (j & 3));
             }
         }
     } else {
@@ -225,8 +225,8 @@ pyramid_kernel(PyramidArgs A) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) ry[j] = reflect101(2 * y + j - 2, A.sh);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = x4 + j;
+        for (int j = 0; j < 8; ++j) {
+            const int x = x8 + j;
             if (x >= dw) break;
             int cx[5];
 #pragma unroll
@@ -238,16 +238,16 @@ pyramid_kernel(PyramidArgs A) {
                 const uint32_t h = row[cx[0]] + 4u * row[cx[1]] + 6u * row[cx[2]] + 4u * row[cx[3]] + row[cx[4]];
                 acc += h * (r == 0 || r == 4 ? 1u : (r == 2 ? 6u : 4u));
             }
-            out |= ((acc + 128u) >> 8) << (8 * j);
+            out[j >> 2] |= ((acc + 128u) >> 8) << (8 * (j & 3));
         }
     }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)y * A.dst_stride + x4) = out;    // padding columns are written as 0
+    *reinterpret_cast<uint2*>(dst + (size_t)y * A.dst_stride + x8) = make_uint2(out[0], out[1]);   // padding columns: 0
 }
 
 cudaError_t launch_pyramid_level(const PyramidArgs& A, int n, int method, cudaStream_t st, int* launches) {
     if (n <= 0) return cudaSuccess;
-    const dim3 block(32, 8);
-    const dim3 grid(((int)A.dst_stride / 4 + 31) / 32, ((A.sh >> 1) + 7) / 8, 2 * n);
+    const dim3 block(8, 32);
+    const dim3 grid(((int)A.dst_stride / 8 + 7) / 8, ((A.sh >> 1) + 31) / 32, 2 * n);
     if (method == PYR_AVG2X2) pyramid_kernel<PYR_AVG2X2><<<grid, block, 0, st>>>(A);
     else pyramid_kernel<PYR_PYRDOWN><<<grid, block, 0, st>>>(A);
     if (launches) *launches += 1;

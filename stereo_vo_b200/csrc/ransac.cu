@@ -291,7 +291,7 @@ cudaError_t alloc_ransac(RansacScratch& R, int n_slots, int kp_cap, std::vector<
 static int ransac_smem(int kp_cap) { return 2 * kp_cap * (int)sizeof(Pt2f); }
 
 cudaError_t configure_ransac(int kp_cap) {
-    return cudaFuncSetAttribute(fundmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ransac_smem(kp_cap));
+    return SVO_RAISE_DYN_SMEM(fundmat_kernel, ransac_smem(kp_cap));
 }
 
 cudaError_t launch_ransac(const Pools& P, const RansacScratch& R, int n, cudaStream_t st, int* launches,

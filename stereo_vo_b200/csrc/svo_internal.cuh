@@ -130,6 +130,20 @@ struct StepTimer {
     void mark(cudaStream_t st) { if (ev) cudaEventRecord(ev[next++], st); }
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (kernel, device) and is shared by every context of the process:
+// it is only ever RAISED, so that creating a small context never takes shared memory away from a larger one that is
+// still alive.  One table per kernel at the call site (SVO_RAISE_DYN_SMEM).
+inline cudaError_t raise_dyn_smem(const void* func, int bytes, int* seen /* [64], zero-initialised */) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && bytes <= seen[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) seen[dev] = bytes;
+    return e;
+}
+#define SVO_RAISE_DYN_SMEM(kernel, bytes) ([&]() { static int seen_[64]; return raise_dyn_smem((const void*)(kernel), (bytes), seen_); }())
+
 __host__ __device__ inline size_t img_idx(int slot, int side) { return (size_t)slot * 2 + side; }
 __host__ __device__ inline size_t frame_idx(int slot, int buf, int side) { return ((size_t)slot * 2 + buf) * 2 + side; }
 __host__ __device__ inline size_t pair_idx(int slot, int buf) { return (size_t)slot * 2 + buf; }

@@ -122,6 +122,23 @@ def test_pipeline_octaves_vs_oracle(config, n_oct, ids, n_frames):
         ctx.close()
 
 
+def test_pipeline_octaves_with_the_band_limited_matchers():
+    """smDescRbR + ifmDescWin (S3:208-408, S4:458-735 loop over the octaves like the brute-force branches)."""
+    frames, cam = synth.make_sequence("c2", seed=6, n_frames=3)
+    ctx = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=1, n_octaves=3, vo_use_matches_ids=1,
+                       match_method=1, if_match_method=1)
+    try:
+        est = orc.OracleEstimatorOctaves(orc.Params(orb_nfeats=500, nOctaves=3, vo_use_matches_ids=True, match_method=1,
+                                                    ifm_method=1), backend="port", ransac=device_masks(ctx))
+        for i, (L, R) in enumerate(frames):
+            o = est.process_new_image_pair(L, R, ocam(cam))
+            r = ctx.process_batch([L], [R], [gcam(cam)])[0]
+            check_frame(ctx, o, r, 0, i, True)
+        assert r.valid and all(len(t) > 10 for t in o["tracked"])
+    finally:
+        ctx.close()
+
+
 def test_bad_tracking_gate_counts_all_octaves():
     """P:326-330 compares the TOTAL over the octaves with bad_tracking_th; an unrelated second frame trips it, the
     frame after that is matched against the kept previous frame (P:86-89)."""

@@ -342,6 +342,46 @@ def test_get_change_in_pose_kat():
             ctx.close()
 
 
+def test_get_change_in_pose_aux_nms_collisions_and_response_ties():
+    """The auxiliary NMS of stage 5 (S5:465-474 -> S2:225-283) on caller data: every point comes with 4 copies at the
+    same or a 4-adjacent pixel and responses drawn from four values, so the survivors depend on the exact permutation
+    std::sort leaves among equal responses (aux_nms_kernel's block-cooperative introsort emulation)."""
+    from katdata import kat_inputs as _kat_inputs
+    a, cam, N = _kat_inputs(True, 1.2, 0.9)
+    rng = np.random.default_rng(5)
+    idx = np.concatenate([np.arange(N), rng.integers(0, N, 3 * N)])
+    arrs = [np.rint(v[idx]).astype(np.float32) for v in a]          # integer pixels: copies share cells
+    shift = rng.integers(-1, 2, (len(idx), 2)).astype(np.float32)
+    shift[:N] = 0
+    shift[rng.random(len(idx)) < 0.5, 1] = 0                          # many 4-adjacent neighbours
+    arrs[0] = arrs[0] + shift
+    resp = rng.integers(1, 5, len(idx)).astype(np.float32)
+    n = len(idx)
+    for sort_mode in (0, 1):
+        ctx = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=1, sort_mode=sort_mode)
+        try:
+            kp = [np.zeros(n, capi.KEYPOINT) for _ in range(4)]
+            for k, v in zip(kp, arrs):
+                k["x"], k["y"], k["response"] = v[:, 0], v[:, 1], 1.0
+            kp[0]["response"] = resp
+            m = np.zeros(n, capi.DMATCH)
+            m["queryIdx"] = m["trainIdx"] = np.arange(n)
+            tp = np.stack([np.arange(n), np.arange(n)], 1)
+            res = ctx.get_change_in_pose(tp, m, m, kp[0], kp[1], kp[2], kp[3], capi.make_camera(500, 500, 320, 240, 0.12))
+            ores, oresid, oinl = orc.stage5(*arrs, resp, np.arange(n), 480, 640, 3, cam, orc.LSParams.defaults(), np.zeros(6),
+                                            sort_mode=sort_mode)
+            got = ctx.residuals(0)
+            kept, okept = got < 1e300, oresid < 1e300                 # suppressed points keep the initial DBL_MAX (S5:296)
+            assert 0.1 * n < okept.sum() < 0.6 * n                    # the suppression is substantial
+            assert np.array_equal(kept, okept), f"sort_mode {sort_mode}: survivors of the aux NMS"
+            np.testing.assert_allclose(got[kept], oresid[okept], rtol=1e-6, atol=1e-9)
+            assert (res.valid, res.error_code, res.num_it, res.num_it_final) == (ores.valid, ores.error_code, ores.num_it, ores.num_it_final)
+            assert np.array_equal(ctx.outliers(0), oinl)
+            np.testing.assert_allclose(res.delta_pose[:], ores.delta_pose[:], atol=1e-7)
+        finally:
+            ctx.close()
+
+
 def test_get_change_in_pose_degenerate():
     from katdata import kat_inputs as _kat_inputs
     a, cam, N = _kat_inputs(False, 1.2, 0.9)

@@ -49,7 +49,6 @@ def test_octave_configuration_is_validated_before_any_device_work(built_lib):
     """Argument errors of svo_create (the reference throws via ASSERT_) do not need a device."""
     capi = built_lib
     for kw, text in ((dict(n_octaves=0), "n_octaves"), (dict(n_octaves=5), "n_octaves"), (dict(pyr_mode=3), "pyr_mode"),
-                     (dict(n_octaves=2, match_method=1), "smDescBF"), (dict(n_octaves=2, if_match_method=1), "smDescBF"),
                      (dict(width=320, height=240, n_octaves=3), "64 x 64"), (dict(width=1024, height=1024, orb_nfeats=1, n_octaves=4), "orb_nfeats")):
         with pytest.raises(capi.SvoError) as e:
             capi.Context(**kw)
