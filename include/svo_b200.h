@@ -257,6 +257,20 @@ int svo_match_hamming_device(svo_ctx* ctx, const uint8_t* d_query, int32_t nq, c
 int svo_match_lr(svo_ctx* ctx, const svo_keypoint* kpsL, const uint8_t* descL, int32_t nL,
                  const svo_keypoint* kpsR, const uint8_t* descR, int32_t nR, svo_dmatch* out, int32_t cap);
 
+/* stage4_track (stage4_match_consecutive.cpp:70-760; ifmDescBF :88-329 or ifmDescWin :435-738 as configured) alone on
+ * caller data, one octave: the previous and the current frame as stages 2 and 3 leave them -- keypoints (integer pixel
+ * coordinates, as FAST gives them), 32-byte descriptors, stereo matches.  out_pairs receives tracked_pairs[0]:
+ * cap x 2 (pre_match_idx, cur_match_idx).  Returns the number of tracked pairs.  Runs on the context's scratch slot;
+ * no sequence slot is touched and no match IDs are assigned. */
+int svo_track(svo_ctx* ctx,
+              const svo_keypoint* pre_left, const uint8_t* pre_desc_left, int32_t n_pl,
+              const svo_keypoint* pre_right, const uint8_t* pre_desc_right, int32_t n_pr,
+              const svo_dmatch* pre_matches, int32_t n_pm,
+              const svo_keypoint* cur_left, const uint8_t* cur_desc_left, int32_t n_cl,
+              const svo_keypoint* cur_right, const uint8_t* cur_desc_right, int32_t n_cr,
+              const svo_dmatch* cur_matches, int32_t n_cm,
+              int64_t* out_pairs, int32_t cap);
+
 /* getChangeInPose (libstereo-odometry.h:162-172, common.cpp:355-413): stage 5 alone on caller data.
  * tracked_pairs: n_tracked x 2 (pre_match_idx, cur_match_idx).  ini_estimation: 6 doubles or NULL
  * (used only when use_custom_initial_pose != 0, which also keeps m_last_computed_pose untouched).
@@ -268,6 +282,16 @@ int svo_get_change_in_pose(svo_ctx* ctx, int32_t slot,
                            const svo_keypoint* cur_left, int32_t n_cl, const svo_keypoint* cur_right, int32_t n_cr,
                            const svo_camera* cam, int32_t use_custom_initial_pose, const double* ini_estimation,
                            svo_result* result);
+
+/* stage5_optimize (stage5_optimization.cpp:392-736) under the name SURVEY section 8(b) lists: same call as
+ * svo_get_change_in_pose, which is the reference's public seam for stage 5 alone. */
+int svo_optimize(svo_ctx* ctx, int32_t slot,
+                 const int64_t* tracked_pairs, int32_t n_tracked,
+                 const svo_dmatch* pre_matches, int32_t n_pre, const svo_dmatch* cur_matches, int32_t n_cur,
+                 const svo_keypoint* pre_left, int32_t n_pl, const svo_keypoint* pre_right, int32_t n_pr,
+                 const svo_keypoint* cur_left, int32_t n_cl, const svo_keypoint* cur_right, int32_t n_cr,
+                 const svo_camera* cam, int32_t use_custom_initial_pose, const double* ini_estimation,
+                 svo_result* result);
 
 /* getProjectedCoords (libstereo-odometry.h:175-182, common.cpp:415-470): the stereo matches of the previous key frame
  * whose other_matches_tracked entry is -1 are triangulated and projected into the left and right image with

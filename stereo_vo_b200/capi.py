@@ -36,6 +36,7 @@ EXPORTS = [
     "svo_get_projected_coords", "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
     "svo_get_keypoints_oct", "svo_get_descriptors_oct", "svo_get_matches_oct", "svo_get_match_ids_oct",
     "svo_get_tracked_pairs_oct", "svo_get_octave_info", "svo_get_octave_stats", "svo_get_pyramid_plane",
+    "svo_track", "svo_optimize",
 ]
 
 
@@ -316,6 +317,22 @@ class Context:
         out = np.zeros(self.kp_cap, DMATCH)
         n = self._check(lib().svo_match_lr(self._h, _vp(kpsL), _vp(descL), len(kpsL), _vp(kpsR), _vp(descR), len(kpsR),
                                            _vp(out), self.kp_cap))
+        return out[:n].copy()
+
+    def track(self, pre, cur):
+        """stage 4 alone: pre / cur = (kpsL, descL, kpsR, descR, matches) of the previous / current frame."""
+        args = []
+        for kl, dl, kr, dr, m in (pre, cur):
+            kl = np.ascontiguousarray(kl, KEYPOINT)
+            kr = np.ascontiguousarray(kr, KEYPOINT)
+            dl = np.ascontiguousarray(dl, np.uint8).reshape(-1, 32)
+            dr = np.ascontiguousarray(dr, np.uint8).reshape(-1, 32)
+            m = np.ascontiguousarray(m, DMATCH)
+            args += [_vp(kl), _vp(dl), len(kl), _vp(kr), _vp(dr), len(kr), _vp(m), len(m)]
+            self._keep = getattr(self, "_keep", []) + [kl, dl, kr, dr, m]
+        out = np.zeros((self.kp_cap, 2), np.int64)
+        n = self._check(lib().svo_track(self._h, *args, _vp(out), self.kp_cap))
+        self._keep = []
         return out[:n].copy()
 
     def get_change_in_pose(self, tracked_pairs, pre_matches, cur_matches, pre_left, pre_right, cur_left, cur_right,

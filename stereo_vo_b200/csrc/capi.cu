@@ -1270,6 +1270,97 @@ int svo_match_lr(svo_ctx* c, const svo_keypoint* kpsL, const uint8_t* descL, int
     return svo_get_matches(c, hs, 0, out, cap);
 }
 
+// one frame of caller data into buffer `buf` of the scratch slot: keypoints, descriptors, stereo matches and the
+// descriptor rows gathered per match (what lr_filter_kernel leaves for stage 4, S4:105-131)
+static int upload_frame(svo_ctx* c, int hs, int buf, const svo_keypoint* kl, const uint8_t* dl, int nl, const svo_keypoint* kr,
+                        const uint8_t* dr, int nr, const svo_dmatch* m, int nm) {
+    const Pools& P = c->P;
+    const int kc = P.p.kp_cap;
+    const size_t fL = frame_idx(hs, buf, 0), fR = frame_idx(hs, buf, 1), pi = pair_idx(hs, buf);
+    int rc = upload_kps(c, kl, nl, P.kp + fL * kc);
+    if (rc) return rc;
+    rc = upload_kps(c, kr, nr, P.kp + fR * kc);
+    if (rc) return rc;
+    std::vector<int4> hm((size_t)nm);
+    std::vector<uint8_t> gl((size_t)nm * 32), gr((size_t)nm * 32);
+    for (int i = 0; i < nm; ++i) {
+        if (m[i].queryIdx < 0 || m[i].queryIdx >= nl || m[i].trainIdx < 0 || m[i].trainIdx >= nr)
+            return fail(c, SVO_ERR_ARG, "match index outside the keypoint lists");
+        hm[i] = make_int4(m[i].queryIdx, m[i].trainIdx, (int)m[i].distance, 0);
+        memcpy(&gl[(size_t)i * 32], dl + (size_t)m[i].queryIdx * 32, 32);
+        memcpy(&gr[(size_t)i * 32], dr + (size_t)m[i].trainIdx * 32, 32);
+    }
+    if (nl) CU(c, cudaMemcpyAsync(P.desc + fL * kc * 2, dl, (size_t)nl * 32, cudaMemcpyHostToDevice, c->stream));
+    if (nr) CU(c, cudaMemcpyAsync(P.desc + fR * kc * 2, dr, (size_t)nr * 32, cudaMemcpyHostToDevice, c->stream));
+    if (nm) {
+        CU(c, cudaMemcpyAsync(P.match + pi * kc, hm.data(), (size_t)nm * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(P.mdesc + fL * kc * 2, gl.data(), (size_t)nm * 32, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(P.mdesc + fR * kc * 2, gr.data(), (size_t)nm * 32, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(c, cudaMemcpyAsync(P.n_kp + fL, &nl, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(P.n_kp + fR, &nr, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(P.n_match + pi, &nm, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));      // the host vectors above go out of scope
+    return SVO_OK;
+}
+
+int svo_track(svo_ctx* c, const svo_keypoint* pre_left, const uint8_t* pre_desc_left, int32_t n_pl,
+              const svo_keypoint* pre_right, const uint8_t* pre_desc_right, int32_t n_pr, const svo_dmatch* pre_matches,
+              int32_t n_pm, const svo_keypoint* cur_left, const uint8_t* cur_desc_left, int32_t n_cl,
+              const svo_keypoint* cur_right, const uint8_t* cur_desc_right, int32_t n_cr, const svo_dmatch* cur_matches,
+              int32_t n_cm, int64_t* out_pairs, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    const int kc = c->P.p.kp_cap;
+    const int32_t counts[6] = {n_pl, n_pr, n_pm, n_cl, n_cr, n_cm};
+    for (int32_t v : counts)
+        if (v < 0 || v > kc) return fail(c, SVO_ERR_ARG, "more keypoints / matches than the context's capacity (kps_to_detect[0])");
+    if ((n_pl && (!pre_left || !pre_desc_left)) || (n_pr && (!pre_right || !pre_desc_right)) || (n_pm && !pre_matches) ||
+        (n_cl && (!cur_left || !cur_desc_left)) || (n_cr && (!cur_right || !cur_desc_right)) || (n_cm && !cur_matches) ||
+        (cap > 0 && !out_pairs) || cap < 0)
+        return fail(c, SVO_ERR_ARG, "NULL argument");
+    if (c->pend_count != 0) return fail(c, SVO_ERR_STATE, "batches are in flight");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const int hs = c->hidden_slot;
+    int rc = set_single_slot(c, hs);
+    if (rc) return rc;
+    SlotState s;
+    memset(&s, 0, sizeof(s));
+    s.cur = 0; s.has_cur = 1; s.has_prev = 1;      // buffer 0 = current frame, buffer 1 = previous frame
+    CU(c, cudaStreamSynchronize(c->stream));
+    rc = put_state(c, hs, s);
+    if (rc) return rc;
+    Result zero;
+    memset(&zero, 0, sizeof(zero));
+    CU(c, cudaMemcpy(c->P.result + hs, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+    rc = upload_frame(c, hs, 1, pre_left, pre_desc_left, n_pl, pre_right, pre_desc_right, n_pr, pre_matches, n_pm);
+    if (rc) return rc;
+    rc = upload_frame(c, hs, 0, cur_left, cur_desc_left, n_cl, cur_right, cur_desc_right, n_cr, cur_matches, n_cm);
+    if (rc) return rc;
+    int L = 0;
+    RansacScratch RS = c->RS;
+    CU(c, launch_track_match(c->P, 1, c->stream, &L));
+    if (c->cfg.fundmat_filter) CU(c, launch_ransac(c->P, RS, 1, c->stream, &L));
+    CU(c, launch_consistency(c->P, 1, c->stream, &L));
+    c->launches += L;
+    CU(c, cudaStreamSynchronize(c->stream));
+    int n = 0;
+    CU(c, cudaMemcpy(&n, c->P.n_tracked + hs, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int2> tmp((size_t)n);
+    if (n) CU(c, cudaMemcpy(tmp.data(), c->P.tracked + (size_t)hs * kc, (size_t)n * sizeof(int2), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; ++i) { out_pairs[2 * i] = tmp[i].x; out_pairs[2 * i + 1] = tmp[i].y; }
+    return n;
+}
+
+int svo_optimize(svo_ctx* c, int32_t slot, const int64_t* tracked_pairs, int32_t n_tracked, const svo_dmatch* pre_matches,
+                 int32_t n_pre, const svo_dmatch* cur_matches, int32_t n_cur, const svo_keypoint* pre_left, int32_t n_pl,
+                 const svo_keypoint* pre_right, int32_t n_pr, const svo_keypoint* cur_left, int32_t n_cl,
+                 const svo_keypoint* cur_right, int32_t n_cr, const svo_camera* cam, int32_t use_custom_initial_pose,
+                 const double* ini_estimation, svo_result* result) {
+    return svo_get_change_in_pose(c, slot, tracked_pairs, n_tracked, pre_matches, n_pre, cur_matches, n_cur, pre_left, n_pl,
+                                  pre_right, n_pr, cur_left, n_cl, cur_right, n_cr, cam, use_custom_initial_pose, ini_estimation,
+                                  result);
+}
+
 int svo_get_change_in_pose(svo_ctx* c, int32_t slot, const int64_t* tracked_pairs, int32_t n_tracked,
                            const svo_dmatch* pre_matches, int32_t n_pre, const svo_dmatch* cur_matches, int32_t n_cur,
                            const svo_keypoint* pre_left, int32_t n_pl, const svo_keypoint* pre_right, int32_t n_pr,

@@ -382,6 +382,37 @@ def test_get_change_in_pose_aux_nms_collisions_and_response_ties():
             ctx.close()
 
 
+@pytest.mark.parametrize("ifm_method", [0, 1])
+def test_track_stage_alone_on_caller_data(ifm_method):
+    """svo_track = stage4_track on caller data (both trackers): the tracked pairs the oracle derives from the same two
+    frames; then svo_optimize (= getChangeInPose) on those pairs gives the pipeline's pose."""
+    frames, cam = synth.make_sequence("c1", seed=13, n_frames=3)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, if_match_method=ifm_method)
+    try:
+        def masks(p1, p2):
+            return None if len(p1) < 7 else ctx.fundmat_ransac(p1, p2)[1]
+        est = orc.OracleEstimator(orc.Params(orb_nfeats=100, ifm_method=ifm_method), backend="port", ransac=masks)
+        outs = [est.process_new_image_pair(L, R, ocam(cam)) for (L, R) in frames]
+        for i in (1, 2):
+            p, q = outs[i - 1]["frame"], outs[i]["frame"]
+            got = ctx.track((p.kpsL, p.descL, p.kpsR, p.descR, p.matches), (q.kpsL, q.descL, q.kpsR, q.descR, q.matches))
+            assert np.array_equal(got, outs[i]["tracked"]) and len(got) > 20
+        z = np.zeros(0, capi.KEYPOINT), np.zeros((0, 32), np.uint8), np.zeros(0, capi.KEYPOINT), np.zeros((0, 32), np.uint8), np.zeros(0, capi.DMATCH)
+        q = outs[1]["frame"]
+        assert len(ctx.track(z, (q.kpsL, q.descL, q.kpsR, q.descR, q.matches))) == 0     # empty previous frame
+        assert len(ctx.track((q.kpsL, q.descL, q.kpsR, q.descR, q.matches), z)) == 0     # empty current frame
+        bad = q.matches.copy()
+        bad["trainIdx"][0] = len(q.kpsR)
+        with pytest.raises(capi.SvoError) as e:
+            ctx.track((q.kpsL, q.descL, q.kpsR, q.descR, bad), (q.kpsL, q.descL, q.kpsR, q.descR, q.matches))
+        assert e.value.code == capi.SVO_ERR_ARG
+        # the sequence slot was not touched: the pipeline on slot 0 still starts from scratch
+        r = ctx.process_batch([frames[0][0]], [frames[0][1]], [gcam(cam)])[0]
+        assert r.error_code == capi.VOEC["voecFirstIteration"]
+    finally:
+        ctx.close()
+
+
 def test_get_change_in_pose_degenerate():
     from katdata import kat_inputs as _kat_inputs
     a, cam, N = _kat_inputs(False, 1.2, 0.9)
