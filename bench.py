@@ -336,7 +336,7 @@ def single_pair_latency(capi, seqs, gc, W, H, nfeats, device_index, n=60):
             "note": "batch of one: the kernels are latency-bound here, throughput needs many sequences per step"}
 
 
-def octaves_throughput(capi, torch, dev, gc, W, H, nfeats, device_index, n_octaves=3, batch=256, steps=20, warmup=3):
+def octaves_throughput(capi, torch, dev, gc, W, H, nfeats, device_index, peak, n_octaves=3, batch=256, steps=20, warmup=3):
     """params_rectify.nOctaves = 3, the reference's ctor default (stage1_rectify.cpp:28): the pyramid is built on the
     device and stages 2-4 run per octave before one flattened stage 5.  Device-resident images, CUDA events on the
     library's stream; a second line beside the headline (which runs the one-octave INI of SURVEY Appendix C)."""
@@ -363,13 +363,33 @@ def octaves_throughput(capi, torch, dev, gc, W, H, nfeats, device_index, n_octav
     ms = e0.elapsed_time(e1) / steps
     res = ctx.fetch_results(batch)
     stats = np.mean([ctx.octave_stats(s) for s in range(0, batch, max(1, batch // 16))], axis=0)
+    # the pyramid alone: the one streaming, HBM-bound kernel of this path.  Algorithmic bytes per level = source image
+    # read once + a quarter of it written; inputs cycle through the distinct batches (larger than L2 together)
+    pyr_ms = []
+    with torch.cuda.stream(stream):
+        for t in range(3 + 10):
+            L, R = dev[t % len(dev)]
+            p0 = torch.cuda.Event(enable_timing=True)
+            p1 = torch.cuda.Event(enable_timing=True)
+            p0.record()
+            ctx.build_pyramid_device(L.data_ptr(), R.data_ptr(), batch, W, W * H)
+            p1.record()
+            p1.synchronize()
+            if t >= 3:
+                pyr_ms.append(p0.elapsed_time(p1))
+    pyr_bytes = sum(2 * batch * (w * h + (w // 2) * (h // 2)) for (w, h) in [tuple(o[:2]) for o in ctx.octave_info[:-1]])
+    pyr_t = float(np.median(pyr_ms))
     out = {"n_octaves": n_octaves, "pairs_per_step": batch, "ms_per_step": round(ms, 4),
            "pairs_per_s": round(batch / ms * 1e3, 1), "valid_results": f"{sum(int(r.valid) for r in res)}/{batch}",
            "launches_per_step": (ctx.kernel_launches() - l0) // steps,
            "per_octave_mean": {"keypoints_left": [round(float(v), 1) for v in stats[:, 0]],
                                "stereo_matches": [round(float(v), 1) for v in stats[:, 2]],
                                "tracked_pairs": [round(float(v), 1) for v in stats[:, 3]]},
-           "octave_sizes": [list(o[:2]) for o in ctx.octave_info], "quotas": [o[2] for o in ctx.octave_info]}
+           "octave_sizes": [list(o[:2]) for o in ctx.octave_info], "quotas": [o[2] for o in ctx.octave_info],
+           "pyramid": {"kernel": "pyramid_kernel (all levels of one step)", "ms": round(pyr_t, 4), "algo_bytes": pyr_bytes,
+                       "hbm_gbs": round(pyr_bytes / (pyr_t * 1e-3) / 1e9, 1),
+                       "hbm_frac": round(pyr_bytes / (pyr_t * 1e-3) / 1e9 / peak, 4) if peak else None,
+                       "note": "two launches (levels 1 and 2) timed together with CUDA events on the library's stream"}}
     ctx.close()
     return out
 
@@ -630,7 +650,7 @@ def run_gpu(args):
         int_roof = 1.0 / max(HM_POPC_PFX / pipe["popc_per_s"], HM_ALU_PFX / pipe["lop3_per_s"])
         micro = stage1 = latency = octaves = None
         if not args.no_micro:
-            octaves = octaves_throughput(capi, torch, dev, gc, W, H, nfeats, local)
+            octaves = octaves_throughput(capi, torch, dev, gc, W, H, nfeats, local, peak)
             micro, _ = c5_microbench(ctx, torch, stream, torch.device("cuda", local), pipe, peak, reps=64, iters=5)
             stage1 = stage1_microbench(ctx, torch, stream, torch.device("cuda", local), W, H, peak)
             latency = single_pair_latency(capi, seqs, gc, W, H, nfeats, local)

@@ -236,6 +236,12 @@ int svo_prepare_rectify_device(svo_ctx* ctx, int32_t n, const uint8_t* d_left, c
                                size_t stride_bytes, size_t image_pitch, int32_t channels,
                                uint8_t* d_out_left, uint8_t* d_out_right);
 
+/* the image pyramid alone (CImagePyramid::buildPyramidFast, stage1_rectify.cpp:80-83) for n device-resident gray pairs
+ * (layout as svo_process_batch_device): octaves 1 .. n_octaves-1 into the context's planes (svo_get_pyramid_plane reads
+ * them).  Only enqueues work on the context's stream; needs n_octaves > 1. */
+int svo_build_pyramid_device(svo_ctx* ctx, int32_t n, const uint8_t* d_left, const uint8_t* d_right, size_t stride_bytes,
+                             size_t image_pitch_bytes);
+
 /* ---- per-stage entries (the internal seams, usable on their own) ---------------------------- */
 /* FAST + ORB::compute + m_non_max_sup + m_update_indexes for one host image
  * (stage2_detect.cpp:502-515, 590-597, 618).  Uses slot 0's scratch; does not touch slot state. */

@@ -36,7 +36,7 @@ EXPORTS = [
     "svo_get_projected_coords", "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
     "svo_get_keypoints_oct", "svo_get_descriptors_oct", "svo_get_matches_oct", "svo_get_match_ids_oct",
     "svo_get_tracked_pairs_oct", "svo_get_octave_info", "svo_get_octave_stats", "svo_get_pyramid_plane",
-    "svo_track", "svo_optimize",
+    "svo_track", "svo_optimize", "svo_build_pyramid_device",
 ]
 
 
@@ -417,6 +417,10 @@ class Context:
         self._check(lib().svo_prepare_rectify_device(self._h, n, C.c_void_p(d_left), C.c_void_p(d_right), C.c_size_t(stride),
                                                      C.c_size_t(image_pitch), channels, C.c_void_p(d_out_left),
                                                      C.c_void_p(d_out_right)))
+
+    def build_pyramid_device(self, d_left, d_right, n, stride, image_pitch):
+        self._check(lib().svo_build_pyramid_device(self._h, n, C.c_void_p(d_left), C.c_void_p(d_right), C.c_size_t(stride),
+                                                   C.c_size_t(image_pitch)))
 
     def set_concurrency(self, chunks):
         self._check(lib().svo_set_concurrency(self._h, int(chunks)))

@@ -747,6 +747,30 @@ int svo_prepare_rectify(svo_ctx* c, const uint8_t* left, const uint8_t* right, s
     return SVO_OK;
 }
 
+int svo_build_pyramid_device(svo_ctx* c, int32_t n, const uint8_t* d_left, const uint8_t* d_right, size_t stride, size_t image_pitch) {
+    if (!c) return SVO_ERR_ARG;
+    if (n <= 0 || n > c->cfg.max_seqs || !d_left || !d_right) return fail(c, SVO_ERR_ARG, "bad argument");
+    if (stride < (size_t)c->cfg.width) return fail(c, SVO_ERR_ARG, "stride smaller than the image width");
+    if (c->n_oct < 2) return fail(c, SVO_ERR_STATE, "the context has one octave: there is no pyramid to build");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const uint8_t* srcL = d_left;
+    const uint8_t* srcR = d_right;
+    size_t src_stride = stride, src_pitch = image_pitch;
+    int sw = c->cfg.width, sh = c->cfg.height, L = 0;
+    for (int k = 1; k < c->n_oct; ++k) {
+        OctaveCtx& o = c->oct[k];
+        PyramidArgs A;
+        A.srcL = srcL; A.srcR = srcR; A.src_stride = src_stride; A.src_image_pitch = src_pitch;
+        A.dstL = o.imgL; A.dstR = o.imgR; A.dst_stride = (size_t)o.pitch; A.dst_image_pitch = (size_t)o.pitch * o.H;
+        A.sw = sw; A.sh = sh;
+        CU(c, launch_pyramid_level(A, n, pyramid_method(c->cfg.pyr_mode, sw), c->stream, &L));
+        srcL = o.imgL; srcR = o.imgR; src_stride = (size_t)o.pitch; src_pitch = A.dst_image_pitch;
+        sw = o.W; sh = o.H;
+    }
+    c->launches += L;
+    return SVO_OK;
+}
+
 int svo_process_batch_device(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t* d_left, const uint8_t* d_right,
                              size_t stride, size_t image_pitch, const svo_camera* cams, const uint8_t* repeat) {
     if (!c) return SVO_ERR_ARG;

@@ -301,3 +301,29 @@ def test_host_shim_vo_save_files_dumps(tmp_path):
             assert np.array_equal(res, np.loadtxt(outdir / f"out_residual_final_{i:04d}.txt").reshape(-1))
     finally:
         ctx.close()
+
+
+def test_build_pyramid_device_alone():
+    """svo_build_pyramid_device (the pyramid of stage1_rectify.cpp:80-83 on images already in HBM) == the oracle's
+    pyramid; a one-octave context refuses the call."""
+    import torch
+    frames, cam = synth.make_sequence("c2", seed=3, n_frames=1)
+    L, R = frames[0]
+    ctx = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=3, n_octaves=3)
+    try:
+        dL = torch.from_numpy(np.stack([L, R, L])).cuda()
+        dR = torch.from_numpy(np.stack([R, L, R])).cuda()
+        ctx.build_pyramid_device(dL.data_ptr(), dR.data_ptr(), 3, 640, 640 * 480)
+        pl, pr = orc.build_pyramid(L, 3), orc.build_pyramid(R, 3)
+        for k in (1, 2):
+            assert np.array_equal(ctx.pyramid_plane(0, k, 0), pl[k]) and np.array_equal(ctx.pyramid_plane(0, k, 1), pr[k])
+            assert np.array_equal(ctx.pyramid_plane(1, k, 0), pr[k]) and np.array_equal(ctx.pyramid_plane(2, k, 1), pr[k])
+    finally:
+        ctx.close()
+    one = capi.Context(width=640, height=480, orb_nfeats=500, max_seqs=1)
+    try:
+        with pytest.raises(capi.SvoError) as e:
+            one.build_pyramid_device(dL.data_ptr(), dR.data_ptr(), 1, 640, 640 * 480)
+        assert e.value.code == capi.SVO_ERR_STATE
+    finally:
+        one.close()
