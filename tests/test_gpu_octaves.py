@@ -313,6 +313,7 @@ def test_build_pyramid_device_alone():
     try:
         dL = torch.from_numpy(np.stack([L, R, L])).cuda()
         dR = torch.from_numpy(np.stack([R, L, R])).cuda()
+        torch.cuda.synchronize()                   # the library works on its own stream
         ctx.build_pyramid_device(dL.data_ptr(), dR.data_ptr(), 3, 640, 640 * 480)
         pl, pr = orc.build_pyramid(L, 3), orc.build_pyramid(R, 3)
         for k in (1, 2):

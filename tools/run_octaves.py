@@ -37,6 +37,7 @@ def main():
         L = np.stack([seqs[i % 4][0][t][0] for i in range(B)])
         R = np.stack([seqs[i % 4][0][t][1] for i in range(B)])
         dev.append((torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()))
+    torch.cuda.synchronize()                       # the library works on its own stream
     ctx = capi.Context(width=W, height=H, orb_nfeats=cfg["orb_nfeats"], max_seqs=B, n_octaves=args.octaves)
     stream = torch.cuda.ExternalStream(ctx.stream())
     cams = [gc] * B
