@@ -65,6 +65,21 @@ def test_no_cpu_fallback_without_device(built_lib):
     assert e.value.code == capi.SVO_ERR_CUDA and "no CPU fallback" in str(e.value)
 
 
+def test_ransac_is_built_without_fma_contraction(built_lib):
+    """The F-matrix RANSAC kernel must evaluate the same IEEE operations as the host build of fundmat_core.cuh that is
+    pinned against cv2: ransac.cu is compiled with --fmad=false, everything else with --fmad=true."""
+    mk = open(os.path.join(ROOT, "stereo_vo_b200", "csrc", "Makefile")).read()
+    assert re.search(r"^ransac\.o: NVFLAGS := .*--fmad=false", mk, re.M)
+    log = os.path.join(ROOT, "stereo_vo_b200", "csrc", "ransac.ptxas.log")
+    assert os.path.exists(log)                    # written by the build; the object exists
+    import shutil
+    if shutil.which("cuobjdump"):
+        sass = subprocess.run(["cuobjdump", "-sass", "-fun", "fundmat_kernel", os.path.join(ROOT, "stereo_vo_b200", "csrc", "ransac.o")],
+                              capture_output=True, text=True).stdout
+        if "DMUL" in sass:                        # explicit products stay products (DFMA only inside division / sqrt / libm)
+            assert sass.count("DMUL") > 200
+
+
 def test_product_does_not_reference_oracle():
     """The shipped package must never import, link or call anything under oracle/."""
     pkg = os.path.join(ROOT, "stereo_vo_b200")
