@@ -33,6 +33,7 @@ static const char* kKernelNames[KT_COUNT] = {
     "gn_kernel"};
 
 enum { kMaxChunks = 8, kDefaultChunks = 2, kMinChunkItems = 32 };
+enum { kMetaRing = 4 };   // pinned staging sets for the batch description of svo_process_batch_device (see upload_batch_meta)
 enum { kDepth = 3 };   // batches in flight (svo_submit_batch / svo_wait_batch): with three staging buffers the copy stream
                        // never waits for the host to see a batch finish before the next upload can start
 
@@ -84,7 +85,14 @@ struct svo_ctx {
     uint32_t* d_sort_scratch = nullptr;
     uint2* d_list_scratch = nullptr;
     uint32_t* d_key_scratch = nullptr;
-    // pinned host staging
+    // pinned host staging of svo_process_batch_device's batch description: a ring, so that a call never overwrites
+    // memory an earlier call's asynchronous copy has not read yet
+    int32_t* m_slots[kMetaRing] = {};
+    uint8_t* m_repeat[kMetaRing] = {};
+    Camera* m_cams[kMetaRing] = {};
+    cudaEvent_t m_ev[kMetaRing] = {};
+    int m_next = 0;
+    // pinned host staging (synchronous entry points)
     int32_t* h_slots = nullptr;
     uint8_t* h_repeat = nullptr;
     Camera* h_cams = nullptr;
@@ -289,13 +297,23 @@ int upload_batch_meta(svo_ctx* c, int n, const int32_t* slots, const svo_camera*
         if (!valid_slot(c, s)) return fail(c, SVO_ERR_ARG, "slot index out of range");
         if (seen[s]) return fail(c, SVO_ERR_ARG, "duplicate slot in one batch");
         seen[s] = 1;
-        c->h_slots[i] = s;
-        memcpy(&c->h_cams[i], &cams[i], sizeof(Camera));
-        c->h_repeat[i] = repeat ? repeat[i] : 0;
     }
-    CU(c, cudaMemcpyAsync(c->P.slots, c->h_slots, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_cams_batch, c->h_cams, n * sizeof(Camera), cudaMemcpyHostToDevice, c->stream));
-    if (repeat) CU(c, cudaMemcpyAsync(c->d_repeat, c->h_repeat, n, cudaMemcpyHostToDevice, c->stream));
+    // The copies below are asynchronous (pinned memory): the staging set must stay untouched until they have run.
+    // Calls may follow each other without a synchronisation (bench.py enqueues hundreds of steps), so each call takes
+    // the next set of a small ring and first waits for the copies that last used it (an event that was never
+    // recorded counts as complete).
+    const int r = c->m_next;
+    c->m_next = (r + 1) % kMetaRing;
+    CU(c, cudaEventSynchronize(c->m_ev[r]));
+    for (int i = 0; i < n; ++i) {
+        c->m_slots[r][i] = slots ? slots[i] : i;
+        memcpy(&c->m_cams[r][i], &cams[i], sizeof(Camera));
+        c->m_repeat[r][i] = repeat ? repeat[i] : 0;
+    }
+    CU(c, cudaMemcpyAsync(c->P.slots, c->m_slots[r], n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_cams_batch, c->m_cams[r], n * sizeof(Camera), cudaMemcpyHostToDevice, c->stream));
+    if (repeat) CU(c, cudaMemcpyAsync(c->d_repeat, c->m_repeat[r], n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaEventRecord(c->m_ev[r], c->stream));
     return SVO_OK;
 }
 
@@ -558,6 +576,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     }
     HA(c->h_slots, S); HA(c->h_repeat, S); HA(c->h_cams, S); HA(c->h_results, S);
     for (int b = 0; b < kDepth; ++b) { HA(c->r_slots[b], S); HA(c->r_repeat[b], S); HA(c->r_cams[b], S); HA(c->r_res[b], S); HA(c->r_state[b], S); }
+    for (int r = 0; r < kMetaRing; ++r) { HA(c->m_slots[r], S); HA(c->m_repeat[r], S); HA(c->m_cams[r], S); }
 #undef DA
 #undef HA
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -567,6 +586,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
         e = cudaStreamCreateWithFlags(&c->aux[j], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[j], cudaEventDisableTiming);
     }
+    for (int r = 0; r < kMetaRing && e == cudaSuccess; ++r) e = cudaEventCreateWithFlags(&c->m_ev[r], cudaEventDisableTiming);
     for (int b = 0; b < kDepth && e == cudaSuccess; ++b) {
         e = cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming);
@@ -595,6 +615,7 @@ void svo_destroy(svo_ctx* c) {
         if (c->ev_join[j]) cudaEventDestroy(c->ev_join[j]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int r = 0; r < kMetaRing; ++r) if (c->m_ev[r]) cudaEventDestroy(c->m_ev[r]);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (void* p : c->dev_allocs) cudaFree(p);
     for (void* p : c->host_allocs) cudaFreeHost(p);
