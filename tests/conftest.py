@@ -22,3 +22,9 @@ def golden():
 def golden_stage1():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "golden_stage1.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_octaves():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_octaves.npz"), allow_pickle=False)

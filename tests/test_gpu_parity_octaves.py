@@ -328,3 +328,39 @@ def test_build_pyramid_device_alone():
         assert e.value.code == capi.SVO_ERR_STATE
     finally:
         one.close()
+
+
+def test_octaves_against_opencv_generated_goldens(golden_octaves):
+    """The device against tests/golden/golden_octaves.npz (real OpenCV FAST / ORB::compute / BFMatcher on every pyramid
+    level, F-matrix filter off): per-octave keypoints, descriptors, stereo matches, match IDs, tracked pairs, status,
+    pose; and the cvPyrDown level of a config-3 image against cv2.pyrDown's own output."""
+    g = golden_octaves
+    frames, cam = synth.make_sequence("c1", seed=3, n_frames=3)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, n_octaves=2, vo_use_matches_ids=1, fundmat_filter=0)
+    try:
+        for i, (L, R) in enumerate(frames):
+            r = ctx.process_batch([L], [R], [gcam(cam)])[0]
+            for k in range(2):
+                assert np.array_equal(xys(ctx.keypoints(0, 0, 0, octave=k)), g[f"f{i}_o{k}_kpsL"])
+                assert np.array_equal(xys(ctx.keypoints(0, 0, 1, octave=k)), g[f"f{i}_o{k}_kpsR"])
+                assert np.array_equal(ctx.descriptors(0, 0, 0, octave=k), g[f"f{i}_o{k}_descL"])
+                assert np.array_equal(ctx.descriptors(0, 0, 1, octave=k), g[f"f{i}_o{k}_descR"])
+                assert np.array_equal(mtuple(ctx.matches(0, 0, octave=k)), g[f"f{i}_o{k}_matches"])
+                assert np.array_equal(ctx.match_ids(0, 0, octave=k), g[f"f{i}_o{k}_ids"])
+                if i > 0:
+                    assert np.array_equal(ctx.tracked_pairs(0, octave=k), g[f"f{i}_o{k}_tracked"])
+            assert [r.error_code, int(r.valid), r.num_it, r.num_it_final] == g[f"f{i}_status"].tolist()
+            if i > 0:
+                np.testing.assert_allclose(r.delta_pose[:3], g[f"f{i}_delta"][:3], atol=POSE_TOL_RAD)
+                np.testing.assert_allclose(r.delta_pose[3:], g[f"f{i}_delta"][3:], atol=POSE_TOL_M)
+                assert np.array_equal(ctx.outliers(0), g[f"f{i}_outliers"])
+                np.testing.assert_allclose(ctx.residuals(0), g[f"f{i}_residual"], rtol=1e-6, atol=1e-9)
+    finally:
+        ctx.close()
+    f3, cam3 = synth.make_sequence("c3", seed=2, n_frames=1)
+    ctx = capi.Context(width=1242, height=375, orb_nfeats=1000, max_seqs=1, max_corners=32768, n_octaves=2)
+    try:
+        ctx.process_batch([f3[0][0]], [f3[0][1]], [gcam(cam3)])
+        assert np.array_equal(ctx.pyramid_plane(0, 1, 0), g["c3_pyrdown_L"]) and np.array_equal(ctx.pyramid_plane(0, 1, 1), g["c3_pyrdown_R"])
+    finally:
+        ctx.close()

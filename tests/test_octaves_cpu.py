@@ -98,3 +98,27 @@ def test_three_octaves_track_and_estimate_the_motion():
     g = r1["gn_dbg"]
     n0 = len(r1["tracked"][0])
     assert g["l1l"][n0:, 0].max() > 320 and np.all(g["l1l"][n0:n0 + len(r1["tracked"][1])] % 2 == 0)
+
+
+def test_oracle_port_reproduces_the_opencv_generated_octave_goldens(golden_octaves):
+    """tests/golden/golden_octaves.npz was generated with the real OpenCV calls on every pyramid level
+    (make_golden_octaves.py); the all-C++ restatement must reproduce it bit for bit."""
+    g = golden_octaves
+    frames, cam = synth.make_sequence("c1", seed=3, n_frames=3)
+    est = orc.OracleEstimatorOctaves(orc.Params(orb_nfeats=100, nOctaves=2, vo_use_matches_ids=True), backend="port", ransac="off")
+    for i, (L, R) in enumerate(frames):
+        o = est.process_new_image_pair(L, R, ocam(cam))
+        for k, f in enumerate(o["frames"]):
+            assert np.array_equal(np.stack([f.kpsL["x"], f.kpsL["y"], f.kpsL["response"]], 1).astype(np.int32), g[f"f{i}_o{k}_kpsL"])
+            assert np.array_equal(f.descL, g[f"f{i}_o{k}_descL"]) and np.array_equal(f.descR, g[f"f{i}_o{k}_descR"])
+            assert np.array_equal(np.stack([f.matches["queryIdx"], f.matches["trainIdx"], f.matches["distance"].astype(np.int32)], 1),
+                                  g[f"f{i}_o{k}_matches"])
+            assert np.array_equal(f.ids, g[f"f{i}_o{k}_ids"])
+            if i > 0:
+                assert np.array_equal(o["tracked"][k], g[f"f{i}_o{k}_tracked"])
+        assert [o["error_code"], int(o["valid"]), o["num_it"], o["num_it_final"]] == g[f"f{i}_status"].tolist()
+        if i > 0:
+            assert np.array_equal(o["pose"]["delta"], g[f"f{i}_delta"]) and np.array_equal(o["outliers"], g[f"f{i}_outliers"])
+    f3, _ = synth.make_sequence("c3", seed=2, n_frames=1)
+    assert np.array_equal(orc.build_pyramid(f3[0][0], 2)[1], g["c3_pyrdown_L"])
+    assert np.array_equal(orc.build_pyramid(f3[0][1], 2)[1], g["c3_pyrdown_R"])
