@@ -10,6 +10,8 @@
 #include "ransac.cuh"
 #include "svo_internal.cuh"
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler (nsys / ncu --nvtx) is attached
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -121,6 +123,16 @@ struct svo_ctx {
 
 namespace {
 
+// NVTX range with the section names of the reference's CTimeLogger (m_profiler.enter/leave: "_stg2" ... "_stg5",
+// "processNewImagePair"; libstereo-odometry.h:521-524): the ranges cover the ENQUEUE of a stage's kernels on the host,
+// profilers project them onto the kernels they launch.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 int fail(svo_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
@@ -195,7 +207,9 @@ int enqueue_octaves(svo_ctx* c, const Pools& P0, const RansacScratch& RS0, int a
     const uint8_t* srcR = d_right + a * image_pitch;
     size_t src_stride = stride, src_pitch = image_pitch;
     int sw = c->cfg.width, sh = c->cfg.height;
+    static const char* const kOctaveRange[kMaxOctaves] = {"_stg2-4.oct=0", "_stg2-4.oct=1", "_stg2-4.oct=2", "_stg2-4.oct=3"};
     for (int k = 0; k < c->n_oct; ++k) {
+        NvtxRange range(kOctaveRange[k]);
         Pools P = k == 0 ? P0 : c->oct[k].P;
         RansacScratch RS = k == 0 ? RS0 : c->oct[k].RS;
         P.slots = P0.slots;
@@ -222,6 +236,7 @@ int enqueue_octaves(svo_ctx* c, const Pools& P0, const RansacScratch& RS0, int a
         if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, RS, n, st, &L, nullptr));
         CU(c, launch_consistency(P, n, st, &L, nullptr));
     }
+    NvtxRange range("_stg5");
     Pools PG = c->PG;
     PG.slots = P0.slots;
     CU(c, launch_flatten_octaves(PG, c->GG, c->OL, n, st, &L));
@@ -243,15 +258,25 @@ int enqueue_items(svo_ctx* c, int a, int n, const uint8_t* d_left, const uint8_t
     L += 2;
     const size_t img2 = 2 * (size_t)a;              // scratch indexed by (item, side)
     if (c->n_oct > 1) return enqueue_octaves(c, P, RS, a, n, d_left, d_right, stride, image_pitch, st, L);
-    CU(c, launch_detect(P, n, d_left + a * image_pitch, d_right + a * image_pitch, stride, image_pitch, c->pitch,
-                        c->d_occ + img2 * c->occ_words, c->occ_words, c->d_sort_scratch + img2 * c->cfg.max_corners,
-                        c->d_list_scratch + img2 * 3 * (c->cfg.max_corners / 16 + 2),
-                        c->d_key_scratch + img2 * c->cfg.max_corners, st, &L, t));
-    CU(c, launch_match_lr(P, n, st, &L, t));
-    CU(c, launch_track_match(P, n, st, &L, t));
-    if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, RS, n, st, &L, t));
-    else if (t) { t->mark(st); t->mark(st); }
-    CU(c, launch_consistency(P, n, st, &L, t));
+    {
+        NvtxRange r("_stg2");
+        CU(c, launch_detect(P, n, d_left + a * image_pitch, d_right + a * image_pitch, stride, image_pitch, c->pitch,
+                            c->d_occ + img2 * c->occ_words, c->occ_words, c->d_sort_scratch + img2 * c->cfg.max_corners,
+                            c->d_list_scratch + img2 * 3 * (c->cfg.max_corners / 16 + 2),
+                            c->d_key_scratch + img2 * c->cfg.max_corners, st, &L, t));
+    }
+    {
+        NvtxRange r("_stg3");
+        CU(c, launch_match_lr(P, n, st, &L, t));
+    }
+    {
+        NvtxRange r("_stg4");
+        CU(c, launch_track_match(P, n, st, &L, t));
+        if (c->cfg.fundmat_filter) CU(c, launch_ransac(P, RS, n, st, &L, t));
+        else if (t) { t->mark(st); t->mark(st); }
+        CU(c, launch_consistency(P, n, st, &L, t));
+    }
+    NvtxRange r("_stg5");
     CU(c, launch_gn(P, c->G, n, GN_FROM_TRACKED, /*custom pose=*/0, /*assume_fast_kps=*/1, st, &L, t));
     return SVO_OK;
 }
@@ -263,6 +288,7 @@ int enqueue_items(svo_ctx* c, int a, int n, const uint8_t* d_left, const uint8_t
 // step runs on the one stream so that every kernel is timed alone.
 int run_step(svo_ctx* c, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride, size_t image_pitch,
              bool have_repeat) {
+    NvtxRange range("processNewImagePair");
     int& L = c->launches_i;
     L = 0;
     StepTimer tm;
