@@ -118,6 +118,37 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, valid
 
 
+def _cpu_single(args):
+    frames, cam, n_pairs, threads = args
+    import cv2
+    cv2.setNumThreads(threads)            # 1 = serial OpenCV; -1 (cv2's reset value) = OpenCV's default thread pool
+    from oracle import oracle as orc
+    camo = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=500), backend="cv2", ransac="cv2")
+    est.process_new_image_pair(*frames[0], camo)
+    t0 = time.perf_counter()
+    for t in range(1, n_pairs + 1):
+        est.process_new_image_pair(*frames[pingpong(t, len(frames))], camo)
+    return n_pairs / (time.perf_counter() - t0), cv2.getNumThreads()
+
+
+def cpu_single_process_variants(seqs, cam, n_pairs=40):
+    """one process with one OpenCV thread, and one process with OpenCV's default threads (each in a
+    fresh process, so that the thread setting cannot leak into the throughput workers)."""
+    import multiprocessing as mp
+    try:
+        import cv2  # noqa: F401
+    except Exception:
+        return None
+    out = {}
+    ctxmp = mp.get_context("fork")
+    for name, threads in (("1_process_1_thread", 1), ("1_process_default_threads", -1)):
+        with ctxmp.Pool(1) as pool:
+            rate, nthr = pool.map(_cpu_single, [(seqs[0], cam, n_pairs, threads)])[0]
+        out[name] = {"pairs_per_s": round(rate, 2), "opencv_threads": nthr, "sample": f"{n_pairs} consecutive {CONFIG} pairs"}
+    return out
+
+
 def cpu_throughput(seqs, cam, pairs_per_proc, procs):
     """pairs/s of the CPU oracle with `procs` processes x 1 OpenCV thread, one sequence each."""
     import multiprocessing as mp
@@ -700,7 +731,7 @@ def run_gpu(args):
             seqs_cpu = seqs
             procs = os.cpu_count() or 1
             v, info = cpu_throughput(seqs_cpu, cam, args.cpu_pairs, procs)
-            line["cpu_baseline"] = dict(info, value=v, unit=UNIT)
+            line["cpu_baseline"] = dict(info, value=v, unit=UNIT, variants=cpu_single_process_variants(seqs_cpu, cam))
         emit(line)
     ctx.close()
     if world > 1:
