@@ -665,10 +665,13 @@ def run_gpu(args):
         dom = max(kernel_ms, key=kernel_ms.get)
         dom_gbs = kernels[dom]["gbs"]
         traffic = None
+        sm_pct = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(dom)
+                tj = json.load(open(tp))
+                traffic = tj.get(dom)
+                sm_pct = tj.get("sm_throughput_pct", {}).get(dom)
             except Exception:
                 traffic = None
         # Hamming stage against its binding (integer-pipe) roof.  The pipeline kernels test a 128-bit prefix of every
@@ -711,7 +714,9 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                          "frac": dom_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "the dominant kernel is integer-ALU bound (FAST ring test + arc min/max), not HBM bound; "
-                                 "frac is reported against HBM as the contract asks"},
+                                 "frac is reported against HBM as the contract asks",
+                         "binding_resource": {"what": "SM instruction issue / ALU pipes", "ncu_sm_throughput_pct": sm_pct,
+                                              "source": "profiles/traffic.json <- profiles/r01z_step_full.md (ncu --set full)"}},
             "kernels": kernels,
             "match_stage": {"pair_distances_per_s": pairdist / (hm_ms * 1e-3) if hm_ms else None,
                             "int_pipe_roof_pair_distances_per_s": int_roof,
