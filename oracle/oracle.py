@@ -293,6 +293,17 @@ def cv2_fast_orb(img, th):
     return cv2_kps_to_array(kps), np.ascontiguousarray(desc)
 
 
+def cv2_orb_detect_and_compute(img, n_feats_to_extract, nlevels, fast_th):
+    """stage2_detect.cpp:484-496 (dmORB, OpenCV >= 3): oriented multi-scale ORB in one call.  There is no C++ restatement
+    of this branch yet: the real OpenCV is the only back-end."""
+    cv2 = _cv2()
+    orb = cv2.ORB_create(int(n_feats_to_extract), 1.2, int(nlevels), 31, 0, 2, cv2.ORB_HARRIS_SCORE, 31, int(fast_th))
+    kps, desc = orb.detectAndCompute(img, None)
+    if desc is None:
+        desc = np.zeros((0, 32), np.uint8)
+    return cv2_kps_to_array(kps), np.ascontiguousarray(desc)
+
+
 def cv2_bf_match(q, t):
     """stage3_match_left_right.cpp:88-94 with the real OpenCV."""
     cv2 = _cv2()
@@ -330,6 +341,8 @@ class Params:
 
     def __init__(self, **kw):
         # TDetectParams (H:383-447)
+        self.detect_method = 1                # TDMethod: 0 = dmORB (cv2 back-end only), 1 = dmFAST_ORB (H:389)
+        self.orb_nlevels = 8
         self.orb_nfeats = 500
         self.initial_FAST_threshold = 20
         self.non_maximal_suppression = True
@@ -418,13 +431,17 @@ class OracleEstimator:
     def detect(self, img):
         H, W = img.shape
         th = self.m_current_fast_th
-        if self.backend == "cv2":
+        if self.p.detect_method == 0:              # dmORB, S2:458-496: more features when the NMS thins them out afterwards
+            assert self.backend == "cv2", "dmORB has no C++ restatement: backend must be cv2"
+            n_extract = int(1.5 * self.p.orb_nfeats) if self.p.non_maximal_suppression else int(self.p.orb_nfeats)
+            kps, desc = cv2_orb_detect_and_compute(img, n_extract, self.p.orb_nlevels, th)
+        elif self.backend == "cv2":
             kps, desc = cv2_fast_orb(img, th)
         else:
             kps = fast9(img, th)
             kps, desc = orb_compute(img, kps)
         raw = (kps.copy(), desc.copy())
-        nOct = int(self.p.nOctaves)
+        nOct = 1 if self.p.detect_method == 0 else int(self.p.nOctaves)      # S1:80: ORB builds its own pyramid
         quota = int(self.p.orb_nfeats * (2 * nOct) / (2 ** nOct - 1))  # S2:405
         if self.p.non_maximal_suppression:
             kps, desc, sel = non_max_sup(quota, kps, desc, self.p.min_distance, H, W, self.sort_mode)
