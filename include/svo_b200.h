@@ -314,6 +314,12 @@ int svo_get_projected_coords(svo_ctx* ctx, const svo_dmatch* pre_matches, int32_
  * when no model was found or n < 7. */
 int svo_fundmat_ransac(svo_ctx* ctx, const float* p1, const float* p2, int32_t n, uint8_t* mask);
 
+/* parity seam inside the call above: the 7-point solver findFundamentalMat runs on every RANSAC sample
+ * (stage4_match_consecutive.cpp:202 -> cv::findFundamentalMat -> run7Point; what cv::findFundamentalMat(7 points,
+ * FM_7POINT) returns).  p1, p2: n_sets x 7 x 2 float32 (host); F: n_sets x 27 doubles (up to three row-major 3x3
+ * models per sample); n_models: n_sets counts.  Returns n_sets. */
+int svo_fundmat_7point(svo_ctx* ctx, const float* p1, const float* p2, int32_t n_sets, double* F, int32_t* n_models);
+
 /* parity seam inside stage 2: the intermediate image planes of the last step for (slot, side).
  * plane 0 = the 7x7 sigma=2 blur cv::ORB::compute applies (stage2_detect.cpp:512), plane 1 = FAST score
  * after 3x3 NMS and the 31-px border filter (0 = no corner).  out: height*width bytes, tightly packed. */

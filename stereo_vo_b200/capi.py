@@ -30,7 +30,7 @@ EXPORTS = [
     "svo_get_keypoints", "svo_get_descriptors", "svo_get_matches", "svo_get_match_ids", "svo_get_tracked_pairs",
     "svo_get_residuals", "svo_get_outliers", "svo_get_track_candidates", "svo_get_plane",
     "svo_detect", "svo_match_hamming", "svo_match_hamming_device", "svo_match_lr", "svo_get_change_in_pose",
-    "svo_fundmat_ransac", "svo_abi_version", "svo_kernel_launches", "svo_stream",
+    "svo_fundmat_ransac", "svo_fundmat_7point", "svo_abi_version", "svo_kernel_launches", "svo_stream",
     "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks", "svo_set_concurrency",
     "svo_set_input_format", "svo_set_rectify_maps", "svo_prepare_rectify", "svo_prepare_rectify_device",
     "svo_get_projected_coords", "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
@@ -367,6 +367,16 @@ class Context:
         mask = np.zeros(max(len(p1), 1), np.uint8)
         n = self._check(lib().svo_fundmat_ransac(self._h, _vp(p1), _vp(p2), len(p1), _vp(mask)))
         return n, mask[:len(p1)].copy()
+
+    def fundmat_7point(self, p1, p2):
+        """run7Point on n sets of 7 correspondences: (n_models[n], F[n, 3, 3, 3])."""
+        p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 7, 2)
+        p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 7, 2)
+        n = len(p1)
+        F = np.zeros((max(n, 1), 27), np.float64)
+        nm = np.zeros(max(n, 1), np.int32)
+        self._check(lib().svo_fundmat_7point(self._h, _vp(p1), _vp(p2), n, _vp(F), _vp(nm)))
+        return nm[:n].copy(), F[:n].reshape(n, 3, 3, 3).copy()
 
     # ---- introspection --------------------------------------------------------------------------------
     def kernel_launches(self):

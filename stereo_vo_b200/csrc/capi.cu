@@ -1546,4 +1546,14 @@ int svo_fundmat_ransac(svo_ctx* c, const float* p1, const float* p2, int32_t n, 
     return inl;
 }
 
+int svo_fundmat_7point(svo_ctx* c, const float* p1, const float* p2, int32_t n_sets, double* F, int32_t* n_models) {
+    if (!c) return SVO_ERR_ARG;
+    if (n_sets < 0 || (n_sets > 0 && (!p1 || !p2 || !F || !n_models))) return fail(c, SVO_ERR_ARG, "bad arguments");
+    CU(c, cudaSetDevice(c->cfg.device));
+    cudaError_t e = fm7_host_points(p1, p2, n_sets, F, n_models, c->stream);
+    if (e != cudaSuccess) return cuda_fail(c, e, "svo_fundmat_7point");
+    if (n_sets > 0) c->launches += 1;
+    return n_sets;
+}
+
 }  // extern "C"

@@ -6,15 +6,17 @@
 //   * 7-point algorithm: null space of the 7x9 epipolar system on normalised points, cubic in lambda
 //   * symmetric epipolar distance max(d1^2 s1, d2^2 s2) in double, compared as float32
 //   * RANSACUpdateNumIters
-// The integer parts (RNG, subsets, iteration counts) are exact.  The 7-point solve uses a Gauss-Jordan
-// null space instead of LAPACK's SVD: the set of candidate matrices is the same, their floating-point
-// rounding differs at the 1e-12 level, which can flip an inlier only if its error lies within that
-// distance of the threshold.
+// The integer parts (RNG, subsets, iteration counts) are exact.  The null space of the 7x9 system is OpenCV's
+// own one-sided Jacobi SVD (core/lapack.cpp JacobiSVDImpl_<double>, which cv::SVDecomp runs for every matrix with
+// fewer than 25 rows even in a LAPACK build), operation for operation: sequential sums, OpenCV's scaled hypot, and
+// the two extra right singular vectors built from the fixed RNG(0x12345678) sign vectors by two Gram-Schmidt
+// passes.  Checked bit for bit against cv2.SVDecomp and cv2.findFundamentalMat(FM_7POINT) (tests/test_host_cpu.py).
 // Host + device; the host build is used by tests/cpp/fundmat_host.cpp to pin this file against cv2.
 #pragma once
 #include <float.h>
 #include <math.h>
 #include <stdint.h>
+#include "cr_math.cuh"
 
 #if defined(__CUDACC__)
 #define SVO_HD2 __host__ __device__ inline
@@ -84,50 +86,69 @@ SVO_HD2 int ransac_update_num_iters(double p, double ep, int model_points, int m
     return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : cv_round(num / denom);
 }
 
-// cv::solveCubic for c[0] x^3 + c[1] x^2 + c[2] x + c[3] = 0; returns the number of real roots
+// cv::solveCubic (core/mathfuncs.cpp, OpenCV 4.13) for c[0] x^3 + c[1] x^2 + c[2] x + c[3] = 0; returns the number of
+// real roots.  4.13 rescales the coefficients by their largest magnitude before the monic normalisation, decides the
+// degree against DBL_EPSILON * that magnitude, and evaluates the discriminant in its expanded, regrouped form; the
+// operation order below is the one of the shipped binary (checked bit for bit against cv2.solveCubic).  libm calls:
+// SVO_POW13 / SVO_ACOS / SVO_COS (glibc on the host; correctly rounded double-double versions on the device).
+#if defined(__CUDA_ARCH__) || defined(SVO_FORCE_CR_LIBM)
+#define SVO_POW13(x) cr::pow13(x)
+#define SVO_ACOS(x) cr::acos_cr(x)
+#define SVO_COS(x) cr::cos_cr(x)
+#else
+#define SVO_POW13(x) pow((x), 1. / 3)
+#define SVO_ACOS(x) acos(x)
+#define SVO_COS(x) cos(x)
+#endif
 SVO_HD2 int solve_cubic(const double* c, double* r) {
     double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
     double x0 = 0., x1 = 0., x2 = 0.;
     int n = 0;
-    if (a0 == 0) {
-        if (a1 == 0) {
-            if (a2 == 0) n = a3 == 0 ? -1 : 0;
+    const double scale = fmax(fabs(a3), fmax(fabs(a2), fmax(fabs(a1), fabs(a0))));
+    if (DBL_EPSILON > scale) { r[0] = r[1] = r[2] = 0; return -1; }
+    const double thr = DBL_EPSILON * scale;
+    if (thr > fabs(a0)) {
+        if (thr > fabs(a1)) {
+            if (thr > fabs(a2)) n = thr > fabs(a3) ? -1 : 0;
             else { x0 = -a3 / a2; n = 1; }
         } else {
             double d = a2 * a2 - 4 * a1 * a3;
             if (d >= 0) {
                 d = sqrt(d);
-                const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+                const double q1 = (d - a2) * 0.5, q2 = (a2 + d) * -0.5;
                 if (fabs(q1) > fabs(q2)) { x0 = q1 / a1; x1 = a3 / q1; }
                 else { x0 = q2 / a1; x1 = a3 / q2; }
                 n = d > 0 ? 2 : 1;
             }
         }
     } else {
+        const double inv = 1. / scale;
+        a0 *= inv; a1 *= inv; a2 *= inv; a3 *= inv;
         a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
         const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
-        const double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
-        const double Qcubed = Q * Q * Q;
-        double d = Qcubed - R * R;
+        const double R = ((a1 + a1) * a1 - 9 * a2) * a1;
+        const double R2 = (R + 27 * a3) * (1. / 54);
+        double d = ((a2 * a2 - 4 * a1 * a3) * (a1 * a1) + (9 * a1 * a3 - a2 * (a2 + a2)) * (a2 + a2) - 27 * a3 * a3) * (1. / 108);
         const double kPi = 3.14159265358979323846;
         if (d > 0) {
-            const double theta = acos(R / sqrt(Qcubed));
+            const double Qcubed = Q * Q * Q;
+            const double theta = SVO_ACOS(R2 / sqrt(Qcubed));
             const double sqrtQ = sqrt(Q);
             const double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
-            x0 = t0 * cos(t1) - t2;
-            x1 = t0 * cos(t1 + (2. * kPi / 3)) - t2;
-            x2 = t0 * cos(t1 + (4. * kPi / 3)) - t2;
+            x0 = t0 * SVO_COS(t1) - t2;
+            x1 = t0 * SVO_COS(t1 + (2. * kPi / 3)) - t2;
+            x2 = t0 * SVO_COS(t1 + (4. * kPi / 3)) - t2;
             n = 3;
         } else if (d == 0) {
-            if (R >= 0) { x0 = -2 * pow(R, 1. / 3) - a1 / 3; x1 = pow(R, 1. / 3) - a1 / 3; }
-            else { x0 = 2 * pow(-R, 1. / 3) - a1 / 3; x1 = -pow(-R, 1. / 3) - a1 / 3; }
+            if (R2 >= 0) { x0 = -2 * SVO_POW13(R2) - a1 / 3; x1 = SVO_POW13(R2) - a1 / 3; }
+            else { x0 = 2 * SVO_POW13(-R2) - a1 / 3; x1 = -SVO_POW13(-R2) - a1 / 3; }
             x2 = 0;
             n = x0 == x1 ? 1 : 2;
             x1 = x0 == x1 ? 0 : x1;
         } else {
             d = sqrt(-d);
-            double e = pow(d + fabs(R), 1. / 3);
-            if (R > 0) e = -e;
+            double e = SVO_POW13(d + fabs(R2));
+            if (R2 > 0) e = -e;
             x0 = (e + Q / e) - a1 * (1. / 3);
             n = 1;
         }
@@ -171,24 +192,109 @@ SVO_HD2 double fm7_entry(const Pt2f* m1, const Pt2f* m2, const Fm7Norm& nm, int 
     return (j < 6 && jj < 2) ? p * q : (j < 6 ? p : q);          // the products only where the reference form has them
 }
 
-// cubic in the pencil f1 + (1 - lambda) ... , roots -> up to 3 de-normalised F matrices.  f1, f2: null-space basis.
-SVO_HD2 int fm7_finish(double* f1, double* f2, const Fm7Norm& nm, double* F /* 27 */) {
-    const double m1cx = nm.m1cx, m1cy = nm.m1cy, m2cx = nm.m2cx, m2cy = nm.m2cy, scale1 = nm.scale1, scale2 = nm.scale2;
-    // orthonormalise (the parametrisation below is basis independent; this only helps conditioning)
-    double n1 = 0;
-    for (int j = 0; j < 9; ++j) n1 += f1[j] * f1[j];
-    n1 = 1. / sqrt(n1);
-    for (int j = 0; j < 9; ++j) f1[j] *= n1;
-    double dot = 0;
-    for (int j = 0; j < 9; ++j) dot += f1[j] * f2[j];
-    double n2 = 0;
-    for (int j = 0; j < 9; ++j) { f2[j] -= dot * f1[j]; n2 += f2[j] * f2[j]; }
-    n2 = 1. / sqrt(n2);
-    for (int j = 0; j < 9; ++j) f2[j] *= n2;
+// cv::hypot of core/lapack.cpp (not libm's)
+SVO_HD2 double cv_hypot(double a, double b) {
+    a = fabs(a);
+    b = fabs(b);
+    if (a > b) { b /= a; return a * sqrt(1 + b * b); }
+    if (b > 0) { a /= b; return b * sqrt(1 + a * a); }
+    return 0;
+}
 
+// SVDecomp(A, W, U, Vt, MODIFY_A + FULL_UV) of run7Point for the 7x9 matrix A: SVD::compute works on the transposed
+// problem (m = 9, n = 7, n1 = 9), i.e. JacobiSVDImpl_ orthogonalises the 7 rows of A in place and appends two rows;
+// rows 7 and 8 of the result are f1 and f2.  U (= Vt of the transposed problem) is not needed and not formed: it
+// never feeds back into the rows.  At: 9 rows of 9 doubles, rows 0..6 = A on entry.
+SVO_HD2 void fm7_svd_rows(double (*At)[9]) {
+    const int m = 9, n = 7, n1 = 9;
+    const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
+    double W[7];
+    for (int i = 0; i < n; i++) {
+        double sd = 0;
+        for (int k = 0; k < m; k++) { const double t = At[i][k]; sd += t * t; }
+        W[i] = sd;
+    }
+    const int max_iter = 30;                              // std::max(m, 30)
+    for (int iter = 0; iter < max_iter; iter++) {
+        bool changed = false;
+        for (int i = 0; i < n - 1; i++)
+            for (int j = i + 1; j < n; j++) {
+                double* Ai = At[i];
+                double* Aj = At[j];
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < m; k++) p += Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                const double beta = a - b, gamma = cv_hypot(p, beta);
+                double c, s;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (int k = 0; k < m; k++) {
+                    const double t0 = c * Ai[k] + s * Aj[k];
+                    const double t1 = -s * Ai[k] + c * Aj[k];
+                    Ai[k] = t0; Aj[k] = t1;
+                    a += t0 * t0; b += t1 * t1;
+                }
+                W[i] = a; W[j] = b;
+                changed = true;
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < n; i++) {
+        double sd = 0;
+        for (int k = 0; k < m; k++) { const double t = At[i][k]; sd += t * t; }
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < n - 1; i++) {                     // selection sort, descending
+        int j = i;
+        for (int k = i + 1; k < n; k++) if (W[j] < W[k]) j = k;
+        if (i != j) {
+            const double tw = W[i]; W[i] = W[j]; W[j] = tw;
+            for (int k = 0; k < m; k++) { const double t = At[i][k]; At[i][k] = At[j][k]; At[j][k] = t; }
+        }
+    }
+    CvRng rng;
+    rng.state = 0x12345678;
+    for (int i = 0; i < n1; i++) {
+        double sd = i < n ? W[i] : 0;
+        for (int ii = 0; ii < 100 && sd <= minval; ii++) {
+            // a zero singular value: random +-1/m vector, projected off the previous rows (twice), normalised
+            const double val0 = 1. / m;
+            for (int k = 0; k < m; k++) At[i][k] = (rng.next() & 256) != 0 ? val0 : -val0;
+            for (int iter = 0; iter < 2; iter++)
+                for (int j = 0; j < i; j++) {
+                    sd = 0;
+                    for (int k = 0; k < m; k++) sd += At[i][k] * At[j][k];
+                    double asum = 0;
+                    for (int k = 0; k < m; k++) {
+                        const double t = At[i][k] - sd * At[j][k];
+                        At[i][k] = t;
+                        asum += fabs(t);
+                    }
+                    asum = asum > eps * 100 ? 1 / asum : 0;
+                    for (int k = 0; k < m; k++) At[i][k] *= asum;
+                }
+            sd = 0;
+            for (int k = 0; k < m; k++) { const double t = At[i][k]; sd += t * t; }
+            sd = sqrt(sd);
+        }
+        const double s = sd > minval ? 1 / sd : 0.;
+        for (int k = 0; k < m; k++) At[i][k] *= s;
+    }
+}
+
+// cubic in the pencil lambda*f1 + (1-lambda)*f2, roots -> up to 3 de-normalised F matrices.  f1, f2: rows 7, 8 of Vt.
+SVO_HD2 int fm7_finish(double* f1, double* f2, const Fm7Norm& nm, double* F /* 27 */) {
     // f ~ lambda*f1 + (1-lambda)*f2, det(f) = 0 gives a cubic in lambda
     for (int i = 0; i < 9; ++i) f1[i] -= f2[i];
-    double c[4], r[3];
+    double c[4], r[3] = {0, 0, 0};
     double t0 = f2[4] * f2[8] - f2[5] * f2[7];
     double t1 = f2[3] * f2[8] - f2[5] * f2[6];
     double t2 = f2[3] * f2[7] - f2[4] * f2[6];
@@ -207,6 +313,10 @@ SVO_HD2 int fm7_finish(double* f1, double* f2, const Fm7Norm& nm, double* F /* 2
            f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) + f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
     const int n = solve_cubic(c, r);
     if (n < 1 || n > 3) return n < 0 ? 0 : n;
+    // T1 = [s1 0 -s1*c1x; 0 s1 -s1*c1y; 0 0 1], T2 likewise; F = T2^T * F * T1 evaluated as cv::gemm does for 3x3
+    // operands: (T2^T * F) first, every entry the left-to-right sum of its three products (zeros included)
+    const double T1[9] = {nm.scale1, 0, -nm.scale1 * nm.m1cx, 0, nm.scale1, -nm.scale1 * nm.m1cy, 0, 0, 1};
+    const double T2t[9] = {nm.scale2, 0, 0, 0, nm.scale2, 0, -nm.scale2 * nm.m2cx, -nm.scale2 * nm.m2cy, 1};
     for (int k = 0; k < n; ++k) {
         double* fm = F + 9 * k;
         double lambda = r[k], mu = 1.;
@@ -214,20 +324,13 @@ SVO_HD2 int fm7_finish(double* f1, double* f2, const Fm7Norm& nm, double* F /* 2
         if (fabs(s) > DBL_EPSILON) { mu = 1. / s; lambda *= mu; fm[8] = 1.; }
         else fm[8] = 0.;
         for (int i = 0; i < 8; ++i) fm[i] = f1[i] * lambda + f2[i] * mu;
-        // de-normalise: F = T2^T * F * T1 with T = [s 0 -s*cx; 0 s -s*cy; 0 0 1]
         double G[9];
-        // G = F * T1
-        for (int i = 0; i < 3; ++i) {
-            G[3 * i + 0] = fm[3 * i + 0] * scale1;
-            G[3 * i + 1] = fm[3 * i + 1] * scale1;
-            G[3 * i + 2] = -fm[3 * i + 0] * scale1 * m1cx - fm[3 * i + 1] * scale1 * m1cy + fm[3 * i + 2];
-        }
-        // F = T2^T * G
-        for (int j = 0; j < 3; ++j) {
-            fm[0 + j] = scale2 * G[0 + j];
-            fm[3 + j] = scale2 * G[3 + j];
-            fm[6 + j] = -scale2 * m2cx * G[0 + j] - scale2 * m2cy * G[3 + j] + G[6 + j];
-        }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                G[3 * i + j] = T2t[3 * i] * fm[j] + T2t[3 * i + 1] * fm[3 + j] + T2t[3 * i + 2] * fm[6 + j];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                fm[3 * i + j] = G[3 * i] * T1[j] + G[3 * i + 1] * T1[3 + j] + G[3 * i + 2] * T1[6 + j];
         if (fabs(fm[8]) > FLT_EPSILON) { const double inv = 1. / fm[8]; for (int i = 0; i < 9; ++i) fm[i] *= inv; }
     }
     return n;
@@ -236,46 +339,12 @@ SVO_HD2 int fm7_finish(double* f1, double* f2, const Fm7Norm& nm, double* F /* 2
 SVO_HD2 int run_7point(const Pt2f* m1, const Pt2f* m2, double* F /* 27 */) {
     Fm7Norm nm;
     if (!fm7_normalise(m1, m2, nm)) return 0;
-    double a[7][9];
+    double a[9][9];
     for (int i = 0; i < 7; ++i)
         for (int j = 0; j < 9; ++j) a[i][j] = fm7_entry(m1, m2, nm, i, j);
-    // null space of the 7x9 system: Gauss-Jordan with complete pivoting
-    int pivcol[7];
-    bool used[9];
-    for (int j = 0; j < 9; ++j) used[j] = false;
-    int rank = 0;
-    for (int r = 0; r < 7; ++r) {
-        int pr = -1, pc = -1;
-        double best = 0;
-        for (int i = r; i < 7; ++i)
-            for (int j = 0; j < 9; ++j)
-                if (!used[j] && fabs(a[i][j]) > best) { best = fabs(a[i][j]); pr = i; pc = j; }
-        if (pr < 0 || best < 1e-13) break;
-        if (pr != r) for (int j = 0; j < 9; ++j) { const double tmp = a[r][j]; a[r][j] = a[pr][j]; a[pr][j] = tmp; }
-        const double inv = 1. / a[r][pc];
-        for (int j = 0; j < 9; ++j) a[r][j] *= inv;
-        for (int i = 0; i < 7; ++i) {
-            if (i == r) continue;
-            const double f = a[i][pc];
-            if (f != 0) for (int j = 0; j < 9; ++j) a[i][j] -= f * a[r][j];
-        }
-        used[pc] = true;
-        pivcol[r] = pc;
-        ++rank;
-    }
-    // basis vectors of the null space for the two (or more) free columns; use the first two free columns
-    double f1[9], f2[9];
-    int freec[9], nfree = 0;
-    for (int j = 0; j < 9; ++j) if (!used[j]) freec[nfree++] = j;
-    if (nfree < 2) return 0;
-    for (int v = 0; v < 2; ++v) {
-        double* f = v == 0 ? f1 : f2;
-        const int fc = freec[v];
-        for (int j = 0; j < 9; ++j) f[j] = 0;
-        f[fc] = 1;
-        for (int r = 0; r < rank; ++r) f[pivcol[r]] = -a[r][fc];
-    }
-    return fm7_finish(f1, f2, nm, F);
+    for (int j = 0; j < 9; ++j) a[7][j] = a[8][j] = 0;
+    fm7_svd_rows(a);
+    return fm7_finish(a[7], a[8], nm, F);
 }
 
 // FMEstimatorCallback::computeError for one correspondence (float32 result)

@@ -58,82 +58,115 @@ ransac_prepare_kernel(Pools P, RansacScratch R) {
 }
 
 
-// run_7point with the null-space step (Gauss-Jordan with complete pivoting on the 7x9 system) spread over the warp:
-// lane j < 9 owns column j in registers, the pivot search is a warp arg-max with the sequential scan's tie order
-// (largest |a|, then smallest row, then smallest column), row swaps / scaling / elimination touch each element with
-// exactly the operations of the sequential loop, so the models are bit-identical to run_7point's.  All 32 lanes must
-// call it; F and the return value are valid on lane 0.  (On one lane the dynamically indexed 7x9 array lives in local
-// memory and this step was more than half of fundmat_kernel's time.)
+// ((v0 + v1) + v2) + ... + v8 over lanes 0..8, on every lane: the left-to-right sum of OpenCV's scalar loops
+__device__ __forceinline__ double ordered_sum9(double v) {
+    const unsigned full = 0xffffffffu;
+    double s = __shfl_sync(full, v, 0);
+#pragma unroll
+    for (int k = 1; k < 9; ++k) s += __shfl_sync(full, v, k);
+    return s;
+}
+
+// run_7point with the SVD step (fm7_svd_rows: OpenCV's one-sided Jacobi on the rows of the 7x9 system, then the two
+// extra right singular vectors) spread over the warp: lane k < 9 owns column k of the 9 rows in registers, every
+// rotation / projection touches its element with exactly the operations of the sequential loops, and every dot product
+// is summed in the sequential order (ordered_sum9), so f1 / f2 and the models are bit-identical to the host build of
+// fundmat_core.cuh that is pinned against cv2.  All 32 lanes must call it; F and the return value are valid on lane 0.
 __device__ int run_7point_warp(const Pt2f* m1, const Pt2f* m2, double* F /* 27, lane 0 */) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     Fm7Norm nm;
     if (!fm7_normalise(m1, m2, nm)) return 0;          // same inputs on every lane: uniform
     const bool colv = lane < 9;
-    double col[7];
+    const int m = 9, n = 7;
+    const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
+    double col[9], W[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) col[i] = colv ? fm7_entry(m1, m2, nm, i, lane) : 0.0;
-    bool used = !colv;                                 // lanes >= 9 never offer a pivot
-    int pivcol[7];
-    int rank = 0;
+    col[7] = col[8] = 0.0;
 #pragma unroll
-    for (int r = 0; r < 7; ++r) {
-        // this column's best candidate among rows r..6 (strict '>' keeps the smallest row among equals)
-        double bv = 0;
-        int bi = -1;
-        if (!used) {
+    for (int i = 0; i < 7; ++i) W[i] = ordered_sum9(col[i] * col[i]);
+    for (int iter = 0; iter < 30; ++iter) {
+        bool changed = false;
 #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                if (i < r) continue;
-                const double v = fabs(col[i]);
-                if (v > bv) { bv = v; bi = i; }
+        for (int i = 0; i < n - 1; ++i) {
+#pragma unroll
+            for (int j = i + 1; j < n; ++j) {
+                double a = W[i], b = W[j];
+                double p = ordered_sum9(col[i] * col[j]);
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                const double beta = a - b, gamma = cv_hypot(p, beta);
+                double c, s;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                const double t0 = c * col[i] + s * col[j];
+                const double t1 = -s * col[i] + c * col[j];
+                col[i] = t0; col[j] = t1;
+                W[i] = ordered_sum9(t0 * t0);
+                W[j] = ordered_sum9(t1 * t1);
+                changed = true;
             }
         }
-        int bl = lane;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {              // arg-max over lanes 0..15: value, then smaller row, then smaller column
-            const double ov = __shfl_xor_sync(full, bv, o);
-            const int oi = __shfl_xor_sync(full, bi, o);
-            const int ol = __shfl_xor_sync(full, bl, o);
-            const bool take = oi >= 0 && (bi < 0 || ov > bv || (ov == bv && (oi < bi || (oi == bi && ol < bl))));
-            if (take) { bv = ov; bi = oi; bl = ol; }
-        }
-        const double best = __shfl_sync(full, bv, 0);
-        const int pr = __shfl_sync(full, bi, 0), pc = __shfl_sync(full, bl, 0);
-        if (pr < 0 || best < 1e-13) break;
-        if (pr != r) {                                 // swap rows r and pr (pr > r)
-            double tmp = col[r];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) if (i == pr) { col[r] = col[i]; col[i] = tmp; }
-        }
-        const double inv = 1. / __shfl_sync(full, col[r], pc);
-        col[r] *= inv;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            if (i == r) continue;
-            const double f = __shfl_sync(full, col[i], pc);
-            if (f != 0) col[i] -= f * col[r];
-        }
-        if (lane == pc) used = true;
-        pivcol[r] = pc;
-        ++rank;
+        if (!changed) break;
     }
-    // the first two free columns span the null-space basis: f[fc] = 1, f[pivcol[r]] = -a[r][fc]
-    const unsigned freem = __ballot_sync(full, !used);
-    if (__popc(freem) < 2) return 0;
-    const int fc0 = __ffs(freem) - 1, fc1 = __ffs(freem & (freem - 1)) - 1;
-    double e1 = lane == fc0 ? 1.0 : 0.0, e2 = lane == fc1 ? 1.0 : 0.0;      // this lane's entries of f1 / f2
 #pragma unroll
-    for (int r = 0; r < 7; ++r) {
-        const double v1 = __shfl_sync(full, col[r], fc0), v2 = __shfl_sync(full, col[r], fc1);
-        if (r < rank && pivcol[r] == lane) { e1 = -v1; e2 = -v2; }
+    for (int i = 0; i < n; ++i) W[i] = sqrt(ordered_sum9(col[i] * col[i]));
+#pragma unroll
+    for (int i = 0; i < n - 1; ++i) {                  // selection sort, descending; first maximum wins
+        int j = i;
+        double wj = W[i];
+#pragma unroll
+        for (int k = i + 1; k < n; ++k) if (wj < W[k]) { j = k; wj = W[k]; }
+        if (j != i) {
+#pragma unroll
+            for (int k = i + 1; k < n; ++k)
+                if (k == j) {
+                    const double tw = W[i]; W[i] = W[k]; W[k] = tw;
+                    const double tc = col[i]; col[i] = col[k]; col[k] = tc;
+                }
+        }
+    }
+    CvRng rng;
+    rng.state = 0x12345678;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        double sd = i < n ? W[i < n ? i : 0] : 0;
+        for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
+            const double val0 = 1. / m;
+            double v = 0;
+            for (int k = 0; k < m; ++k) {
+                const double vk = (rng.next() & 256) != 0 ? val0 : -val0;
+                if (k == lane) v = vk;
+            }
+            col[i] = v;
+            for (int it2 = 0; it2 < 2; ++it2) {
+#pragma unroll
+                for (int j = 0; j < i; ++j) {
+                    sd = ordered_sum9(col[i] * col[j]);
+                    const double t = col[i] - sd * col[j];
+                    double asum = ordered_sum9(fabs(t));
+                    asum = asum > eps * 100 ? 1 / asum : 0;
+                    col[i] = t * asum;
+                }
+            }
+            sd = sqrt(ordered_sum9(col[i] * col[i]));
+        }
+        const double s = sd > minval ? 1 / sd : 0.;
+        col[i] *= s;
     }
     double f1[9], f2[9];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) { f1[j] = __shfl_sync(full, e1, j); f2[j] = __shfl_sync(full, e2, j); }
-    int n = 0;
-    if (lane == 0) n = fm7_finish(f1, f2, nm, F);
-    return __shfl_sync(full, n, 0);
+    for (int j = 0; j < 9; ++j) { f1[j] = __shfl_sync(full, col[7], j); f2[j] = __shfl_sync(full, col[8], j); }
+    int nr = 0;
+    if (lane == 0) nr = fm7_finish(f1, f2, nm, F);
+    return __shfl_sync(full, nr, 0);
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -326,6 +359,49 @@ cudaError_t ransac_host_points(const RansacScratch& R, int scratch_slot, const f
         else if ((e = cudaMemcpy(mask, R.inl + prob * R.kp_cap, n, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+// parity seam: run7Point alone, one warp per 7-point sample (svo_fundmat_7point)
+__global__ void __launch_bounds__(RS_THREADS)
+fm7_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, int n_sets, double* __restrict__ F,
+           int32_t* __restrict__ n_models) {
+    __shared__ Pt2f s1[RS_WARPS][7], s2[RS_WARPS][7];
+    __shared__ double sF[RS_WARPS][27];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int set = blockIdx.x * RS_WARPS + wid;
+    if (set >= n_sets) return;
+    if (lane < 7) {
+        const float2 a = p1[set * 7 + lane], b = p2[set * 7 + lane];
+        s1[wid][lane].x = a.x; s1[wid][lane].y = a.y; s2[wid][lane].x = b.x; s2[wid][lane].y = b.y;
+    }
+    if (lane < 27) sF[wid][lane] = 0;
+    __syncwarp();
+    const int nm = run_7point_warp(s1[wid], s2[wid], sF[wid]);
+    __syncwarp();
+    if (lane < 27) F[(size_t)set * 27 + lane] = sF[wid][lane];
+    if (lane == 0) n_models[set] = nm;
+}
+
+cudaError_t fm7_host_points(const float* p1, const float* p2, int n_sets, double* F, int32_t* n_models, cudaStream_t st) {
+    if (n_sets <= 0) return cudaSuccess;
+    float2 *d1 = nullptr, *d2 = nullptr;
+    double* dF = nullptr;
+    int32_t* dn = nullptr;
+    cudaError_t e;
+    const size_t pb = (size_t)n_sets * 7 * sizeof(float2);
+    if ((e = cudaMalloc(&d1, pb)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d2, pb)) == cudaSuccess && (e = cudaMalloc(&dF, (size_t)n_sets * 27 * sizeof(double))) == cudaSuccess &&
+        (e = cudaMalloc(&dn, (size_t)n_sets * sizeof(int32_t))) == cudaSuccess &&
+        (e = cudaMemcpyAsync(d1, p1, pb, cudaMemcpyHostToDevice, st)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(d2, p2, pb, cudaMemcpyHostToDevice, st)) == cudaSuccess) {
+        fm7_kernel<<<(n_sets + RS_WARPS - 1) / RS_WARPS, RS_THREADS, 0, st>>>(d1, d2, n_sets, dF, dn);
+        if ((e = cudaGetLastError()) == cudaSuccess &&
+            (e = cudaMemcpyAsync(F, dF, (size_t)n_sets * 27 * sizeof(double), cudaMemcpyDeviceToHost, st)) == cudaSuccess &&
+            (e = cudaMemcpyAsync(n_models, dn, (size_t)n_sets * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+    }
+    cudaFree(d1); cudaFree(d2); cudaFree(dF); cudaFree(dn);
+    return e;
 }
 
 }  // namespace svo

@@ -23,4 +23,6 @@ cudaError_t launch_ransac(const Pools& P, const RansacScratch& R, int n, cudaStr
 // stand-alone: host points -> host mask (svo_fundmat_ransac)
 cudaError_t ransac_host_points(const RansacScratch& R, int scratch_slot, const float* p1, const float* p2, int n,
                                uint8_t* mask, int* n_inliers, cudaStream_t st);
+// stand-alone run7Point on n_sets samples of 7 correspondences (svo_fundmat_7point)
+cudaError_t fm7_host_points(const float* p1, const float* p2, int n_sets, double* F, int32_t* n_models, cudaStream_t st);
 }  // namespace svo

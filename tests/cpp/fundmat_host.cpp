@@ -64,3 +64,18 @@ extern "C" int fundmat_host(const float* p1, const float* p2, int n, uint8_t* ma
     if (bestF) std::memcpy(bestF, best, sizeof(best));
     return good;
 }
+
+// run7Point alone (cv2.findFundamentalMat(p1[:7], p2[:7], FM_7POINT) returns its stacked 3x3 models)
+extern "C" int fundmat_host_7point(const float* p1, const float* p2, double* F27) {
+    return run_7point(reinterpret_cast<const Pt2f*>(p1), reinterpret_cast<const Pt2f*>(p2), F27);
+}
+
+// the SVD step alone: At = 9 x 9 row-major, rows 0..6 = A; cv2.SVDecomp(A, flags=FULL_UV)[2] is the result
+extern "C" void fundmat_host_svd_rows(double* At) { fm7_svd_rows(reinterpret_cast<double (*)[9]>(At)); }
+
+// the correctly rounded libm replacements the device build of solve_cubic uses (csrc/cr_math.cuh)
+// (cr_math.cuh comes in through fundmat_core.cuh)
+extern "C" double cr_pow13(double x) { return svo::cr::pow13(x); }
+extern "C" double cr_cos(double x) { return svo::cr::cos_cr(x); }
+extern "C" double cr_acos(double x) { return svo::cr::acos_cr(x); }
+extern "C" int fundmat_host_cubic(const double* c, double* r) { return solve_cubic(c, r); }

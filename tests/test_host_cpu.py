@@ -152,6 +152,106 @@ def test_fundmat_core_equals_opencv_ransac(fundmat_host):
     assert bad == 0, f"{bad}/{total} masks differ"
 
 
+@pytest.fixture(scope="module")
+def fundmat_lib(tmp_path_factory):
+    so = tmp_path_factory.mktemp("fm7") / "libfundmat_host7.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-mfma", "-o", str(so),
+                           os.path.join(ROOT, "tests", "cpp", "fundmat_host.cpp")])
+    lib = C.CDLL(str(so))
+    for f in (lib.cr_pow13, lib.cr_cos, lib.cr_acos):
+        f.restype = C.c_double
+        f.argtypes = [C.c_double]
+    return lib
+
+
+def test_fm7_svd_is_opencv_jacobi_svd_bit_for_bit(fundmat_lib):
+    """fm7_svd_rows (csrc/fundmat_core.cuh) = the SVDecomp(A, W, U, Vt, MODIFY_A + FULL_UV) call of run7Point: all nine
+    right singular vectors, including the two null-space rows built from OpenCV's fixed RNG stream, equal cv2's bits."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for t in range(300):
+        A = rng.normal(size=(7, 9))
+        if t % 3 == 0:
+            A[:, 8] = 1.0
+        if t % 50 == 7:
+            A[3] = A[2]                                  # rank deficient: a zero singular value among the first seven
+        _, _, vt = cv2.SVDecomp(A.copy(), flags=cv2.SVD_FULL_UV)
+        At = np.zeros((9, 9))
+        At[:7] = A
+        fundmat_lib.fundmat_host_svd_rows(At.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(At, vt), t
+
+
+def test_solve_cubic_is_opencv_solve_cubic_bit_for_bit(fundmat_lib):
+    """solve_cubic = cv::solveCubic of OpenCV 4.13 (coefficient rescaling, expanded discriminant), incl. degenerate degrees."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for t in range(6000):
+        c = rng.normal(size=4) * 10.0 ** rng.integers(-3, 4)
+        if t % 7 == 0:
+            c[0] = 0.0
+        if t % 49 == 0:
+            c[1] = 0.0
+        if t % 11 == 0:
+            c[0] *= 1e-18
+        if t % 13 == 0:                                   # double root: d == 0 exactly for small integers
+            a, b = rng.integers(-5, 6, 2)
+            c = np.array([1.0, -(2 * a + b), a * a + 2 * a * b, -a * a * b], np.float64)
+        n, roots = cv2.solveCubic(c)
+        r = np.zeros(3)
+        k = fundmat_lib.fundmat_host_cubic(c.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p))
+        assert k == n, (t, c, n, k)
+        assert np.array_equal(roots.ravel()[:max(n, 0)], r[:max(n, 0)]), (t, c)
+
+
+def test_run7point_is_opencv_run7point_bit_for_bit(fundmat_lib):
+    """cv2.findFundamentalMat(7 points, FM_7POINT) returns run7Point's stacked models: same count, same bits."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for t in range(3000):
+        p1 = rng.uniform(0, 640, (7, 2)).astype(np.float32)
+        p2 = (p1 + rng.normal(0, 6, (7, 2))).astype(np.float32)
+        if t % 2 == 0:
+            p1, p2 = np.round(p1), np.round(p2)
+        if t % 10 == 0:                                   # sideways motion of coplanar points: the degenerate samples
+            p2 = (p1 + np.array([float(rng.integers(1, 9)), 0.0], np.float32)).astype(np.float32)
+        try:
+            F, _ = cv2.findFundamentalMat(p1, p2, cv2.FM_7POINT)
+        except cv2.error:
+            continue                                     # cv2's own rowRange assertion (DESIGN.md limit (d))
+        Fm = np.zeros(27)
+        k = fundmat_lib.fundmat_host_7point(p1.ctypes.data_as(C.c_void_p), p2.ctypes.data_as(C.c_void_p), Fm.ctypes.data_as(C.c_void_p))
+        if F is None:
+            assert k <= 0, t
+            continue
+        assert F.shape[0] == 3 * k and np.array_equal(F.ravel(), Fm[:9 * k]), t
+
+
+def test_cr_math_is_correctly_rounded_and_agrees_with_glibc(fundmat_lib):
+    """csrc/cr_math.cuh (what the device evaluates instead of libdevice's 1-2 ulp pow / acos / cos): equal to the
+    correctly rounded value (mpmath, 250 bits) on every sample, and to glibc on all but its own rare misroundings."""
+    mpmath = pytest.importorskip("mpmath")
+    import math
+    mpmath.mp.prec = 250
+    rng = np.random.default_rng(1)
+    y = mpmath.mpf(1 / 3)
+    n, differ = 6000, 0
+    for i in range(n):
+        x = float(rng.uniform(1e-6, 3)) if i % 2 else float(10 ** rng.uniform(-12, 6))
+        m = fundmat_lib.cr_pow13(x)
+        assert m == float(mpmath.power(mpmath.mpf(x), y)), x
+        differ += m != math.pow(x, 1 / 3)
+        a = float(rng.uniform(0, 5.3)) if i % 3 else float(rng.uniform(-100, 100))
+        m = fundmat_lib.cr_cos(a)
+        assert m == float(mpmath.cos(mpmath.mpf(a))), a
+        differ += m != math.cos(a)
+        v = float(rng.uniform(-1, 1)) if i % 3 else float((1 - 10 ** rng.uniform(-12, 0)) * rng.choice([-1, 1]))
+        m = fundmat_lib.cr_acos(v)
+        assert m == float(mpmath.acos(mpmath.mpf(v))), v
+        differ += m != math.acos(v)
+    assert differ <= 3 * n * 0.004, differ               # glibc: < 1 ulp, correctly rounded in ~99.9 % of the calls
+
+
 def test_fundmat_core_golden_masks(fundmat_host, golden):
     for i in (1, 2):
         for side in "LR":

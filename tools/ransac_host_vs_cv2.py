@@ -18,8 +18,11 @@ from stereo_vo_b200 import synth          # noqa: E402
 def main():
     n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 6
     n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-    so = "/tmp/libfundmat_host_census.so"
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so,
+    so = "/tmp/libfundmat_host_census%s.so" % os.environ.get("SVO_CENSUS_CR", "")
+    # SVO_CENSUS_CR=1: build with the correctly rounded pow / acos / cos of csrc/cr_math.cuh (what the device evaluates)
+    # instead of glibc's (what OpenCV on the host evaluates)
+    extra = ["-DSVO_FORCE_CR_LIBM", "-mfma"] if os.environ.get("SVO_CENSUS_CR") == "1" else []
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", *extra, "-o", so,
                            os.path.join(ROOT, "tests", "cpp", "fundmat_host.cpp")])
     lib = C.CDLL(so)
     stats = {}
