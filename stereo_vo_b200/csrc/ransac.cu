@@ -2,10 +2,10 @@
 // stage4_match_consecutive.cpp:171-241 on sm_100a, one CTA per (stereo pair, side).
 //
 // OpenCV's estimator is sequential (adaptive iteration count, one RNG stream), but iteration k's
-// sample does not depend on the models of earlier iterations: thread 0 draws the next 8 samples
-// from the exact cv::RNG stream (including the duplicate and collinearity re-draws), the 8 warps solve
-// and score them concurrently, and thread 0 then replays OpenCV's "best so far / update niters" logic in
-// iteration order.  The result is the inlier mask OpenCV returns (see fundmat_core.cuh for the one
+// sample does not depend on the models of earlier iterations: thread 0 draws the next RS_BATCH samples
+// from the exact cv::RNG stream (including the duplicate and collinearity re-draws), every warp solves
+// three of them side by side and scores their models, and thread 0 then replays OpenCV's "best so far /
+// update niters" logic in iteration order.  The result is the inlier mask OpenCV returns (see fundmat_core.cuh for the one
 // floating-point caveat).  With >= 15 points this is RANSAC, with 8..14 LMedS, with 7 an all-ones mask
 // and with < 7 no mask (zero inliers), as in cv::findFundamentalMat.
 #include "fundmat_core.cuh"
@@ -13,19 +13,21 @@
 
 namespace svo {
 
-constexpr int RS_WARPS = 8;
+constexpr int RS_WARPS = 2;                      // warps per (stereo pair, side) problem
+constexpr int RS_GROUPS = 3;                     // 7-point samples solved side by side in one warp (9 lanes each)
+constexpr int RS_BATCH = RS_WARPS * RS_GROUPS;   // RANSAC iterations evaluated per round
 constexpr int RS_THREADS = RS_WARPS * 32;
 
 struct RsShared {
     CvRng rng;
-    double F[RS_WARPS][27];
+    double F[RS_BATCH][27];
     double best[9];
     double minMedian;
-    Pt2f ms1[RS_WARPS][7], ms2[RS_WARPS][7];
-    int found[RS_WARPS];
-    int nmodels[RS_WARPS];
-    int good[RS_WARPS][3];
-    float median[RS_WARPS][3];
+    Pt2f ms1[RS_BATCH][7], ms2[RS_BATCH][7];
+    int found[RS_BATCH];
+    int nmodels[RS_BATCH];
+    int good[RS_BATCH][3];
+    float median[RS_BATCH][3];
     int iter_base, niters, maxGood, stop, have_model;
     int wsum[RS_WARPS];
 };
@@ -58,115 +60,131 @@ ransac_prepare_kernel(Pools P, RansacScratch R) {
 }
 
 
-// ((v0 + v1) + v2) + ... + v8 over lanes 0..8, on every lane: the left-to-right sum of OpenCV's scalar loops
-__device__ __forceinline__ double ordered_sum9(double v) {
+// ((v0 + v1) + v2) + ... + v8 over the 9 lanes of this lane's group (base = first lane of the group), on every lane
+// of the group: the left-to-right sum of OpenCV's scalar loops
+__device__ __forceinline__ double ordered_sum9(double v, int base) {
     const unsigned full = 0xffffffffu;
-    double s = __shfl_sync(full, v, 0);
+    double s = __shfl_sync(full, v, base);
 #pragma unroll
-    for (int k = 1; k < 9; ++k) s += __shfl_sync(full, v, k);
+    for (int k = 1; k < 9; ++k) s += __shfl_sync(full, v, base + k);
     return s;
 }
 
 // run_7point with the SVD step (fm7_svd_rows: OpenCV's one-sided Jacobi on the rows of the 7x9 system, then the two
-// extra right singular vectors) spread over the warp: lane k < 9 owns column k of the 9 rows in registers, every
-// rotation / projection touches its element with exactly the operations of the sequential loops, and every dot product
-// is summed in the sequential order (ordered_sum9), so f1 / f2 and the models are bit-identical to the host build of
-// fundmat_core.cuh that is pinned against cv2.  All 32 lanes must call it; F and the return value are valid on lane 0.
-__device__ int run_7point_warp(const Pt2f* m1, const Pt2f* m2, double* F /* 27, lane 0 */) {
+// extra right singular vectors) spread over the warp, three samples side by side: lanes 9g .. 9g+8 own the nine columns
+// of sample g's rows in registers.  Every rotation / projection touches its element with exactly the operations of the
+// sequential loops and every dot product is summed in the sequential order (ordered_sum9), so f1 / f2 and the models
+// are bit-identical to the host build of fundmat_core.cuh that is pinned against cv2.  The three samples run in lockstep:
+// OpenCV's data-dependent branches ("rows already orthogonal: skip", "beta < 0", hypot's operand order, "no rotation in
+// this sweep: stop") are evaluated as selects, a skipped rotation leaves its rows untouched, and a sample that has
+// converged idles through the sweeps the others still need (a converged sweep changes nothing).
+// ms1 / ms2: RS_GROUPS x 7 points, valid[g] != 1 marks an unused group; F: RS_GROUPS x 27, nm_out: RS_GROUPS counts,
+// written by the first lane of each group.  All 32 lanes must call it.
+__device__ void run_7point_warp3(const Pt2f (*ms1)[7], const Pt2f (*ms2)[7], const int* valid, double (*F)[27], int* nm_out) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
+    const int g = lane < 27 ? lane / 9 : 2;
+    const int base = 9 * g;
+    const int kcol = lane - base;                      // 0..8: a column; 9..13 (lanes 27..31): no column
+    const bool colv = kcol < 9;
+    const Pt2f* m1 = ms1[g];
+    const Pt2f* m2 = ms2[g];
     Fm7Norm nm;
-    if (!fm7_normalise(m1, m2, nm)) return 0;          // same inputs on every lane: uniform
-    const bool colv = lane < 9;
+    bool ok = valid[g] == 1;
+    if (ok) ok = fm7_normalise(m1, m2, nm);
     const int m = 9, n = 7;
     const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
     double col[9], W[7];
+    // an unused / degenerate group works on orthonormal dummy rows: no rotations, no zero singular values
 #pragma unroll
-    for (int i = 0; i < 7; ++i) col[i] = colv ? fm7_entry(m1, m2, nm, i, lane) : 0.0;
+    for (int i = 0; i < 7; ++i) col[i] = !colv ? 0.0 : (ok ? fm7_entry(m1, m2, nm, i, kcol) : (kcol == i ? 1.0 : 0.0));
     col[7] = col[8] = 0.0;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) W[i] = ordered_sum9(col[i] * col[i]);
+    for (int i = 0; i < 7; ++i) W[i] = ordered_sum9(col[i] * col[i], base);
     for (int iter = 0; iter < 30; ++iter) {
         bool changed = false;
 #pragma unroll
         for (int i = 0; i < n - 1; ++i) {
 #pragma unroll
             for (int j = i + 1; j < n; ++j) {
-                double a = W[i], b = W[j];
-                double p = ordered_sum9(col[i] * col[j]);
-                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                const double a = W[i], b = W[j];
+                double p = ordered_sum9(col[i] * col[j], base);
+                const bool rot = !(fabs(p) <= eps * sqrt(a * b));
+                if (!__any_sync(full, rot)) continue;  // warp-uniform
                 p *= 2;
-                const double beta = a - b, gamma = cv_hypot(p, beta);
-                double c, s;
-                if (beta < 0) {
-                    const double delta = (gamma - beta) * 0.5;
-                    s = sqrt(delta / gamma);
-                    c = p / (gamma * s * 2);
-                } else {
-                    c = sqrt((gamma + beta) / (gamma * 2));
-                    s = p / (gamma * c * 2);
-                }
+                const double beta = a - b;
+                // gamma = cv_hypot(p, beta)
+                const double ap = fabs(p), ab = fabs(beta);
+                const double hi = ap > ab ? ap : ab, lo = ap > ab ? ab : ap;
+                const double q = lo / hi;
+                const double gamma = hi > 0 ? hi * sqrt(1 + q * q) : 0.0;
+                // beta < 0: s = sqrt(((gamma - beta)*0.5)/gamma), c = p/(gamma*s*2); else c = sqrt((gamma+beta)/(gamma*2)), s = p/(gamma*c*2)
+                const bool neg = beta < 0;
+                const double num = neg ? (gamma - beta) * 0.5 : (gamma + beta);
+                const double den = neg ? gamma : gamma * 2;
+                const double first = sqrt(num / den);
+                const double second = p / (gamma * first * 2);
+                const double c = neg ? second : first, s = neg ? first : second;
                 const double t0 = c * col[i] + s * col[j];
                 const double t1 = -s * col[i] + c * col[j];
-                col[i] = t0; col[j] = t1;
-                W[i] = ordered_sum9(t0 * t0);
-                W[j] = ordered_sum9(t1 * t1);
-                changed = true;
+                const double wa = ordered_sum9(t0 * t0, base), wb = ordered_sum9(t1 * t1, base);
+                if (rot) { col[i] = t0; col[j] = t1; W[i] = wa; W[j] = wb; changed = true; }
             }
         }
-        if (!changed) break;
+        if (!__any_sync(full, changed)) break;
     }
 #pragma unroll
-    for (int i = 0; i < n; ++i) W[i] = sqrt(ordered_sum9(col[i] * col[i]));
+    for (int i = 0; i < n; ++i) W[i] = sqrt(ordered_sum9(col[i] * col[i], base));
 #pragma unroll
     for (int i = 0; i < n - 1; ++i) {                  // selection sort, descending; first maximum wins
         int j = i;
         double wj = W[i];
 #pragma unroll
         for (int k = i + 1; k < n; ++k) if (wj < W[k]) { j = k; wj = W[k]; }
-        if (j != i) {
 #pragma unroll
-            for (int k = i + 1; k < n; ++k)
-                if (k == j) {
-                    const double tw = W[i]; W[i] = W[k]; W[k] = tw;
-                    const double tc = col[i]; col[i] = col[k]; col[k] = tc;
-                }
-        }
+        for (int k = i + 1; k < n; ++k)
+            if (k == j) {
+                const double tw = W[i]; W[i] = W[k]; W[k] = tw;
+                const double tc = col[i]; col[i] = col[k]; col[k] = tc;
+            }
     }
     CvRng rng;
     rng.state = 0x12345678;
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         double sd = i < n ? W[i < n ? i : 0] : 0;
-        for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
+        for (int ii = 0; ii < 100; ++ii) {
+            const bool need = sd <= minval;            // this group draws another vector
+            if (!__any_sync(full, need)) break;
             const double val0 = 1. / m;
             double v = 0;
+            CvRng r2 = rng;
             for (int k = 0; k < m; ++k) {
-                const double vk = (rng.next() & 256) != 0 ? val0 : -val0;
-                if (k == lane) v = vk;
+                const double vk = (r2.next() & 256) != 0 ? val0 : -val0;
+                if (k == kcol) v = vk;
             }
-            col[i] = v;
+            if (need) rng = r2;
+            double ci = need ? v : col[i];
             for (int it2 = 0; it2 < 2; ++it2) {
 #pragma unroll
                 for (int j = 0; j < i; ++j) {
-                    sd = ordered_sum9(col[i] * col[j]);
-                    const double t = col[i] - sd * col[j];
-                    double asum = ordered_sum9(fabs(t));
+                    const double d = ordered_sum9(ci * col[j], base);
+                    const double t = ci - d * col[j];
+                    double asum = ordered_sum9(fabs(t), base);
                     asum = asum > eps * 100 ? 1 / asum : 0;
-                    col[i] = t * asum;
+                    ci = t * asum;
                 }
             }
-            sd = sqrt(ordered_sum9(col[i] * col[i]));
+            const double nsd = sqrt(ordered_sum9(ci * ci, base));
+            if (need) { col[i] = ci; sd = nsd; }
         }
-        const double s = sd > minval ? 1 / sd : 0.;
-        col[i] *= s;
+        const double sc = sd > minval ? 1 / sd : 0.;
+        col[i] *= sc;
     }
     double f1[9], f2[9];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) { f1[j] = __shfl_sync(full, col[7], j); f2[j] = __shfl_sync(full, col[8], j); }
-    int nr = 0;
-    if (lane == 0) nr = fm7_finish(f1, f2, nm, F);
-    return __shfl_sync(full, nr, 0);
+    for (int j = 0; j < 9; ++j) { f1[j] = __shfl_sync(full, col[7], base + j); f2[j] = __shfl_sync(full, col[8], base + j); }
+    if (kcol == 0 && lane < 27) nm_out[g] = ok ? fm7_finish(f1, f2, nm, F[g]) : 0;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -212,10 +230,10 @@ fundmat_kernel(RansacScratch R) {
     const float thr = (float)(kFmThreshold * kFmThreshold);
 
     while (!sh.stop) {
-        // ---- thread 0: the next RS_WARPS samples from the cv::RNG stream ------------------------------
+        // ---- thread 0: the next RS_BATCH samples from the cv::RNG stream ------------------------------
         if (tid == 0) {
-            for (int w = 0; w < RS_WARPS; ++w) {
-                sh.found[w] = -1;   // not needed
+            for (int w = 0; w < RS_BATCH; ++w) sh.found[w] = -1;
+            for (int w = 0; w < RS_BATCH; ++w) {
                 if (sh.iter_base + w >= sh.niters) break;
                 int idx[7];
                 const bool ok = get_subset7(m1, m2, n, sh.rng, lmeds ? 1000 : 10000, idx, sh.ms1[w], sh.ms2[w]);
@@ -224,47 +242,46 @@ fundmat_kernel(RansacScratch R) {
             }
         }
         __syncthreads();
-        // ---- every warp: solve and score its sample -------------------------------------------------
-        if (sh.found[wid] == 1) {
-            {
-                const int nm7 = run_7point_warp(sh.ms1[wid], sh.ms2[wid], sh.F[wid]);
-                if (lane == 0) sh.nmodels[wid] = nm7;
+        // ---- every warp: solve its three samples ---------------------------------------------------------
+        const int w0 = wid * RS_GROUPS;
+        if (sh.found[w0] == 1)                         // samples are drawn in order: none of the later ones without the first
+            run_7point_warp3(sh.ms1 + w0, sh.ms2 + w0, sh.found + w0, sh.F + w0, sh.nmodels + w0);
+        __syncthreads();
+        // ---- OpenCV's sequential loop over the iterations of this round: the whole CTA scores one sample's models,
+        //      thread 0 does the "best so far / update niters" bookkeeping; samples beyond the (shrinking) iteration
+        //      count are never scored ---------------------------------------------------------------------------
+        for (int w = 0; w < RS_BATCH; ++w) {
+            const int iter = sh.iter_base + w;
+            if (iter >= sh.niters || sh.found[w] != 1) {       // uniform: shared state, read after a barrier
+                if (tid == 0) sh.stop = 1;                     // getSubset failed: return false (iter 0) or break
+                break;
             }
-            __syncwarp();
-            const int nm = sh.nmodels[wid];
+            const int nm = sh.nmodels[w];
             for (int i = 0; i < nm; ++i) {
-                const double* F = sh.F[wid] + 9 * i;
+                const double* F = sh.F[w] + 9 * i;
                 if (!lmeds) {
                     int good = 0;
-                    for (int k = lane; k < n; k += 32) good += fm_error(F, m1[k], m2[k]) <= thr ? 1 : 0;
+                    for (int k = tid; k < n; k += RS_THREADS) good += fm_error(F, m1[k], m2[k]) <= thr ? 1 : 0;
                     for (int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(0xffffffffu, good, o);
-                    if (lane == 0) sh.good[wid][i] = good;
-                } else if (lane == 0) {
+                    if (lane == 0) sh.wsum[wid] = good;
+                } else if (tid == 0) {
                     float e[14];
-                    for (int k = 0; k < n; ++k) {   // n <= 14: insertion sort, element n/2 is nth_element's answer
+                    for (int k = 0; k < n; ++k) {       // n <= 14: insertion sort, element n/2 is nth_element's answer
                         const float v = fm_error(F, m1[k], m2[k]);
                         int j = k;
                         while (j > 0 && e[j - 1] > v) { e[j] = e[j - 1]; --j; }
                         e[j] = v;
                     }
-                    sh.median[wid][i] = e[n / 2];
+                    sh.median[w][i] = e[n / 2];
                 }
-            }
-        }
-        __syncthreads();
-        // ---- thread 0: OpenCV's sequential bookkeeping, in iteration order ------------------------------
-        if (tid == 0) {
-            for (int w = 0; w < RS_WARPS; ++w) {
-                const int iter = sh.iter_base + w;
-                if (iter >= sh.niters) { sh.stop = 1; break; }
-                if (sh.found[w] != 1) { sh.stop = 1; break; }   // getSubset failed: return false (iter 0) or break
-                const int nm = sh.nmodels[w];
-                for (int i = 0; i < nm; ++i) {
+                __syncthreads();
+                if (tid == 0) {
                     if (!lmeds) {
-                        const int good = sh.good[w][i];
+                        int good = 0;
+                        for (int q = 0; q < RS_WARPS; ++q) good += sh.wsum[q];
                         if (good > max(sh.maxGood, kFmModelPoints - 1)) {
                             sh.maxGood = good;
-                            for (int q = 0; q < 9; ++q) sh.best[q] = sh.F[w][9 * i + q];
+                            for (int q = 0; q < 9; ++q) sh.best[q] = F[q];
                             sh.have_model = 1;
                             sh.niters = ransac_update_num_iters(kFmConfidence, (double)(n - good) / n, kFmModelPoints, sh.niters);
                         }
@@ -272,13 +289,17 @@ fundmat_kernel(RansacScratch R) {
                         const double med = (double)sh.median[w][i];
                         if (med < sh.minMedian) {
                             sh.minMedian = med;
-                            for (int q = 0; q < 9; ++q) sh.best[q] = sh.F[w][9 * i + q];
+                            for (int q = 0; q < 9; ++q) sh.best[q] = F[q];
                             sh.have_model = 1;
                         }
                     }
                 }
+                __syncthreads();
             }
-            sh.iter_base += RS_WARPS;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            sh.iter_base += RS_BATCH;
             if (sh.iter_base >= sh.niters) sh.stop = 1;
         }
         __syncthreads();
@@ -361,25 +382,35 @@ cudaError_t ransac_host_points(const RansacScratch& R, int scratch_slot, const f
     return cudaSuccess;
 }
 
-// parity seam: run7Point alone, one warp per 7-point sample (svo_fundmat_7point)
+// parity seam: run7Point alone, RS_GROUPS samples per warp (svo_fundmat_7point)
 __global__ void __launch_bounds__(RS_THREADS)
 fm7_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, int n_sets, double* __restrict__ F,
            int32_t* __restrict__ n_models) {
-    __shared__ Pt2f s1[RS_WARPS][7], s2[RS_WARPS][7];
-    __shared__ double sF[RS_WARPS][27];
+    __shared__ Pt2f s1[RS_BATCH][7], s2[RS_BATCH][7];
+    __shared__ double sF[RS_BATCH][27];
+    __shared__ int sv[RS_BATCH], sn[RS_BATCH];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int set = blockIdx.x * RS_WARPS + wid;
-    if (set >= n_sets) return;
-    if (lane < 7) {
-        const float2 a = p1[set * 7 + lane], b = p2[set * 7 + lane];
-        s1[wid][lane].x = a.x; s1[wid][lane].y = a.y; s2[wid][lane].x = b.x; s2[wid][lane].y = b.y;
+    const int w0 = wid * RS_GROUPS;
+    const int set0 = (blockIdx.x * RS_WARPS + wid) * RS_GROUPS;
+    if (set0 >= n_sets) return;
+    for (int g = 0; g < RS_GROUPS; ++g) {
+        const int set = set0 + g;
+        if (lane == 0) { sv[w0 + g] = set < n_sets ? 1 : 0; sn[w0 + g] = 0; }
+        if (lane < 7 && set < n_sets) {
+            const float2 a = p1[set * 7 + lane], b = p2[set * 7 + lane];
+            s1[w0 + g][lane].x = a.x; s1[w0 + g][lane].y = a.y; s2[w0 + g][lane].x = b.x; s2[w0 + g][lane].y = b.y;
+        }
+        if (lane < 27) sF[w0 + g][lane] = 0;
     }
-    if (lane < 27) sF[wid][lane] = 0;
     __syncwarp();
-    const int nm = run_7point_warp(s1[wid], s2[wid], sF[wid]);
+    run_7point_warp3(s1 + w0, s2 + w0, sv + w0, sF + w0, sn + w0);
     __syncwarp();
-    if (lane < 27) F[(size_t)set * 27 + lane] = sF[wid][lane];
-    if (lane == 0) n_models[set] = nm;
+    for (int g = 0; g < RS_GROUPS; ++g) {
+        const int set = set0 + g;
+        if (set >= n_sets) break;
+        if (lane < 27) F[(size_t)set * 27 + lane] = sF[w0 + g][lane];
+        if (lane == 0) n_models[set] = sn[w0 + g];
+    }
 }
 
 cudaError_t fm7_host_points(const float* p1, const float* p2, int n_sets, double* F, int32_t* n_models, cudaStream_t st) {
@@ -394,7 +425,7 @@ cudaError_t fm7_host_points(const float* p1, const float* p2, int n_sets, double
         (e = cudaMalloc(&dn, (size_t)n_sets * sizeof(int32_t))) == cudaSuccess &&
         (e = cudaMemcpyAsync(d1, p1, pb, cudaMemcpyHostToDevice, st)) == cudaSuccess &&
         (e = cudaMemcpyAsync(d2, p2, pb, cudaMemcpyHostToDevice, st)) == cudaSuccess) {
-        fm7_kernel<<<(n_sets + RS_WARPS - 1) / RS_WARPS, RS_THREADS, 0, st>>>(d1, d2, n_sets, dF, dn);
+        fm7_kernel<<<(n_sets + RS_BATCH - 1) / RS_BATCH, RS_THREADS, 0, st>>>(d1, d2, n_sets, dF, dn);
         if ((e = cudaGetLastError()) == cudaSuccess &&
             (e = cudaMemcpyAsync(F, dF, (size_t)n_sets * 27 * sizeof(double), cudaMemcpyDeviceToHost, st)) == cudaSuccess &&
             (e = cudaMemcpyAsync(n_models, dn, (size_t)n_sets * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) == cudaSuccess)
