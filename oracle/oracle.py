@@ -229,6 +229,26 @@ def projected_coords(pre_matches, pre_left, pre_right, other_matches_tracked, ca
     return out[:n].copy()
 
 
+def aux_nms_mask(xy, response, H, W, min_distance, num_out=None, sort_mode=0):
+    """auxiliary m_non_max_sup (stage2_detect.cpp:225-283) alone: survivors mask"""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    resp = np.ascontiguousarray(response, np.float32)
+    out = np.zeros(max(len(xy), 1), np.uint8)
+    lib().orc_aux_non_max_sup(_p(xy), _p(resp), len(xy), int(H), int(W), int(len(xy) if num_out is None else num_out),
+                              int(min_distance), int(sort_mode), _p(out))
+    return out[:len(xy)].astype(bool)
+
+
+def pinhole_projection(lmks, cam, delta_pose):
+    """m_pinhole_stereo_projection (stage5_optimization.cpp:35-257) alone: (n x 4 float32 pixels, n x 4 x 6 Jacobians)"""
+    lm = np.ascontiguousarray(lmks, np.float64).reshape(-1, 3)
+    dp = np.ascontiguousarray(delta_pose, np.float64)
+    px = np.zeros((len(lm), 4), np.float32)
+    J = np.zeros((len(lm), 4, 6))
+    lib().orc_pinhole_projection(_p(lm), len(lm), C.byref(cam), _p(dp), _p(px), _p(J))
+    return px, J
+
+
 def track_consistency(matL, matR, inlL, inlR):
     l = np.ascontiguousarray(matL, DMATCH)
     r = np.ascontiguousarray(matR, DMATCH)
@@ -330,6 +350,45 @@ def cv2_fmat_mask(p1, p2):
     if mask is None:
         return None
     return np.ascontiguousarray(mask.ravel().astype(np.uint8))
+
+
+_fm_host = None
+
+
+def host_fmat_mask(p1, p2):
+    """The host build of stereo_vo_b200/csrc/fundmat_core.cuh (tests/cpp/fundmat_host.cpp): bit-identical to
+    cv2.findFundamentalMat on every input cv2 answers (tests/test_host_cpu.py, tools/ransac_host_vs_cv2.py).  Used ONLY
+    where cv2 4.13 itself raises (its solveCubic returns -1 for a sample whose cubic vanishes and runKernel then asks
+    for a negative row range, matrix.cpp:764): this continues the way OpenCV's loop does for any other sample without a
+    model (nmodels <= 0 -> next iteration)."""
+    global _fm_host
+    if _fm_host is None:
+        so = os.path.join(_HERE, "libfundmat_host.so")
+        src = os.path.join(os.path.dirname(_HERE), "tests", "cpp", "fundmat_host.cpp")
+        hdr = os.path.join(os.path.dirname(_HERE), "stereo_vo_b200", "csrc", "fundmat_core.cuh")
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
+        _fm_host = C.CDLL(so)
+    p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)
+    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+    n = len(p1)
+    if n < 7:
+        return None
+    mask = np.zeros(n, np.uint8)
+    _fm_host.fundmat_host(_p(p1), _p(p2), n, _p(mask), None)
+    return mask
+
+
+def cv2_fmat_mask_tolerant(p1, p2):
+    """cv2.findFundamentalMat; where cv2 4.13 raises its internal assertion, the host build of the same arithmetic."""
+    try:
+        return cv2_fmat_mask(p1, p2)
+    except _cv2().error:
+        cv2_fmat_mask_tolerant.raised += 1
+        return host_fmat_mask(p1, p2)
+
+
+cv2_fmat_mask_tolerant.raised = 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -489,7 +548,7 @@ class OracleEstimator:
         if self.ransac == "off":
             inlL = inlR = None
         else:
-            fn = cv2_fmat_mask if self.ransac == "cv2" else self.ransac
+            fn = cv2_fmat_mask if self.ransac == "cv2" else (cv2_fmat_mask_tolerant if self.ransac == "cv2_tolerant" else self.ransac)
             inlL = fn(p1L, p2L)
             inlR = fn(p1R, p2R)
         tracked = track_consistency(matL, matR, inlL, inlR)
@@ -507,7 +566,7 @@ class OracleEstimator:
         keep = np.ones(len(cand), bool)
         inlL = inlR = None
         if self.ransac != "off" and len(cand):
-            fn = cv2_fmat_mask if self.ransac == "cv2" else self.ransac
+            fn = cv2_fmat_mask if self.ransac == "cv2" else (cv2_fmat_mask_tolerant if self.ransac == "cv2_tolerant" else self.ransac)
             inlL = fn(p1L, p2L)                    # S4:693-713: the right filter only runs when the left one found >= 8
             if inlL is not None and int(np.count_nonzero(inlL)) >= 8:
                 inlR = fn(p1R, p2R)
@@ -587,9 +646,11 @@ class OracleEstimator:
                         ids[k] = self.m_last_match_ID
                         self.m_last_match_ID += 1
                 f.ids = ids
-            out["tracked_feats_from_last_frame"] = len(tracked)
-            # S4:743-752
-            out["tracked_feats_from_last_KF"] = int((f.ids <= self.m_last_kf_max_id).sum()) if self.p.vo_use_matches_ids else 0
+            # S4:743-752 (members); the RESULT fields are assigned at S5:724-725 only, when stage 5 runs to its end
+            n_frame = len(tracked)
+            n_kf = int((f.ids <= self.m_last_kf_max_id).sum()) if self.p.vo_use_matches_ids else 0
+            out["m_num_tracked_pairs_from_last_frame"], out["m_num_tracked_pairs_from_last_kf"] = n_frame, n_kf
+            out["tracked_feats_from_last_frame"] = out["tracked_feats_from_last_KF"] = 0
             if len(tracked) < self.p.bad_tracking_th:  # P:326-330
                 self.m_error = out["error_code"] = VOEC["voecBadTracking"]
             if self.m_error != VOEC["voecBadTracking"]:
@@ -603,6 +664,7 @@ class OracleEstimator:
                 out["out_residual"] = residual
                 out["outliers"] = inl
                 if res.reached_end:
+                    out["tracked_feats_from_last_frame"], out["tracked_feats_from_last_KF"] = n_frame, n_kf
                     out["pose"] = dict(rotvec=np.array(res.out_pose_rotvec[:]), t=np.array(res.out_pose_t[:]),
                                        mat=np.array(res.out_pose_mat[:]).reshape(4, 4),
                                        ypr=np.array(res.out_pose_ypr[:]), delta=np.array(res.delta_pose[:]))
@@ -687,6 +749,14 @@ class OracleEstimatorOctaves(OracleEstimator):
         super().__init__(params, backend, ransac, sort_mode)
         self.pyr_mode = pyr_mode
 
+    def set_this_frame_as_kf(self):                  # H:675-683: octave 0 only ("const size_t octave = 0")
+        assert self.cur is not None and self.cur[0].ids is not None and len(self.cur[0].ids) > 0
+        self.m_last_kf_max_id = int(self.cur[0].ids.max())
+
+    def set_ids(self, ids):                          # H:685-694: octave 0 only
+        f = self.cur if self.cur is not None else self.prev
+        f[0].ids = np.array(ids, np.int64)
+
     def detect_octave(self, img, quota):
         H, W = img.shape
         th = self.m_current_fast_th
@@ -762,10 +832,10 @@ class OracleEstimatorOctaves(OracleEstimator):
                 f.ids = ids
         out["tracked"] = tracked_all
         out["track_dbg"] = dbg_all
-        total = sum(len(t) for t in tracked_all)      # S4:743-752
-        out["tracked_feats_from_last_frame"] = total
-        out["tracked_feats_from_last_KF"] = (sum(int((f.ids <= self.m_last_kf_max_id).sum()) for f in frames)
-                                             if self.p.vo_use_matches_ids else 0)
+        total = sum(len(t) for t in tracked_all)      # S4:743-752 (members; the result fields: S5:724-725)
+        n_kf = (sum(int((f.ids <= self.m_last_kf_max_id).sum()) for f in frames) if self.p.vo_use_matches_ids else 0)
+        out["m_num_tracked_pairs_from_last_frame"], out["m_num_tracked_pairs_from_last_kf"] = total, n_kf
+        out["tracked_feats_from_last_frame"] = out["tracked_feats_from_last_KF"] = 0
         if total < self.p.bad_tracking_th:            # P:326-330
             self.m_error = out["error_code"] = VOEC["voecBadTracking"]
             if not repeat:
@@ -799,6 +869,7 @@ class OracleEstimatorOctaves(OracleEstimator):
         out.update(gn=res, gn_dbg=dict(flat, ini=ini), error_code=res.error_code, valid=bool(res.valid), num_it=res.num_it,
                    num_it_final=res.num_it_final, out_residual=residual, outliers=inl)
         if res.reached_end:
+            out["tracked_feats_from_last_frame"], out["tracked_feats_from_last_KF"] = total, n_kf
             out["pose"] = dict(rotvec=np.array(res.out_pose_rotvec[:]), t=np.array(res.out_pose_t[:]),
                                mat=np.array(res.out_pose_mat[:]).reshape(4, 4), ypr=np.array(res.out_pose_ypr[:]),
                                delta=np.array(res.delta_pose[:]))

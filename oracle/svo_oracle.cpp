@@ -683,7 +683,7 @@ int orc_match_rbr(const OrcKeyPoint* kpsL, const uint8_t* descL, int nL, const i
     int m = 0;
     for (int i = 0; i < nL; ++i)                                           // S3:398-410
         if (left_match[i] != INVALID) {
-            OrcDMatch d = {i, left_match[i], 0, (float)right_assign[left_match[i]].second};
+            OrcDMatch d = {i, left_match[i], -1, (float)right_assign[left_match[i]].second};   // cv::DMatch(q, t, d): imgIdx = -1 (S3:404)
             out[m++] = d;
         }
     return m;
@@ -956,6 +956,25 @@ int orc_projected_coords(const OrcDMatch* pre_matches, int n_matches, const OrcK
         ++n;
     }
     return n;
+}
+
+// ---- test hooks for tests/test_ref_cpu.py (restatement vs the reference's compiled text) ----
+// auxiliary m_non_max_sup S2:225-283 alone
+void orc_aux_non_max_sup(const float* xy, const float* response, int n, int imgH, int imgW, int num_out, int min_distance,
+                         int sort_mode, uint8_t* survivors_out) {
+    std::vector<char> s;
+    aux_non_max_sup(xy, response, (size_t)n, s, (size_t)imgH, (size_t)imgW, (size_t)num_out, min_distance, sort_mode);
+    for (int i = 0; i < n; ++i) survivors_out[i] = (uint8_t)s[i];
+}
+// m_pinhole_stereo_projection S5:35-257 alone: pixels (4 floats) and the 4x6 Jacobian per landmark
+void orc_pinhole_projection(const double* lmks, int n, const OrcCamera* cam, const double* dp, float* px4, double* jac24) {
+    RotDeriv R;
+    rot_and_derivs(dp, R);
+    for (int i = 0; i < n; ++i) {
+        double J[4][6];
+        project_one(Lmk{lmks[3 * i], lmks[3 * i + 1], lmks[3 * i + 2]}, *cam, dp, R, px4 + 4 * i, J);
+        std::memcpy(jac24 + 24 * i, J, sizeof J);
+    }
 }
 
 int orc_sizeof_keypoint() { return (int)sizeof(OrcKeyPoint); }

@@ -1038,8 +1038,10 @@ int svo_get_matches_oct(svo_ctx* c, int32_t slot, int32_t octave, int32_t which,
     CU(c, cudaMemcpy(&n, Pk->n_match + pi, sizeof(int), cudaMemcpyDeviceToHost));
     std::vector<int4> tmp(n);
     if (n) CU(c, cudaMemcpy(tmp.data(), Pk->match + pi * Pk->p.kp_cap, n * sizeof(int4), cudaMemcpyDeviceToHost));
+    // imgIdx: 0 from BFMatcher::match (S3:91-94), -1 from the cv::DMatch(q, t, d) constructor of the row-by-row branch (S3:404)
+    const int img_idx_field = c->cfg.match_method == 1 ? -1 : 0;
     for (int i = 0; i < n && i < cap; ++i) {
-        svo_dmatch m = {tmp[i].x, tmp[i].y, 0, (float)tmp[i].z};
+        svo_dmatch m = {tmp[i].x, tmp[i].y, img_idx_field, (float)tmp[i].z};
         out[i] = m;
     }
     return n;

@@ -394,7 +394,10 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
 
     if (external != GN_EXTERNAL) {
         if (!st.has_prev) return;               // voecFirstIteration already reported (P:348-352)
-        if (st.m_error == 5) return;            // voecBadTracking: stage 5 is skipped (P:332)
+        if (st.m_error == 5) {                  // voecBadTracking: stage 5 is skipped (P:332) ...
+            if (tid == 0) res.tracked_frame = res.tracked_kf = 0;   // ... and with it S5:724-725 (see the end of this kernel)
+            return;
+        }
     }
     const int T = P.n_tracked[slot];
     const int cur = st.cur, prev = cur ^ 1;
@@ -478,8 +481,10 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
     __syncthreads();
 
     int n_non_masked = triangulate(G, base, T, cam, s_cnt);
+    // result.tracked_feats_from_last_frame / _KF are assigned at S5:724-725 only, i.e. when stage 5 runs to its end;
+    // every early return leaves the caller's fresh TStereoOdometryResult at 0 (svo_get_octave_stats keeps the counts)
     if (n_non_masked < 8) {   // S5:521-526
-        if (tid == 0) { res.valid = 0; res.n_residuals = 0; }
+        if (tid == 0) { res.valid = 0; res.n_residuals = 0; if (external != GN_EXTERNAL) res.tracked_frame = res.tracked_kf = 0; }
         return;
     }
 
@@ -491,7 +496,7 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
         eval_rgn(G, base, T, cam, p, sh);
         if (tid == 0) res.error_code = sh.fail ? 1 : 0;   // S5:564: result.error_code = out_error_code
         if (sh.fail) {
-            if (tid == 0) { st.m_error = 1; res.valid = 0; res.num_it = num_it; }   // S5:384, S5:569-573
+            if (tid == 0) { st.m_error = 1; res.valid = 0; res.num_it = num_it; if (external != GN_EXTERNAL) res.tracked_frame = res.tracked_kf = 0; }   // S5:384, S5:569-573
             return;
         }
         if (tid == 0) {
@@ -536,7 +541,7 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
     __syncthreads();
     n_non_masked = triangulate(G, base, T, cam, s_cnt);
     if (n_non_masked < 8) {   // S5:616-621
-        if (tid == 0) { res.valid = 0; res.n_residuals = T; }
+        if (tid == 0) { res.valid = 0; res.n_residuals = T; if (external != GN_EXTERNAL) res.tracked_frame = res.tracked_kf = 0; }
         return;
     }
 
@@ -549,7 +554,7 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
         __syncthreads();
         eval_rgn(G, base, T, cam, p, sh);
         if (sh.fail) {   // S5:670-675 (result.error_code is not touched here; m_error is, S5:384)
-            if (tid == 0) { st.m_error = 1; res.valid = 0; res.n_residuals = T; res.num_it_final = num_it_final; }
+            if (tid == 0) { st.m_error = 1; res.valid = 0; res.n_residuals = T; res.num_it_final = num_it_final; if (external != GN_EXTERNAL) res.tracked_frame = res.tracked_kf = 0; }
             return;
         }
         if (tid == 0) {

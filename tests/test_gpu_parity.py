@@ -23,7 +23,8 @@ def xys(k):
 
 
 def mtuple(m):
-    return np.stack([m["queryIdx"], m["trainIdx"], m["distance"].astype(np.int32)], 1)
+    """all four cv::DMatch fields (imgIdx is 0 from BFMatcher::match, -1 from the row-by-row matcher's constructor)"""
+    return np.stack([m["queryIdx"], m["trainIdx"], m["distance"].astype(np.int32), m["imgIdx"]], 1)
 
 
 def ocam(cam):
@@ -526,7 +527,9 @@ def _run_sequence(ctx, est, frames, cam, slot=0, check_golden=None, golden=None)
             if t["inlL"] is not None and est.ransac != "off":
                 assert np.array_equal(il, t["inlL"]) and np.array_equal(ir, t["inlR"]), f"frame {i}: RANSAC masks"
             assert np.array_equal(ctx.tracked_pairs(slot), o["tracked"]), f"frame {i}: tracked pairs"
-            assert r.tracked_feats_from_last_frame == len(o["tracked"])
+            # the result field is only assigned when stage 5 runs to its end (S5:724-725); the count itself: octave_stats
+            assert r.tracked_feats_from_last_frame == o["tracked_feats_from_last_frame"]
+            assert ctx.octave_stats(slot)[0, 3] == len(o["tracked"])
         assert (r.error_code, bool(r.valid), r.num_it, r.num_it_final) == (o["error_code"], o["valid"], o["num_it"], o["num_it_final"]), \
             f"frame {i}: status {list(r.delta_pose)} vs {None if o['pose'] is None else o['pose']['delta']}"
         if o["pose"] is not None:
@@ -541,7 +544,7 @@ def _run_sequence(ctx, est, frames, cam, slot=0, check_golden=None, golden=None)
         if check_golden is not None:
             g = golden
             assert np.array_equal(xys(ctx.keypoints(slot, 0, 0)), g[f"{check_golden}_f{i}_kpsL"])
-            assert np.array_equal(mtuple(ctx.matches(slot, 0)), g[f"{check_golden}_f{i}_matches"])
+            assert np.array_equal(mtuple(ctx.matches(slot, 0))[:, :3], g[f"{check_golden}_f{i}_matches"])
             assert np.array_equal(ctx.tracked_pairs(slot) if i > 0 else np.zeros((0, 2), np.int64), g[f"{check_golden}_f{i}_tracked"])
             if i > 0:
                 np.testing.assert_allclose(r.delta_pose[:], g[f"{check_golden}_f{i}_delta"], atol=POSE_TOL_RAD)
