@@ -140,6 +140,16 @@ void svo_destroy(svo_ctx* ctx);                                 /* ~CStereoOdome
 const char* svo_last_error(const svo_ctx* ctx);                 /* ctx may be NULL: last creation error */
 int  svo_reset_slot(svo_ctx* ctx, int32_t slot);                /* fresh estimator state for one slot */
 
+/* setFASTThreshold / setORBThreshold / resetFASTThreshold / resetORBThreshold (libstereo-odometry.h:529-541):
+ * m_current_fast_th and m_current_orb_th of one slot (slot = -1: every slot), read at every following call
+ * (stage2_detect.cpp:510, stage3_match_left_right.cpp:164, stage4_match_consecutive.cpp:149).  Nothing else of the
+ * slot's state changes: external adaptive loops adjust these between frames while tracking continues.  A negative value
+ * keeps that threshold; the clamping to [fast_min_th, fast_max_th] / [orb_min_th, orb_max_th] (:531,:538) is the
+ * caller's (the host shim does it).  Stream-ordered: applies to steps submitted after this call.
+ * svo_reset_slot returns a slot to the configured values (svo_config.fast_threshold / orb_threshold). */
+int  svo_set_thresholds(svo_ctx* ctx, int32_t slot, int32_t fast_th, int32_t orb_th);
+int  svo_get_thresholds(svo_ctx* ctx, int32_t slot, int32_t* fast_th, int32_t* orb_th);   /* getFASTThreshold / getORBThreshold */
+
 /* ---- the pipeline: processNewImagePair (process_new_image_pair.cpp:41-385) ----------------- */
 /* One call == one processNewImagePair per listed slot, all slots advanced together on the GPU.
  * left/right: n pointers to 8-bit images (host memory), row stride in bytes: gray and rectified unless
@@ -159,6 +169,16 @@ int svo_submit_batch(svo_ctx* ctx, int32_t n, const int32_t* slots,
                      const uint8_t* const* left, const uint8_t* const* right, size_t stride_bytes,
                      const svo_camera* cams, const uint8_t* repeat);
 int svo_wait_batch(svo_ctx* ctx, svo_result* results);
+/* The variable-length members of TStereoOdometryResult (libstereo-odometry.h:239-240) with every batch:
+ * after svo_set_result_detail(ctx, 1) each submitted batch also copies out_residual and outliers of its slots to the
+ * host (same stream, same event), and svo_wait_batch_detail hands them out: item i's vectors start at
+ * residuals[i*cap] / outliers[i*cap], results[i].n_residuals / n_outliers entries are valid (at most cap each;
+ * the context's capacity is 2*orb_nfeats per octave).  Either array may be NULL. */
+/* page-locked host memory for image buffers given to svo_submit_batch (cudaHostAlloc, portable); NULL on failure */
+void* svo_host_alloc(size_t bytes);
+void  svo_host_free(void* p);
+int svo_set_result_detail(svo_ctx* ctx, int32_t on);
+int svo_wait_batch_detail(svo_ctx* ctx, svo_result* results, double* residuals, int64_t* outliers, int32_t cap);
 
 /* Same, images already resident in device memory (HBM): d_left/d_right point to n images each,
  * image i at d_left + i*image_pitch_bytes, rows `stride_bytes` apart.  Results stay on the device
@@ -205,6 +225,15 @@ int svo_get_pyramid_plane(svo_ctx* ctx, int32_t item, int32_t octave, int32_t si
  * and the two RANSAC inlier masks (stage4_match_consecutive.cpp:145-160, 202, 237) */
 int svo_get_track_candidates(svo_ctx* ctx, int32_t slot, int32_t* out_query, int32_t* out_trainL,
                              int32_t* out_trainR, uint8_t* out_inlL, uint8_t* out_inlR, int32_t cap);
+/* survivors of stage 5's auxiliary non-maximal suppression (stage5_optimization.cpp:465-474) over the flattened tracked
+ * pairs of all octaves (:419-461), as the first Gauss-Newton loop starts with them: the rows the reference writes to
+ * optimization.txt (:477-492).  Returns the number of tracked pairs. */
+int svo_get_stage5_survivors(svo_ctx* ctx, int32_t slot, uint8_t* out, int32_t cap);
+/* the same for one octave, plus the Hamming distances of the surviving matL / matR entries (what the reference prints as
+ * the fifth column of l-l_%04d.txt / r-r_%04d.txt, stage4_match_consecutive.cpp:193-195, 228-230); any pointer may be NULL */
+int svo_get_track_candidates_oct(svo_ctx* ctx, int32_t slot, int32_t octave, int32_t* out_query, int32_t* out_trainL,
+                                 int32_t* out_trainR, uint8_t* out_inlL, uint8_t* out_inlR, float* out_distL, float* out_distR,
+                                 int32_t cap);
 
 /* ---- match-ID / key-frame control (libstereo-odometry.h:675-726); need vo_use_matches_ids ----- */
 int svo_set_this_frame_as_kf(svo_ctx* ctx, int32_t slot);         /* setThisFrameAsKF(): m_last_kf_max_id = max current ID, H:675-683 */

@@ -30,7 +30,7 @@ EXPORTS = [
     "svo_get_keypoints", "svo_get_descriptors", "svo_get_matches", "svo_get_match_ids", "svo_get_tracked_pairs",
     "svo_get_residuals", "svo_get_outliers", "svo_get_track_candidates", "svo_get_plane",
     "svo_detect", "svo_match_hamming", "svo_match_hamming_device", "svo_match_lr", "svo_get_change_in_pose",
-    "svo_fundmat_ransac", "svo_fundmat_7point", "svo_abi_version", "svo_kernel_launches", "svo_stream",
+    "svo_fundmat_ransac", "svo_fundmat_7point", "svo_set_thresholds", "svo_get_thresholds", "svo_host_alloc", "svo_host_free", "svo_set_result_detail", "svo_wait_batch_detail", "svo_get_track_candidates_oct", "svo_get_stage5_survivors", "svo_abi_version", "svo_kernel_launches", "svo_stream",
     "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks", "svo_set_concurrency",
     "svo_set_input_format", "svo_set_rectify_maps", "svo_prepare_rectify", "svo_prepare_rectify_device",
     "svo_get_projected_coords", "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
@@ -384,6 +384,16 @@ class Context:
 
     def stream(self):
         return lib().svo_stream(self._h)
+
+    # ---- dynamic thresholds (libstereo-odometry.h:529-541) -----------------------------------------------
+    def set_thresholds(self, fast_th=-1, orb_th=-1, slot=-1):
+        """m_current_fast_th / m_current_orb_th of one slot (-1: every slot); a negative value keeps that threshold."""
+        self._check(lib().svo_set_thresholds(self._h, int(slot), int(fast_th), int(orb_th)))
+
+    def thresholds(self, slot=0):
+        f, o = C.c_int32(0), C.c_int32(0)
+        self._check(lib().svo_get_thresholds(self._h, int(slot), C.byref(f), C.byref(o)))
+        return f.value, o.value
 
     # ---- match IDs / key frames (libstereo-odometry.h:675-726) ---------------------------------------------
     def set_this_frame_as_kf(self, slot=0):

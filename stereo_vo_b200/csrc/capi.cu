@@ -77,6 +77,10 @@ struct svo_ctx {
     Camera* r_cams[kDepth] = {};
     Result* r_res[kDepth] = {};
     SlotState* r_state[kDepth] = {};
+    // svo_set_result_detail(1): the variable-length members of TStereoOdometryResult travel with every batch
+    int detail = 0;
+    double* r_resid[kDepth] = {};      // [n_slots][PG.kp_cap]
+    int32_t* r_outl[kDepth] = {};      // [n_slots][PG.kp_cap]
     cudaEvent_t ev_h2d[kDepth] = {}, ev_done[kDepth] = {};
     int pend_n[kDepth] = {}, pend_lo[kDepth] = {}, pend_hi[kDepth] = {};
     int pend_head = 0, pend_count = 0;
@@ -188,6 +192,14 @@ __global__ void reset_slot_kernel(Pools P, int slot) {
     Result r;
     memset(&r, 0, sizeof(r));
     P.result[slot] = r;
+}
+
+// setFASTThreshold / setORBThreshold (libstereo-odometry.h:529-541): only the two ints change, the sequence state stays
+__global__ void set_thresholds_kernel(Pools P, int slot_lo, int slot_hi, int fast_th, int orb_th) {
+    const int s = slot_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > slot_hi) return;
+    if (fast_th >= 0) P.state[s].fast_th1 = fast_th + 1;
+    if (orb_th >= 0) P.state[s].orb_th1 = orb_th + 1;
 }
 
 bool valid_slot(const svo_ctx* c, int slot) { return slot >= 0 && slot < c->cfg.max_seqs; }
@@ -548,7 +560,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     DA(c->d_list_scratch, (size_t)S * 2 * 3 * (cfg->max_corners / 16 + 2));
     DA(c->d_key_scratch, (size_t)S * 2 * cfg->max_corners);
     GnScratch& G = c->G;
-    DA(G.prev, S * cap); DA(G.obs, S * cap); DA(G.lmk, S * cap * 3); DA(G.mask, S * cap);
+    DA(G.prev, S * cap); DA(G.obs, S * cap); DA(G.lmk, S * cap * 3); DA(G.mask, S * cap); DA(G.mask0, S * cap);
     DA(G.cur_idx, S * cap); DA(G.ini_pose, S * 6);
     G.residual = P.residual;
     G.occ = c->d_occ;               // the aux NMS of stage 5 runs after stage 2 is finished: same scratch
@@ -594,7 +606,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
             PG.p.kp_cap = (int)total_cap;
             PG.tracked = nullptr;                      // GN_FLATTENED reads GnScratch::cur_idx instead
             DA(PG.n_tracked, S); DA(PG.residual, S * total_cap); DA(PG.outliers, S * total_cap);
-            DA(GG.prev, S * total_cap); DA(GG.obs, S * total_cap); DA(GG.lmk, S * total_cap * 3); DA(GG.mask, S * total_cap);
+            DA(GG.prev, S * total_cap); DA(GG.obs, S * total_cap); DA(GG.lmk, S * total_cap * 3); DA(GG.mask, S * total_cap); DA(GG.mask0, S * total_cap);
             DA(GG.cur_idx, S * total_cap); DA(GG.ini_pose, S * 6);
             DA(GG.occ, (size_t)S * 2 * c->occ_words);      // own grid: stage 5 of one group may overlap stage 2 of another
             GG.residual = PG.residual;
@@ -655,6 +667,37 @@ int svo_reset_slot(svo_ctx* c, int32_t slot) {
     CU(c, cudaGetLastError());
     return SVO_OK;
 }
+
+int svo_set_thresholds(svo_ctx* c, int32_t slot, int32_t fast_th, int32_t orb_th) {
+    if (!c) return SVO_ERR_ARG;
+    if (slot != -1 && !valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "slot index out of range (-1 = every slot)");
+    if (fast_th == 0 || fast_th > 254) return fail(c, SVO_ERR_ARG, "fast_th must be within [1, 254] (negative: keep)");
+    if (orb_th > 0x7FFE) return fail(c, SVO_ERR_ARG, "orb_th out of range (negative: keep)");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const int lo = slot < 0 ? 0 : slot, hi = slot < 0 ? c->cfg.max_seqs - 1 : slot;
+    set_thresholds_kernel<<<(hi - lo + 128) / 128, 128, 0, c->stream>>>(c->P, lo, hi, fast_th, orb_th);   // stream-ordered
+    CU(c, cudaGetLastError());
+    return SVO_OK;
+}
+
+int svo_get_thresholds(svo_ctx* c, int32_t slot, int32_t* fast_th, int32_t* orb_th) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "slot index out of range");
+    SlotState s;
+    int rc = get_state(c, slot, &s);
+    if (rc) return rc;
+    if (fast_th) *fast_th = slot_fast_th(c->P.p, s);
+    if (orb_th) *orb_th = slot_orb_th(c->P.p, s);
+    return SVO_OK;
+}
+
+// page-locked host memory for the image buffers handed to svo_submit_batch (pageable memory works too, but the copies
+// then go through the driver's staging buffers and do not overlap)
+void* svo_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : nullptr;
+}
+void svo_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int svo_synchronize(svo_ctx* c) {
     if (!c) return SVO_ERR_ARG;
@@ -928,24 +971,53 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
     if (rc != SVO_OK) return rc;
     CU(c, cudaMemcpyAsync(c->r_res[b] + lo, c->P.result + lo, (size_t)(hi - lo + 1) * sizeof(Result), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(c->r_state[b] + lo, c->P.state + lo, (size_t)(hi - lo + 1) * sizeof(SlotState), cudaMemcpyDeviceToHost, c->stream));
+    if (c->detail) {   // result.out_residual / result.outliers of every slot of the batch (libstereo-odometry.h:239-240)
+        const size_t gc = (size_t)c->PG.p.kp_cap;
+        CU(c, cudaMemcpyAsync(c->r_resid[b] + lo * gc, c->PG.residual + lo * gc, (size_t)(hi - lo + 1) * gc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(c->r_outl[b] + lo * gc, c->PG.outliers + lo * gc, (size_t)(hi - lo + 1) * gc * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(c, cudaEventRecord(c->ev_done[b], c->stream));
     c->pend_n[b] = n; c->pend_lo[b] = lo; c->pend_hi[b] = hi;
     ++c->pend_count;
     return SVO_OK;
 }
 
-int svo_wait_batch(svo_ctx* c, svo_result* results) {
+int svo_set_result_detail(svo_ctx* c, int32_t on) {
+    if (!c) return SVO_ERR_ARG;
+    if (c->pend_count != 0) return fail(c, SVO_ERR_STATE, "batches are in flight");
+    if (on && !c->r_resid[0]) {
+        const size_t cnt = (size_t)c->n_slots_alloc * c->PG.p.kp_cap;
+        for (int b = 0; b < kDepth; ++b) {
+            cudaError_t e = halloc(c, &c->r_resid[b], cnt);
+            if (e == cudaSuccess) e = halloc(c, &c->r_outl[b], cnt);
+            if (e != cudaSuccess) return cuda_fail(c, e, "cudaMallocHost (result detail rings)");
+        }
+    }
+    c->detail = on ? 1 : 0;
+    return SVO_OK;
+}
+
+int svo_wait_batch(svo_ctx* c, svo_result* results) { return svo_wait_batch_detail(c, results, nullptr, nullptr, 0); }
+
+int svo_wait_batch_detail(svo_ctx* c, svo_result* results, double* residuals, int64_t* outliers, int32_t cap) {
     if (!c || !results) return SVO_ERR_ARG;
     if (c->pend_count == 0) return fail(c, SVO_ERR_STATE, "no batch in flight");
+    if ((residuals || outliers) && !c->detail) return fail(c, SVO_ERR_STATE, "svo_set_result_detail(ctx, 1) was not called before the submit");
     const int b = c->pend_head;
     CU(c, cudaEventSynchronize(c->ev_done[b]));
     int rc = SVO_OK;
+    const size_t gc = (size_t)c->PG.p.kp_cap;
     for (int i = 0; i < c->pend_n[b]; ++i) {
         const int s = c->r_slots[b][i];
         memcpy(&results[i], &c->r_res[b][s], sizeof(svo_result));
         const int st = c->r_state[b][s].status;
         results[i].status = st;
         if (st != 0) { results[i].valid = 0; rc = st; }
+        if (residuals) memcpy(residuals + (size_t)i * cap, c->r_resid[b] + s * gc, sizeof(double) * (size_t)std::min(std::max(results[i].n_residuals, 0), cap));
+        if (outliers) {
+            const int m = std::min(std::max(results[i].n_outliers, 0), cap);
+            for (int k = 0; k < m; ++k) outliers[(size_t)i * cap + k] = c->r_outl[b][s * gc + k];
+        }
     }
     c->pend_head = (c->pend_head + 1) % kDepth;
     --c->pend_count;
@@ -1174,20 +1246,49 @@ int svo_get_outliers(svo_ctx* c, int32_t slot, int64_t* out, int32_t cap) {
     return r.n_outliers;
 }
 
-int svo_get_track_candidates(svo_ctx* c, int32_t slot, int32_t* out_query, int32_t* out_trainL, int32_t* out_trainR,
-                             uint8_t* out_inlL, uint8_t* out_inlR, int32_t cap) {
+// survivors of stage 5's auxiliary non-maximal suppression (S5:465-474) over the flattened tracked pairs (S5:419-461),
+// as the first Gauss-Newton loop starts with them: what optimization.txt lists (S5:477-492)
+int svo_get_stage5_survivors(svo_ctx* c, int32_t slot, uint8_t* out, int32_t cap) {
     if (!c) return SVO_ERR_ARG;
     if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
     CU(c, cudaStreamSynchronize(c->stream));
+    const GnScratch& G = c->n_oct > 1 ? c->GG : c->G;
+    const size_t gc = (size_t)c->PG.p.kp_cap;
+    int T = 0;
+    CU(c, cudaMemcpy(&T, c->PG.n_tracked + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    T = std::max(0, std::min(T, (int)gc));
+    const int m = std::min(T, (int)cap);
+    if (m > 0 && out) CU(c, cudaMemcpy(out, G.mask0 + slot * gc, (size_t)m, cudaMemcpyDeviceToHost));
+    return T;
+}
+
+int svo_get_track_candidates(svo_ctx* c, int32_t slot, int32_t* out_query, int32_t* out_trainL, int32_t* out_trainR,
+                             uint8_t* out_inlL, uint8_t* out_inlR, int32_t cap) {
+    return svo_get_track_candidates_oct(c, slot, 0, out_query, out_trainL, out_trainR, out_inlL, out_inlR, nullptr, nullptr, cap);
+}
+
+int svo_get_track_candidates_oct(svo_ctx* c, int32_t slot, int32_t octave, int32_t* out_query, int32_t* out_trainL, int32_t* out_trainR,
+                                 uint8_t* out_inlL, uint8_t* out_inlR, float* out_distL, float* out_distR, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    const Pools* Pk = octave_pools(c, octave);
+    if (!Pk) return fail(c, SVO_ERR_ARG, "octave out of range");
+    CU(c, cudaStreamSynchronize(c->stream));
     int n = 0;
-    CU(c, cudaMemcpy(&n, c->P.n_tcand + slot, sizeof(int), cudaMemcpyDeviceToHost));
-    const size_t kc = c->P.p.kp_cap;
+    CU(c, cudaMemcpy(&n, Pk->n_tcand + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    const size_t kc = Pk->p.kp_cap;
     std::vector<int4> tmp(n);
     std::vector<uint8_t> il(n), ir(n);
+    std::vector<uint32_t> bl, br;
     if (n) {
-        CU(c, cudaMemcpy(tmp.data(), c->P.tcand + (size_t)slot * kc, n * sizeof(int4), cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(il.data(), c->P.inl + ((size_t)slot * 2 + 0) * kc, n, cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(ir.data(), c->P.inl + ((size_t)slot * 2 + 1) * kc, n, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(tmp.data(), Pk->tcand + (size_t)slot * kc, n * sizeof(int4), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(il.data(), Pk->inl + ((size_t)slot * 2 + 0) * kc, n, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(ir.data(), Pk->inl + ((size_t)slot * 2 + 1) * kc, n, cudaMemcpyDeviceToHost));
+        if ((out_distL || out_distR) && c->cfg.if_match_method == 0) {   // the BF distances of matL / matR (S4:141-142), by query index
+            bl.resize(kc); br.resize(kc);
+            CU(c, cudaMemcpy(bl.data(), Pk->tr_best + ((size_t)slot * 2 + 0) * kc, kc * 4, cudaMemcpyDeviceToHost));
+            CU(c, cudaMemcpy(br.data(), Pk->tr_best + ((size_t)slot * 2 + 1) * kc, kc * 4, cudaMemcpyDeviceToHost));
+        }
     }
     for (int i = 0; i < n && i < cap; ++i) {
         if (out_query) out_query[i] = tmp[i].x;
@@ -1195,6 +1296,8 @@ int svo_get_track_candidates(svo_ctx* c, int32_t slot, int32_t* out_query, int32
         if (out_trainR) out_trainR[i] = tmp[i].z;
         if (out_inlL) out_inlL[i] = il[i];
         if (out_inlR) out_inlR[i] = ir[i];
+        if (out_distL) out_distL[i] = bl.empty() ? 0.f : (float)(bl[tmp[i].x] >> 16);
+        if (out_distR) out_distR[i] = br.empty() ? 0.f : (float)(br[tmp[i].x] >> 16);
     }
     return n;
 }

@@ -239,7 +239,7 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
 
     // 3a. FAST pre-test on the tile plus a 1-px ring (needed by the 3x3 NMS): one work item = one staged word
     //     (4 pixels) of rows -1 .. TH; survivors are appended to s_list (order is irrelevant)
-    const int th = P.p.fast_th;
+    const int th = slot_fast_th(P.p, P.state[slot]);     // m_current_fast_th of this estimator (S2:510)
     {
         const unsigned t_hi = (unsigned)(257 + th) * 0x00010001u;
         const unsigned t_lo = ((unsigned)(255 - th) & 0xFFFFu) * 0x00010001u;

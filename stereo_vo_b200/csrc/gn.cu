@@ -462,6 +462,9 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
         }
     }
     __syncthreads();
+    // the survivors as stage 5 starts with them (what the reference lists in optimization.txt, S5:477-492); G.mask
+    // itself loses the outliers of the first loop later (S5:601-605)
+    for (int i = tid; i < T; i += GN_THREADS) G.mask0[base + i] = G.mask[base + i];
 
     // ---- initial pose (S5:500-507) ------------------------------------------------------------------
     if (tid == 0) {

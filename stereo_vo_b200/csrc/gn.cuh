@@ -9,6 +9,7 @@ struct GnScratch {            // per-slot scratch, [max_seqs][kp_cap] unless not
     float4* obs;              // current frame: left x, left y, right x, right y
     double* lmk;              // [..][3] triangulated landmarks
     uint8_t* mask;            // survivors
+    uint8_t* mask0;           // survivors of the aux NMS before the first loop removes outliers (optimization.txt, S5:477-492)
     double* residual;         // == Pools::residual
     int32_t* cur_idx;         // external path: tracked_pairs[i].second
     uint32_t* occ;            // [max_seqs][occ_words] occupancy grid of the aux NMS

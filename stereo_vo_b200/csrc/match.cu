@@ -150,7 +150,7 @@ hamming_pipeline_kernel(Pools P, int mode_base, int n_modes) {
     const int item = blockIdx.y / n_modes, mode = mode_base + blockIdx.y % n_modes;
     const HammingProblem h = pipeline_problem(P, mode, item);
     // distances above orb_th are dropped by lr_filter_kernel / track_filter_kernel: (orb_th + 1, index 0) stands for them
-    const uint32_t cut = (uint32_t)min(max(P.p.orb_th, 0) + 1, 0x7FFF);
+    const uint32_t cut = (uint32_t)min(max(slot_orb_th(P.p, P.state[P.slots[item]]), 0) + 1, 0x7FFF);
     hamming_body<true>(h, s_t, cut << 16);
 }
 
@@ -210,6 +210,7 @@ lr_filter_kernel(Pools P) {
     const int2* __restrict__ kpR = P.kp + fR * cap;
     const int tid = threadIdx.x;
     const int n_in = (nR > 0) ? nL : 0;   // BFMatcher returns no matches for an empty train set
+    const int orb_th = slot_orb_th(P.p, st);          // m_current_orb_th (S3:164)
 
     // P:254-267 (resetIds()): before stage 3 the previous frame's IDs are renumbered 0..N-1, the ID generator
     // restarts behind them and the previous frame becomes the key frame.  (The reference dereferences a null
@@ -251,7 +252,7 @@ lr_filter_kernel(Pools P) {
             // S3:162-165: float differences truncated to int (coordinates are integers here)
             const int diff = (int)((float)((unsigned)l.x >> 16) - (float)((unsigned)r.x >> 16));
             const int disp = (int)((float)(l.x & 0xFFFF) - (float)(r.x & 0xFFFF));
-            if ((double)abs(diff) > P.p.max_y_diff || (float)dist > (float)P.p.orb_th ||
+            if ((double)abs(diff) > P.p.max_y_diff || (float)dist > (float)orb_th ||
                 (double)disp < 1.0 || (double)disp > (double)P.p.W) keep = 0;
         }
         int total;
@@ -311,7 +312,7 @@ track_filter_kernel(Pools P) {
     uint8_t* state = reinterpret_cast<uint8_t*>(s_mem + 3 * cap);
     const uint32_t* __restrict__ bl = P.tr_best + ((size_t)slot * 2 + 0) * cap;
     const uint32_t* __restrict__ br = P.tr_best + ((size_t)slot * 2 + 1) * cap;
-    const uint32_t th = (uint32_t)P.p.orb_th;
+    const uint32_t th = (uint32_t)slot_orb_th(P.p, st);          // m_current_orb_th (S4:149)
     for (int k = tid; k < n_in; k += FT) {
         const uint32_t a = bl[k], b = br[k];
         s_ab[k] = (a << 16) | (b & 0xFFFFu);

@@ -26,6 +26,8 @@ struct SlotState {                  // mutable members of the estimator (libster
     int32_t status;                 // svo_status of the step (capacity overflow ...)
     uint32_t it_counter;            // m_it_counter
     int32_t  reset_ids;             // m_reset: renumber the previous frame's match IDs at the next step (P:254-267)
+    int32_t fast_th1, orb_th1;      // m_current_fast_th + 1 / m_current_orb_th + 1 once a setter ran (libstereo-odometry.h:529-541);
+                                    // 0 = still the configured value (Params::fast_th / orb_th, H:661-662)
     long long last_match_id;        // m_last_match_ID
     long long last_kf_max_id;       // m_last_kf_max_id
     double last_pose[6];            // m_last_computed_pose
@@ -69,6 +71,10 @@ struct Result {
     int32_t n_residuals;
     int32_t status;
 };
+
+// m_current_fast_th / m_current_orb_th of a slot: read at every call (S2:510, S3:164, S4:149)
+__host__ __device__ inline int slot_fast_th(const Params& p, const SlotState& s) { return s.fast_th1 ? s.fast_th1 - 1 : p.fast_th; }
+__host__ __device__ inline int slot_orb_th(const Params& p, const SlotState& s) { return s.orb_th1 ? s.orb_th1 - 1 : p.orb_th; }
 
 // All device pointers of a context, passed by value to kernels.
 struct Pools {

@@ -155,28 +155,58 @@ void CStereoOdometryEstimator::loadParamsFromConfigFileName(const std::string& f
 // ---- match IDs / key frames (H:675-726) ---------------------------------------------------------------------
 void CStereoOdometryEstimator::setThisFrameAsKF() {
     if (!m_ctx) throw std::runtime_error("[VO Error -- setThisFrameAsKF] Current frame does not exist");
-    if (svo_set_this_frame_as_kf(m_ctx, 0) != SVO_OK) throw_last(m_ctx, "setThisFrameAsKF");
+    if (svo_set_this_frame_as_kf(m_ctx, m_slot) != SVO_OK) throw_last(m_ctx, "setThisFrameAsKF");
 }
 void CStereoOdometryEstimator::resetIds() {
     if (!m_ctx) throw std::runtime_error("[Visual Odometry Error] no frame has been processed yet.");
-    if (svo_reset_ids(m_ctx, 0) != SVO_OK) throw_last(m_ctx, "resetIds");
+    if (svo_reset_ids(m_ctx, m_slot) != SVO_OK) throw_last(m_ctx, "resetIds");
 }
 void CStereoOdometryEstimator::setIds(const std::vector<size_t>& ids) {
     if (!m_ctx) throw std::runtime_error("[Visual Odometry Error] no frame has been processed yet.");
     std::vector<int64_t> v(ids.begin(), ids.end());
-    if (svo_set_ids(m_ctx, 0, v.data(), (int32_t)v.size()) != SVO_OK) throw_last(m_ctx, "setIds");
+    if (svo_set_ids(m_ctx, m_slot, v.data(), (int32_t)v.size()) != SVO_OK) throw_last(m_ctx, "setIds");
 }
 void CStereoOdometryEstimator::setMaxMatchID(size_t id) {
     if (!m_ctx) throw std::runtime_error("[Visual Odometry Error] no frame has been processed yet.");
-    if (svo_set_max_match_id(m_ctx, 0, (int64_t)id) != SVO_OK) throw_last(m_ctx, "setMaxMatchID");
+    if (svo_set_max_match_id(m_ctx, m_slot, (int64_t)id) != SVO_OK) throw_last(m_ctx, "setMaxMatchID");
 }
 std::vector<size_t> CStereoOdometryEstimator::getCopyCurrentIDs(size_t octave) {
     if (!m_ctx || octave >= (size_t)params_rectify.nOctaves) return std::vector<size_t>();
-    const int cap = 2 * (int)params_detect.orb_nfeats + 16;
-    std::vector<int64_t> ids(cap);
-    const int n = svo_get_match_ids_oct(m_ctx, 0, (int32_t)octave, 0, ids.data(), cap);
+    const int cap = keypoint_capacity((int)octave);
+    std::vector<int64_t> ids((size_t)cap);
+    const int n = svo_get_match_ids_oct(m_ctx, m_slot, (int32_t)octave, 0, ids.data(), cap);
     if (n < 0) throw_last(m_ctx, "svo_get_match_ids_oct");
-    return std::vector<size_t>(ids.begin(), ids.begin() + n);
+    return std::vector<size_t>(ids.begin(), ids.begin() + std::min(n, cap));
+}
+
+// capacity of the per-octave keypoint / match arrays of the context: 2*orb_nfeats-derived quota with the NMS, the corner
+// capacity (max_corners) without it (svo_get_octave_info)
+int CStereoOdometryEstimator::keypoint_capacity(int octave) const {
+    int32_t info[4] = {0, 0, 0, 0};
+    if (!m_ctx || svo_get_octave_info(m_ctx, octave, info) < 1) return 0;
+    return info[3];
+}
+
+// S3:425-445
+std::vector<size_t> CStereoOdometryEstimator::getMatchesRowIndex(size_t octave) {
+    if (!m_ctx || octave >= (size_t)params_rectify.nOctaves) return std::vector<size_t>();
+    const int cap = keypoint_capacity((int)octave);
+    int32_t info[4];
+    svo_get_octave_info(m_ctx, (int)octave, info);
+    std::vector<svo_keypoint> kl((size_t)cap);
+    std::vector<svo_dmatch> m((size_t)cap);
+    const int nl = svo_get_keypoints_oct(m_ctx, m_slot, (int)octave, 0, 0, kl.data(), cap);
+    const int nm = svo_get_matches_oct(m_ctx, m_slot, (int)octave, 0, m.data(), cap);
+    if (nl < 0 || nm < 0) throw_last(m_ctx, "getMatchesRowIndex");
+    const size_t imgH = (size_t)info[1], nFeats = (size_t)std::min(nm, cap);
+    std::vector<size_t> idx(imgH + 1);
+    size_t k = 0;
+    for (size_t y = 0; y < imgH; ++y) {
+        idx[y] = k;
+        while (k < nFeats && kl[(size_t)m[k].queryIdx].y <= (float)(int)y) ++k;
+    }
+    idx[imgH] = (size_t)std::min(nl, cap);          // "[nRows] = total # of feats": the left FEATURE count (S3:443)
+    return idx;
 }
 
 void CStereoOdometryEstimator::setRectifyMaps(const std::vector<int16_t>& xyL, const std::vector<uint16_t>& aL,
@@ -190,19 +220,16 @@ void CStereoOdometryEstimator::setRectifyMaps(const std::vector<int16_t>& xyL, c
 CStereoOdometryEstimator::CStereoOdometryEstimator() {}
 
 CStereoOdometryEstimator::~CStereoOdometryEstimator() {
-    if (m_ctx) svo_destroy(m_ctx);
+    if (m_ctx && !m_pool) svo_destroy(m_ctx);
+    if (m_aux_ctx) svo_destroy(m_aux_ctx);
 }
 
 void CStereoOdometryEstimator::throw_last(svo_ctx* c, const char* what) {
     throw std::runtime_error(std::string("[Visual Odometry Error] ") + what + ": " + svo_last_error(c));
 }
 
-// (Re)create the device context when the image size or any parameter changed.  Parameters are plain
-// members in the reference too, read at every call; here they are baked into the context, so a change
-// costs one re-creation (sequence state is lost, as after constructing a new estimator).
-void CStereoOdometryEstimator::ensure_context(int width, int height) {
-    if (m_ctx && !m_dirty && width == m_w && height == m_h) return;
-    // process_new_image_pair.cpp:54-76: only the FAST+ORB / DescBF / DescBF path exists here
+// process_new_image_pair.cpp:54-76: the methods this build has
+void CStereoOdometryEstimator::check_methods() const {
     if (params_detect.detect_method != TDetectParams::dmFAST_ORB)
         throw std::runtime_error("[Visual Odometry Error] Detect method not correct (this build has dmFAST_ORB only).");
     if (params_lr_match.match_method != TLeftRightMatchParams::smDescBF && params_lr_match.match_method != TLeftRightMatchParams::smDescRbR)
@@ -213,13 +240,15 @@ void CStereoOdometryEstimator::ensure_context(int width, int height) {
         throw std::runtime_error("[Visual Odometry Error] nOctaves must be within [1, 4].");
     if (params_detect.nmsMethod != TDetectParams::nmsmStandard)
         throw std::runtime_error("[Visual Odometry Error] Invalid non-maximal-suppression method (nmsmStandard only).");
-    if (m_ctx) { svo_destroy(m_ctx); m_ctx = nullptr; }
+}
+
+svo_config CStereoOdometryEstimator::make_config(int width, int height, int max_seqs) const {
     svo_config cfg;
     svo_default_config(&cfg);
     cfg.device = m_device;
     cfg.width = width;
     cfg.height = height;
-    cfg.max_seqs = 1;
+    cfg.max_seqs = max_seqs;
     cfg.orb_nfeats = (int32_t)params_detect.orb_nfeats;
     cfg.fast_threshold = m_current_fast_th;
     cfg.non_maximal_suppression = params_detect.non_maximal_suppression ? 1 : 0;
@@ -245,6 +274,27 @@ void CStereoOdometryEstimator::ensure_context(int width, int height) {
     cfg.orb_max_distance = params_lr_match.orb_max_distance;
     cfg.n_octaves = params_rectify.nOctaves;      // stage1_rectify.cpp:80 (dmORB, which forces one octave, is not built)
     cfg.pyr_mode = params_rectify.pyr_mode;
+    return cfg;
+}
+
+// m_current_fast_th / m_current_orb_th to the device (H:529-541): two ints of this estimator's slot, nothing else
+void CStereoOdometryEstimator::push_thresholds() {
+    if (!m_ctx || (m_dirty && !m_pool)) return;     // no context yet (or about to be rebuilt): svo_create takes the values
+    if (svo_set_thresholds(m_ctx, m_slot, m_current_fast_th, m_current_orb_th) != SVO_OK) throw_last(m_ctx, "svo_set_thresholds");
+}
+
+// (Re)create the device context when the image size or a params_* member changed (applyParams / loadParamsFromConfigFile).
+// The params_* members are baked into the context (they size its arrays); the two dynamic thresholds are not, see
+// push_thresholds().  A pooled estimator never rebuilds: its context belongs to the pool.
+void CStereoOdometryEstimator::ensure_context(int width, int height) {
+    if (m_pool) {
+        if (width != m_w || height != m_h) throw std::runtime_error("[Visual Odometry Error] image size differs from the pool's.");
+        return;
+    }
+    if (m_ctx && !m_dirty && width == m_w && height == m_h) return;
+    check_methods();
+    if (m_ctx) { svo_destroy(m_ctx); m_ctx = nullptr; }
+    const svo_config cfg = make_config(width, height, 1);
     if (svo_create(&cfg, &m_ctx) != SVO_OK) throw_last(nullptr, "svo_create");
     m_w = width;
     m_h = height;
@@ -252,6 +302,23 @@ void CStereoOdometryEstimator::ensure_context(int width, int height) {
     m_in_channels = 1;          // a fresh context takes gray, rectified images
     m_maps_on_device = false;
     m_rectify_active = false;
+}
+
+// getChangeInPose / getProjectedCoords take the image size from the camera model (common.cpp:402-403).  They run on
+// this estimator's own slot when that size is the running one (or nothing runs yet), and on a private scratch context
+// otherwise -- a live sequence is never torn down by them.
+svo_ctx* CStereoOdometryEstimator::context_for_size(int width, int height, int* slot) {
+    if (m_ctx && !(m_dirty && !m_pool) && width == m_w && height == m_h) { *slot = m_slot; return m_ctx; }
+    if (!m_ctx && !m_pool) { ensure_context(width, height); *slot = m_slot; return m_ctx; }
+    if (!m_aux_ctx || m_aux_w != width || m_aux_h != height) {
+        check_methods();
+        if (m_aux_ctx) { svo_destroy(m_aux_ctx); m_aux_ctx = nullptr; }
+        const svo_config cfg = make_config(width, height, 1);
+        if (svo_create(&cfg, &m_aux_ctx) != SVO_OK) throw_last(nullptr, "svo_create");
+        m_aux_w = width; m_aux_h = height;
+    }
+    *slot = 0;
+    return m_aux_ctx;
 }
 
 static svo_camera to_cam(const TStereoCamera& s) {
@@ -262,7 +329,8 @@ static svo_camera to_cam(const TStereoCamera& s) {
     return c;
 }
 
-static void fill_result(svo_ctx* ctx, const svo_result& r, CStereoOdometryEstimator::TStereoOdometryResult& out, bool pose_valid) {
+static void fill_result(svo_ctx* ctx, int slot, const svo_result& r, const double* residuals, const int64_t* outliers,
+                        CStereoOdometryEstimator::TStereoOdometryResult& out, bool pose_valid) {
     out.num_it = r.num_it;
     out.num_it_final = r.num_it_final;
     out.valid = r.valid != 0;
@@ -273,11 +341,16 @@ static void fill_result(svo_ctx* ctx, const svo_result& r, CStereoOdometryEstima
         std::memcpy(out.outPose.m, r.out_pose, sizeof(r.out_pose));
         std::memcpy(out.outPose.ypr, r.out_pose_ypr, sizeof(r.out_pose_ypr));
     }
-    std::vector<int64_t> tmp((size_t)std::max(r.n_outliers, 0));
-    if (r.n_outliers > 0) svo_get_outliers(ctx, 0, tmp.data(), r.n_outliers);
-    out.outliers.assign(tmp.begin(), tmp.end());
-    out.out_residual.resize((size_t)std::max(r.n_residuals, 0));
-    if (r.n_residuals > 0) svo_get_residuals(ctx, 0, out.out_residual.data(), r.n_residuals);
+    const int no = std::max(r.n_outliers, 0), nr = std::max(r.n_residuals, 0);
+    if (outliers) out.outliers.assign(outliers, outliers + no);
+    else {
+        std::vector<int64_t> tmp((size_t)no);
+        if (no > 0) svo_get_outliers(ctx, slot, tmp.data(), no);
+        out.outliers.assign(tmp.begin(), tmp.end());
+    }
+    out.out_residual.resize((size_t)nr);
+    if (residuals) std::copy(residuals, residuals + nr, out.out_residual.begin());
+    else if (nr > 0) svo_get_residuals(ctx, slot, out.out_residual.data(), nr);
 }
 
 // ---- params_general.vo_save_files: the per-frame text dumps of the reference ---------------------------------
@@ -285,7 +358,10 @@ static void fill_result(svo_ctx* ctx, const svo_result& r, CStereoOdometryEstima
 // (left/right_feats_%04d.txt, left/right_desc_o%02d_%04d.yml in cv::FileStorage's YAML layout), :278-287
 // (matches_%04d.txt), stage4_match_consecutive.cpp:81-82,308-328 (inter_frame_matching_%04d.txt) and
 // stage5_optimization.cpp:703-713 (out_residual_%04d.txt and out_residual_final_%04d.txt: the reference writes the
-// final residual vector to both).  Not written: l-l / r-r_%04d.txt (S4:176-232) and optimization.txt (S5:477-490).
+// final residual vector to both), stage4_match_consecutive.cpp:173-234 (l-l_%04d.txt / r-r_%04d.txt: the greedy-filtered
+// left-left / right-right lists with their Hamming distances; the reference re-opens the same name for every octave, so
+// the LAST octave's list is what stays on disk) and stage5_optimization.cpp:477-492 (optimization.txt in the working
+// directory: the eight coordinates of every survivor of stage 5's auxiliary non-maximal suppression).
 static FILE* open_dump(const std::string& dir, const char* fmt, int a, int b = -1) {
     char name[128];
     if (b < 0) std::snprintf(name, sizeof(name), fmt, a);
@@ -299,20 +375,21 @@ void CStereoOdometryEstimator::save_files(const TStereoOdometryResult& result, b
     const std::string& dir = params_general.vo_out_dir;
     const int it = (int)m_it_counter;
     const int n_oct = (int)result.detected_feats.size();
-    const int cap = 2 * (int)params_detect.orb_nfeats + 16;
-    struct Oct { std::vector<KeyPoint> kp[2][2]; std::vector<DMatch> m[2]; };      // [which][side], [which]
+    struct Oct { std::vector<KeyPoint> kp[2][2]; std::vector<DMatch> m[2]; std::vector<int64_t> tp; };   // [which][side], [which]
     std::vector<Oct> oc((size_t)n_oct);
     auto kps = [&](int octave, int which, int side, std::vector<KeyPoint>& out) {
+        const int cap = keypoint_capacity(octave);
         out.resize((size_t)cap);
-        const int n = svo_get_keypoints_oct(m_ctx, 0, octave, which, side, reinterpret_cast<svo_keypoint*>(out.data()), cap);
+        const int n = svo_get_keypoints_oct(m_ctx, m_slot, octave, which, side, reinterpret_cast<svo_keypoint*>(out.data()), cap);
         if (n < 0) throw_last(m_ctx, "svo_get_keypoints_oct");
-        out.resize((size_t)n);
+        out.resize((size_t)std::min(n, cap));
     };
     auto matches = [&](int octave, int which, std::vector<DMatch>& out) {
+        const int cap = keypoint_capacity(octave);
         out.resize((size_t)cap);
-        const int n = svo_get_matches_oct(m_ctx, 0, octave, which, reinterpret_cast<svo_dmatch*>(out.data()), cap);
+        const int n = svo_get_matches_oct(m_ctx, m_slot, octave, which, reinterpret_cast<svo_dmatch*>(out.data()), cap);
         if (n < 0) throw_last(m_ctx, "svo_get_matches_oct");
-        out.resize((size_t)n);
+        out.resize((size_t)std::min(n, cap));
     };
     for (int k = 0; k < n_oct; ++k) {
         for (int which = 0; which < (have_prev ? 2 : 1); ++which) {
@@ -327,7 +404,7 @@ void CStereoOdometryEstimator::save_files(const TStereoOdometryResult& result, b
             const std::vector<KeyPoint>& v = oc[k].kp[0][side];
             for (const KeyPoint& p : v) std::fprintf(f, "%d %.2f %.2f %.8f\n", k, p.pt.x, p.pt.y, p.response);
             std::vector<uint8_t> desc(v.size() * 32);
-            if (!v.empty() && svo_get_descriptors_oct(m_ctx, 0, k, 0, side, desc.data(), (int32_t)v.size()) < 0) throw_last(m_ctx, "svo_get_descriptors_oct");
+            if (!v.empty() && svo_get_descriptors_oct(m_ctx, m_slot, k, 0, side, desc.data(), (int32_t)v.size()) < 0) throw_last(m_ctx, "svo_get_descriptors_oct");
             FILE* y = open_dump(dir, side ? "right_desc_o%02d_%04d.yml" : "left_desc_o%02d_%04d.yml", k, it);
             std::fprintf(y, "%%YAML:1.0\n---\n%s: !!opencv-matrix\n   rows: %d\n   cols: 32\n   dt: u\n   data: [ ", side ? "rightDescMat" : "leftDescMat", (int)v.size());
             for (size_t i = 0; i < desc.size(); ++i) std::fprintf(y, "%s%d", i ? (i % 16 ? ", " : ",\n       ") : "", (int)desc[i]);
@@ -343,9 +420,12 @@ void CStereoOdometryEstimator::save_files(const TStereoOdometryResult& result, b
     if (!have_prev) return;
     f = open_dump(dir, "inter_frame_matching_%04d.txt", it);
     for (int k = 0; k < n_oct; ++k) {
-        std::vector<int64_t> tp((size_t)2 * cap);
-        const int n = svo_get_tracked_pairs_oct(m_ctx, 0, k, tp.data(), cap);
+        const int cap = keypoint_capacity(k);
+        std::vector<int64_t>& tp = oc[k].tp;
+        tp.resize((size_t)2 * cap);
+        const int n = std::min(svo_get_tracked_pairs_oct(m_ctx, m_slot, k, tp.data(), cap), cap);
         if (n < 0) throw_last(m_ctx, "svo_get_tracked_pairs_oct");
+        tp.resize((size_t)2 * n);
         for (int i = 0; i < n; ++i) {
             const DMatch& pm = oc[k].m[1][(size_t)tp[2 * i]];
             const DMatch& cm = oc[k].m[0][(size_t)tp[2 * i + 1]];
@@ -356,7 +436,51 @@ void CStereoOdometryEstimator::save_files(const TStereoOdometryResult& result, b
         }
     }
     std::fclose(f);
+    // l-l / r-r (S4:173-234, brute-force tracker only): "prev.x prev.y cur.x cur.y distance" per surviving matL / matR entry
+    if (params_if_match.ifm_method == TInterFrameMatchingParams::ifmDescBF) {
+        const int k = n_oct - 1;                             // the reference overwrites the file octave after octave
+        const int cap = keypoint_capacity(k);
+        std::vector<int32_t> q((size_t)cap), tl((size_t)cap), tr((size_t)cap);
+        std::vector<float> dl((size_t)cap), dr((size_t)cap);
+        const int n = std::min(svo_get_track_candidates_oct(m_ctx, m_slot, k, q.data(), tl.data(), tr.data(), nullptr, nullptr, dl.data(), dr.data(), cap), cap);
+        if (n < 0) throw_last(m_ctx, "svo_get_track_candidates_oct");
+        for (int side = 0; side < 2; ++side) {
+            FILE* fl = open_dump(dir, side ? "r-r_%04d.txt" : "l-l_%04d.txt", it);
+            for (int i = 0; i < n; ++i) {
+                const DMatch& pm = oc[k].m[1][(size_t)q[i]];
+                const DMatch& cm = oc[k].m[0][(size_t)(side ? tr[i] : tl[i])];
+                const KeyPoint& a = oc[k].kp[1][side][(size_t)(side ? pm.trainIdx : pm.queryIdx)];
+                const KeyPoint& b = oc[k].kp[0][side][(size_t)(side ? cm.trainIdx : cm.queryIdx)];
+                std::fprintf(fl, "%.2f %.2f %.2f %.2f %.2f\n", a.pt.x, a.pt.y, b.pt.x, b.pt.y, side ? dr[i] : dl[i]);
+            }
+            std::fclose(fl);
+        }
+    }
     if (result.error_code == voecBadTracking) return;       // stage 5 did not run (P:332)
+    {   // optimization.txt (S5:477-492): in the working directory, overwritten at every call
+        size_t total = 0;
+        for (int k = 0; k < n_oct; ++k) total += oc[k].tp.size() / 2;
+        std::vector<uint8_t> surv(total + 1);
+        const int T = svo_get_stage5_survivors(m_ctx, m_slot, surv.data(), (int32_t)total);
+        if (T < 0) throw_last(m_ctx, "svo_get_stage5_survivors");
+        FILE* fo = std::fopen("optimization.txt", "wt");
+        if (fo) {
+            size_t i = 0;
+            for (int k = 0; k < n_oct; ++k) {
+                const float sc = n_oct > 1 ? (float)(1 << k) : 1.f;          // S5:422-456
+                for (size_t j = 0; j + 1 < oc[k].tp.size(); j += 2, ++i) {
+                    if (i >= (size_t)T || !surv[i]) continue;
+                    const DMatch& pm = oc[k].m[1][(size_t)oc[k].tp[j]];
+                    const DMatch& cm = oc[k].m[0][(size_t)oc[k].tp[j + 1]];
+                    const KeyPoint &pl = oc[k].kp[1][0][pm.queryIdx], &pr = oc[k].kp[1][1][pm.trainIdx];
+                    const KeyPoint &cl = oc[k].kp[0][0][cm.queryIdx], &cr = oc[k].kp[0][1][cm.trainIdx];
+                    std::fprintf(fo, "%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f\n", pl.pt.x * sc, pl.pt.y * sc, pr.pt.x * sc, pr.pt.y * sc,
+                                 cl.pt.x * sc, cl.pt.y * sc, cr.pt.x * sc, cr.pt.y * sc);
+                }
+            }
+            std::fclose(fo);
+        }
+    }
     for (const char* fmt : {"out_residual_%04d.txt", "out_residual_final_%04d.txt"}) {
         FILE* fr = open_dump(dir, fmt, it);
         for (double v : result.out_residual) std::fprintf(fr, "%.3f\n", v);
@@ -364,7 +488,7 @@ void CStereoOdometryEstimator::save_files(const TStereoOdometryResult& result, b
     }
 }
 
-void CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& request_data, TStereoOdometryResult& result) {
+static void check_request(const CStereoOdometryEstimator::TStereoOdometryRequest& request_data) {
     if (!request_data.stereo_imgs)   // process_new_image_pair.cpp:81
         throw std::runtime_error("Pointer 'request_data.stereo_imgs' must be set to stereo observation data!");
     if (request_data.use_precomputed_data)
@@ -374,13 +498,16 @@ void CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& reque
     if (!L.data || !R.data || L.width != R.width || L.height != R.height || L.stride != R.stride || L.channels != R.channels ||
         (L.channels != 1 && L.channels != 3))
         throw std::runtime_error("[Visual Odometry Error] left/right images must be 8-bit gray or BGR with equal geometry.");
-    ensure_context(L.width, L.height);
-    // stage 1 (stage1_rectify.cpp:37-93) runs on the device: tell the context what the images are
+}
+
+// stage 1 (stage1_rectify.cpp:37-93) runs on the device: tell the context what the images are
+void CStereoOdometryEstimator::apply_stage1_format(const CObservationStereoImages& obs) {
+    const CImage& L = obs.imageLeft;
     if (L.channels != m_in_channels) {
         if (svo_set_input_format(m_ctx, L.channels) != SVO_OK) throw_last(m_ctx, "svo_set_input_format");
         m_in_channels = L.channels;
     }
-    const bool rectify = !request_data.stereo_imgs->areImagesRectified();
+    const bool rectify = !obs.areImagesRectified();
     if (rectify && m_map_a[0].size() != (size_t)L.width * L.height)
         throw std::runtime_error("[Visual Odometry Error] unrectified images need setRectifyMaps() with maps of the image size.");
     if (rectify != m_rectify_active || (rectify && !m_maps_on_device)) {
@@ -390,13 +517,13 @@ void CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& reque
         m_rectify_active = rectify;
         m_maps_on_device = rectify;
     }
-    result.error_code = voecNone;                         // P:50
-    const svo_camera cam = to_cam(request_data.stereo_cam);
-    svo_result r;
-    const int rc = svo_process_pair(m_ctx, L.data, R.data, L.stride, &cam, request_data.repeat ? 1 : 0, &r);
-    if (rc != SVO_OK) throw_last(m_ctx, "svo_process_pair");
+}
+
+// everything processNewImagePair does after the stages: result struct (P:171-176, 274-276 + stage 5's fields), dumps, counter
+void CStereoOdometryEstimator::finish_step(const svo_result& r, const double* residuals, const int64_t* outliers, bool repeat,
+                                           TStereoOdometryResult& result) {
     int32_t stats[4 * 4];
-    const int n_oct = svo_get_octave_stats(m_ctx, 0, stats, 4);
+    const int n_oct = svo_get_octave_stats(m_ctx, m_slot, stats, 4);
     if (n_oct < 1) throw_last(m_ctx, "svo_get_octave_stats");
     result.detected_feats.resize((size_t)n_oct);                                                           // P:171-176
     result.stereo_matches.resize((size_t)n_oct);                                                           // P:274-276
@@ -404,14 +531,122 @@ void CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& reque
         result.detected_feats[k] = std::make_pair((size_t)stats[4 * k], (size_t)stats[4 * k + 1]);
         result.stereo_matches[k] = (size_t)stats[4 * k + 2];
     }
-    fill_result(m_ctx, r, result, r.n_residuals > 0 && (r.valid || r.error_code == voecIncrFuncCostStg2 || r.error_code == voecIncrFuncCostStg1));
+    fill_result(m_ctx, m_slot, r, residuals, outliers, result,
+                r.n_residuals > 0 && (r.valid || r.error_code == voecIncrFuncCostStg2 || r.error_code == voecIncrFuncCostStg1));
     if (params_general.vo_save_files) {
         struct stat sb;                                     // P:46-47: the output directory is created on demand
         if (stat(params_general.vo_out_dir.c_str(), &sb) != 0 && mkdir(params_general.vo_out_dir.c_str(), 0777) != 0)
             throw std::runtime_error("[Visual Odometry Error] cannot create '" + params_general.vo_out_dir + "'");
         save_files(result, r.error_code != voecFirstIteration);
     }
-    if (!request_data.repeat) ++m_it_counter;              // P:380-381
+    if (!repeat) ++m_it_counter;                            // P:380-381
+}
+
+void CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& request_data, TStereoOdometryResult& result) {
+    check_request(request_data);
+    const CImage& L = request_data.stereo_imgs->imageLeft;
+    const CImage& R = request_data.stereo_imgs->imageRight;
+    ensure_context(L.width, L.height);
+    apply_stage1_format(*request_data.stereo_imgs);
+    result.error_code = voecNone;                         // P:50
+    const svo_camera cam = to_cam(request_data.stereo_cam);
+    svo_result r;
+    const int32_t slot = m_slot;
+    const uint8_t rep = request_data.repeat ? 1 : 0;
+    const uint8_t* lp = L.data;
+    const uint8_t* rp = R.data;
+    const int rc = svo_process_batch(m_ctx, 1, &slot, &lp, &rp, L.stride, &cam, request_data.repeat ? &rep : nullptr, &r);
+    if (rc != SVO_OK) throw_last(m_ctx, "svo_process_batch");
+    finish_step(r, nullptr, nullptr, request_data.repeat, result);
+}
+
+// ---- CStereoOdometryPool -----------------------------------------------------------------------------------------
+CStereoOdometryPool::CStereoOdometryPool(const CStereoOdometryEstimator& params, int width, int height, size_t n_estimators, int device) {
+    if (n_estimators < 1) throw std::runtime_error("[Visual Odometry Error] a pool needs at least one estimator.");
+    params.check_methods();
+    svo_config cfg = params.make_config(width, height, (int)n_estimators);
+    cfg.device = device;
+    if (svo_create(&cfg, &m_ctx) != SVO_OK) CStereoOdometryEstimator::throw_last(nullptr, "svo_create");
+    if (svo_set_result_detail(m_ctx, 1) != SVO_OK) { svo_destroy(m_ctx); CStereoOdometryEstimator::throw_last(nullptr, "svo_set_result_detail"); }
+    m_w = width; m_h = height;
+    int32_t info[4];
+    const int n_oct = svo_get_octave_info(m_ctx, 0, info);
+    m_cap_total = 0;
+    for (int k = 0; k < n_oct; ++k) { svo_get_octave_info(m_ctx, k, info); m_cap_total += info[3]; }
+    m_est.reserve(n_estimators);
+    for (size_t k = 0; k < n_estimators; ++k) {
+        CStereoOdometryEstimator* e = new CStereoOdometryEstimator();
+        e->params_rectify = params.params_rectify; e->params_detect = params.params_detect; e->params_lr_match = params.params_lr_match;
+        e->params_if_match = params.params_if_match; e->params_least_squares = params.params_least_squares;
+        e->params_general = params.params_general;
+        e->m_current_fast_th = params.m_current_fast_th; e->m_current_orb_th = params.m_current_orb_th;
+        e->m_ctx = m_ctx; e->m_pool = this; e->m_slot = (int)k; e->m_w = width; e->m_h = height; e->m_device = device; e->m_dirty = false;
+        m_est.push_back(e);
+    }
+}
+
+CStereoOdometryPool::~CStereoOdometryPool() {
+    for (CStereoOdometryEstimator* e : m_est) delete e;
+    if (m_ctx) svo_destroy(m_ctx);
+}
+
+void CStereoOdometryPool::submit(const std::vector<size_t>& which, std::vector<Request>& requests) {
+    const size_t n = which.size();
+    if (n == 0 || n != requests.size()) throw std::runtime_error("[Visual Odometry Error] submit: one request per listed estimator.");
+    std::vector<int32_t> slots(n);
+    std::vector<const uint8_t*> L(n), R(n);
+    std::vector<svo_camera> cams(n);
+    Pending pd;
+    pd.which = which;
+    pd.repeat.resize(n);
+    bool any_repeat = false;
+    for (size_t i = 0; i < n; ++i) {
+        if (which[i] >= m_est.size()) throw std::runtime_error("[Visual Odometry Error] submit: estimator index out of range.");
+        check_request(requests[i]);
+        const CObservationStereoImages& o = *requests[i].stereo_imgs;
+        if (o.imageLeft.width != m_w || o.imageLeft.height != m_h || o.imageLeft.stride != requests[0].stereo_imgs->imageLeft.stride ||
+            o.imageLeft.channels != requests[0].stereo_imgs->imageLeft.channels || o.areImagesRectified() != requests[0].stereo_imgs->areImagesRectified())
+            throw std::runtime_error("[Visual Odometry Error] submit: all images of a batch share size, stride, format and rectification state.");
+        slots[i] = (int32_t)which[i];
+        L[i] = o.imageLeft.data; R[i] = o.imageRight.data;
+        cams[i] = to_cam(requests[i].stereo_cam);
+        pd.repeat[i] = requests[i].repeat ? 1 : 0;
+        any_repeat = any_repeat || requests[i].repeat;
+    }
+    m_est[which[0]]->apply_stage1_format(*requests[0].stereo_imgs);          // the stage-1 format is a property of the shared context
+    for (size_t i = 1; i < n; ++i) {
+        CStereoOdometryEstimator* e = m_est[which[i]];
+        e->m_in_channels = m_est[which[0]]->m_in_channels; e->m_rectify_active = m_est[which[0]]->m_rectify_active;
+        e->m_maps_on_device = m_est[which[0]]->m_maps_on_device;
+    }
+    const int rc = svo_submit_batch(m_ctx, (int32_t)n, slots.data(), L.data(), R.data(), requests[0].stereo_imgs->imageLeft.stride,
+                                    cams.data(), any_repeat ? pd.repeat.data() : nullptr);
+    if (rc != SVO_OK) CStereoOdometryEstimator::throw_last(m_ctx, "svo_submit_batch");
+    m_pending.push_back(pd);
+}
+
+void CStereoOdometryPool::wait(std::vector<Result>& results) {
+    if (m_pending.empty()) throw std::runtime_error("[Visual Odometry Error] wait: no batch in flight.");
+    const Pending pd = m_pending.front();
+    m_pending.erase(m_pending.begin());
+    const size_t n = pd.which.size();
+    m_res.resize(n);
+    m_resid.resize(n * (size_t)m_cap_total);
+    m_outl.resize(n * (size_t)m_cap_total);
+    const int rc = svo_wait_batch_detail(m_ctx, m_res.data(), m_resid.data(), m_outl.data(), m_cap_total);
+    if (rc != SVO_OK) CStereoOdometryEstimator::throw_last(m_ctx, "svo_wait_batch_detail");
+    results.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        results[i].error_code = voecNone;                  // P:50
+        m_est[pd.which[i]]->finish_step(m_res[i], m_resid.data() + i * (size_t)m_cap_total, m_outl.data() + i * (size_t)m_cap_total,
+                                        pd.repeat[i] != 0, results[i]);
+    }
+}
+
+void CStereoOdometryPool::processNewImagePairs(const std::vector<size_t>& which, std::vector<Request>& requests, std::vector<Result>& results) {
+    if (!m_pending.empty()) throw std::runtime_error("[Visual Odometry Error] processNewImagePairs: batches are still in flight.");
+    submit(which, requests);
+    wait(results);
 }
 
 bool CStereoOdometryEstimator::getChangeInPose(const vector_index_pairs_t& tracked_pairs, const std::vector<DMatch>& pre_matches,
@@ -423,14 +658,15 @@ bool CStereoOdometryEstimator::getChangeInPose(const vector_index_pairs_t& track
     const int w = stereo_camera.leftCamera.ncols ? (int)stereo_camera.leftCamera.ncols : m_w;
     const int h = stereo_camera.leftCamera.nrows ? (int)stereo_camera.leftCamera.nrows : m_h;
     if (w <= 0 || h <= 0) throw std::runtime_error("[Visual Odometry Error] getChangeInPose needs leftCamera.ncols/nrows.");
-    ensure_context(w, h);
+    int slot = 0;
+    svo_ctx* ctx = context_for_size(w, h, &slot);
     std::vector<int64_t> tp(2 * tracked_pairs.size());
     for (size_t i = 0; i < tracked_pairs.size(); ++i) { tp[2 * i] = (int64_t)tracked_pairs[i].first; tp[2 * i + 1] = (int64_t)tracked_pairs[i].second; }
     const svo_camera cam = to_cam(stereo_camera);
     svo_result r;
     const bool custom = params_least_squares.use_custom_initial_pose;
     const int rc = svo_get_change_in_pose(
-        m_ctx, 0, tp.data(), (int32_t)tracked_pairs.size(),
+        ctx, slot, tp.data(), (int32_t)tracked_pairs.size(),
         reinterpret_cast<const svo_dmatch*>(pre_matches.data()), (int32_t)pre_matches.size(),
         reinterpret_cast<const svo_dmatch*>(cur_matches.data()), (int32_t)cur_matches.size(),
         reinterpret_cast<const svo_keypoint*>(pre_left_feats.data()), (int32_t)pre_left_feats.size(),
@@ -438,8 +674,8 @@ bool CStereoOdometryEstimator::getChangeInPose(const vector_index_pairs_t& track
         reinterpret_cast<const svo_keypoint*>(cur_left_feats.data()), (int32_t)cur_left_feats.size(),
         reinterpret_cast<const svo_keypoint*>(cur_right_feats.data()), (int32_t)cur_right_feats.size(),
         &cam, custom ? 1 : 0, custom && ini_estimation.size() == 6 ? ini_estimation.data() : nullptr, &r);
-    if (rc < 0) throw_last(m_ctx, "svo_get_change_in_pose");
-    fill_result(m_ctx, r, result, r.n_residuals > 0);
+    if (rc < 0) throw_last(ctx, "svo_get_change_in_pose");
+    fill_result(ctx, slot, r, nullptr, nullptr, result, r.n_residuals > 0);
     return result.valid;
 }
 
@@ -452,7 +688,8 @@ void CStereoOdometryEstimator::getProjectedCoords(const std::vector<DMatch>& pre
         throw std::runtime_error("[Visual Odometry Error] getProjectedCoords: more tracking flags than matches.");
     const int w = stereo_camera.leftCamera.ncols ? (int)stereo_camera.leftCamera.ncols : (m_w ? m_w : 640);
     const int h = stereo_camera.leftCamera.nrows ? (int)stereo_camera.leftCamera.nrows : (m_h ? m_h : 480);
-    ensure_context(w, h);
+    int slot_unused = 0;
+    svo_ctx* ctx = context_for_size(w, h, &slot_unused);
     // C:459-464: auxPose = change_pose^-1, then its rotation-vector form [w1 w2 w3 t1 t2 t3]
     const double* M = change_pose.m;
     double Ri[9], ti[3];
@@ -477,11 +714,11 @@ void CStereoOdometryEstimator::getProjectedCoords(const std::vector<DMatch>& pre
     for (size_t m = 0; m < other_matches_tracked.size(); ++m) flags[m] = other_matches_tracked[m].first;
     const svo_camera cam = to_cam(stereo_camera);
     std::vector<float> out(4 * std::max<size_t>(1, pre_matches.size()));
-    const int n = svo_get_projected_coords(m_ctx, reinterpret_cast<const svo_dmatch*>(pre_matches.data()), (int32_t)pre_matches.size(),
+    const int n = svo_get_projected_coords(ctx, reinterpret_cast<const svo_dmatch*>(pre_matches.data()), (int32_t)pre_matches.size(),
                                            reinterpret_cast<const svo_keypoint*>(pre_left_feats.data()), (int32_t)pre_left_feats.size(),
                                            reinterpret_cast<const svo_keypoint*>(pre_right_feats.data()), (int32_t)pre_right_feats.size(),
                                            flags.data(), &cam, dp, out.data(), (int32_t)pre_matches.size());
-    if (n < 0) throw_last(m_ctx, "svo_get_projected_coords");
+    if (n < 0) throw_last(ctx, "svo_get_projected_coords");
     pro_pre_feats.resize((size_t)n);
     for (int i = 0; i < n; ++i) {
         pro_pre_feats[i].first = Point2f{out[4 * i], out[4 * i + 1]};
@@ -492,24 +729,25 @@ void CStereoOdometryEstimator::getProjectedCoords(const std::vector<DMatch>& pre
 void CStereoOdometryEstimator::getValues(std::vector<KeyPoint>& leftKP, std::vector<KeyPoint>& rightKP, Mat& leftDesc, Mat& rightDesc,
                                          std::vector<DMatch>& matches, std::vector<size_t>& matches_id) {
     if (!m_ctx) throw std::runtime_error("[Visual Odometry Error] no current frame.");
-    const int cap = 2 * (int)params_detect.orb_nfeats + 16;
+    const int cap = keypoint_capacity(0);               // octave 0 only, as in the reference (H:709)
     auto kps = [&](int side, std::vector<KeyPoint>& out, Mat& desc) {
-        out.resize(cap);
-        const int n = svo_get_keypoints(m_ctx, 0, 0, side, reinterpret_cast<svo_keypoint*>(out.data()), cap);
+        out.resize((size_t)cap);
+        int n = svo_get_keypoints(m_ctx, m_slot, 0, side, reinterpret_cast<svo_keypoint*>(out.data()), cap);
         if (n < 0) throw_last(m_ctx, "svo_get_keypoints");
-        out.resize(n);
+        n = std::min(n, cap);
+        out.resize((size_t)n);
         desc.rows = n; desc.cols = 32; desc.data.resize((size_t)n * 32);
-        if (n && svo_get_descriptors(m_ctx, 0, 0, side, desc.data.data(), n) < 0) throw_last(m_ctx, "svo_get_descriptors");
+        if (n && svo_get_descriptors(m_ctx, m_slot, 0, side, desc.data.data(), n) < 0) throw_last(m_ctx, "svo_get_descriptors");
     };
     kps(0, leftKP, leftDesc);
     kps(1, rightKP, rightDesc);
-    matches.resize(cap);
-    const int m = svo_get_matches(m_ctx, 0, 0, reinterpret_cast<svo_dmatch*>(matches.data()), cap);
+    matches.resize((size_t)cap);
+    const int m = svo_get_matches(m_ctx, m_slot, 0, reinterpret_cast<svo_dmatch*>(matches.data()), cap);
     if (m < 0) throw_last(m_ctx, "svo_get_matches");
-    matches.resize(m);
-    std::vector<int64_t> ids(cap);
-    const int ni = svo_get_match_ids(m_ctx, 0, 0, ids.data(), cap);
-    matches_id.assign(ids.begin(), ids.begin() + std::max(ni, 0));
+    matches.resize((size_t)std::min(m, cap));
+    std::vector<int64_t> ids((size_t)cap);
+    const int ni = svo_get_match_ids(m_ctx, m_slot, 0, ids.data(), cap);
+    matches_id.assign(ids.begin(), ids.begin() + std::min(std::max(ni, 0), cap));
 }
 
 }  // namespace rso

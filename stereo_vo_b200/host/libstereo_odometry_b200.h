@@ -108,6 +108,8 @@ typedef std::vector<std::pair<size_t, size_t> > vector_index_pairs_t;
 
 enum VOErrorCode { voecNone, voecBadCondNumber, voecIncrFuncCostStg1, voecIncrFuncCostStg2, voecFirstIteration, voecBadTracking };  // H:142
 
+class CStereoOdometryPool;
+
 class CStereoOdometryEstimator {
 public:
     struct TStereoOdometryRequest {                 // H:205-233
@@ -208,13 +210,18 @@ public:
     void getValues(std::vector<KeyPoint>& leftKP, std::vector<KeyPoint>& rightKP, Mat& leftDesc, Mat& rightDesc,
                    std::vector<DMatch>& matches, std::vector<size_t>& matches_id);
 
-    // H:529-541
+    // H:529-541.  As in the reference these only change two ints that the next call reads (S2:510, S3:164, S4:149):
+    // the previous frame, m_last_computed_pose, the error state and the match IDs stay (svo_set_thresholds).
     int getFASTThreshold() const { return m_current_fast_th; }
-    void setFASTThreshold(int v) { m_current_fast_th = std::min(params_detect.fast_max_th, std::max(params_detect.fast_min_th, v)); m_dirty = true; }
-    void resetFASTThreshold() { m_current_fast_th = params_detect.initial_FAST_threshold; m_dirty = true; }
+    void setFASTThreshold(int v) { m_current_fast_th = std::min(params_detect.fast_max_th, std::max(params_detect.fast_min_th, v)); push_thresholds(); }
+    void resetFASTThreshold() { m_current_fast_th = params_detect.initial_FAST_threshold; push_thresholds(); }
+    bool isFASTThMin() const { return m_current_fast_th == params_detect.fast_min_th; }
+    bool isFASTThMax() const { return m_current_fast_th == params_detect.fast_max_th; }
     int getORBThreshold() const { return m_current_orb_th; }
-    void setORBThreshold(int v) { m_current_orb_th = std::min(params_lr_match.orb_max_th, std::max(params_lr_match.orb_min_th, v)); m_dirty = true; }
-    void resetORBThreshold() { m_current_orb_th = (int)params_lr_match.orb_max_distance; m_dirty = true; }
+    void setORBThreshold(int v) { m_current_orb_th = std::min(params_lr_match.orb_max_th, std::max(params_lr_match.orb_min_th, v)); push_thresholds(); }
+    void resetORBThreshold() { m_current_orb_th = (int)params_lr_match.orb_max_distance; push_thresholds(); }
+    bool isORBThMin() const { return m_current_orb_th == params_lr_match.orb_min_th; }
+    bool isORBThMax() const { return m_current_orb_th == params_lr_match.orb_max_th; }
     void setVerbosityLevel(int level) { m_verbose_level = level; }
 
     /** Loads configuration from an INI file (H:554-663).  Sections must be (in this order) related to:
@@ -231,6 +238,11 @@ public:
     void setIds(const std::vector<size_t>& ids);
     void setMaxMatchID(size_t id);
     std::vector<size_t> getCopyCurrentIDs(size_t octave = 0);   // getRefCurrentIDs(octave) by value (state lives on the device)
+    /** lr_pairing_data[octave].matches_lr_row_index of the current frame (H:786-789, built at S3:425-445): for every image
+      * row the index of the first stereo match at or below it, plus the final entry = number of LEFT features (sic, S3:443).
+      * Rebuilt here from the frame's keypoints and matches ("kept in shim"); the device rebuilds it for its own
+      * windowed tracker. */
+    std::vector<size_t> getMatchesRowIndex(size_t octave = 0);
 
     /** Rectification maps for observations with rectified == false: what CStereoRectifyMap::setFromCamParams computes
       * on first use (S1:69-70) with cv::initUndistortRectifyMap(..., CV_16SC2): per side H*W (x, y) int16 pairs and
@@ -240,16 +252,31 @@ public:
 
     /** Apply the param structs (what loadParamsFromConfigFile does at H:554-663, minus the INI parsing):
       * re-reads every params_* member and resets both thresholds (H:661-662). */
-    void applyParams() { resetFASTThreshold(); resetORBThreshold(); m_dirty = true; }
+    void applyParams() { m_dirty = true; resetFASTThreshold(); resetORBThreshold(); }
 
     /** CUDA device ordinal used by this estimator (default 0); must be set before the first call. */
     void setDevice(int device) { m_device = device; m_dirty = true; }
 
+    /** true when this estimator is one slot of a CStereoOdometryPool (shared device context) */
+    bool pooled() const { return m_pool != nullptr; }
+
 private:
+    friend class CStereoOdometryPool;
     void ensure_context(int width, int height);
+    svo_ctx* context_for_size(int width, int height, int* slot);   // getChangeInPose / getProjectedCoords never tear a live sequence down
+    void push_thresholds();
+    svo_config make_config(int width, int height, int max_seqs) const;
+    void check_methods() const;
+    void apply_stage1_format(const CObservationStereoImages& obs);
+    void finish_step(const svo_result& r, const double* residuals, const int64_t* outliers, bool repeat, TStereoOdometryResult& result);
+    int keypoint_capacity(int octave) const;
     void save_files(const TStereoOdometryResult& result, bool have_prev);   // params_general.vo_save_files
     static void throw_last(svo_ctx* c, const char* what);
-    svo_ctx* m_ctx = nullptr;
+    svo_ctx* m_ctx = nullptr;           // owned unless m_pool is set
+    svo_ctx* m_aux_ctx = nullptr;       // scratch context for getChangeInPose / getProjectedCoords on another image size
+    int m_aux_w = 0, m_aux_h = 0;
+    CStereoOdometryPool* m_pool = nullptr;
+    int m_slot = 0;
     int m_w = 0, m_h = 0, m_device = 0;
     bool m_dirty = true;
     int m_current_fast_th = 20, m_current_orb_th = 60;   // ctor values, common.cpp:35-36
@@ -259,6 +286,49 @@ private:
     bool m_maps_on_device = false, m_rectify_active = false;
     std::vector<int16_t> m_map_xy[2];
     std::vector<uint16_t> m_map_a[2];
+};
+
+/** A pool of estimators on one GPU that share ONE device context.
+  *
+  * The reference's boundary is one processNewImagePair per estimator (libstereo-odometry.h:157-159).  A B200 advances
+  * hundreds of independent stereo sequences in the time of one, so the pool binds estimator k to slot k of a single
+  * svo_ctx: every estimator keeps its own previous frame, m_last_computed_pose, error state, thresholds and match IDs
+  * (all the members of H:733-754), and all of them are advanced together by one call:
+  *   - processNewImagePairs(): one processNewImagePair per listed estimator, synchronous;
+  *   - submit() / wait(): the same, asynchronous, up to three batches in flight (uploads of the next batches overlap the
+  *     kernels of the current one);
+  *   - pool[k].processNewImagePair(req, res) still works for one estimator at a time.
+  * Results are complete TStereoOdometryResult objects (outPose, outliers, out_residual, counters, per-octave statistics).
+  * All estimators of a pool share the parameter set the pool was created from (thresholds are per estimator). */
+class CStereoOdometryPool {
+public:
+    typedef CStereoOdometryEstimator::TStereoOdometryRequest Request;
+    typedef CStereoOdometryEstimator::TStereoOdometryResult Result;
+    /** params: an estimator whose params_* members (and current thresholds) configure the pool */
+    CStereoOdometryPool(const CStereoOdometryEstimator& params, int width, int height, size_t n_estimators, int device = 0);
+    ~CStereoOdometryPool();
+    CStereoOdometryPool(const CStereoOdometryPool&) = delete;
+    CStereoOdometryPool& operator=(const CStereoOdometryPool&) = delete;
+    size_t size() const { return m_est.size(); }
+    CStereoOdometryEstimator& operator[](size_t k) { return *m_est[k]; }
+
+    /** requests[i] goes to estimator which[i] (distinct); results[i] receives its TStereoOdometryResult */
+    void processNewImagePairs(const std::vector<size_t>& which, std::vector<Request>& requests, std::vector<Result>& results);
+    void submit(const std::vector<size_t>& which, std::vector<Request>& requests);
+    /** blocks until the OLDEST submitted batch is complete */
+    void wait(std::vector<Result>& results);
+    size_t in_flight() const { return m_pending.size(); }
+    svo_ctx* context() { return m_ctx; }
+
+private:
+    struct Pending { std::vector<size_t> which; std::vector<uint8_t> repeat; };
+    svo_ctx* m_ctx = nullptr;
+    int m_w = 0, m_h = 0, m_cap_total = 0;
+    std::vector<CStereoOdometryEstimator*> m_est;
+    std::vector<Pending> m_pending;
+    std::vector<svo_result> m_res;
+    std::vector<double> m_resid;
+    std::vector<int64_t> m_outl;
 };
 
 }  // namespace rso

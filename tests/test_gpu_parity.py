@@ -1174,3 +1174,176 @@ def test_concurrent_groups_give_identical_results(n):
             ctx.close()
     assert outs[1] == outs[3] == outs[4] == outs[8]
     assert sum(k[-1] for k in outs[1][0]) == n               # every slot produced a valid pose
+
+
+# ------------------------------------------------------------------------------------ bounded parity soak
+@pytest.mark.parametrize("cfg,n_seeds,n_frames,n_oct,seed0", [("c1", 16, 12, 1, 100), ("c2", 8, 8, 1, 100), ("c3", 6, 6, 1, 100),
+                                                              ("c2", 4, 6, 3, 100), ("c1", 4, 8, 2, 100), ("c3", 2, 4, 2, 100)])
+def test_parity_soak(cfg, n_seeds, n_frames, n_oct, seed0):
+    """40 seeded sequences (BASELINE configs 1-3, one to three octaves), every frame against the oracle with the REAL
+    OpenCV calls (cv2 FAST / ORB::compute / BFMatcher / findFundamentalMat + the glue pinned to the reference's compiled
+    text by tests/test_ref_cpu.py): keypoints, responses, descriptors, stereo matches, greedy lists, both RANSAC masks,
+    tracked pairs, inlier lists, iteration counts bit-exact; pose within north_star's 1e-4 rad / 1e-3 m (observed 1e-14).
+    The sequences include round 1's deviating inputs (c1 seeds 100 / 105, c3 seed 103: RANSAC masks differed from cv2
+    before the 7-point solver became OpenCV's own arithmetic)."""
+    pytest.importorskip("cv2")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import soak_parity
+    r = soak_parity.soak(n_seeds, n_frames, cfg, n_oct, "cv2_tolerant", seed0)
+    assert r["bad"] == 0 and r["dead"] == 0 and r["compared"] == n_seeds * n_frames, r
+    assert r["worst_rot"] < POSE_TOL_RAD * 1e-6 and r["worst_t"] < POSE_TOL_M * 1e-6, r
+
+
+# ------------------------------------------------------------------------------------ round 2: boundary
+def _write_sequences(path, seqs, cam, W, H):
+    import struct
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4i5d", W, H, len(seqs), len(seqs[0]), cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"]))
+        for frames in seqs:
+            for (L, R) in frames:
+                f.write(L.tobytes())
+                f.write(R.tobytes())
+
+
+def test_thresholds_change_between_frames_without_losing_the_sequence():
+    """svo_set_thresholds = setFASTThreshold / setORBThreshold (libstereo-odometry.h:529-541): two ints that the next call
+    reads (S2:510, S3:164, S4:149).  Changed at frame 3 (and again at 5) of a running sequence: every frame equals the
+    oracle with the same change, tracking continues across the change (no voecFirstIteration), other slots keep theirs."""
+    frames, cam = synth.make_sequence("c1", seed=40, n_frames=8)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=3)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend="port", ransac="off")
+    est_b = orc.OracleEstimator(orc.Params(orb_nfeats=100), backend="port", ransac="off")
+    ctx2 = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=3, fundmat_filter=0)
+    try:
+        for c in (ctx, ctx2):
+            assert c.thresholds(1) == (20, 40)
+        for i, (L, R) in enumerate(frames):
+            if i == 3:
+                ctx2.set_thresholds(12, 55, slot=1)
+                est.m_current_fast_th, est.m_current_orb_th = 12, 55
+                assert ctx2.thresholds(1) == (12, 55) and ctx2.thresholds(0) == (20, 40) and ctx2.thresholds(2) == (20, 40)
+            if i == 5:
+                ctx2.set_thresholds(fast_th=30, slot=1)              # the ORB threshold stays
+                est.m_current_fast_th = 30
+                assert ctx2.thresholds(1) == (30, 55)
+            o = est.process_new_image_pair(L, R, ocam(cam))
+            ob = est_b.process_new_image_pair(L, R, ocam(cam))
+            r = ctx2.process_batch([L, L, L], [R, R, R], [gcam(cam)] * 3)
+            for slot, oo in ((0, ob), (1, o), (2, ob)):
+                k = ctx2.keypoints(slot, 0, 0)
+                assert np.array_equal(xys(k), xys(oo["frame"].kpsL)), (i, slot)
+                assert np.array_equal(mtuple(ctx2.matches(slot, 0)), mtuple(oo["frame"].matches)), (i, slot)
+                assert (r[slot].error_code, bool(r[slot].valid)) == (oo["error_code"], oo["valid"]), (i, slot)
+                if i > 0:
+                    assert np.array_equal(ctx2.tracked_pairs(slot), oo["tracked"]), (i, slot)
+                    assert r[slot].tracked_feats_from_last_frame == len(oo["tracked"]) > 20, (i, slot)
+        # the keypoint sets really changed with the threshold
+        assert not np.array_equal(xys(ctx2.keypoints(1, 0, 0)), xys(ctx2.keypoints(0, 0, 0)))
+        with pytest.raises(RuntimeError):
+            ctx2.set_thresholds(fast_th=0)
+        ctx2.reset_slot(1)                                         # a fresh estimator: back to the configured values
+        assert ctx2.thresholds(1) == (20, 40)
+    finally:
+        ctx.close()
+        ctx2.close()
+
+
+def test_estimator_pool_equals_estimators_alone(tmp_path):
+    """rso::CStereoOdometryPool (many CStereoOdometryEstimator instances on one device context): every estimator's
+    complete TStereoOdometryResult -- pose, outliers, out_residual, counters, per-octave statistics -- equals what the same
+    sequence gives through a stand-alone estimator, synchronously and with three batches in flight, with the dynamic
+    thresholds changed at frame 3 (the sequence is not reset by the setters)."""
+    import subprocess
+    drv = os.path.join(ROOT, "stereo_vo_b200", "host", "svo_pool_driver")
+    assert os.path.exists(drv), "host shim not built (run __graft_entry__.build())"
+    seqs = []
+    for s in range(5):
+        frames, cam = synth.make_sequence("c1", seed=200 + s, n_frames=7)
+        seqs.append(frames)
+    path = tmp_path / "seqs.bin"
+    _write_sequences(path, seqs, cam, 320, 240)
+    p = subprocess.run([drv, "check", str(path), "100"], capture_output=True, text=True)
+    assert p.returncode == 0 and "failures=0" in p.stdout, p.stdout + p.stderr
+
+
+def test_result_detail_travels_with_the_batch():
+    """svo_set_result_detail + svo_wait_batch_detail: out_residual / outliers of every slot arrive with the batch and equal
+    the per-slot readers."""
+    import ctypes as C
+    frames, cam = synth.make_sequence("c1", seed=3, n_frames=3)
+    n = 4
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=n)
+    lib = capi.lib()
+    try:
+        assert lib.svo_set_result_detail(ctx._h, 1) == 0
+        cap = 200
+        for (L, R) in frames:
+            Ls = [np.ascontiguousarray(L) for _ in range(n)]
+            Rs = [np.ascontiguousarray(R) for _ in range(n)]
+            lp = (C.c_void_p * n)(*[a.ctypes.data for a in Ls])
+            rp = (C.c_void_p * n)(*[a.ctypes.data for a in Rs])
+            cams = (capi.Camera * n)(*[gcam(cam)] * n)
+            assert lib.svo_submit_batch(ctx._h, n, None, lp, rp, C.c_size_t(320), cams, None) == 0
+            res = (capi.Result * n)()
+            resid = np.zeros((n, cap))
+            outl = np.zeros((n, cap), np.int64)
+            assert lib.svo_wait_batch_detail(ctx._h, res, resid.ctypes.data_as(C.c_void_p), outl.ctypes.data_as(C.c_void_p), cap) == 0
+        for s in range(n):
+            assert res[s].valid and res[s].n_residuals > 50
+            assert np.array_equal(resid[s, :res[s].n_residuals], ctx.residuals(s))
+            assert np.array_equal(outl[s, :res[s].n_outliers], ctx.outliers(s))
+    finally:
+        ctx.close()
+
+
+def test_host_shim_dump_files_equal_the_references_own(tmp_path):
+    """params_general.vo_save_files: the shim's per-frame files against the files the REFERENCE's own writers produce
+    (oracle/_ref = the reference's compiled text; P:179-204,278-287, S4:80-82,173-234,308-327, S5:477-492,703-713):
+    left/right_feats, matches, inter_frame_matching, l-l, r-r and optimization.txt byte for byte, the residual files to
+    the printed precision."""
+    import struct
+    import subprocess
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref is not built")
+    demo = os.path.join(ROOT, "stereo_vo_b200", "host", "svo_demo")
+    frames, cam = synth.make_sequence("c1", seed=70, n_frames=4)
+    seq = tmp_path / "seq.bin"
+    with open(seq, "wb") as f:
+        f.write(struct.pack("<3i5d", 320, 240, len(frames), cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"]))
+        for (L, R) in frames:
+            f.write(L.tobytes())
+            f.write(R.tobytes())
+    for n_oct in (1, 2):
+        mine, theirs = tmp_path / f"mine{n_oct}", tmp_path / f"ref{n_oct}"
+        mine.mkdir()
+        text = open(os.path.join(ROOT, "stereo_vo_b200", "host", "hot_path.ini")).read()
+        text = text.replace("orb_nfeats = 500", "orb_nfeats = 100").replace("nOctaves = 1", f"nOctaves = {n_oct}")
+        text = text.replace("vo_save_files = false", f"vo_save_files = true\nvo_out_dir = {mine}")
+        ini = tmp_path / f"cfg{n_oct}.ini"
+        ini.write_text(text)
+        p = subprocess.run([demo, str(seq), str(tmp_path / "camera_pose.txt"), str(ini)], capture_output=True, text=True, cwd=mine)
+        assert p.returncode == 0, p.stdout + p.stderr
+        r = ref.RefEstimator(orc.Params(orb_nfeats=100, nOctaves=n_oct), backend="port", ransac="cv2_tolerant")
+        r.set_save_files(str(theirs))
+        try:
+            for (L, R) in frames:
+                r.process_new_image_pair(L, R, ocam(cam))
+        finally:
+            r.close()
+        last = len(frames) - 1
+        names = [f"{side}_feats_{i:04d}.txt" for side in ("left", "right") for i in range(len(frames))]
+        names += [f"matches_{i:04d}.txt" for i in range(len(frames))]
+        names += [f"{n}_{i:04d}.txt" for n in ("inter_frame_matching", "l-l", "r-r") for i in range(1, len(frames))]
+        names += ["optimization.txt"]
+        for name in names:
+            a, b = (mine / name).read_text(), (theirs / name).read_text()
+            assert a == b, f"{n_oct} octave(s): {name} differs"
+            assert len(a) > 0 or name.startswith(("l-l", "r-r")), name
+        for i in range(1, len(frames)):
+            for n in ("out_residual", "out_residual_final"):
+                a = np.loadtxt(mine / f"{n}_{i:04d}.txt")
+                b = np.loadtxt(theirs / f"{n}_{i:04d}.txt")
+                assert a.shape == b.shape
+                np.testing.assert_allclose(a, b, rtol=1e-9, atol=1.1e-3)
