@@ -173,12 +173,15 @@ int svo_wait_batch(svo_ctx* ctx, svo_result* results);
  * after svo_set_result_detail(ctx, 1) each submitted batch also copies out_residual and outliers of its slots to the
  * host (same stream, same event), and svo_wait_batch_detail hands them out: item i's vectors start at
  * residuals[i*cap] / outliers[i*cap], results[i].n_residuals / n_outliers entries are valid (at most cap each;
- * the context's capacity is 2*orb_nfeats per octave).  Either array may be NULL. */
+ * the context's capacity is 2*orb_nfeats per octave).  octave_stats: 16 values per item, 4 per octave as
+ * svo_get_octave_stats returns them (detected left, detected right, stereo matches, tracked pairs) -- the state of THAT
+ * batch, while svo_get_octave_stats reads the newest step.  Any of the three arrays may be NULL. */
+int svo_set_result_detail(svo_ctx* ctx, int32_t on);
+int svo_wait_batch_detail(svo_ctx* ctx, svo_result* results, double* residuals, int64_t* outliers, int32_t cap,
+                          int32_t* octave_stats);
 /* page-locked host memory for image buffers given to svo_submit_batch (cudaHostAlloc, portable); NULL on failure */
 void* svo_host_alloc(size_t bytes);
 void  svo_host_free(void* p);
-int svo_set_result_detail(svo_ctx* ctx, int32_t on);
-int svo_wait_batch_detail(svo_ctx* ctx, svo_result* results, double* residuals, int64_t* outliers, int32_t cap);
 
 /* Same, images already resident in device memory (HBM): d_left/d_right point to n images each,
  * image i at d_left + i*image_pitch_bytes, rows `stride_bytes` apart.  Results stay on the device

@@ -81,6 +81,7 @@ struct svo_ctx {
     int detail = 0;
     double* r_resid[kDepth] = {};      // [n_slots][PG.kp_cap]
     int32_t* r_outl[kDepth] = {};      // [n_slots][PG.kp_cap]
+    int32_t* r_stats[kDepth] = {};     // [n_slots][kMaxOctaves*4] per-octave counters (result.detected_feats / stereo_matches)
     cudaEvent_t ev_h2d[kDepth] = {}, ev_done[kDepth] = {};
     int pend_n[kDepth] = {}, pend_lo[kDepth] = {}, pend_hi[kDepth] = {};
     int pend_head = 0, pend_count = 0;
@@ -975,6 +976,7 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
         const size_t gc = (size_t)c->PG.p.kp_cap;
         CU(c, cudaMemcpyAsync(c->r_resid[b] + lo * gc, c->PG.residual + lo * gc, (size_t)(hi - lo + 1) * gc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(c->r_outl[b] + lo * gc, c->PG.outliers + lo * gc, (size_t)(hi - lo + 1) * gc * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(c->r_stats[b] + stat_idx(lo, 0, 0), c->P.oct_stats + stat_idx(lo, 0, 0), (size_t)(hi - lo + 1) * kMaxOctaves * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     }
     CU(c, cudaEventRecord(c->ev_done[b], c->stream));
     c->pend_n[b] = n; c->pend_lo[b] = lo; c->pend_hi[b] = hi;
@@ -990,6 +992,7 @@ int svo_set_result_detail(svo_ctx* c, int32_t on) {
         for (int b = 0; b < kDepth; ++b) {
             cudaError_t e = halloc(c, &c->r_resid[b], cnt);
             if (e == cudaSuccess) e = halloc(c, &c->r_outl[b], cnt);
+            if (e == cudaSuccess) e = halloc(c, &c->r_stats[b], (size_t)c->n_slots_alloc * kMaxOctaves * 4);
             if (e != cudaSuccess) return cuda_fail(c, e, "cudaMallocHost (result detail rings)");
         }
     }
@@ -997,12 +1000,12 @@ int svo_set_result_detail(svo_ctx* c, int32_t on) {
     return SVO_OK;
 }
 
-int svo_wait_batch(svo_ctx* c, svo_result* results) { return svo_wait_batch_detail(c, results, nullptr, nullptr, 0); }
+int svo_wait_batch(svo_ctx* c, svo_result* results) { return svo_wait_batch_detail(c, results, nullptr, nullptr, 0, nullptr); }
 
-int svo_wait_batch_detail(svo_ctx* c, svo_result* results, double* residuals, int64_t* outliers, int32_t cap) {
+int svo_wait_batch_detail(svo_ctx* c, svo_result* results, double* residuals, int64_t* outliers, int32_t cap, int32_t* octave_stats) {
     if (!c || !results) return SVO_ERR_ARG;
     if (c->pend_count == 0) return fail(c, SVO_ERR_STATE, "no batch in flight");
-    if ((residuals || outliers) && !c->detail) return fail(c, SVO_ERR_STATE, "svo_set_result_detail(ctx, 1) was not called before the submit");
+    if ((residuals || outliers || octave_stats) && !c->detail) return fail(c, SVO_ERR_STATE, "svo_set_result_detail(ctx, 1) was not called before the submit");
     const int b = c->pend_head;
     CU(c, cudaEventSynchronize(c->ev_done[b]));
     int rc = SVO_OK;
@@ -1018,6 +1021,7 @@ int svo_wait_batch_detail(svo_ctx* c, svo_result* results, double* residuals, in
             const int m = std::min(std::max(results[i].n_outliers, 0), cap);
             for (int k = 0; k < m; ++k) outliers[(size_t)i * cap + k] = c->r_outl[b][s * gc + k];
         }
+        if (octave_stats) memcpy(octave_stats + (size_t)i * kMaxOctaves * 4, c->r_stats[b] + stat_idx(s, 0, 0), kMaxOctaves * 4 * sizeof(int32_t));
     }
     c->pend_head = (c->pend_head + 1) % kDepth;
     --c->pend_count;

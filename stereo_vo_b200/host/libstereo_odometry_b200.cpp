@@ -520,10 +520,12 @@ void CStereoOdometryEstimator::apply_stage1_format(const CObservationStereoImage
 }
 
 // everything processNewImagePair does after the stages: result struct (P:171-176, 274-276 + stage 5's fields), dumps, counter
-void CStereoOdometryEstimator::finish_step(const svo_result& r, const double* residuals, const int64_t* outliers, bool repeat,
-                                           TStereoOdometryResult& result) {
+void CStereoOdometryEstimator::finish_step(const svo_result& r, const double* residuals, const int64_t* outliers, const int32_t* batch_stats,
+                                           bool repeat, TStereoOdometryResult& result) {
     int32_t stats[4 * 4];
-    const int n_oct = svo_get_octave_stats(m_ctx, m_slot, stats, 4);
+    int n_oct = params_rectify.nOctaves;
+    if (batch_stats) std::memcpy(stats, batch_stats, sizeof stats);      // the counters of THIS batch (later ones may be running)
+    else n_oct = svo_get_octave_stats(m_ctx, m_slot, stats, 4);
     if (n_oct < 1) throw_last(m_ctx, "svo_get_octave_stats");
     result.detected_feats.resize((size_t)n_oct);                                                           // P:171-176
     result.stereo_matches.resize((size_t)n_oct);                                                           // P:274-276
@@ -557,7 +559,7 @@ void CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& reque
     const uint8_t* rp = R.data;
     const int rc = svo_process_batch(m_ctx, 1, &slot, &lp, &rp, L.stride, &cam, request_data.repeat ? &rep : nullptr, &r);
     if (rc != SVO_OK) throw_last(m_ctx, "svo_process_batch");
-    finish_step(r, nullptr, nullptr, request_data.repeat, result);
+    finish_step(r, nullptr, nullptr, nullptr, request_data.repeat, result);
 }
 
 // ---- CStereoOdometryPool -----------------------------------------------------------------------------------------
@@ -633,13 +635,14 @@ void CStereoOdometryPool::wait(std::vector<Result>& results) {
     m_res.resize(n);
     m_resid.resize(n * (size_t)m_cap_total);
     m_outl.resize(n * (size_t)m_cap_total);
-    const int rc = svo_wait_batch_detail(m_ctx, m_res.data(), m_resid.data(), m_outl.data(), m_cap_total);
+    m_stats.resize(n * 16);
+    const int rc = svo_wait_batch_detail(m_ctx, m_res.data(), m_resid.data(), m_outl.data(), m_cap_total, m_stats.data());
     if (rc != SVO_OK) CStereoOdometryEstimator::throw_last(m_ctx, "svo_wait_batch_detail");
     results.resize(n);
     for (size_t i = 0; i < n; ++i) {
         results[i].error_code = voecNone;                  // P:50
         m_est[pd.which[i]]->finish_step(m_res[i], m_resid.data() + i * (size_t)m_cap_total, m_outl.data() + i * (size_t)m_cap_total,
-                                        pd.repeat[i] != 0, results[i]);
+                                        m_stats.data() + i * 16, pd.repeat[i] != 0, results[i]);
     }
 }
 

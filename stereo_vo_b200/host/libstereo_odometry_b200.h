@@ -268,7 +268,8 @@ private:
     svo_config make_config(int width, int height, int max_seqs) const;
     void check_methods() const;
     void apply_stage1_format(const CObservationStereoImages& obs);
-    void finish_step(const svo_result& r, const double* residuals, const int64_t* outliers, bool repeat, TStereoOdometryResult& result);
+    void finish_step(const svo_result& r, const double* residuals, const int64_t* outliers, const int32_t* batch_stats, bool repeat,
+                     TStereoOdometryResult& result);
     int keypoint_capacity(int octave) const;
     void save_files(const TStereoOdometryResult& result, bool have_prev);   // params_general.vo_save_files
     static void throw_last(svo_ctx* c, const char* what);
@@ -329,6 +330,7 @@ private:
     std::vector<svo_result> m_res;
     std::vector<double> m_resid;
     std::vector<int64_t> m_outl;
+    std::vector<int32_t> m_stats;
 };
 
 }  // namespace rso

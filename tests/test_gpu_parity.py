@@ -1288,11 +1288,14 @@ def test_result_detail_travels_with_the_batch():
             res = (capi.Result * n)()
             resid = np.zeros((n, cap))
             outl = np.zeros((n, cap), np.int64)
-            assert lib.svo_wait_batch_detail(ctx._h, res, resid.ctypes.data_as(C.c_void_p), outl.ctypes.data_as(C.c_void_p), cap) == 0
+            stats = np.zeros((n, 16), np.int32)
+            assert lib.svo_wait_batch_detail(ctx._h, res, resid.ctypes.data_as(C.c_void_p), outl.ctypes.data_as(C.c_void_p), cap,
+                                             stats.ctypes.data_as(C.c_void_p)) == 0
         for s in range(n):
             assert res[s].valid and res[s].n_residuals > 50
             assert np.array_equal(resid[s, :res[s].n_residuals], ctx.residuals(s))
             assert np.array_equal(outl[s, :res[s].n_outliers], ctx.outliers(s))
+            assert np.array_equal(stats[s, :4], ctx.octave_stats(s)[0])
     finally:
         ctx.close()
 
