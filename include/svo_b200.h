@@ -138,7 +138,7 @@ void svo_default_config(svo_config* cfg);                       /* ctor defaults
 int  svo_create(const svo_config* cfg, svo_ctx** out);          /* CStereoOdometryEstimator(), common.cpp:28-50 */
 void svo_destroy(svo_ctx* ctx);                                 /* ~CStereoOdometryEstimator(), common.cpp:52-61 */
 const char* svo_last_error(const svo_ctx* ctx);                 /* ctx may be NULL: last creation error */
-int  svo_reset_slot(svo_ctx* ctx, int32_t slot);                /* fresh estimator state for one slot */
+int  svo_reset_slot(svo_ctx* ctx, int32_t slot);                /* fresh estimator state for one slot (-1: every slot) */
 
 /* setFASTThreshold / setORBThreshold / resetFASTThreshold / resetORBThreshold (libstereo-odometry.h:529-541):
  * m_current_fast_th and m_current_orb_th of one slot (slot = -1: every slot), read at every following call
@@ -228,6 +228,9 @@ int svo_get_pyramid_plane(svo_ctx* ctx, int32_t item, int32_t octave, int32_t si
  * and the two RANSAC inlier masks (stage4_match_consecutive.cpp:145-160, 202, 237) */
 int svo_get_track_candidates(svo_ctx* ctx, int32_t slot, int32_t* out_query, int32_t* out_trainL,
                              int32_t* out_trainR, uint8_t* out_inlL, uint8_t* out_inlR, int32_t cap);
+/* statistics of the two cv::findFundamentalMat calls of the slot's last step, octave 0 (stage4_match_consecutive.cpp:202,237):
+ * out6 = {points, inliers, iterations executed} for the left-left and then the right-right problem */
+int svo_get_ransac_stats(svo_ctx* ctx, int32_t slot, int32_t* out6);
 /* survivors of stage 5's auxiliary non-maximal suppression (stage5_optimization.cpp:465-474) over the flattened tracked
  * pairs of all octaves (:419-461), as the first Gauss-Newton loop starts with them: the rows the reference writes to
  * optimization.txt (:477-492).  Returns the number of tracked pairs. */

@@ -54,7 +54,7 @@ _FFM = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double
 _PYR = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int)
 
 _lib = None
-_state = dict(backend="cv2", ransac="cv2", keep=None, raised=0)
+_state = dict(backend="cv2", ransac="cv2", keep=None, raised=0, last_fast=None)
 
 
 def _arr(ptr, dtype, n):
@@ -69,12 +69,32 @@ def _image(ptr, w, h, stride):
     return np.ascontiguousarray(a)
 
 
+def _fast_kps_to_array(cvk):
+    """cv2.KeyPoint list of FastFeatureDetector -> structured array without a Python loop per field: FAST reports size 7,
+    angle -1, octave 0, class_id -1 for every corner (checked on the first one)"""
+    import cv2
+    n = len(cvk)
+    out = np.zeros(n, KP)
+    if n == 0:
+        return out
+    k0 = cvk[0]
+    if (k0.size, k0.angle, k0.octave, k0.class_id) != (7.0, -1.0, 0, -1):
+        return orc.cv2_kps_to_array(cvk)
+    pts = cv2.KeyPoint_convert(cvk)
+    out["x"], out["y"] = pts[:, 0], pts[:, 1]
+    out["response"] = np.fromiter((k.response for k in cvk), np.float32, n)
+    out["size"], out["angle"], out["class_id"] = 7.0, -1.0, -1
+    return out
+
+
 def _cb_fast(img, w, h, stride, th, out, cap):
     try:
         im = _image(img, w, h, stride)
         if _state["backend"] == "cv2":
             import cv2
-            kps = orc.cv2_kps_to_array(cv2.FastFeatureDetector_create(int(th)).detect(im))
+            cvk = cv2.FastFeatureDetector_create(int(th)).detect(im)
+            kps = _fast_kps_to_array(cvk)
+            _state["last_fast"] = (cvk, kps)            # stage2_detect.cpp:511-512 hands the same list to ORB::compute next
         else:
             kps = orc.fast9(im, th)
         n = len(kps)
@@ -91,10 +111,14 @@ def _cb_orb_compute(img, w, h, stride, kps_io, n_in, desc_out):
         kin = _arr(kps_io, KP, n_in).copy()
         if _state["backend"] == "cv2":
             import cv2
-            cvk = [cv2.KeyPoint(float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]),
-                                int(k["octave"]), int(k["class_id"])) for k in kin]
+            last = _state.get("last_fast")
+            if last is not None and len(last[1]) == n_in and np.array_equal(last[1], kin):
+                cvk = last[0]                            # the very list FAST returned: no need to rebuild 10 k Python objects
+            else:
+                cvk = [cv2.KeyPoint(float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]),
+                                    int(k["octave"]), int(k["class_id"])) for k in kin]
             cvk, desc = cv2.ORB_create().compute(im, cvk)
-            kps = orc.cv2_kps_to_array(cvk)
+            kps = _fast_kps_to_array(cvk)
             desc = np.zeros((0, 32), np.uint8) if desc is None else desc
         else:
             kps, desc = orc.orb_compute(im, kin)
@@ -310,7 +334,9 @@ class RefEstimator:
         return out
 
     # -- processNewImagePair -------------------------------------------------------------------------------
-    def process_new_image_pair(self, imgL, imgR, cam, repeat=False):
+    def process_new_image_pair(self, imgL, imgR, cam, repeat=False, light=False):
+        """light=True: only the TStereoOdometryResult fields (what a caller of the class gets back); the default also reads
+        the frame data, the per-octave counters and the tracked pairs for the parity tests"""
         self._enter()
         imgL = np.ascontiguousarray(imgL, np.uint8)
         imgR = np.ascontiguousarray(imgR, np.uint8)
@@ -321,6 +347,10 @@ class RefEstimator:
         if rc != 0:
             raise RuntimeError("the reference threw: " + self.L.svo_ref_last_error().decode(errors="replace"))
         out = self._result(r)
+        out["outliers"] = self._get(self.L.svo_ref_get_outliers, np.int64)
+        out["out_residual"] = self._get(self.L.svo_ref_get_residuals, np.float64)
+        if light:
+            return out
         n_oct = self.L.svo_ref_n_octaves(self.h, 0)
         out["frames"] = [self.frame(0, k) for k in range(n_oct)]
         out["frame"] = out["frames"][0]
@@ -328,8 +358,6 @@ class RefEstimator:
         self.L.svo_ref_get_counts(self.h, _vp(cnt), n_oct)
         out["detected_feats"] = [(int(cnt[3 * k]), int(cnt[3 * k + 1])) for k in range(n_oct)]
         out["stereo_matches"] = [int(cnt[3 * k + 2]) for k in range(n_oct)]
-        out["outliers"] = self._get(self.L.svo_ref_get_outliers, np.int64)
-        out["out_residual"] = self._get(self.L.svo_ref_get_residuals, np.float64)
         out["tracked"] = [self.tracked(k) for k in range(n_oct)]
         return out
 

@@ -30,7 +30,7 @@ EXPORTS = [
     "svo_get_keypoints", "svo_get_descriptors", "svo_get_matches", "svo_get_match_ids", "svo_get_tracked_pairs",
     "svo_get_residuals", "svo_get_outliers", "svo_get_track_candidates", "svo_get_plane",
     "svo_detect", "svo_match_hamming", "svo_match_hamming_device", "svo_match_lr", "svo_get_change_in_pose",
-    "svo_fundmat_ransac", "svo_fundmat_7point", "svo_set_thresholds", "svo_get_thresholds", "svo_host_alloc", "svo_host_free", "svo_set_result_detail", "svo_wait_batch_detail", "svo_get_track_candidates_oct", "svo_get_stage5_survivors", "svo_abi_version", "svo_kernel_launches", "svo_stream",
+    "svo_fundmat_ransac", "svo_fundmat_7point", "svo_set_thresholds", "svo_get_thresholds", "svo_host_alloc", "svo_host_free", "svo_set_result_detail", "svo_wait_batch_detail", "svo_get_track_candidates_oct", "svo_get_stage5_survivors", "svo_get_ransac_stats", "svo_abi_version", "svo_kernel_launches", "svo_stream",
     "svo_enable_stage_timing", "svo_get_stage_times", "svo_measure_pipe_peaks", "svo_set_concurrency",
     "svo_set_input_format", "svo_set_rectify_maps", "svo_prepare_rectify", "svo_prepare_rectify_device",
     "svo_get_projected_coords", "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
@@ -224,6 +224,9 @@ class Context:
     def reset_slot(self, slot):
         self._check(lib().svo_reset_slot(self._h, slot))
 
+    def reset_all(self):
+        self._check(lib().svo_reset_slot(self._h, -1))
+
     # ---- readers (octave = index into the image pyramid, params_rectify.nOctaves) ------------------
     def _octave_info(self, octave):
         out = (C.c_int32 * 4)()
@@ -377,6 +380,12 @@ class Context:
         nm = np.zeros(max(n, 1), np.int32)
         self._check(lib().svo_fundmat_7point(self._h, _vp(p1), _vp(p2), n, _vp(F), _vp(nm)))
         return nm[:n].copy(), F[:n].reshape(n, 3, 3, 3).copy()
+
+    def ransac_stats(self, slot=0):
+        """{points, inliers, iterations} of the left-left and right-right findFundamentalMat calls of the last step"""
+        out = np.zeros(6, np.int32)
+        self._check(lib().svo_get_ransac_stats(self._h, int(slot), _vp(out)))
+        return out.reshape(2, 3)
 
     # ---- introspection --------------------------------------------------------------------------------
     def kernel_launches(self):

@@ -79,6 +79,7 @@ struct svo_ctx {
     SlotState* r_state[kDepth] = {};
     // svo_set_result_detail(1): the variable-length members of TStereoOdometryResult travel with every batch
     int detail = 0;
+    bool batch_copy_ok = true;         // cudaMemcpyBatchAsync accepted by this driver (scattered image uploads)
     double* r_resid[kDepth] = {};      // [n_slots][PG.kp_cap]
     int32_t* r_outl[kDepth] = {};      // [n_slots][PG.kp_cap]
     int32_t* r_stats[kDepth] = {};     // [n_slots][kMaxOctaves*4] per-octave counters (result.detected_feats / stereo_matches)
@@ -186,7 +187,9 @@ __global__ void upload_meta_kernel(int32_t* __restrict__ d_slots, Camera* __rest
     if (h_repeat) d_repeat[i] = h_repeat[i];
 }
 
-__global__ void reset_slot_kernel(Pools P, int slot) {
+__global__ void reset_slot_kernel(Pools P, int slot_lo, int slot_hi) {
+    const int slot = slot_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot > slot_hi) return;
     SlotState s;
     memset(&s, 0, sizeof(s));
     P.state[slot] = s;
@@ -663,8 +666,9 @@ void svo_destroy(svo_ctx* c) {
 
 int svo_reset_slot(svo_ctx* c, int32_t slot) {
     if (!c) return SVO_ERR_ARG;
-    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "slot index out of range");
-    reset_slot_kernel<<<1, 1, 0, c->stream>>>(c->P, slot);
+    if (slot != -1 && !valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "slot index out of range (-1 = every slot)");
+    const int lo = slot < 0 ? 0 : slot, hi = slot < 0 ? c->cfg.max_seqs - 1 : slot;
+    reset_slot_kernel<<<(hi - lo + 128) / 128, 128, 0, c->stream>>>(c->P, lo, hi);
     CU(c, cudaGetLastError());
     return SVO_OK;
 }
@@ -944,6 +948,26 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
     if (contig && stride == up_pitch) {
         CU(c, cudaMemcpyAsync(upL, left[0], up_plane * n, cudaMemcpyHostToDevice, c->copy_stream));
         CU(c, cudaMemcpyAsync(upR, right[0], up_plane * n, cudaMemcpyHostToDevice, c->copy_stream));
+    } else if (stride == up_pitch) {
+        // separately allocated images with the plane's own row pitch (one buffer per camera image, the usual caller): one
+        // batched copy call for the 2n planes; per-image copies if the driver refuses the batch
+        std::vector<void*> dsts(2 * (size_t)n), srcs(2 * (size_t)n);
+        std::vector<size_t> sizes(2 * (size_t)n, up_plane);
+        for (int i = 0; i < n; ++i) {
+            dsts[2 * i] = upL + i * up_plane; srcs[2 * i] = const_cast<uint8_t*>(left[i]);
+            dsts[2 * i + 1] = upR + i * up_plane; srcs[2 * i + 1] = const_cast<uint8_t*>(right[i]);
+        }
+        cudaError_t eb = cudaErrorNotSupported;
+        if (c->batch_copy_ok) {
+            cudaMemcpyAttributes attr;
+            memset(&attr, 0, sizeof attr);
+            attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;     // the sources stay valid until the matching wait
+            size_t attr_idx = 0, fail_idx = 0;
+            eb = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &attr, &attr_idx, 1, &fail_idx, c->copy_stream);
+            if (eb != cudaSuccess) { cudaGetLastError(); c->batch_copy_ok = false; }
+        }
+        if (eb != cudaSuccess)
+            for (size_t k = 0; k < dsts.size(); ++k) CU(c, cudaMemcpyAsync(dsts[k], srcs[k], up_plane, cudaMemcpyHostToDevice, c->copy_stream));
     } else {
         for (int i = 0; i < n; ++i) {
             CU(c, cudaMemcpy2DAsync(upL + i * up_plane, up_pitch, left[i], stride, row_bytes, H, cudaMemcpyHostToDevice, c->copy_stream));
@@ -1248,6 +1272,19 @@ int svo_get_outliers(svo_ctx* c, int32_t slot, int64_t* out, int32_t cap) {
     if (r.n_outliers) CU(c, cudaMemcpy(tmp.data(), c->PG.outliers + (size_t)slot * c->PG.p.kp_cap, r.n_outliers * 4, cudaMemcpyDeviceToHost));
     for (int i = 0; i < r.n_outliers && i < cap; ++i) out[i] = tmp[i];
     return r.n_outliers;
+}
+
+// statistics of the two findFundamentalMat calls of the slot's last step (octave 0): points, inliers, iterations executed
+int svo_get_ransac_stats(svo_ctx* c, int32_t slot, int32_t* out6) {
+    if (!c || !out6) return SVO_ERR_ARG;
+    if (!valid_slot(c, slot)) return fail(c, SVO_ERR_ARG, "bad slot");
+    CU(c, cudaStreamSynchronize(c->stream));
+    int32_t a[2], b[2], d[2];
+    CU(c, cudaMemcpy(a, c->RS.n_pts + (size_t)slot * 2, 8, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(b, c->RS.n_inl + (size_t)slot * 2, 8, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(d, c->RS.n_iter + (size_t)slot * 2, 8, cudaMemcpyDeviceToHost));
+    out6[0] = a[0]; out6[1] = b[0]; out6[2] = d[0]; out6[3] = a[1]; out6[4] = b[1]; out6[5] = d[1];
+    return SVO_OK;
 }
 
 // survivors of stage 5's auxiliary non-maximal suppression (S5:465-474) over the flattened tracked pairs (S5:419-461),

@@ -203,12 +203,12 @@ fundmat_kernel(RansacScratch R) {
     const float2* __restrict__ g2 = R.p2 + prob * R.kp_cap;
 
     if (n < 7) {                       // findFundamentalMat returns an empty Mat and no mask
-        if (tid == 0) R.n_inl[prob] = 0;
+        if (tid == 0) { R.n_inl[prob] = 0; R.n_iter[prob] = 0; }
         return;
     }
     if (n == 7) {                      // mask.setTo(1)
         if (tid < 7) mask[tid] = 1;
-        if (tid == 0) R.n_inl[prob] = 7;
+        if (tid == 0) { R.n_inl[prob] = 7; R.n_iter[prob] = 0; }
         return;
     }
     for (int i = tid; i < n; i += RS_THREADS) {
@@ -324,6 +324,7 @@ fundmat_kernel(RansacScratch R) {
         int tot = 0;
         for (int w = 0; w < RS_WARPS; ++w) tot += sh.wsum[w];
         R.n_inl[prob] = tot;
+        R.n_iter[prob] = min(sh.iter_base, sh.niters);
     }
 }
 
@@ -339,7 +340,11 @@ cudaError_t alloc_ransac(RansacScratch& R, int n_slots, int kp_cap, std::vector<
     e = cudaMalloc(&p, (size_t)n_slots * 2 * sizeof(int32_t));
     if (e != cudaSuccess) return e;
     allocs.push_back(p); R.n_pts = (int32_t*)p;
-    return cudaMemset(R.n_pts, 0, (size_t)n_slots * 2 * sizeof(int32_t));
+    if ((e = cudaMemset(R.n_pts, 0, (size_t)n_slots * 2 * sizeof(int32_t))) != cudaSuccess) return e;
+    e = cudaMalloc(&p, (size_t)n_slots * 2 * sizeof(int32_t));
+    if (e != cudaSuccess) return e;
+    allocs.push_back(p); R.n_iter = (int32_t*)p;
+    return cudaMemset(R.n_iter, 0, (size_t)n_slots * 2 * sizeof(int32_t));
 }
 
 static int ransac_smem(int kp_cap) { return 2 * kp_cap * (int)sizeof(Pt2f); }

@@ -9,6 +9,7 @@ struct RansacScratch {
     float2* p1;        // [n_slots*2][kp_cap] points of the previous frame (left-left, right-right problems)
     float2* p2;        // [n_slots*2][kp_cap] points of the current frame
     int32_t* n_pts;    // [n_slots*2]
+    int32_t* n_iter;   // [n_slots*2] RANSAC / LMedS iterations OpenCV's loop executes for this problem (statistics)
     int kp_cap;
     int32_t* slots;    // == Pools::slots (batch item -> slot)
     uint8_t* inl;      // == Pools::inl    [n_slots*2][kp_cap] output masks

@@ -108,3 +108,22 @@ def make_sequence(config="c2", seed=0, n_frames=4, dx=0.05, dyaw_deg=0.2):
         t = -R @ cw
         frames.append((sc.render(R, t, False), sc.render(R, t, True)))
     return frames, sc.camera()
+
+
+def make_sequence_two_motions(config="c2", seed=0, n_frames=4, frac=0.38):
+    """A sequence with an independently moving part: the right `frac` of every image (left and right camera alike) shows the
+    same scene under a second rigid motion.  Features inside it are detected, stereo-matched and tracked like any other, but
+    they contradict the dominant motion: about `frac` of the tracks are outliers for the two F-matrix RANSAC filters and for
+    the robust Gauss-Newton, so the adaptive RANSAC loop has to run many iterations instead of stopping after the first
+    model (the plain sequences are ~99 % inliers)."""
+    a, cam = make_sequence(config, seed=seed, n_frames=n_frames)
+    b, _ = make_sequence(config, seed=seed, n_frames=n_frames, dx=-0.04, dyaw_deg=-0.35)
+    W = a[0][0].shape[1]
+    x0 = int(round(W * (1.0 - frac)))
+    out = []
+    for (La, Ra), (Lb, Rb) in zip(a, b):
+        L, R = La.copy(), Ra.copy()
+        L[:, x0:] = Lb[:, x0:]
+        R[:, x0:] = Rb[:, x0:]
+        out.append((L, R))
+    return out, cam
