@@ -28,7 +28,7 @@ struct RsShared {
     int nmodels[RS_BATCH];
     int good[RS_BATCH][3];
     float median[RS_BATCH][3];
-    int iter_base, niters, maxGood, stop, have_model;
+    int iter_base, niters, maxGood, stop, have_model, n_scored;
     int wsum[RS_WARPS];
 };
 
@@ -222,6 +222,7 @@ fundmat_kernel(RansacScratch R) {
         sh.maxGood = 0;
         sh.stop = 0;
         sh.have_model = 0;
+        sh.n_scored = 0;
         sh.minMedian = DBL_MAX;
         if (lmeds) { const int it = ransac_update_num_iters(kFmConfidence, 0.45, kFmModelPoints, kFmMaxIters); sh.niters = it > 3 ? it : 3; }
         else sh.niters = kFmMaxIters;
@@ -257,6 +258,7 @@ fundmat_kernel(RansacScratch R) {
                 break;
             }
             const int nm = sh.nmodels[w];
+            if (tid == 0) ++sh.n_scored;                       // an iteration OpenCV's loop executes
             for (int i = 0; i < nm; ++i) {
                 const double* F = sh.F[w] + 9 * i;
                 if (!lmeds) {
@@ -324,7 +326,7 @@ fundmat_kernel(RansacScratch R) {
         int tot = 0;
         for (int w = 0; w < RS_WARPS; ++w) tot += sh.wsum[w];
         R.n_inl[prob] = tot;
-        R.n_iter[prob] = min(sh.iter_base, sh.niters);
+        R.n_iter[prob] = sh.n_scored;
     }
 }
 

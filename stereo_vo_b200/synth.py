@@ -95,7 +95,7 @@ def yaw_rot(a):
     return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
 
 
-def make_sequence(config="c2", seed=0, n_frames=4, dx=0.05, dyaw_deg=0.2):
+def make_sequence(config="c2", seed=0, n_frames=4, dx=0.05, dyaw_deg=0.2, dy=0.0):
     """Returns (frames, cam) with frames = list of (left, right) uint8 images."""
     cfg = CONFIGS[config]
     sc = Scene(seed, cfg["W"], cfg["H"], cfg["fx"], cfg["baseline"])
@@ -103,7 +103,7 @@ def make_sequence(config="c2", seed=0, n_frames=4, dx=0.05, dyaw_deg=0.2):
     for f in range(n_frames):
         # camera moves by +dx along x and yaws by dyaw per frame: world->camera is the inverse
         Rwc = yaw_rot(np.deg2rad(dyaw_deg) * f)          # camera orientation in world
-        cw = np.array([dx * f, 0.0, 0.0])                # camera centre in world
+        cw = np.array([dx * f, dy * f, 0.0])             # camera centre in world
         R = Rwc.T
         t = -R @ cw
         frames.append((sc.render(R, t, False), sc.render(R, t, True)))
@@ -117,7 +117,8 @@ def make_sequence_two_motions(config="c2", seed=0, n_frames=4, frac=0.38):
     the robust Gauss-Newton, so the adaptive RANSAC loop has to run many iterations instead of stopping after the first
     model (the plain sequences are ~99 % inliers)."""
     a, cam = make_sequence(config, seed=seed, n_frames=n_frames)
-    b, _ = make_sequence(config, seed=seed, n_frames=n_frames, dx=-0.04, dyaw_deg=-0.35)
+    # the second motion goes DOWN as well: its tracks are off the epipolar lines of the (horizontal) dominant motion
+    b, _ = make_sequence(config, seed=seed, n_frames=n_frames, dx=-0.02, dyaw_deg=-0.1, dy=0.05)
     W = a[0][0].shape[1]
     x0 = int(round(W * (1.0 - frac)))
     out = []
