@@ -30,6 +30,9 @@ struct RsShared {
     float median[RS_BATCH][3];
     int iter_base, niters, maxGood, stop, have_model, n_scored;
     int wsum[RS_WARPS];
+    CvRng rng_after[RS_BATCH];     // speculative sampling: the RNG state behind every sample of the round
+    int idx[RS_BATCH][7];
+    int collinear[RS_BATCH];
 };
 
 // S4:181-232: point sets of the left-left and right-right problems from the greedy-filtered lists
@@ -231,15 +234,49 @@ fundmat_kernel(RansacScratch R) {
     const float thr = (float)(kFmThreshold * kFmThreshold);
 
     while (!sh.stop) {
-        // ---- thread 0: the next RS_BATCH samples from the cv::RNG stream ------------------------------
+        // ---- the next RS_BATCH samples from the cv::RNG stream.  Drawing is sequential (one stream, re-draws on duplicate
+        //      indices and on collinear samples), but the collinearity test -- the expensive part -- only rarely fails: thread
+        //      0 draws all samples assuming they pass, RS_BATCH threads test them in parallel, and from the first failing
+        //      sample on thread 0 falls back to the exact sequential getSubset ------------------------------------------------
         if (tid == 0) {
             for (int w = 0; w < RS_BATCH; ++w) sh.found[w] = -1;
+            CvRng rg = sh.rng;
             for (int w = 0; w < RS_BATCH; ++w) {
                 if (sh.iter_base + w >= sh.niters) break;
-                int idx[7];
-                const bool ok = get_subset7(m1, m2, n, sh.rng, lmeds ? 1000 : 10000, idx, sh.ms1[w], sh.ms2[w]);
-                sh.found[w] = ok ? 1 : 0;
-                if (!ok) break;
+                for (int i = 0; i < 7; ++i) {
+                    int idx_i;
+                    while (true) {
+                        idx_i = rg.uniform(0, n);
+                        bool dup = false;
+                        for (int j = 0; j < i; ++j) dup = dup || (sh.idx[w][j] == idx_i);
+                        if (!dup) break;
+                    }
+                    sh.idx[w][i] = idx_i;
+                    sh.ms1[w][i] = m1[idx_i];
+                    sh.ms2[w][i] = m2[idx_i];
+                }
+                sh.rng_after[w] = rg;
+                sh.found[w] = 1;
+            }
+        }
+        __syncthreads();
+        if (tid < RS_BATCH) sh.collinear[tid] = sh.found[tid] == 1 && (last_point_collinear(sh.ms1[tid], 7) || last_point_collinear(sh.ms2[tid], 7));
+        __syncthreads();
+        if (tid == 0) {
+            int bad = -1;
+            for (int w = 0; w < RS_BATCH && bad < 0; ++w) if (sh.found[w] == 1 && sh.collinear[w]) bad = w;
+            if (bad < 0) {
+                for (int w = RS_BATCH - 1; w >= 0; --w) if (sh.found[w] == 1) { sh.rng = sh.rng_after[w]; break; }
+            } else {                                   // exact sequential path from the first collinear sample on
+                sh.rng = bad == 0 ? sh.rng : sh.rng_after[bad - 1];
+                for (int w = bad; w < RS_BATCH; ++w) {
+                    sh.found[w] = -1;
+                    if (sh.iter_base + w >= sh.niters) continue;
+                    int idx[7];
+                    const bool ok = get_subset7(m1, m2, n, sh.rng, lmeds ? 1000 : 10000, idx, sh.ms1[w], sh.ms2[w]);
+                    sh.found[w] = ok ? 1 : 0;
+                    if (!ok) { for (int v = w + 1; v < RS_BATCH; ++v) sh.found[v] = -1; break; }
+                }
             }
         }
         __syncthreads();
