@@ -959,7 +959,7 @@ def run_gpu(args):
 
     sharded = None
     if not args.no_micro or world > 1:
-        sharded = c5_sharded(capi, torch, dist, local, world, rank, pipe, reps=max(8, 64 // world))
+        sharded = c5_sharded(capi, torch, dist, local, world, rank, pipe, reps=64)          # weak scaling: 64 problems per GPU
 
     if rank == 0:
         value = pairs_all / (ms * 1e-3)

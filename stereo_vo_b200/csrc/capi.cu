@@ -13,10 +13,12 @@
 #include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler (nsys / ncu --nvtx) is attached
 
 #include <cmath>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace svo;
@@ -80,6 +82,8 @@ struct svo_ctx {
     // svo_set_result_detail(1): the variable-length members of TStereoOdometryResult travel with every batch
     int detail = 0;
     bool batch_copy_ok = true;         // cudaMemcpyBatchAsync accepted by this driver (scattered image uploads)
+    uint8_t* h_stage[kDepth] = {};     // pinned staging for images that arrive in pageable host memory (allocated on demand)
+    size_t h_stage_bytes = 0;
     double* r_resid[kDepth] = {};      // [n_slots][PG.kp_cap]
     int32_t* r_outl[kDepth] = {};      // [n_slots][PG.kp_cap]
     int32_t* r_stats[kDepth] = {};     // [n_slots][kMaxOctaves*4] per-octave counters (result.detected_feats / stereo_matches)
@@ -661,6 +665,7 @@ void svo_destroy(svo_ctx* c) {
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (void* p : c->dev_allocs) cudaFree(p);
     for (void* p : c->host_allocs) cudaFreeHost(p);
+    for (int k = 0; k < kDepth; ++k) if (c->h_stage[k]) cudaFreeHost(c->h_stage[k]);
     delete c;
 }
 
@@ -945,7 +950,42 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
     bool contig = true;
     for (int i = 1; i < n && contig; ++i)
         contig = left[i] == left[0] + (size_t)i * stride * H && right[i] == right[0] + (size_t)i * stride * H;
-    if (contig && stride == up_pitch) {
+    // images in ordinary (pageable) host memory -- what an MRPT CImage or a cv::Mat holds: the driver would stage every
+    // one of the 2n copies through its own bounce buffer, synchronously.  They are gathered into a pinned block of the
+    // library by a few host threads instead (memcpy at memory speed) and go up as two large asynchronous copies.
+    bool pageable = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, left[0]) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+    if (pageable) {
+        const size_t need = 2 * (size_t)c->cfg.max_seqs * up_plane;
+        if (c->h_stage_bytes < need) {
+            for (int k = 0; k < kDepth; ++k) {
+                if (c->h_stage[k]) { cudaFreeHost(c->h_stage[k]); c->h_stage[k] = nullptr; }
+                CU(c, cudaHostAlloc((void**)&c->h_stage[k], need, cudaHostAllocDefault));
+            }
+            c->h_stage_bytes = need;
+        }
+        uint8_t* hs = c->h_stage[b];
+        const int nthr = std::max(1, std::min(8, std::min(n, (int)std::thread::hardware_concurrency())));
+        auto work = [&](int t) {
+            for (int i = t; i < n; i += nthr)
+                for (int side = 0; side < 2; ++side) {
+                    const uint8_t* src = side ? right[i] : left[i];
+                    uint8_t* dst = hs + ((size_t)side * n + i) * up_plane;
+                    if (stride == up_pitch) memcpy(dst, src, up_plane);
+                    else for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * up_pitch, src + (size_t)y * stride, row_bytes);
+                }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        CU(c, cudaMemcpyAsync(upL, hs, up_plane * n, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaMemcpyAsync(upR, hs + (size_t)n * up_plane, up_plane * n, cudaMemcpyHostToDevice, c->copy_stream));
+    } else if (contig && stride == up_pitch) {
         CU(c, cudaMemcpyAsync(upL, left[0], up_plane * n, cudaMemcpyHostToDevice, c->copy_stream));
         CU(c, cudaMemcpyAsync(upR, right[0], up_plane * n, cudaMemcpyHostToDevice, c->copy_stream));
     } else if (stride == up_pitch) {
