@@ -30,17 +30,28 @@ def main(rep, pairs, how):
             return None
     res = {"source": f"{rep.split('/')[-1]}: {how}", "pairs_per_launch": int(pairs), "dram_bytes_per_launch": {},
            "warp_instructions_per_launch": {}, "sm_throughput_pct": {}, "duration_us": {}}
-    seen_hamming = 0
+    # the capture window may hold more than one step and start in the middle of one: cut it at begin_step launches and
+    # keep the complete step with the longest total duration (a tracking step; the first frame of a sequence skips stages 3-5)
+    steps, cur = [], None
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
         short = name.split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
-        if short == "hamming_pipeline_kernel":
+        if not short:
+            continue
+        if short == "begin_step_kernel":
+            cur = []
+            steps.append(cur)
+        if cur is not None:
+            cur.append((short, r))
+    n_kern = max(len(s) for s in steps)
+    best = max((s for s in steps if len(s) == n_kern), key=lambda s: sum(val(r, "gpu__time_duration.sum") or 0 for _, r in s))
+    seen_hamming = 0
+    for short, r in best:
+        if short in ("hamming_pipeline_kernel", "hamming_kernel"):
             short = "hamming_kernel(lr)" if seen_hamming == 0 else "hamming_kernel(track)"
             seen_hamming += 1
         if short == "begin_step_kernel":
             short = "begin_step"
-        if short in res["duration_us"]:
-            continue                                     # the first launch of each kernel = the captured step
         rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
         res["dram_bytes_per_launch"][short] = int((rd or 0) + (wr or 0))
         res["warp_instructions_per_launch"][short] = int(val(r, "smsp__inst_executed.sum") or 0)

@@ -419,7 +419,9 @@ void octave_quotas(int orb_nfeats, int n_oct, int* q) {
 cudaError_t alloc_octave_arrays(svo_ctx* c, Pools& P, size_t S, size_t plane, size_t cap) {
     cudaError_t e;
 #define OA(ptr, count) do { if ((e = dalloc(c, &(ptr), (count))) != cudaSuccess) return e; } while (0)
-    OA(P.blur, S * 2 * plane); OA(P.score, S * 2 * plane);
+    OA(P.blur, S * 2 * plane);
+    OA(P.tile_seg, S * 2 * (size_t)tiles_x_of(P.p.W) * tiles_y_of(P.p.H) * kTileH);
+    OA(P.tile_list, S * 2 * (size_t)tiles_x_of(P.p.W) * tiles_y_of(P.p.H) * kTileCap);
     OA(P.cand_pos, S * 2 * (size_t)P.p.max_corners); OA(P.n_cand, S * 2);
     OA(P.kp, S * 4 * cap); OA(P.desc, S * 4 * cap * 2); OA(P.n_kp, S * 4);
     OA(P.match, S * 2 * cap); OA(P.n_match, S * 2); OA(P.mdesc, S * 4 * cap * 2); OA(P.match_id, S * 2 * cap);
@@ -543,7 +545,9 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
 #define DA(ptr, count) do { cudaError_t e2 = dalloc(c, &(ptr), (count)); if (e2 != cudaSuccess) { int rc = cuda_fail(nullptr, e2, "cudaMalloc " #ptr); svo_destroy(c); return rc; } } while (0)
 #define HA(ptr, count) do { cudaError_t e2 = halloc(c, &(ptr), (count)); if (e2 != cudaSuccess) { int rc = cuda_fail(nullptr, e2, "cudaMallocHost " #ptr); svo_destroy(c); return rc; } } while (0)
     DA(P.state, S); DA(P.result, S); DA(P.cam, S);
-    DA(P.blur, S * 2 * plane); DA(P.score, S * 2 * plane);
+    DA(P.blur, S * 2 * plane);
+    DA(P.tile_seg, S * 2 * (size_t)tiles_x_of(cfg->width) * tiles_y_of(cfg->height) * kTileH);
+    DA(P.tile_list, S * 2 * (size_t)tiles_x_of(cfg->width) * tiles_y_of(cfg->height) * kTileCap);
     DA(P.cand_pos, (size_t)S * 2 * cfg->max_corners); DA(P.n_cand, S * 2);
     DA(P.kp, S * 4 * cap); DA(P.desc, S * 4 * cap * 2); DA(P.n_kp, S * 4);
     DA(P.match, S * 2 * cap); DA(P.n_match, S * 2); DA(P.mdesc, S * 4 * cap * 2); DA(P.match_id, S * 2 * cap);
@@ -1417,8 +1421,28 @@ int svo_get_plane(svo_ctx* c, int32_t slot, int32_t side, int32_t plane, uint8_t
     if (slot == -1) slot = c->hidden_slot;   // the scratch slot used by svo_detect
     if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (side | 1) != 1 || (plane | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/side/plane");
     CU(c, cudaStreamSynchronize(c->stream));
-    const uint8_t* src = (plane ? c->P.score : c->P.blur) + img_idx(slot, side) * (size_t)c->pitch * c->cfg.height;
-    CU(c, cudaMemcpy2D(out, c->cfg.width, src, c->pitch, c->cfg.width, c->cfg.height, cudaMemcpyDeviceToHost));
+    const int W = c->cfg.width, H = c->cfg.height;
+    if (plane == 0) {
+        const uint8_t* src = c->P.blur + img_idx(slot, side) * (size_t)c->pitch * H;
+        CU(c, cudaMemcpy2D(out, W, src, c->pitch, W, H, cudaMemcpyDeviceToHost));
+        return SVO_OK;
+    }
+    // the score plane is not kept on the device: rebuilt here from the per-tile corner lists
+    const int tx = tiles_x_of(W), ty = tiles_y_of(H);
+    const size_t tiles = (size_t)tx * ty;
+    std::vector<uint16_t> seg(tiles * kTileH), lst(tiles * kTileCap);
+    CU(c, cudaMemcpy(seg.data(), c->P.tile_seg + img_idx(slot, side) * tiles * kTileH, seg.size() * 2, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(lst.data(), c->P.tile_list + img_idx(slot, side) * tiles * kTileCap, lst.size() * 2, cudaMemcpyDeviceToHost));
+    memset(out, 0, (size_t)W * H);
+    for (int y = 0; y < H; ++y)
+        for (int t = 0; t < tx; ++t) {
+            const uint16_t sg = seg[(size_t)y * tx + t];
+            const uint16_t* band = &lst[((size_t)(y / kTileH) * tx + t) * kTileCap + (size_t)((y % kTileH) / kBandH) * kBandCap];
+            for (int k = sg >> 8; k < (sg >> 8) + (sg & 0xFF) && k < kBandCap; ++k) {
+                const int x = t * kTileW + (band[k] & 0xFF);
+                if (x < W) out[(size_t)y * W + x] = (uint8_t)(band[k] >> 8);
+            }
+        }
     return SVO_OK;
 }
 

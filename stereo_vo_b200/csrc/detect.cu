@@ -31,7 +31,7 @@ namespace svo {
 //   3c strict 3x3 NMS + ORB border filter over the corner list (dense)
 //   4  blur column pass + stores, 4 pixels per work item
 // ------------------------------------------------------------------------------------------------
-constexpr int TW = 64, TH = 32, HALO = 4;
+constexpr int TW = kTileW, TH = kTileH, HALO = 4;
 constexpr int SIN_W = TW + 2 * HALO;   // 72 bytes per staged row ...
 constexpr int SIN_WW = SIN_W / 4;      // ... = 18 words
 // TMA wants the box to start at a multiple of 16 bytes in x and to be a multiple of 16 bytes wide: the staged box begins
@@ -42,6 +42,9 @@ constexpr int SIN_XOFF = 12;           // bytes; a multiple of 4, so staged word
 constexpr int SIN_H = TH + 2 * HALO;   // 40
 constexpr int SC_H = TH + 2;           // score rows: tile rows -1 .. TH (row r <-> tile row r-1); columns as in s_in
 constexpr int K1_THREADS = 256;
+// bit 7 of every non-zero byte
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t w) { return ((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w) & 0x80808080u; }
+
 constexpr int K1_NCAND = SC_H * (TW + 2);
 constexpr int K1_ITEMS3 = SC_H * SIN_WW;   // pre-test work items (row, word)
 
@@ -139,11 +142,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     } while (!done);
 }
 
+// one lane's add on a shared counter, as the single ATOMS it is (atomicAdd() under `lane == 0` makes the compiler wrap it in
+// its own vote / find-leader / popc aggregation, ~17 instructions per call; the warps here have aggregated by ballot already)
+__device__ __forceinline__ int smem_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
+
 // USE_TMA: the tile (+ halo) comes in with one cp.async.bulk.tensor per CTA from a tensor map over the batch's images
 // (zero fill outside the image; the few halo bytes that REFLECT_101 needs are patched afterwards, border tiles only).
 // Needs 16-byte aligned images / strides; launch_detect falls back to the load loop otherwise.
 template <bool USE_TMA>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, 6)
 fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __restrict__ imgR,
                  size_t stride, size_t image_pitch, int pitch_out, const __grid_constant__ CUtensorMap tmL,
                  const __grid_constant__ CUtensorMap tmR) {
@@ -187,10 +198,19 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
         if (c_lo > 0 || c_hi < SIN_W || r_lo > 0 || r_hi < SIN_H) {
             __syncthreads();
             uint8_t* s_inb = reinterpret_cast<uint8_t*>(s_inl);
-            for (int i = tid; i < SIN_H * SIN_W; i += K1_THREADS) {
-                const int r = i / SIN_W, c = i - r * SIN_W;
-                if (r < r_lo || r >= r_hi || c < c_lo || c >= c_hi)
-                    s_inb[r * SIN_P + c] = __ldg(img + (size_t)reflect1(y0 - HALO + r, H) * stride + reflect1(x0 - HALO + c, W));
+            // rows above / below the image (whole staged rows), then columns left / right of it (the corners twice: harmless)
+            const int n_rows = r_lo + (SIN_H - r_hi), n_cols = c_lo + (SIN_W - c_hi);
+            for (int i = tid; i < n_rows * SIN_W; i += K1_THREADS) {
+                int r = i / SIN_W;
+                const int c = i - r * SIN_W;
+                if (r >= r_lo) r += r_hi - r_lo;
+                s_inb[r * SIN_P + c] = __ldg(img + (size_t)reflect1(y0 - HALO + r, H) * stride + reflect1(x0 - HALO + c, W));
+            }
+            for (int i = tid; i < n_cols * SIN_H; i += K1_THREADS) {
+                const int r = i / n_cols;
+                int c = i - r * n_cols;
+                if (c >= c_lo) c += c_hi - c_lo;
+                s_inb[r * SIN_P + c] = __ldg(img + (size_t)reflect1(y0 - HALO + r, H) * stride + reflect1(x0 - HALO + c, W));
             }
         }
     } else {
@@ -271,7 +291,7 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
             const unsigned b2 = __ballot_sync(0xffffffffu, c2), b3 = __ballot_sync(0xffffffffu, c3);
             const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
             int base = 0;
-            if (lane == 0 && (n0 + n1 + n2 + n3) > 0) base = atomicAdd(&s_n[0], n0 + n1 + n2 + n3);
+            if (lane == 0 && (n0 + n1 + n2 + n3) > 0) base = smem_add(&s_n[0], n0 + n1 + n2 + n3);
             base = __shfl_sync(0xffffffffu, base, 0);
             const int e = r * SIN_P + 4 * cw;
             if (c0) s_list[base + __popc(b0 & lt_mask)] = (uint16_t)e;
@@ -295,7 +315,7 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
             }
             const unsigned b = __ballot_sync(0xffffffffu, sc > 0);
             int base = 0;
-            if (lane == 0 && b) base = atomicAdd(&s_n[1], __popc(b));
+            if (lane == 0 && b) base = smem_add(&s_n[1], __popc(b));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (sc > 0) s_corner[base + __popc(b & lt_mask)] = (uint16_t)e;
         }
@@ -322,7 +342,6 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
 
     // 4. blur column pass + stores; 4 pixels per work item, 32-bit stores
     uint8_t* __restrict__ blur_out = P.blur + img_idx(slot, side) * (size_t)pitch_out * H;
-    uint8_t* __restrict__ score_out = P.score + img_idx(slot, side) * (size_t)pitch_out * H;
     for (int i = tid; i < TH * TW / 4; i += K1_THREADS) {
         const int r = i / (TW / 4), c4 = (i - r * (TW / 4)) * 4;
         const int gy = y0 + r, gx = x0 + c4;
@@ -348,7 +367,42 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
             bw |= v << (8 * q);
         }
         *reinterpret_cast<uint32_t*>(blur_out + (size_t)gy * pitch_out + gx) = bw;
-        *reinterpret_cast<uint32_t*>(score_out + (size_t)gy * pitch_out + gx) = s_nmsw[i];
+    }
+
+    // 5. the tile's corners as compact lists in row-major order: thread t owns pixels 8t .. 8t+7 of the tile (row t / 8), a
+    //    warp owns a band of kBandH rows with its own kBandCap entries of the tile's list (strict 3x3 maxima: at most one per
+    //    2x2 block, so a band cannot overflow) - a warp scan places the corners, no block-wide step.  Every image row of
+    //    the tile (a "segment") records where its corners start inside the band's list and how many they are.
+    {
+        static_assert(K1_THREADS * 8 == TW * TH && 32 * 8 == kBandH * TW, "one thread per 8 pixels, one warp per band");
+        const uint32_t w0 = s_nmsw[2 * tid], w1 = s_nmsw[2 * tid + 1];
+        uint32_t m0 = nonzero_bytes(w0), m1 = nonzero_bytes(w1);
+        const int cnt = __popc(m0) + __popc(m1);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const size_t tile = ((size_t)img_idx(slot, side) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const int row_lo = __shfl_up_sync(0xffffffffu, incl, 8);      // inclusive count at the end of the previous row
+        if ((tid & 7) == 7) {
+            const int lo = lane >= 8 ? row_lo : 0;
+            const size_t y = (size_t)blockIdx.y * TH + (tid >> 3);
+            P.tile_seg[((size_t)img_idx(slot, side) * gridDim.y * TH + y) * gridDim.x + blockIdx.x] = (uint16_t)((lo << 8) | (incl - lo));
+        }
+        uint16_t* __restrict__ lst = P.tile_list + tile * kTileCap + (tid >> 5) * kBandCap + (incl - cnt);
+        const int xb = (tid & 7) * 8;
+        while (m0) {
+            const int bit = __ffs(m0) - 1;               // 7, 15, 23 or 31
+            m0 &= m0 - 1;
+            *lst++ = (uint16_t)((((w0 >> (bit - 7)) & 0xFFu) << 8) | (uint32_t)(xb + (bit >> 3)));
+        }
+        while (m1) {
+            const int bit = __ffs(m1) - 1;
+            m1 &= m1 - 1;
+            *lst++ = (uint16_t)((((w1 >> (bit - 7)) & 0xFFu) << 8) | (uint32_t)(xb + 4 + (bit >> 3)));
+        }
     }
 }
 
@@ -362,9 +416,6 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
 // ------------------------------------------------------------------------------------------------
 constexpr int K2_THREADS = 256;
 constexpr int K2_SEGS = 4;          // 16-pixel score segments per thread per compaction round
-
-// bit 7 of every non-zero byte
-__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t w) { return ((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w) & 0x80808080u; }
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -432,67 +483,51 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
     const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
     const int slot = P.slots[item];
     const int tid = threadIdx.x;
-    const uint8_t* __restrict__ score = P.score + img_idx(slot, side) * (size_t)pitch * H;
     uint32_t* __restrict__ cand_pos = P.cand_pos + img_idx(slot, side) * (size_t)P.p.max_corners;
 
-    // ---- A. ordered compaction ---------------------------------------------------------------
-    const int segs = pitch / 16;
-    const int rows = max(0, H - 2 * kOrbEdge);
-    const int total_segs = rows * segs;
-    int base = 0;
-    bool overflow = false;
-    for (int g0 = 0; g0 < total_segs; g0 += K2_THREADS * K2_SEGS) {
-        // K2_SEGS consecutive 16-pixel segments per thread, all loads in flight before the block scan
-        uint4 v[K2_SEGS];
-        int cnt = 0;
-#pragma unroll
-        for (int u = 0; u < K2_SEGS; ++u) {
-            const int g = g0 + tid * K2_SEGS + u;
-            v[u] = make_uint4(0, 0, 0, 0);
-            if (g < total_segs) {
-                const int r = g / segs;
-                v[u] = *reinterpret_cast<const uint4*>(score + (size_t)(kOrbEdge + r) * pitch + (g - r * segs) * 16);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < K2_SEGS; ++u)
-            cnt += __popc(nonzero_bytes(v[u].x)) + __popc(nonzero_bytes(v[u].y)) + __popc(nonzero_bytes(v[u].z)) +
-                   __popc(nonzero_bytes(v[u].w));
-        int total;
-        const int off = block_exclusive_scan(cnt, s_warp, total);
+    // ---- A. the row-major candidate list from fast_blur_kernel's per-tile lists --------------------------
+    // a segment = the corners of one image row inside one tile; segments in (row, tile column) order are the row-major
+    // order of cv::FAST's keypoint list.  Every thread takes a contiguous run of segments, a block scan places them.
+    const int tiles_x = tiles_x_of(W), tiles_y = tiles_y_of(H);
+    const uint16_t* __restrict__ seg = P.tile_seg + img_idx(slot, side) * (size_t)tiles_x * tiles_y * kTileH;
+    const uint16_t* __restrict__ tlst = P.tile_list + img_idx(slot, side) * (size_t)tiles_x * tiles_y * kTileCap;
+    const int total_segs = H * tiles_x;                   // segment g = y * tiles_x + tx: the layout of tile_seg
+    const int spt = (total_segs + K2_THREADS - 1) / K2_THREADS;
+    const int g_lo = min(total_segs, tid * spt), g_hi = min(total_segs, g_lo + spt);
+    int cnt = 0;
+    for (int g = g_lo; g < g_hi; ++g) cnt += (int)(seg[g] & 0xFFu);
+    int total;
+    int o = block_exclusive_scan(cnt, s_warp, total);
+    const bool overflow = total > P.p.max_corners;
+    const int n = min(total, P.p.max_corners);
+    // sorted in shared memory when the candidates fit into smem_corners words, in the global array otherwise
+    uint32_t* s_a = n <= smem_corners ? smem : g_a;
+    {
+        // one word per corner first (where its list entry is + its row inside the band), so that the entries themselves are
+        // fetched by independent loads, one corner per thread, instead of a dependent chain per run of segments
+        static_assert(kTileCap == 512 && kBandCap == 64 && kBandH == 4, "entry index: tile << 9 | band << 6 | k");
+        uint32_t* stage = n <= smem_corners ? smem : tmp;
         if (cnt) {
-            int o = base + off;
-#pragma unroll
-            for (int u = 0; u < K2_SEGS; ++u) {
-                const int g = g0 + tid * K2_SEGS + u;
-                const int r = g / segs;
-                const int y = kOrbEdge + r, x = (g - r * segs) * 16;
-                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t m = nonzero_bytes(w[q]);
-                    while (m) {                              // corners are sparse: visit only the non-zero bytes, in x order
-                        const int bit = __ffs(m) - 1;        // 7, 15, 23 or 31
-                        m &= m - 1;
-                        const uint32_t sc = (w[q] >> (bit - 7)) & 0xFFu;
-                        if (o < P.p.max_corners) {
-                            g_a[o] = (sc << 24) | (uint32_t)o;
-                            cand_pos[o] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * q + (bit >> 3));
-                        }
-                        ++o;
-                    }
-                }
+            for (int g = g_lo; g < g_hi; ++g) {
+                const uint32_t sg = seg[g];
+                const int c = (int)(sg & 0xFFu);
+                if (!c) continue;
+                const int y = g / tiles_x, tx = g - y * tiles_x;
+                const uint32_t code = ((uint32_t)(y & (kBandH - 1)) << 30) |
+                                      (((uint32_t)(y / kTileH) * tiles_x + tx) << 9 | (uint32_t)((y & (kTileH - 1)) / kBandH) << 6) + (sg >> 8);
+                for (int k = 0; k < c; ++k, ++o)
+                    if (o < n) stage[o] = code + k;
             }
         }
-        base += total;
-    }
-    if (base > P.p.max_corners) { overflow = true; base = P.p.max_corners; }
-    const int n = base;
-    uint32_t* s_a = g_a;
-    __syncthreads();
-    if (n <= smem_corners) {
-        s_a = smem;
-        for (int i = tid; i < n; i += K2_THREADS) s_a[i] = g_a[i];
+        __syncthreads();
+        for (int i = tid; i < n; i += K2_THREADS) {
+            const uint32_t code = stage[i], ent = code & 0x3FFFFFFFu;
+            const uint32_t v = tlst[ent];
+            const int tile = (int)(ent >> 9), ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y = ty * kTileH + (int)((ent >> 6) & 7u) * kBandH + (int)(code >> 30);
+            s_a[i] = ((v >> 8) << 24) | (uint32_t)i;
+            cand_pos[i] = ((uint32_t)y << 16) | (uint32_t)(tx * kTileW + (int)(v & 0xFFu));
+        }
     }
     if (tid == 0) {
         P.n_cand[img_idx(slot, side)] = n;

@@ -16,6 +16,12 @@ namespace svo {
 
 constexpr int kOrbEdge = 31;        // cv::ORB edgeThreshold (border filter inside ORB::compute)
 constexpr int kMaxImgDim = 4096;    // x and y are packed in 16 bits each, grid occupancy bitmaps sized from it
+constexpr int kTileW = 64, kTileH = 32;        // fast_blur_kernel's tile
+constexpr int kTileCap = (kTileW / 2) * (kTileH / 2);   // strict 3x3 maxima: at most one per 2x2 block
+constexpr int kBandH = 4;                                // rows of a tile that one warp of fast_blur_kernel lists (256 pixels)
+constexpr int kBandCap = (kTileW / 2) * (kBandH / 2);   // list entries of one band (same 2x2 argument): 8 bands x 64 = kTileCap
+__host__ __device__ inline int tiles_x_of(int W) { return (W + kTileW - 1) / kTileW; }
+__host__ __device__ inline int tiles_y_of(int H) { return (H + kTileH - 1) / kTileH; }
 constexpr int kMaxOctaves = 4;      // params_rectify.nOctaves (reference default 3, stage1_rectify.cpp:28)
 
 struct SlotState {                  // mutable members of the estimator (libstereo-odometry.h:733-754)
@@ -84,7 +90,12 @@ struct Pools {
     Camera* cam;           // [max_seqs]
     // per (slot, side) scratch of one step
     uint8_t* blur;         // [max_seqs*2][H*W]   7x7 blurred image
-    uint8_t* score;        // [max_seqs*2][H*W]   FAST score after 3x3 NMS and 31-px border filter, 0 = none
+    // FAST corners after 3x3 NMS and the 31-px border filter, as compact per-tile lists (tiles of kTileW x kTileH pixels,
+    // fast_blur_kernel's CTA tile): no dense score plane is written or read
+    uint16_t* tile_seg;    // [max_seqs*2][tiles_y*kTileH][tiles_x]   one word per SEGMENT (image row y inside tile column tx):
+                           //                                 (first entry inside the band's list) << 8 | corners of the segment
+    uint16_t* tile_list;   // [max_seqs*2][tiles][kTileCap]   (score << 8 | x in tile); band b at [b * kBandCap ..), rows top to
+                           //                                 bottom, x ascending inside the band
     uint32_t* cand_pos;    // [max_seqs*2][max_corners]  y<<16|x of raw corners in row-major order
     int32_t* n_cand;       // [max_seqs*2]
     // per (slot, buf, side) frame data
