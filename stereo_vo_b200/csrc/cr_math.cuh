@@ -11,8 +11,10 @@
 
 #if defined(__CUDACC__)
 #define SVO_CR_HD __host__ __device__ inline
+#define SVO_CR_CALL __host__ __device__ __noinline__ inline   // entry points: one copy per kernel (code size)
 #else
 #define SVO_CR_HD inline
+#define SVO_CR_CALL inline
 #endif
 
 namespace svo {
@@ -58,7 +60,7 @@ SVO_CR_HD dd mul_d(dd a, double b) {
 
 // x^(1./3) for x > 0, the exponent being the double next to one third (what std::pow(x, 1./3) computes):
 // cube root by one double-double Newton step from cbrt(), times x^-(1/3 - fl(1/3)) = 1 - delta*ln(x)
-SVO_CR_HD double pow13(double x) {
+SVO_CR_CALL double pow13(double x) {
     if (!(x > 0) || x > 1e300 || x < 1e-300) return pow(x, 1. / 3);
     const double c0 = cbrt(x);
     const dd c2 = two_prod(c0, c0);
@@ -115,7 +117,7 @@ SVO_CR_HD dd sin_kernel(dd r) {
     return add(mul(mul(p, z), r), r);                    // r + r*z*p
 }
 
-SVO_CR_HD dd cos_dd(double t) {
+SVO_CR_CALL dd cos_dd(double t) {
     dd r;
     const int q = reduce_pio2(t, r);
     dd v = (q & 1) ? sin_kernel(r) : cos_kernel(r);
@@ -123,14 +125,14 @@ SVO_CR_HD dd cos_dd(double t) {
     return v;
 }
 
-SVO_CR_HD double cos_cr(double t) {
+SVO_CR_CALL double cos_cr(double t) {
     if (!(fabs(t) < 1048576.0)) return cos(t);
     const dd v = cos_dd(t);
     return v.hi + v.lo;
 }
 
 // acos(v), |v| < 1: one Newton step y = y0 + (cos(y0) - v) / sin(y0) with cos(y0) in double-double
-SVO_CR_HD double acos_cr(double v) {
+SVO_CR_CALL double acos_cr(double v) {
     const double y0 = acos(v);
     if (!(fabs(v) < 1.0) || y0 < 1e-6) return y0;
     const dd c = cos_dd(y0);

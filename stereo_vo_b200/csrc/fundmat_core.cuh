@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define SVO_HD2 __host__ __device__ inline
+#define SVO_HD2_CALL __host__ __device__ __noinline__ inline   // kept out of line on the device (instruction-cache footprint)
 #else
 #define SVO_HD2 inline
+#define SVO_HD2_CALL inline
 #endif
 
 namespace svo {
@@ -39,7 +41,7 @@ struct CvRng {
 struct Pt2f { float x, y; };
 
 // haveCollinearPoints(ms, count): only the last point is tested against all pairs of earlier ones
-SVO_HD2 bool last_point_collinear(const Pt2f* p, int count) {
+SVO_HD2_CALL bool last_point_collinear(const Pt2f* p, int count) {
     const int i = count - 1;
     for (int j = 0; j < i; j++) {
         const double dx1 = p[j].x - p[i].x, dy1 = p[j].y - p[i].y;
@@ -52,7 +54,7 @@ SVO_HD2 bool last_point_collinear(const Pt2f* p, int count) {
 }
 
 // getSubset(m1, m2, ms1, ms2, rng, maxAttempts): returns false when no valid subset was found
-SVO_HD2 bool get_subset7(const Pt2f* m1, const Pt2f* m2, int count, CvRng& rng, int max_attempts, int* idx,
+SVO_HD2_CALL bool get_subset7(const Pt2f* m1, const Pt2f* m2, int count, CvRng& rng, int max_attempts, int* idx,
                          Pt2f* ms1, Pt2f* ms2) {
     for (int iters = 0; iters < max_attempts; ++iters) {
         for (int i = 0; i < 7; ++i) {
@@ -75,7 +77,7 @@ SVO_HD2 bool get_subset7(const Pt2f* m1, const Pt2f* m2, int count, CvRng& rng, 
 SVO_HD2 int cv_round(double v) { return (int)nearbyint(v); }   // cvRound: round half to even
 
 // RANSACUpdateNumIters(p, ep, modelPoints, maxIters)
-SVO_HD2 int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
+SVO_HD2_CALL int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
     p = fmax(p, 0.); p = fmin(p, 1.);
     ep = fmax(ep, 0.); ep = fmin(ep, 1.);
     double num = fmax(1. - p, DBL_MIN);
@@ -100,7 +102,7 @@ SVO_HD2 int ransac_update_num_iters(double p, double ep, int model_points, int m
 #define SVO_ACOS(x) acos(x)
 #define SVO_COS(x) cos(x)
 #endif
-SVO_HD2 int solve_cubic(const double* c, double* r) {
+SVO_HD2_CALL int solve_cubic(const double* c, double* r) {
     double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
     double x0 = 0., x1 = 0., x2 = 0.;
     int n = 0;
@@ -291,7 +293,7 @@ SVO_HD2 void fm7_svd_rows(double (*At)[9]) {
 }
 
 // cubic in the pencil lambda*f1 + (1-lambda)*f2, roots -> up to 3 de-normalised F matrices.  f1, f2: rows 7, 8 of Vt.
-SVO_HD2 int fm7_finish(double* f1, double* f2, const Fm7Norm& nm, double* F /* 27 */) {
+SVO_HD2_CALL int fm7_finish(double* f1, double* f2, const Fm7Norm& nm, double* F /* 27 */) {
     // f ~ lambda*f1 + (1-lambda)*f2, det(f) = 0 gives a cubic in lambda
     for (int i = 0; i < 9; ++i) f1[i] -= f2[i];
     double c[4], r[3] = {0, 0, 0};

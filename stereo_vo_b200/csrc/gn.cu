@@ -98,7 +98,8 @@ __device__ void rot_and_derivs(const double* dp, RotDeriv& o) {
 // for sm_100a (the column pass acted on rows); this form was validated on the device.
 __device__ __forceinline__ double& sym(double* A, int i, int j) { return i <= j ? A[6 * i + j] : A[6 * j + i]; }
 
-__device__ bool solve6(const double* Hu /* 21 upper-triangle entries, row-major */, const double* g, double* x) {
+// (out of line, loops kept as loops: the rarely taken fallback was 60 KB of the kernel's code when unrolled and inlined twice)
+__device__ __noinline__ bool solve6(const double* Hu /* 21 upper-triangle entries, row-major */, const double* g, double* x) {
     double A[36], V[36];
     bool finite = true;
     {
@@ -111,6 +112,7 @@ __device__ bool solve6(const double* Hu /* 21 upper-triangle entries, row-major 
             }
     }
     if (!finite) return false;
+#pragma unroll 1
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0, diag = 0;
         for (int i = 0; i < 6; ++i) {
@@ -118,7 +120,9 @@ __device__ bool solve6(const double* Hu /* 21 upper-triangle entries, row-major 
             for (int j = i + 1; j < 6; ++j) off += A[6 * i + j] * A[6 * i + j];
         }
         if (off <= diag * 1e-32) break;
+#pragma unroll 1
         for (int p = 0; p < 5; ++p)
+#pragma unroll 1
             for (int q = p + 1; q < 6; ++q) {
                 const double apq = A[6 * p + q];
                 if (apq == 0.0) continue;
@@ -216,7 +220,7 @@ __device__ __forceinline__ bool chol6_solve(const double* Hu, const double* g, d
     return fin;
 }
 
-__device__ void rodrigues(const double* w, double R[3][3]) {
+__device__ __noinline__ void rodrigues(const double* w, double R[3][3]) {
     const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
     double a, b;
     if (th < 1e-12) { a = 1.0; b = 0.5; }

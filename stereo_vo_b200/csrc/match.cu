@@ -718,7 +718,7 @@ static int rbr_smem(const Params& p) { return (2 * p.H + 2 * p.kp_cap) * (int)si
 static int win_smem(const Params& p) { return (2 * (p.H + 1) + p.kp_cap) * (int)sizeof(uint32_t); }
 
 // a batch too small to fill the GPU with one CTA per query block (the literal one-estimator seam): split the train set so
-// that a few hundred CTAs share the scan; latency of the Hamming stages at batch 1: 0.19 -> 0.05 ms
+// that a few hundred CTAs share the scan; the three Hamming problems of one pair at batch 1: 0.19 -> 0.04 ms (tools/latency_breakdown.py)
 static int hamming_splits(int ctas) {
     int s = 1;
     while (s < 16 && ctas * s * 2 <= 296) s *= 2;

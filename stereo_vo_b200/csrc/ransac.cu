@@ -33,6 +33,7 @@ struct RsShared {
     CvRng rng_after[RS_BATCH];     // speculative sampling: the RNG state behind every sample of the round
     int idx[RS_BATCH][7];
     int collinear[RS_BATCH];
+    double svd[RS_WARPS][16 * 32];  // run_7point_warp3's rows, [row][lane] per warp
 };
 
 // S4:181-232: point sets of the left-left and right-right problems from the greedy-filtered lists
@@ -75,15 +76,19 @@ __device__ __forceinline__ double ordered_sum9(double v, int base) {
 
 // run_7point with the SVD step (fm7_svd_rows: OpenCV's one-sided Jacobi on the rows of the 7x9 system, then the two
 // extra right singular vectors) spread over the warp, three samples side by side: lanes 9g .. 9g+8 own the nine columns
-// of sample g's rows in registers.  Every rotation / projection touches its element with exactly the operations of the
-// sequential loops and every dot product is summed in the sequential order (ordered_sum9), so f1 / f2 and the models
-// are bit-identical to the host build of fundmat_core.cuh that is pinned against cv2.  The three samples run in lockstep:
+// of sample g's rows.  Every rotation / projection touches its element with exactly the operations of the sequential
+// loops and every dot product is summed in the sequential order (ordered_sum9), so f1 / f2 and the models are
+// bit-identical to the host build of fundmat_core.cuh that is pinned against cv2.  The three samples run in lockstep:
 // OpenCV's data-dependent branches ("rows already orthogonal: skip", "beta < 0", hypot's operand order, "no rotation in
 // this sweep: stop") are evaluated as selects, a skipped rotation leaves its rows untouched, and a sample that has
 // converged idles through the sweeps the others still need (a converged sweep changes nothing).
+// The rows live in shared memory (svd: 16 x 32 doubles of this warp, element [row][lane], only ever touched by its own
+// lane), so that the pair loops are real loops: fully unrolled on register arrays the function was 250 KB of code and
+// the kernel spent half of its issue slots waiting for instructions.  Out of line for the same reason.
 // ms1 / ms2: RS_GROUPS x 7 points, valid[g] != 1 marks an unused group; F: RS_GROUPS x 27, nm_out: RS_GROUPS counts,
 // written by the first lane of each group.  All 32 lanes must call it.
-__device__ void run_7point_warp3(const Pt2f (*ms1)[7], const Pt2f (*ms2)[7], const int* valid, double (*F)[27], int* nm_out) {
+__device__ __noinline__ void run_7point_warp3(const Pt2f (*ms1)[7], const Pt2f (*ms2)[7], const int* valid, double (*F)[27],
+                                              int* nm_out, double* svd) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     const int g = lane < 27 ? lane / 9 : 2;
@@ -97,21 +102,24 @@ __device__ void run_7point_warp3(const Pt2f (*ms1)[7], const Pt2f (*ms2)[7], con
     if (ok) ok = fm7_normalise(m1, m2, nm);
     const int m = 9, n = 7;
     const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
-    double col[9], W[7];
+    double* const col = svd + lane;                    // row i of this lane's column: col[32 * i], i < 9
+    double* const W = svd + 9 * 32 + lane;             // W[32 * i], i < 7
     // an unused / degenerate group works on orthonormal dummy rows: no rotations, no zero singular values
-#pragma unroll
-    for (int i = 0; i < 7; ++i) col[i] = !colv ? 0.0 : (ok ? fm7_entry(m1, m2, nm, i, kcol) : (kcol == i ? 1.0 : 0.0));
-    col[7] = col[8] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) W[i] = ordered_sum9(col[i] * col[i], base);
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) col[32 * i] = !colv ? 0.0 : (ok ? fm7_entry(m1, m2, nm, i, kcol) : (kcol == i ? 1.0 : 0.0));
+    col[32 * 7] = col[32 * 8] = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) W[32 * i] = ordered_sum9(col[32 * i] * col[32 * i], base);
+#pragma unroll 1
     for (int iter = 0; iter < 30; ++iter) {
         bool changed = false;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < n - 1; ++i) {
-#pragma unroll
+#pragma unroll 1
             for (int j = i + 1; j < n; ++j) {
-                const double a = W[i], b = W[j];
-                double p = ordered_sum9(col[i] * col[j], base);
+                const double ci = col[32 * i], cj = col[32 * j];
+                const double a = W[32 * i], b = W[32 * j];
+                double p = ordered_sum9(ci * cj, base);
                 const bool rot = !(fabs(p) <= eps * sqrt(a * b));
                 if (!__any_sync(full, rot)) continue;  // warp-uniform
                 p *= 2;
@@ -128,34 +136,32 @@ __device__ void run_7point_warp3(const Pt2f (*ms1)[7], const Pt2f (*ms2)[7], con
                 const double first = sqrt(num / den);
                 const double second = p / (gamma * first * 2);
                 const double c = neg ? second : first, s = neg ? first : second;
-                const double t0 = c * col[i] + s * col[j];
-                const double t1 = -s * col[i] + c * col[j];
+                const double t0 = c * ci + s * cj;
+                const double t1 = -s * ci + c * cj;
                 const double wa = ordered_sum9(t0 * t0, base), wb = ordered_sum9(t1 * t1, base);
-                if (rot) { col[i] = t0; col[j] = t1; W[i] = wa; W[j] = wb; changed = true; }
+                if (rot) { col[32 * i] = t0; col[32 * j] = t1; W[32 * i] = wa; W[32 * j] = wb; changed = true; }
             }
         }
         if (!__any_sync(full, changed)) break;
     }
-#pragma unroll
-    for (int i = 0; i < n; ++i) W[i] = sqrt(ordered_sum9(col[i] * col[i], base));
-#pragma unroll
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) W[32 * i] = sqrt(ordered_sum9(col[32 * i] * col[32 * i], base));
+#pragma unroll 1
     for (int i = 0; i < n - 1; ++i) {                  // selection sort, descending; first maximum wins
         int j = i;
-        double wj = W[i];
-#pragma unroll
-        for (int k = i + 1; k < n; ++k) if (wj < W[k]) { j = k; wj = W[k]; }
-#pragma unroll
-        for (int k = i + 1; k < n; ++k)
-            if (k == j) {
-                const double tw = W[i]; W[i] = W[k]; W[k] = tw;
-                const double tc = col[i]; col[i] = col[k]; col[k] = tc;
-            }
+        double wj = W[32 * i];
+        for (int k = i + 1; k < n; ++k) if (wj < W[32 * k]) { j = k; wj = W[32 * k]; }
+        if (j != i) {
+            const double tw = W[32 * i]; W[32 * i] = W[32 * j]; W[32 * j] = tw;
+            const double tc = col[32 * i]; col[32 * i] = col[32 * j]; col[32 * j] = tc;
+        }
     }
     CvRng rng;
     rng.state = 0x12345678;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 9; ++i) {
-        double sd = i < n ? W[i < n ? i : 0] : 0;
+        double sd = i < n ? W[32 * i] : 0;
+#pragma unroll 1
         for (int ii = 0; ii < 100; ++ii) {
             const bool need = sd <= minval;            // this group draws another vector
             if (!__any_sync(full, need)) break;
@@ -167,26 +173,29 @@ __device__ void run_7point_warp3(const Pt2f (*ms1)[7], const Pt2f (*ms2)[7], con
                 if (k == kcol) v = vk;
             }
             if (need) rng = r2;
-            double ci = need ? v : col[i];
+            double ci = need ? v : col[32 * i];
+#pragma unroll 1
             for (int it2 = 0; it2 < 2; ++it2) {
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < i; ++j) {
-                    const double d = ordered_sum9(ci * col[j], base);
-                    const double t = ci - d * col[j];
+                    const double cj = col[32 * j];
+                    const double d = ordered_sum9(ci * cj, base);
+                    const double t = ci - d * cj;
                     double asum = ordered_sum9(fabs(t), base);
                     asum = asum > eps * 100 ? 1 / asum : 0;
                     ci = t * asum;
                 }
             }
             const double nsd = sqrt(ordered_sum9(ci * ci, base));
-            if (need) { col[i] = ci; sd = nsd; }
+            if (need) { col[32 * i] = ci; sd = nsd; }
         }
         const double sc = sd > minval ? 1 / sd : 0.;
-        col[i] *= sc;
+        col[32 * i] *= sc;
     }
     double f1[9], f2[9];
+    const double c7 = col[32 * 7], c8 = col[32 * 8];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) { f1[j] = __shfl_sync(full, col[7], base + j); f2[j] = __shfl_sync(full, col[8], base + j); }
+    for (int j = 0; j < 9; ++j) { f1[j] = __shfl_sync(full, c7, base + j); f2[j] = __shfl_sync(full, c8, base + j); }
     if (kcol == 0 && lane < 27) nm_out[g] = ok ? fm7_finish(f1, f2, nm, F[g]) : 0;
 }
 
@@ -283,7 +292,7 @@ fundmat_kernel(RansacScratch R) {
         // ---- every warp: solve its three samples ---------------------------------------------------------
         const int w0 = wid * RS_GROUPS;
         if (sh.found[w0] == 1)                         // samples are drawn in order: none of the later ones without the first
-            run_7point_warp3(sh.ms1 + w0, sh.ms2 + w0, sh.found + w0, sh.F + w0, sh.nmodels + w0);
+            run_7point_warp3(sh.ms1 + w0, sh.ms2 + w0, sh.found + w0, sh.F + w0, sh.nmodels + w0, sh.svd[wid]);
         __syncthreads();
         // ---- OpenCV's sequential loop over the iterations of this round: the whole CTA scores one sample's models,
         //      thread 0 does the "best so far / update niters" bookkeeping; samples beyond the (shrinking) iteration
@@ -433,6 +442,7 @@ fm7_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, int n_s
     __shared__ Pt2f s1[RS_BATCH][7], s2[RS_BATCH][7];
     __shared__ double sF[RS_BATCH][27];
     __shared__ int sv[RS_BATCH], sn[RS_BATCH];
+    __shared__ double s_svd[RS_WARPS][16 * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int w0 = wid * RS_GROUPS;
     const int set0 = (blockIdx.x * RS_WARPS + wid) * RS_GROUPS;
@@ -447,7 +457,7 @@ fm7_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, int n_s
         if (lane < 27) sF[w0 + g][lane] = 0;
     }
     __syncwarp();
-    run_7point_warp3(s1 + w0, s2 + w0, sv + w0, sF + w0, sn + w0);
+    run_7point_warp3(s1 + w0, s2 + w0, sv + w0, sF + w0, sn + w0, s_svd[wid]);
     __syncwarp();
     for (int g = 0; g < RS_GROUPS; ++g) {
         const int set = set0 + g;
