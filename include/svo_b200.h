@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SVO_B200_ABI_VERSION 3
+#define SVO_B200_ABI_VERSION 4
 
 typedef enum svo_status {
     SVO_OK = 0,
@@ -109,6 +109,12 @@ typedef struct svo_config {
     int32_t pyr_mode;             /* how CImagePyramid::buildPyramidFast halves an octave (stage1_rectify.cpp:82-83):
                                      0 = as MRPT 1.x picks (2x2 rounded average when the width is a multiple of 16,
                                      cvPyrDown otherwise), 1 = always the 2x2 average, 2 = always cv::pyrDown */
+    /* detector (ABI version 4) */
+    int32_t detect_method;        /* TDetectParams::TDMethod (libstereo-odometry.h:388): 1 = dmFAST_ORB (stage2_detect.cpp:502-515,
+                                     the named path), 0 = dmORB: the full multi-scale cv::ORB::detectAndCompute (:458-496) with
+                                     1.5 x orb_nfeats features (with NMS), Harris score, oriented + steered BRIEF; keypoints
+                                     then carry float coordinates, angle and octave.  n_octaves must be 1 with dmORB */
+    int32_t orb_nlevels;          /* params_detect.orb_nlevels: pyramid levels of cv::ORB (8) */
 } svo_config;
 
 /* POD mirror of TStereoOdometryResult (libstereo-odometry.h:235-264).  detected_* / stereo_matches describe octave 0
@@ -359,6 +365,15 @@ int svo_fundmat_7point(svo_ctx* ctx, const float* p1, const float* p2, int32_t n
  * plane 0 = the 7x7 sigma=2 blur cv::ORB::compute applies (stage2_detect.cpp:512), plane 1 = FAST score
  * after 3x3 NMS and the 31-px border filter (0 = no corner).  out: height*width bytes, tightly packed. */
 int svo_get_plane(svo_ctx* ctx, int32_t slot, int32_t side, int32_t plane, uint8_t* out);
+
+/* parity seams of the dmORB detector (svo_config.detect_method = 0, stage2_detect.cpp:458-496):
+ * svo_get_orb_raw_keypoints: the keypoint vector cv::ORB::detectAndCompute returned for (slot, side) in the last step, i.e.
+ *   BEFORE the reference's m_non_max_sup / m_update_indexes (cv::KeyPoint layout: pt, size, angle, response, octave).
+ * svo_get_orb_level: size of pyramid level `level` (w, h; out may be NULL) and one of its planes: plane 0 = the level image
+ *   (cv::resize INTER_LINEAR_EXACT from the level below; levels >= 1, kept per batch item: meaningful after svo_detect or a
+ *   batch whose item 0 is this slot), plane 1 = its 7x7 sigma-2 blur.  out: h*w bytes, tightly packed. */
+int svo_get_orb_raw_keypoints(svo_ctx* ctx, int32_t slot, int32_t side, svo_keypoint* out, int32_t cap);
+int svo_get_orb_level(svo_ctx* ctx, int32_t slot, int32_t side, int32_t level, int32_t plane, uint8_t* out, int32_t* w, int32_t* h);
 
 /* ---- introspection -------------------------------------------------------------------------- */
 int svo_abi_version(void);

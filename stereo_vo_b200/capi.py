@@ -36,7 +36,7 @@ EXPORTS = [
     "svo_get_projected_coords", "svo_set_this_frame_as_kf", "svo_reset_ids", "svo_set_ids", "svo_set_max_match_id",
     "svo_get_keypoints_oct", "svo_get_descriptors_oct", "svo_get_matches_oct", "svo_get_match_ids_oct",
     "svo_get_tracked_pairs_oct", "svo_get_octave_info", "svo_get_octave_stats", "svo_get_pyramid_plane",
-    "svo_track", "svo_optimize", "svo_build_pyramid_device",
+    "svo_track", "svo_optimize", "svo_build_pyramid_device", "svo_get_orb_raw_keypoints", "svo_get_orb_level",
 ]
 
 
@@ -53,7 +53,7 @@ class Config(C.Structure):
                 ("use_previous_pose_as_initial", C.c_int32), ("vo_use_matches_ids", C.c_int32), ("sort_mode", C.c_int32),
                 ("match_method", C.c_int32), ("if_match_method", C.c_int32), ("ifm_win_w", C.c_int32),
                 ("ifm_win_h", C.c_int32), ("orb_max_distance", C.c_double),
-                ("n_octaves", C.c_int32), ("pyr_mode", C.c_int32)]
+                ("n_octaves", C.c_int32), ("pyr_mode", C.c_int32), ("detect_method", C.c_int32), ("orb_nlevels", C.c_int32)]
 
 
 class Camera(C.Structure):
@@ -288,6 +288,20 @@ class Context:
         ir = np.zeros(self.kp_cap, np.uint8)
         n = self._check(lib().svo_get_track_candidates(self._h, slot, _vp(q), _vp(tl), _vp(tr), _vp(il), _vp(ir), self.kp_cap))
         return q[:n].copy(), tl[:n].copy(), tr[:n].copy(), il[:n].copy(), ir[:n].copy()
+
+    def orb_raw_keypoints(self, slot=0, side=0):
+        """cv::ORB::detectAndCompute's keypoints of the last step (dmORB), before m_non_max_sup / m_update_indexes"""
+        cap = 4 * self.cfg.orb_nfeats + 256
+        out = np.zeros(cap, KEYPOINT)
+        n = self._check(lib().svo_get_orb_raw_keypoints(self._h, slot, side, _vp(out), cap))
+        return out[:n].copy()
+
+    def orb_level(self, slot=0, side=0, level=1, plane=0):
+        w, h = C.c_int32(0), C.c_int32(0)
+        self._check(lib().svo_get_orb_level(self._h, slot, side, level, plane, None, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self._check(lib().svo_get_orb_level(self._h, slot, side, level, plane, _vp(out), C.byref(w), C.byref(h)))
+        return out
 
     def plane(self, slot=0, side=0, plane=0):
         out = np.zeros((self.cfg.height, self.cfg.width), np.uint8)

@@ -9,6 +9,7 @@
 #include "prepare.cuh"
 #include "ransac.cuh"
 #include "svo_internal.cuh"
+#include "orb.cuh"
 
 #include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler (nsys / ncu --nvtx) is attached
 
@@ -62,6 +63,7 @@ struct svo_ctx {
     Pools PG;
     GnScratch GG;
     OctaveList OL;
+    OrbDev orb;                 // detect_method == 0 (dmORB): pyramid levels and scratch of cv::ORB::detectAndCompute
     cudaStream_t stream = nullptr;
     std::vector<void*> dev_allocs;
     std::vector<void*> host_allocs;
@@ -280,6 +282,12 @@ int enqueue_items(svo_ctx* c, int a, int n, const uint8_t* d_left, const uint8_t
     if (c->n_oct > 1) return enqueue_octaves(c, P, RS, a, n, d_left, d_right, stride, image_pitch, st, L);
     {
         NvtxRange r("_stg2");
+        if (c->cfg.detect_method == 0) {
+            CU(c, launch_orb_detect(P, c->orb, n, d_left, d_right, stride, image_pitch, a, c->d_occ + img2 * c->occ_words, c->occ_words,
+                                    c->d_sort_scratch + img2 * c->cfg.max_corners,
+                                    c->d_list_scratch + img2 * 3 * (c->cfg.max_corners / 16 + 2), st, &L));
+            if (t) { t->mark(st); t->mark(st); t->mark(st); }
+        } else
         CU(c, launch_detect(P, n, d_left + a * image_pitch, d_right + a * image_pitch, stride, image_pitch, c->pitch,
                             c->d_occ + img2 * c->occ_words, c->occ_words, c->d_sort_scratch + img2 * c->cfg.max_corners,
                             c->d_list_scratch + img2 * 3 * (c->cfg.max_corners / 16 + 2),
@@ -297,7 +305,8 @@ int enqueue_items(svo_ctx* c, int a, int n, const uint8_t* d_left, const uint8_t
         CU(c, launch_consistency(P, n, st, &L, t));
     }
     NvtxRange r("_stg5");
-    CU(c, launch_gn(P, c->G, n, GN_FROM_TRACKED, /*custom pose=*/0, /*assume_fast_kps=*/1, st, &L, t));
+    // dmORB keypoints of different levels can share a grid cell: the aux NMS of S5:465-474 really runs
+    CU(c, launch_gn(P, c->G, n, GN_FROM_TRACKED, /*custom pose=*/0, /*assume_fast_kps=*/c->cfg.detect_method == 0 ? 0 : 1, st, &L, t));
     return SVO_OK;
 }
 
@@ -476,6 +485,8 @@ void svo_default_config(svo_config* cfg) {
     cfg->orb_max_distance = 40.0;
     cfg->n_octaves = 1;                  // SURVEY Appendix C (the reference's ctor default is 3, stage1_rectify.cpp:28)
     cfg->pyr_mode = 0;                   // as MRPT picks: 2x2 average when width % 16 == 0, cvPyrDown otherwise
+    cfg->detect_method = 1;              // dmFAST_ORB, the named path (the reference's ctor default is dmFASTER, unimplemented there)
+    cfg->orb_nlevels = 8;                // TDetectParams ctor (libstereo-odometry.h:397)
 }
 
 const char* svo_last_error(const svo_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -501,6 +512,17 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     if (cfg->pyr_mode < 0 || cfg->pyr_mode > 2) return fail(nullptr, SVO_ERR_ARG, "pyr_mode must be 0 (as MRPT), 1 (2x2 average) or 2 (pyrDown)");
     if ((cfg->width >> (n_oct - 1)) < 64 || (cfg->height >> (n_oct - 1)) < 64)
         return fail(nullptr, SVO_ERR_ARG, "the smallest octave must be at least 64 x 64");
+    if ((cfg->detect_method | 1) != 1) return fail(nullptr, SVO_ERR_ARG, "Unknown detection method (dmORB = 0 or dmFAST_ORB = 1)");
+    if (cfg->detect_method == 0) {
+        if (n_oct != 1) return fail(nullptr, SVO_ERR_ARG, "dmORB builds its own pyramid: n_octaves must be 1 (stage2_detect.cpp:460)");
+        if (cfg->orb_nlevels < 1 || cfg->orb_nlevels > kOrbMaxLevels) return fail(nullptr, SVO_ERR_ARG, "orb_nlevels must be within [1, 8]");
+        if (cfg->match_method != 0 || cfg->if_match_method != 0)
+            return fail(nullptr, SVO_ERR_ARG, "dmORB is built for the brute-force matchers (smDescBF / ifmDescBF) only");
+        if (cfg->sort_mode != 0) return fail(nullptr, SVO_ERR_ARG, "sort_mode 1 is not available with dmORB");
+        const OrbLevels G = orb_levels(cfg->width, cfg->height, cfg->orb_nlevels, 1);
+        if (G.w[cfg->orb_nlevels - 1] < 64 || G.h[cfg->orb_nlevels - 1] < 64)
+            return fail(nullptr, SVO_ERR_ARG, "the smallest ORB level must be at least 64 x 64 (lower orb_nlevels)");
+    }
     int quotas[kMaxOctaves];
     octave_quotas(cfg->orb_nfeats, n_oct, quotas);    // kps_to_detect[], stage2_detect.cpp:404-407
     const int quota = quotas[0];                      // 2 * orb_nfeats for nOctaves = 1
@@ -534,6 +556,7 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     p.match_method = cfg->match_method; p.ifm_method = cfg->if_match_method;
     p.ifm_win_w = cfg->ifm_win_w; p.ifm_win_h = cfg->ifm_win_h;
     p.rbr_max_distance = (int32_t)(size_t)cfg->orb_max_distance;
+    p.detect_method = cfg->detect_method;
 
     const int S = cfg->max_seqs + 1;
     c->n_slots_alloc = S;
@@ -550,6 +573,14 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     DA(P.tile_list, S * 2 * (size_t)tiles_x_of(cfg->width) * tiles_y_of(cfg->height) * kTileCap);
     DA(P.cand_pos, (size_t)S * 2 * cfg->max_corners); DA(P.n_cand, S * 2);
     DA(P.kp, S * 4 * cap); DA(P.desc, S * 4 * cap * 2); DA(P.n_kp, S * 4);
+    P.kpf = nullptr; P.kpo = nullptr;
+    if (cfg->detect_method == 0) {
+        DA(P.kpf, S * 4 * cap); DA(P.kpo, S * 4 * cap);
+        // S2:460-464: more features when the NMS thins them out afterwards
+        const int n_extract = cfg->non_maximal_suppression ? (int)(size_t)(1.5 * cfg->orb_nfeats) : cfg->orb_nfeats;
+        cudaError_t e2 = alloc_orb(c->orb, p, S, cfg->orb_nlevels, n_extract, c->dev_allocs);
+        if (e2 != cudaSuccess) { int rc = cuda_fail(nullptr, e2, "alloc_orb"); svo_destroy(c); return rc; }
+    }
     DA(P.match, S * 2 * cap); DA(P.n_match, S * 2); DA(P.mdesc, S * 4 * cap * 2); DA(P.match_id, S * 2 * cap);
     DA(P.lr_best, S * cap); DA(P.tr_best, S * 2 * cap); DA(P.tcand, S * cap); DA(P.n_tcand, S);
     DA(P.inl, S * 2 * cap); DA(P.n_inl, S * 2); DA(P.tracked, S * cap); DA(P.n_tracked, S);
@@ -1132,6 +1163,21 @@ int svo_get_keypoints_oct(svo_ctx* c, int32_t slot, int32_t octave, int32_t whic
     const size_t f = frame_idx(slot, frame_buf(s, which), side);
     int n = 0;
     CU(c, cudaMemcpy(&n, Pk->n_kp + f, sizeof(int), cudaMemcpyDeviceToHost));
+    if (Pk->kpf) {                                     // dmORB: cv::ORB's keypoints
+        std::vector<float4> kf(n);
+        std::vector<int32_t> ko(n);
+        if (n) {
+            CU(c, cudaMemcpy(kf.data(), Pk->kpf + f * Pk->p.kp_cap, n * sizeof(float4), cudaMemcpyDeviceToHost));
+            CU(c, cudaMemcpy(ko.data(), Pk->kpo + f * Pk->p.kp_cap, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        }
+        for (int i = 0; i < n && i < cap; ++i) {
+            svo_keypoint k;
+            k.x = kf[i].x; k.y = kf[i].y; k.response = kf[i].z; k.angle = kf[i].w; k.octave = ko[i];
+            k.size = (float)kOrbPatch * c->orb.L[ko[i]].scale; k.class_id = -1;
+            out[i] = k;
+        }
+        return n;
+    }
     std::vector<int2> tmp(n);
     if (n) CU(c, cudaMemcpy(tmp.data(), Pk->kp + f * Pk->p.kp_cap, n * sizeof(int2), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n && i < cap; ++i) {
@@ -1446,6 +1492,52 @@ int svo_get_plane(svo_ctx* c, int32_t slot, int32_t side, int32_t plane, uint8_t
     return SVO_OK;
 }
 
+int svo_get_orb_raw_keypoints(svo_ctx* c, int32_t slot, int32_t side, svo_keypoint* out, int32_t cap) {
+    if (!c) return SVO_ERR_ARG;
+    if (c->cfg.detect_method != 0) return fail(c, SVO_ERR_STATE, "the context does not run dmORB");
+    if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (side | 1) != 1) return fail(c, SVO_ERR_ARG, "bad slot/side");
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const size_t im = img_idx(slot, side);
+    int n = 0;
+    CU(c, cudaMemcpy(&n, c->orb.n_raw + im, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<float4> kf(n);
+    std::vector<int32_t> ko(n);
+    if (n) {
+        CU(c, cudaMemcpy(kf.data(), c->orb.raw + im * c->orb.raw_cap, n * sizeof(float4), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(ko.data(), c->orb.raw_oct + im * c->orb.raw_cap, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < n && i < cap; ++i) {
+        svo_keypoint k;
+        k.x = kf[i].x; k.y = kf[i].y; k.response = kf[i].z; k.angle = kf[i].w; k.octave = ko[i];
+        k.size = (float)kOrbPatch * c->orb.L[ko[i]].scale; k.class_id = -1;
+        out[i] = k;
+    }
+    return n;
+}
+
+int svo_get_orb_level(svo_ctx* c, int32_t slot, int32_t side, int32_t level, int32_t plane, uint8_t* out, int32_t* w, int32_t* h) {
+    if (!c) return SVO_ERR_ARG;
+    if (c->cfg.detect_method != 0) return fail(c, SVO_ERR_STATE, "the context does not run dmORB");
+    if ((!valid_slot(c, slot) && slot != c->hidden_slot) || (side | 1) != 1 || level < 0 || level >= c->orb.n_levels || (plane | 1) != 1)
+        return fail(c, SVO_ERR_ARG, "bad slot/side/level/plane");
+    const OrbLevelDev& L = c->orb.L[level];
+    if (w) *w = L.w;
+    if (h) *h = L.h;
+    if (!out) return SVO_OK;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const uint8_t* src;
+    if (plane == 1) src = L.blur + img_idx(slot, side) * (size_t)L.pitch * L.h;
+    else {
+        if (level == 0) return fail(c, SVO_ERR_ARG, "level 0 is the caller's image");
+        // level images are kept per batch item of the last step: the per-stage entry (svo_detect) uses item 0
+        src = (side ? L.imgR : L.imgL);
+    }
+    CU(c, cudaMemcpy2D(out, L.w, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return SVO_OK;
+}
+
 // ---- per-stage entries ---------------------------------------------------------------------------
 int svo_detect(svo_ctx* c, const uint8_t* img, size_t stride, svo_keypoint* out_kps, uint8_t* out_desc, int32_t cap) {
     if (!c) return SVO_ERR_ARG;
@@ -1461,6 +1553,10 @@ int svo_detect(svo_ctx* c, const uint8_t* img, size_t stride, svo_keypoint* out_
     CU(c, cudaMemcpy2DAsync(c->d_stageR, c->pitch, img, stride, W, H, cudaMemcpyHostToDevice, c->stream));
     CU(c, launch_begin_step(c->P, 1, nullptr, c->stream));
     int L = 1;
+    if (c->cfg.detect_method == 0)
+        CU(c, launch_orb_detect(c->P, c->orb, 1, c->d_stageL, c->d_stageR, c->pitch, plane, 0, c->d_occ, c->occ_words,
+                                c->d_sort_scratch, c->d_list_scratch, c->stream, &L));
+    else
     CU(c, launch_detect(c->P, 1, c->d_stageL, c->d_stageR, c->pitch, plane, c->pitch, c->d_occ, c->occ_words,
                         c->d_sort_scratch, c->d_list_scratch, c->d_key_scratch, c->stream, &L));
     c->launches += L;

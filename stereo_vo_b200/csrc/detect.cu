@@ -795,6 +795,19 @@ static bool make_plane_map(CUtensorMap* tm, const uint8_t* d_plane, int pitch, i
     return make_plane_map(tm, d_plane, pitch, H, n_images, (size_t)pitch, (size_t)pitch * H, box_w, box_h);
 }
 
+cudaError_t launch_fast_blur_only(const Pools& PL, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
+                                  size_t image_pitch, int pitch_out, cudaStream_t st) {
+    const dim3 g1((PL.p.W + TW - 1) / TW, (PL.p.H + TH - 1) / TH, 2 * n);
+    CUtensorMap tmL, tmR;
+    if (make_image_map(&tmL, d_left, PL.p.W, PL.p.H, n, stride, image_pitch) && make_image_map(&tmR, d_right, PL.p.W, PL.p.H, n, stride, image_pitch))
+        fast_blur_kernel<true><<<g1, K1_THREADS, 0, st>>>(PL, d_left, d_right, stride, image_pitch, pitch_out, tmL, tmR);
+    else {
+        memset(&tmL, 0, sizeof(tmL));
+        fast_blur_kernel<false><<<g1, K1_THREADS, 0, st>>>(PL, d_left, d_right, stride, image_pitch, pitch_out, tmL, tmL);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_detect(const Pools& P, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
                           size_t image_pitch, int pitch_out, uint32_t* occ_scratch, int occ_words_per_img,
                           uint32_t* sort_scratch, uint2* list_scratch, uint32_t* key_scratch, cudaStream_t st, int* launches,

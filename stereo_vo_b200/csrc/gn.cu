@@ -410,17 +410,15 @@ gn_kernel(Pools P, GnScratch G, int external, int use_custom_pose, int assume_fa
     if (external == GN_FROM_TRACKED) {
         const int4* mp = P.match + pair_idx(slot, prev) * cap;
         const int4* mc = P.match + pair_idx(slot, cur) * cap;
-        const int2* kpl = P.kp + frame_idx(slot, prev, 0) * cap;
-        const int2* kpr = P.kp + frame_idx(slot, prev, 1) * cap;
-        const int2* kcl = P.kp + frame_idx(slot, cur, 0) * cap;
-        const int2* kcr = P.kp + frame_idx(slot, cur, 1) * cap;
+        const size_t fpl = frame_idx(slot, prev, 0) * cap, fpr = frame_idx(slot, prev, 1) * cap;
+        const size_t fcl = frame_idx(slot, cur, 0) * cap, fcr = frame_idx(slot, cur, 1) * cap;
         for (int i = tid; i < T; i += GN_THREADS) {
             const int2 tp = P.tracked[base + i];
             const int4 a = mp[tp.x], b = mc[tp.y];
-            const int2 pl = kpl[a.x], pr = kpr[a.y], cl = kcl[b.x], cr = kcr[b.y];
-            G.prev[base + i] = make_float4((float)(pl.x & 0xFFFF), (float)((unsigned)pl.x >> 16), (float)(pr.x & 0xFFFF), (float)pl.y);
-            G.obs[base + i] = make_float4((float)(cl.x & 0xFFFF), (float)((unsigned)cl.x >> 16),
-                                          (float)(cr.x & 0xFFFF), (float)((unsigned)cr.x >> 16));
+            const float2 pl = kp_xy(P, fpl, a.x), pr = kp_xy(P, fpr, a.y), cl = kp_xy(P, fcl, b.x), cr = kp_xy(P, fcr, b.y);
+            const float resp = P.kpf ? P.kpf[fpl + a.x].z : (float)P.kp[fpl + a.x].y;     // KeyPoint::response of the previous-left point
+            G.prev[base + i] = make_float4(pl.x, pl.y, pr.x, resp);
+            G.obs[base + i] = make_float4(cl.x, cl.y, cr.x, cr.y);
         }
     }
     for (int i = tid; i < T; i += GN_THREADS) G.residual[base + i] = DBL_MAX;   // S5:296

@@ -225,8 +225,6 @@ lr_filter_kernel(Pools P) {
     const size_t fL = frame_idx(slot, cur, 0), fR = frame_idx(slot, cur, 1);
     const int nL = P.n_kp[fL], nR = P.n_kp[fR];
     const uint32_t* __restrict__ best = P.lr_best + (size_t)slot * cap;
-    const int2* __restrict__ kpL = P.kp + fL * cap;
-    const int2* __restrict__ kpR = P.kp + fR * cap;
     const int tid = threadIdx.x;
     const int n_in = (nR > 0) ? nL : 0;   // BFMatcher returns no matches for an empty train set
     const int orb_th = slot_orb_th(P.p, st);          // m_current_orb_th (S3:164)
@@ -267,10 +265,10 @@ lr_filter_kernel(Pools P) {
             dist = (int)(b >> 16);
             keep = 1;
             if (P.p.robust_1to1 && (int)(s_rc[t] & 0xFFFFu) != k) keep = 0;
-            const int2 l = kpL[k], r = kpR[t];
-            // S3:162-165: float differences truncated to int (coordinates are integers here)
-            const int diff = (int)((float)((unsigned)l.x >> 16) - (float)((unsigned)r.x >> 16));
-            const int disp = (int)((float)(l.x & 0xFFFF) - (float)(r.x & 0xFFFF));
+            const float2 l = kp_xy(P, fL * cap, k), r = kp_xy(P, fR * cap, t);
+            // S3:162-165: float differences truncated to int
+            const int diff = (int)__fsub_rn(l.y, r.y);
+            const int disp = (int)__fsub_rn(l.x, r.x);
             if ((double)abs(diff) > P.p.max_y_diff || (float)dist > (float)orb_th ||
                 (double)disp < 1.0 || (double)disp > (double)P.p.W) keep = 0;
         }

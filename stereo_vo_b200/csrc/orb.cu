@@ -1,0 +1,461 @@
+// orb.cu -- the dmORB detector on the device: cv::ORB::detectAndCompute as the reference calls it
+// (stage2_detect.cpp:458-496: nfeatures = 1.5 x orb_nfeats with NMS, scale 1.2, orb_nlevels levels, edge 31, HARRIS_SCORE,
+// patch 31, fastThreshold = m_current_fast_th), followed by the reference's own m_non_max_sup (S2:296-370) and
+// m_update_indexes (S2:65-130) on the float keypoints.
+//
+//   orb_resize_kernel    level l from level l-1, cv::resize(INTER_LINEAR_EXACT) (8.8 fixed point, tables from the host)
+//   fast_blur_kernel     (detect.cu) per level: FAST + 3x3 NMS + 31-px border filter as tile lists, 7x7 sigma-2 blur plane
+//   orb_select_kernel    one CTA per image, level after level: row-major corner list -> retainBest(2 N_l) by FAST response
+//                        -> Harris -> retainBest(N_l) -> IC angle -> pt * scale          (computeKeyPoints)
+//   orb_nms_sort_kernel  one CTA per image: std::sort by response + occupancy grid + std::sort by row (emulated libstdc++)
+//   orb_describe_kernel  one warp per surviving keypoint: steered BRIEF on the blurred level   (computeOrbDescriptors)
+//
+// retainBest is std::nth_element + std::partition on the keypoint vector; the order they leave decides which equal
+// responses survive and the order of the output, so both are emulated (orb_core.cuh), the large partitions of
+// nth_element with the block- / warp-cooperative partition of introsort_emul.cuh.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "orb.cuh"
+
+namespace svo {
+
+namespace {
+
+constexpr int OT = 256;                   // threads of the per-image kernels
+
+__device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int wsum = (lane < OT / 32) ? s_warp[lane] : 0;
+    int wincl = wsum;
+#pragma unroll
+    for (int o = 1; o < OT / 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += t;
+    }
+    const int wexcl = __shfl_sync(0xffffffffu, wincl - wsum, wid);
+    total = __shfl_sync(0xffffffffu, wincl, OT / 32 - 1);
+    __syncthreads();
+    return wexcl + incl - v;
+}
+
+// ---- level l from level l-1 ------------------------------------------------------------------------------------------
+// src: by batch item (level 0 = the caller's images, levels >= 1 = the level planes); 4 output pixels per thread
+__global__ void __launch_bounds__(128)
+orb_resize_kernel(const uint8_t* __restrict__ srcL, const uint8_t* __restrict__ srcR, size_t sstride, size_t simage_pitch, int sw, int sh,
+                  OrbLevelDev D) {
+    const int item = blockIdx.z >> 1, side = blockIdx.z & 1;
+    const int y = blockIdx.y, x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x4 >= D.pitch) return;
+    const uint8_t* src = (side ? srcR : srcL) + (size_t)item * simage_pitch;
+    uint8_t* dst = (side ? D.imgR : D.imgL) + (size_t)item * D.pitch * D.h + (size_t)y * D.pitch;
+    const int yo = D.yofs[y], yc = D.yc1[y];
+    const uint8_t* r0 = src + (size_t)yo * sstride;
+    const uint8_t* r1 = r0 + sstride;
+    uint32_t w = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int x = x4 + q;
+        uint32_t v = 0;
+        if (x < D.w) {
+            const int xo = D.xofs[x], xc = D.xc1[x];
+            const uint32_t h0 = r0[xo] * (256 - xc) + r0[xo + 1] * xc;          // ufixedpoint16 (8.8)
+            const uint32_t h1 = r1[xo] * (256 - xc) + r1[xo + 1] * xc;
+            v = (h0 * (256 - yc) + h1 * yc + (1u << 15)) >> 16;                 // ufixedpoint32 -> uint8, round half up
+        }
+        w |= v << (8 * q);
+    }
+    *reinterpret_cast<uint32_t*>(dst + x4) = w;
+}
+
+// ---- std::nth_element with the block ------------------------------------------------------------------------------------
+// a[0..n): indices; all threads call.  tmp: n words, s_blk: 64 * (OT / 32) ints (shared), s_cut: one int (shared)
+template <class C>
+__device__ void nth_element_block(const C& c, uint32_t* a, int n, int nth, uint32_t* tmp, int* s_blk, int* s_cut) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n == 0 || nth == n) return;
+    int first = 0, last = n;
+    int depth = 2 * floor_log2(n);
+    uint16_t* pos16 = reinterpret_cast<uint16_t*>(tmp);
+    while (last - first > 64 && depth > 0 && n < 65536) {
+        --depth;
+        if (tid == 0) median_to_first_(c, a, first, first + 1, first + (last - first) / 2, last - 1);
+        __syncthreads();
+        int cut;
+        if (last - first >= kBlockPartMin) {
+            cut = block_unguarded_partition(c, a, first, last, pos16, pos16 + n, s_blk);
+        } else {
+            if (warp == 0) {
+                const int cw = warp_unguarded_partition(c, a, first, last, s_blk);
+                if (lane == 0) *s_cut = cw;
+            }
+            __syncthreads();
+            cut = *s_cut;
+            __syncthreads();
+        }
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    __syncthreads();
+    if (tid == 0) introselect_seq(c, a, first, last, nth, depth);
+    __syncthreads();
+}
+
+// KeyPointsFilter::retainBest on idx[0..n) (block-wide); returns the new size on every thread
+__device__ int retain_best_block(uint32_t* idx, int n, const float* resp, int n_points, uint32_t* tmp, int* s_blk, int* s_cut) {
+    if (!(n_points >= 0 && n > n_points)) return n;
+    if (n_points == 0) return 0;
+    nth_element_block(OrbRespGreater{resp}, idx, n, n_points - 1, tmp, s_blk, s_cut);
+    if (threadIdx.x == 0) {
+        const float ambiguous = resp[idx[n_points - 1]];
+        *s_cut = partition_seq(OrbRespGE{resp, ambiguous}, idx, n_points, n);
+    }
+    __syncthreads();
+    const int m = *s_cut;
+    __syncthreads();
+    return m;
+}
+
+// ---- computeKeyPoints -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OT)
+orb_select_kernel(Pools P, OrbDev D, const uint8_t* __restrict__ img0L, const uint8_t* __restrict__ img0R, size_t stride0,
+                  size_t image_pitch0, int item0, int smem_cap) {
+    extern __shared__ __align__(16) uint32_t osm[];
+    uint32_t* s_idx = osm;                                           // [smem_cap]
+    float* s_resp = reinterpret_cast<float*>(osm + smem_cap);       // [smem_cap]
+    __shared__ int s_warp[OT / 32];
+    __shared__ int s_blk[64 * (OT / 32)];
+    __shared__ int s_cut;
+    const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
+    const int slot = P.slots[item];
+    const int tid = threadIdx.x;
+    const size_t im = img_idx(slot, side);
+    uint32_t* g_idx = D.idx + im * D.cap;
+    float* g_resp = D.resp + im * D.cap;
+    uint32_t* pos = D.pos + im * D.cap;
+    uint32_t* tmp = D.tmp + im * D.cap;
+    float4* raw = D.raw + im * D.raw_cap;
+    int32_t* raw_oct = D.raw_oct + im * D.raw_cap;
+    int n_out = 0;
+    bool overflow = false;
+
+    for (int l = 0; l < D.n_levels; ++l) {
+        const OrbLevelDev& Lv = D.L[l];
+        const int W = Lv.w, H = Lv.h;
+        const uint8_t* img;
+        int step;
+        if (l == 0) { img = (side ? img0R : img0L) + (size_t)(item0 + item) * image_pitch0; step = (int)stride0; }
+        else { img = (side ? Lv.imgR : Lv.imgL) + (size_t)(item0 + item) * Lv.pitch * H; step = Lv.pitch; }
+        // A. the level's FAST corners in row-major order (cv::FAST's keypoint order) from fast_blur_kernel's tile lists
+        const int tiles_x = tiles_x_of(W), tiles_y = tiles_y_of(H);
+        const uint16_t* __restrict__ seg = Lv.tile_seg + im * (size_t)tiles_x * tiles_y * kTileH;
+        const uint16_t* __restrict__ tlst = Lv.tile_list + im * (size_t)tiles_x * tiles_y * kTileCap;
+        const int total_segs = H * tiles_x;
+        const int spt = (total_segs + OT - 1) / OT;
+        const int g_lo = min(total_segs, tid * spt), g_hi = min(total_segs, g_lo + spt);
+        int cnt = 0;
+        for (int g = g_lo; g < g_hi; ++g) cnt += (int)(seg[g] & 0xFFu);
+        int total;
+        int o = block_excl_scan(cnt, s_warp, total);
+        if (total > D.cap) overflow = true;
+        const int n = min(total, D.cap);
+        uint32_t* idx = n <= smem_cap ? s_idx : g_idx;
+        float* resp = n <= smem_cap ? s_resp : g_resp;
+        if (cnt) {
+            for (int g = g_lo; g < g_hi; ++g) {
+                const uint32_t sg = seg[g];
+                const int c = (int)(sg & 0xFFu);
+                if (!c) continue;
+                const int y = g / tiles_x, tx = g - y * tiles_x;
+                const uint32_t code = ((uint32_t)(y & (kBandH - 1)) << 30) |
+                                      (((uint32_t)(y / kTileH) * tiles_x + tx) << 9 | (uint32_t)((y & (kTileH - 1)) / kBandH) << 6) + (sg >> 8);
+                for (int k = 0; k < c; ++k, ++o)
+                    if (o < n) idx[o] = code + k;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += OT) {
+            const uint32_t code = idx[i], ent = code & 0x3FFFFFFFu;
+            const uint32_t v = tlst[ent];
+            const int tile = (int)(ent >> 9), ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y = ty * kTileH + (int)((ent >> 6) & 7u) * kBandH + (int)(code >> 30);
+            idx[i] = (uint32_t)i;
+            resp[i] = (float)(v >> 8);                                   // cv::FAST: response = score
+            pos[i] = ((uint32_t)y << 16) | (uint32_t)(tx * kTileW + (int)(v & 0xFFu));
+        }
+        __syncthreads();
+        // B. retainBest(2 * featuresNum) by FAST response (HARRIS_SCORE keeps twice as many for the second cull)
+        const int n2 = retain_best_block(idx, n, resp, 2 * Lv.nfeat, tmp, s_blk, &s_cut);
+        // C. HarrisResponses of the survivors
+        for (int k = tid; k < n2; k += OT) {
+            const uint32_t i = idx[k], p = pos[i];
+            resp[i] = orb_harris(img, step, (int)(p & 0xFFFFu), (int)(p >> 16));
+        }
+        __syncthreads();
+        // D. retainBest(featuresNum) by Harris response
+        const int n3 = retain_best_block(idx, n2, resp, Lv.nfeat, tmp, s_blk, &s_cut);
+        // E. ICAngles, pt *= scale; appended behind the coarser... finer levels (allKeypoints is in level order)
+        for (int k = tid; k < n3; k += OT) {
+            const int q = n_out + k;
+            if (q >= D.raw_cap) continue;
+            const uint32_t i = idx[k], p = pos[i];
+            const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
+            const float ang = orb_ic_angle(img, step, x, y);
+            raw[q] = make_float4(__fmul_rn((float)x, Lv.scale), __fmul_rn((float)y, Lv.scale), resp[i], ang);
+            raw_oct[q] = l;
+        }
+        if (n_out + n3 > D.raw_cap) overflow = true;
+        n_out = min(n_out + n3, D.raw_cap);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        D.n_raw[im] = n_out;
+        if (overflow) P.state[slot].status = -3;       // SVO_ERR_CAPACITY
+    }
+}
+
+// ---- m_non_max_sup + m_update_indexes on detectAndCompute's keypoints ---------------------------------------------------
+struct IndexedAscComp {                 // KpRowSorter on float rows: comp(a, b) = y[a] < y[b]  (libstereo-odometry.h:120-127)
+    const float* key;
+    __device__ __forceinline__ bool lt(uint32_t a, uint32_t b) const { return key[a] < key[b]; }
+};
+
+__global__ void __launch_bounds__(OT)
+orb_nms_sort_kernel(Pools P, OrbDev D, uint32_t* __restrict__ occ_scratch, int occ_words_per_img, uint32_t* __restrict__ sort_scratch,
+                    uint2* __restrict__ list_scratch) {
+    extern __shared__ __align__(16) uint32_t osm[];
+    const int rc = D.raw_cap;
+    uint32_t* s_a = osm;                                             // [raw_cap] indices sorted by response
+    uint32_t* s_b = osm + rc;                                        // [raw_cap] positions sorted by row
+    float* s_key = reinterpret_cast<float*>(osm + 2 * rc);          // [raw_cap] response, then pt.y of the selection
+    __shared__ int s_cnt[3];
+    __shared__ int s_pos[64 * (OT / 32)];
+    __shared__ int s_nsel;
+    const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
+    const int slot = P.slots[item];
+    const int tid = threadIdx.x;
+    const size_t im = img_idx(slot, side);
+    const float4* __restrict__ raw = D.raw + im * D.raw_cap;
+    const int32_t* __restrict__ raw_oct = D.raw_oct + im * D.raw_cap;
+    const int n = D.n_raw[im];
+    const int list_cap = P.p.max_corners / 16 + 2;
+    uint2* listA = list_scratch + (size_t)blockIdx.x * 3 * list_cap;
+    uint2* listB = listA + list_cap;
+    uint2* listS = listB + list_cap;
+    uint32_t* tmp = sort_scratch + (size_t)blockIdx.x * P.p.max_corners;
+    const int W = P.p.W, H = P.p.H;
+
+    for (int i = tid; i < n; i += OT) { s_a[i] = (uint32_t)i; s_key[i] = raw[i].z; }
+    __syncthreads();
+    int n_sel;
+    if (P.p.nms) {
+        introsort_block(IndexedDescComp{s_key}, s_a, n, listA, listB, listS, s_cnt, tmp, s_pos, n);      // S2:322-324
+        if (tid == 0) {
+            const unsigned cell = (unsigned)(P.p.min_distance / 2.0);     // S2:331
+            const float cell_inv = 1.0f / (float)cell;                     // S2:332
+            const unsigned glx = (unsigned)(1 + W * cell_inv), gly = (unsigned)(1 + H * cell_inv);
+            uint32_t* occ = occ_scratch + (size_t)blockIdx.x * occ_words_per_img;
+            for (unsigned i = 0; i < (glx * gly + 31) / 32; ++i) occ[i] = 0;
+            auto get = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; return (occ[b >> 5] >> (b & 31)) & 1u; };
+            auto set = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; occ[b >> 5] |= 1u << (b & 31); };
+            int c = 0, k = 0;
+            while (c < P.p.quota && c < P.p.kp_cap && k < n) {
+                const uint32_t id = s_a[k++];
+                const float4 kp = raw[id];
+                const unsigned sx = (unsigned)__fmul_rn(kp.x, cell_inv), sy = (unsigned)__fmul_rn(kp.y, cell_inv);
+                if (get(sx, sy)) continue;
+                set(sx, sy);
+                if (sx > 0) set(sx - 1, sy);
+                if (sy > 0) set(sx, sy - 1);
+                if (sx < glx - 1) set(sx + 1, sy);
+                if (sy < gly - 1) set(sx, sy + 1);
+                s_a[c++] = id;
+            }
+            s_nsel = c;
+        }
+        __syncthreads();
+        n_sel = s_nsel;
+    } else {
+        n_sel = min(n, P.p.kp_cap);                   // feats_vector.swap(...)  S2:613
+    }
+    __syncthreads();
+    // m_update_indexes: std::sort of the positions by pt.y
+    for (int k = tid; k < n_sel; k += OT) { s_b[k] = (uint32_t)k; s_key[k] = 0.f; }
+    __syncthreads();
+    for (int k = tid; k < n_sel; k += OT) s_key[k] = raw[s_a[k]].y;
+    __syncthreads();
+    introsort_block(IndexedAscComp{s_key}, s_b, n_sel, listA, listB, listS, s_cnt, tmp, s_pos, n_sel);   // S2:87-89
+    const int cur = P.state[slot].cur;
+    const size_t f = frame_idx(slot, cur, side);
+    float4* __restrict__ kpf = P.kpf + f * (size_t)P.p.kp_cap;
+    int32_t* __restrict__ kpo = P.kpo + f * (size_t)P.p.kp_cap;
+    int2* __restrict__ kp = P.kp + f * (size_t)P.p.kp_cap;
+    for (int i = tid; i < n_sel; i += OT) {
+        const uint32_t id = s_a[s_b[i]];
+        const float4 v = raw[id];
+        kpf[i] = v;
+        kpo[i] = raw_oct[id];
+        kp[i] = make_int2((int)(((unsigned)(int)v.y << 16) | ((unsigned)(int)v.x & 0xFFFFu)), 0);   // truncated copy for index-only readers
+    }
+    if (tid == 0) {
+        P.n_kp[f] = n_sel;
+        P.oct_stats[stat_idx(slot, P.octave, side)] = n_sel;
+        if (side == 0) P.result[slot].detected_left = n_sel; else P.result[slot].detected_right = n_sel;
+    }
+}
+
+// ---- computeOrbDescriptors ------------------------------------------------------------------------------------------------
+struct OrbPattern { int8_t v[256][4]; };
+constexpr OrbPattern make_orb_pattern() {
+    constexpr int pat[256][4] = {
+#include "orb_pattern.inc"
+    };
+    OrbPattern t{};
+    for (int i = 0; i < 256; ++i)
+        for (int k = 0; k < 4; ++k) t.v[i][k] = (int8_t)pat[i][k];
+    return t;
+}
+__device__ const OrbPattern g_orb_pattern = make_orb_pattern();
+
+constexpr int OD_WARPS = 8;
+__global__ void __launch_bounds__(OD_WARPS * 32)
+orb_describe_kernel(Pools P, OrbDev D) {
+    const int item = blockIdx.y >> 1, side = blockIdx.y & 1;
+    const int slot = P.slots[item];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cur = P.state[slot].cur;
+    const size_t f = frame_idx(slot, cur, side);
+    const int n = P.n_kp[f];
+    const int i = blockIdx.x * OD_WARPS + warp;
+    if (i >= n) return;
+    const float4 kp = P.kpf[f * (size_t)P.p.kp_cap + i];
+    const int oct = P.kpo[f * (size_t)P.p.kp_cap + i];
+    const OrbLevelDev& Lv = D.L[oct];
+    const float inv = __fdiv_rn(1.f, Lv.scale);
+    const int cy = __float2int_rn(__fmul_rn(kp.y, inv)), cx = __float2int_rn(__fmul_rn(kp.x, inv));
+    float a, b;
+    orb_cos_sin(kp.w, a, b);
+    const uint8_t* __restrict__ center = Lv.blur + img_idx(slot, side) * (size_t)Lv.pitch * Lv.h + (size_t)cy * Lv.pitch + cx;
+    uint32_t byte = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int8_t* p = g_orb_pattern.v[lane * 8 + t];
+        int x0, y0, x1, y1;
+        orb_steer(p[0], p[1], a, b, x0, y0);
+        orb_steer(p[2], p[3], a, b, x1, y1);
+        const int t0 = center[y0 * Lv.pitch + x0], t1 = center[y1 * Lv.pitch + x1];
+        byte |= (t0 < t1 ? 1u : 0u) << t;
+    }
+    // 32 descriptor bytes of the keypoint: assemble words with shuffles, lanes 0..7 store
+    uint32_t w = byte;
+    w |= __shfl_down_sync(0xffffffffu, byte, 1) << 8;
+    w |= __shfl_down_sync(0xffffffffu, byte, 2) << 16;
+    w |= __shfl_down_sync(0xffffffffu, byte, 3) << 24;
+    uint32_t* out = reinterpret_cast<uint32_t*>(P.desc + (f * (size_t)P.p.kp_cap + i) * 2);
+    if ((lane & 3) == 0) out[lane >> 2] = w;
+}
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------------------------------------------------
+static int orb_select_smem_cap(const OrbDev& D) { return D.cap < 12288 ? D.cap : 12288; }
+
+cudaError_t alloc_orb(OrbDev& D, const Params& p, int n_slots, int n_levels, int n_extract, std::vector<void*>& allocs) {
+    memset(&D, 0, sizeof(D));
+    if (n_levels < 1 || n_levels > kOrbMaxLevels) return cudaErrorInvalidValue;
+    const OrbLevels G = orb_levels(p.W, p.H, n_levels, n_extract);
+    D.n_levels = n_levels;
+    D.n_extract = n_extract;
+    D.cap = p.max_corners;
+    D.raw_cap = 2 * n_extract + 64;
+    const size_t S = (size_t)n_slots;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** ptr, size_t bytes) { if (e != cudaSuccess) return; e = cudaMalloc(ptr, bytes ? bytes : 1); if (e == cudaSuccess) { allocs.push_back(*ptr); e = cudaMemset(*ptr, 0, bytes ? bytes : 1); } };
+    auto upload = [&](const std::vector<uint16_t>& v, const uint16_t** out) {
+        void* d = nullptr;
+        A(&d, v.size() * sizeof(uint16_t));
+        if (e == cudaSuccess) e = cudaMemcpy(d, v.data(), v.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+        *out = (const uint16_t*)d;
+    };
+    for (int l = 0; l < n_levels; ++l) {
+        OrbLevelDev& L = D.L[l];
+        L.w = G.w[l]; L.h = G.h[l]; L.pitch = (G.w[l] + 15) & ~15; L.nfeat = G.nfeat[l]; L.scale = G.scale[l];
+        if (L.w < 64 || L.h < 64) return cudaErrorInvalidValue;          // FAST + the 31-px border need some image
+        const size_t plane = (size_t)L.pitch * L.h;
+        if (l > 0) {
+            A((void**)&L.imgL, S * plane); A((void**)&L.imgR, S * plane);
+            // uniform tables: out-of-range outputs replicate the border pixel with weights (256, 0) / (0, 256)
+            auto tables = [&](int src, int dst, const uint16_t** dofs, const uint16_t** dc1) {
+                const OrbAxis ax = orb_resize_axis(src, dst);
+                std::vector<uint16_t> ofs(dst), c1(dst);
+                for (int v = 0; v < dst; ++v) {
+                    if (v < ax.lo) { ofs[v] = 0; c1[v] = 0; }
+                    else if (v >= ax.hi) { ofs[v] = (uint16_t)(src - 2); c1[v] = 256; }
+                    else { ofs[v] = (uint16_t)ax.ofs[v]; c1[v] = (uint16_t)ax.c1[v]; }
+                }
+                upload(ofs, dofs); upload(c1, dc1);
+            };
+            tables(G.w[l - 1], L.w, &L.xofs, &L.xc1);
+            tables(G.h[l - 1], L.h, &L.yofs, &L.yc1);
+        }
+        A((void**)&L.blur, S * 2 * plane);
+        const size_t tiles = (size_t)tiles_x_of(L.w) * tiles_y_of(L.h);
+        A((void**)&L.tile_seg, S * 2 * tiles * kTileH * sizeof(uint16_t));
+        A((void**)&L.tile_list, S * 2 * tiles * kTileCap * sizeof(uint16_t));
+    }
+    A((void**)&D.idx, S * 2 * D.cap * sizeof(uint32_t));
+    A((void**)&D.resp, S * 2 * D.cap * sizeof(float));
+    A((void**)&D.pos, S * 2 * D.cap * sizeof(uint32_t));
+    A((void**)&D.tmp, S * 2 * D.cap * sizeof(uint32_t));
+    A((void**)&D.raw, S * 2 * D.raw_cap * sizeof(float4));
+    A((void**)&D.raw_oct, S * 2 * D.raw_cap * sizeof(int32_t));
+    A((void**)&D.n_raw, S * 2 * sizeof(int32_t));
+    if (e != cudaSuccess) return e;
+    e = SVO_RAISE_DYN_SMEM(orb_select_kernel, orb_select_smem_cap(D) * 8);
+    if (e != cudaSuccess) return e;
+    return SVO_RAISE_DYN_SMEM(orb_nms_sort_kernel, D.raw_cap * 12);
+}
+
+cudaError_t launch_orb_detect(const Pools& P, const OrbDev& D, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
+                              size_t image_pitch, int item0, uint32_t* occ_scratch, int occ_words_per_img, uint32_t* sort_scratch,
+                              uint2* list_scratch, cudaStream_t st, int* launches) {
+    // the pyramid, level after level (each level is resized from the previous one), and FAST + blur of every level
+    const uint8_t *sL = d_left + (size_t)item0 * image_pitch, *sR = d_right + (size_t)item0 * image_pitch;
+    size_t sstride = stride, spitch = image_pitch;
+    int sw = P.p.W, sh = P.p.H;
+    int L = 0;
+    for (int l = 0; l < D.n_levels; ++l) {
+        const OrbLevelDev& Lv = D.L[l];
+        if (l > 0) {
+            OrbLevelDev Dl = Lv;
+            Dl.imgL += (size_t)item0 * Lv.pitch * Lv.h; Dl.imgR += (size_t)item0 * Lv.pitch * Lv.h;
+            const dim3 g((Lv.pitch / 4 + 127) / 128, Lv.h, 2 * n);
+            orb_resize_kernel<<<g, 128, 0, st>>>(sL, sR, sstride, spitch, sw, sh, Dl);
+            sL = Dl.imgL; sR = Dl.imgR; sstride = (size_t)Lv.pitch; spitch = (size_t)Lv.pitch * Lv.h; sw = Lv.w; sh = Lv.h;
+            ++L;
+        }
+        Pools PL = P;
+        PL.p.W = Lv.w; PL.p.H = Lv.h;
+        PL.blur = Lv.blur; PL.tile_seg = Lv.tile_seg; PL.tile_list = Lv.tile_list;
+        cudaError_t e = launch_fast_blur_only(PL, n, sL, sR, sstride, spitch, Lv.pitch, st);
+        if (e != cudaSuccess) return e;
+        ++L;
+    }
+    const int cap = orb_select_smem_cap(D);
+    orb_select_kernel<<<2 * n, OT, cap * 8, st>>>(P, D, d_left, d_right, stride, image_pitch, item0, cap);
+    orb_nms_sort_kernel<<<2 * n, OT, D.raw_cap * 12, st>>>(P, D, occ_scratch, occ_words_per_img, sort_scratch, list_scratch);
+    const dim3 gd((P.p.kp_cap + OD_WARPS - 1) / OD_WARPS, 2 * n);
+    orb_describe_kernel<<<gd, OD_WARPS * 32, 0, st>>>(P, D);
+    if (launches) *launches += L + 3;
+    return cudaGetLastError();
+}
+
+}  // namespace svo

@@ -48,16 +48,14 @@ ransac_prepare_kernel(Pools P, RansacScratch R) {
     const int4* __restrict__ mp = P.match + pair_idx(slot, prev) * cap;
     const int4* __restrict__ mc = P.match + pair_idx(slot, cur) * cap;
     for (int side = 0; side < 2; ++side) {
-        const int2* __restrict__ kp = P.kp + frame_idx(slot, prev, side) * cap;
-        const int2* __restrict__ kc = P.kp + frame_idx(slot, cur, side) * cap;
+        const size_t fp = frame_idx(slot, prev, side) * cap, fc = frame_idx(slot, cur, side) * cap;
         float2* __restrict__ o1 = R.p1 + ((size_t)slot * 2 + side) * cap;
         float2* __restrict__ o2 = R.p2 + ((size_t)slot * 2 + side) * cap;
         for (int k = threadIdx.x; k < n; k += blockDim.x) {
             const int4 c = tc[k];
             const int4 a = mp[c.x], b = mc[side ? c.z : c.y];
-            const int2 p = kp[side ? a.y : a.x], q = kc[side ? b.y : b.x];
-            o1[k] = make_float2((float)(p.x & 0xFFFF), (float)((unsigned)p.x >> 16));
-            o2[k] = make_float2((float)(q.x & 0xFFFF), (float)((unsigned)q.x >> 16));
+            o1[k] = kp_xy(P, fp, side ? a.y : a.x);
+            o2[k] = kp_xy(P, fc, side ? b.y : b.x);
         }
         if (threadIdx.x == 0) R.n_pts[slot * 2 + side] = n;
     }

@@ -58,6 +58,7 @@ struct Params {                     // device copy of svo_config (see include/sv
     int32_t ifm_method;             // TIFMMethod: 0 = ifmDescBF, 1 = ifmDescWin (libstereo-odometry.h:291)
     int32_t ifm_win_w, ifm_win_h;   // inter-frame search window (libstereo-odometry.h:294)
     int32_t rbr_max_distance;       // size_t(params_lr_match.orb_max_distance) (stage3_match_left_right.cpp:206)
+    int32_t detect_method;          // TDMethod: 0 = dmORB (stage2_detect.cpp:458-496), 1 = dmFAST_ORB (:502-515)
 };
 
 // Device result record: same layout as svo_result in include/svo_b200.h (static_assert in capi.cu).
@@ -100,6 +101,9 @@ struct Pools {
     int32_t* n_cand;       // [max_seqs*2]
     // per (slot, buf, side) frame data
     int2* kp;              // [max_seqs*2*2][kp_cap]  {y<<16|x, score}
+    float4* kpf;           // dmORB only (else nullptr): [max_seqs*2*2][kp_cap] cv::KeyPoint {pt.x, pt.y, response, angle} -- the
+                           // multi-scale detector yields float coordinates; kp then holds their truncated copy
+    int32_t* kpo;          // dmORB only: [max_seqs*2*2][kp_cap] cv::KeyPoint::octave
     uint4* desc;           // [max_seqs*2*2][kp_cap][2]
     int32_t* n_kp;         // [max_seqs*2*2]
     // per (slot, buf) stereo matches
@@ -164,6 +168,14 @@ inline cudaError_t raise_dyn_smem(const void* func, int bytes, int* seen /* [64]
 __host__ __device__ inline size_t img_idx(int slot, int side) { return (size_t)slot * 2 + side; }
 __host__ __device__ inline size_t frame_idx(int slot, int buf, int side) { return ((size_t)slot * 2 + buf) * 2 + side; }
 __host__ __device__ inline size_t pair_idx(int slot, int buf) { return (size_t)slot * 2 + buf; }
+#if defined(__CUDACC__)
+// pt of keypoint i of the frame whose keypoints start at fbase = frame_idx(...) * kp_cap
+__device__ __forceinline__ float2 kp_xy(const Pools& P, size_t fbase, int i) {
+    if (P.kpf) { const float4 k = P.kpf[fbase + i]; return make_float2(k.x, k.y); }
+    const int2 k = P.kp[fbase + i];
+    return make_float2((float)(k.x & 0xFFFF), (float)((unsigned)k.x >> 16));
+}
+#endif
 __host__ __device__ inline size_t stat_idx(int slot, int octave, int what) { return ((size_t)slot * kMaxOctaves + octave) * 4 + what; }
 
 }  // namespace svo

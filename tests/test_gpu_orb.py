@@ -1,0 +1,139 @@
+"""-m gpu: the dmORB detector (svo_config.detect_method = 0, stage2_detect.cpp:458-496) against the real OpenCV.
+
+cv::ORB::detectAndCompute is third-party code the reference calls; cv2 4.13 (the OpenCV of this image) IS the oracle here,
+called with exactly the reference's arguments (oracle.cv2_orb_detect_and_compute).  The reference's own glue behind it
+(m_non_max_sup, m_update_indexes, stages 3-5 on float keypoints) is checked against the restated oracle, which
+tests/test_ref_cpu.py pins against the reference's compiled text (incl. the dmORB branch)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from stereo_vo_b200 import capi, synth
+
+cv2 = pytest.importorskip("cv2")
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("x", "y", "size", "angle", "response", "octave")
+
+
+def _images():
+    out = []
+    for cfg, seed in (("c1", 3), ("c2", 2), ("c3", 1)):
+        frames, _ = synth.make_sequence(cfg, seed=seed, n_frames=1)
+        out.append((cfg, frames[0][0]))
+        out.append((cfg, frames[0][1]))
+    return out
+
+
+def _assert_kps_equal(a, b, what):
+    assert len(a) == len(b), f"{what}: {len(a)} vs {len(b)} keypoints"
+    for f in FIELDS:
+        assert np.array_equal(a[f], b[f]), f"{what}: field {f} differs at {np.nonzero(a[f] != b[f])[0][:5]}"
+
+
+@pytest.mark.parametrize("nfeats,fast_th", [(200, 20), (500, 20), (100, 7)])
+def test_orb_detect_and_compute_equals_opencv(nfeats, fast_th):
+    """raw output of detectAndCompute (all keypoint fields, order) and the final keypoints + descriptors of stage 2"""
+    for cfg, img in _images():
+        H, W = img.shape
+        ctx = capi.Context(width=W, height=H, orb_nfeats=nfeats, max_seqs=1, detect_method=0, fast_threshold=fast_th, max_corners=60000)
+        try:
+            kps, desc = ctx.detect(img)
+            raw = ctx.orb_raw_keypoints(ctx.cfg.max_seqs, 0)                 # svo_detect works on the hidden slot
+            ref_k, ref_d = orc.cv2_orb_detect_and_compute(img, int(1.5 * nfeats), 8, fast_th)
+            _assert_kps_equal(raw, ref_k, f"{cfg} {W}x{H} raw")
+            est = orc.OracleEstimator(orc.Params(orb_nfeats=nfeats, detect_method=0, initial_FAST_threshold=fast_th),
+                                      backend="cv2", ransac="off")
+            ok, od, _ = est.detect(img)
+            _assert_kps_equal(kps, ok, f"{cfg} {W}x{H} after m_non_max_sup + m_update_indexes")
+            assert np.array_equal(desc, od), f"{cfg}: descriptors differ in rows {np.nonzero((desc != od).any(axis=1))[0][:8]}"
+        finally:
+            ctx.close()
+
+
+def test_orb_pyramid_levels_equal_opencv_resize_and_blur():
+    from oracle import pyoracle
+    frames, _ = synth.make_sequence("c2", seed=5, n_frames=1)
+    img = frames[0][0]
+    ctx = capi.Context(width=640, height=480, orb_nfeats=300, max_seqs=1, detect_method=0)
+    try:
+        ctx.detect(img)
+        hs = ctx.cfg.max_seqs
+        prev = img
+        for level in range(1, 8):
+            got = ctx.orb_level(hs, 0, level, 0)
+            want = cv2.resize(prev, (got.shape[1], got.shape[0]), interpolation=cv2.INTER_LINEAR_EXACT)
+            assert np.array_equal(got, want), f"level {level} image"
+            assert np.array_equal(ctx.orb_level(hs, 0, level, 1), pyoracle.blur7_exact(want)), f"level {level} blur"
+            prev = want
+        assert ctx.orb_level(hs, 0, 1, 0).shape == (400, 533)
+    finally:
+        ctx.close()
+
+
+def test_orb_without_nms_keeps_opencvs_list():
+    frames, _ = synth.make_sequence("c1", seed=8, n_frames=1)
+    img = frames[0][0]
+    ctx = capi.Context(width=320, height=240, orb_nfeats=150, max_seqs=1, detect_method=0, non_maximal_suppression=0, max_corners=4096)
+    try:
+        kps, desc = ctx.detect(img)
+        est = orc.OracleEstimator(orc.Params(orb_nfeats=150, detect_method=0, non_maximal_suppression=False), backend="cv2", ransac="off")
+        ok, od, _ = est.detect(img)
+        _assert_kps_equal(kps, ok, "no NMS")
+        assert np.array_equal(desc, od)
+    finally:
+        ctx.close()
+
+
+def _run(cfg_name, nfeats, seed, n_frames, **params):
+    frames, cam = synth.make_sequence(cfg_name, seed=seed, n_frames=n_frames)
+    H, W = frames[0][0].shape
+    ctx = capi.Context(width=W, height=H, orb_nfeats=nfeats, max_seqs=2, detect_method=0, **params)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=nfeats, detect_method=0, **params), backend="cv2", ransac="cv2_tolerant")
+    oc = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    gc = capi.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    n_valid = 0
+    try:
+        for i, (L, R) in enumerate(frames):
+            o = est.process_new_image_pair(L, R, oc)
+            r = ctx.process_batch([L], [R], [gc], slots=[1])[0]
+            f = o["frame"]
+            _assert_kps_equal(ctx.keypoints(1, 0, 0), f.kpsL, f"frame {i} left")
+            _assert_kps_equal(ctx.keypoints(1, 0, 1), f.kpsR, f"frame {i} right")
+            assert np.array_equal(ctx.descriptors(1, 0, 0), f.descL) and np.array_equal(ctx.descriptors(1, 0, 1), f.descR)
+            m = ctx.matches(1, 0)
+            assert np.array_equal(np.stack([m["queryIdx"], m["trainIdx"], m["distance"].astype(np.int32)], 1),
+                                  np.stack([f.matches["queryIdx"], f.matches["trainIdx"], f.matches["distance"].astype(np.int32)], 1)), f"frame {i}: stereo matches"
+            if i > 0 and "track_dbg" in o:
+                q, tl, tr, il, ir = ctx.track_candidates(1)
+                t = o["track_dbg"]
+                assert np.array_equal(q, t["matL"]["queryIdx"]) and np.array_equal(tl, t["matL"]["trainIdx"])
+                if t["inlL"] is not None:
+                    assert np.array_equal(il, t["inlL"]) and np.array_equal(ir, t["inlR"]), f"frame {i}: RANSAC masks"
+                assert np.array_equal(ctx.tracked_pairs(1), o["tracked"]), f"frame {i}: tracked pairs"
+            assert (r.error_code, bool(r.valid), r.num_it, r.num_it_final) == (o["error_code"], o["valid"], o["num_it"], o["num_it_final"]), f"frame {i}"
+            if o["pose"] is not None:
+                np.testing.assert_allclose(r.delta_pose[:3], o["pose"]["delta"][:3], atol=1e-4)
+                np.testing.assert_allclose(r.delta_pose[3:], o["pose"]["delta"][3:], atol=1e-3)
+                assert np.array_equal(ctx.outliers(1), o["outliers"]), f"frame {i}: inlier list"
+                n_valid += bool(r.valid)
+    finally:
+        ctx.close()
+    return n_valid
+
+
+def test_pipeline_orb_c1_equals_oracle():
+    assert _run("c1", 150, seed=4, n_frames=5) >= 3
+
+
+def test_pipeline_orb_c2_equals_oracle():
+    assert _run("c2", 500, seed=1, n_frames=4, max_y_diff=2.0) >= 2
+
+
+def test_orb_config_is_validated():
+    with pytest.raises(Exception):
+        capi.Context(width=640, height=480, max_seqs=1, detect_method=0, n_octaves=2)
+    with pytest.raises(Exception):
+        capi.Context(width=640, height=480, max_seqs=1, detect_method=0, match_method=1)
+    with pytest.raises(Exception):
+        capi.Context(width=640, height=480, max_seqs=1, detect_method=2)

@@ -29,7 +29,7 @@ def test_library_exports_every_header_symbol(built_lib):
     for name in declared:
         assert hasattr(L, name), f"{name} is declared in svo_b200.h but not exported"
     assert sorted(capi.EXPORTS) == declared
-    assert L.svo_abi_version() == 3
+    assert L.svo_abi_version() == 4
 
 
 def test_struct_layouts_match_header(built_lib):
