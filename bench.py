@@ -1001,7 +1001,7 @@ def run_gpu(args):
         hm_ms = kernel_ms.get("hamming_kernel(lr)", 0) + kernel_ms.get("hamming_kernel(track)", 0)
         pairdist = B * (Nkp * Nkp + 2 * M * M)
         int_roof = 1.0 / max(HM_POPC_PFX / pipe["popc_per_s"], HM_ALU_PFX / pipe["lop3_per_s"])
-        micro = stage1 = latency = octaves = c3 = outl = klass = None
+        micro = stage1 = latency = octaves = c3 = outl = dmorb = klass = None
         if not args.no_micro:
             octaves = octaves_throughput(capi, torch, pb.dev, gc, W, H, nfeats, local, peak)
             micro, _ = c5_microbench(ctx, torch, stream, device, pipe, peak, reps=64, iters=5)
@@ -1014,6 +1014,8 @@ def run_gpu(args):
             klass = class_api_bench(seqs, cam, B, max(8, min(args.steps, 60)), 3, nfeats, local, rank)
             c3 = side_workload(capi, torch, local, "c3", 1000, 128, 4, 8, 20, 3)
             outl = side_workload(capi, torch, local, "c2", 500, 256, 8, 8, 20, 3, two_motions=True)
+            dmorb = side_workload(capi, torch, local, "c2", 500, 128, 8, 8, 10, 3, detect_method=0, max_y_diff=2.0)
+            dmorb["workload"] += "; detect_method = dmORB (cv::ORB::detectAndCompute with 750 features on 8 levels, oriented, then the reference's NMS): SURVEY 8(f) rank 4"
         if micro is not None and sharded is not None:
             micro["sharded"] = sharded
         elif sharded is not None:
@@ -1072,6 +1074,7 @@ def run_gpu(args):
             "match_microbench": micro,
             "c3": c3,
             "outlier_heavy": outl,
+            "dmorb": dmorb,
             "stage1": stage1,
             "single_pair": latency,
             "octaves": octaves,

@@ -171,7 +171,7 @@ void CStereoOdometryEstimator::setMaxMatchID(size_t id) {
     if (svo_set_max_match_id(m_ctx, m_slot, (int64_t)id) != SVO_OK) throw_last(m_ctx, "setMaxMatchID");
 }
 std::vector<size_t> CStereoOdometryEstimator::getCopyCurrentIDs(size_t octave) {
-    if (!m_ctx || octave >= (size_t)params_rectify.nOctaves) return std::vector<size_t>();
+    if (!m_ctx || octave >= (size_t)n_octaves()) return std::vector<size_t>();
     const int cap = keypoint_capacity((int)octave);
     std::vector<int64_t> ids((size_t)cap);
     const int n = svo_get_match_ids_oct(m_ctx, m_slot, (int32_t)octave, 0, ids.data(), cap);
@@ -189,7 +189,7 @@ int CStereoOdometryEstimator::keypoint_capacity(int octave) const {
 
 // S3:425-445
 std::vector<size_t> CStereoOdometryEstimator::getMatchesRowIndex(size_t octave) {
-    if (!m_ctx || octave >= (size_t)params_rectify.nOctaves) return std::vector<size_t>();
+    if (!m_ctx || octave >= (size_t)n_octaves()) return std::vector<size_t>();
     const int cap = keypoint_capacity((int)octave);
     int32_t info[4];
     svo_get_octave_info(m_ctx, (int)octave, info);
@@ -230,8 +230,11 @@ void CStereoOdometryEstimator::throw_last(svo_ctx* c, const char* what) {
 
 // process_new_image_pair.cpp:54-76: the methods this build has
 void CStereoOdometryEstimator::check_methods() const {
-    if (params_detect.detect_method != TDetectParams::dmFAST_ORB)
-        throw std::runtime_error("[Visual Odometry Error] Detect method not correct (this build has dmFAST_ORB only).");
+    if (params_detect.detect_method != TDetectParams::dmFAST_ORB && params_detect.detect_method != TDetectParams::dmORB)
+        throw std::runtime_error("[Visual Odometry Error] Detect method not correct (this build has dmFAST_ORB and dmORB).");
+    if (params_detect.detect_method == TDetectParams::dmORB &&
+        (params_lr_match.match_method != TLeftRightMatchParams::smDescBF || params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescBF))
+        throw std::runtime_error("[Visual Odometry Error] dmORB is built for smDescBF / ifmDescBF only.");
     if (params_lr_match.match_method != TLeftRightMatchParams::smDescBF && params_lr_match.match_method != TLeftRightMatchParams::smDescRbR)
         throw std::runtime_error("[Visual Odometry Error] Stereo matching method not correct (this build has smDescBF and smDescRbR).");
     if (params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescBF && params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescWin)
@@ -272,7 +275,9 @@ svo_config CStereoOdometryEstimator::make_config(int width, int height, int max_
     cfg.ifm_win_w = params_if_match.ifm_win_w;
     cfg.ifm_win_h = params_if_match.ifm_win_h;
     cfg.orb_max_distance = params_lr_match.orb_max_distance;
-    cfg.n_octaves = params_rectify.nOctaves;      // stage1_rectify.cpp:80 (dmORB, which forces one octave, is not built)
+    cfg.n_octaves = n_octaves();                  // stage1_rectify.cpp:80: dmORB builds its own pyramid and forces one octave
+    cfg.detect_method = (int32_t)params_detect.detect_method;
+    cfg.orb_nlevels = (int32_t)params_detect.orb_nlevels;
     cfg.pyr_mode = params_rectify.pyr_mode;
     return cfg;
 }
@@ -523,7 +528,7 @@ void CStereoOdometryEstimator::apply_stage1_format(const CObservationStereoImage
 void CStereoOdometryEstimator::finish_step(const svo_result& r, const double* residuals, const int64_t* outliers, const int32_t* batch_stats,
                                            bool repeat, TStereoOdometryResult& result) {
     int32_t stats[4 * 4];
-    int n_oct = params_rectify.nOctaves;
+    int n_oct = n_octaves();
     if (batch_stats) std::memcpy(stats, batch_stats, sizeof stats);      // the counters of THIS batch (later ones may be running)
     else n_oct = svo_get_octave_stats(m_ctx, m_slot, stats, 4);
     if (n_oct < 1) throw_last(m_ctx, "svo_get_octave_stats");

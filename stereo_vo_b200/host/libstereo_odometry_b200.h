@@ -158,7 +158,7 @@ public:
     struct TDetectParams {                          // H:383-447, stage2_detect.cpp:44-58
         enum NMSMethod { nmsmStandard, nmsmAdaptive };
         enum TDMethod { dmORB, dmFAST_ORB, dmFASTER, dmKLT };
-        TDMethod detect_method = dmFAST_ORB;        // the reference's ctor default is dmFASTER; this shim only has the hot path
+        TDMethod detect_method = dmFAST_ORB;        // the reference's ctor default is dmFASTER (unimplemented there); built here: dmFAST_ORB, dmORB
         bool non_maximal_suppression = true;
         NMSMethod nmsMethod = nmsmStandard;
         size_t min_distance = 3;
@@ -267,6 +267,8 @@ private:
     void push_thresholds();
     svo_config make_config(int width, int height, int max_seqs) const;
     void check_methods() const;
+    // stage1_rectify.cpp:80: n_octaves = detect_method == dmORB ? 1 : params_rectify.nOctaves
+    int n_octaves() const { return params_detect.detect_method == TDetectParams::dmORB ? 1 : params_rectify.nOctaves; }
     void apply_stage1_format(const CObservationStereoImages& obs);
     void finish_step(const svo_result& r, const double* residuals, const int64_t* outliers, const int32_t* batch_stats, bool repeat,
                      TStereoOdometryResult& result);

@@ -137,3 +137,42 @@ def test_orb_config_is_validated():
         capi.Context(width=640, height=480, max_seqs=1, detect_method=0, match_method=1)
     with pytest.raises(Exception):
         capi.Context(width=640, height=480, max_seqs=1, detect_method=2)
+
+
+def test_host_shim_runs_dmorb_from_the_ini(tmp_path):
+    """rso::CStereoOdometryEstimator (host shim) with detect_method = dmORB selected in the INI file (H:554-663): the demo
+    loop's composed camera poses equal the oracle's with the same detector; nOctaves of the INI is ignored (S1:80)."""
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    demo = os.path.join(root, "stereo_vo_b200", "host", "svo_demo")
+    assert os.path.exists(demo), "host shim not built (run __graft_entry__.build())"
+    frames, cam = synth.make_sequence("c1", seed=12, n_frames=4)
+    seq = tmp_path / "seq.bin"
+    with open(seq, "wb") as f:
+        f.write(struct.pack("<3i5d", 320, 240, len(frames), cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"]))
+        for (L, R) in frames:
+            f.write(L.tobytes())
+            f.write(R.tobytes())
+    text = open(os.path.join(root, "stereo_vo_b200", "host", "hot_path.ini")).read()
+    assert "detect_method = 1" in text and "orb_nfeats = 500" in text and "nOctaves = 1" in text
+    text = text.replace("detect_method = 1", "detect_method = 0").replace("orb_nfeats = 500", "orb_nfeats = 150").replace("nOctaves = 1", "nOctaves = 3")
+    ini = tmp_path / "cfg.ini"
+    ini.write_text(text)
+    out = tmp_path / "camera_pose.txt"
+    p = subprocess.run([demo, str(seq), str(out), str(ini)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    got = np.loadtxt(out).reshape(-1, 6)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=150, detect_method=0, nOctaves=3), backend="cv2", ransac="cv2_tolerant")
+    oc = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    pose = np.eye(4)
+    exp = []
+    for (L, R) in frames:
+        o = est.process_new_image_pair(L, R, oc)
+        if o["valid"]:
+            pose = pose @ o["pose"]["mat"]
+        ypr = [np.arctan2(pose[1, 0], pose[0, 0]), np.arctan2(-pose[2, 0], np.hypot(pose[0, 0], pose[1, 0])), np.arctan2(pose[2, 1], pose[2, 2])]
+        exp.append([pose[0, 3], pose[1, 3], pose[2, 3]] + ypr)
+    np.testing.assert_allclose(got, np.array(exp), atol=1.5e-3)     # the file holds %.3f values
+    assert abs(got[-1, 0]) > 0.05                                   # the sequence moves
