@@ -109,19 +109,83 @@ __device__ void nth_element_block(const C& c, uint32_t* a, int n, int nth, uint3
     __syncthreads();
 }
 
+// std::partition(idx + first, idx + n, resp >= v) as retainBest uses it: the vector is resized to the partition point right
+// after, so only the kept prefix [first, first + T) matters.  The bidirectional std::partition leaves the trues of that
+// prefix in place and fills its k-th false position (ascending) with the k-th true of the rest taken from the END
+// (descending) -- computed here by all threads with two ordered compactions.  tmp: n words.  Returns first + T.
+__device__ int partition_tail_block(uint32_t* idx, int first, int n, const float* resp, float v, uint32_t* tmp, int* s_warp) {
+    const int tid = threadIdx.x;
+    int c = 0;
+    for (int i = first + tid; i < n; i += OT) c += resp[idx[i]] >= v ? 1 : 0;
+    int T;
+    block_excl_scan(c, s_warp, T);
+    const int mid = first + T;
+    int K, K2;
+    {   // false positions of [first, mid), ascending
+        const int per = (mid - first + OT - 1) / OT;
+        const int lo = min(mid, first + tid * per), hi = min(mid, lo + per);
+        int cf = 0;
+        for (int i = lo; i < hi; ++i) cf += resp[idx[i]] >= v ? 0 : 1;
+        int off = block_excl_scan(cf, s_warp, K);
+        for (int i = lo; i < hi; ++i) if (!(resp[idx[i]] >= v)) tmp[off++] = (uint32_t)i;
+    }
+    {   // the trues of [mid, n), ascending by position
+        const int per = (n - mid + OT - 1) / OT;
+        const int lo = min(n, mid + tid * per), hi = min(n, lo + per);
+        int ct = 0;
+        for (int i = lo; i < hi; ++i) ct += resp[idx[i]] >= v ? 1 : 0;
+        int off = K + block_excl_scan(ct, s_warp, K2);
+        for (int i = lo; i < hi; ++i) if (resp[idx[i]] >= v) tmp[off++] = idx[i];
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += OT) idx[tmp[k]] = tmp[K + (K - 1 - k)];
+    __syncthreads();
+    return mid;
+}
+
 // KeyPointsFilter::retainBest on idx[0..n) (block-wide); returns the new size on every thread
-__device__ int retain_best_block(uint32_t* idx, int n, const float* resp, int n_points, uint32_t* tmp, int* s_blk, int* s_cut) {
+__device__ int retain_best_block(uint32_t* idx, int n, const float* resp, int n_points, uint32_t* tmp, int* s_blk, int* s_cut, int* s_warp) {
     if (!(n_points >= 0 && n > n_points)) return n;
     if (n_points == 0) return 0;
     nth_element_block(OrbRespGreater{resp}, idx, n, n_points - 1, tmp, s_blk, s_cut);
-    if (threadIdx.x == 0) {
-        const float ambiguous = resp[idx[n_points - 1]];
-        *s_cut = partition_seq(OrbRespGE{resp, ambiguous}, idx, n_points, n);
+    const float ambiguous = resp[idx[n_points - 1]];
+    return partition_tail_block(idx, n_points, n, resp, ambiguous, tmp, s_warp);
+}
+
+// HarrisResponses / ICAngles of one keypoint by a warp: the sums are integers, so the lanes may add in any order
+__device__ __forceinline__ float harris_warp(const uint8_t* __restrict__ img, int step, int x0, int y0, int lane) {
+    int a = 0, b = 0, c = 0;
+    for (int k = lane; k < kOrbHarrisBlock * kOrbHarrisBlock; k += 32) {
+        const int i = k / kOrbHarrisBlock, j = k - i * kOrbHarrisBlock;
+        const uint8_t* p = img + (y0 - kOrbHarrisBlock / 2 + i) * step + (x0 - kOrbHarrisBlock / 2 + j);
+        const int Ix = (p[1] - p[-1]) * 2 + (p[-step + 1] - p[-step - 1]) + (p[step + 1] - p[step - 1]);
+        const int Iy = (p[step] - p[-step]) * 2 + (p[step - 1] - p[-step - 1]) + (p[step + 1] - p[-step + 1]);
+        a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
     }
-    __syncthreads();
-    const int m = *s_cut;
-    __syncthreads();
-    return m;
+    a = __reduce_add_sync(0xffffffffu, a); b = __reduce_add_sync(0xffffffffu, b); c = __reduce_add_sync(0xffffffffu, c);
+    return orb_harris_from_sums(a, b, c);
+}
+
+__device__ __forceinline__ float ic_angle_warp(const uint8_t* __restrict__ img, int step, int x0, int y0, int lane) {
+    const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    const uint8_t* center = img + y0 * step + x0;
+    const int v = lane & 15, half = lane >> 4;           // lane = row v of the half-disc, columns u < 0 (half 0) or u >= 0 (half 1)
+    const int d = umax[v];
+    const int u_lo = half ? 0 : -d, u_hi = half ? d : -1;
+    int m_01 = 0, m_10 = 0;
+    if (v == 0) {
+        for (int u = u_lo; u <= u_hi; ++u) m_10 += u * center[u];
+    } else {
+        int v_sum = 0;
+        for (int u = u_lo; u <= u_hi; ++u) {
+            const int val_plus = center[u + v * step], val_minus = center[u - v * step];
+            v_sum += (val_plus - val_minus);
+            m_10 += u * (val_plus + val_minus);
+        }
+        m_01 = v * v_sum;
+    }
+    m_01 = __reduce_add_sync(0xffffffffu, m_01); m_10 = __reduce_add_sync(0xffffffffu, m_10);
+    return orb_fast_atan2((float)m_01, (float)m_10);
 }
 
 // ---- computeKeyPoints -------------------------------------------------------------------------------------------------
@@ -138,16 +202,17 @@ orb_select_kernel(Pools P, OrbDev D, const uint8_t* __restrict__ img0L, const ui
     const int slot = P.slots[item];
     const int tid = threadIdx.x;
     const size_t im = img_idx(slot, side);
-    uint32_t* g_idx = D.idx + im * D.cap;
-    float* g_resp = D.resp + im * D.cap;
-    uint32_t* pos = D.pos + im * D.cap;
-    uint32_t* tmp = D.tmp + im * D.cap;
-    float4* raw = D.raw + im * D.raw_cap;
-    int32_t* raw_oct = D.raw_oct + im * D.raw_cap;
+    const int l = blockIdx.y;                                        // one CTA per (image, level)
+    const size_t il = im * D.n_levels + l;
+    uint32_t* g_idx = D.idx + il * D.cap;
+    float* g_resp = D.resp + il * D.cap;
+    uint32_t* pos = D.pos + il * D.cap;
+    uint32_t* tmp = D.tmp + il * D.cap;
+    float4* raw = D.lraw + il * D.lvl_cap;
     int n_out = 0;
     bool overflow = false;
 
-    for (int l = 0; l < D.n_levels; ++l) {
+    {
         const OrbLevelDev& Lv = D.L[l];
         const int W = Lv.w, H = Lv.h;
         const uint8_t* img;
@@ -193,31 +258,28 @@ orb_select_kernel(Pools P, OrbDev D, const uint8_t* __restrict__ img0L, const ui
         }
         __syncthreads();
         // B. retainBest(2 * featuresNum) by FAST response (HARRIS_SCORE keeps twice as many for the second cull)
-        const int n2 = retain_best_block(idx, n, resp, 2 * Lv.nfeat, tmp, s_blk, &s_cut);
+        const int n2 = retain_best_block(idx, n, resp, 2 * Lv.nfeat, tmp, s_blk, &s_cut, s_warp);
         // C. HarrisResponses of the survivors
-        for (int k = tid; k < n2; k += OT) {
+        for (int k = tid >> 5; k < n2; k += OT / 32) {
             const uint32_t i = idx[k], p = pos[i];
-            resp[i] = orb_harris(img, step, (int)(p & 0xFFFFu), (int)(p >> 16));
+            const float h = harris_warp(img, step, (int)(p & 0xFFFFu), (int)(p >> 16), tid & 31);
+            if ((tid & 31) == 0) resp[i] = h;
         }
         __syncthreads();
         // D. retainBest(featuresNum) by Harris response
-        const int n3 = retain_best_block(idx, n2, resp, Lv.nfeat, tmp, s_blk, &s_cut);
-        // E. ICAngles, pt *= scale; appended behind the coarser... finer levels (allKeypoints is in level order)
-        for (int k = tid; k < n3; k += OT) {
-            const int q = n_out + k;
-            if (q >= D.raw_cap) continue;
+        const int n3 = retain_best_block(idx, n2, resp, Lv.nfeat, tmp, s_blk, &s_cut, s_warp);
+        // E. ICAngles, pt *= scale
+        for (int k = tid >> 5; k < min(n3, D.lvl_cap); k += OT / 32) {
             const uint32_t i = idx[k], p = pos[i];
             const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
-            const float ang = orb_ic_angle(img, step, x, y);
-            raw[q] = make_float4(__fmul_rn((float)x, Lv.scale), __fmul_rn((float)y, Lv.scale), resp[i], ang);
-            raw_oct[q] = l;
+            const float ang = ic_angle_warp(img, step, x, y, tid & 31);
+            if ((tid & 31) == 0) raw[k] = make_float4(__fmul_rn((float)x, Lv.scale), __fmul_rn((float)y, Lv.scale), resp[i], ang);
         }
-        if (n_out + n3 > D.raw_cap) overflow = true;
-        n_out = min(n_out + n3, D.raw_cap);
-        __syncthreads();
+        if (n3 > D.lvl_cap) overflow = true;
+        n_out = min(n3, D.lvl_cap);
     }
     if (tid == 0) {
-        D.n_raw[im] = n_out;
+        D.n_lraw[il] = n_out;
         if (overflow) P.state[slot].status = -3;       // SVO_ERR_CAPACITY
     }
 }
@@ -243,9 +305,24 @@ orb_nms_sort_kernel(Pools P, OrbDev D, uint32_t* __restrict__ occ_scratch, int o
     const int slot = P.slots[item];
     const int tid = threadIdx.x;
     const size_t im = img_idx(slot, side);
-    const float4* __restrict__ raw = D.raw + im * D.raw_cap;
-    const int32_t* __restrict__ raw_oct = D.raw_oct + im * D.raw_cap;
-    const int n = D.n_raw[im];
+    // allKeypoints: the levels' keypoints one after the other (computeKeyPoints appends level by level)
+    float4* __restrict__ raw = D.raw + im * D.raw_cap;
+    int32_t* __restrict__ raw_oct = D.raw_oct + im * D.raw_cap;
+    int n = 0;
+    bool overflow = false;
+    for (int l = 0; l < D.n_levels; ++l) {
+        const int nl = D.n_lraw[im * D.n_levels + l];
+        const float4* __restrict__ src = D.lraw + (im * D.n_levels + l) * D.lvl_cap;
+        for (int k = tid; k < nl; k += OT)
+            if (n + k < D.raw_cap) { raw[n + k] = src[k]; raw_oct[n + k] = l; }
+        if (n + nl > D.raw_cap) overflow = true;
+        n = min(n + nl, D.raw_cap);
+    }
+    if (tid == 0) {
+        D.n_raw[im] = n;
+        if (overflow) P.state[slot].status = -3;       // SVO_ERR_CAPACITY
+    }
+    __syncthreads();
     const int list_cap = P.p.max_corners / 16 + 2;
     uint2* listA = list_scratch + (size_t)blockIdx.x * 3 * list_cap;
     uint2* listB = listA + list_cap;
@@ -366,7 +443,7 @@ orb_describe_kernel(Pools P, OrbDev D) {
 }  // namespace
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
-static int orb_select_smem_cap(const OrbDev& D) { return D.cap < 12288 ? D.cap : 12288; }
+static int orb_select_smem_cap(const OrbDev& D) { return D.cap < 8192 ? D.cap : 8192; }   // 64 KB: three CTAs per SM
 
 cudaError_t alloc_orb(OrbDev& D, const Params& p, int n_slots, int n_levels, int n_extract, std::vector<void*>& allocs) {
     memset(&D, 0, sizeof(D));
@@ -376,6 +453,7 @@ cudaError_t alloc_orb(OrbDev& D, const Params& p, int n_slots, int n_levels, int
     D.n_extract = n_extract;
     D.cap = p.max_corners;
     D.raw_cap = 2 * n_extract + 64;
+    D.lvl_cap = 2 * G.nfeat[0] + 64;            // retainBest(N_l) keeps N_l + the ties of the boundary response
     const size_t S = (size_t)n_slots;
     cudaError_t e = cudaSuccess;
     auto A = [&](void** ptr, size_t bytes) { if (e != cudaSuccess) return; e = cudaMalloc(ptr, bytes ? bytes : 1); if (e == cudaSuccess) { allocs.push_back(*ptr); e = cudaMemset(*ptr, 0, bytes ? bytes : 1); } };
@@ -411,10 +489,12 @@ cudaError_t alloc_orb(OrbDev& D, const Params& p, int n_slots, int n_levels, int
         A((void**)&L.tile_seg, S * 2 * tiles * kTileH * sizeof(uint16_t));
         A((void**)&L.tile_list, S * 2 * tiles * kTileCap * sizeof(uint16_t));
     }
-    A((void**)&D.idx, S * 2 * D.cap * sizeof(uint32_t));
-    A((void**)&D.resp, S * 2 * D.cap * sizeof(float));
-    A((void**)&D.pos, S * 2 * D.cap * sizeof(uint32_t));
-    A((void**)&D.tmp, S * 2 * D.cap * sizeof(uint32_t));
+    A((void**)&D.idx, S * 2 * n_levels * D.cap * sizeof(uint32_t));
+    A((void**)&D.resp, S * 2 * n_levels * D.cap * sizeof(float));
+    A((void**)&D.pos, S * 2 * n_levels * D.cap * sizeof(uint32_t));
+    A((void**)&D.tmp, S * 2 * n_levels * D.cap * sizeof(uint32_t));
+    A((void**)&D.lraw, S * 2 * n_levels * D.lvl_cap * sizeof(float4));
+    A((void**)&D.n_lraw, S * 2 * n_levels * sizeof(int32_t));
     A((void**)&D.raw, S * 2 * D.raw_cap * sizeof(float4));
     A((void**)&D.raw_oct, S * 2 * D.raw_cap * sizeof(int32_t));
     A((void**)&D.n_raw, S * 2 * sizeof(int32_t));
@@ -450,7 +530,7 @@ cudaError_t launch_orb_detect(const Pools& P, const OrbDev& D, int n, const uint
         ++L;
     }
     const int cap = orb_select_smem_cap(D);
-    orb_select_kernel<<<2 * n, OT, cap * 8, st>>>(P, D, d_left, d_right, stride, image_pitch, item0, cap);
+    orb_select_kernel<<<dim3(2 * n, D.n_levels), OT, cap * 8, st>>>(P, D, d_left, d_right, stride, image_pitch, item0, cap);
     orb_nms_sort_kernel<<<2 * n, OT, D.raw_cap * 12, st>>>(P, D, occ_scratch, occ_words_per_img, sort_scratch, list_scratch);
     const dim3 gd((P.p.kp_cap + OD_WARPS - 1) / OD_WARPS, 2 * n);
     orb_describe_kernel<<<gd, OD_WARPS * 32, 0, st>>>(P, D);

@@ -22,12 +22,16 @@ struct OrbDev {
     int32_t n_extract;                // nfeatures handed to cv::ORB::create (S2:460-464)
     int32_t cap;                      // candidates per level and image (= max_corners)
     int32_t raw_cap;                  // keypoints per image that detectAndCompute may return
+    int32_t lvl_cap;                  // ... per level
     OrbLevelDev L[kOrbMaxLevels];
-    // per (slot, side) scratch of one step
-    uint32_t* idx;                    // [max_seqs*2][cap]     the keypoint vector of the level being filtered (indices)
-    float* resp;                      // [max_seqs*2][cap]     response per candidate: FAST score, then Harris
-    uint32_t* pos;                    // [max_seqs*2][cap]     y<<16 | x in level coordinates
-    uint32_t* tmp;                    // [max_seqs*2][cap]     partition scratch
+    // per (slot, side, level) scratch of one step
+    uint32_t* idx;                    // [..][cap]     the keypoint vector of the level being filtered (indices)
+    float* resp;                      // [..][cap]     response per candidate: FAST score, then Harris
+    uint32_t* pos;                    // [..][cap]     y<<16 | x in level coordinates
+    uint32_t* tmp;                    // [..][cap]     partition scratch
+    float4* lraw;                     // [..][lvl_cap] the level's keypoints {pt.x, pt.y, response, angle}
+    int32_t* n_lraw;                  // [..]
+    // per (slot, side)
     float4* raw;                      // [max_seqs*2][raw_cap] detectAndCompute's keypoints {pt.x, pt.y, response, angle}
     int32_t* raw_oct;                 // [max_seqs*2][raw_cap] octave
     int32_t* n_raw;                   // [max_seqs*2]

@@ -154,16 +154,8 @@ SVO_HD int orb_retain_best(uint32_t* idx, int n, const float* resp, int n_points
 }
 
 // ---- HarrisResponses (blockSize 7, k = 0.04) on the unblurred level image ----------------------------------------
-SVO_HD float orb_harris(const uint8_t* img, int step, int x0, int y0) {
-    const int r = kOrbHarrisBlock / 2;
-    int a = 0, b = 0, c = 0;
-    for (int i = 0; i < kOrbHarrisBlock; ++i)
-        for (int j = 0; j < kOrbHarrisBlock; ++j) {
-            const uint8_t* p = img + (y0 - r + i) * step + (x0 - r + j);
-            const int Ix = (p[1] - p[-1]) * 2 + (p[-step + 1] - p[-step - 1]) + (p[step + 1] - p[step - 1]);
-            const int Iy = (p[step] - p[-step]) * 2 + (p[step - 1] - p[-step - 1]) + (p[step + 1] - p[-step + 1]);
-            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
-        }
+// the float formula on the three integer sums: (a*b - c*c - k*(a+b)*(a+b)) * scale^4, every operation rounded to float
+SVO_HD float orb_harris_from_sums(int a, int b, int c) {
     const float scale = 1.f / ((1 << 2) * kOrbHarrisBlock * 255.f);
     const float s2 = scale * scale, s3 = s2 * scale, s4 = s3 * scale;        // scale * scale * scale * scale, left to right
     const float fa = (float)a, fb = (float)b, fc = (float)c;
@@ -176,6 +168,18 @@ SVO_HD float orb_harris(const uint8_t* img, int step, int x0, int y0) {
     const float t = (0.04f * s) * s;
     return ((ab - cc) - t) * s4;
 #endif
+}
+SVO_HD float orb_harris(const uint8_t* img, int step, int x0, int y0) {
+    const int r = kOrbHarrisBlock / 2;
+    int a = 0, b = 0, c = 0;
+    for (int i = 0; i < kOrbHarrisBlock; ++i)
+        for (int j = 0; j < kOrbHarrisBlock; ++j) {
+            const uint8_t* p = img + (y0 - r + i) * step + (x0 - r + j);
+            const int Ix = (p[1] - p[-1]) * 2 + (p[-step + 1] - p[-step - 1]) + (p[step + 1] - p[step - 1]);
+            const int Iy = (p[step] - p[-step]) * 2 + (p[step - 1] - p[-step - 1]) + (p[step + 1] - p[-step + 1]);
+            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+        }
+    return orb_harris_from_sums(a, b, c);
 }
 
 // ---- cv::fastAtan2 (degrees) ---------------------------------------------------------------------------------------

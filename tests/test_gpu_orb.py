@@ -176,3 +176,13 @@ def test_host_shim_runs_dmorb_from_the_ini(tmp_path):
         exp.append([pose[0, 3], pose[1, 3], pose[2, 3]] + ypr)
     np.testing.assert_allclose(got, np.array(exp), atol=1.5e-3)     # the file holds %.3f values
     assert abs(got[-1, 0]) > 0.05                                   # the sequence moves
+
+
+def test_orb_soak_many_sequences():
+    """bounded soak of the dmORB pipeline: 7 seeded sequences (c1, c2), every frame compared with the oracle"""
+    valid = 0
+    for seed in range(30, 35):
+        valid += _run("c1", 120, seed=seed, n_frames=6)
+    for seed in (40, 41):
+        valid += _run("c2", 400, seed=seed, n_frames=4, max_y_diff=2.0)
+    assert valid >= 20
