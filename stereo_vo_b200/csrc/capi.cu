@@ -606,7 +606,8 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     DA(G.prev, S * cap); DA(G.obs, S * cap); DA(G.lmk, S * cap * 3); DA(G.mask, S * cap); DA(G.mask0, S * cap);
     DA(G.cur_idx, S * cap); DA(G.ini_pose, S * 6);
     G.residual = P.residual;
-    G.occ = c->d_occ;               // the aux NMS of stage 5 runs after stage 2 is finished: same scratch
+    // own grid, indexed by slot: stage 5 of one group of slots may overlap stage 2 of another group (indexed by batch item)
+    DA(G.occ, (size_t)S * 2 * c->occ_words);
     G.occ_words = 2 * c->occ_words;
     {
         cudaError_t e2 = alloc_ransac(c->RS, S, kp_cap, c->dev_allocs);
