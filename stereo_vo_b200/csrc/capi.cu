@@ -1607,15 +1607,25 @@ int svo_match_hamming(svo_ctx* c, const uint8_t* query, int32_t nq, const uint8_
     return nq;
 }
 
-static int upload_kps(svo_ctx* c, const svo_keypoint* k, int n, int2* d_dst) {
+// caller keypoints into the frame whose keypoints start at element fbase (= frame_idx * kp_cap) of the octave-0 arrays
+static int upload_kps(svo_ctx* c, const svo_keypoint* k, int n, size_t fbase) {
     std::vector<int2> tmp(n);
+    const bool float_kp = c->P.kpf != nullptr;          // dmORB context: cv::ORB keypoints, any float coordinates
     for (int i = 0; i < n; ++i) {
         const float x = k[i].x, y = k[i].y;
-        if (!(x >= 0 && y >= 0 && x < kMaxImgDim && y < kMaxImgDim) || x != std::floor(x) || y != std::floor(y))
-            return fail(c, SVO_ERR_ARG, "svo_match_lr needs integer keypoint coordinates inside the image (FAST keypoints)");
+        if (!(x >= 0 && y >= 0 && x < kMaxImgDim && y < kMaxImgDim) || (!float_kp && (x != std::floor(x) || y != std::floor(y))))
+            return fail(c, SVO_ERR_ARG, "keypoint coordinates must lie inside the image (and be integers unless detect_method = dmORB)");
         tmp[i] = make_int2(((int)y << 16) | (int)x, (int)k[i].response);
     }
-    if (n) CU(c, cudaMemcpyAsync(d_dst, tmp.data(), n * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    if (n) CU(c, cudaMemcpyAsync(c->P.kp + fbase, tmp.data(), n * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    std::vector<float4> kf;
+    std::vector<int32_t> ko;
+    if (float_kp && n) {
+        kf.resize(n); ko.resize(n);
+        for (int i = 0; i < n; ++i) { kf[i] = make_float4(k[i].x, k[i].y, k[i].response, k[i].angle); ko[i] = k[i].octave; }
+        CU(c, cudaMemcpyAsync(c->P.kpf + fbase, kf.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->P.kpo + fbase, ko.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    }
     CU(c, cudaStreamSynchronize(c->stream));
     return SVO_OK;
 }
@@ -1634,9 +1644,9 @@ int svo_match_lr(svo_ctx* c, const svo_keypoint* kpsL, const uint8_t* descL, int
     rc = get_state(c, hs, &s);
     if (rc) return rc;
     const size_t fL = frame_idx(hs, s.cur, 0), fR = frame_idx(hs, s.cur, 1);
-    rc = upload_kps(c, kpsL, nL, c->P.kp + fL * kc);
+    rc = upload_kps(c, kpsL, nL, fL * kc);
     if (rc) return rc;
-    rc = upload_kps(c, kpsR, nR, c->P.kp + fR * kc);
+    rc = upload_kps(c, kpsR, nR, fR * kc);
     if (rc) return rc;
     if (nL) CU(c, cudaMemcpyAsync(c->P.desc + fL * kc * 2, descL, (size_t)nL * 32, cudaMemcpyHostToDevice, c->stream));
     if (nR) CU(c, cudaMemcpyAsync(c->P.desc + fR * kc * 2, descR, (size_t)nR * 32, cudaMemcpyHostToDevice, c->stream));
@@ -1655,9 +1665,9 @@ static int upload_frame(svo_ctx* c, int hs, int buf, const svo_keypoint* kl, con
     const Pools& P = c->P;
     const int kc = P.p.kp_cap;
     const size_t fL = frame_idx(hs, buf, 0), fR = frame_idx(hs, buf, 1), pi = pair_idx(hs, buf);
-    int rc = upload_kps(c, kl, nl, P.kp + fL * kc);
+    int rc = upload_kps(c, kl, nl, fL * kc);
     if (rc) return rc;
-    rc = upload_kps(c, kr, nr, P.kp + fR * kc);
+    rc = upload_kps(c, kr, nr, fR * kc);
     if (rc) return rc;
     std::vector<int4> hm((size_t)nm);
     std::vector<uint8_t> gl((size_t)nm * 32), gr((size_t)nm * 32);

@@ -186,3 +186,40 @@ def test_orb_soak_many_sequences():
     for seed in (40, 41):
         valid += _run("c2", 400, seed=seed, n_frames=4, max_y_diff=2.0)
     assert valid >= 20
+
+
+def test_orb_flat_image_and_single_blob():
+    flat = np.full((240, 320), 128, np.uint8)
+    blob = flat.copy()
+    blob[100:140, 150:190] = 220
+    ctx = capi.Context(width=320, height=240, orb_nfeats=100, max_seqs=1, detect_method=0)
+    try:
+        for img in (flat, blob):
+            kps, desc = ctx.detect(img)
+            raw = ctx.orb_raw_keypoints(ctx.cfg.max_seqs, 0)
+            ref_k, ref_d = orc.cv2_orb_detect_and_compute(img, 150, 8, 20)
+            _assert_kps_equal(raw, ref_k, "raw")
+            est = orc.OracleEstimator(orc.Params(orb_nfeats=100, detect_method=0), backend="cv2", ransac="off")
+            ok, od, _ = est.detect(img)
+            _assert_kps_equal(kps, ok, "final")
+            assert np.array_equal(desc, od)
+        assert len(ctx.detect(flat)[0]) == 0
+    finally:
+        ctx.close()
+
+
+def test_orb_match_lr_seam_takes_float_keypoints():
+    """svo_match_lr on caller data in a dmORB context: cv::ORB keypoints (float coordinates) go through the stage-3 filter"""
+    frames, _ = synth.make_sequence("c1", seed=21, n_frames=1)
+    L, R = frames[0]
+    ctx = capi.Context(width=320, height=240, orb_nfeats=150, max_seqs=1, detect_method=0, max_y_diff=2.0)
+    try:
+        kl, dl = ctx.detect(L)
+        kr, dr = ctx.detect(R)
+        got = ctx.match_lr(kl, dl, kr, dr)
+        want = orc.lr_filter(orc.cv2_bf_match(dl, dr), kl, kr, False, 2.0, 40, 320)
+        assert len(got) == len(want) > 20
+        assert np.array_equal(got["queryIdx"], want["queryIdx"]) and np.array_equal(got["trainIdx"], want["trainIdx"])
+        assert (kl["x"] != np.floor(kl["x"])).any()          # the coarser levels give non-integer coordinates
+    finally:
+        ctx.close()
