@@ -519,6 +519,10 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
         if (cfg->match_method != 0 || cfg->if_match_method != 0)
             return fail(nullptr, SVO_ERR_ARG, "dmORB is built for the brute-force matchers (smDescBF / ifmDescBF) only");
         if (cfg->sort_mode != 0) return fail(nullptr, SVO_ERR_ARG, "sort_mode 1 is not available with dmORB");
+        {   // the sort scratch of the context (sized by max_corners) must hold detectAndCompute's whole keypoint list
+            const int n_extract = cfg->non_maximal_suppression ? (int)(size_t)(1.5 * cfg->orb_nfeats) : cfg->orb_nfeats;
+            if (cfg->max_corners < 2 * n_extract + 64) return fail(nullptr, SVO_ERR_ARG, "max_corners too small for dmORB (needs 2 x extracted features + 64)");
+        }
         const OrbLevels G = orb_levels(cfg->width, cfg->height, cfg->orb_nlevels, 1);
         if (G.w[cfg->orb_nlevels - 1] < 64 || G.h[cfg->orb_nlevels - 1] < 64)
             return fail(nullptr, SVO_ERR_ARG, "the smallest ORB level must be at least 64 x 64 (lower orb_nlevels)");

@@ -130,6 +130,24 @@ def test_pipeline_orb_c2_equals_oracle():
     assert _run("c2", 500, seed=1, n_frames=4, max_y_diff=2.0) >= 2
 
 
+def test_orb_other_level_counts_and_c3_size():
+    """orb_nlevels = 4 on a c3-sized image (1242x375, 600 features)"""
+    frames, _ = synth.make_sequence("c3", seed=2, n_frames=1)
+    img = frames[0][0]
+    ctx = capi.Context(width=1242, height=375, orb_nfeats=400, max_seqs=1, detect_method=0, orb_nlevels=4, max_corners=32768)
+    try:
+        kps, desc = ctx.detect(img)
+        raw = ctx.orb_raw_keypoints(ctx.cfg.max_seqs, 0)
+        ref_k, _ = orc.cv2_orb_detect_and_compute(img, 600, 4, 20)
+        _assert_kps_equal(raw, ref_k, "raw, 4 levels")
+        est = orc.OracleEstimator(orc.Params(orb_nfeats=400, detect_method=0, orb_nlevels=4), backend="cv2", ransac="off")
+        ok, od, _ = est.detect(img)
+        _assert_kps_equal(kps, ok, "final, 4 levels")
+        assert np.array_equal(desc, od) and set(kps["octave"]) <= {0, 1, 2, 3}
+    finally:
+        ctx.close()
+
+
 def test_orb_config_is_validated():
     with pytest.raises(Exception):
         capi.Context(width=640, height=480, max_seqs=1, detect_method=0, n_octaves=2)

@@ -85,6 +85,18 @@ def test_orb_core_equals_opencv_detect_and_compute(orb_lib, nfeatures, fast_th):
     assert total > 500
 
 
+@pytest.mark.parametrize("nlevels", [1, 4, 6])
+def test_orb_core_other_level_counts(orb_lib, nlevels):
+    """params_detect.orb_nlevels other than the default 8"""
+    for img in _cases()[:4]:
+        orb = cv2.ORB_create(400, 1.2, nlevels, 31, 0, 2, cv2.ORB_HARRIS_SCORE, 31, 20)
+        kps, d = orb.detectAndCompute(img, None)
+        mine, md, _ = host_orb(orb_lib, img, 400, nlevels, 20)
+        ref = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float32).reshape(-1, 6)
+        assert np.array_equal(ref, mine)
+        assert np.array_equal(d, md)
+
+
 def test_orb_resize_is_inter_linear_exact(orb_lib):
     rng = np.random.default_rng(0)
     for (W, H) in [(640, 480), (752, 480), (1242, 375), (320, 240), (533, 400), (89, 67)]:
