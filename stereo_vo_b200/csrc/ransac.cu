@@ -4,7 +4,7 @@
 // OpenCV's estimator is sequential (adaptive iteration count, one RNG stream), but iteration k's
 // sample does not depend on the models of earlier iterations: thread 0 draws the next RS_BATCH samples
 // from the exact cv::RNG stream (including the duplicate and collinearity re-draws), every warp solves
-// three of them side by side and scores their models, and thread 0 then replays OpenCV's "best so far /
+// one of them (its Jacobi rotations as a wavefront) and the CTA scores their models, and thread 0 then replays OpenCV's "best so far /
 // update niters" logic in iteration order.  The result is the inlier mask OpenCV returns (see fundmat_core.cuh for the one
 // floating-point caveat).  With >= 15 points this is RANSAC, with 8..14 LMedS, with 7 an all-ones mask
 // and with < 7 no mask (zero inliers), as in cv::findFundamentalMat.
@@ -13,8 +13,8 @@
 
 namespace svo {
 
-constexpr int RS_WARPS = 2;                      // warps per (stereo pair, side) problem
-constexpr int RS_GROUPS = 3;                     // 7-point samples solved side by side in one warp (9 lanes each)
+constexpr int RS_WARPS = 6;                      // warps per (stereo pair, side) problem
+constexpr int RS_GROUPS = 1;                     // 7-point samples per warp (run_7point_wave: one, its row pairs side by side)
 constexpr int RS_BATCH = RS_WARPS * RS_GROUPS;   // RANSAC iterations evaluated per round
 constexpr int RS_THREADS = RS_WARPS * 32;
 
@@ -33,7 +33,7 @@ struct RsShared {
     CvRng rng_after[RS_BATCH];     // speculative sampling: the RNG state behind every sample of the round
     int idx[RS_BATCH][7];
     int collinear[RS_BATCH];
-    double svd[RS_WARPS][16 * 32];  // run_7point_warp3's rows, [row][lane] per warp
+    double svd[RS_WARPS][96];       // run_7point_wave's rows and norms, per warp
 };
 
 // S4:181-232: point sets of the left-left and right-right problems from the greedy-filtered lists
@@ -73,128 +73,156 @@ __device__ __forceinline__ double ordered_sum9(double v, int base) {
 }
 
 // run_7point with the SVD step (fm7_svd_rows: OpenCV's one-sided Jacobi on the rows of the 7x9 system, then the two
-// extra right singular vectors) spread over the warp, three samples side by side: lanes 9g .. 9g+8 own the nine columns
-// of sample g's rows.  Every rotation / projection touches its element with exactly the operations of the sequential
-// loops and every dot product is summed in the sequential order (ordered_sum9), so f1 / f2 and the models are
-// bit-identical to the host build of fundmat_core.cuh that is pinned against cv2.  The three samples run in lockstep:
-// OpenCV's data-dependent branches ("rows already orthogonal: skip", "beta < 0", hypot's operand order, "no rotation in
-// this sweep: stop") are evaluated as selects, a skipped rotation leaves its rows untouched, and a sample that has
-// converged idles through the sweeps the others still need (a converged sweep changes nothing).
-// The rows live in shared memory (svd: 16 x 32 doubles of this warp, element [row][lane], only ever touched by its own
-// lane), so that the pair loops are real loops: fully unrolled on register arrays the function was 250 KB of code and
-// the kernel spent half of its issue slots waiting for instructions.  Out of line for the same reason.
-// ms1 / ms2: RS_GROUPS x 7 points, valid[g] != 1 marks an unused group; F: RS_GROUPS x 27, nm_out: RS_GROUPS counts,
-// written by the first lane of each group.  All 32 lanes must call it.
-__device__ __noinline__ void run_7point_warp3(const Pt2f (*ms1)[7], const Pt2f (*ms2)[7], const int* valid, double (*F)[27],
-                                              int* nm_out, double* svd) {
+// extra right singular vectors) by ONE WARP PER SAMPLE, the rotations of a sweep as a wavefront.
+// OpenCV walks the row pairs (i, j), i < j, in order; pair (i, j) only needs row i as (i, j-1) left it and row j as
+// (i-1, j) left it, so all pairs with the same i + j are independent: 11 wavefront steps of up to three pairs replace the
+// 21 sequential pair steps of a sweep (the chain of IEEE divisions and square roots per pair is what the kernel waits
+// for).  Lanes 9p .. 9p+8 (p = 0..2) own the nine columns of the p-th pair of the step.  Every rotation touches its
+// elements with exactly the operations of the sequential loops, every dot product is summed in the sequential order
+// (ordered_sum9), a pair sees exactly the rows and norms the sequential order would hand it, and "changed" is an OR:
+// f1 / f2 and the models are bit-identical to the host build of fundmat_core.cuh that is pinned against cv2.
+// OpenCV's data-dependent branches ("rows already orthogonal: skip", "beta < 0", hypot's operand order) are selects.
+// The rows live in shared memory (svd: 96 doubles of this warp: rows[9][9], then W[7]); loops stay loops and the function
+// out of line: fully unrolled on register arrays it was 250 KB of code and the kernel waited for instructions.
+// ms1 / ms2: the sample's 7 points, valid[0] != 1 marks an unused warp; F: 27 doubles, nm_out: the model count.
+// All 32 lanes must call it.
+__device__ __noinline__ void run_7point_wave(const Pt2f (*ms1)[7], const Pt2f (*ms2)[7], const int* valid, double (*F)[27],
+                                             int* nm_out, double* svd) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
-    const int g = lane < 27 ? lane / 9 : 2;
-    const int base = 9 * g;
-    const int kcol = lane - base;                      // 0..8: a column; 9..13 (lanes 27..31): no column
-    const bool colv = kcol < 9;
-    const Pt2f* m1 = ms1[g];
-    const Pt2f* m2 = ms2[g];
+    const int pg = lane < 27 ? lane / 9 : 2;           // pair of the wavefront step this lane works for
+    const int base = 9 * pg;
+    const int k = lane - base;                         // 0..8: a column; 9..13 (lanes 27..31): no column
+    const bool colv = k < 9;
+    const int kc = colv ? k : 0;
+    const Pt2f* m1 = ms1[0];
+    const Pt2f* m2 = ms2[0];
     Fm7Norm nm;
-    bool ok = valid[g] == 1;
+    bool ok = valid[0] == 1;
     if (ok) ok = fm7_normalise(m1, m2, nm);
     const int m = 9, n = 7;
     const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
-    double* const col = svd + lane;                    // row i of this lane's column: col[32 * i], i < 9
-    double* const W = svd + 9 * 32 + lane;             // W[32 * i], i < 7
-    // an unused / degenerate group works on orthonormal dummy rows: no rotations, no zero singular values
+    double* const rows = svd;                          // rows[9 * i + k], i < 9
+    double* const W = svd + 81;                        // W[i], i < 7
+    // an unused / degenerate sample works on orthonormal dummy rows: no rotations, no zero singular values
+    for (int i = pg; i < 7; i += 3)
+        if (colv) rows[9 * i + k] = ok ? fm7_entry(m1, m2, nm, i, k) : (k == i ? 1.0 : 0.0);
+    if (pg == 0 && colv) { rows[63 + k] = 0.0; rows[72 + k] = 0.0; }
+    __syncwarp();
 #pragma unroll 1
-    for (int i = 0; i < 7; ++i) col[32 * i] = !colv ? 0.0 : (ok ? fm7_entry(m1, m2, nm, i, kcol) : (kcol == i ? 1.0 : 0.0));
-    col[32 * 7] = col[32 * 8] = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < 7; ++i) W[32 * i] = ordered_sum9(col[32 * i] * col[32 * i], base);
+    for (int i0 = 0; i0 < 7; i0 += 3) {
+        const int i = min(i0 + pg, 6);
+        const double c = rows[9 * i + kc];
+        const double w = ordered_sum9(c * c, base);
+        if (k == 0 && i0 + pg < 7) W[i] = w;
+    }
+    __syncwarp();
 #pragma unroll 1
     for (int iter = 0; iter < 30; ++iter) {
         bool changed = false;
 #pragma unroll 1
-        for (int i = 0; i < n - 1; ++i) {
-#pragma unroll 1
-            for (int j = i + 1; j < n; ++j) {
-                const double ci = col[32 * i], cj = col[32 * j];
-                const double a = W[32 * i], b = W[32 * j];
-                double p = ordered_sum9(ci * cj, base);
-                const bool rot = !(fabs(p) <= eps * sqrt(a * b));
-                if (!__any_sync(full, rot)) continue;  // warp-uniform
-                p *= 2;
-                const double beta = a - b;
-                // gamma = cv_hypot(p, beta)
-                const double ap = fabs(p), ab = fabs(beta);
-                const double hi = ap > ab ? ap : ab, lo = ap > ab ? ab : ap;
-                const double q = lo / hi;
-                const double gamma = hi > 0 ? hi * sqrt(1 + q * q) : 0.0;
-                // beta < 0: s = sqrt(((gamma - beta)*0.5)/gamma), c = p/(gamma*s*2); else c = sqrt((gamma+beta)/(gamma*2)), s = p/(gamma*c*2)
-                const bool neg = beta < 0;
-                const double num = neg ? (gamma - beta) * 0.5 : (gamma + beta);
-                const double den = neg ? gamma : gamma * 2;
-                const double first = sqrt(num / den);
-                const double second = p / (gamma * first * 2);
-                const double c = neg ? second : first, s = neg ? first : second;
-                const double t0 = c * ci + s * cj;
-                const double t1 = -s * ci + c * cj;
-                const double wa = ordered_sum9(t0 * t0, base), wb = ordered_sum9(t1 * t1, base);
-                if (rot) { col[32 * i] = t0; col[32 * j] = t1; W[32 * i] = wa; W[32 * j] = wb; changed = true; }
+        for (int t = 1; t <= 2 * n - 3; ++t) {         // pairs (i, t - i), max(0, t - 6) <= i <= (t - 1) / 2
+            const int imin = t > n - 1 ? t - (n - 1) : 0, imax = (t - 1) / 2;
+            const bool has = colv && imin + pg <= imax;
+            const int i = has ? imin + pg : 0, j = has ? t - i : 1;
+            const double ci = rows[9 * i + kc], cj = rows[9 * j + kc];
+            const double a = W[i], b = W[j];
+            double p = ordered_sum9(ci * cj, base);
+            const bool rot = has && !(fabs(p) <= eps * sqrt(a * b));
+            if (!__any_sync(full, rot)) continue;      // warp-uniform; nothing was written
+            p *= 2;
+            const double beta = a - b;
+            // gamma = cv_hypot(p, beta)
+            const double ap = fabs(p), ab = fabs(beta);
+            const double hi = ap > ab ? ap : ab, lo = ap > ab ? ab : ap;
+            const double q = lo / hi;
+            const double gamma = hi > 0 ? hi * sqrt(1 + q * q) : 0.0;
+            // beta < 0: s = sqrt(((gamma - beta)*0.5)/gamma), c = p/(gamma*s*2); else c = sqrt((gamma+beta)/(gamma*2)), s = p/(gamma*c*2)
+            const bool neg = beta < 0;
+            const double num = neg ? (gamma - beta) * 0.5 : (gamma + beta);
+            const double den = neg ? gamma : gamma * 2;
+            const double first = sqrt(num / den);
+            const double second = p / (gamma * first * 2);
+            const double c = neg ? second : first, s = neg ? first : second;
+            const double t0 = c * ci + s * cj;
+            const double t1 = -s * ci + c * cj;
+            const double wa = ordered_sum9(t0 * t0, base), wb = ordered_sum9(t1 * t1, base);
+            __syncwarp();                              // every lane holds its operands: the pairs of a step share no row
+            if (rot) {
+                rows[9 * i + kc] = t0; rows[9 * j + kc] = t1;
+                if (k == 0) { W[i] = wa; W[j] = wb; }
+                changed = true;
             }
+            __syncwarp();
         }
         if (!__any_sync(full, changed)) break;
     }
 #pragma unroll 1
-    for (int i = 0; i < n; ++i) W[32 * i] = sqrt(ordered_sum9(col[32 * i] * col[32 * i], base));
-#pragma unroll 1
-    for (int i = 0; i < n - 1; ++i) {                  // selection sort, descending; first maximum wins
-        int j = i;
-        double wj = W[32 * i];
-        for (int k = i + 1; k < n; ++k) if (wj < W[32 * k]) { j = k; wj = W[32 * k]; }
-        if (j != i) {
-            const double tw = W[32 * i]; W[32 * i] = W[32 * j]; W[32 * j] = tw;
-            const double tc = col[32 * i]; col[32 * i] = col[32 * j]; col[32 * j] = tc;
-        }
+    for (int i0 = 0; i0 < 7; i0 += 3) {
+        const int i = min(i0 + pg, 6);
+        const double c = rows[9 * i + kc];
+        const double w = sqrt(ordered_sum9(c * c, base));
+        __syncwarp();
+        if (k == 0 && i0 + pg < 7) W[i] = w;
     }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < n - 1; ++i) {                  // selection sort, descending; first maximum wins (uniform over the warp)
+        int j = i;
+        double wj = W[i];
+        for (int kk = i + 1; kk < n; ++kk) if (wj < W[kk]) { j = kk; wj = W[kk]; }
+        __syncwarp();
+        if (j != i) {
+            if (lane == 0) { const double tw = W[i]; W[i] = W[j]; W[j] = tw; }
+            if (pg == 0 && colv) { const double tc = rows[9 * i + k]; rows[9 * i + k] = rows[9 * j + k]; rows[9 * j + k] = tc; }
+        }
+        __syncwarp();
+    }
+    // the rows of the null space: every lane group repeats the same computation on the same rows (all 32 lanes take part
+    // in the shuffles), group 0 writes
     CvRng rng;
     rng.state = 0x12345678;
 #pragma unroll 1
     for (int i = 0; i < 9; ++i) {
-        double sd = i < n ? W[32 * i] : 0;
+        double sd = i < n ? W[i] : 0;
+        double ci_cur = rows[9 * i + kc];
 #pragma unroll 1
         for (int ii = 0; ii < 100; ++ii) {
-            const bool need = sd <= minval;            // this group draws another vector
-            if (!__any_sync(full, need)) break;
+            const bool need = sd <= minval;            // draw another vector
+            if (!need) break;                          // uniform: sd is the same on every lane
             const double val0 = 1. / m;
             double v = 0;
-            CvRng r2 = rng;
-            for (int k = 0; k < m; ++k) {
-                const double vk = (r2.next() & 256) != 0 ? val0 : -val0;
-                if (k == kcol) v = vk;
+            for (int kk = 0; kk < m; ++kk) {
+                const double vk = (rng.next() & 256) != 0 ? val0 : -val0;
+                if (kk == kc) v = vk;
             }
-            if (need) rng = r2;
-            double ci = need ? v : col[32 * i];
+            double ci = v;
 #pragma unroll 1
             for (int it2 = 0; it2 < 2; ++it2) {
 #pragma unroll 1
                 for (int j = 0; j < i; ++j) {
-                    const double cj = col[32 * j];
+                    const double cj = rows[9 * j + kc];
                     const double d = ordered_sum9(ci * cj, base);
-                    const double t = ci - d * cj;
-                    double asum = ordered_sum9(fabs(t), base);
+                    const double tt = ci - d * cj;
+                    double asum = ordered_sum9(fabs(tt), base);
                     asum = asum > eps * 100 ? 1 / asum : 0;
-                    ci = t * asum;
+                    ci = tt * asum;
                 }
             }
-            const double nsd = sqrt(ordered_sum9(ci * ci, base));
-            if (need) { col[32 * i] = ci; sd = nsd; }
+            sd = sqrt(ordered_sum9(ci * ci, base));
+            ci_cur = ci;
         }
+        // lanes without a column (27..31) ran on group 2's sums: sd and the loop trip count are the same everywhere
         const double sc = sd > minval ? 1 / sd : 0.;
-        col[32 * i] *= sc;
+        __syncwarp();
+        if (pg == 0 && colv) rows[9 * i + k] = ci_cur * sc;
+        __syncwarp();
     }
-    double f1[9], f2[9];
-    const double c7 = col[32 * 7], c8 = col[32 * 8];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) { f1[j] = __shfl_sync(full, c7, base + j); f2[j] = __shfl_sync(full, c8, base + j); }
-    if (kcol == 0 && lane < 27) nm_out[g] = ok ? fm7_finish(f1, f2, nm, F[g]) : 0;
+    if (lane == 0) {
+        double f1[9], f2[9];
+        for (int j = 0; j < 9; ++j) { f1[j] = rows[63 + j]; f2[j] = rows[72 + j]; }
+        nm_out[0] = ok ? fm7_finish(f1, f2, nm, F[0]) : 0;
+    }
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -287,10 +315,10 @@ fundmat_kernel(RansacScratch R) {
             }
         }
         __syncthreads();
-        // ---- every warp: solve its three samples ---------------------------------------------------------
+        // ---- every warp: solve its sample -----------------------------------------------------------------
         const int w0 = wid * RS_GROUPS;
         if (sh.found[w0] == 1)                         // samples are drawn in order: none of the later ones without the first
-            run_7point_warp3(sh.ms1 + w0, sh.ms2 + w0, sh.found + w0, sh.F + w0, sh.nmodels + w0, sh.svd[wid]);
+            run_7point_wave(sh.ms1 + w0, sh.ms2 + w0, sh.found + w0, sh.F + w0, sh.nmodels + w0, sh.svd[wid]);
         __syncthreads();
         // ---- OpenCV's sequential loop over the iterations of this round: the whole CTA scores one sample's models,
         //      thread 0 does the "best so far / update niters" bookkeeping; samples beyond the (shrinking) iteration
@@ -440,7 +468,7 @@ fm7_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, int n_s
     __shared__ Pt2f s1[RS_BATCH][7], s2[RS_BATCH][7];
     __shared__ double sF[RS_BATCH][27];
     __shared__ int sv[RS_BATCH], sn[RS_BATCH];
-    __shared__ double s_svd[RS_WARPS][16 * 32];
+    __shared__ double s_svd[RS_WARPS][96];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int w0 = wid * RS_GROUPS;
     const int set0 = (blockIdx.x * RS_WARPS + wid) * RS_GROUPS;
@@ -455,7 +483,7 @@ fm7_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, int n_s
         if (lane < 27) sF[w0 + g][lane] = 0;
     }
     __syncwarp();
-    run_7point_warp3(s1 + w0, s2 + w0, sv + w0, sF + w0, sn + w0, s_svd[wid]);
+    run_7point_wave(s1 + w0, s2 + w0, sv + w0, sF + w0, sn + w0, s_svd[wid]);
     __syncwarp();
     for (int g = 0; g < RS_GROUPS; ++g) {
         const int set = set0 + g;
