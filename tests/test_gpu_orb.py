@@ -241,3 +241,43 @@ def test_orb_match_lr_seam_takes_float_keypoints():
         assert (kl["x"] != np.floor(kl["x"])).any()          # the coarser levels give non-integer coordinates
     finally:
         ctx.close()
+
+
+def _rows(k):
+    return np.stack([k["x"], k["y"], k["size"], k["angle"], k["response"], k["octave"].astype(np.float32)], 1).astype(np.float32)
+
+
+def test_orb_against_the_committed_opencv_golden():
+    """tests/golden/golden_orb.npz (generated from cv2 by make_golden_orb.py): raw + final keypoints and descriptors of three
+    cases, and a 3-frame c1 sequence through the whole pipeline (matches, RANSAC masks, tracked pairs, status, pose)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_orb.npz"))
+    for ci, case in enumerate(g["cases"]):
+        cfg, seed, nfeats, th = str(case).split()
+        frames, _ = synth.make_sequence(cfg, seed=int(seed), n_frames=1)
+        img = frames[0][0]
+        ctx = capi.Context(width=img.shape[1], height=img.shape[0], orb_nfeats=int(nfeats), max_seqs=1, detect_method=0,
+                           fast_threshold=int(th), max_corners=32768)
+        try:
+            kps, desc = ctx.detect(img)
+            assert np.array_equal(_rows(ctx.orb_raw_keypoints(ctx.cfg.max_seqs, 0)), g[f"case{ci}_raw_kps"]), f"case {ci}: raw keypoints"
+            assert np.array_equal(_rows(kps), g[f"case{ci}_final_kps"]) and np.array_equal(desc, g[f"case{ci}_final_desc"]), f"case {ci}: final"
+        finally:
+            ctx.close()
+    frames, cam = synth.make_sequence("c1", seed=4, n_frames=3)
+    gc = capi.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    ctx = capi.Context(width=320, height=240, orb_nfeats=150, max_seqs=1, detect_method=0)
+    try:
+        for i, (L, R) in enumerate(frames):
+            r = ctx.process_batch([L], [R], [gc], slots=[0])[0]
+            assert np.array_equal(_rows(ctx.keypoints(0, 0, 0)), g[f"seq_f{i}_kpsL"]) and np.array_equal(ctx.descriptors(0, 0, 0), g[f"seq_f{i}_descL"])
+            m = ctx.matches(0, 0)
+            assert np.array_equal(np.stack([m["queryIdx"], m["trainIdx"], m["distance"].astype(np.int32)], 1), g[f"seq_f{i}_matches"])
+            assert [r.error_code, int(r.valid), r.num_it, r.num_it_final] == g[f"seq_f{i}_status"].tolist()
+            if i > 0:
+                _, _, _, il, ir = ctx.track_candidates(0)
+                assert np.array_equal(il, g[f"seq_f{i}_inlL"]) and np.array_equal(ir, g[f"seq_f{i}_inlR"])
+                assert np.array_equal(ctx.tracked_pairs(0), g[f"seq_f{i}_tracked"])
+                np.testing.assert_allclose(r.delta_pose[:], g[f"seq_f{i}_delta"], atol=1e-9)
+    finally:
+        ctx.close()

@@ -114,3 +114,15 @@ def test_retain_best_walks_the_heap_select_path(orb_lib):
     orb_lib.orb_host_levels(640, 480, 8, 750, _p(scale), _p(w), _p(h), _p(nf))
     assert list(w) == [640, 533, 444, 370, 309, 257, 214, 179] and list(h) == [480, 400, 333, 278, 231, 193, 161, 134]
     assert int(nf.sum()) == 750 and nf[0] > nf[1] > nf[6]
+
+
+def test_orb_core_equals_committed_golden(orb_lib):
+    """the committed cv2-generated fixture (tests/golden/make_golden_orb.py): raw detectAndCompute output of three cases"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_orb.npz"))
+    for ci, case in enumerate(g["cases"]):
+        cfg, seed, nfeats, th = str(case).split()
+        frames, _ = synth.make_sequence(cfg, seed=int(seed), n_frames=1)
+        mine, md, _ = host_orb(orb_lib, frames[0][0], int(1.5 * int(nfeats)), 8, int(th))
+        # host_orb rows: x, y, size, angle, response, octave (same column order as the fixture)
+        assert np.array_equal(mine, g[f"case{ci}_raw_kps"]), f"case {ci}: keypoints"
+        assert np.array_equal(md, g[f"case{ci}_raw_desc"]), f"case {ci}: descriptors"
