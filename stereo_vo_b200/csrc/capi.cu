@@ -516,8 +516,6 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
     if (cfg->detect_method == 0) {
         if (n_oct != 1) return fail(nullptr, SVO_ERR_ARG, "dmORB builds its own pyramid: n_octaves must be 1 (stage2_detect.cpp:460)");
         if (cfg->orb_nlevels < 1 || cfg->orb_nlevels > kOrbMaxLevels) return fail(nullptr, SVO_ERR_ARG, "orb_nlevels must be within [1, 8]");
-        if (cfg->match_method != 0 || cfg->if_match_method != 0)
-            return fail(nullptr, SVO_ERR_ARG, "dmORB is built for the brute-force matchers (smDescBF / ifmDescBF) only");
         if (cfg->sort_mode != 0) return fail(nullptr, SVO_ERR_ARG, "sort_mode 1 is not available with dmORB");
         {   // the sort scratch of the context (sized by max_corners) must hold detectAndCompute's whole keypoint list
             const int n_extract = cfg->non_maximal_suppression ? (int)(size_t)(1.5 * cfg->orb_nfeats) : cfg->orb_nfeats;

@@ -404,6 +404,14 @@ __device__ __forceinline__ int count_rows_le(RowOf rows, int n, int r) {
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (rows(mid) <= r) lo = mid + 1; else hi = mid; }
     return lo;
 }
+// the same for float rows (dmORB keypoints): the reference compares pt.y <= int(y) in float (S3:436)
+template <class RowOf>
+__device__ __forceinline__ int count_rows_le_f(RowOf rows, int n, int r) {
+    int lo = 0, hi = n;
+    const float rf = (float)r;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (rows(mid) <= rf) lo = mid + 1; else hi = mid; }
+    return lo;
+}
 
 // pyr_feats_index as m_update_indexes leaves it (S2:103-129): rows before the first feature row and from the last
 // feature row on hold 0, the others the number of features with row <= r.
@@ -462,9 +470,9 @@ rbr_match_kernel(Pools P) {
             const int L0 = idxL[y], L1 = idxL[y + 1];
             const int R0 = idxR[max(0, y - tol)], R1 = idxR[min(H - 1, y + tol)];
             if (i >= L0 && i < L1 && R1 != R0) {
-                const float xl = (float)(l.x & 0xFFFF);
+                const float xl = kp_xy(P, fL * cap, i).x;
                 for (int j = R0; j < R1; ++j) {
-                    const int disparity = (int)(xl - (float)(kpR[j].x & 0xFFFF));
+                    const int disparity = (int)__fsub_rn(xl, kp_xy(P, fR * cap, j).x);      // S3:285: float difference, truncated
                     if (disparity < 1 || disparity > max_disparity) continue;
                     const unsigned d = hamming256_u8(dL + 2 * (size_t)i, dR + 2 * (size_t)j);
                     if (d > max_distance) continue;
@@ -537,19 +545,17 @@ win_track_kernel(Pools P) {
     const int Mp = st.has_prev ? P.n_match[pair_idx(slot, prev)] : 0;
     const int4* __restrict__ mp = P.match + pair_idx(slot, prev) * cap;
     const int4* __restrict__ mc = P.match + pair_idx(slot, cur) * cap;
-    const int2* __restrict__ pL = P.kp + frame_idx(slot, prev, 0) * cap;
-    const int2* __restrict__ pR = P.kp + frame_idx(slot, prev, 1) * cap;
-    const int2* __restrict__ cL = P.kp + frame_idx(slot, cur, 0) * cap;
-    const int2* __restrict__ cR = P.kp + frame_idx(slot, cur, 1) * cap;
+    const size_t fpL = frame_idx(slot, prev, 0) * cap, fpR = frame_idx(slot, prev, 1) * cap;
+    const size_t fcL = frame_idx(slot, cur, 0) * cap, fcR = frame_idx(slot, cur, 1) * cap;
     const uint4* __restrict__ pD = P.desc + frame_idx(slot, prev, 0) * cap * 2;
     const uint4* __restrict__ cD = P.desc + frame_idx(slot, cur, 0) * cap * 2;
 
     // matches_lr_row_index[y] = number of matches whose left keypoint lies above row y; [H] = number of left features
     for (int y = tid; y <= H; y += FT) {
         pidx[y] = y == H ? P.n_kp[frame_idx(slot, prev, 0)]
-                         : count_rows_le([&](int k) { return (int)((unsigned)pL[mp[k].x].x >> 16); }, Mp, y - 1);
+                         : count_rows_le_f([&](int k) { return kp_xy(P, fpL, mp[k].x).y; }, Mp, y - 1);
         cidx[y] = y == H ? P.n_kp[frame_idx(slot, cur, 0)]
-                         : count_rows_le([&](int k) { return (int)((unsigned)cL[mc[k].x].x >> 16); }, Mc, y - 1);
+                         : count_rows_le_f([&](int k) { return kp_xy(P, fcL, mc[k].x).y; }, Mc, y - 1);
     }
     for (int k = tid; k < Mc; k += FT) curm[k] = 0xFFFFFFFFu;
     __syncthreads();
@@ -557,22 +563,24 @@ win_track_kernel(Pools P) {
     const int win_w = P.p.ifm_win_w, win_h = P.p.ifm_win_h;
     for (int pi = tid; pi < Mp; pi += FT) {
         const int4 m = mp[pi];
-        const int2 a = pL[m.x], b = pR[m.y];
-        const int y = (int)((unsigned)a.x >> 16);
+        const float2 a = kp_xy(P, fpL, m.x), b = kp_xy(P, fpR, m.y);
+        // the loop row that owns this match: pidx[y] <= pi < pidx[y + 1], i.e. the first y with pt.y <= y (S3:436) -- the row
+        // itself for integer coordinates, the next one for dmORB's fractional ones
+        const int y = (int)ceilf(a.y);
         if (y >= H - 1) continue;                                         // S4:512: rows 0 .. H-2
         const int p0 = pidx[y], p1 = pidx[y + 1];
         if (pi < p0 || pi >= p1) continue;
         const int wy_min = max(0, y - win_w), wy_max = min(H - 1, y + win_w);     // sic: the vertical window uses win_w
         const int c0 = cidx[wy_min], c1 = min(cidx[wy_max + 1], Mc);
         if (c1 <= c0) continue;
-        const float axf = (float)(a.x & 0xFFFF), bxf = (float)(b.x & 0xFFFF);
-        const int xl0 = max(0, (int)(axf - (float)win_h)), xl1 = min(W - 1, (int)(axf + (float)win_h));
-        const int xr0 = max(0, (int)(bxf - (float)win_h)), xr1 = min(W - 1, (int)(bxf + (float)win_h));
+        const float axf = a.x, bxf = b.x;
+        const int xl0 = max(0, (int)__fsub_rn(axf, (float)win_h)), xl1 = min(W - 1, (int)__fadd_rn(axf, (float)win_h));
+        const int xr0 = max(0, (int)__fsub_rn(bxf, (float)win_h)), xr1 = min(W - 1, (int)__fadd_rn(bxf, (float)win_h));
         unsigned best = 255u, best_ci = 0xFFFFu;
         for (int ci = c0; ci < c1; ++ci) {
             const int4 c = mc[ci];
-            const int fx = cL[c.x].x & 0xFFFF, gx = cR[c.y].x & 0xFFFF;
-            if (fx < xl0 || fx > xl1 || gx < xr0 || gx > xr1) continue;
+            const float fx = kp_xy(P, fcL, c.x).x, gx = kp_xy(P, fcR, c.y).x;
+            if (fx < (float)xl0 || fx > (float)xl1 || gx < (float)xr0 || gx > (float)xr1) continue;
             const unsigned d = hamming256_u8(pD + 2 * (size_t)m.x, cD + 2 * (size_t)c.x);   // left descriptors only (S4:585-603)
             if (d < best) { best = d; best_ci = (unsigned)ci; }
         }

@@ -232,9 +232,6 @@ void CStereoOdometryEstimator::throw_last(svo_ctx* c, const char* what) {
 void CStereoOdometryEstimator::check_methods() const {
     if (params_detect.detect_method != TDetectParams::dmFAST_ORB && params_detect.detect_method != TDetectParams::dmORB)
         throw std::runtime_error("[Visual Odometry Error] Detect method not correct (this build has dmFAST_ORB and dmORB).");
-    if (params_detect.detect_method == TDetectParams::dmORB &&
-        (params_lr_match.match_method != TLeftRightMatchParams::smDescBF || params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescBF))
-        throw std::runtime_error("[Visual Odometry Error] dmORB is built for smDescBF / ifmDescBF only.");
     if (params_lr_match.match_method != TLeftRightMatchParams::smDescBF && params_lr_match.match_method != TLeftRightMatchParams::smDescRbR)
         throw std::runtime_error("[Visual Odometry Error] Stereo matching method not correct (this build has smDescBF and smDescRbR).");
     if (params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescBF && params_if_match.ifm_method != TInterFrameMatchingParams::ifmDescWin)

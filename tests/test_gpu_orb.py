@@ -148,11 +148,42 @@ def test_orb_other_level_counts_and_c3_size():
         ctx.close()
 
 
+@pytest.mark.parametrize("match_method,ifm_method", [(1, 0), (0, 1), (1, 1)])
+def test_pipeline_orb_with_the_band_limited_matchers(match_method, ifm_method):
+    """dmORB keypoints (float coordinates) through smDescRbR (S3:185-419) and ifmDescWin (S4:435-738): the float
+    comparisons of those branches (disparity, row lists pt.y <= int(y), column windows) against the oracle, which
+    tests/test_ref_cpu.py pins against the reference's compiled text for these combinations"""
+    frames, cam = synth.make_sequence("c1", seed=61, n_frames=5)
+    ctx = capi.Context(width=320, height=240, orb_nfeats=150, max_seqs=1, detect_method=0, match_method=match_method,
+                       if_match_method=ifm_method, max_y_diff=2.0)
+    est = orc.OracleEstimator(orc.Params(orb_nfeats=150, detect_method=0, match_method=match_method, ifm_method=ifm_method, max_y_diff=2.0),
+                              backend="cv2", ransac="cv2_tolerant")
+    oc = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    gc = capi.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    try:
+        n_tracked = 0
+        for i, (L, R) in enumerate(frames):
+            o = est.process_new_image_pair(L, R, oc)
+            r = ctx.process_batch([L], [R], [gc], slots=[0])[0]
+            f = o["frame"]
+            _assert_kps_equal(ctx.keypoints(0, 0, 0), f.kpsL, f"frame {i} left")
+            m = ctx.matches(0, 0)
+            assert np.array_equal(np.stack([m["queryIdx"], m["trainIdx"], m["distance"].astype(np.int32), m["imgIdx"]], 1),
+                                  np.stack([f.matches["queryIdx"], f.matches["trainIdx"], f.matches["distance"].astype(np.int32), f.matches["imgIdx"]], 1)), f"frame {i}: stereo matches"
+            if i > 0:
+                assert np.array_equal(ctx.tracked_pairs(0), o["tracked"]), f"frame {i}: tracked pairs"
+                n_tracked += len(o["tracked"])
+            assert (r.error_code, bool(r.valid), r.num_it, r.num_it_final) == (o["error_code"], o["valid"], o["num_it"], o["num_it_final"]), f"frame {i}"
+            if o["pose"] is not None:
+                np.testing.assert_allclose(r.delta_pose[:], o["pose"]["delta"], atol=1e-4)
+        assert n_tracked > 40
+    finally:
+        ctx.close()
+
+
 def test_orb_config_is_validated():
     with pytest.raises(Exception):
         capi.Context(width=640, height=480, max_seqs=1, detect_method=0, n_octaves=2)
-    with pytest.raises(Exception):
-        capi.Context(width=640, height=480, max_seqs=1, detect_method=0, match_method=1)
     with pytest.raises(Exception):
         capi.Context(width=640, height=480, max_seqs=1, detect_method=2)
 

@@ -257,6 +257,13 @@ def test_dmorb_branch_equals_reference():
     assert run_both("c1", 100, 60, 4, detect_method=0) == 4
 
 
+@pytest.mark.parametrize("kw", [dict(match_method=1), dict(ifm_method=1), dict(match_method=1, ifm_method=1)])
+def test_dmorb_with_the_band_limited_matchers_equals_reference(kw):
+    """dmORB's float keypoints through smDescRbR / ifmDescWin: the float comparisons of those branches"""
+    pytest.importorskip("cv2")
+    assert run_both("c1", 100, 61, 4, detect_method=0, **kw) == 4
+
+
 def test_reference_dump_files(tmp_path):
     """vo_save_files: the reference's own writers (P:179-204,278-287, S4:80-82,173-234,308-327, S5:477-492,703-713)
     produce the per-frame files the host shim reproduces; their contents agree with the state read back."""
