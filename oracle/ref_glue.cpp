@@ -144,10 +144,15 @@ void svo_ref_set_ids(void* h, const int64_t* ids, int n) { std::vector<size_t> v
 int svo_ref_process(void* h, const uint8_t* L, const uint8_t* R, int w, int hgt, int stride, const double* camv, int repeat, double* out) {
     Handle* H = (Handle*)h;
     char cwd[4096];
-    const bool files = H->est.params_general.vo_save_files || H->est.params_general.vo_debug;
-    if (files) {                                       // optimization.txt / dist.txt go to the working directory (S5:479, S3:243)
+    bool files = H->est.params_general.vo_save_files || H->est.params_general.vo_debug;
+    // optimization.txt goes to the working directory (S5:479); the row-by-row matcher ALWAYS writes its debug file
+    // dist.txt there (S3:243): keep both out of the caller's directory
+    const bool rbr = H->est.params_lr_match.match_method == CStereoOdometryEstimator::TLeftRightMatchParams::smDescRbR;
+    if (files || rbr) {
         if (!getcwd(cwd, sizeof cwd)) return -1;
-        if (chdir(H->est.params_general.vo_out_dir.c_str()) != 0) { g_err = "cannot enter vo_out_dir"; return -1; }
+        const char* dir = files ? H->est.params_general.vo_out_dir.c_str() : "/tmp";
+        if (chdir(dir) != 0) { g_err = "cannot enter the output directory"; return -1; }
+        files = true;
     }
     int rc = 0;
     try {
