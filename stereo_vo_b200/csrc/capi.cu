@@ -74,6 +74,9 @@ struct svo_ctx {
     uint8_t* d_stageR = nullptr;
     // kDepth-deep submit/wait pipeline: staging images, pinned meta/result rings, events
     cudaStream_t copy_stream = nullptr;
+    enum { kCopyLanes = 4 };           // scattered uploads (one pointer per image) are spread over several streams: more copy
+    cudaStream_t copy_lane[kCopyLanes] = {};   // descriptors in flight when the host side of the link is busy (8 ranks copying)
+    cudaEvent_t ev_lane[kCopyLanes] = {}, ev_lane_go = nullptr;
     uint8_t* d_stL[kDepth] = {};
     uint8_t* d_stR[kDepth] = {};
     int32_t* r_slots[kDepth] = {};
@@ -665,6 +668,11 @@ int svo_create(const svo_config* cfg, svo_ctx** out) {
 #undef HA
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < svo_ctx::kCopyLanes && e == cudaSuccess; ++k) {
+        e = cudaStreamCreateWithFlags(&c->copy_lane[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_lane[k], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_lane_go, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     for (int j = 0; j < kMaxChunks && e == cudaSuccess; ++j) {
         e = cudaStreamCreateWithFlags(&c->aux[j], cudaStreamNonBlocking);
@@ -692,6 +700,11 @@ void svo_destroy(svo_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (int k = 0; k < svo_ctx::kCopyLanes; ++k) {
+        if (c->copy_lane[k]) { cudaStreamSynchronize(c->copy_lane[k]); cudaStreamDestroy(c->copy_lane[k]); }
+        if (c->ev_lane[k]) cudaEventDestroy(c->ev_lane[k]);
+    }
+    if (c->ev_lane_go) cudaEventDestroy(c->ev_lane_go);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int b = 0; b < kDepth; ++b) { if (c->ev_h2d[b]) cudaEventDestroy(c->ev_h2d[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); }
     for (int j = 0; j < kMaxChunks; ++j) {
@@ -1041,7 +1054,21 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
             memset(&attr, 0, sizeof attr);
             attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;     // the sources stay valid until the matching wait
             size_t attr_idx = 0, fail_idx = 0;
-            eb = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &attr, &attr_idx, 1, &fail_idx, c->copy_stream);
+            const int lanes = (n >= 64 && !getenv("SVO_ONE_COPY_LANE")) ? svo_ctx::kCopyLanes : 1;
+            if (lanes == 1) {
+                eb = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &attr, &attr_idx, 1, &fail_idx, c->copy_stream);
+            } else {
+                // the lanes start behind what the copy stream has queued (the staging buffer's previous user) and meet in it again
+                eb = cudaEventRecord(c->ev_lane_go, c->copy_stream);
+                for (int k = 0; k < lanes && eb == cudaSuccess; ++k) {
+                    const size_t lo = dsts.size() * k / lanes, hi = dsts.size() * (k + 1) / lanes;
+                    eb = cudaStreamWaitEvent(c->copy_lane[k], c->ev_lane_go, 0);
+                    if (eb == cudaSuccess)
+                        eb = cudaMemcpyBatchAsync(dsts.data() + lo, srcs.data() + lo, sizes.data() + lo, hi - lo, &attr, &attr_idx, 1, &fail_idx, c->copy_lane[k]);
+                    if (eb == cudaSuccess) eb = cudaEventRecord(c->ev_lane[k], c->copy_lane[k]);
+                    if (eb == cudaSuccess) eb = cudaStreamWaitEvent(c->copy_stream, c->ev_lane[k], 0);
+                }
+            }
             if (eb != cudaSuccess) { cudaGetLastError(); c->batch_copy_ok = false; }
         }
         if (eb != cudaSuccess)
