@@ -10,6 +10,7 @@
 // filter of ORB::compute is applied before the selection, so the results are identical.
 #include "detect.cuh"
 #include "introsort_emul.cuh"
+#include "corner_lists.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cstdlib>
@@ -417,29 +418,6 @@ fast_blur_kernel(Pools P, const uint8_t* __restrict__ imgL, const uint8_t* __res
 constexpr int K2_THREADS = 256;
 constexpr int K2_SEGS = 4;          // 16-pixel score segments per thread per compaction round
 
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    int wsum = (lane < K2_THREADS / 32) ? s_warp[lane] : 0;
-    int wincl = wsum;
-#pragma unroll
-    for (int o = 1; o < K2_THREADS / 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, wincl, o);
-        if (lane >= o) wincl += t;
-    }
-    const int wexcl = __shfl_sync(0xffffffffu, wincl - wsum, wid);
-    total = __shfl_sync(0xffffffffu, wincl, K2_THREADS / 32 - 1);
-    __syncthreads();
-    return wexcl + incl - v;
-}
-
 // rank-based stable sort (diagnostic sort_mode = 1): O(n^2 / threads)
 template <bool Desc, int Shift>
 __device__ void block_stable_sort(uint32_t* a, uint32_t* tmp, int n) {
@@ -491,42 +469,21 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
     const int tiles_x = tiles_x_of(W), tiles_y = tiles_y_of(H);
     const uint16_t* __restrict__ seg = P.tile_seg + img_idx(slot, side) * (size_t)tiles_x * tiles_y * kTileH;
     const uint16_t* __restrict__ tlst = P.tile_list + img_idx(slot, side) * (size_t)tiles_x * tiles_y * kTileCap;
-    const int total_segs = H * tiles_x;                   // segment g = y * tiles_x + tx: the layout of tile_seg
-    const int spt = (total_segs + K2_THREADS - 1) / K2_THREADS;
-    const int g_lo = min(total_segs, tid * spt), g_hi = min(total_segs, g_lo + spt);
-    int cnt = 0;
-    for (int g = g_lo; g < g_hi; ++g) cnt += (int)(seg[g] & 0xFFu);
+    const CornerRun run = corner_run(seg, H * tiles_x, K2_THREADS, tid);
     int total;
-    int o = block_exclusive_scan(cnt, s_warp, total);
+    const int o = block_exclusive_scan<K2_THREADS>(run.cnt, s_warp, total);
     const bool overflow = total > P.p.max_corners;
     const int n = min(total, P.p.max_corners);
     // sorted in shared memory when the candidates fit into smem_corners words, in the global array otherwise
     uint32_t* s_a = n <= smem_corners ? smem : g_a;
     {
-        // one word per corner first (where its list entry is + its row inside the band), so that the entries themselves are
-        // fetched by independent loads, one corner per thread, instead of a dependent chain per run of segments
-        static_assert(kTileCap == 512 && kBandCap == 64 && kBandH == 4, "entry index: tile << 9 | band << 6 | k");
         uint32_t* stage = n <= smem_corners ? smem : tmp;
-        if (cnt) {
-            for (int g = g_lo; g < g_hi; ++g) {
-                const uint32_t sg = seg[g];
-                const int c = (int)(sg & 0xFFu);
-                if (!c) continue;
-                const int y = g / tiles_x, tx = g - y * tiles_x;
-                const uint32_t code = ((uint32_t)(y & (kBandH - 1)) << 30) |
-                                      (((uint32_t)(y / kTileH) * tiles_x + tx) << 9 | (uint32_t)((y & (kTileH - 1)) / kBandH) << 6) + (sg >> 8);
-                for (int k = 0; k < c; ++k, ++o)
-                    if (o < n) stage[o] = code + k;
-            }
-        }
+        corner_codes(seg, run, tiles_x, o, n, stage);
         __syncthreads();
         for (int i = tid; i < n; i += K2_THREADS) {
-            const uint32_t code = stage[i], ent = code & 0x3FFFFFFFu;
-            const uint32_t v = tlst[ent];
-            const int tile = (int)(ent >> 9), ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const int y = ty * kTileH + (int)((ent >> 6) & 7u) * kBandH + (int)(code >> 30);
-            s_a[i] = ((v >> 8) << 24) | (uint32_t)i;
-            cand_pos[i] = ((uint32_t)y << 16) | (uint32_t)(tx * kTileW + (int)(v & 0xFFu));
+            const Corner c = corner_fetch(tlst, stage[i], tiles_x);
+            s_a[i] = ((uint32_t)c.score << 24) | (uint32_t)i;
+            cand_pos[i] = ((uint32_t)c.y << 16) | (uint32_t)c.x;
         }
     }
     if (tid == 0) {

@@ -18,35 +18,13 @@
 #include <string.h>
 
 #include "orb.cuh"
+#include "corner_lists.cuh"
 
 namespace svo {
 
 namespace {
 
 constexpr int OT = 256;                   // threads of the per-image kernels
-
-__device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int& total) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    int wsum = (lane < OT / 32) ? s_warp[lane] : 0;
-    int wincl = wsum;
-#pragma unroll
-    for (int o = 1; o < OT / 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, wincl, o);
-        if (lane >= o) wincl += t;
-    }
-    const int wexcl = __shfl_sync(0xffffffffu, wincl - wsum, wid);
-    total = __shfl_sync(0xffffffffu, wincl, OT / 32 - 1);
-    __syncthreads();
-    return wexcl + incl - v;
-}
 
 // ---- level l from level l-1 ------------------------------------------------------------------------------------------
 // src: by batch item (level 0 = the caller's images, levels >= 1 = the level planes); 4 output pixels per thread
@@ -118,7 +96,7 @@ __device__ int partition_tail_block(uint32_t* idx, int first, int n, const float
     int c = 0;
     for (int i = first + tid; i < n; i += OT) c += resp[idx[i]] >= v ? 1 : 0;
     int T;
-    block_excl_scan(c, s_warp, T);
+    block_exclusive_scan<OT>(c, s_warp, T);
     const int mid = first + T;
     int K, K2;
     {   // false positions of [first, mid), ascending
@@ -126,7 +104,7 @@ __device__ int partition_tail_block(uint32_t* idx, int first, int n, const float
         const int lo = min(mid, first + tid * per), hi = min(mid, lo + per);
         int cf = 0;
         for (int i = lo; i < hi; ++i) cf += resp[idx[i]] >= v ? 0 : 1;
-        int off = block_excl_scan(cf, s_warp, K);
+        int off = block_exclusive_scan<OT>(cf, s_warp, K);
         for (int i = lo; i < hi; ++i) if (!(resp[idx[i]] >= v)) tmp[off++] = (uint32_t)i;
     }
     {   // the trues of [mid, n), ascending by position
@@ -134,7 +112,7 @@ __device__ int partition_tail_block(uint32_t* idx, int first, int n, const float
         const int lo = min(n, mid + tid * per), hi = min(n, lo + per);
         int ct = 0;
         for (int i = lo; i < hi; ++i) ct += resp[idx[i]] >= v ? 1 : 0;
-        int off = K + block_excl_scan(ct, s_warp, K2);
+        int off = K + block_exclusive_scan<OT>(ct, s_warp, K2);
         for (int i = lo; i < hi; ++i) if (resp[idx[i]] >= v) tmp[off++] = idx[i];
     }
     __syncthreads();
@@ -223,38 +201,20 @@ orb_select_kernel(Pools P, OrbDev D, const uint8_t* __restrict__ img0L, const ui
         const int tiles_x = tiles_x_of(W), tiles_y = tiles_y_of(H);
         const uint16_t* __restrict__ seg = Lv.tile_seg + im * (size_t)tiles_x * tiles_y * kTileH;
         const uint16_t* __restrict__ tlst = Lv.tile_list + im * (size_t)tiles_x * tiles_y * kTileCap;
-        const int total_segs = H * tiles_x;
-        const int spt = (total_segs + OT - 1) / OT;
-        const int g_lo = min(total_segs, tid * spt), g_hi = min(total_segs, g_lo + spt);
-        int cnt = 0;
-        for (int g = g_lo; g < g_hi; ++g) cnt += (int)(seg[g] & 0xFFu);
+        const CornerRun run = corner_run(seg, H * tiles_x, OT, tid);
         int total;
-        int o = block_excl_scan(cnt, s_warp, total);
+        const int o = block_exclusive_scan<OT>(run.cnt, s_warp, total);
         if (total > D.cap) overflow = true;
         const int n = min(total, D.cap);
         uint32_t* idx = n <= smem_cap ? s_idx : g_idx;
         float* resp = n <= smem_cap ? s_resp : g_resp;
-        if (cnt) {
-            for (int g = g_lo; g < g_hi; ++g) {
-                const uint32_t sg = seg[g];
-                const int c = (int)(sg & 0xFFu);
-                if (!c) continue;
-                const int y = g / tiles_x, tx = g - y * tiles_x;
-                const uint32_t code = ((uint32_t)(y & (kBandH - 1)) << 30) |
-                                      (((uint32_t)(y / kTileH) * tiles_x + tx) << 9 | (uint32_t)((y & (kTileH - 1)) / kBandH) << 6) + (sg >> 8);
-                for (int k = 0; k < c; ++k, ++o)
-                    if (o < n) idx[o] = code + k;
-            }
-        }
+        corner_codes(seg, run, tiles_x, o, n, idx);
         __syncthreads();
         for (int i = tid; i < n; i += OT) {
-            const uint32_t code = idx[i], ent = code & 0x3FFFFFFFu;
-            const uint32_t v = tlst[ent];
-            const int tile = (int)(ent >> 9), ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const int y = ty * kTileH + (int)((ent >> 6) & 7u) * kBandH + (int)(code >> 30);
+            const Corner c = corner_fetch(tlst, idx[i], tiles_x);
             idx[i] = (uint32_t)i;
-            resp[i] = (float)(v >> 8);                                   // cv::FAST: response = score
-            pos[i] = ((uint32_t)y << 16) | (uint32_t)(tx * kTileW + (int)(v & 0xFFu));
+            resp[i] = (float)c.score;                                    // cv::FAST: response = score
+            pos[i] = ((uint32_t)c.y << 16) | (uint32_t)c.x;
         }
         __syncthreads();
         // B. retainBest(2 * featuresNum) by FAST response (HARRIS_SCORE keeps twice as many for the second cull)
