@@ -29,8 +29,7 @@ constexpr int OT = 256;                   // threads of the per-image kernels
 // ---- level l from level l-1 ------------------------------------------------------------------------------------------
 // src: by batch item (level 0 = the caller's images, levels >= 1 = the level planes); 4 output pixels per thread
 __global__ void __launch_bounds__(128)
-orb_resize_kernel(const uint8_t* __restrict__ srcL, const uint8_t* __restrict__ srcR, size_t sstride, size_t simage_pitch, int sw, int sh,
-                  OrbLevelDev D) {
+orb_resize_kernel(const uint8_t* __restrict__ srcL, const uint8_t* __restrict__ srcR, size_t sstride, size_t simage_pitch, OrbLevelDev D) {
     const int item = blockIdx.z >> 1, side = blockIdx.z & 1;
     const int y = blockIdx.y, x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x4 >= D.pitch) return;
@@ -470,7 +469,6 @@ cudaError_t launch_orb_detect(const Pools& P, const OrbDev& D, int n, const uint
     // the pyramid, level after level (each level is resized from the previous one), and FAST + blur of every level
     const uint8_t *sL = d_left + (size_t)item0 * image_pitch, *sR = d_right + (size_t)item0 * image_pitch;
     size_t sstride = stride, spitch = image_pitch;
-    int sw = P.p.W, sh = P.p.H;
     int L = 0;
     for (int l = 0; l < D.n_levels; ++l) {
         const OrbLevelDev& Lv = D.L[l];
@@ -478,8 +476,8 @@ cudaError_t launch_orb_detect(const Pools& P, const OrbDev& D, int n, const uint
             OrbLevelDev Dl = Lv;
             Dl.imgL += (size_t)item0 * Lv.pitch * Lv.h; Dl.imgR += (size_t)item0 * Lv.pitch * Lv.h;
             const dim3 g((Lv.pitch / 4 + 127) / 128, Lv.h, 2 * n);
-            orb_resize_kernel<<<g, 128, 0, st>>>(sL, sR, sstride, spitch, sw, sh, Dl);
-            sL = Dl.imgL; sR = Dl.imgR; sstride = (size_t)Lv.pitch; spitch = (size_t)Lv.pitch * Lv.h; sw = Lv.w; sh = Lv.h;
+            orb_resize_kernel<<<g, 128, 0, st>>>(sL, sR, sstride, spitch, Dl);
+            sL = Dl.imgL; sR = Dl.imgR; sstride = (size_t)Lv.pitch; spitch = (size_t)Lv.pitch * Lv.h;
             ++L;
         }
         Pools PL = P;
