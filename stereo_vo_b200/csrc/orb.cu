@@ -250,8 +250,8 @@ struct IndexedAscComp {                 // KpRowSorter on float rows: comp(a, b)
 };
 
 __global__ void __launch_bounds__(OT)
-orb_nms_sort_kernel(Pools P, OrbDev D, uint32_t* __restrict__ occ_scratch, int occ_words_per_img, uint32_t* __restrict__ sort_scratch,
-                    uint2* __restrict__ list_scratch) {
+orb_nms_sort_kernel(Pools P, OrbDev D, uint32_t* __restrict__ occ_scratch, int occ_words_per_img, int occ_smem_words,
+                    uint32_t* __restrict__ sort_scratch, uint2* __restrict__ list_scratch) {
     extern __shared__ __align__(16) uint32_t osm[];
     const int rc = D.raw_cap;
     uint32_t* s_a = osm;                                             // [raw_cap] indices sorted by response
@@ -294,19 +294,25 @@ orb_nms_sort_kernel(Pools P, OrbDev D, uint32_t* __restrict__ occ_scratch, int o
     int n_sel;
     if (P.p.nms) {
         introsort_block(IndexedDescComp{s_key}, s_a, n, listA, listB, listS, s_cnt, tmp, s_pos, n);      // S2:322-324
+        const unsigned cell = (unsigned)(P.p.min_distance / 2.0);     // S2:331
+        const float cell_inv = 1.0f / (float)cell;                     // S2:332
+        const unsigned glx = (unsigned)(1 + W * cell_inv), gly = (unsigned)(1 + H * cell_inv);
+        const unsigned occ_words = (glx * gly + 31) / 32;
+        // the occupancy grid lives in shared memory when it fits (the walk below is one thread's chain of dependent accesses)
+        uint32_t* occ = (int)occ_words <= occ_smem_words ? osm + 3 * rc : occ_scratch + (size_t)blockIdx.x * occ_words_per_img;
+        for (unsigned i = tid; i < occ_words; i += OT) occ[i] = 0;
+        for (int i = tid; i < n; i += OT) {            // the grid cell of every keypoint (s_b is free until the row sort)
+            const float4 kp = raw[i];
+            s_b[i] = ((unsigned)__fmul_rn(kp.x, cell_inv) << 16) | (unsigned)__fmul_rn(kp.y, cell_inv);
+        }
+        __syncthreads();
         if (tid == 0) {
-            const unsigned cell = (unsigned)(P.p.min_distance / 2.0);     // S2:331
-            const float cell_inv = 1.0f / (float)cell;                     // S2:332
-            const unsigned glx = (unsigned)(1 + W * cell_inv), gly = (unsigned)(1 + H * cell_inv);
-            uint32_t* occ = occ_scratch + (size_t)blockIdx.x * occ_words_per_img;
-            for (unsigned i = 0; i < (glx * gly + 31) / 32; ++i) occ[i] = 0;
             auto get = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; return (occ[b >> 5] >> (b & 31)) & 1u; };
             auto set = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; occ[b >> 5] |= 1u << (b & 31); };
             int c = 0, k = 0;
             while (c < P.p.quota && c < P.p.kp_cap && k < n) {
                 const uint32_t id = s_a[k++];
-                const float4 kp = raw[id];
-                const unsigned sx = (unsigned)__fmul_rn(kp.x, cell_inv), sy = (unsigned)__fmul_rn(kp.y, cell_inv);
+                const unsigned sx = s_b[id] >> 16, sy = s_b[id] & 0xFFFFu;
                 if (get(sx, sy)) continue;
                 set(sx, sy);
                 if (sx > 0) set(sx - 1, sy);
@@ -402,6 +408,15 @@ orb_describe_kernel(Pools P, OrbDev D) {
 }  // namespace
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
+// words of the occupancy grid of m_non_max_sup that orb_nms_sort_kernel keeps in shared memory (0: the grid stays in global memory)
+static int orb_nms_occ_smem_words(const Params& p) {
+    const unsigned cell = (unsigned)(p.min_distance / 2.0);
+    const float inv = 1.0f / (float)cell;
+    const unsigned glx = (unsigned)(1 + p.W * inv), gly = (unsigned)(1 + p.H * inv);
+    const unsigned words = (glx * gly + 31) / 32;
+    return words * 4 <= 96 * 1024 ? (int)words : 0;
+}
+
 static int orb_select_smem_cap(const OrbDev& D) { return D.cap < 8192 ? D.cap : 8192; }   // 64 KB: three CTAs per SM
 
 cudaError_t alloc_orb(OrbDev& D, const Params& p, int n_slots, int n_levels, int n_extract, std::vector<void*>& allocs) {
@@ -460,7 +475,7 @@ cudaError_t alloc_orb(OrbDev& D, const Params& p, int n_slots, int n_levels, int
     if (e != cudaSuccess) return e;
     e = SVO_RAISE_DYN_SMEM(orb_select_kernel, orb_select_smem_cap(D) * 8);
     if (e != cudaSuccess) return e;
-    return SVO_RAISE_DYN_SMEM(orb_nms_sort_kernel, D.raw_cap * 12);
+    return SVO_RAISE_DYN_SMEM(orb_nms_sort_kernel, D.raw_cap * 12 + 4 * orb_nms_occ_smem_words(p));
 }
 
 cudaError_t launch_orb_detect(const Pools& P, const OrbDev& D, int n, const uint8_t* d_left, const uint8_t* d_right, size_t stride,
@@ -489,7 +504,8 @@ cudaError_t launch_orb_detect(const Pools& P, const OrbDev& D, int n, const uint
     }
     const int cap = orb_select_smem_cap(D);
     orb_select_kernel<<<dim3(2 * n, D.n_levels), OT, cap * 8, st>>>(P, D, d_left, d_right, stride, image_pitch, item0, cap);
-    orb_nms_sort_kernel<<<2 * n, OT, D.raw_cap * 12, st>>>(P, D, occ_scratch, occ_words_per_img, sort_scratch, list_scratch);
+    const int occ_smem = orb_nms_occ_smem_words(P.p);
+    orb_nms_sort_kernel<<<2 * n, OT, D.raw_cap * 12 + 4 * occ_smem, st>>>(P, D, occ_scratch, occ_words_per_img, occ_smem, sort_scratch, list_scratch);
     const dim3 gd((P.p.kp_cap + OD_WARPS - 1) / OD_WARPS, 2 * n);
     orb_describe_kernel<<<gd, OD_WARPS * 32, 0, st>>>(P, D);
     if (launches) *launches += L + 3;
