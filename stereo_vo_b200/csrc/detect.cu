@@ -510,11 +510,12 @@ select_kernel(Pools P, int pitch, uint32_t* __restrict__ occ_scratch, int occ_wo
             // corner only blocks its own pixel and the 4 neighbours: nothing is ever rejected.
             n_sel = min(n, P.p.quota);
         } else {
+            const float cell_inv = 1.0f / (float)cell;                 // S2:332
+            const unsigned glx = (unsigned)(1 + W * cell_inv), gly = (unsigned)(1 + H * cell_inv);
+            uint32_t* occ = occ_scratch + (size_t)blockIdx.x * occ_words_per_img;
+            for (unsigned i = tid; i < (glx * gly + 31) / 32; i += K2_THREADS) occ[i] = 0;
+            __syncthreads();
             if (tid == 0) {
-                const float cell_inv = 1.0f / (float)cell;                 // S2:332
-                const unsigned glx = (unsigned)(1 + W * cell_inv), gly = (unsigned)(1 + H * cell_inv);
-                uint32_t* occ = occ_scratch + (size_t)blockIdx.x * occ_words_per_img;
-                for (unsigned i = 0; i < (glx * gly + 31) / 32; ++i) occ[i] = 0;
                 auto get = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; return (occ[b >> 5] >> (b & 31)) & 1u; };
                 auto set = [&](unsigned x, unsigned y) { const unsigned b = x * gly + y; occ[b >> 5] |= 1u << (b & 31); };
                 int c = 0, k = 0;
