@@ -824,6 +824,8 @@ def run_gpu(args):
         raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # pageable host images are gathered into pinned staging by host threads of the library: share the cores between the ranks
+    os.environ.setdefault("SVO_GATHER_THREADS", str(max(4, min(16, (os.cpu_count() or 16) // world))))
     numa = bind_to_gpu_numa(torch, local) if not args.no_numa else {"disabled": True}
     if world > 1:
         dist.init_process_group("nccl", device_id=device)

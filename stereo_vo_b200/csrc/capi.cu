@@ -1020,7 +1020,7 @@ int svo_submit_batch(svo_ctx* c, int32_t n, const int32_t* slots, const uint8_t*
             c->h_stage_bytes = need;
         }
         uint8_t* hs = c->h_stage[b];
-        const int nthr = std::max(1, std::min(8, std::min(n, (int)std::thread::hardware_concurrency())));
+        const int nthr = std::max(1, std::min(getenv("SVO_GATHER_THREADS") ? atoi(getenv("SVO_GATHER_THREADS")) : 16, std::min(n, (int)std::thread::hardware_concurrency())));
         auto work = [&](int t) {
             for (int i = t; i < n; i += nthr)
                 for (int side = 0; side < 2; ++side) {
