@@ -312,3 +312,32 @@ def test_orb_against_the_committed_opencv_golden():
                 np.testing.assert_allclose(r.delta_pose[:], g[f"seq_f{i}_delta"], atol=1e-9)
     finally:
         ctx.close()
+
+
+def test_orb_batch_of_slots_thresholds_and_repeat():
+    """three estimators on one context with dmORB: slot 1 changes its FAST / ORB thresholds at frame 2 (the FAST threshold is
+    cv::ORB's fastThreshold, S2:491), slot 2 repeats frame 3 (request.repeat, P:86-100); every slot equals its own oracle"""
+    frames, cam = synth.make_sequence("c1", seed=77, n_frames=6)
+    oc = orc.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    gc = capi.make_camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["baseline"])
+    ctx = capi.Context(width=320, height=240, orb_nfeats=120, max_seqs=3, detect_method=0, fundmat_filter=0)
+    ests = [orc.OracleEstimator(orc.Params(orb_nfeats=120, detect_method=0), backend="cv2", ransac="off") for _ in range(3)]
+    try:
+        for i, (L, R) in enumerate(frames):
+            if i == 2:
+                ctx.set_thresholds(11, 50, slot=1)
+                ests[1].m_current_fast_th, ests[1].m_current_orb_th = 11, 50
+            rep = [False, False, i == 3]
+            outs = [e.process_new_image_pair(L, R, oc, repeat=rp) if rp else e.process_new_image_pair(L, R, oc) for e, rp in zip(ests, rep)]
+            r = ctx.process_batch([L, L, L], [R, R, R], [gc] * 3, repeat=rep)
+            for slot, o in enumerate(outs):
+                _assert_kps_equal(ctx.keypoints(slot, 0, 0), o["frame"].kpsL, f"frame {i} slot {slot}")
+                assert np.array_equal(ctx.descriptors(slot, 0, 1), o["frame"].descR)
+                m = ctx.matches(slot, 0)
+                assert np.array_equal(m["trainIdx"], o["frame"].matches["trainIdx"]), (i, slot)
+                assert (r[slot].error_code, bool(r[slot].valid)) == (o["error_code"], o["valid"]), (i, slot)
+                if i > 0:
+                    assert np.array_equal(ctx.tracked_pairs(slot), o["tracked"]), (i, slot)
+        assert len(ctx.keypoints(1, 0, 0)) != len(ctx.keypoints(0, 0, 0)) or not np.array_equal(ctx.keypoints(1, 0, 0)["x"], ctx.keypoints(0, 0, 0)["x"])
+    finally:
+        ctx.close()
